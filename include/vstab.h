@@ -1,0 +1,201 @@
+/*
+ * vstab.h — C ABI of libvstab.so: B200 (sm_100a) kernels for the alignment-and-warp
+ * hot path of catid/video_stabilizer.
+ *
+ * This is the boundary a maintainer of the reference binds against: every entry point
+ * below replaces one Halide AOT pipeline (generators.cpp), one OpenCV call or one block of
+ * host orchestration on the path.  Citations are file:line in the reference tree.
+ * INTEGRATION.md shows the reference-side wrappers (imgproc.cpp / alignment.cpp /
+ * stabilizer.cpp) rewritten against this header.
+ *
+ * Conventions
+ *  - every function returns 0 (VS_OK) or a negative vs_status; vs_last_error() gives text.
+ *  - no exceptions, no C++ types, no torch types cross this boundary.
+ *  - `mem` says where the data pointers of that call live: VS_MEM_HOST (the call copies
+ *    in, runs, copies out and returns when the result is in host memory) or VS_MEM_DEVICE
+ *    (pointers are device pointers, the call only enqueues work on the context's stream).
+ *  - images are row-major; `stride` is in ELEMENTS of the image type between rows;
+ *    `batch` images are `batch_stride` elements apart.  One launch processes the batch.
+ *  - "planar (w,h,c)" arrays are Halide::Runtime::Buffer<T>(w,h,c) dense layout:
+ *    index = (c*h + y)*w + x.
+ *  - there is no CPU fallback anywhere in this library: without a CUDA device every
+ *    compute entry point fails with VS_ERR_CUDA.
+ */
+#ifndef VSTAB_H
+#define VSTAB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_ABI_VERSION 1
+#define VS_MAX_LEVELS 12
+
+typedef enum vs_status {
+    VS_OK = 0,
+    VS_ERR_INVALID = -1,     /* bad argument */
+    VS_ERR_CUDA = -2,        /* CUDA runtime / launch failure, or no device */
+    VS_ERR_UNSUPPORTED = -3, /* valid request this build does not implement */
+    VS_ERR_NOMEM = -4
+} vs_status;
+
+enum { VS_MEM_HOST = 0, VS_MEM_DEVICE = 1 };
+
+/* BGR warp interpolation / border (imgproc.cpp:446-484 uses CV_EXACT + CONSTANT0) */
+enum { VS_WARP_CV_EXACT_BILINEAR = 0, VS_WARP_FLOAT_BILINEAR = 1, VS_WARP_LANCZOS2 = 2 };
+enum { VS_BORDER_CONSTANT0 = 0, VS_BORDER_REPEAT_EDGE = 1 };
+
+typedef struct vs_ctx vs_ctx;
+typedef struct vs_clip vs_clip;
+
+typedef struct vs_img {
+    void*   data;
+    int32_t width, height;
+    int64_t stride;        /* elements between rows (bytes for u8; BGR counts bytes too) */
+    int32_t batch;         /* >= 1 */
+    int64_t batch_stride;  /* elements between images of the batch */
+} vs_img;
+
+/* ------------------------------------------------------------------ context */
+int vs_abi_version(void);
+int vs_device_count(void);
+/* One context per GPU and per host thread that drives it.  Owns a stream and scratch. */
+int vs_ctx_create(int device, vs_ctx** out);
+int vs_ctx_destroy(vs_ctx* ctx);
+/* Borrow an external cudaStream_t (e.g. torch's current stream) so that the caller's
+ * CUDA events see this library's launches.  NULL restores the context's own stream. */
+int vs_ctx_set_stream(vs_ctx* ctx, void* cuda_stream);
+int vs_ctx_synchronize(vs_ctx* ctx);
+/* text of the last error on this context (or of the last failed vs_ctx_create if NULL) */
+const char* vs_last_error(const vs_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
+int64_t vs_ctx_launch_count(const vs_ctx* ctx);
+/* device memory helpers for callers without their own allocator (C++ host layer) */
+int vs_dev_alloc(vs_ctx* ctx, size_t bytes, void** out);
+int vs_dev_free(vs_ctx* ctx, void* p);
+int vs_host_alloc_pinned(vs_ctx* ctx, size_t bytes, void** out);
+int vs_host_free_pinned(vs_ctx* ctx, void* p);
+int vs_memcpy_h2d(vs_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async on stream */
+int vs_memcpy_d2h(vs_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async on stream */
+
+/* ------------------------------------------------- single operators (1:1) */
+/* cv::cvtColor(BGR2GRAY), alignment.cpp:212.  bgr: interleaved, width in pixels,
+ * stride in bytes.  gray: u8. */
+int vs_bgr2gray_u8(vs_ctx*, const vs_img* bgr, const vs_img* gray, int mem);
+
+/* pyr_down(), generators.cpp:56-92 via PyrDown(), imgproc.cpp:108-114.  The output
+ * extent defines the work; input is read through repeat-edge. */
+int vs_pyr_down_u8(vs_ctx*, const vs_img* in, const vs_img* out, int mem);
+
+/* grad_xy(), generators.cpp:202-224 via GradXY(), imgproc.cpp:135-142. */
+int vs_grad_xy_u8_f32(vs_ctx*, const vs_img* in, const vs_img* grad_x, const vs_img* grad_y, int mem);
+
+/* tile-size rule of GradArgMax(), imgproc.cpp:151-162 */
+int vs_grad_argmax_tile_size(int width, int height);
+/* grad_argmax_N(), generators.cpp:260-294 via GradArgMax(), imgproc.cpp:144-202.
+ * local_max_x/y: u16 planar (tw,th,2), tw = width/tile, th = height/tile. */
+int vs_grad_argmax_f32_u16(vs_ctx*, const vs_img* grad_x, const vs_img* grad_y, int tile,
+                           uint16_t* local_max_x, uint16_t* local_max_y, int mem);
+
+/* sparse_jac(), generators.cpp:332-386 via SparseJacobian(), imgproc.cpp:26-44.
+ * local_max_*: u16 planar (tw,th,2); out_*: f32 planar (tw,th,4). */
+int vs_sparse_jac_f32(vs_ctx*, const vs_img* grad_x, const vs_img* grad_y,
+                      const uint16_t* local_max_x, const uint16_t* local_max_y,
+                      int tw, int th, float* out_x, float* out_y, int mem);
+
+/* sparse_warpdiff(), generators.cpp:646-700.  A,B,TX,TY are the pipeline's f32
+ * upper-left-origin parameters (SparseWarpDiff(), imgproc.cpp:94-104, computes them).
+ * local_max: u16 planar (tw,th,2); out: u16 (tw,th). */
+int vs_sparse_warpdiff_u8_u16(vs_ctx*, const vs_img* tmpl, const vs_img* keyframe,
+                              const uint16_t* local_max, int tw, int th,
+                              float A, float B, float TX, float TY, uint16_t* out, int mem);
+
+/* sparse_ica(), generators.cpp:429-596.  selected_*: u16 planar (k,2); jac_*: f32 planar
+ * (k,4); out: 4 doubles (SparseICA(), imgproc.cpp:46-78). */
+int vs_sparse_ica_f64(vs_ctx*, const vs_img* tmpl, const vs_img* keyframe,
+                      const uint16_t* selected_x, int kx, const uint16_t* selected_y, int ky,
+                      const float* jac_x, const float* jac_y,
+                      float A, float B, float TX, float TY, double* out4, int mem);
+
+/* image_warp(), generators.cpp:126-164 (ImageWarp(), imgproc.cpp:116-133 computes the
+ * f32 parameters).  params: 4 floats {A,B,TX,TY} per batch image. */
+int vs_image_warp_u8_f32(vs_ctx*, const vs_img* in, const float* params4, const vs_img* out, int mem);
+
+/* The BGR warp of warpBySimilarityTransform(), imgproc.cpp:446-484:
+ * cv::warpAffine(src, dst, M, size, INTER_LINEAR, BORDER_CONSTANT, 0) without
+ * WARP_INVERSE_MAP.  M: 6 doubles (row-major 2x3 forward matrix) per batch image, always
+ * in host memory.  dst may be a cropped window: dst pixel (x,y) is output pixel
+ * (x+dst_x0, y+dst_y0) of the full-size warp (stabilizer.cpp:102-109 crop fused). */
+int vs_bgr_warp_u8(vs_ctx*, const vs_img* src, const double* M6, const vs_img* dst,
+                   int dst_x0, int dst_y0, int mode, int border, int mem);
+
+/* ------------------------------------------- fused, batched, device-resident */
+/* VideoAlignerParams, alignment.hpp:5-41 */
+typedef struct vs_align_params {
+    int32_t phase_correlate;          /* nonzero -> VS_ERR_UNSUPPORTED (default off upstream) */
+    double  phase_correlate_threshold;
+    double  threshold;
+    float   smallest_fraction;
+    int32_t max_iters;
+    int32_t pyramid_min_width;
+    int32_t pyramid_min_height;
+    double  max_displacement;
+} vs_align_params;
+void vs_align_params_default(vs_align_params* p);
+
+/* One alignment job: which frame slot is the template, which is the keyframe, and
+ * whether the result is inverted (alignment.cpp:396-397, :690-693). */
+typedef struct vs_pair {
+    int32_t template_slot;
+    int32_t keyframe_slot;
+    int32_t invert;
+} vs_pair;
+
+enum { VS_CLIP_DEBUG_TAPS = 1 };  /* keep per-pair warpdiff / selection for inspection */
+
+/* A clip is `capacity` frame slots of one size resident on the GPU: BGR frame, gray
+ * pyramid (ComputePyramid, alignment.cpp:149-235) and keyframe features
+ * (ComputeKeyFrame, alignment.cpp:237-276).  VideoAligner uses 2 slots, the batched
+ * pipeline uses one slot per frame of a chunk.  max_pairs bounds one vs_clip_align call. */
+int vs_clip_create(vs_ctx*, int width, int height, int capacity, int max_pairs,
+                   const vs_align_params* params, int flags, vs_clip** out);
+int vs_clip_destroy(vs_clip*);
+int vs_clip_levels(const vs_clip*);
+int vs_clip_level_info(const vs_clip*, int level, int* w, int* h, int* tile, int* tw, int* th);
+
+/* copy n BGR frames (interleaved u8, row_stride bytes between rows, frame_stride bytes
+ * between frames) into slots [slot0, slot0+n) */
+int vs_clip_upload(vs_clip*, int slot0, int n, const uint8_t* bgr,
+                   int64_t row_stride, int64_t frame_stride, int mem);
+/* BGR -> gray -> full pyramid for slots [slot0, slot0+n) */
+int vs_clip_build_pyramids(vs_clip*, int slot0, int n);
+/* fused grad_xy + grad_argmax + sparse_jac on every level, for the listed slots (host array) */
+int vs_clip_build_keyframes(vs_clip*, const int32_t* slots, int n);
+/* AlignNextFrame's per-level loop (alignment.cpp:390-693) for n pairs in one launch.
+ * pairs: host array.  out_transform: 4 doubles per pair {A,B,TX,TY}; out_status: 1 = ok,
+ * 0 = false (non-convergence / over-displacement); out_iters: levels ints per pair
+ * (may be NULL).  Outputs live in `mem`. */
+int vs_clip_align(vs_clip*, const vs_pair* pairs, int n,
+                  double* out_transform, int32_t* out_status, int32_t* out_iters, int mem);
+/* warpBySimilarityTransform (imgproc.cpp:446-484) + crop (stabilizer.cpp:102-109) for the
+ * listed slots.  transforms: 4 doubles per frame (centre-based correction), host array.
+ * out: (w-2crop)x(h-2crop) BGR frames, dense, out_frame_stride bytes apart, in `mem`. */
+int vs_clip_warp(vs_clip*, const int32_t* slots, int n, const double* transforms,
+                 int mode, int border, int crop, uint8_t* out, int64_t out_frame_stride, int mem);
+
+/* inspection taps (host outputs, synchronous) used by the bit-exact parity tests */
+int vs_clip_get_bgr(vs_clip*, int slot, uint8_t* out /* w*h*3 dense */);
+int vs_clip_get_gray(vs_clip*, int slot, int level, uint8_t* out /* w*h dense */);
+int vs_clip_get_keypoints(vs_clip*, int slot, int level, int axis, uint16_t* out /* planar (tw,th,2) */);
+int vs_clip_get_jacobians(vs_clip*, int slot, int level, int axis, float* out /* planar (tw,th,4) */);
+/* need VS_CLIP_DEBUG_TAPS; pair = index within the last vs_clip_align call */
+int vs_clip_get_warpdiff(vs_clip*, int pair, int level, int axis, uint16_t* out /* (tw,th) */);
+int vs_clip_get_selected(vs_clip*, int pair, int level, int axis, uint32_t* out_order, int* out_k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSTAB_H */

@@ -1,0 +1,404 @@
+// vs_clip.cu — device-resident frame store and the batched alignment / warp pipeline.
+//
+// HBM layout of a clip (all sized at creation, nothing is allocated on the hot path):
+//   bgr      [capacity][h][bgr_pitch]                     interleaved BGR, pitch = align(3w,128)
+//   pyr      [capacity][pyr_slot_bytes]                   gray pyramid, level l at lv[l].img_off,
+//                                                         rows lv[l].pitch = align(w_l,128) bytes apart
+//   kp       [capacity][2 axes][total_tiles] u32          keypoint (y<<16|x) per tile, levels concatenated
+//   jac      [capacity][2 axes][total_tiles] float4       Jacobian per keypoint (reference channel order)
+//   pairs / out_T / out_status / out_iters               per vs_clip_align call, max_pairs entries
+//   dbg_*    optional (VS_CLIP_DEBUG_TAPS)               warpdiff and selection order per pair
+#include "vs_internal.h"
+
+#include <string.h>
+
+struct vs_clip {
+    vs_ctx* ctx = nullptr;
+    int w = 0, h = 0, capacity = 0, max_pairs = 0, flags = 0;
+    vs_align_params params;
+    VsClipGeom g;
+    size_t bgr_pitch = 0, bgr_slot_bytes = 0;
+    uint8_t* d_bgr = nullptr;
+    uint8_t* d_pyr = nullptr;
+    uint32_t* d_kp = nullptr;
+    float4* d_jac = nullptr;
+    vs_pair* d_pairs = nullptr;
+    double* d_T = nullptr;
+    int32_t* d_status = nullptr;
+    int32_t* d_iters = nullptr;
+    int32_t* d_slots = nullptr;       // max(capacity, max_pairs) ints
+    VsWarpCoef* d_coef = nullptr;     // capacity entries
+    uint16_t* d_dbg_wd = nullptr;
+    uint16_t* d_dbg_order = nullptr;
+    int32_t* d_dbg_count = nullptr;
+    uint8_t* d_warp_out = nullptr;    // staging for VS_MEM_HOST warps, grown on demand
+    size_t warp_out_bytes = 0;
+    int last_pairs = 0;
+};
+
+namespace {
+
+#define VS_TRY(expr) do { int _r = (expr); if (_r != VS_OK) return _r; } while (0)
+
+template <typename T>
+int dev_alloc(vs_ctx* ctx, T** p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) return VS_OK;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess)
+        return vs_set_error(ctx, VS_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+    return VS_OK;
+}
+
+void free_all(vs_clip* c)
+{
+    cudaFree(c->d_bgr); cudaFree(c->d_pyr); cudaFree(c->d_kp); cudaFree(c->d_jac); cudaFree(c->d_pairs);
+    cudaFree(c->d_T); cudaFree(c->d_status); cudaFree(c->d_iters); cudaFree(c->d_slots); cudaFree(c->d_coef);
+    cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_warp_out);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pairs,
+                   const vs_align_params* params, int flags, vs_clip** out)
+{
+    if (!ctx || !out) return VS_ERR_INVALID;
+    *out = nullptr;
+    VS_REQUIRE(ctx, width > 0 && height > 0 && capacity > 0 && max_pairs >= 0, "clip_create: bad geometry");
+    VS_REQUIRE(ctx, width <= 65535 && height <= 65535, "clip_create: keypoint coordinates must fit in u16");
+    vs_align_params P;
+    if (params) P = *params; else vs_align_params_default(&P);
+    if (P.phase_correlate)
+        return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "phase_correlate initialisation (alignment.cpp:369-388) is not implemented");
+    VS_REQUIRE(ctx, P.max_iters >= 1, "clip_create: max_iters must be >= 1");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    vs_clip* c = new vs_clip();
+    c->ctx = ctx; c->w = width; c->h = height; c->capacity = capacity; c->max_pairs = max_pairs;
+    c->flags = flags; c->params = P;
+
+    // level count exactly as ComputePyramid (alignment.cpp:164-169)
+    VsClipGeom& g = c->g;
+    memset(&g, 0, sizeof(g));
+    {
+        int w = width, h = height, levels = 0;
+        do { levels++; w /= 2; h /= 2; } while (w >= P.pyramid_min_width && h >= P.pyramid_min_height);
+        if (levels > VS_MAX_LEVELS) { delete c; return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "more than %d pyramid levels", VS_MAX_LEVELS); }
+        g.levels = levels;
+    }
+    {
+        int w = width, h = height;
+        size_t off = 0; int toff = 0;
+        for (int l = 0; l < g.levels; l++) {
+            if (l > 0) { w /= 2; h /= 2; }
+            if (w < 1 || h < 1) { delete c; return vs_set_error(ctx, VS_ERR_INVALID, "image too small for its pyramid"); }
+            VsLevel& L = g.lv[l];
+            L.w = w; L.h = h; L.pitch = (int)vs_align_up((size_t)w, 128);
+            L.tile = vs_grad_argmax_tile_size(w, h);
+            L.tw = w / L.tile; L.th = h / L.tile; L.ntiles = L.tw * L.th;
+            L.img_off = (uint32_t)off; L.tile_off = (uint32_t)toff;
+            off += (size_t)L.pitch * h;
+            toff += L.ntiles;
+            g.max_tiles = L.ntiles > g.max_tiles ? L.ntiles : g.max_tiles;
+            if (L.ntiles < 1) { delete c; return vs_set_error(ctx, VS_ERR_INVALID, "pyramid level %d has no tiles", l); }
+        }
+        g.total_tiles = toff;
+        g.pyr_slot_bytes = vs_align_up(off, 256);
+    }
+    if (g.max_tiles > 65535 || (size_t)2 * g.max_tiles * 4 > 200 * 1024) {
+        const int mt = g.max_tiles;
+        delete c;
+        return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "%d tiles on a level exceeds the on-chip selection capacity", mt);
+    }
+    c->bgr_pitch = vs_align_up((size_t)width * 3, 128);
+    c->bgr_slot_bytes = c->bgr_pitch * height;
+
+    int r = VS_OK;
+    size_t feat = (size_t)capacity * 2 * g.total_tiles;
+    int nslots = capacity > max_pairs ? capacity : max_pairs;
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_bgr, c->bgr_slot_bytes * capacity);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_pyr, g.pyr_slot_bytes * capacity);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_kp, feat);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_jac, feat);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_pairs, (size_t)max_pairs);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_T, (size_t)max_pairs * 4);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_status, (size_t)max_pairs);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_iters, (size_t)max_pairs * g.levels);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_slots, (size_t)nslots);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_coef, (size_t)capacity);
+    if (r == VS_OK && (flags & VS_CLIP_DEBUG_TAPS)) {
+        r = dev_alloc(ctx, &c->d_dbg_wd, (size_t)max_pairs * 2 * g.total_tiles);
+        if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_order, (size_t)max_pairs * 2 * g.total_tiles);
+        if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_count, (size_t)max_pairs * 2 * g.levels);
+    }
+    if (r != VS_OK) { free_all(c); delete c; return r; }
+    // padding bytes of the pyramid rows are never read as pixels, but keep them defined
+    cudaMemsetAsync(c->d_pyr, 0, g.pyr_slot_bytes * capacity, ctx->stream);
+    cudaMemsetAsync(c->d_bgr, 0, c->bgr_slot_bytes * capacity, ctx->stream);
+    *out = c;
+    return VS_OK;
+}
+
+int vs_clip_destroy(vs_clip* c)
+{
+    if (!c) return VS_OK;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    free_all(c);
+    delete c;
+    return VS_OK;
+}
+
+int vs_clip_levels(const vs_clip* c) { return c ? c->g.levels : 0; }
+
+int vs_clip_level_info(const vs_clip* c, int level, int* w, int* h, int* tile, int* tw, int* th)
+{
+    if (!c || level < 0 || level >= c->g.levels) return VS_ERR_INVALID;
+    const VsLevel& L = c->g.lv[level];
+    if (w) *w = L.w; if (h) *h = L.h; if (tile) *tile = L.tile; if (tw) *tw = L.tw; if (th) *th = L.th;
+    return VS_OK;
+}
+
+int vs_clip_upload(vs_clip* c, int slot0, int n, const uint8_t* bgr, int64_t row_stride, int64_t frame_stride, int mem)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, slot0 >= 0 && n >= 0 && slot0 + n <= c->capacity, "clip_upload: slot range out of bounds");
+    VS_REQUIRE(ctx, n == 0 || bgr, "clip_upload: source is NULL");
+    VS_REQUIRE(ctx, row_stride >= (int64_t)c->w * 3, "clip_upload: row_stride smaller than a row");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaMemcpyKind kind = mem == VS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (frame_stride == row_stride * c->h) {
+        // frames are back to back: one 2-D copy for the whole range
+        VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)slot0 * c->bgr_slot_bytes, c->bgr_pitch, bgr, (size_t)row_stride,
+                                       (size_t)c->w * 3, (size_t)c->h * n, kind, ctx->stream));
+    } else {
+        for (int i = 0; i < n; i++)
+            VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)(slot0 + i) * c->bgr_slot_bytes, c->bgr_pitch,
+                                           bgr + (size_t)frame_stride * i, (size_t)row_stride, (size_t)c->w * 3, c->h,
+                                           kind, ctx->stream));
+    }
+    return VS_OK;
+}
+
+int vs_clip_build_pyramids(vs_clip* c, int slot0, int n)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, slot0 >= 0 && n >= 0 && slot0 + n <= c->capacity, "clip_build_pyramids: slot range out of bounds");
+    if (n == 0) return VS_OK;
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const VsClipGeom& g = c->g;
+    VsDevImg bgr{c->d_bgr + (size_t)slot0 * c->bgr_slot_bytes, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
+    uint8_t* pyr0 = c->d_pyr + (size_t)slot0 * g.pyr_slot_bytes;
+    VsDevImg prev{pyr0 + g.lv[0].img_off, g.lv[0].w, g.lv[0].h, g.lv[0].pitch, n, (int64_t)g.pyr_slot_bytes};
+    VS_TRY(vsk_bgr2gray(ctx, bgr, prev));
+    for (int l = 1; l < g.levels; l++) {
+        VsDevImg cur{pyr0 + g.lv[l].img_off, g.lv[l].w, g.lv[l].h, g.lv[l].pitch, n, (int64_t)g.pyr_slot_bytes};
+        VS_TRY(vsk_pyr_down(ctx, prev, cur));
+        prev = cur;
+    }
+    return VS_OK;
+}
+
+int vs_clip_build_keyframes(vs_clip* c, const int32_t* slots, int n)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, n >= 0 && n <= c->capacity && (n == 0 || slots), "clip_build_keyframes: bad slot list");
+    if (n == 0) return VS_OK;
+    for (int i = 0; i < n; i++) VS_REQUIRE(ctx, slots[i] >= 0 && slots[i] < c->capacity, "clip_build_keyframes: slot out of range");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpyAsync(c->d_slots, slots, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    return vsk_keyframe_features(ctx, c->g, c->d_pyr, c->d_slots, n, c->d_kp, c->d_jac);
+}
+
+int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_t* out_status, int32_t* out_iters, int mem)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, n >= 0 && n <= c->max_pairs, "clip_align: more pairs than max_pairs");
+    VS_REQUIRE(ctx, mem == VS_MEM_HOST || mem == VS_MEM_DEVICE, "clip_align: bad mem");
+    if (n == 0) return VS_OK;
+    VS_REQUIRE(ctx, pairs && out_T && out_status, "clip_align: NULL pointer");
+    for (int i = 0; i < n; i++)
+        VS_REQUIRE(ctx, pairs[i].template_slot >= 0 && pairs[i].template_slot < c->capacity &&
+                        pairs[i].keyframe_slot >= 0 && pairs[i].keyframe_slot < c->capacity, "clip_align: slot out of range");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpyAsync(c->d_pairs, pairs, (size_t)n * sizeof(vs_pair), cudaMemcpyHostToDevice, ctx->stream));
+    const bool dev_out = mem == VS_MEM_DEVICE;
+    VsSolveArgs a;
+    a.pyr = c->d_pyr; a.kp = c->d_kp; a.jac = c->d_jac; a.pairs = c->d_pairs; a.n_pairs = n;
+    a.threshold = c->params.threshold; a.fraction = c->params.smallest_fraction;
+    a.max_iters = c->params.max_iters; a.max_displacement = c->params.max_displacement;
+    a.out_T = dev_out ? out_T : c->d_T;
+    a.out_status = dev_out ? out_status : c->d_status;
+    a.out_iters = dev_out ? out_iters : (out_iters ? c->d_iters : nullptr);
+    a.dbg_warpdiff = c->d_dbg_wd; a.dbg_order = c->d_dbg_order; a.dbg_count = c->d_dbg_count;
+    if (c->d_dbg_count)   // -1 marks levels a pair never reached
+        VS_CUDA(ctx, cudaMemsetAsync(c->d_dbg_count, 0xFF, (size_t)c->max_pairs * 2 * c->g.levels * sizeof(int32_t), ctx->stream));
+    VS_TRY(vsk_solve_pairs(ctx, c->g, a));
+    c->last_pairs = n;
+    if (!dev_out) {
+        VS_CUDA(ctx, cudaMemcpyAsync(out_T, c->d_T, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        VS_CUDA(ctx, cudaMemcpyAsync(out_status, c->d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_iters)
+            VS_CUDA(ctx, cudaMemcpyAsync(out_iters, c->d_iters, (size_t)n * c->g.levels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return VS_OK;
+}
+
+int vs_clip_warp(vs_clip* c, const int32_t* slots, int n, const double* transforms, int mode, int border, int crop,
+                 uint8_t* out, int64_t out_frame_stride, int mem)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, n >= 0 && n <= c->capacity, "clip_warp: more frames than capacity");
+    VS_REQUIRE(ctx, mem == VS_MEM_HOST || mem == VS_MEM_DEVICE, "clip_warp: bad mem");
+    if (n == 0) return VS_OK;
+    VS_REQUIRE(ctx, slots && transforms && out, "clip_warp: NULL pointer");
+    VS_REQUIRE(ctx, crop >= 0 && 2 * crop < c->w && 2 * crop < c->h, "clip_warp: crop too large");
+    const int ow = c->w - 2 * crop, oh = c->h - 2 * crop;
+    VS_REQUIRE(ctx, out_frame_stride >= (int64_t)ow * oh * 3, "clip_warp: out_frame_stride smaller than a frame");
+    for (int i = 0; i < n; i++) VS_REQUIRE(ctx, slots[i] >= 0 && slots[i] < c->capacity, "clip_warp: slot out of range");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    std::vector<VsWarpCoef> coef(n);
+    for (int i = 0; i < n; i++) {
+        double M[6];
+        vs_forward_matrix_from_transform(transforms + 4 * i, c->w, c->h, M);
+        vs_warp_coef_from_forward(M, &coef[i]);
+    }
+    VS_CUDA(ctx, cudaMemcpyAsync(c->d_coef, coef.data(), (size_t)n * sizeof(VsWarpCoef), cudaMemcpyHostToDevice, ctx->stream));
+    VS_CUDA(ctx, cudaMemcpyAsync(c->d_slots, slots, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+
+    uint8_t* d_out = out;
+    int64_t d_stride = out_frame_stride;
+    if (mem == VS_MEM_HOST) {
+        size_t need = (size_t)ow * oh * 3 * n;
+        if (need > c->warp_out_bytes) {
+            VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(c->d_warp_out); c->d_warp_out = nullptr; c->warp_out_bytes = 0;
+            VS_TRY(dev_alloc(ctx, &c->d_warp_out, need));
+            c->warp_out_bytes = need;
+        }
+        d_out = c->d_warp_out;
+        d_stride = (int64_t)ow * oh * 3;
+    }
+    VsDevImg src{c->d_bgr, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
+    VsDevImg dst{d_out, ow, oh, (int64_t)ow * 3, n, d_stride};
+    VS_TRY(vsk_bgr_warp_slots(ctx, src, c->d_slots, c->d_coef, dst, crop, crop, mode, border));
+    if (mem == VS_MEM_HOST) {
+        VS_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)out_frame_stride, d_out, (size_t)d_stride, (size_t)ow * oh * 3, n,
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+        VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------ inspection taps
+
+int vs_clip_get_bgr(vs_clip* c, int slot, uint8_t* out)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, slot >= 0 && slot < c->capacity && out, "clip_get_bgr: bad arguments");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)c->w * 3, c->d_bgr + (size_t)slot * c->bgr_slot_bytes, c->bgr_pitch,
+                                   (size_t)c->w * 3, c->h, cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VS_OK;
+}
+
+int vs_clip_get_gray(vs_clip* c, int slot, int level, uint8_t* out)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, slot >= 0 && slot < c->capacity && level >= 0 && level < c->g.levels && out, "clip_get_gray: bad arguments");
+    const VsLevel& L = c->g.lv[level];
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpy2DAsync(out, L.w, c->d_pyr + (size_t)slot * c->g.pyr_slot_bytes + L.img_off, L.pitch, L.w, L.h,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VS_OK;
+}
+
+int vs_clip_get_keypoints(vs_clip* c, int slot, int level, int axis, uint16_t* out)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, slot >= 0 && slot < c->capacity && level >= 0 && level < c->g.levels && (axis == 0 || axis == 1) && out,
+               "clip_get_keypoints: bad arguments");
+    const VsLevel& L = c->g.lv[level];
+    std::vector<uint32_t> tmp(L.ntiles);
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpyAsync(tmp.data(), c->d_kp + ((size_t)slot * 2 + axis) * c->g.total_tiles + L.tile_off,
+                                 (size_t)L.ntiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int t = 0; t < L.ntiles; t++) { out[t] = (uint16_t)(tmp[t] & 0xffff); out[L.ntiles + t] = (uint16_t)(tmp[t] >> 16); }
+    return VS_OK;
+}
+
+int vs_clip_get_jacobians(vs_clip* c, int slot, int level, int axis, float* out)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, slot >= 0 && slot < c->capacity && level >= 0 && level < c->g.levels && (axis == 0 || axis == 1) && out,
+               "clip_get_jacobians: bad arguments");
+    const VsLevel& L = c->g.lv[level];
+    std::vector<float4> tmp(L.ntiles);
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpyAsync(tmp.data(), c->d_jac + ((size_t)slot * 2 + axis) * c->g.total_tiles + L.tile_off,
+                                 (size_t)L.ntiles * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int t = 0; t < L.ntiles; t++) {
+        out[t] = tmp[t].x; out[L.ntiles + t] = tmp[t].y; out[2 * L.ntiles + t] = tmp[t].z; out[3 * L.ntiles + t] = tmp[t].w;
+    }
+    return VS_OK;
+}
+
+int vs_clip_get_warpdiff(vs_clip* c, int pair, int level, int axis, uint16_t* out)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, c->d_dbg_wd, "clip_get_warpdiff: clip was created without VS_CLIP_DEBUG_TAPS");
+    VS_REQUIRE(ctx, pair >= 0 && pair < c->last_pairs && level >= 0 && level < c->g.levels && (axis == 0 || axis == 1) && out,
+               "clip_get_warpdiff: bad arguments");
+    const VsLevel& L = c->g.lv[level];
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpyAsync(out, c->d_dbg_wd + ((size_t)pair * 2 + axis) * c->g.total_tiles + L.tile_off,
+                                 (size_t)L.ntiles * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VS_OK;
+}
+
+int vs_clip_get_selected(vs_clip* c, int pair, int level, int axis, uint32_t* out_order, int* out_k)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, c->d_dbg_order, "clip_get_selected: clip was created without VS_CLIP_DEBUG_TAPS");
+    VS_REQUIRE(ctx, pair >= 0 && pair < c->last_pairs && level >= 0 && level < c->g.levels && (axis == 0 || axis == 1) &&
+                    out_order && out_k, "clip_get_selected: bad arguments");
+    const VsLevel& L = c->g.lv[level];
+    int k = 0;
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpyAsync(&k, c->d_dbg_count + ((size_t)pair * 2 + axis) * c->g.levels + level, sizeof(int),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (k < 0 || k > L.ntiles) return vs_set_error(ctx, VS_ERR_INVALID, "clip_get_selected: level %d was not reached by this pair", level);
+    std::vector<uint16_t> tmp(k);
+    if (k) {
+        VS_CUDA(ctx, cudaMemcpyAsync(tmp.data(), c->d_dbg_order + ((size_t)pair * 2 + axis) * c->g.total_tiles + L.tile_off,
+                                     (size_t)k * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (int i = 0; i < k; i++) out_order[i] = tmp[i];
+    *out_k = k;
+    return VS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// vs_internal.h — device-pointer launchers behind the C ABI.  Everything here takes
+// DEVICE pointers and only enqueues work on ctx->stream.
+#pragma once
+#include "vs_common.cuh"
+
+// Dense image descriptor (device memory).  stride/batch_stride in elements.
+struct VsDevImg {
+    void* data;
+    int w, h;
+    int64_t stride;
+    int batch;
+    int64_t batch_stride;
+};
+
+static inline VsDevImg vs_dev_img(const vs_img* im)
+{
+    VsDevImg d;
+    d.data = im->data; d.w = im->width; d.h = im->height; d.stride = im->stride;
+    d.batch = im->batch < 1 ? 1 : im->batch; d.batch_stride = im->batch_stride;
+    return d;
+}
+
+// ---- dense kernels (vs_kernels_dense.cu)
+int vsk_bgr2gray(vs_ctx*, const VsDevImg& bgr, const VsDevImg& gray);
+int vsk_pyr_down(vs_ctx*, const VsDevImg& in, const VsDevImg& out);
+int vsk_grad_xy(vs_ctx*, const VsDevImg& in, const VsDevImg& gx, const VsDevImg& gy);
+int vsk_image_warp(vs_ctx*, const VsDevImg& in, const float* d_params4, const VsDevImg& out);
+
+// inverse-map coefficients of one BGR warp, computed on the host exactly like
+// cv::warpAffine does (f64 inverse of the forward 2x3 matrix)
+struct VsWarpCoef {
+    double i00, i01, i02, i10, i11, i12;
+};
+void vs_warp_coef_from_forward(const double* M6, VsWarpCoef* out);
+// imgproc.cpp:458-466 — centre-based similarity -> forward 2x3 matrix
+void vs_forward_matrix_from_transform(const double* T4, int cols, int rows, double* M6);
+// d_coef: device array of `src.batch` VsWarpCoef
+int vsk_bgr_warp(vs_ctx*, const VsDevImg& src, const VsWarpCoef* d_coef, const VsDevImg& dst,
+                 int dst_x0, int dst_y0, int mode, int border);
+// same, but image b of the batch reads slot d_slots[b] of `src` (src.batch_stride apart)
+int vsk_bgr_warp_slots(vs_ctx*, const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
+                       const VsDevImg& dst, int dst_x0, int dst_y0, int mode, int border);
+
+// ---- sparse kernels (vs_kernels_sparse.cu)
+int vsk_grad_argmax(vs_ctx*, const VsDevImg& gx, const VsDevImg& gy, int tile,
+                    uint16_t* d_lmx, uint16_t* d_lmy);
+int vsk_sparse_jac(vs_ctx*, const VsDevImg& gx, const VsDevImg& gy, const uint16_t* d_lmx,
+                   const uint16_t* d_lmy, int tw, int th, float* d_jx, float* d_jy);
+int vsk_sparse_warpdiff(vs_ctx*, const VsDevImg& tmpl, const VsDevImg& key, const uint16_t* d_lm,
+                        int tw, int th, float A, float B, float TX, float TY, uint16_t* d_out);
+int vsk_sparse_ica(vs_ctx*, const VsDevImg& tmpl, const VsDevImg& key, const uint16_t* d_selx, int kx,
+                   const uint16_t* d_sely, int ky, const float* d_jx, const float* d_jy,
+                   float A, float B, float TX, float TY, double* d_out4);
+
+// ---- fused clip pipeline (vs_clip.cu uses these from vs_kernels_sparse.cu)
+struct VsLevel {
+    int w, h, pitch;          // gray level geometry; pitch in bytes
+    int tile, tw, th, ntiles;
+    uint32_t img_off;         // byte offset of this level inside a slot's pyramid block
+    uint32_t tile_off;        // tile offset of this level inside a per-axis feature array
+};
+
+struct VsClipGeom {
+    int levels;
+    int total_tiles;          // sum of ntiles over levels
+    int max_tiles;            // max ntiles over levels
+    size_t pyr_slot_bytes;    // bytes of one slot's pyramid block
+    VsLevel lv[VS_MAX_LEVELS];
+};
+
+struct VsSolveArgs {
+    const uint8_t* pyr;       // slot-major pyramid store
+    const uint32_t* kp;       // [slot][axis][total_tiles] packed (y<<16 | x)
+    const float4* jac;        // [slot][axis][total_tiles]
+    const vs_pair* pairs;     // device array
+    int n_pairs;
+    double threshold;
+    float fraction;
+    int max_iters;
+    double max_displacement;
+    double* out_T;            // 4 per pair
+    int32_t* out_status;      // 1 per pair
+    int32_t* out_iters;       // levels per pair
+    uint16_t* dbg_warpdiff;   // [pair][axis][total_tiles] or null
+    uint16_t* dbg_order;      // [pair][axis][total_tiles] or null
+    int32_t* dbg_count;       // [pair][axis][levels] or null
+};
+
+int vsk_keyframe_features(vs_ctx*, const VsClipGeom& g, const uint8_t* d_pyr, const int32_t* d_slots,
+                          int n_slots, uint32_t* d_kp, float4* d_jac);
+int vsk_solve_pairs(vs_ctx*, const VsClipGeom& g, const VsSolveArgs& a);

@@ -1,0 +1,443 @@
+// vs_kernels_dense.cu — full-frame kernels: BGR->gray, pyr_down, grad_xy, image_warp, BGR warp.
+// All are HBM-bound byte/integer work: coalesced vector loads, packed 16-bit SIMD-in-register
+// arithmetic where the math allows it, no tensor cores (nothing here is a contraction).
+#include "vs_internal.h"
+
+#include <math.h>
+
+namespace {
+
+// ------------------------------------------------------------------ BGR -> gray
+// cv::cvtColor(BGR2GRAY) (alignment.cpp:212): (3735 B + 19235 G + 9798 R + 16384) >> 15.
+// One thread converts 16 pixels: 3 x 16-byte loads, 1 x 16-byte store.
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r)
+{
+    return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t* v, int k)
+{
+    return (v[k >> 2] >> (8 * (k & 3))) & 0xffu;
+}
+
+__global__ void __launch_bounds__(128)
+k_bgr2gray(const uint8_t* __restrict__ bgr, int64_t in_stride, int64_t in_bs,
+           uint8_t* __restrict__ gray, int64_t out_stride, int64_t out_bs, int w, int h, int vec_ok)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int y = blockIdx.y;
+    if (x0 >= w) return;
+    const uint8_t* src = bgr + (size_t)blockIdx.z * in_bs + (size_t)y * in_stride + (size_t)x0 * 3;
+    uint8_t* dst = gray + (size_t)blockIdx.z * out_bs + (size_t)y * out_stride + x0;
+    if (vec_ok && x0 + 16 <= w) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
+        uint32_t v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int p = q * 4 + i;
+                acc |= gray_of(byte_of(v, 3 * p), byte_of(v, 3 * p + 1), byte_of(v, 3 * p + 2)) << (8 * i);
+            }
+            o[q] = acc;
+        }
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        int n = min(16, w - x0);
+        for (int i = 0; i < n; i++)
+            dst[i] = (uint8_t)gray_of(src[3 * i], src[3 * i + 1], src[3 * i + 2]);
+    }
+}
+
+// ------------------------------------------------------------------ pyr_down
+// generators.cpp:56-92: out(x,y) = (sum_j sum_i k_j k_i in(clamp(2x+i), clamp(2y+j))) >> 8,
+// k = [1 4 6 4 1].  A CTA produces a 64x16 output tile from a 136x35 byte input tile staged
+// in shared memory (edges clamped while staging).  Each thread produces 4 adjacent outputs
+// with packed arithmetic: two 16-bit lanes per register hold the vertical sums of two
+// columns (max 16*255 = 4080), the horizontal pass stays below 65536 (16*4080 = 65280).
+constexpr int PD_TOW = 64, PD_TOH = 16;
+constexpr int PD_IN_W = 2 * PD_TOW + 8;   // 136 bytes = 34 words, origin at 2*ox0 - 4
+constexpr int PD_IN_H = 2 * PD_TOH + 3;   // 35 rows, origin at 2*oy0 - 2
+constexpr int PD_IN_WORDS = PD_IN_W / 4;
+
+__global__ void __launch_bounds__(256)
+k_pyr_down(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, int iw, int ih,
+           uint8_t* __restrict__ out, int64_t out_stride, int64_t out_bs, int ow, int oh, int in_aligned4)
+{
+    __shared__ uint32_t tile[PD_IN_H][PD_IN_WORDS];
+    const int ox0 = blockIdx.x * PD_TOW, oy0 = blockIdx.y * PD_TOH;
+    const uint8_t* src = in + (size_t)blockIdx.z * in_bs;
+    uint8_t* dst = out + (size_t)blockIdx.z * out_bs;
+    const int ix0 = 2 * ox0 - 4, iy0 = 2 * oy0 - 2;
+
+    for (int i = threadIdx.x; i < PD_IN_H * PD_IN_WORDS; i += 256) {
+        int r = i / PD_IN_WORDS, c = i - r * PD_IN_WORDS;
+        int gy = vs_clampi(iy0 + r, 0, ih - 1);
+        int gx = ix0 + 4 * c;
+        const uint8_t* row = src + (size_t)gy * in_stride;
+        uint32_t v;
+        if (in_aligned4 && gx >= 0 && gx + 3 < iw) {
+            v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+        } else {
+            uint32_t b0 = __ldg(row + vs_clampi(gx, 0, iw - 1));
+            uint32_t b1 = __ldg(row + vs_clampi(gx + 1, 0, iw - 1));
+            uint32_t b2 = __ldg(row + vs_clampi(gx + 2, 0, iw - 1));
+            uint32_t b3 = __ldg(row + vs_clampi(gx + 3, 0, iw - 1));
+            v = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        tile[r][c] = v;
+    }
+    __syncthreads();
+
+    const int q = threadIdx.x & 15, ry = threadIdx.x >> 4;
+    // vertical pass on 4 words (16 input columns): even bytes -> E, odd bytes -> O
+    uint32_t E[4], O[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t w0 = tile[2 * ry + 0][2 * q + k], w1 = tile[2 * ry + 1][2 * q + k];
+        uint32_t w2 = tile[2 * ry + 2][2 * q + k], w3 = tile[2 * ry + 3][2 * q + k];
+        uint32_t w4 = tile[2 * ry + 4][2 * q + k];
+        const uint32_t M = 0x00FF00FFu;
+        E[k] = (w0 & M) + (w4 & M) + 4u * ((w1 & M) + (w3 & M)) + 6u * (w2 & M);
+        O[k] = ((w0 >> 8) & M) + ((w4 >> 8) & M) + 4u * (((w1 >> 8) & M) + ((w3 >> 8) & M)) +
+               6u * ((w2 >> 8) & M);
+    }
+    // horizontal pass: out_i = Ev[i+1] + 6 Ev[i+2] + Ev[i+3] + 4 (Od[i+1] + Od[i+2])
+    uint32_t e12 = __byte_perm(E[0], E[1], 0x5432), e34 = __byte_perm(E[1], E[2], 0x5432);
+    uint32_t e56 = __byte_perm(E[2], E[3], 0x5432);
+    uint32_t o12 = __byte_perm(O[0], O[1], 0x5432), o34 = __byte_perm(O[1], O[2], 0x5432);
+    uint32_t s01 = e12 + e34 + 6u * E[1] + 4u * (o12 + O[1]);
+    uint32_t s23 = e34 + e56 + 6u * E[2] + 4u * (o34 + O[2]);
+    uint32_t r01 = (s01 >> 8) & 0x00FF00FFu, r23 = (s23 >> 8) & 0x00FF00FFu;
+    uint32_t packed = __byte_perm(r01, r23, 0x6420);
+
+    const int ox = ox0 + 4 * q, oy = oy0 + ry;
+    if (oy < oh && ox < ow) {
+        uint8_t* o = dst + (size_t)oy * out_stride + ox;
+        if (ox + 4 <= ow && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+            *reinterpret_cast<uint32_t*>(o) = packed;
+        } else {
+            for (int i = 0; i < 4 && ox + i < ow; i++) o[i] = (uint8_t)(packed >> (8 * i));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ grad_xy
+// generators.cpp:202-224: 0.5*(I(x+1,y)-I(x-1,y)), 0.5*(I(x,y+1)-I(x,y-1)), repeat-edge.
+__global__ void __launch_bounds__(128)
+k_grad_xy(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, int iw, int ih,
+          float* __restrict__ gx, int64_t gx_stride, int64_t gx_bs,
+          float* __restrict__ gy, int64_t gy_stride, int64_t gy_bs, int ow, int oh, int vec_ok)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x0 >= ow) return;
+    const uint8_t* src = in + (size_t)blockIdx.z * in_bs;
+    const uint8_t* rc = src + (size_t)vs_clampi(y, 0, ih - 1) * in_stride;
+    const uint8_t* rp = src + (size_t)vs_clampi(y + 1, 0, ih - 1) * in_stride;
+    const uint8_t* rm = src + (size_t)vs_clampi(y - 1, 0, ih - 1) * in_stride;
+    float ax[4], ay[4];
+    float c[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) c[i] = (float)__ldg(rc + vs_clampi(x0 - 1 + i, 0, iw - 1));
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int xc = vs_clampi(x0 + i, 0, iw - 1);
+        ax[i] = __fmul_rn(0.5f, __fsub_rn(c[i + 2], c[i]));
+        ay[i] = __fmul_rn(0.5f, __fsub_rn((float)__ldg(rp + xc), (float)__ldg(rm + xc)));
+    }
+    float* ox = gx + (size_t)blockIdx.z * gx_bs + (size_t)y * gx_stride + x0;
+    float* oy = gy + (size_t)blockIdx.z * gy_bs + (size_t)y * gy_stride + x0;
+    if (vec_ok && x0 + 4 <= ow) {
+        *reinterpret_cast<float4*>(ox) = make_float4(ax[0], ax[1], ax[2], ax[3]);
+        *reinterpret_cast<float4*>(oy) = make_float4(ay[0], ay[1], ay[2], ay[3]);
+    } else {
+        for (int i = 0; i < 4 && x0 + i < ow; i++) { ox[i] = ax[i]; oy[i] = ay[i]; }
+    }
+}
+
+// ------------------------------------------------------------------ image_warp
+// generators.cpp:126-164: pull-mapped bilinear with repeat-edge; Halide's float lerp is
+// a*(1-t) + b*t.  params: {A,B,TX,TY} f32 per batch image (UL origin, imgproc.cpp:125-131).
+__global__ void __launch_bounds__(128)
+k_image_warp(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, int iw, int ih,
+             const float* __restrict__ params, float* __restrict__ out, int64_t out_stride,
+             int64_t out_bs, int ow, int oh, int vec_ok)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x0 >= ow) return;
+    const uint8_t* src = in + (size_t)blockIdx.z * in_bs;
+    const float A = params[blockIdx.z * 4 + 0], B = params[blockIdx.z * 4 + 1];
+    const float TX = params[blockIdx.z * 4 + 2], TY = params[blockIdx.z * 4 + 3];
+    const float onepA = __fadd_rn(1.0f, A);
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float fx = (float)(x0 + i), fy = (float)y;
+        float Wx = __fadd_rn(__fsub_rn(__fmul_rn(onepA, fx), __fmul_rn(B, fy)), TX);
+        float Wy = __fadd_rn(__fadd_rn(__fmul_rn(B, fx), __fmul_rn(onepA, fy)), TY);
+        int flx = (int)floorf(Wx), fly = (int)floorf(Wy);
+        float wx = __fsub_rn(Wx, (float)flx), wy = __fsub_rn(Wy, (float)fly);
+        int xa = vs_clampi(flx, 0, iw - 1), xb = vs_clampi(flx + 1, 0, iw - 1);
+        int ya = vs_clampi(fly, 0, ih - 1), yb = vs_clampi(fly + 1, 0, ih - 1);
+        float p00 = (float)__ldg(src + (size_t)ya * in_stride + xa);
+        float p10 = (float)__ldg(src + (size_t)ya * in_stride + xb);
+        float p01 = (float)__ldg(src + (size_t)yb * in_stride + xa);
+        float p11 = (float)__ldg(src + (size_t)yb * in_stride + xb);
+        float omx = __fsub_rn(1.0f, wx), omy = __fsub_rn(1.0f, wy);
+        float top = __fadd_rn(__fmul_rn(p00, omx), __fmul_rn(p10, wx));
+        float bot = __fadd_rn(__fmul_rn(p01, omx), __fmul_rn(p11, wx));
+        r[i] = __fadd_rn(__fmul_rn(top, omy), __fmul_rn(bot, wy));
+    }
+    float* o = out + (size_t)blockIdx.z * out_bs + (size_t)y * out_stride + x0;
+    if (vec_ok && x0 + 4 <= ow) {
+        *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+        for (int i = 0; i < 4 && x0 + i < ow; i++) o[i] = r[i];
+    }
+}
+
+// ------------------------------------------------------------------ BGR warp
+// warpBySimilarityTransform (imgproc.cpp:446-484).  Mode 0 is bit-exact with
+// cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT): 10-bit fixed-point coordinates rounded to
+// 1/32 px, integer weights; (sum w p + 16384) >> 15 with w = wx*wy*32 equals
+// (sum wx*wy*p + 512) >> 10.
+template <int MODE, int BORDER>
+__device__ __forceinline__ float bgr_tap_f(const uint8_t* __restrict__ src, int64_t stride, int w, int h,
+                                           int x, int y, int c)
+{
+    if (BORDER == VS_BORDER_REPEAT_EDGE) {
+        x = vs_clampi(x, 0, w - 1); y = vs_clampi(y, 0, h - 1);
+    } else if (x < 0 || x >= w || y < 0 || y >= h) {
+        return 0.0f;
+    }
+    return (float)__ldg(src + (size_t)y * stride + 3 * x + c);
+}
+
+template <int MODE, int BORDER>
+__global__ void __launch_bounds__(256)
+k_bgr_warp(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
+           const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
+           uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
+           int dst_x0, int dst_y0)
+{
+    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yo = blockIdx.y;
+    if (xo >= dw) return;
+    const int b = blockIdx.z;
+    const int slot = slots ? slots[b] : b;
+    const uint8_t* src = src_base + (size_t)slot * src_bs;
+    uint8_t* d = dst_base + (size_t)b * dst_bs + (size_t)yo * dst_stride + 3 * xo;
+    const VsWarpCoef cf = coefs[b];
+    const int x = xo + dst_x0, y = yo + dst_y0;
+
+    if (MODE == VS_WARP_CV_EXACT_BILINEAR) {
+        int adelta = __double2int_rn(cf.i00 * (double)x * 1024.0);
+        int bdelta = __double2int_rn(cf.i10 * (double)x * 1024.0);
+        int X0 = __double2int_rn((cf.i01 * (double)y + cf.i02) * 1024.0) + 16;
+        int Y0 = __double2int_rn((cf.i11 * (double)y + cf.i12) * 1024.0) + 16;
+        int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+        int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
+        int w00 = (32 - fx) * (32 - fy), w10 = fx * (32 - fy), w01 = (32 - fx) * fy, w11 = fx * fy;
+        int x1 = sx + 1, y1 = sy + 1;
+        bool in00, in10, in01, in11;
+        int cx0 = sx, cx1 = x1, cy0 = sy, cy1 = y1;
+        if (BORDER == VS_BORDER_REPEAT_EDGE) {
+            cx0 = vs_clampi(sx, 0, w - 1); cx1 = vs_clampi(x1, 0, w - 1);
+            cy0 = vs_clampi(sy, 0, h - 1); cy1 = vs_clampi(y1, 0, h - 1);
+            in00 = in10 = in01 = in11 = true;
+        } else {
+            bool xin0 = sx >= 0 && sx < w, xin1 = x1 >= 0 && x1 < w;
+            bool yin0 = sy >= 0 && sy < h, yin1 = y1 >= 0 && y1 < h;
+            in00 = xin0 && yin0; in10 = xin1 && yin0; in01 = xin0 && yin1; in11 = xin1 && yin1;
+        }
+        const uint8_t* r0 = src + (size_t)cy0 * src_stride;
+        const uint8_t* r1 = src + (size_t)cy1 * src_stride;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            int p00 = in00 ? (int)__ldg(r0 + 3 * cx0 + c) : 0;
+            int p10 = in10 ? (int)__ldg(r0 + 3 * cx1 + c) : 0;
+            int p01 = in01 ? (int)__ldg(r1 + 3 * cx0 + c) : 0;
+            int p11 = in11 ? (int)__ldg(r1 + 3 * cx1 + c) : 0;
+            int v = w00 * p00 + w10 * p10 + w01 * p01 + w11 * p11;
+            d[c] = (uint8_t)((v + 512) >> 10);
+        }
+        return;
+    }
+
+    const float f00 = (float)cf.i00, f01 = (float)cf.i01, f02 = (float)cf.i02;
+    const float f10 = (float)cf.i10, f11 = (float)cf.i11, f12 = (float)cf.i12;
+    float Wx = __fadd_rn(__fadd_rn(__fmul_rn(f00, (float)x), __fmul_rn(f01, (float)y)), f02);
+    float Wy = __fadd_rn(__fadd_rn(__fmul_rn(f10, (float)x), __fmul_rn(f11, (float)y)), f12);
+    float fWx = floorf(Wx), fWy = floorf(Wy);
+    float rx = __fsub_rn(Wx, fWx), ry = __fsub_rn(Wy, fWy);
+    int ix = (int)fWx, iy = (int)fWy;
+    if (MODE == VS_WARP_FLOAT_BILINEAR) {
+        float omx = __fsub_rn(1.0f, rx), omy = __fsub_rn(1.0f, ry);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float p00 = bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix, iy, c);
+            float p10 = bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix + 1, iy, c);
+            float p01 = bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix, iy + 1, c);
+            float p11 = bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix + 1, iy + 1, c);
+            float top = __fadd_rn(__fmul_rn(p00, omx), __fmul_rn(p10, rx));
+            float bot = __fadd_rn(__fmul_rn(p01, omx), __fmul_rn(p11, rx));
+            float v = __fadd_rn(__fmul_rn(top, omy), __fmul_rn(bot, ry));
+            v = fminf(fmaxf(__fadd_rn(v, 0.5f), 0.0f), 255.0f);
+            d[c] = (uint8_t)v;
+        }
+    } else {
+        float wx[5], wy[5];
+#pragma unroll
+        for (int u = 0; u < 5; u++) {
+            wx[u] = vs_lanczos2(__fsub_rn((float)(u - 2), rx));
+            wy[u] = vs_lanczos2(__fsub_rn((float)(u - 2), ry));
+        }
+        float num0 = 0.0f, num1 = 0.0f, num2 = 0.0f, den = 0.0f;
+#pragma unroll
+        for (int ty = 1; ty < 5; ty++) {
+#pragma unroll
+            for (int tx = 1; tx < 5; tx++) {   // column/row 0 weights are exactly 0
+                float w2 = __fmul_rn(wx[tx], wy[ty]);
+                num0 = __fadd_rn(num0, __fmul_rn(w2, bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix + tx - 2, iy + ty - 2, 0)));
+                num1 = __fadd_rn(num1, __fmul_rn(w2, bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix + tx - 2, iy + ty - 2, 1)));
+                num2 = __fadd_rn(num2, __fmul_rn(w2, bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix + tx - 2, iy + ty - 2, 2)));
+                den = __fadd_rn(den, w2);
+            }
+        }
+        float v0 = fminf(fmaxf(__fadd_rn(__fdiv_rn(num0, den), 0.5f), 0.0f), 255.0f);
+        float v1 = fminf(fmaxf(__fadd_rn(__fdiv_rn(num1, den), 0.5f), 0.0f), 255.0f);
+        float v2 = fminf(fmaxf(__fadd_rn(__fdiv_rn(num2, den), 0.5f), 0.0f), 255.0f);
+        d[0] = (uint8_t)v0; d[1] = (uint8_t)v1; d[2] = (uint8_t)v2;
+    }
+}
+
+inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace
+
+// ================================================================== launchers
+
+int vsk_bgr2gray(vs_ctx* ctx, const VsDevImg& bgr, const VsDevImg& gray)
+{
+    VS_REQUIRE(ctx, bgr.w == gray.w && bgr.h == gray.h && bgr.batch == gray.batch, "bgr2gray: shape mismatch");
+    if (bgr.w <= 0 || bgr.h <= 0) return VS_OK;
+    VS_REQUIRE(ctx, bgr.h <= 65535 && bgr.batch <= 65535, "bgr2gray: image too tall / batch too large");
+    int vec_ok = aligned_to(bgr.data, 16) && bgr.stride % 16 == 0 && bgr.batch_stride % 16 == 0 &&
+                 aligned_to(gray.data, 16) && gray.stride % 16 == 0 && gray.batch_stride % 16 == 0;
+    dim3 block(128), grid(vs_cdiv(vs_cdiv(bgr.w, 16), 128), bgr.h, bgr.batch);
+    k_bgr2gray<<<grid, block, 0, ctx->stream>>>((const uint8_t*)bgr.data, bgr.stride, bgr.batch_stride,
+                                                (uint8_t*)gray.data, gray.stride, gray.batch_stride,
+                                                bgr.w, bgr.h, vec_ok);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+int vsk_pyr_down(vs_ctx* ctx, const VsDevImg& in, const VsDevImg& out)
+{
+    VS_REQUIRE(ctx, in.batch == out.batch, "pyr_down: batch mismatch");
+    VS_REQUIRE(ctx, in.w > 0 && in.h > 0, "pyr_down: empty input");
+    if (out.w <= 0 || out.h <= 0) return VS_OK;
+    VS_REQUIRE(ctx, out.batch <= 65535 && vs_cdiv(out.h, PD_TOH) <= 65535, "pyr_down: grid too large");
+    int in_al = aligned_to(in.data, 4) && in.stride % 4 == 0 && in.batch_stride % 4 == 0;
+    dim3 block(256), grid(vs_cdiv(out.w, PD_TOW), vs_cdiv(out.h, PD_TOH), out.batch);
+    k_pyr_down<<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
+                                                (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h, in_al);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+int vsk_grad_xy(vs_ctx* ctx, const VsDevImg& in, const VsDevImg& gx, const VsDevImg& gy)
+{
+    VS_REQUIRE(ctx, gx.w == gy.w && gx.h == gy.h && in.batch == gx.batch && in.batch == gy.batch, "grad_xy: shape mismatch");
+    VS_REQUIRE(ctx, in.w > 0 && in.h > 0, "grad_xy: empty input");
+    if (gx.w <= 0 || gx.h <= 0) return VS_OK;
+    VS_REQUIRE(ctx, gx.h <= 65535 && gx.batch <= 65535, "grad_xy: grid too large");
+    int vec_ok = aligned_to(gx.data, 16) && gx.stride % 4 == 0 && gx.batch_stride % 4 == 0 &&
+                 aligned_to(gy.data, 16) && gy.stride % 4 == 0 && gy.batch_stride % 4 == 0;
+    dim3 block(128), grid(vs_cdiv(vs_cdiv(gx.w, 4), 128), gx.h, gx.batch);
+    k_grad_xy<<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
+                                               (float*)gx.data, gx.stride, gx.batch_stride,
+                                               (float*)gy.data, gy.stride, gy.batch_stride, gx.w, gx.h, vec_ok);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+int vsk_image_warp(vs_ctx* ctx, const VsDevImg& in, const float* d_params4, const VsDevImg& out)
+{
+    VS_REQUIRE(ctx, in.batch == out.batch, "image_warp: batch mismatch");
+    VS_REQUIRE(ctx, in.w > 0 && in.h > 0, "image_warp: empty input");
+    if (out.w <= 0 || out.h <= 0) return VS_OK;
+    VS_REQUIRE(ctx, out.h <= 65535 && out.batch <= 65535, "image_warp: grid too large");
+    int vec_ok = aligned_to(out.data, 16) && out.stride % 4 == 0 && out.batch_stride % 4 == 0;
+    dim3 block(128), grid(vs_cdiv(vs_cdiv(out.w, 4), 128), out.h, out.batch);
+    k_image_warp<<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
+                                                  d_params4, (float*)out.data, out.stride, out.batch_stride,
+                                                  out.w, out.h, vec_ok);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+// cv::warpAffine inverts the forward matrix in f64 (no WARP_INVERSE_MAP at imgproc.cpp:472)
+void vs_warp_coef_from_forward(const double* M, VsWarpCoef* o)
+{
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1.0 / D : 0;
+    double A11 = M[4] * D, A22 = M[0] * D;
+    o->i00 = A11; o->i01 = M[1] * (-D); o->i10 = M[3] * (-D); o->i11 = A22;
+    o->i02 = -o->i00 * M[2] - o->i01 * M[5];
+    o->i12 = -o->i10 * M[2] - o->i11 * M[5];
+}
+
+void vs_forward_matrix_from_transform(const double* T, int cols, int rows, double* M)
+{
+    double cx = (cols - 1) * 0.5, cy = (rows - 1) * 0.5;
+    double tx_ul = T[2] - T[0] * cx + T[1] * cy;
+    double ty_ul = T[3] - T[1] * cx - T[0] * cy;
+    M[0] = 1.0 + T[0]; M[1] = -T[1]; M[2] = tx_ul;
+    M[3] = T[1]; M[4] = 1.0 + T[0]; M[5] = ty_ul;
+}
+
+template <int MODE>
+static void launch_bgr_warp(int border, dim3 grid, dim3 block, cudaStream_t s,
+                            const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
+                            const VsDevImg& dst, int dst_x0, int dst_y0)
+{
+    if (border == VS_BORDER_REPEAT_EDGE)
+        k_bgr_warp<MODE, VS_BORDER_REPEAT_EDGE><<<grid, block, 0, s>>>(
+            (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
+            (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0);
+    else
+        k_bgr_warp<MODE, VS_BORDER_CONSTANT0><<<grid, block, 0, s>>>(
+            (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
+            (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0);
+}
+
+int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
+                       const VsDevImg& dst, int dst_x0, int dst_y0, int mode, int border)
+{
+    VS_REQUIRE(ctx, src.w > 0 && src.h > 0, "bgr_warp: empty source");
+    VS_REQUIRE(ctx, mode >= 0 && mode <= 2 && (border == 0 || border == 1), "bgr_warp: bad mode/border");
+    if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
+    VS_REQUIRE(ctx, dst.h <= 65535 && dst.batch <= 65535, "bgr_warp: grid too large");
+    dim3 block(256), grid(vs_cdiv(dst.w, 256), dst.h, dst.batch);
+    if (mode == VS_WARP_CV_EXACT_BILINEAR)
+        launch_bgr_warp<VS_WARP_CV_EXACT_BILINEAR>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
+    else if (mode == VS_WARP_FLOAT_BILINEAR)
+        launch_bgr_warp<VS_WARP_FLOAT_BILINEAR>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
+    else
+        launch_bgr_warp<VS_WARP_LANCZOS2>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+int vsk_bgr_warp(vs_ctx* ctx, const VsDevImg& src, const VsWarpCoef* d_coef, const VsDevImg& dst,
+                 int dst_x0, int dst_y0, int mode, int border)
+{
+    VS_REQUIRE(ctx, src.batch == dst.batch, "bgr_warp: batch mismatch");
+    return vsk_bgr_warp_slots(ctx, src, nullptr, d_coef, dst, dst_x0, dst_y0, mode, border);
+}

@@ -1,0 +1,491 @@
+// vs_kernels_sparse.cu — keypoint kernels: per-tile gradient argmax, Jacobians, Lanczos-2
+// warp-diff, and the per-pair inverse-compositional Gauss-Newton solver that runs the whole
+// coarse-to-fine loop of VideoAligner::AlignNextFrame (alignment.cpp:390-693) on the device,
+// one CTA per frame pair, many pairs per launch.
+#include "vs_internal.h"
+#include "vs_introselect.cuh"
+#include "vs_linalg4.cuh"
+
+namespace {
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------- grad_argmax (f32 planes)
+// generators.cpp:260-294.  One warp per tile.  Key = (bits(|g|)+1) << 32 | (N*N-1 - scan
+// index): the maximum key is the first maximum in (r.y outer, r.x inner) order; a NaN never
+// wins (as with Halide's strict '>' against the running best).
+__global__ void __launch_bounds__(256)
+k_grad_argmax(const float* __restrict__ gx, int64_t gxs, const float* __restrict__ gy, int64_t gys,
+              int tile, int tw, int th, uint16_t* __restrict__ lmx, uint16_t* __restrict__ lmy)
+{
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wid >= tw * th) return;
+    const int tx = wid % tw, ty = wid / tw;
+    const int n = tile * tile;
+    unsigned long long bx = 0, by = 0;
+    for (int p = lane; p < n; p += 32) {
+        int ry = p / tile, rx = p - ry * tile;
+        float a = fabsf(__ldg(gx + (size_t)(ty * tile + ry) * gxs + tx * tile + rx));
+        float b = fabsf(__ldg(gy + (size_t)(ty * tile + ry) * gys + tx * tile + rx));
+        unsigned long long inv = (unsigned long long)(n - 1 - p);
+        unsigned long long ka = isnan(a) ? 0ull : (((unsigned long long)__float_as_uint(a) + 1ull) << 32) | inv;
+        unsigned long long kb = isnan(b) ? 0ull : (((unsigned long long)__float_as_uint(b) + 1ull) << 32) | inv;
+        bx = ka > bx ? ka : bx;
+        by = kb > by ? kb : by;
+    }
+    bx = warp_max_u64(bx);
+    by = warp_max_u64(by);
+    if (lane == 0) {
+        int px = (bx >> 32) == 0 ? 0 : n - 1 - (int)(bx & 0xffffffffu);
+        int py = (by >> 32) == 0 ? 0 : n - 1 - (int)(by & 0xffffffffu);
+        size_t plane = (size_t)tw * th, t = (size_t)ty * tw + tx;
+        lmx[t] = (uint16_t)(px % tile + tx * tile);
+        lmx[plane + t] = (uint16_t)(px / tile + ty * tile);
+        lmy[t] = (uint16_t)(py % tile + tx * tile);
+        lmy[plane + t] = (uint16_t)(py / tile + ty * tile);
+    }
+}
+
+// ------------------------------------------------------------- sparse_jac (f32 planes)
+// generators.cpp:332-386
+__device__ __forceinline__ float4 jac_x(float g, int ix, int iy, int w, int h)
+{
+    float cx = __fmul_rn((float)w, 0.5f), cy = __fmul_rn((float)h, 0.5f);
+    float scale = __fdiv_rn(1.f, (float)w);
+    float u = __fsub_rn((float)ix, cx), v = __fsub_rn((float)iy, cy);
+    float g2 = __fmul_rn(2.f, g);
+    return make_float4(__fmul_rn(__fmul_rn(g2, u), scale), __fmul_rn(__fmul_rn(g2, -v), scale), g2, 0.f);
+}
+__device__ __forceinline__ float4 jac_y(float g, int ix, int iy, int w, int h)
+{
+    float cx = __fmul_rn((float)w, 0.5f), cy = __fmul_rn((float)h, 0.5f);
+    float scale = __fdiv_rn(1.f, (float)w);
+    float u = __fsub_rn((float)ix, cx), v = __fsub_rn((float)iy, cy);
+    float g2 = __fmul_rn(2.f, g);
+    return make_float4(__fmul_rn(__fmul_rn(g2, v), scale), __fmul_rn(__fmul_rn(g2, u), scale), 0.f, g2);
+}
+
+__global__ void __launch_bounds__(128)
+k_sparse_jac(const float* __restrict__ gx, int64_t gxs, const float* __restrict__ gy, int64_t gys,
+             int w, int h, const uint16_t* __restrict__ lmx, const uint16_t* __restrict__ lmy,
+             int tw, int th, float* __restrict__ jx, float* __restrict__ jy)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int plane = tw * th;
+    if (t >= plane) return;
+    int ix0 = min((int)lmx[t], w - 1), iy0 = min((int)lmx[plane + t], h - 1);
+    int ix1 = min((int)lmy[t], w - 1), iy1 = min((int)lmy[plane + t], h - 1);
+    float4 a = jac_x(__ldg(gx + (size_t)iy0 * gxs + ix0), ix0, iy0, w, h);
+    float4 b = jac_y(__ldg(gy + (size_t)iy1 * gys + ix1), ix1, iy1, w, h);
+    jx[t] = a.x; jx[plane + t] = a.y; jx[2 * plane + t] = a.z; jx[3 * plane + t] = a.w;
+    jy[t] = b.x; jy[plane + t] = b.y; jy[2 * plane + t] = b.z; jy[3 * plane + t] = b.w;
+}
+
+// ------------------------------------------------------------- keyframe features (fused)
+// ComputeKeyFrame (alignment.cpp:237-276) without materialising the f32 gradient planes:
+// gray level -> per-tile argmax of |gx| and |gy| -> keypoint + Jacobian.  One warp per tile,
+// all levels and all requested slots in one launch.  2|g| = |I(+1) - I(-1)| is an integer in
+// [0,255], so key = 2|g| << 16 | (N*N-1 - scan index) reproduces Halide's first-maximum rule.
+__global__ void __launch_bounds__(256)
+k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t* __restrict__ slots,
+                    uint32_t* __restrict__ kp, float4* __restrict__ jac)
+{
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wid >= g.total_tiles) return;
+    const int slot = slots[blockIdx.y];
+    int lvl = 0;
+    while (lvl + 1 < g.levels && wid >= (int)g.lv[lvl + 1].tile_off) lvl++;
+    const VsLevel L = g.lv[lvl];
+    const int t = wid - (int)L.tile_off;
+    const int tx = t % L.tw, ty = t / L.tw;
+    const uint8_t* img = pyr + (size_t)slot * g.pyr_slot_bytes + L.img_off;
+    const int N = L.tile, n = N * N;
+    uint32_t bx = 0, by = 0;
+    for (int p = lane; p < n; p += 32) {
+        int ry = p / N, rx = p - ry * N;
+        int x = tx * N + rx, y = ty * N + ry;
+        const uint8_t* row = img + (size_t)y * L.pitch;
+        int xp = __ldg(row + min(x + 1, L.w - 1)), xm = __ldg(row + max(x - 1, 0));
+        int yp = __ldg(img + (size_t)min(y + 1, L.h - 1) * L.pitch + x);
+        int ym = __ldg(img + (size_t)max(y - 1, 0) * L.pitch + x);
+        uint32_t inv = (uint32_t)(n - 1 - p);
+        bx = max(bx, ((uint32_t)abs(xp - xm) << 16) | inv);
+        by = max(by, ((uint32_t)abs(yp - ym) << 16) | inv);
+    }
+    bx = __reduce_max_sync(0xffffffffu, bx);
+    by = __reduce_max_sync(0xffffffffu, by);
+    if (lane < 2) {
+        const int axis = lane;
+        int p = n - 1 - (int)((axis == 0 ? bx : by) & 0xffffu);
+        int x = tx * N + p % N, y = ty * N + p / N;
+        float gval;
+        float4 J;
+        if (axis == 0) {
+            const uint8_t* row = img + (size_t)y * L.pitch;
+            gval = __fmul_rn(0.5f, __fsub_rn((float)__ldg(row + min(x + 1, L.w - 1)), (float)__ldg(row + max(x - 1, 0))));
+            J = jac_x(gval, x, y, L.w, L.h);
+        } else {
+            gval = __fmul_rn(0.5f, __fsub_rn((float)__ldg(img + (size_t)min(y + 1, L.h - 1) * L.pitch + x),
+                                             (float)__ldg(img + (size_t)max(y - 1, 0) * L.pitch + x)));
+            J = jac_y(gval, x, y, L.w, L.h);
+        }
+        size_t o = ((size_t)slot * 2 + axis) * g.total_tiles + wid;
+        kp[o] = ((uint32_t)y << 16) | (uint32_t)x;
+        jac[o] = J;
+    }
+}
+
+// ------------------------------------------------------------- sparse_warpdiff (standalone)
+// generators.cpp:646-700
+__global__ void __launch_bounds__(128)
+k_sparse_warpdiff(const uint8_t* __restrict__ tmpl, int64_t ts, const uint8_t* __restrict__ key, int64_t ks,
+                  int w, int h, const uint16_t* __restrict__ lm, int plane,
+                  float A, float B, float TX, float TY, uint16_t* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= plane) return;
+    int px = min((int)lm[t], w - 1), py = min((int)lm[plane + t], h - 1);
+    float s = vs_lanczos_sample(key, w, h, (int)ks, (float)px, (float)py, A, B, TX, TY);
+    float d = fabsf(__fsub_rn(s, (float)__ldg(tmpl + (size_t)py * ts + px)));
+    d = fmaxf(fminf(d, 65535.0f), 0.0f);
+    out[t] = (uint16_t)d;
+}
+
+// ------------------------------------------------------------- sparse_ica (standalone)
+// generators.cpp:429-596.  Single CTA; f32 J*r products accumulated in f64.
+__global__ void __launch_bounds__(256)
+k_sparse_ica(const uint8_t* __restrict__ tmpl, int64_t ts, const uint8_t* __restrict__ key, int64_t ks,
+             int w, int h, const uint16_t* __restrict__ selx, int kx, const uint16_t* __restrict__ sely, int ky,
+             const float* __restrict__ jx, const float* __restrict__ jy,
+             float A, float B, float TX, float TY, double* __restrict__ out)
+{
+    __shared__ double red[8][4];
+    double acc[4] = {0, 0, 0, 0};
+    for (int i = threadIdx.x; i < kx + ky; i += blockDim.x) {
+        const bool isx = i < kx;
+        const int j = isx ? i : i - kx, k = isx ? kx : ky;
+        const uint16_t* sel = isx ? selx : sely;
+        const float* jac = isx ? jx : jy;
+        int px = sel[j], py = sel[k + j];
+        float warped = vs_lanczos_sample(key, w, h, (int)ks, (float)px, (float)py, A, B, TX, TY);
+        int tx = min(px, w - 1), ty = min(py, h - 1);
+        float residual = __fsub_rn((float)__ldg(tmpl + (size_t)ty * ts + tx), warped);
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[c] += (double)__fmul_rn(jac[(size_t)c * k + j], residual);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        double v = vs_warp_reduce_sum(acc[c]);
+        if (lane == 0) red[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); wv++) s += red[wv][threadIdx.x];
+        out[threadIdx.x] = s * 0.5;
+    }
+}
+
+// ------------------------------------------------------------- per-pair solver
+constexpr int SOLVE_THREADS = 256;
+constexpr int SOLVE_WARPS = SOLVE_THREADS / 32;
+enum { FLAG_CONTINUE = 0, FLAG_CONVERGED = 1, FLAG_FAIL = 2 };
+
+struct SolveShared {
+    double T[4];
+    double Hinv[16];
+    double red[SOLVE_WARPS][12];
+    double c0[4][2], c1[4][2];
+    int flag;
+    int status;
+};
+
+template <int N>
+__device__ __forceinline__ void block_reduce(double* v, SolveShared& sh, double* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        double r = vs_warp_reduce_sum(v[i]);
+        if (lane == 0) sh.red[warp][i] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            double s = 0;
+            for (int w = 0; w < SOLVE_WARPS; w++) s += sh.red[w][i];
+            total[i] = s;
+        }
+    }
+}
+
+__device__ __forceinline__ double dist2d(const double* a, const double* b)
+{
+    double dx = a[0] - b[0], dy = a[1] - b[1];
+    return sqrt(dx * dx + dy * dy);
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_solve_pairs(VsClipGeom g, VsSolveArgs a)
+{
+    extern __shared__ uint32_t dyn_keys[];   // keys[2][max_tiles]: abs_delta << 16 | tile
+    __shared__ SolveShared sh;
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.x;
+    if (pair >= a.n_pairs) return;
+    const vs_pair pr = a.pairs[pair];
+    const uint8_t* tpyr = a.pyr + (size_t)pr.template_slot * g.pyr_slot_bytes;
+    const uint8_t* kpyr = a.pyr + (size_t)pr.keyframe_slot * g.pyr_slot_bytes;
+    const size_t feat = (size_t)pr.keyframe_slot * 2 * g.total_tiles;
+    uint32_t* const keys0 = dyn_keys;
+    uint32_t* const keys1 = dyn_keys + g.max_tiles;
+
+    if (tid == 0) {
+        sh.T[0] = sh.T[1] = sh.T[2] = sh.T[3] = 0.0;
+        sh.status = 1;
+        if (a.out_iters) for (int l = 0; l < g.levels; l++) a.out_iters[(size_t)pair * g.levels + l] = 0;
+    }
+
+    for (int lvl = g.levels - 1; lvl >= 0; lvl--) {
+        const VsLevel L = g.lv[lvl];
+        const uint8_t* timg = tpyr + L.img_off;
+        const uint8_t* kimg = kpyr + L.img_off;
+        const uint32_t* const kpl0 = a.kp + feat + L.tile_off;
+        const uint32_t* const kpl1 = kpl0 + g.total_tiles;
+        const float4* const jcl0 = a.jac + feat + L.tile_off;
+        const float4* const jcl1 = jcl0 + g.total_tiles;
+        const int nt = L.ntiles;
+        const int k = vs_sel::selected_count(nt, a.fraction);
+        __syncthreads();   // sh.T of the previous level (or the initial identity) is visible
+
+        // ---- SparseWarpDiff for both keypoint sets with the incoming transform (alignment.cpp:409-431)
+        float P[4];
+        vs_ul_params_half(sh.T, L.w, L.h, P);
+        for (int i = tid; i < 2 * nt; i += SOLVE_THREADS) {
+            const int axis = i >= nt, t = i - axis * nt;
+            uint32_t kv = __ldg((axis ? kpl1 : kpl0) + t);
+            int px = min((int)(kv & 0xffffu), L.w - 1), py = min((int)(kv >> 16), L.h - 1);
+            float s = vs_lanczos_sample(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3]);
+            float d = fabsf(__fsub_rn(s, (float)__ldg(timg + (size_t)py * L.pitch + px)));
+            d = fmaxf(fminf(d, 65535.0f), 0.0f);
+            uint32_t u = (uint32_t)d;
+            (axis ? keys1 : keys0)[t] = (u << 16) | (uint32_t)t;
+            if (a.dbg_warpdiff)
+                a.dbg_warpdiff[((size_t)pair * 2 + axis) * g.total_tiles + L.tile_off + t] = (uint16_t)u;
+        }
+        __syncthreads();
+
+        // ---- keep the k smallest: exact replay of std::nth_element (alignment.cpp:460-486)
+        if (tid == 0) vs_sel::nth_element_serial(keys0, nt, k);
+        if (tid == 32) vs_sel::nth_element_serial(keys1, nt, k);
+        __syncthreads();
+
+        if (a.dbg_order) {
+            for (int i = tid; i < 2 * k; i += SOLVE_THREADS) {
+                const int axis = i >= k, j = i - axis * k;
+                a.dbg_order[((size_t)pair * 2 + axis) * g.total_tiles + L.tile_off + j] = (uint16_t)((axis ? keys1 : keys0)[j] & 0xffffu);
+            }
+            if (tid < 2) a.dbg_count[((size_t)pair * 2 + tid) * g.levels + lvl] = k;
+        }
+
+        // ---- H = sum j j^T in f64 (alignment.cpp:278-332); X rows are (a,b,c,0), Y rows (a,b,0,c)
+        {
+            double hs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = tid; i < 2 * k; i += SOLVE_THREADS) {
+                const int axis = i >= k, j = i - axis * k;
+                const int t = (int)((axis ? keys1 : keys0)[j] & 0xffffu);
+                float4 J = __ldg((axis ? jcl1 : jcl0) + t);
+                double ja = J.x, jb = J.y, jc = axis == 0 ? J.z : J.w;
+                hs[0] += ja * ja; hs[1] += ja * jb; hs[2] += jb * jb;
+                if (axis == 0) { hs[3] += ja * jc; hs[4] += jb * jc; hs[5] += jc * jc; }
+                else           { hs[6] += ja * jc; hs[7] += jb * jc; hs[8] += jc * jc; }
+            }
+            double tot[9];
+            block_reduce<9>(hs, sh, tot);
+            if (tid == 0) {
+                double H[16];
+                H[0] = tot[0]; H[1] = tot[1]; H[2] = tot[3]; H[3] = tot[6];
+                H[4] = tot[1]; H[5] = tot[2]; H[6] = tot[4]; H[7] = tot[7];
+                H[8] = tot[3]; H[9] = tot[4]; H[10] = tot[5]; H[11] = 0.0;
+                H[12] = tot[6]; H[13] = tot[7]; H[14] = 0.0; H[15] = tot[8];
+                vs_condition_and_invert(H, sh.Hinv);
+                // corner bookkeeping (alignment.cpp:585-598)
+                const double cx = L.w * 0.5, cy = L.h * 0.5;
+                const double xr = (double)((float)L.w - 1.f), yb = (double)((float)L.h - 1.f);
+                const double cr[4][2] = {{0.0, 0.0}, {xr, 0.0}, {0.0, yb}, {xr, yb}};
+                for (int c = 0; c < 4; c++) {
+                    vs_tf_warp_center(sh.T, cr[c][0], cr[c][1], cx, cy, sh.c0[c]);
+                    sh.c1[c][0] = sh.c0[c][0]; sh.c1[c][1] = sh.c0[c][1];
+                }
+                sh.flag = FLAG_CONTINUE;
+            }
+        }
+        __syncthreads();
+
+        // ---- inverse-compositional Gauss-Newton iterations (alignment.cpp:600-668)
+        int iters = 0;
+        int flag = FLAG_CONTINUE;
+        for (int iter = 0; iter < a.max_iters; iter++) {
+            iters++;
+            vs_ul_params_half(sh.T, L.w, L.h, P);
+            double b[4] = {0, 0, 0, 0};
+            for (int i = tid; i < 2 * k; i += SOLVE_THREADS) {
+                const int axis = i >= k, j = i - axis * k;
+                const int t = (int)((axis ? keys1 : keys0)[j] & 0xffffu);
+                uint32_t kv = __ldg((axis ? kpl1 : kpl0) + t);
+                int px = (int)(kv & 0xffffu), py = (int)(kv >> 16);
+                float4 J = __ldg((axis ? jcl1 : jcl0) + t);
+                float warped = vs_lanczos_sample(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3]);
+                int qx = min(px, L.w - 1), qy = min(py, L.h - 1);
+                float r = __fsub_rn((float)__ldg(timg + (size_t)qy * L.pitch + qx), warped);
+                b[0] += (double)__fmul_rn(J.x, r);
+                b[1] += (double)__fmul_rn(J.y, r);
+                if (axis == 0) b[2] += (double)__fmul_rn(J.z, r);
+                else           b[3] += (double)__fmul_rn(J.w, r);
+            }
+            double tot[4];
+            block_reduce<4>(b, sh, tot);
+            if (tid == 0) {
+                double bb[4], dt[4];
+                for (int c = 0; c < 4; c++) bb[c] = tot[c] * 0.5;
+                for (int r = 0; r < 4; r++) {
+                    double s = 0;
+                    for (int c = 0; c < 4; c++) s += sh.Hinv[r * 4 + c] * bb[c];
+                    dt[r] = s;
+                }
+                const double scale = 1.0 / L.w;
+                double delta[4] = {dt[0] * scale, dt[1] * scale, dt[2], dt[3]};
+                double Tn[4];
+                vs_tf_compose(delta, sh.T, Tn);
+                sh.T[0] = Tn[0]; sh.T[1] = Tn[1]; sh.T[2] = Tn[2]; sh.T[3] = Tn[3];
+                const double cx = L.w * 0.5, cy = L.h * 0.5;
+                const double xr = (double)((float)L.w - 1.f), yb = (double)((float)L.h - 1.f);
+                const double cr[4][2] = {{0.0, 0.0}, {xr, 0.0}, {0.0, yb}, {xr, yb}};
+                double d12 = 0.0;
+                for (int c = 0; c < 4; c++) {
+                    double c2[2];
+                    vs_tf_warp_center(sh.T, cr[c][0], cr[c][1], cx, cy, c2);
+                    d12 = fmax(d12, dist2d(c2, sh.c1[c]));
+                    sh.c1[c][0] = c2[0]; sh.c1[c][1] = c2[1];
+                }
+                int f = FLAG_CONTINUE;
+                if (d12 < a.threshold) f = FLAG_CONVERGED;
+                else if (iter >= a.max_iters - 1) f = FLAG_FAIL;
+                sh.flag = f;
+            }
+            __syncthreads();
+            flag = sh.flag;
+            if (flag != FLAG_CONTINUE) break;
+        }
+
+        if (tid == 0) {
+            if (a.out_iters) a.out_iters[(size_t)pair * g.levels + lvl] = iters;
+            if (flag == FLAG_FAIL) {
+                sh.status = 0;
+            } else {
+                double d01 = 0.0;
+                for (int c = 0; c < 4; c++) d01 = fmax(d01, dist2d(sh.c0[c], sh.c1[c]));
+                if (d01 > a.max_displacement) sh.status = 0;
+                else if (lvl > 0) { sh.T[2] *= 2.0; sh.T[3] *= 2.0; }
+            }
+        }
+        __syncthreads();
+        if (sh.status == 0) break;
+    }
+
+    if (tid == 0) {
+        double T[4] = {sh.T[0], sh.T[1], sh.T[2], sh.T[3]};
+        if (sh.status == 1 && pr.invert) {
+            double Ti[4];
+            vs_tf_inverse(T, Ti);
+            T[0] = Ti[0]; T[1] = Ti[1]; T[2] = Ti[2]; T[3] = Ti[3];
+        }
+        for (int c = 0; c < 4; c++) a.out_T[(size_t)pair * 4 + c] = T[c];
+        a.out_status[pair] = sh.status;
+    }
+}
+
+}  // namespace
+
+// ================================================================== launchers
+
+int vsk_grad_argmax(vs_ctx* ctx, const VsDevImg& gx, const VsDevImg& gy, int tile, uint16_t* d_lmx, uint16_t* d_lmy)
+{
+    VS_REQUIRE(ctx, tile >= 1 && gx.w == gy.w && gx.h == gy.h, "grad_argmax: bad arguments");
+    VS_REQUIRE(ctx, gx.w <= 65535 && gx.h <= 65535, "grad_argmax: coordinates must fit in u16");
+    int tw = gx.w / tile, th = gy.h / tile;
+    if (tw * th <= 0) return VS_OK;
+    k_grad_argmax<<<vs_cdiv(tw * th, 8), 256, 0, ctx->stream>>>((const float*)gx.data, gx.stride, (const float*)gy.data,
+                                                                gy.stride, tile, tw, th, d_lmx, d_lmy);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+int vsk_sparse_jac(vs_ctx* ctx, const VsDevImg& gx, const VsDevImg& gy, const uint16_t* d_lmx, const uint16_t* d_lmy,
+                   int tw, int th, float* d_jx, float* d_jy)
+{
+    if (tw * th <= 0) return VS_OK;
+    k_sparse_jac<<<vs_cdiv(tw * th, 128), 128, 0, ctx->stream>>>((const float*)gx.data, gx.stride, (const float*)gy.data,
+                                                                 gy.stride, gx.w, gx.h, d_lmx, d_lmy, tw, th, d_jx, d_jy);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+int vsk_sparse_warpdiff(vs_ctx* ctx, const VsDevImg& tmpl, const VsDevImg& key, const uint16_t* d_lm, int tw, int th,
+                        float A, float B, float TX, float TY, uint16_t* d_out)
+{
+    VS_REQUIRE(ctx, tmpl.w == key.w && tmpl.h == key.h, "warpdiff: template/keyframe size mismatch");
+    if (tw * th <= 0) return VS_OK;
+    k_sparse_warpdiff<<<vs_cdiv(tw * th, 128), 128, 0, ctx->stream>>>((const uint8_t*)tmpl.data, tmpl.stride,
+                                                                      (const uint8_t*)key.data, key.stride, key.w, key.h,
+                                                                      d_lm, tw * th, A, B, TX, TY, d_out);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+int vsk_sparse_ica(vs_ctx* ctx, const VsDevImg& tmpl, const VsDevImg& key, const uint16_t* d_selx, int kx,
+                   const uint16_t* d_sely, int ky, const float* d_jx, const float* d_jy,
+                   float A, float B, float TX, float TY, double* d_out4)
+{
+    VS_REQUIRE(ctx, tmpl.w == key.w && tmpl.h == key.h, "ica: template/keyframe size mismatch");
+    k_sparse_ica<<<1, 256, 0, ctx->stream>>>((const uint8_t*)tmpl.data, tmpl.stride, (const uint8_t*)key.data, key.stride,
+                                             key.w, key.h, d_selx, kx, d_sely, ky, d_jx, d_jy, A, B, TX, TY, d_out4);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+int vsk_keyframe_features(vs_ctx* ctx, const VsClipGeom& g, const uint8_t* d_pyr, const int32_t* d_slots, int n_slots,
+                          uint32_t* d_kp, float4* d_jac)
+{
+    if (n_slots <= 0) return VS_OK;
+    VS_REQUIRE(ctx, n_slots <= 65535, "keyframe: too many slots in one call");
+    dim3 grid(vs_cdiv(g.total_tiles, 8), n_slots);
+    k_keyframe_features<<<grid, 256, 0, ctx->stream>>>(g, d_pyr, d_slots, d_kp, d_jac);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
+{
+    if (a.n_pairs <= 0) return VS_OK;
+    size_t smem = (size_t)2 * g.max_tiles * sizeof(uint32_t);
+    VS_REQUIRE(ctx, g.max_tiles <= 65535, "solve: more than 65535 tiles per level");
+    VS_REQUIRE(ctx, smem <= 200 * 1024, "solve: level too large for the shared-memory selection");
+    if (smem > 48 * 1024)
+        VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_pairs<<<a.n_pairs, SOLVE_THREADS, smem, ctx->stream>>>(g, a);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
