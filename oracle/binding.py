@@ -161,7 +161,8 @@ def sparse_jac(gx, gy, lmx, lmy):
     _, th, tw = lmx.shape
     jx = np.zeros((4, th, tw), np.float32)
     jy = np.zeros((4, th, tw), np.float32)
-    load().vo_sparse_jac(_p(gx), _p(gy), w, h, _p(np.ascontiguousarray(lmx)), _p(np.ascontiguousarray(lmy)), tw, th, _p(jx), _p(jy))
+    lmx, lmy = np.ascontiguousarray(lmx, np.uint16), np.ascontiguousarray(lmy, np.uint16)
+    load().vo_sparse_jac(_p(gx), _p(gy), w, h, _p(lmx), _p(lmy), tw, th, _p(jx), _p(jy))
     return jx, jy
 
 
@@ -172,7 +173,8 @@ def sparse_warpdiff(tmpl, key, lm, T):
     _, th, tw = lm.shape
     out = np.zeros((th, tw), np.uint16)
     T = _t(T)
-    load().vo_sparse_warpdiff(_p(tmpl), _p(key), w, h, _p(np.ascontiguousarray(lm)), tw, th, _p(T), _p(out))
+    lm = np.ascontiguousarray(lm, np.uint16)
+    load().vo_sparse_warpdiff(_p(tmpl), _p(key), w, h, _p(lm), tw, th, _p(T), _p(out))
     return out
 
 
@@ -208,29 +210,35 @@ def warp_bgr(src, T, mode=0, border=0, crop=0, fast=False):
     return out
 
 
+# NOTE: every array handed to ctypes is bound to a local first; `_p(_t(x))` alone would let
+# the temporary be collected before the call.
 def tf_inverse(T):
     out = np.zeros(4)
-    load().vo_tf_inverse(_p(_t(T)), _p(out))
+    a = _t(T)
+    load().vo_tf_inverse(_p(a), _p(out))
     return out
 
 
 def tf_compose(T1, T2):
     out = np.zeros(4)
-    load().vo_tf_compose(_p(_t(T1)), _p(_t(T2)), _p(out))
+    a, b = _t(T1), _t(T2)
+    load().vo_tf_compose(_p(a), _p(b), _p(out))
     return out
 
 
 def tf_warp(T, x, y, center=None):
     out = np.zeros(2)
+    a = _t(T)
     if center is None:
-        load().vo_tf_warp(_p(_t(T)), x, y, _p(out))
+        load().vo_tf_warp(_p(a), float(x), float(y), _p(out))
     else:
-        load().vo_tf_warp_center(_p(_t(T)), x, y, center[0], center[1], _p(out))
+        load().vo_tf_warp_center(_p(a), float(x), float(y), float(center[0]), float(center[1]), _p(out))
     return out
 
 
 def tf_max_corner_displacement(T, w, h):
-    return load().vo_tf_max_corner_displacement(_p(_t(T)), float(w), float(h))
+    a = _t(T)
+    return load().vo_tf_max_corner_displacement(_p(a), float(w), float(h))
 
 
 def svd4(H):
@@ -342,7 +350,8 @@ class Smoother:
 
     def update(self, meas):
         out = np.zeros(4)
-        ok = self.lib.vo_smoother_update(self.h, _p(_t(meas)), _p(out))
+        m = _t(meas)
+        ok = self.lib.vo_smoother_update(self.h, _p(m), _p(out))
         return bool(ok), out
 
 

@@ -32,16 +32,29 @@ def run_oracle(ob, frames, params=None):
     return al, res
 
 
-def check_clip_against_oracle(gpu, ob, frames, deep=True):
+def make_params(ob, **kw):
+    """The same VideoAlignerParams for the oracle and for the C ABI."""
+    from video_stabilizer_b200 import _capi as capi
+    po = ob.align_params_default()
+    pg = capi.VsAlignParams()
+    capi.load().vs_align_params_default(pg)
+    for k, v in kw.items():
+        setattr(po, k, v)
+        setattr(pg, k, v)
+    return po, pg
+
+
+def check_clip_against_oracle(gpu, ob, frames, deep=True, **param_overrides):
     from video_stabilizer_b200.clip import Clip, pairs_for_frames
     n, h, w, _ = frames.shape
-    clip = Clip(w, h, n, debug=True, ctx=gpu)
+    po, pg = make_params(ob, **param_overrides)
+    clip = Clip(w, h, n, params=pg, debug=True, ctx=gpu)
     clip.upload(0, frames)
     clip.build_pyramids(0, n)
     pairs, keyframes = pairs_for_frames(0, n)
     clip.build_keyframes(keyframes)
     T, status, iters = clip.align(pairs)
-    al, ref = run_oracle(ob, frames)
+    al, ref = run_oracle(ob, frames, po)
     assert clip.levels == al.levels
     worst = 0.0
     for i in range(1, n):
@@ -97,8 +110,15 @@ def test_failure_paths_match_oracle(gpu, ob):
     from video_stabilizer_b200 import synth
     w, h = 320, 180
     frames, _ = synth.make_clip_numpy(w, h, 6, 5, step=14.0, limit=60.0, ab=0.02)
-    worst, T, status, ref = check_clip_against_oracle(gpu, ob, frames, deep=False)
-    assert not status.all(), "the test clip should contain pairs the reference fails on"
+    # hitting max_iters without converging returns false (alignment.cpp:661-667)
+    worst, T, status, ref = check_clip_against_oracle(gpu, ob, frames, deep=False, max_iters=3)
+    assert not status.all(), "max_iters=3 should make the reference give up on some pairs"
+    # converged displacement above max_displacement returns false (alignment.cpp:670-677)
+    worst, T, status, ref = check_clip_against_oracle(gpu, ob, frames, deep=False, max_displacement=0.75)
+    assert not status.all(), "max_displacement=0.75 should reject some pairs"
+    # other parameter settings keep parity too
+    check_clip_against_oracle(gpu, ob, frames, deep=False, threshold=0.1, smallest_fraction=0.5)
+    check_clip_against_oracle(gpu, ob, frames, deep=False, pyramid_min_width=60, pyramid_min_height=30)
     rng = np.random.default_rng(0)
     noise = rng.integers(0, 256, (4, h, w, 3), dtype=np.uint8)     # unrelated frames
     check_clip_against_oracle(gpu, ob, noise, deep=False)

@@ -125,6 +125,13 @@ def _u8(a):
     return a
 
 
+def _f32(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype != np.float32:
+        raise TypeError("expected a float32 image")
+    return a
+
+
 # ----------------------------------------------------------------- operator wrappers
 def BGR2Gray(bgr: np.ndarray, ctx: Context | None = None) -> np.ndarray:
     """cv::cvtColor(BGR2GRAY) as used at alignment.cpp:212."""
@@ -136,17 +143,21 @@ def BGR2Gray(bgr: np.ndarray, ctx: Context | None = None) -> np.ndarray:
     return out
 
 
+# NOTE: arrays are bound to locals before their address is taken: a descriptor only holds
+# the raw pointer, so a temporary contiguous copy must outlive the call.
 def PyrDown(input: np.ndarray, output: np.ndarray, ctx: Context | None = None) -> bool:
     """imgproc.hpp:16-18.  Caller allocates `output`; its extent defines the work."""
     ctx = ctx or default_context()
-    r = ctx.lib.vs_pyr_down_u8(ctx.handle, C.byref(capi.img_of(_u8(input))), C.byref(capi.img_of(output)), capi.VS_MEM_HOST)
+    src = _u8(input)
+    r = ctx.lib.vs_pyr_down_u8(ctx.handle, C.byref(capi.img_of(src)), C.byref(capi.img_of(output)), capi.VS_MEM_HOST)
     return r == 0
 
 
 def GradXY(input: np.ndarray, output_x: np.ndarray, output_y: np.ndarray, ctx: Context | None = None) -> bool:
     """imgproc.hpp:20-23."""
     ctx = ctx or default_context()
-    r = ctx.lib.vs_grad_xy_u8_f32(ctx.handle, C.byref(capi.img_of(_u8(input))), C.byref(capi.img_of(output_x)),
+    src = _u8(input)
+    r = ctx.lib.vs_grad_xy_u8_f32(ctx.handle, C.byref(capi.img_of(src)), C.byref(capi.img_of(output_x)),
                                   C.byref(capi.img_of(output_y)), capi.VS_MEM_HOST)
     return r == 0
 
@@ -160,6 +171,7 @@ def GradArgMax(grad_x: np.ndarray, grad_y: np.ndarray, ctx: Context | None = Non
     tw, th = w // tile, grad_y.shape[0] // tile
     lmx = np.zeros((2, th, tw), np.uint16)
     lmy = np.zeros((2, th, tw), np.uint16)
+    grad_x, grad_y = _f32(grad_x), _f32(grad_y)
     r = ctx.lib.vs_grad_argmax_f32_u16(ctx.handle, C.byref(capi.img_of(grad_x)), C.byref(capi.img_of(grad_y)), tile,
                                        capi.ptr(lmx), capi.ptr(lmy), capi.VS_MEM_HOST)
     return r == 0, tile, lmx, lmy
@@ -171,9 +183,10 @@ def SparseJacobian(grad_x, grad_y, local_max_x, local_max_y, ctx: Context | None
     _, th, tw = local_max_x.shape
     ox = np.zeros((4, th, tw), np.float32)
     oy = np.zeros((4, th, tw), np.float32)
+    grad_x, grad_y = _f32(grad_x), _f32(grad_y)
+    lx, ly = np.ascontiguousarray(local_max_x, np.uint16), np.ascontiguousarray(local_max_y, np.uint16)
     r = ctx.lib.vs_sparse_jac_f32(ctx.handle, C.byref(capi.img_of(grad_x)), C.byref(capi.img_of(grad_y)),
-                                  capi.ptr(np.ascontiguousarray(local_max_x)), capi.ptr(np.ascontiguousarray(local_max_y)),
-                                  tw, th, capi.ptr(ox), capi.ptr(oy), capi.VS_MEM_HOST)
+                                  capi.ptr(lx), capi.ptr(ly), tw, th, capi.ptr(ox), capi.ptr(oy), capi.VS_MEM_HOST)
     return r == 0, ox, oy
 
 
@@ -184,10 +197,9 @@ def SparseWarpDiff(input_template, input_keyframe, local_max, transform: Similar
     h, w = input_template.shape
     A, B, TX, TY = _ul_params_half(transform, w, h)
     out = np.zeros((th, tw), np.uint16)
-    r = ctx.lib.vs_sparse_warpdiff_u8_u16(ctx.handle, C.byref(capi.img_of(_u8(input_template))),
-                                          C.byref(capi.img_of(_u8(input_keyframe))),
-                                          capi.ptr(np.ascontiguousarray(local_max)), tw, th, A, B, TX, TY,
-                                          capi.ptr(out), capi.VS_MEM_HOST)
+    tm, kf, lm = _u8(input_template), _u8(input_keyframe), np.ascontiguousarray(local_max, np.uint16)
+    r = ctx.lib.vs_sparse_warpdiff_u8_u16(ctx.handle, C.byref(capi.img_of(tm)), C.byref(capi.img_of(kf)),
+                                          capi.ptr(lm), tw, th, A, B, TX, TY, capi.ptr(out), capi.VS_MEM_HOST)
     return r == 0, out
 
 
@@ -199,9 +211,10 @@ def SparseICA(input_template, input_keyframe, selected_pixels_x, selected_pixels
     h, w = input_template.shape
     A, B, TX, TY = _ul_params_half(transform, w, h)
     out = np.zeros(4, np.float64)
-    sx, sy = np.ascontiguousarray(selected_pixels_x), np.ascontiguousarray(selected_pixels_y)
-    jx, jy = np.ascontiguousarray(selected_jacobians_x), np.ascontiguousarray(selected_jacobians_y)
-    r = ctx.lib.vs_sparse_ica_f64(ctx.handle, C.byref(capi.img_of(_u8(input_template))), C.byref(capi.img_of(_u8(input_keyframe))),
+    sx, sy = np.ascontiguousarray(selected_pixels_x, np.uint16), np.ascontiguousarray(selected_pixels_y, np.uint16)
+    jx, jy = np.ascontiguousarray(selected_jacobians_x, np.float32), np.ascontiguousarray(selected_jacobians_y, np.float32)
+    tm, kf = _u8(input_template), _u8(input_keyframe)
+    r = ctx.lib.vs_sparse_ica_f64(ctx.handle, C.byref(capi.img_of(tm)), C.byref(capi.img_of(kf)),
                                   capi.ptr(sx), sx.shape[1], capi.ptr(sy), sy.shape[1], capi.ptr(jx), capi.ptr(jy),
                                   A, B, TX, TY, capi.ptr(out), capi.VS_MEM_HOST)
     return r == 0, out
@@ -214,7 +227,8 @@ def ImageWarp(input: np.ndarray, transform: SimilarityTransform, output: np.ndar
     cx, cy = (w - 1) * 0.5, (h - 1) * 0.5
     p = np.array([transform.A, transform.B, transform.TX - transform.A * cx + transform.B * cy,
                   transform.TY - transform.B * cx - transform.A * cy], dtype=np.float64).astype(np.float32)
-    r = ctx.lib.vs_image_warp_u8_f32(ctx.handle, C.byref(capi.img_of(_u8(input))), capi.ptr(p),
+    src = _u8(input)
+    r = ctx.lib.vs_image_warp_u8_f32(ctx.handle, C.byref(capi.img_of(src)), capi.ptr(p),
                                      C.byref(capi.img_of(output)), capi.VS_MEM_HOST)
     return r == 0
 
