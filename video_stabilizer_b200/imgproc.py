@@ -118,18 +118,24 @@ def _ul_params_half(t: SimilarityTransform, w: int, h: int):
             np.float32(t.TX - t.A * hw + t.B * hh), np.float32(t.TY - t.B * hw - t.A * hh))
 
 
-def _u8(a):
-    a = np.ascontiguousarray(a)
-    if a.dtype != np.uint8:
-        raise TypeError("expected a uint8 image")
+def _dense_rows(a, dtype):
+    """Row-strided views are passed through as they are (the ABI takes a row stride); only
+    arrays whose rows are not dense get copied."""
+    a = np.asarray(a)
+    if a.dtype != dtype:
+        raise TypeError("expected a %s image" % np.dtype(dtype).name)
+    inner = a.strides[1:] == tuple(int(np.prod(a.shape[i + 1:])) * a.itemsize for i in range(1, a.ndim))
+    if not inner or a.strides[0] < 0 or a.strides[0] % a.itemsize:
+        a = np.ascontiguousarray(a)
     return a
+
+
+def _u8(a):
+    return _dense_rows(a, np.uint8)
 
 
 def _f32(a):
-    a = np.ascontiguousarray(a)
-    if a.dtype != np.float32:
-        raise TypeError("expected a float32 image")
-    return a
+    return _dense_rows(a, np.float32)
 
 
 # ----------------------------------------------------------------- operator wrappers
