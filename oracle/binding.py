@@ -380,3 +380,187 @@ class Stabilizer:
         if has:
             frame = out.ravel()[: oh.value * ow.value * 3].reshape(oh.value, ow.value, 3).copy()
         return frame, bool(ok.value), meas, corr
+
+
+# ===================================================================== oracle/_ref
+# The reference's OWN alignment.cpp / imgproc.cpp / smoother.cpp / stabilizer.cpp compiled
+# unmodified against shim headers (oracle/Makefile `ref`).  Built here when /root/reference
+# is present; on the GPU box only the prebuilt oracle/_ref/*.so exist.
+REFERENCE_DIR = "/root/reference"
+_ref_libs = {}
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libvs_ref.so")) or os.path.isdir(REFERENCE_DIR)
+
+
+def load_ref(fast: bool = False):
+    name = "libvs_ref_fast.so" if fast else "libvs_ref.so"
+    if name in _ref_libs:
+        return _ref_libs[name]
+    path = os.path.join(_HERE, "_ref", name)
+    if os.path.isdir(REFERENCE_DIR):
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)   # no-op when up to date
+    if not os.path.exists(path):
+        raise RuntimeError("oracle/_ref is not built and %s is absent" % REFERENCE_DIR)
+    lib = C.CDLL(path)
+    P, I, D = C.c_void_p, C.c_int, C.c_double
+    PI = C.POINTER(I)
+    lib.vr_tf_inverse.argtypes = [P, P]
+    lib.vr_tf_compose.argtypes = [P, P, P]
+    lib.vr_tf_warp.argtypes = [P, D, D, P]
+    lib.vr_tf_warp_center.argtypes = [P, D, D, D, D, P]
+    lib.vr_tf_max_corner_displacement.restype = D
+    lib.vr_tf_max_corner_displacement.argtypes = [P, D, D]
+    lib.vr_aligner_create.restype = P
+    lib.vr_aligner_destroy.argtypes = [P]
+    lib.vr_aligner_align.argtypes = [P, P, I, I, C.POINTER(AlignParams), P]
+    lib.vr_aligner_levels.argtypes = [P]
+    lib.vr_aligner_curr_index.argtypes = [P]
+    lib.vr_aligner_tile_size.argtypes = [P, I]
+    for f in ("vr_aligner_pyramid", "vr_aligner_keypoints", "vr_aligner_jacobians", "vr_aligner_warpdiff",
+              "vr_aligner_selected_pixels"):
+        getattr(lib, f).restype = P
+    lib.vr_aligner_pyramid.argtypes = [P, I, I, PI, PI]
+    lib.vr_aligner_keypoints.argtypes = [P, I, I, PI, PI]
+    lib.vr_aligner_jacobians.argtypes = [P, I, I]
+    lib.vr_aligner_warpdiff.argtypes = [P, I, I]
+    lib.vr_aligner_selected_pixels.argtypes = [P, I, I, PI]
+    lib.vr_smoother_create.restype = P
+    lib.vr_smoother_create.argtypes = [I, I, D]
+    lib.vr_smoother_destroy.argtypes = [P]
+    lib.vr_smoother_update.argtypes = [P, P, P]
+    lib.vr_stabilizer_create.restype = P
+    lib.vr_stabilizer_create.argtypes = [C.POINTER(StabParams)]
+    lib.vr_stabilizer_destroy.argtypes = [P]
+    lib.vr_stabilizer_process.argtypes = [P, P, I, I, P, PI, PI, P]
+    _ref_libs[name] = lib
+    return lib
+
+
+def _view(ptr, shape, dtype):
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.zeros(shape, dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape).copy()
+
+
+class RefAligner:
+    """The reference's own VideoAligner (alignment.cpp), through oracle/_ref."""
+
+    def __init__(self, params: AlignParams | None = None, fast: bool = False):
+        self.lib = load_ref(fast)
+        self.h = C.c_void_p(self.lib.vr_aligner_create())
+        self.params = params or align_params_default()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.vr_aligner_destroy(self.h)
+            self.h = None
+
+    def align(self, bgr):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        h, w, _ = bgr.shape
+        T = np.zeros(4)
+        ok = self.lib.vr_aligner_align(self.h, _p(bgr), w, h, C.byref(self.params), _p(T))
+        return bool(ok), T
+
+    @property
+    def levels(self):
+        return self.lib.vr_aligner_levels(self.h)
+
+    @property
+    def curr(self):
+        return self.lib.vr_aligner_curr_index(self.h)
+
+    def tile_size(self, level):
+        return self.lib.vr_aligner_tile_size(self.h, level)
+
+    def pyramid(self, slot, level):
+        w, h = C.c_int(), C.c_int()
+        p = self.lib.vr_aligner_pyramid(self.h, slot, level, C.byref(w), C.byref(h))
+        return _view(p, (h.value, w.value), np.uint8)
+
+    def keypoints(self, level, axis):
+        tw, th = C.c_int(), C.c_int()
+        p = self.lib.vr_aligner_keypoints(self.h, level, axis, C.byref(tw), C.byref(th))
+        return _view(p, (2, th.value, tw.value), np.uint16)
+
+    def jacobians(self, level, axis):
+        kp = self.keypoints(level, axis)
+        return _view(self.lib.vr_aligner_jacobians(self.h, level, axis), (4,) + kp.shape[1:], np.float32)
+
+    def warpdiff(self, level, axis):
+        kp = self.keypoints(level, axis)
+        return _view(self.lib.vr_aligner_warpdiff(self.h, level, axis), kp.shape[1:], np.uint16)
+
+    def selected_pixels(self, level, axis):
+        k = C.c_int()
+        p = self.lib.vr_aligner_selected_pixels(self.h, level, axis, C.byref(k))
+        return _view(p, (2, k.value), np.uint16)
+
+
+class RefSmoother:
+    def __init__(self, lag_behind, lag_ahead, lam):
+        self.lib = load_ref()
+        self.h = C.c_void_p(self.lib.vr_smoother_create(lag_behind, lag_ahead, lam))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.vr_smoother_destroy(self.h)
+            self.h = None
+
+    def update(self, meas):
+        out = np.zeros(4)
+        m = _t(meas)
+        ok = self.lib.vr_smoother_update(self.h, _p(m), _p(out))
+        return bool(ok), out
+
+
+class RefStabilizer:
+    """The reference's own VideoStabilizer (stabilizer.cpp), through oracle/_ref."""
+
+    def __init__(self, params: StabParams | None = None, fast: bool = False):
+        self.lib = load_ref(fast)
+        self.params = params or stab_params_default()
+        self.h = C.c_void_p(self.lib.vr_stabilizer_create(C.byref(self.params)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.vr_stabilizer_destroy(self.h)
+            self.h = None
+
+    def process(self, bgr):
+        """Returns (frame or None, accum[4])."""
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        h, w, _ = bgr.shape
+        out = np.empty((h, w, 3), np.uint8)
+        ow, oh = C.c_int(), C.c_int()
+        accum = np.zeros(4)
+        has = self.lib.vr_stabilizer_process(self.h, _p(bgr), w, h, _p(out), C.byref(ow), C.byref(oh), _p(accum))
+        frame = None
+        if has:
+            frame = out.ravel()[: oh.value * ow.value * 3].reshape(oh.value, ow.value, 3).copy()
+        return frame, accum
+
+
+def ref_tf(name, *args):
+    """vr_tf_* through the reference's SimilarityTransform: name in inverse/compose/max_corner_displacement."""
+    lib = load_ref()
+    if name == "inverse":
+        out, a = np.zeros(4), _t(args[0])
+        lib.vr_tf_inverse(_p(a), _p(out))
+        return out
+    if name == "compose":
+        out, a, b = np.zeros(4), _t(args[0]), _t(args[1])
+        lib.vr_tf_compose(_p(a), _p(b), _p(out))
+        return out
+    if name == "max_corner_displacement":
+        a = _t(args[0])
+        return lib.vr_tf_max_corner_displacement(_p(a), float(args[1]), float(args[2]))
+    if name == "warp_center":
+        out, a = np.zeros(2), _t(args[0])
+        lib.vr_tf_warp_center(_p(a), float(args[1]), float(args[2]), float(args[3]), float(args[4]), _p(out))
+        return out
+    raise ValueError(name)

@@ -1,0 +1,3 @@
+// stands in for the generated Halide header of the same name
+#pragma once
+#include "ref_pipelines.h"

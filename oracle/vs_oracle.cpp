@@ -216,31 +216,36 @@ void vo_sparse_jac(const float* gx, const float* gy, int w, int h,
 
 // imgproc.cpp:80-106 + generators.cpp:646-700 — |Lanczos2(keyframe, W(p)) - template(p)|,
 // clamped to [0,65535] and truncated to u16, for every tile keypoint.
-void vo_sparse_warpdiff(const uint8_t* tmpl, const uint8_t* key, int w, int h,
-                        const uint16_t* lm, int tw, int th, const double T[4],
-                        uint16_t* out)
+void vo_k_sparse_warpdiff(const uint8_t* tmpl, const uint8_t* key, int w, int h,
+                          const uint16_t* lm, int tw, int th, float A, float B, float TX, float TY,
+                          uint16_t* out)
 {
-    float P[4];
-    ul_params_half(T, w, h, P);
     size_t plane = (size_t)tw * th;
     for (size_t t = 0; t < plane; t++) {
         int px = std::min<int>(lm[t], w - 1);
         int py = std::min<int>(lm[plane + t], h - 1);
-        float s = lanczos_sample(key, w, h, (float)px, (float)py, P[0], P[1], P[2], P[3]);
+        float s = lanczos_sample(key, w, h, (float)px, (float)py, A, B, TX, TY);
         float d = std::fabs(s - (float)tmpl[(size_t)py * w + px]);
         d = std::max(std::min(d, 65535.0f), 0.0f);
         out[t] = (uint16_t)d;
     }
 }
 
-// imgproc.cpp:46-78 + generators.cpp:429-596 — b = 0.5 * (sum_X Jx r + sum_Y Jy r);
-// J*r is an f32 product, accumulated serially in f64 per channel.
-void vo_sparse_ica(const uint8_t* tmpl, const uint8_t* key, int w, int h,
-                   const uint16_t* selx, int kx, const uint16_t* sely, int ky,
-                   const float* jx, const float* jy, const double T[4], double out[4])
+void vo_sparse_warpdiff(const uint8_t* tmpl, const uint8_t* key, int w, int h,
+                        const uint16_t* lm, int tw, int th, const double T[4],
+                        uint16_t* out)
 {
     float P[4];
     ul_params_half(T, w, h, P);
+    vo_k_sparse_warpdiff(tmpl, key, w, h, lm, tw, th, P[0], P[1], P[2], P[3], out);
+}
+
+// imgproc.cpp:46-78 + generators.cpp:429-596 — b = 0.5 * (sum_X Jx r + sum_Y Jy r);
+// J*r is an f32 product, accumulated serially in f64 per channel.
+void vo_k_sparse_ica(const uint8_t* tmpl, const uint8_t* key, int w, int h,
+                     const uint16_t* selx, int kx, const uint16_t* sely, int ky,
+                     const float* jx, const float* jy, float A, float B, float TX, float TY, double out[4])
+{
     double rx[4] = {0, 0, 0, 0}, ry[4] = {0, 0, 0, 0};
     for (int axis = 0; axis < 2; axis++) {
         const uint16_t* sel = axis == 0 ? selx : sely;
@@ -249,7 +254,7 @@ void vo_sparse_ica(const uint8_t* tmpl, const uint8_t* key, int w, int h,
         double* acc = axis == 0 ? rx : ry;
         for (int i = 0; i < k; i++) {
             int px = sel[i], py = sel[(size_t)k + i];
-            float warped = lanczos_sample(key, w, h, (float)px, (float)py, P[0], P[1], P[2], P[3]);
+            float warped = lanczos_sample(key, w, h, (float)px, (float)py, A, B, TX, TY);
             int tx = std::min(px, w - 1), ty = std::min(py, h - 1);
             float residual = (float)tmpl[(size_t)ty * w + tx] - warped;
             for (int c = 0; c < 4; c++) {
@@ -261,15 +266,20 @@ void vo_sparse_ica(const uint8_t* tmpl, const uint8_t* key, int w, int h,
     for (int c = 0; c < 4; c++) out[c] = (rx[c] + ry[c]) * (double)0.5f;
 }
 
+void vo_sparse_ica(const uint8_t* tmpl, const uint8_t* key, int w, int h,
+                   const uint16_t* selx, int kx, const uint16_t* sely, int ky,
+                   const float* jx, const float* jy, const double T[4], double out[4])
+{
+    float P[4];
+    ul_params_half(T, w, h, P);
+    vo_k_sparse_ica(tmpl, key, w, h, selx, kx, sely, ky, jx, jy, P[0], P[1], P[2], P[3], out);
+}
+
 // imgproc.cpp:116-133 + generators.cpp:126-164 — pull-mapped bilinear, repeat-edge.
 // Halide's float lerp(a,b,t) is a*(1-t) + b*t.
-void vo_image_warp(const uint8_t* in, int iw, int ih, const double T[4],
-                   float* out, int ow, int oh)
+void vo_k_image_warp(const uint8_t* in, int iw, int ih, float A, float B, float TX, float TY,
+                     float* out, int ow, int oh)
 {
-    double cx = (iw - 1) * 0.5, cy = (ih - 1) * 0.5;
-    float A = (float)T[0], B = (float)T[1];
-    float TX = (float)(T[2] - T[0] * cx + T[1] * cy);
-    float TY = (float)(T[3] - T[1] * cx - T[0] * cy);
     for (int y = 0; y < oh; y++) {
         for (int x = 0; x < ow; x++) {
             float Wx = (1.0f + A) * (float)x - B * (float)y + TX;
@@ -285,6 +295,16 @@ void vo_image_warp(const uint8_t* in, int iw, int ih, const double T[4],
             out[(size_t)y * ow + x] = top * (1.0f - wy) + bot * wy;
         }
     }
+}
+
+void vo_image_warp(const uint8_t* in, int iw, int ih, const double T[4],
+                   float* out, int ow, int oh)
+{
+    double cx = (iw - 1) * 0.5, cy = (ih - 1) * 0.5;
+    float A = (float)T[0], B = (float)T[1];
+    float TX = (float)(T[2] - T[0] * cx + T[1] * cy);
+    float TY = (float)(T[3] - T[1] * cx - T[0] * cy);
+    vo_k_image_warp(in, iw, ih, A, B, TX, TY, out, ow, oh);
 }
 
 //------------------------------------------------------------------------------

@@ -49,6 +49,17 @@ void vo_sparse_ica(const uint8_t* tmpl, const uint8_t* key, int w, int h,
 void vo_image_warp(const uint8_t* in, int iw, int ih, const double T[4],
                    float* out, int ow, int oh);
 
+/* kernel-level entry points: the f32 upper-left-origin parameters exactly as the Halide
+ * pipelines receive them (used by oracle/ref_shim to stand in for the AOT pipelines) */
+void vo_k_sparse_warpdiff(const uint8_t* tmpl, const uint8_t* key, int w, int h,
+                          const uint16_t* lm, int tw, int th, float A, float B, float TX, float TY,
+                          uint16_t* out);
+void vo_k_sparse_ica(const uint8_t* tmpl, const uint8_t* key, int w, int h,
+                     const uint16_t* selx, int kx, const uint16_t* sely, int ky,
+                     const float* jx, const float* jy, float A, float B, float TX, float TY, double out[4]);
+void vo_k_image_warp(const uint8_t* in, int iw, int ih, float A, float B, float TX, float TY,
+                     float* out, int ow, int oh);
+
 /* BGR warp, same convention as warpBySimilarityTransform (imgproc.cpp:446-484):
  * dst(M p) = src(p) with M built from the centre-based transform.
  * mode: 0 = OpenCV-exact fixed-point bilinear, 1 = float bilinear, 2 = Lanczos-2
