@@ -73,6 +73,16 @@ int vs_ctx_synchronize(vs_ctx* ctx);
 const char* vs_last_error(const vs_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
 int64_t vs_ctx_launch_count(const vs_ctx* ctx);
+/* Per-kernel device timing: when enabled every launch of this context is bracketed by a
+ * CUDA event pair on the launching stream.  read() synchronizes the stream and returns the
+ * launches and summed milliseconds of one kernel since the last reset. */
+enum { VS_KERNEL_BGR2GRAY = 0, VS_KERNEL_PYR_DOWN, VS_KERNEL_GRAD_XY, VS_KERNEL_IMAGE_WARP, VS_KERNEL_BGR_WARP,
+       VS_KERNEL_GRAD_ARGMAX, VS_KERNEL_SPARSE_JAC, VS_KERNEL_WARPDIFF, VS_KERNEL_ICA, VS_KERNEL_KEYFRAME,
+       VS_KERNEL_SOLVE, VS_KERNEL_INGEST, VS_KERNEL_COUNT };
+int vs_ctx_profile_enable(vs_ctx* ctx, int enable);
+int vs_ctx_profile_reset(vs_ctx* ctx);
+int vs_ctx_profile_read(vs_ctx* ctx, int kernel, int64_t* launches, double* total_ms);
+const char* vs_kernel_name(int kernel);
 /* device memory helpers for callers without their own allocator (C++ host layer) */
 int vs_dev_alloc(vs_ctx* ctx, size_t bytes, void** out);
 int vs_dev_free(vs_ctx* ctx, void* p);
@@ -163,6 +173,11 @@ enum { VS_CLIP_DEBUG_TAPS = 1 };  /* keep per-pair warpdiff / selection for insp
 int vs_clip_create(vs_ctx*, int width, int height, int capacity, int max_pairs,
                    const vs_align_params* params, int flags, vs_clip** out);
 int vs_clip_destroy(vs_clip*);
+/* Replace the solver parameters (threshold, smallest_fraction, max_iters, max_displacement)
+ * for later vs_clip_align calls: AlignNextFrame takes its params per call (alignment.hpp:55-58).
+ * pyramid_min_* only act when the pyramid is laid out, i.e. at creation, as upstream
+ * (alignment.cpp:155-169). */
+int vs_clip_set_params(vs_clip*, const vs_align_params* params);
 int vs_clip_levels(const vs_clip*);
 int vs_clip_level_info(const vs_clip*, int level, int* w, int* h, int* tile, int* tw, int* th);
 

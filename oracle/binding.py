@@ -372,7 +372,8 @@ class Stabilizer:
         """Returns (frame or None, meas_ok, meas[4], correction[4])."""
         bgr = np.ascontiguousarray(bgr, np.uint8)
         h, w, _ = bgr.shape
-        out = np.empty((h, w, 3), np.uint8)
+        self._max_bytes = max(getattr(self, "_max_bytes", 0), h * w * 3)   # the delayed frame may be larger
+        out = np.empty(self._max_bytes, np.uint8)
         ow, oh, ok = C.c_int(), C.c_int(), C.c_int()
         meas, corr = np.zeros(4), np.zeros(4)
         has = self.lib.vo_stabilizer_process(self.h, _p(bgr), w, h, _p(out), C.byref(ow), C.byref(oh), C.byref(ok), _p(meas), _p(corr))
@@ -535,7 +536,8 @@ class RefStabilizer:
         """Returns (frame or None, accum[4])."""
         bgr = np.ascontiguousarray(bgr, np.uint8)
         h, w, _ = bgr.shape
-        out = np.empty((h, w, 3), np.uint8)
+        self._max_bytes = max(getattr(self, "_max_bytes", 0), h * w * 3)
+        out = np.empty(self._max_bytes, np.uint8)
         ow, oh = C.c_int(), C.c_int()
         accum = np.zeros(4)
         has = self.lib.vr_stabilizer_process(self.h, _p(bgr), w, h, _p(out), C.byref(ow), C.byref(oh), _p(accum))

@@ -947,6 +947,7 @@ struct vo_stabilizer {
     int frame_index = 0;
     std::deque<std::array<double, 4>> meas;
     std::deque<std::vector<uint8_t>> frames;
+    std::deque<std::pair<int, int>> frame_sizes;   // each buffered frame keeps its own size (stabilizer.cpp:15,91-99)
     double accum[4] = {0, 0, 0, 0};
 };
 
@@ -972,6 +973,7 @@ int vo_stabilizer_process(vo_stabilizer* s, const uint8_t* bgr, int w, int h,
     const vo_stab_params& P = s->params;
     ++s->frame_index;
     s->frames.emplace_back(bgr, bgr + (size_t)w * h * 3);
+    s->frame_sizes.emplace_back(w, h);
 
     double cur[4];
     int success = vo_aligner_align(s->aligner, bgr, w, h, &P.aligner, cur);
@@ -1014,13 +1016,15 @@ int vo_stabilizer_process(vo_stabilizer* s, const uint8_t* bgr, int w, int h,
     if (s->frames.empty()) return 0;
     std::vector<uint8_t> frame = std::move(s->frames.front());
     s->frames.pop_front();
+    const int fw = s->frame_sizes.front().first, fh = s->frame_sizes.front().second;
+    s->frame_sizes.pop_front();
     double corr[4];
     vo_tf_inverse(na, corr);
     if (correction_out) for (int c = 0; c < 4; c++) correction_out[c] = corr[c];
     int crop = P.crop_pixels > 0 ? P.crop_pixels : 0;
-    vo_warp_bgr(frame.data(), w, h, corr, out, 0, 0, crop);
-    *out_w = w - 2 * crop;
-    *out_h = h - 2 * crop;
+    vo_warp_bgr(frame.data(), fw, fh, corr, out, 0, 0, crop);   // warped at the buffered frame's own size
+    *out_w = fw - 2 * crop;
+    *out_h = fh - 2 * crop;
     return 1;
 }
 

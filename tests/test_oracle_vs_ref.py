@@ -118,3 +118,17 @@ def test_stabilizer_equals_reference_sources(ref, crop, enable):
             assert np.array_equal(fa, fr), ("stabilized frame", i)
             assert np.array_equal(corr, ref.tf_inverse(accum)), ("correction", i)
     assert produced == 26 - 10
+
+
+def test_stabilizer_size_change_equals_reference_sources(ref):
+    """Buffered frames keep their own size when the input size changes mid-stream."""
+    p = ref.stab_params_default()
+    p.lag, p.smoother_memory, p.crop_pixels = 4, 2, 8
+    seq = list(_clip(320, 180, 8, 1)) + list(_clip(256, 144, 8, 2))
+    a, r = ref.Stabilizer(p), ref.RefStabilizer(p)
+    for i, f in enumerate(seq):
+        fa = a.process(f)[0]
+        fr = r.process(f)[0]
+        assert (fa is None) == (fr is None), i
+        if fa is not None:
+            assert fa.shape == fr.shape and np.array_equal(fa, fr), i

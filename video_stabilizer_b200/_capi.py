@@ -17,6 +17,7 @@ VS_MEM_HOST, VS_MEM_DEVICE = 0, 1
 VS_WARP_CV_EXACT_BILINEAR, VS_WARP_FLOAT_BILINEAR, VS_WARP_LANCZOS2 = 0, 1, 2
 VS_BORDER_CONSTANT0, VS_BORDER_REPEAT_EDGE = 0, 1
 VS_CLIP_DEBUG_TAPS = 1
+VS_KERNEL_COUNT = 12
 
 
 class VsImg(C.Structure):
@@ -47,6 +48,10 @@ SYMBOLS = {
     "vs_ctx_synchronize": (C.c_int, [_P]),
     "vs_last_error": (C.c_char_p, [_P]),
     "vs_ctx_launch_count": (C.c_int64, [_P]),
+    "vs_ctx_profile_enable": (C.c_int, [_P, C.c_int]),
+    "vs_ctx_profile_reset": (C.c_int, [_P]),
+    "vs_ctx_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "vs_kernel_name": (C.c_char_p, [C.c_int]),
     "vs_dev_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "vs_dev_free": (C.c_int, [_P, _P]),
     "vs_host_alloc_pinned": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
@@ -68,6 +73,7 @@ SYMBOLS = {
     "vs_align_params_default": (None, [C.POINTER(VsAlignParams)]),
     "vs_clip_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(VsAlignParams), C.c_int, C.POINTER(_P)]),
     "vs_clip_destroy": (C.c_int, [_P]),
+    "vs_clip_set_params": (C.c_int, [_P, C.POINTER(VsAlignParams)]),
     "vs_clip_levels": (C.c_int, [_P]),
     "vs_clip_level_info": (C.c_int, [_P, C.c_int] + [C.POINTER(C.c_int)] * 5),
     "vs_clip_upload": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64, C.c_int64, C.c_int]),

@@ -68,13 +68,14 @@ def build_host(force: bool = False) -> str | None:
     if not srcs:
         return None
     deps = srcs + glob.glob(os.path.join(host_dir, "*.hpp")) + glob.glob(os.path.join(host_dir, "*.h")) + \
-        glob.glob(os.path.join(host_dir, "compat", "*")) + glob.glob(os.path.join(INCLUDE, "*.h")) + \
+        glob.glob(os.path.join(INCLUDE, "compat", "*.h")) + glob.glob(os.path.join(INCLUDE, "compat", "*", "*")) + \
+        glob.glob(os.path.join(INCLUDE, "*.h")) + \
         [LIB_CUDA, os.path.abspath(__file__)]
     if not force and _newer(LIB_HOST, deps):
         return LIB_HOST
     cxx = shutil.which("g++") or "g++"
     _run([cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-pthread",
-          "-I", INCLUDE, "-I", host_dir, "-I", os.path.join(host_dir, "compat"),
+          "-I", INCLUDE, "-I", host_dir, "-idirafter", os.path.join(INCLUDE, "compat"),
           "-o", LIB_HOST] + srcs + ["-L", PKG_DIR, "-lvstab", "-Wl,-rpath,$ORIGIN"])
     return LIB_HOST
 

@@ -1,0 +1,146 @@
+// clip_stabilizer.cpp — see clip_stabilizer.hpp.
+#include "clip_stabilizer.hpp"
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+
+#include "aligner_impl.hpp"
+
+namespace vstab {
+
+ClipStabilizer::ClipStabilizer(int device, int width, int height, int chunk_frames, const VideoStabilizerParams& params)
+    : m_w(width), m_h(height), m_chunk(chunk_frames), m_capacity(chunk_frames + std::max(0, params.lag) + 1),
+      m_crop(std::max(0, params.crop_pixels)), m_params(params), m_trajectory(params)
+{
+    if (width <= 0 || height <= 0 || chunk_frames <= 0) throw std::runtime_error("ClipStabilizer: bad geometry");
+    if (2 * m_crop >= width || 2 * m_crop >= height) throw std::runtime_error("ClipStabilizer: crop_pixels removes the whole frame");
+    if (params.aligner.phase_correlate) throw std::runtime_error("ClipStabilizer: phase_correlate initialisation is not implemented on the GPU path");
+    if (vs_ctx_create(device, &m_ctx) != VS_OK)
+        throw std::runtime_error(std::string("ClipStabilizer: cannot create a GPU context: ") + vs_last_error(nullptr));
+    vs_align_params cp;
+    to_c_params(params.aligner, &cp);
+    if (vs_clip_create(m_ctx, width, height, m_capacity, chunk_frames, &cp, 0, &m_clip) != VS_OK) {
+        std::string msg = std::string("ClipStabilizer: ") + vs_last_error(m_ctx);
+        vs_ctx_destroy(m_ctx);
+        m_ctx = nullptr;
+        throw std::runtime_error(msg);
+    }
+    m_pairs.reserve(chunk_frames); m_T.resize((size_t)chunk_frames * 4); m_status.resize(chunk_frames); m_slots.reserve(chunk_frames);
+}
+
+ClipStabilizer::~ClipStabilizer()
+{
+    if (m_clip) vs_clip_destroy(m_clip);
+    if (m_ctx) vs_ctx_destroy(m_ctx);
+}
+
+void ClipStabilizer::reset()
+{
+    m_fed = m_emitted = 0;
+    m_trajectory = StabilizerTrajectory(m_params);
+    m_meas.clear(); m_ok.clear(); m_corr.clear();
+}
+
+void ClipStabilizer::check(int rc, const char* what) const
+{
+    if (rc != VS_OK) throw std::runtime_error(std::string("ClipStabilizer: ") + what + ": " + vs_last_error(m_ctx));
+}
+
+// frames [first_frame, first_frame+n) occupy at most two contiguous slot runs of the ring
+template <typename F>
+void ClipStabilizer::for_slot_runs(long first_frame, int n, F f) const
+{
+    int done = 0;
+    while (done < n) {
+        const int slot = (int)((first_frame + done) % m_capacity);
+        const int run = std::min(n - done, m_capacity - slot);
+        f(slot, done, run);
+        done += run;
+    }
+}
+
+void ClipStabilizer::upload_only(long first_frame, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, int mem)
+{
+    if (n < 0 || n > m_capacity) throw std::runtime_error("ClipStabilizer: more frames than ring slots");
+    for_slot_runs(first_frame, n, [&](int slot, int done, int run) {
+        check(vs_clip_upload(m_clip, slot, run, frames + (size_t)frame_stride * done, row_stride, frame_stride, mem), "upload");
+    });
+}
+
+int ClipStabilizer::feed(const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, int mem,
+                         uint8_t* out, int64_t out_frame_stride, int out_mem)
+{
+    if (n < 0 || n > m_chunk) throw std::runtime_error("ClipStabilizer: feed() takes at most chunk_frames frames");
+    upload_only(m_fed, frames, n, row_stride, frame_stride, mem);
+    return process(n, out, out_frame_stride, out_mem);
+}
+
+int ClipStabilizer::feed_resident(int n, uint8_t* out, int64_t out_frame_stride, int out_mem)
+{
+    if (n < 0 || n > m_chunk) throw std::runtime_error("ClipStabilizer: feed_resident() takes at most chunk_frames frames");
+    return process(n, out, out_frame_stride, out_mem);
+}
+
+int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int out_mem)
+{
+    m_meas.assign(n, SimilarityTransform());
+    m_ok.assign(n, 0);
+    m_corr.clear();
+    if (n == 0) return 0;
+    const long f0 = m_fed;
+
+    // ---- pyramids of the new frames, keyframe features of the odd ones
+    for_slot_runs(f0, n, [&](int slot, int, int run) { check(vs_clip_build_pyramids(m_clip, slot, run), "pyramids"); });
+    m_slots.clear();
+    for (long f = f0; f < f0 + n; f++)
+        if (f & 1) m_slots.push_back((int32_t)(f % m_capacity));
+    if (!m_slots.empty()) check(vs_clip_build_keyframes(m_clip, m_slots.data(), (int)m_slots.size()), "keyframes");
+
+    // ---- one solver launch over every pair (f-1 -> f); roles as reference alignment.cpp:357,396-397,690-693
+    m_pairs.clear();
+    for (long f = std::max(f0, 1L); f < f0 + n; f++) {
+        vs_pair p;
+        const int cur = (int)(f % m_capacity), prev = (int)((f - 1) % m_capacity);
+        if (f & 1) { p.template_slot = prev; p.keyframe_slot = cur; p.invert = 0; }
+        else       { p.template_slot = cur; p.keyframe_slot = prev; p.invert = 1; }
+        m_pairs.push_back(p);
+    }
+    const int np = (int)m_pairs.size();
+    if (np) check(vs_clip_align(m_clip, m_pairs.data(), np, m_T.data(), m_status.data(), nullptr, VS_MEM_HOST), "align");
+
+    // ---- sequential host trajectory
+    std::vector<int32_t> due_slots;
+    std::vector<double> due_T;
+    const int first_pair_frame = (int)(std::max(f0, 1L) - f0);
+    for (int i = 0; i < n; i++) {
+        SimilarityTransform meas;
+        bool ok = false;
+        if (i >= first_pair_frame) {
+            const int p = i - first_pair_frame;
+            meas.A = m_T[4 * p]; meas.B = m_T[4 * p + 1]; meas.TX = m_T[4 * p + 2]; meas.TY = m_T[4 * p + 3];
+            ok = m_status[p] != 0;
+        }
+        m_meas[i] = meas;
+        m_ok[i] = ok ? 1 : 0;
+        SimilarityTransform corr;
+        if (m_trajectory.push(meas, ok, m_w, m_h, corr)) {
+            m_corr.push_back(corr);
+            due_slots.push_back((int32_t)((m_emitted + (long)due_slots.size()) % m_capacity));
+            due_T.insert(due_T.end(), {corr.A, corr.B, corr.TX, corr.TY});
+        }
+    }
+    m_fed = f0 + n;
+
+    // ---- one warp launch over the frames that became due (crop fused)
+    const int produced = (int)due_slots.size();
+    if (produced) {
+        if (!out) throw std::runtime_error("ClipStabilizer: output buffer is NULL");
+        check(vs_clip_warp(m_clip, due_slots.data(), produced, due_T.data(), VS_WARP_CV_EXACT_BILINEAR, VS_BORDER_CONSTANT0,
+                           m_crop, out, out_frame_stride, out_mem), "warp");
+    }
+    m_emitted += produced;
+    return produced;
+}
+
+}  // namespace vstab

@@ -1,0 +1,81 @@
+// clip_stabilizer.hpp — batched form of VideoStabilizer for throughput: many frames per
+// call, every stage one launch over the whole batch (north_star: "many frame pairs are
+// batched per launch so the 2k-point sparse solves fill the SMs").
+//
+// feed(n frames) produces exactly the frames n successive VideoStabilizer::processFrame
+// calls would have produced, in the same order:
+//   H2D (if host input) -> BGR->gray + pyramid for the n frames -> keyframe features for the
+//   odd frames -> ONE solver launch over the n alignment pairs -> D2H of 4 doubles + status
+//   per pair -> sequential host trajectory (L1 smoother, accumulate, decay) -> ONE warp launch
+//   (crop fused) over the frames that became due -> D2H (if host output).
+// Frames stay resident in a device ring of chunk_frames + lag + 1 slots, so a pair may span
+// two feed() calls and delayed frames are warped without a second upload.
+#pragma once
+
+#include <stdint.h>
+
+#include <vector>
+
+#include "stabilizer.hpp"
+#include "vstab.h"
+
+namespace vstab {
+
+class ClipStabilizer {
+public:
+    // Throws std::runtime_error when the device or its memory is unavailable.
+    ClipStabilizer(int device, int width, int height, int chunk_frames, const VideoStabilizerParams& params);
+    ~ClipStabilizer();
+    ClipStabilizer(const ClipStabilizer&) = delete;
+    ClipStabilizer& operator=(const ClipStabilizer&) = delete;
+
+    // Start a new video: frame numbering (and with it the keyframe parity), the trajectory
+    // and the delay line start over.
+    void reset();
+
+    // Feed the next n (<= chunk_frames) frames.  `frames`: interleaved BGR, row_stride /
+    // frame_stride in bytes, in host (VS_MEM_HOST) or device (VS_MEM_DEVICE) memory.
+    // Stabilized frames that became due are written densely ((w-2c) x (h-2c) x 3 each,
+    // out_frame_stride bytes apart) to `out` in `out_mem`; returns how many (<= n).
+    int feed(const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, int mem,
+             uint8_t* out, int64_t out_frame_stride, int out_mem);
+
+    // Same, for frames that are already in the ring: slots are assigned in feed order,
+    // frame f of the video lives in slot f % ring_capacity(); upload_only() places frames
+    // there without processing them (lets a benchmark exclude H2D from its timed region).
+    void upload_only(long first_frame, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, int mem);
+    int feed_resident(int n, uint8_t* out, int64_t out_frame_stride, int out_mem);
+
+    int out_width() const { return m_w - 2 * m_crop; }
+    int out_height() const { return m_h - 2 * m_crop; }
+    int ring_capacity() const { return m_capacity; }
+    long frames_fed() const { return m_fed; }
+    vs_ctx* context() const { return m_ctx; }
+    vs_clip* clip() const { return m_clip; }
+
+    // per-frame records of the last feed() (index i = i-th frame of that call)
+    const std::vector<SimilarityTransform>& measurements() const { return m_meas; }
+    const std::vector<uint8_t>& successes() const { return m_ok; }
+    // corrections of the frames produced by the last feed(), in output order
+    const std::vector<SimilarityTransform>& corrections() const { return m_corr; }
+
+private:
+    int m_w, m_h, m_chunk, m_capacity, m_crop;
+    VideoStabilizerParams m_params;
+    vs_ctx* m_ctx = nullptr;
+    vs_clip* m_clip = nullptr;
+    StabilizerTrajectory m_trajectory;
+    long m_fed = 0;        // frames fed since reset
+    long m_emitted = 0;    // frames produced since reset
+    std::vector<SimilarityTransform> m_meas, m_corr;
+    std::vector<uint8_t> m_ok;
+    std::vector<vs_pair> m_pairs;
+    std::vector<double> m_T;
+    std::vector<int32_t> m_status, m_slots;
+
+    void check(int rc, const char* what) const;
+    template <typename F> void for_slot_runs(long first_frame, int n, F f) const;
+    int process(int n, uint8_t* out, int64_t out_frame_stride, int out_mem);
+};
+
+}  // namespace vstab

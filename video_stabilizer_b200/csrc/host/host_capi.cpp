@@ -1,0 +1,300 @@
+// host_capi.cpp — C forwarders over the host classes (include/vstab_host.h).
+#include "vstab_host.h"
+
+#include <string.h>
+
+#include <exception>
+#include <string>
+
+#include "aligner_impl.hpp"
+#include "clip_stabilizer.hpp"
+#include "stabilizer.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+
+template <typename F>
+int guarded(F f)
+{
+    try {
+        return f();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+    } catch (...) {
+        g_err = "unknown C++ exception";
+    }
+    return -1;
+}
+
+SimilarityTransform tf(const double* T)
+{
+    SimilarityTransform t;
+    t.A = T[0]; t.B = T[1]; t.TX = T[2]; t.TY = T[3];
+    return t;
+}
+void put(const SimilarityTransform& t, double* T) { T[0] = t.A; T[1] = t.B; T[2] = t.TX; T[3] = t.TY; }
+
+VideoAlignerParams align_params(const vs_align_params* p)
+{
+    VideoAlignerParams q;
+    if (!p) return q;
+    q.phase_correlate = p->phase_correlate != 0;
+    q.phase_correlate_threshold = p->phase_correlate_threshold;
+    q.threshold = p->threshold;
+    q.smallest_fraction = p->smallest_fraction;
+    q.max_iters = p->max_iters;
+    q.pyramid_min_width = p->pyramid_min_width;
+    q.pyramid_min_height = p->pyramid_min_height;
+    q.max_displacement = p->max_displacement;
+    return q;
+}
+
+VideoStabilizerParams stab_params(const vsh_stab_params* p)
+{
+    VideoStabilizerParams q;
+    if (!p) return q;
+    q.aligner = align_params(&p->aligner);
+    q.lag = p->lag; q.smoother_memory = p->smoother_memory; q.lambda = p->lambda;
+    q.enable_smoother = p->enable_smoother != 0; q.crop_pixels = p->crop_pixels;
+    q.min_disp = p->min_disp; q.max_disp = p->max_disp; q.min_decay = p->min_decay; q.max_decay = p->max_decay;
+    return q;
+}
+
+template <typename T>
+Halide::Runtime::Buffer<T> wrap2(const T* p, int w, int h) { return Halide::Runtime::Buffer<T>(const_cast<T*>(p), w, h); }
+template <typename T>
+Halide::Runtime::Buffer<T> wrap3(const T* p, int w, int h, int c)
+{
+    halide_dimension_t shape[3] = {halide_dimension_t(0, w, 1), halide_dimension_t(0, h, w), halide_dimension_t(0, c, w * h)};
+    return Halide::Runtime::Buffer<T>(const_cast<T*>(p), 3, shape);
+}
+
+struct AlignerBox : public VideoAligner {
+    void set_device(int d) { impl_->device = d; }
+};
+
+}  // namespace
+
+extern "C" {
+
+void vsh_stab_params_default(vsh_stab_params* p)
+{
+    if (!p) return;
+    VideoStabilizerParams d;
+    vs_align_params_default(&p->aligner);
+    p->lag = d.lag; p->smoother_memory = d.smoother_memory; p->lambda = d.lambda;
+    p->enable_smoother = d.enable_smoother ? 1 : 0; p->crop_pixels = d.crop_pixels;
+    p->min_disp = d.min_disp; p->max_disp = d.max_disp; p->min_decay = d.min_decay; p->max_decay = d.max_decay;
+}
+
+const char* vsh_last_error(void) { return g_err.c_str(); }
+
+void vsh_tf_inverse(const double T[4], double out[4]) { put(tf(T).inverse(), out); }
+void vsh_tf_compose(const double T1[4], const double T2[4], double out[4]) { put(tf(T1).compose(tf(T2)), out); }
+void vsh_tf_warp(const double T[4], double px, double py, double out[2])
+{
+    Point p = tf(T).warp(Point{px, py});
+    out[0] = p.x; out[1] = p.y;
+}
+void vsh_tf_warp_center(const double T[4], double px, double py, double cx, double cy, double out[2])
+{
+    Point p = tf(T).warp(Point{px, py}, cx, cy);
+    out[0] = p.x; out[1] = p.y;
+}
+double vsh_tf_max_corner_displacement(const double T[4], double w, double h) { return tf(T).maxCornerDisplacement(w, h); }
+
+int vsh_PyrDown(const uint8_t* in, int iw, int ih, uint8_t* out, int ow, int oh)
+{
+    return guarded([&] {
+        auto a = wrap2(in, iw, ih); auto b = wrap2(out, ow, oh);
+        return PyrDown(a, b) ? 1 : 0;
+    });
+}
+
+int vsh_GradXY(const uint8_t* in, int w, int h, float* gx, float* gy)
+{
+    return guarded([&] {
+        auto a = wrap2(in, w, h); auto x = wrap2(gx, w, h); auto y = wrap2(gy, w, h);
+        return GradXY(a, x, y) ? 1 : 0;
+    });
+}
+
+int vsh_GradArgMax(const float* gx, const float* gy, int w, int h, int* tile, uint16_t* lmx, uint16_t* lmy, int capacity)
+{
+    return guarded([&] {
+        auto x = wrap2(gx, w, h); auto y = wrap2(gy, w, h);
+        Halide::Runtime::Buffer<uint16_t> ox, oy;   // callee allocates, as upstream
+        int t = 0;
+        if (!GradArgMax(x, y, t, ox, oy)) return 0;
+        *tile = t;
+        const size_t n = ox.number_of_elements();
+        if ((size_t)capacity < n) throw std::runtime_error("vsh_GradArgMax: output capacity too small");
+        memcpy(lmx, ox.data(), n * sizeof(uint16_t));
+        memcpy(lmy, oy.data(), n * sizeof(uint16_t));
+        return 1;
+    });
+}
+
+int vsh_SparseJacobian(const float* gx, const float* gy, int w, int h, const uint16_t* lmx, const uint16_t* lmy,
+                       int tw, int th, float* jx, float* jy)
+{
+    return guarded([&] {
+        auto x = wrap2(gx, w, h); auto y = wrap2(gy, w, h);
+        auto lx = wrap3(lmx, tw, th, 2); auto ly = wrap3(lmy, tw, th, 2);
+        Halide::Runtime::Buffer<float> ox, oy;
+        if (!SparseJacobian(x, y, lx, ly, ox, oy)) return 0;
+        memcpy(jx, ox.data(), ox.size_in_bytes());
+        memcpy(jy, oy.data(), oy.size_in_bytes());
+        return 1;
+    });
+}
+
+int vsh_SparseWarpDiff(const uint8_t* tmpl, const uint8_t* key, int w, int h, const uint16_t* lm, int tw, int th,
+                       const double T[4], uint16_t* out)
+{
+    return guarded([&] {
+        auto t = wrap2(tmpl, w, h); auto k = wrap2(key, w, h);
+        auto l = wrap3(lm, tw, th, 2);
+        Halide::Runtime::Buffer<uint16_t> o;
+        if (!SparseWarpDiff(t, k, l, tf(T), o)) return 0;
+        memcpy(out, o.data(), o.size_in_bytes());
+        return 1;
+    });
+}
+
+int vsh_SparseICA(const uint8_t* tmpl, const uint8_t* key, int w, int h, const uint16_t* selx, int kx,
+                  const uint16_t* sely, int ky, const float* jx, const float* jy, const double T[4], double out[4])
+{
+    return guarded([&] {
+        auto t = wrap2(tmpl, w, h); auto k = wrap2(key, w, h);
+        auto sx = wrap2(selx, kx, 2); auto sy = wrap2(sely, ky, 2);
+        auto ax = wrap2(jx, kx, 4); auto ay = wrap2(jy, ky, 4);
+        Halide::Runtime::Buffer<double> o;
+        if (!SparseICA(t, k, sx, sy, ax, ay, tf(T), o)) return 0;
+        for (int i = 0; i < 4; i++) out[i] = o(i);
+        return 1;
+    });
+}
+
+int vsh_ImageWarp(const uint8_t* in, int w, int h, const double T[4], float* out, int ow, int oh)
+{
+    return guarded([&] {
+        auto a = wrap2(in, w, h); auto o = wrap2(out, ow, oh);
+        return ImageWarp(a, tf(T), o) ? 1 : 0;
+    });
+}
+
+int vsh_warpBySimilarityTransform(const uint8_t* bgr, int w, int h, int64_t row_stride, const double T[4], uint8_t* out)
+{
+    return guarded([&] {
+        cv::Mat src(h, w, CV_8UC3, (void*)bgr, (size_t)row_stride);
+        cv::Mat dst = warpBySimilarityTransform(src, tf(T));
+        for (int y = 0; y < h; y++) memcpy(out + (size_t)y * w * 3, dst.ptr(y), (size_t)w * 3);
+        return 0;
+    });
+}
+
+void* vsh_smoother_create(int lag_behind, int lag_ahead, double lambda) { return new L1SmootherCenter(lag_behind, lag_ahead, lambda); }
+void vsh_smoother_destroy(void* s) { delete (L1SmootherCenter*)s; }
+int vsh_smoother_update(void* s, const double meas[4], double out[4])
+{
+    SimilarityTransform o;
+    bool r = ((L1SmootherCenter*)s)->update(tf(meas), o);
+    put(o, out);
+    return r ? 1 : 0;
+}
+void vsh_tvl1_relax(const double* data, int n, double lambda, int iterations, double* out) { vstab::tvl1_relax(data, n, lambda, iterations, out); }
+
+void* vsh_trajectory_create(const vsh_stab_params* p) { return new vstab::StabilizerTrajectory(stab_params(p)); }
+void vsh_trajectory_destroy(void* t) { delete (vstab::StabilizerTrajectory*)t; }
+int vsh_trajectory_push(void* t, const double meas[4], int success, int w, int h, double correction[4])
+{
+    SimilarityTransform c;
+    bool due = ((vstab::StabilizerTrajectory*)t)->push(tf(meas), success != 0, w, h, c);
+    put(c, correction);
+    return due ? 1 : 0;
+}
+
+void* vsh_aligner_create(int device)
+{
+    AlignerBox* a = nullptr;
+    guarded([&] { a = new AlignerBox(); a->set_device(device); return 0; });
+    return a;
+}
+void vsh_aligner_destroy(void* a) { delete (AlignerBox*)a; }
+int vsh_aligner_align(void* a, const uint8_t* bgr, int w, int h, int64_t row_stride, const vs_align_params* params, double T[4])
+{
+    return guarded([&] {
+        cv::Mat frame(h, w, CV_8UC3, (void*)bgr, (size_t)row_stride);
+        SimilarityTransform t;
+        bool ok = ((AlignerBox*)a)->AlignNextFrame(frame, t, align_params(params));
+        put(t, T);
+        return ok ? 1 : 0;
+    });
+}
+
+namespace {
+struct StabBox : public VideoStabilizer {
+    StabBox(const VideoStabilizerParams& p, int device) : VideoStabilizer(p) { static_cast<AlignerBox&>(aligner).set_device(device); }
+};
+}  // namespace
+
+void* vsh_stabilizer_create(const vsh_stab_params* p, int device)
+{
+    StabBox* s = nullptr;
+    guarded([&] { s = new StabBox(stab_params(p), device); return 0; });
+    return s;
+}
+void vsh_stabilizer_destroy(void* s) { delete (StabBox*)s; }
+int vsh_stabilizer_process(void* s, const uint8_t* bgr, int w, int h, int64_t row_stride, uint8_t* out, int* out_w, int* out_h)
+{
+    return guarded([&] {
+        cv::Mat frame(h, w, CV_8UC3, (void*)bgr, (size_t)row_stride);
+        cv::Mat r = ((StabBox*)s)->processFrame(frame);
+        if (r.empty()) { *out_w = *out_h = 0; return 0; }
+        *out_w = r.cols; *out_h = r.rows;
+        for (int y = 0; y < r.rows; y++) memcpy(out + (size_t)y * r.cols * 3, r.ptr(y), (size_t)r.cols * 3);
+        return 1;
+    });
+}
+
+void* vsh_clipstab_create(int device, int width, int height, int chunk_frames, const vsh_stab_params* p)
+{
+    vstab::ClipStabilizer* c = nullptr;
+    guarded([&] { c = new vstab::ClipStabilizer(device, width, height, chunk_frames, stab_params(p)); return 0; });
+    return c;
+}
+void vsh_clipstab_destroy(void* c) { delete (vstab::ClipStabilizer*)c; }
+int vsh_clipstab_reset(void* c) { return guarded([&] { ((vstab::ClipStabilizer*)c)->reset(); return 0; }); }
+int vsh_clipstab_feed(void* c, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, int mem,
+                      uint8_t* out, int64_t out_frame_stride, int out_mem)
+{
+    return guarded([&] { return ((vstab::ClipStabilizer*)c)->feed(frames, n, row_stride, frame_stride, mem, out, out_frame_stride, out_mem); });
+}
+int vsh_clipstab_upload_only(void* c, int64_t first_frame, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, int mem)
+{
+    return guarded([&] { ((vstab::ClipStabilizer*)c)->upload_only((long)first_frame, frames, n, row_stride, frame_stride, mem); return 0; });
+}
+int vsh_clipstab_feed_resident(void* c, int n, uint8_t* out, int64_t out_frame_stride, int out_mem)
+{
+    return guarded([&] { return ((vstab::ClipStabilizer*)c)->feed_resident(n, out, out_frame_stride, out_mem); });
+}
+int vsh_clipstab_last_records(void* c, double* meas, uint8_t* ok, double* corrections)
+{
+    auto* s = (vstab::ClipStabilizer*)c;
+    if (meas) for (size_t i = 0; i < s->measurements().size(); i++) put(s->measurements()[i], meas + 4 * i);
+    if (ok) for (size_t i = 0; i < s->successes().size(); i++) ok[i] = s->successes()[i];
+    if (corrections) for (size_t i = 0; i < s->corrections().size(); i++) put(s->corrections()[i], corrections + 4 * i);
+    return (int)s->corrections().size();
+}
+int vsh_clipstab_out_size(void* c, int* w, int* h)
+{
+    auto* s = (vstab::ClipStabilizer*)c;
+    *w = s->out_width(); *h = s->out_height();
+    return 0;
+}
+vs_ctx* vsh_clipstab_context(void* c) { return ((vstab::ClipStabilizer*)c)->context(); }
+vs_clip* vsh_clipstab_clip(void* c) { return ((vstab::ClipStabilizer*)c)->clip(); }
+
+}  // extern "C"

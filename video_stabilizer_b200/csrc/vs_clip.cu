@@ -152,6 +152,19 @@ int vs_clip_destroy(vs_clip* c)
     return VS_OK;
 }
 
+int vs_clip_set_params(vs_clip* c, const vs_align_params* params)
+{
+    if (!c || !params) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    if (params->phase_correlate)
+        return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "phase_correlate initialisation (alignment.cpp:369-388) is not implemented");
+    VS_REQUIRE(ctx, params->max_iters >= 1, "clip_set_params: max_iters must be >= 1");
+    const int mw = c->params.pyramid_min_width, mh = c->params.pyramid_min_height;
+    c->params = *params;
+    c->params.pyramid_min_width = mw; c->params.pyramid_min_height = mh;
+    return VS_OK;
+}
+
 int vs_clip_levels(const vs_clip* c) { return c ? c->g.levels : 0; }
 
 int vs_clip_level_info(const vs_clip* c, int level, int* w, int* h, int* tile, int* tw, int* th)

@@ -11,7 +11,25 @@
 
 #include "vstab.h"
 
+// kernel ids of the per-kernel timing facility (vs_ctx_profile_*); order = VS_KERNEL_* in vstab.h
+enum VsKernelId {
+    VSK_BGR2GRAY = 0, VSK_PYR_DOWN, VSK_GRAD_XY, VSK_IMAGE_WARP, VSK_BGR_WARP, VSK_GRAD_ARGMAX,
+    VSK_SPARSE_JAC, VSK_WARPDIFF, VSK_ICA, VSK_KEYFRAME, VSK_SOLVE, VSK_INGEST, VSK_COUNT
+};
+
+// CUDA-event pair around every launch, on the launching stream, resolved lazily
+struct VsProfiler {
+    struct Span { cudaEvent_t a, b; int id; };
+    std::vector<Span> pending;
+    std::vector<cudaEvent_t> pool;
+    double ms[VSK_COUNT] = {0};
+    int64_t n[VSK_COUNT] = {0};
+    int open_id = -1;
+    cudaEvent_t open_a = nullptr;
+};
+
 struct vs_ctx {
+    VsProfiler* prof = nullptr;
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -36,9 +54,15 @@ void vs_scratch_reset(vs_ctx* ctx);
                                 cudaGetErrorString(_e), __FILE__, __LINE__);                  \
     } while (0)
 
+void vs_prof_begin(vs_ctx* ctx, int id);
+void vs_prof_end(vs_ctx* ctx);
+// put directly before a kernel launch that VS_LAUNCH_CHECK follows
+#define VS_LAUNCH_BEGIN(ctx, id) do { if ((ctx)->prof) vs_prof_begin((ctx), (id)); } while (0)
+
 #define VS_LAUNCH_CHECK(ctx)                                                                  \
     do {                                                                                      \
         (ctx)->launches++;                                                                    \
+        if ((ctx)->prof) vs_prof_end(ctx);                                                    \
         cudaError_t _e = cudaGetLastError();                                                  \
         if (_e != cudaSuccess)                                                                \
             return vs_set_error((ctx), VS_ERR_CUDA, "kernel launch failed: %s (%s:%d)",       \

@@ -50,7 +50,93 @@ void* vs_scratch_alloc(vs_ctx* ctx, size_t bytes)
     return (char*)ctx->scratch + off;
 }
 
+// ---------------------------------------------------------------- per-kernel timing
+static cudaEvent_t prof_event(VsProfiler* p)
+{
+    if (!p->pool.empty()) { cudaEvent_t e = p->pool.back(); p->pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void vs_prof_begin(vs_ctx* ctx, int id)
+{
+    VsProfiler* p = ctx->prof;
+    p->open_id = id;
+    p->open_a = prof_event(p);
+    cudaEventRecord(p->open_a, ctx->stream);
+}
+
+void vs_prof_end(vs_ctx* ctx)
+{
+    VsProfiler* p = ctx->prof;
+    if (p->open_id < 0) return;
+    cudaEvent_t b = prof_event(p);
+    cudaEventRecord(b, ctx->stream);
+    p->pending.push_back({p->open_a, b, p->open_id});
+    p->open_id = -1;
+}
+
+static void prof_resolve(vs_ctx* ctx)
+{
+    VsProfiler* p = ctx->prof;
+    if (!p) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& s : p->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { p->ms[s.id] += ms; p->n[s.id]++; }
+        p->pool.push_back(s.a); p->pool.push_back(s.b);
+    }
+    p->pending.clear();
+}
+
+static void prof_destroy(vs_ctx* ctx)
+{
+    VsProfiler* p = ctx->prof;
+    if (!p) return;
+    prof_resolve(ctx);
+    for (cudaEvent_t e : p->pool) cudaEventDestroy(e);
+    delete p;
+    ctx->prof = nullptr;
+}
+
 extern "C" {
+
+int vs_ctx_profile_enable(vs_ctx* ctx, int enable)
+{
+    if (!ctx) return VS_ERR_INVALID;
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (enable && !ctx->prof) ctx->prof = new VsProfiler();
+    if (!enable) prof_destroy(ctx);
+    return VS_OK;
+}
+
+int vs_ctx_profile_reset(vs_ctx* ctx)
+{
+    if (!ctx) return VS_ERR_INVALID;
+    if (!ctx->prof) return VS_OK;
+    prof_resolve(ctx);
+    for (int i = 0; i < VSK_COUNT; i++) { ctx->prof->ms[i] = 0; ctx->prof->n[i] = 0; }
+    return VS_OK;
+}
+
+int vs_ctx_profile_read(vs_ctx* ctx, int kernel, int64_t* launches, double* total_ms)
+{
+    if (!ctx || kernel < 0 || kernel >= VSK_COUNT) return VS_ERR_INVALID;
+    if (!ctx->prof) { if (launches) *launches = 0; if (total_ms) *total_ms = 0; return VS_OK; }
+    prof_resolve(ctx);
+    if (launches) *launches = ctx->prof->n[kernel];
+    if (total_ms) *total_ms = ctx->prof->ms[kernel];
+    return VS_OK;
+}
+
+const char* vs_kernel_name(int kernel)
+{
+    static const char* names[VSK_COUNT] = {"bgr2gray", "pyr_down", "grad_xy", "image_warp", "bgr_warp", "grad_argmax",
+                                           "sparse_jac", "sparse_warpdiff", "sparse_ica", "keyframe_features", "solve_pairs",
+                                           "ingest_bgr_gray_l1"};
+    return kernel >= 0 && kernel < VSK_COUNT ? names[kernel] : "";
+}
 
 int vs_abi_version(void) { return VS_ABI_VERSION; }
 
@@ -94,6 +180,7 @@ int vs_ctx_destroy(vs_ctx* ctx)
     if (!ctx) return VS_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    prof_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

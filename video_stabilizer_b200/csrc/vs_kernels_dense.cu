@@ -330,6 +330,7 @@ int vsk_bgr2gray(vs_ctx* ctx, const VsDevImg& bgr, const VsDevImg& gray)
     int vec_ok = aligned_to(bgr.data, 16) && bgr.stride % 16 == 0 && bgr.batch_stride % 16 == 0 &&
                  aligned_to(gray.data, 16) && gray.stride % 16 == 0 && gray.batch_stride % 16 == 0;
     dim3 block(128), grid(vs_cdiv(vs_cdiv(bgr.w, 16), 128), bgr.h, bgr.batch);
+    VS_LAUNCH_BEGIN(ctx, VSK_BGR2GRAY);
     k_bgr2gray<<<grid, block, 0, ctx->stream>>>((const uint8_t*)bgr.data, bgr.stride, bgr.batch_stride,
                                                 (uint8_t*)gray.data, gray.stride, gray.batch_stride,
                                                 bgr.w, bgr.h, vec_ok);
@@ -345,6 +346,7 @@ int vsk_pyr_down(vs_ctx* ctx, const VsDevImg& in, const VsDevImg& out)
     VS_REQUIRE(ctx, out.batch <= 65535 && vs_cdiv(out.h, PD_TOH) <= 65535, "pyr_down: grid too large");
     int in_al = aligned_to(in.data, 4) && in.stride % 4 == 0 && in.batch_stride % 4 == 0;
     dim3 block(256), grid(vs_cdiv(out.w, PD_TOW), vs_cdiv(out.h, PD_TOH), out.batch);
+    VS_LAUNCH_BEGIN(ctx, VSK_PYR_DOWN);
     k_pyr_down<<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
                                                 (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h, in_al);
     VS_LAUNCH_CHECK(ctx);
@@ -360,6 +362,7 @@ int vsk_grad_xy(vs_ctx* ctx, const VsDevImg& in, const VsDevImg& gx, const VsDev
     int vec_ok = aligned_to(gx.data, 16) && gx.stride % 4 == 0 && gx.batch_stride % 4 == 0 &&
                  aligned_to(gy.data, 16) && gy.stride % 4 == 0 && gy.batch_stride % 4 == 0;
     dim3 block(128), grid(vs_cdiv(vs_cdiv(gx.w, 4), 128), gx.h, gx.batch);
+    VS_LAUNCH_BEGIN(ctx, VSK_GRAD_XY);
     k_grad_xy<<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
                                                (float*)gx.data, gx.stride, gx.batch_stride,
                                                (float*)gy.data, gy.stride, gy.batch_stride, gx.w, gx.h, vec_ok);
@@ -375,6 +378,7 @@ int vsk_image_warp(vs_ctx* ctx, const VsDevImg& in, const float* d_params4, cons
     VS_REQUIRE(ctx, out.h <= 65535 && out.batch <= 65535, "image_warp: grid too large");
     int vec_ok = aligned_to(out.data, 16) && out.stride % 4 == 0 && out.batch_stride % 4 == 0;
     dim3 block(128), grid(vs_cdiv(vs_cdiv(out.w, 4), 128), out.h, out.batch);
+    VS_LAUNCH_BEGIN(ctx, VSK_IMAGE_WARP);
     k_image_warp<<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
                                                   d_params4, (float*)out.data, out.stride, out.batch_stride,
                                                   out.w, out.h, vec_ok);
@@ -425,6 +429,7 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
     if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
     VS_REQUIRE(ctx, dst.h <= 65535 && dst.batch <= 65535, "bgr_warp: grid too large");
     dim3 block(256), grid(vs_cdiv(dst.w, 256), dst.h, dst.batch);
+    VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
     if (mode == VS_WARP_CV_EXACT_BILINEAR)
         launch_bgr_warp<VS_WARP_CV_EXACT_BILINEAR>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
     else if (mode == VS_WARP_FLOAT_BILINEAR)

@@ -427,6 +427,7 @@ int vsk_grad_argmax(vs_ctx* ctx, const VsDevImg& gx, const VsDevImg& gy, int til
     VS_REQUIRE(ctx, gx.w <= 65535 && gx.h <= 65535, "grad_argmax: coordinates must fit in u16");
     int tw = gx.w / tile, th = gy.h / tile;
     if (tw * th <= 0) return VS_OK;
+    VS_LAUNCH_BEGIN(ctx, VSK_GRAD_ARGMAX);
     k_grad_argmax<<<vs_cdiv(tw * th, 8), 256, 0, ctx->stream>>>((const float*)gx.data, gx.stride, (const float*)gy.data,
                                                                 gy.stride, tile, tw, th, d_lmx, d_lmy);
     VS_LAUNCH_CHECK(ctx);
@@ -437,6 +438,7 @@ int vsk_sparse_jac(vs_ctx* ctx, const VsDevImg& gx, const VsDevImg& gy, const ui
                    int tw, int th, float* d_jx, float* d_jy)
 {
     if (tw * th <= 0) return VS_OK;
+    VS_LAUNCH_BEGIN(ctx, VSK_SPARSE_JAC);
     k_sparse_jac<<<vs_cdiv(tw * th, 128), 128, 0, ctx->stream>>>((const float*)gx.data, gx.stride, (const float*)gy.data,
                                                                  gy.stride, gx.w, gx.h, d_lmx, d_lmy, tw, th, d_jx, d_jy);
     VS_LAUNCH_CHECK(ctx);
@@ -448,6 +450,7 @@ int vsk_sparse_warpdiff(vs_ctx* ctx, const VsDevImg& tmpl, const VsDevImg& key, 
 {
     VS_REQUIRE(ctx, tmpl.w == key.w && tmpl.h == key.h, "warpdiff: template/keyframe size mismatch");
     if (tw * th <= 0) return VS_OK;
+    VS_LAUNCH_BEGIN(ctx, VSK_WARPDIFF);
     k_sparse_warpdiff<<<vs_cdiv(tw * th, 128), 128, 0, ctx->stream>>>((const uint8_t*)tmpl.data, tmpl.stride,
                                                                       (const uint8_t*)key.data, key.stride, key.w, key.h,
                                                                       d_lm, tw * th, A, B, TX, TY, d_out);
@@ -460,6 +463,7 @@ int vsk_sparse_ica(vs_ctx* ctx, const VsDevImg& tmpl, const VsDevImg& key, const
                    float A, float B, float TX, float TY, double* d_out4)
 {
     VS_REQUIRE(ctx, tmpl.w == key.w && tmpl.h == key.h, "ica: template/keyframe size mismatch");
+    VS_LAUNCH_BEGIN(ctx, VSK_ICA);
     k_sparse_ica<<<1, 256, 0, ctx->stream>>>((const uint8_t*)tmpl.data, tmpl.stride, (const uint8_t*)key.data, key.stride,
                                              key.w, key.h, d_selx, kx, d_sely, ky, d_jx, d_jy, A, B, TX, TY, d_out4);
     VS_LAUNCH_CHECK(ctx);
@@ -472,6 +476,7 @@ int vsk_keyframe_features(vs_ctx* ctx, const VsClipGeom& g, const uint8_t* d_pyr
     if (n_slots <= 0) return VS_OK;
     VS_REQUIRE(ctx, n_slots <= 65535, "keyframe: too many slots in one call");
     dim3 grid(vs_cdiv(g.total_tiles, 8), n_slots);
+    VS_LAUNCH_BEGIN(ctx, VSK_KEYFRAME);
     k_keyframe_features<<<grid, 256, 0, ctx->stream>>>(g, d_pyr, d_slots, d_kp, d_jac);
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
@@ -485,6 +490,7 @@ int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
     VS_REQUIRE(ctx, smem <= 200 * 1024, "solve: level too large for the shared-memory selection");
     if (smem > 48 * 1024)
         VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);
     k_solve_pairs<<<a.n_pairs, SOLVE_THREADS, smem, ctx->stream>>>(g, a);
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;

@@ -1,0 +1,385 @@
+"""ctypes binding of libvstab_host.so (include/vstab_host.h): the C++ host layer that keeps
+the reference's classes — VideoAligner, VideoStabilizer, L1SmootherCenter,
+SimilarityTransform, the imgproc.hpp operators — on top of the CUDA C ABI.
+
+Used by the tests and bench.py; C++ callers include the .hpp files directly.  The transform
+algebra, smoother and trajectory are host-only C++ and work without a GPU; everything that
+touches an image raises without one (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi as capi
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libvstab_host.so")
+
+
+class VshStabParams(C.Structure):
+    _fields_ = [("aligner", capi.VsAlignParams), ("lag", C.c_int32), ("smoother_memory", C.c_int32), ("lambda_", C.c_double),
+                ("enable_smoother", C.c_int32), ("crop_pixels", C.c_int32), ("min_disp", C.c_double), ("max_disp", C.c_double),
+                ("min_decay", C.c_double), ("max_decay", C.c_double)]
+
+
+_P, _I, _D, _I64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
+_PI = C.POINTER(C.c_int)
+_AP = C.POINTER(capi.VsAlignParams)
+_SP = C.POINTER(VshStabParams)
+SYMBOLS = {
+    "vsh_stab_params_default": (None, [_SP]),
+    "vsh_last_error": (C.c_char_p, []),
+    "vsh_tf_inverse": (None, [_P, _P]),
+    "vsh_tf_compose": (None, [_P, _P, _P]),
+    "vsh_tf_warp": (None, [_P, _D, _D, _P]),
+    "vsh_tf_warp_center": (None, [_P, _D, _D, _D, _D, _P]),
+    "vsh_tf_max_corner_displacement": (_D, [_P, _D, _D]),
+    "vsh_PyrDown": (_I, [_P, _I, _I, _P, _I, _I]),
+    "vsh_GradXY": (_I, [_P, _I, _I, _P, _P]),
+    "vsh_GradArgMax": (_I, [_P, _P, _I, _I, _PI, _P, _P, _I]),
+    "vsh_SparseJacobian": (_I, [_P, _P, _I, _I, _P, _P, _I, _I, _P, _P]),
+    "vsh_SparseWarpDiff": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P]),
+    "vsh_SparseICA": (_I, [_P, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P]),
+    "vsh_ImageWarp": (_I, [_P, _I, _I, _P, _P, _I, _I]),
+    "vsh_warpBySimilarityTransform": (_I, [_P, _I, _I, _I64, _P, _P]),
+    "vsh_smoother_create": (_P, [_I, _I, _D]),
+    "vsh_smoother_destroy": (None, [_P]),
+    "vsh_smoother_update": (_I, [_P, _P, _P]),
+    "vsh_tvl1_relax": (None, [_P, _I, _D, _I, _P]),
+    "vsh_trajectory_create": (_P, [_SP]),
+    "vsh_trajectory_destroy": (None, [_P]),
+    "vsh_trajectory_push": (_I, [_P, _P, _I, _I, _I, _P]),
+    "vsh_aligner_create": (_P, [_I]),
+    "vsh_aligner_destroy": (None, [_P]),
+    "vsh_aligner_align": (_I, [_P, _P, _I, _I, _I64, _AP, _P]),
+    "vsh_stabilizer_create": (_P, [_SP, _I]),
+    "vsh_stabilizer_destroy": (None, [_P]),
+    "vsh_stabilizer_process": (_I, [_P, _P, _I, _I, _I64, _P, _PI, _PI]),
+    "vsh_clipstab_create": (_P, [_I, _I, _I, _I, _SP]),
+    "vsh_clipstab_destroy": (None, [_P]),
+    "vsh_clipstab_reset": (_I, [_P]),
+    "vsh_clipstab_feed": (_I, [_P, _P, _I, _I64, _I64, _I, _P, _I64, _I]),
+    "vsh_clipstab_upload_only": (_I, [_P, _I64, _P, _I, _I64, _I64, _I]),
+    "vsh_clipstab_feed_resident": (_I, [_P, _I, _P, _I64, _I]),
+    "vsh_clipstab_last_records": (_I, [_P, _P, _P, _P]),
+    "vsh_clipstab_out_size": (_I, [_P, _PI, _PI]),
+    "vsh_clipstab_context": (_P, [_P]),
+    "vsh_clipstab_clip": (_P, [_P]),
+}
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    capi.load()   # libvstab.so first, so the host library's dependency resolves to the same image
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libvstab_host.so is not built (%s). Run `python -m video_stabilizer_b200.build`." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _raise(what):
+    raise HostError("%s: %s" % (what, (load().vsh_last_error() or b"").decode()))
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _t(T):
+    return np.ascontiguousarray(T, np.float64)
+
+
+def stab_params_default() -> VshStabParams:
+    p = VshStabParams()
+    load().vsh_stab_params_default(C.byref(p))
+    return p
+
+
+# ---- SimilarityTransform
+def tf_inverse(T):
+    a, out = _t(T), np.zeros(4)
+    load().vsh_tf_inverse(_p(a), _p(out))
+    return out
+
+
+def tf_compose(T1, T2):
+    a, b, out = _t(T1), _t(T2), np.zeros(4)
+    load().vsh_tf_compose(_p(a), _p(b), _p(out))
+    return out
+
+
+def tf_warp(T, x, y, center=None):
+    a, out = _t(T), np.zeros(2)
+    if center is None:
+        load().vsh_tf_warp(_p(a), float(x), float(y), _p(out))
+    else:
+        load().vsh_tf_warp_center(_p(a), float(x), float(y), float(center[0]), float(center[1]), _p(out))
+    return out
+
+
+def tf_max_corner_displacement(T, w, h):
+    a = _t(T)
+    return load().vsh_tf_max_corner_displacement(_p(a), float(w), float(h))
+
+
+# ---- imgproc.hpp operators through the C++ wrappers (dense host arrays)
+def PyrDown(img, ow=None, oh=None):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    ow, oh = (w // 2 if ow is None else ow), (h // 2 if oh is None else oh)
+    out = np.empty((oh, ow), np.uint8)
+    r = load().vsh_PyrDown(_p(img), w, h, _p(out), ow, oh)
+    if r < 0:
+        _raise("PyrDown")
+    return bool(r), out
+
+
+def GradXY(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    gx, gy = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
+    r = load().vsh_GradXY(_p(img), w, h, _p(gx), _p(gy))
+    if r < 0:
+        _raise("GradXY")
+    return bool(r), gx, gy
+
+
+def GradArgMax(gx, gy):
+    gx, gy = np.ascontiguousarray(gx, np.float32), np.ascontiguousarray(gy, np.float32)
+    h, w = gx.shape
+    cap = (w // 2) * (h // 2) * 2
+    lmx, lmy = np.zeros(cap, np.uint16), np.zeros(cap, np.uint16)
+    tile = C.c_int()
+    r = load().vsh_GradArgMax(_p(gx), _p(gy), w, h, C.byref(tile), _p(lmx), _p(lmy), cap)
+    if r < 0:
+        _raise("GradArgMax")
+    t = tile.value
+    tw, th = w // t, h // t
+    return bool(r), t, lmx[:2 * tw * th].reshape(2, th, tw).copy(), lmy[:2 * tw * th].reshape(2, th, tw).copy()
+
+
+def SparseJacobian(gx, gy, lmx, lmy):
+    gx, gy = np.ascontiguousarray(gx, np.float32), np.ascontiguousarray(gy, np.float32)
+    lmx, lmy = np.ascontiguousarray(lmx, np.uint16), np.ascontiguousarray(lmy, np.uint16)
+    h, w = gx.shape
+    _, th, tw = lmx.shape
+    jx, jy = np.zeros((4, th, tw), np.float32), np.zeros((4, th, tw), np.float32)
+    r = load().vsh_SparseJacobian(_p(gx), _p(gy), w, h, _p(lmx), _p(lmy), tw, th, _p(jx), _p(jy))
+    if r < 0:
+        _raise("SparseJacobian")
+    return bool(r), jx, jy
+
+
+def SparseWarpDiff(tmpl, key, lm, T):
+    tmpl, key = np.ascontiguousarray(tmpl, np.uint8), np.ascontiguousarray(key, np.uint8)
+    lm, T = np.ascontiguousarray(lm, np.uint16), _t(T)
+    h, w = key.shape
+    _, th, tw = lm.shape
+    out = np.zeros((th, tw), np.uint16)
+    r = load().vsh_SparseWarpDiff(_p(tmpl), _p(key), w, h, _p(lm), tw, th, _p(T), _p(out))
+    if r < 0:
+        _raise("SparseWarpDiff")
+    return bool(r), out
+
+
+def SparseICA(tmpl, key, selx, sely, jx, jy, T):
+    tmpl, key = np.ascontiguousarray(tmpl, np.uint8), np.ascontiguousarray(key, np.uint8)
+    selx, sely = np.ascontiguousarray(selx, np.uint16), np.ascontiguousarray(sely, np.uint16)
+    jx, jy, T = np.ascontiguousarray(jx, np.float32), np.ascontiguousarray(jy, np.float32), _t(T)
+    h, w = key.shape
+    out = np.zeros(4)
+    r = load().vsh_SparseICA(_p(tmpl), _p(key), w, h, _p(selx), selx.shape[1], _p(sely), sely.shape[1], _p(jx), _p(jy), _p(T), _p(out))
+    if r < 0:
+        _raise("SparseICA")
+    return bool(r), out
+
+
+def ImageWarp(img, T, ow=None, oh=None):
+    img, T = np.ascontiguousarray(img, np.uint8), _t(T)
+    h, w = img.shape
+    ow, oh = (w if ow is None else ow), (h if oh is None else oh)
+    out = np.empty((oh, ow), np.float32)
+    r = load().vsh_ImageWarp(_p(img), w, h, _p(T), _p(out), ow, oh)
+    if r < 0:
+        _raise("ImageWarp")
+    return bool(r), out
+
+
+def warpBySimilarityTransform(bgr, T):
+    bgr, T = np.ascontiguousarray(bgr, np.uint8), _t(T)
+    h, w, _ = bgr.shape
+    out = np.empty((h, w, 3), np.uint8)
+    if load().vsh_warpBySimilarityTransform(_p(bgr), w, h, bgr.strides[0], _p(T), _p(out)) < 0:
+        _raise("warpBySimilarityTransform")
+    return out
+
+
+# ---- host-only classes
+def tvl1_relax(data, lam, iterations=100):
+    d = np.ascontiguousarray(data, np.float64)
+    out = np.zeros_like(d)
+    load().vsh_tvl1_relax(_p(d), d.size, float(lam), iterations, _p(out))
+    return out
+
+
+class _Handle:
+    _destroy = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            getattr(load(), self._destroy)(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class L1SmootherCenter(_Handle):
+    _destroy = "vsh_smoother_destroy"
+
+    def __init__(self, lag_behind, lag_ahead, lam=1.0):
+        self.h = C.c_void_p(load().vsh_smoother_create(lag_behind, lag_ahead, float(lam)))
+
+    def update(self, meas):
+        m, out = _t(meas), np.zeros(4)
+        ok = load().vsh_smoother_update(self.h, _p(m), _p(out))
+        return bool(ok), out
+
+
+class StabilizerTrajectory(_Handle):
+    _destroy = "vsh_trajectory_destroy"
+
+    def __init__(self, params: VshStabParams | None = None):
+        self.params = params or stab_params_default()
+        self.h = C.c_void_p(load().vsh_trajectory_create(C.byref(self.params)))
+
+    def push(self, meas, success, w, h):
+        m, out = _t(meas), np.zeros(4)
+        due = load().vsh_trajectory_push(self.h, _p(m), int(bool(success)), w, h, _p(out))
+        return bool(due), out
+
+
+# ---- GPU classes
+class VideoAligner(_Handle):
+    _destroy = "vsh_aligner_destroy"
+
+    def __init__(self, device: int = -1):
+        self.h = C.c_void_p(load().vsh_aligner_create(device))
+        if not self.h:
+            _raise("VideoAligner")
+
+    def AlignNextFrame(self, frame, params: capi.VsAlignParams | None = None):
+        frame = np.ascontiguousarray(frame, np.uint8)
+        h, w, _ = frame.shape
+        T = np.zeros(4)
+        r = load().vsh_aligner_align(self.h, _p(frame), w, h, frame.strides[0], C.byref(params) if params is not None else None, _p(T))
+        if r < 0:
+            _raise("AlignNextFrame")
+        return bool(r), T
+
+
+class VideoStabilizer(_Handle):
+    _destroy = "vsh_stabilizer_destroy"
+
+    def __init__(self, params: VshStabParams | None = None, device: int = -1):
+        self.params = params or stab_params_default()
+        self.h = C.c_void_p(load().vsh_stabilizer_create(C.byref(self.params), device))
+        if not self.h:
+            _raise("VideoStabilizer")
+
+    def processFrame(self, frame):
+        frame = np.ascontiguousarray(frame, np.uint8)
+        h, w, _ = frame.shape
+        # the frame that comes back is `lag` frames old and may have another (earlier) size
+        self._max_bytes = max(getattr(self, "_max_bytes", 0), h * w * 3)
+        out = np.empty(self._max_bytes, np.uint8)
+        ow, oh = C.c_int(), C.c_int()
+        r = load().vsh_stabilizer_process(self.h, _p(frame), w, h, frame.strides[0], _p(out), C.byref(ow), C.byref(oh))
+        if r < 0:
+            _raise("processFrame")
+        if r == 0:
+            return None
+        return out.ravel()[: oh.value * ow.value * 3].reshape(oh.value, ow.value, 3).copy()
+
+
+class ClipStabilizer(_Handle):
+    """Batched VideoStabilizer (clip_stabilizer.hpp)."""
+    _destroy = "vsh_clipstab_destroy"
+
+    def __init__(self, width, height, chunk_frames, params: VshStabParams | None = None, device: int = 0):
+        self.params = params or stab_params_default()
+        self.width, self.height, self.chunk = width, height, chunk_frames
+        self.h = C.c_void_p(load().vsh_clipstab_create(device, width, height, chunk_frames, C.byref(self.params)))
+        if not self.h:
+            _raise("ClipStabilizer")
+        ow, oh = C.c_int(), C.c_int()
+        load().vsh_clipstab_out_size(self.h, C.byref(ow), C.byref(oh))
+        self.out_w, self.out_h = ow.value, oh.value
+        self.out_frame_bytes = self.out_w * self.out_h * 3
+        self.ctx_handle = C.c_void_p(load().vsh_clipstab_context(self.h))
+
+    def reset(self):
+        if load().vsh_clipstab_reset(self.h) < 0:
+            _raise("reset")
+
+    def feed(self, frames: np.ndarray) -> np.ndarray:
+        """frames: (n,h,w,3) u8 host array; returns the (k,oh,ow,3) stabilized frames that became due."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = frames.shape[0]
+        out = np.empty((n, self.out_h, self.out_w, 3), np.uint8)
+        k = load().vsh_clipstab_feed(self.h, _p(frames), n, frames.strides[1], frames.strides[0], capi.VS_MEM_HOST,
+                                     _p(out), self.out_frame_bytes, capi.VS_MEM_HOST)
+        if k < 0:
+            _raise("feed")
+        return out[:k]
+
+    def feed_ptr(self, ptr: int, n: int, row_stride: int, frame_stride: int, mem: int, out_ptr: int, out_mem: int) -> int:
+        k = load().vsh_clipstab_feed(self.h, C.c_void_p(ptr), n, row_stride, frame_stride, mem, C.c_void_p(out_ptr),
+                                     self.out_frame_bytes, out_mem)
+        if k < 0:
+            _raise("feed")
+        return k
+
+    def upload_only(self, first_frame: int, ptr: int, n: int, row_stride: int, frame_stride: int, mem: int):
+        if load().vsh_clipstab_upload_only(self.h, first_frame, C.c_void_p(ptr), n, row_stride, frame_stride, mem) < 0:
+            _raise("upload_only")
+
+    def feed_resident(self, n: int, out_ptr: int, out_mem: int) -> int:
+        k = load().vsh_clipstab_feed_resident(self.h, n, C.c_void_p(out_ptr), self.out_frame_bytes, out_mem)
+        if k < 0:
+            _raise("feed_resident")
+        return k
+
+    def last_records(self, n: int):
+        meas, ok, corr = np.zeros((n, 4)), np.zeros(n, np.uint8), np.zeros((n, 4))
+        k = load().vsh_clipstab_last_records(self.h, _p(meas), _p(ok), _p(corr))
+        return meas, ok.astype(bool), corr[:k]
+
+    @property
+    def launches(self) -> int:
+        return int(capi.load().vs_ctx_launch_count(self.ctx_handle))
+
+    def set_stream(self, stream: int | None):
+        capi.check(self.ctx_handle, capi.load().vs_ctx_set_stream(self.ctx_handle, C.c_void_p(stream or 0)), "vs_ctx_set_stream")
+
+    def synchronize(self):
+        capi.check(self.ctx_handle, capi.load().vs_ctx_synchronize(self.ctx_handle), "vs_ctx_synchronize")
