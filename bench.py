@@ -246,8 +246,11 @@ def run_gpu_arm(args):
     p = host.stab_params_default()
     p.crop_pixels = crop
     cs = host.ClipStabilizer(W, H, F, p, device=local)
-    stream = torch.cuda.current_stream()
-    cs.set_stream(stream.cuda_stream)          # torch's CUDA events now see the library's launches
+    # a real (non-default) torch stream, borrowed by the library: the CUDA events of the timed
+    # region are recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
+    cs.set_stream(stream.cuda_stream)
     lib = capi.load()
     n_out = F - p.lag
     out_dev = torch.empty((n_out, cs.out_h, cs.out_w, 3), dtype=torch.uint8, device="cuda")

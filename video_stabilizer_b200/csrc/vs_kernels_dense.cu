@@ -316,6 +316,205 @@ k_bgr_warp(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src
     }
 }
 
+// ------------------------------------------------------------------ BGR warp, cv-exact, tiled
+// The production form of mode 0 (the warp VideoStabilizer runs on every output frame).
+// A CTA of 128 threads produces a 128 x 16 pixel output tile:
+//   1. thread t owns output column t: its two column terms adelta/bdelta (the only f64 work)
+//      are computed once and reused for the 16 rows; the 16 row terms X0/Y0 go to shared memory.
+//   2. the source bounding box of the tile follows from its four corners (the fixed-point
+//      map is a sum of a monotone function of x and a monotone function of y).  It is staged
+//      in shared memory with coalesced 32-bit loads (all of a thread's loads are issued before
+//      the first is consumed) as one 8-byte entry per source pixel x:
+//          .x = (B[x], B[x+1], G[x], G[x+1])      .y = (R[x], R[x+1], 0, 0)
+//      i.e. the two horizontal taps of every channel sit in adjacent bytes.  Texels outside
+//      the image are staged as the border value (0, or the clamped edge texel), so sampling
+//      needs no border logic.
+//   3. a pixel is then two conflict-free 8-byte shared loads (top and bottom row) and six
+//      IDP.2A dot products against the packed 16-bit weight pairs (w00|w10<<16, w01|w11<<16);
+//      results are collected in a shared tile and written out as 16-byte vectors.
+// A tile whose bounding box does not fit (large rotations or scales) takes the direct
+// global-memory path, decided per CTA.
+constexpr int WT_W = 128, WT_H = 16, WT_THREADS = 128;
+constexpr int WT_SRC_ENTRIES = 2560;                     // staged source capacity (20 KB): (128+8) x 18 fits
+constexpr int WT_OUT_ROW_WORDS = WT_W * 3 / 4;           // packed BGR bytes of one output row
+constexpr int WT_OUT_WORDS = WT_OUT_ROW_WORDS * WT_H;    // 6 KB
+constexpr int WT_SMEM_BYTES = WT_SRC_ENTRIES * 8 + WT_OUT_WORDS * 4;
+constexpr int WT_PREFETCH = 5;                           // staging tasks per thread kept in flight
+
+template <int BORDER>
+__device__ __forceinline__ uint32_t bgr_texel_word(const uint8_t* __restrict__ src, int64_t stride, int w, int h, int x, int y)
+{
+    if (BORDER == VS_BORDER_REPEAT_EDGE) {
+        x = vs_clampi(x, 0, w - 1); y = vs_clampi(y, 0, h - 1);
+    } else if (x < 0 || x >= w || y < 0 || y >= h) {
+        return 0u;
+    }
+    const uint8_t* p = src + (size_t)y * stride + 3 * x;
+    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+}
+
+// staged entry of pixel x from the BGRX words of x and x+1
+__device__ __forceinline__ uint2 wt_entry(uint32_t p, uint32_t pn)
+{
+    return make_uint2(__byte_perm(p, pn, 0x5140), __byte_perm(p, pn, 0x7362));
+}
+
+// One output pixel from the staged entries of (sx,sy) and (sx,sy+1).
+// (sum w p + 16384) >> 15 with w = 32 wx wy  ==  (sum wx wy p + 512) >> 10
+__device__ __forceinline__ uint32_t cv_blend(uint2 top, uint2 bot, int fx, int fy)
+{
+    const uint32_t hpair = (uint32_t)fx * 65535u + 32u;          // (32-fx) | fx << 16
+    const uint32_t wt = (uint32_t)(32 - fy) * hpair;             // w00 | w10 << 16, each <= 1024
+    const uint32_t wb = (uint32_t)fy * hpair;                    // w01 | w11 << 16
+    uint32_t b = __dp2a_lo(wt, top.x, 512u), g = __dp2a_hi(wt, top.x, 512u), r = __dp2a_lo(wt, top.y, 512u);
+    b = __dp2a_lo(wb, bot.x, b); g = __dp2a_hi(wb, bot.x, g); r = __dp2a_lo(wb, bot.y, r);
+    return (b >> 10) | ((g >> 10) << 8) | ((r >> 10) << 16);
+}
+
+template <int BORDER>
+__global__ void __launch_bounds__(WT_THREADS)
+k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
+                    const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
+                    uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
+                    int dst_x0, int dst_y0, int src_al4, int dst_al16)
+{
+    extern __shared__ __align__(16) uint32_t wt_smem[];
+    uint2* const S = reinterpret_cast<uint2*>(wt_smem);
+    uint32_t* const O = wt_smem + WT_SRC_ENTRIES * 2;
+    __shared__ int2 sXY0[WT_H];
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const int ox0 = blockIdx.x * WT_W, oy0 = blockIdx.y * WT_H;
+    const int tw = min(WT_W, dw - ox0), th = min(WT_H, dh - oy0);
+    const int slot = slots ? slots[b] : b;
+    const uint8_t* src = src_base + (size_t)slot * src_bs;
+    uint8_t* dst = dst_base + (size_t)b * dst_bs;
+    const VsWarpCoef cf = coefs[b];
+
+    // column terms of this thread, row terms of the tile (cv::warpAffine's adelta/bdelta, X0/Y0)
+    const int xcol = ox0 + min(tid, tw - 1) + dst_x0;
+    const int adelta = __double2int_rn(cf.i00 * (double)xcol * 1024.0);
+    const int bdelta = __double2int_rn(cf.i10 * (double)xcol * 1024.0);
+    if (tid < WT_H) {
+        const int y = oy0 + min(tid, th - 1) + dst_y0;
+        sXY0[tid] = make_int2(__double2int_rn((cf.i01 * (double)y + cf.i02) * 1024.0) + 16,
+                              __double2int_rn((cf.i11 * (double)y + cf.i12) * 1024.0) + 16);
+    }
+    __syncthreads();
+
+    // source bounding box from the four corners (each term is monotone in its variable)
+    const int xl = ox0 + dst_x0, xr = ox0 + tw - 1 + dst_x0;
+    const int aL = __double2int_rn(cf.i00 * (double)xl * 1024.0), aR = __double2int_rn(cf.i00 * (double)xr * 1024.0);
+    const int bL = __double2int_rn(cf.i10 * (double)xl * 1024.0), bR = __double2int_rn(cf.i10 * (double)xr * 1024.0);
+    const int X0t = sXY0[0].x, X0b = sXY0[th - 1].x, Y0t = sXY0[0].y, Y0b = sXY0[th - 1].y;
+    const int sxmin = (min(X0t, X0b) + min(aL, aR)) >> 10, sxmax = (max(X0t, X0b) + max(aL, aR)) >> 10;
+    const int symin = (min(Y0t, Y0b) + min(bL, bR)) >> 10, symax = (max(Y0t, Y0b) + max(bL, bR)) >> 10;
+    const int bx0 = (sxmin >> 2) * 4;                            // 4-pixel (12-byte, 3-word) staging granules
+    const int ngran = ((sxmax - bx0) >> 2) + 1;                  // entries bx0 .. sxmax (entry x also carries x+1)
+    const int pitch = ngran * 4;                                 // entries per staged row
+    const int by0 = symin, nrows = symax + 1 - symin + 1;
+    const int ntask = nrows * ngran;
+    const bool staged = (long long)pitch * nrows <= WT_SRC_ENTRIES;
+
+    if (staged) {
+        // task / ngran == umulhi(task, magic) for task < 2^16 (ngran == 1 would overflow the magic number)
+        const uint32_t magic = ngran > 1 ? 0xffffffffu / (uint32_t)ngran + 1u : 0u;
+        for (int base = 0; base < ntask; base += WT_THREADS * WT_PREFETCH) {
+            uint32_t wq[WT_PREFETCH][4];
+            bool fast[WT_PREFETCH];
+#pragma unroll
+            for (int k = 0; k < WT_PREFETCH; k++) {
+                const int task = base + k * WT_THREADS + tid;
+                const int r = ngran > 1 ? (int)__umulhi((uint32_t)task, magic) : task, q = task - r * ngran;
+                const int y = by0 + r, x = bx0 + 4 * q;
+                fast[k] = task < ntask && src_al4 && x >= 0 && x + 5 < w && y >= 0 && y < h;   // the 4th word ends inside the row
+                if (fast[k]) {
+                    const uint32_t* g = reinterpret_cast<const uint32_t*>(src + (size_t)y * src_stride + 3 * x);
+                    wq[k][0] = __ldg(g); wq[k][1] = __ldg(g + 1); wq[k][2] = __ldg(g + 2); wq[k][3] = __ldg(g + 3);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < WT_PREFETCH; k++) {
+                const int task = base + k * WT_THREADS + tid;
+                if (task >= ntask) break;
+                const int r = ngran > 1 ? (int)__umulhi((uint32_t)task, magic) : task, q = task - r * ngran;
+                uint2 e0, e1, e2, e3;
+                if (fast[k]) {
+                    const uint32_t w0 = wq[k][0], w1 = wq[k][1], w2 = wq[k][2], w3 = wq[k][3];
+                    // stream bytes of pixel j start at 3j; entry j = (b[3j], b[3j+3], b[3j+1], b[3j+4]), (b[3j+2], b[3j+5])
+                    e0 = make_uint2(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x0052) & 0xffffu);
+                    e1 = make_uint2(__byte_perm(w0, w1, 0x7463), __byte_perm(w1, w2, 0x0041) & 0xffffu);
+                    e2 = make_uint2(__byte_perm(w1, w2, 0x6352), __byte_perm(w2, w2, 0x0030) & 0xffffu);
+                    e3 = make_uint2(__byte_perm(w2, w3, 0x5241), __byte_perm(w2, w3, 0x0063) & 0xffffu);
+                } else {
+                    const int y = by0 + r, x = bx0 + 4 * q;
+                    const uint32_t p0 = bgr_texel_word<BORDER>(src, src_stride, w, h, x, y);
+                    const uint32_t p1 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 1, y);
+                    const uint32_t p2 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 2, y);
+                    const uint32_t p3 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 3, y);
+                    const uint32_t p4 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 4, y);
+                    e0 = wt_entry(p0, p1); e1 = wt_entry(p1, p2); e2 = wt_entry(p2, p3); e3 = wt_entry(p3, p4);
+                }
+                uint4* d = reinterpret_cast<uint4*>(S + (size_t)r * pitch + 4 * q);
+                d[0] = make_uint4(e0.x, e0.y, e1.x, e1.y);
+                d[1] = make_uint4(e2.x, e2.y, e3.x, e3.y);
+            }
+        }
+        __syncthreads();
+    }
+
+    {
+        // every thread runs the loop (columns beyond the tile edge repeat the last column) so the
+        // warp shuffles below are always executed by full warps
+        const uint2* const Sorg = S + (-by0 * pitch - bx0);
+        const int k4 = tid & 3;
+        // lane 4j+k (k<3) assembles packed word k of the 12 bytes of pixels 4j..4j+3 from its own
+        // BGRX word and its right neighbour's: B0G0R0B1 | G1R1B2G2 | R2B3G3R3
+        const uint32_t sel = k4 == 0 ? 0x4210u : (k4 == 1 ? 0x5421u : 0x6542u);
+        uint32_t* const Orow = O + 3 * (tid >> 2) + k4;
+#pragma unroll 4
+        for (int r = 0; r < WT_H; r++) {
+            if (r >= th) break;
+            const int2 xy0 = sXY0[r];
+            const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
+            const int sx = sfx >> 10, sy = sfy >> 10, fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
+            uint2 top, bot;
+            if (staged) {
+                const uint2* p = Sorg + (sy * pitch + sx);
+                top = p[0]; bot = p[pitch];
+            } else {
+                const uint32_t t00 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx, sy);
+                const uint32_t t10 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx + 1, sy);
+                const uint32_t t01 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx, sy + 1);
+                const uint32_t t11 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx + 1, sy + 1);
+                top = wt_entry(t00, t10); bot = wt_entry(t01, t11);
+            }
+            const uint32_t px = cv_blend(top, bot, fx, fy);
+            const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
+            if (k4 < 3) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
+        }
+    }
+    __syncthreads();
+
+    // write the tile: 16-byte vectors when the destination rows allow it
+    const int row_bytes = tw * 3;
+    if (dst_al16 && (row_bytes & 15) == 0) {
+        const int vec_per_row = row_bytes >> 4;
+        for (int i = tid; i < th * vec_per_row; i += WT_THREADS) {
+            const int r = i / vec_per_row, v = i - r * vec_per_row;
+            const uint4 val = *reinterpret_cast<const uint4*>(O + r * WT_OUT_ROW_WORDS + 4 * v);
+            *(reinterpret_cast<uint4*>(dst + (size_t)(oy0 + r) * dst_stride + (size_t)ox0 * 3) + v) = val;
+        }
+    } else {
+        const uint8_t* Ob = reinterpret_cast<const uint8_t*>(O);
+        for (int i = tid; i < th * row_bytes; i += WT_THREADS) {
+            const int r = i / row_bytes, c = i - r * row_bytes;
+            dst[(size_t)(oy0 + r) * dst_stride + (size_t)ox0 * 3 + c] = Ob[r * (WT_OUT_ROW_WORDS * 4) + c];
+        }
+    }
+}
+
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 }  // namespace
@@ -428,6 +627,28 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
     VS_REQUIRE(ctx, mode >= 0 && mode <= 2 && (border == 0 || border == 1), "bgr_warp: bad mode/border");
     if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
     VS_REQUIRE(ctx, dst.h <= 65535 && dst.batch <= 65535, "bgr_warp: grid too large");
+    if (mode == VS_WARP_CV_EXACT_BILINEAR) {
+        VS_REQUIRE(ctx, vs_cdiv(dst.h, WT_H) <= 65535, "bgr_warp: grid too large");
+        // per device, so set on every launch (multi-GPU processes drive several devices)
+        if (border == VS_BORDER_REPEAT_EDGE)
+            VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tiled<VS_BORDER_REPEAT_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
+        else
+            VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tiled<VS_BORDER_CONSTANT0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
+        const int src_al4 = aligned_to(src.data, 4) && src.stride % 4 == 0 && src.batch_stride % 4 == 0;
+        const int dst_al16 = aligned_to(dst.data, 16) && dst.stride % 16 == 0 && dst.batch_stride % 16 == 0;
+        dim3 tgrid(vs_cdiv(dst.w, WT_W), vs_cdiv(dst.h, WT_H), dst.batch);
+        VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
+        if (border == VS_BORDER_REPEAT_EDGE)
+            k_bgr_warp_cv_tiled<VS_BORDER_REPEAT_EDGE><<<tgrid, WT_THREADS, WT_SMEM_BYTES, ctx->stream>>>(
+                (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
+                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al16);
+        else
+            k_bgr_warp_cv_tiled<VS_BORDER_CONSTANT0><<<tgrid, WT_THREADS, WT_SMEM_BYTES, ctx->stream>>>(
+                (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
+                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al16);
+        VS_LAUNCH_CHECK(ctx);
+        return VS_OK;
+    }
     dim3 block(256), grid(vs_cdiv(dst.w, 256), dst.h, dst.batch);
     VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
     if (mode == VS_WARP_CV_EXACT_BILINEAR)
