@@ -54,75 +54,94 @@ k_bgr2gray(const uint8_t* __restrict__ bgr, int64_t in_stride, int64_t in_bs,
 
 // ------------------------------------------------------------------ pyr_down
 // generators.cpp:56-92: out(x,y) = (sum_j sum_i k_j k_i in(clamp(2x+i), clamp(2y+j))) >> 8,
-// k = [1 4 6 4 1].  A CTA produces a 64x16 output tile from a 136x35 byte input tile staged
-// in shared memory (edges clamped while staging).  Each thread produces 4 adjacent outputs
-// with packed arithmetic: two 16-bit lanes per register hold the vertical sums of two
-// columns (max 16*255 = 4080), the horizontal pass stays below 65536 (16*4080 = 65280).
-constexpr int PD_TOW = 64, PD_TOH = 16;
-constexpr int PD_IN_W = 2 * PD_TOW + 8;   // 136 bytes = 34 words, origin at 2*ox0 - 4
-constexpr int PD_IN_H = 2 * PD_TOH + 3;   // 35 rows, origin at 2*oy0 - 2
-constexpr int PD_IN_WORDS = PD_IN_W / 4;
+// k = [1 4 6 4 1].  Streaming, register-only: a thread owns 4 adjacent output columns and
+// walks down PD_ROWS output rows.  Per input row it loads the 12 bytes it needs as one
+// 8-byte word pair plus the two/one halo bytes on either side and forms the four horizontal
+// sums with IDP.4A against constant weight words; the vertical pass runs on a sliding window
+// of five rows, two outputs per register in 16-bit lanes (horizontal sums <= 4080, vertical
+// sums <= 65280: no carry between lanes).  The truncating >> 8 and the packing of the four
+// output bytes are one PRMT.  No shared memory, no barriers; the 3-row halo of a strip is
+// re-read from L1/L2.
+constexpr int PD_ROWS = 8;
 
-__global__ void __launch_bounds__(256)
-k_pyr_down(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, int iw, int ih,
-           uint8_t* __restrict__ out, int64_t out_stride, int64_t out_bs, int ow, int oh, int in_aligned4)
+// horizontal sums of outputs x..x+3 (x = first output column) from
+//   a16 = in[2x-2], in[2x-1] (low two bytes)   b = in[2x .. 2x+7]   c8 = in[2x+8]
+__device__ __forceinline__ void pd_hsum(uint32_t a16, uint2 b, uint32_t c8, uint32_t& h01, uint32_t& h23)
 {
-    __shared__ uint32_t tile[PD_IN_H][PD_IN_WORDS];
-    const int ox0 = blockIdx.x * PD_TOW, oy0 = blockIdx.y * PD_TOH;
-    const uint8_t* src = in + (size_t)blockIdx.z * in_bs;
-    uint8_t* dst = out + (size_t)blockIdx.z * out_bs;
-    const int ix0 = 2 * ox0 - 4, iy0 = 2 * oy0 - 2;
+    const uint32_t h0 = __dp4a(b.x, 0x00010406u, __dp4a(a16, 0x00000401u, 0u));
+    const uint32_t h1 = __dp4a(b.y, 0x00000001u, __dp4a(b.x, 0x04060401u, 0u));
+    const uint32_t h2 = __dp4a(b.y, 0x00010406u, __dp4a(b.x, 0x04010000u, 0u));
+    const uint32_t h3 = __dp4a(b.y, 0x04060401u, c8);
+    h01 = h0 | (h1 << 16);
+    h23 = h2 | (h3 << 16);
+}
 
-    for (int i = threadIdx.x; i < PD_IN_H * PD_IN_WORDS; i += 256) {
-        int r = i / PD_IN_WORDS, c = i - r * PD_IN_WORDS;
-        int gy = vs_clampi(iy0 + r, 0, ih - 1);
-        int gx = ix0 + 4 * c;
-        const uint8_t* row = src + (size_t)gy * in_stride;
-        uint32_t v;
-        if (in_aligned4 && gx >= 0 && gx + 3 < iw) {
-            v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-        } else {
-            uint32_t b0 = __ldg(row + vs_clampi(gx, 0, iw - 1));
-            uint32_t b1 = __ldg(row + vs_clampi(gx + 1, 0, iw - 1));
-            uint32_t b2 = __ldg(row + vs_clampi(gx + 2, 0, iw - 1));
-            uint32_t b3 = __ldg(row + vs_clampi(gx + 3, 0, iw - 1));
-            v = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-        }
-        tile[r][c] = v;
-    }
-    __syncthreads();
-
-    const int q = threadIdx.x & 15, ry = threadIdx.x >> 4;
-    // vertical pass on 4 words (16 input columns): even bytes -> E, odd bytes -> O
-    uint32_t E[4], O[4];
+template <bool FAST>
+__device__ __forceinline__ void pd_load_row(const uint8_t* __restrict__ src, int64_t stride, int iw, int ih, int row, int x4,
+                                            uint32_t& h01, uint32_t& h23)
+{
+    const uint8_t* r = src + (size_t)vs_clampi(row, 0, ih - 1) * stride;
+    uint32_t a16, c8;
+    uint2 b;
+    if (FAST) {
+        // 2*x4 .. 2*x4+7 inside the row, 8-byte aligned
+        b = __ldg(reinterpret_cast<const uint2*>(r + 2 * x4));
+        a16 = x4 > 0 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(r + 2 * x4 - 2)) : (b.x & 0xffu) * 0x0101u;
+        c8 = __ldg(r + min(2 * x4 + 8, iw - 1));
+    } else {
+        uint32_t v[11];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint32_t w0 = tile[2 * ry + 0][2 * q + k], w1 = tile[2 * ry + 1][2 * q + k];
-        uint32_t w2 = tile[2 * ry + 2][2 * q + k], w3 = tile[2 * ry + 3][2 * q + k];
-        uint32_t w4 = tile[2 * ry + 4][2 * q + k];
-        const uint32_t M = 0x00FF00FFu;
-        E[k] = (w0 & M) + (w4 & M) + 4u * ((w1 & M) + (w3 & M)) + 6u * (w2 & M);
-        O[k] = ((w0 >> 8) & M) + ((w4 >> 8) & M) + 4u * (((w1 >> 8) & M) + ((w3 >> 8) & M)) +
-               6u * ((w2 >> 8) & M);
+        for (int i = 0; i < 11; i++) v[i] = __ldg(r + vs_clampi(2 * x4 - 2 + i, 0, iw - 1));
+        a16 = v[0] | (v[1] << 8);
+        b.x = v[2] | (v[3] << 8) | (v[4] << 16) | (v[5] << 24);
+        b.y = v[6] | (v[7] << 8) | (v[8] << 16) | (v[9] << 24);
+        c8 = v[10];
     }
-    // horizontal pass: out_i = Ev[i+1] + 6 Ev[i+2] + Ev[i+3] + 4 (Od[i+1] + Od[i+2])
-    uint32_t e12 = __byte_perm(E[0], E[1], 0x5432), e34 = __byte_perm(E[1], E[2], 0x5432);
-    uint32_t e56 = __byte_perm(E[2], E[3], 0x5432);
-    uint32_t o12 = __byte_perm(O[0], O[1], 0x5432), o34 = __byte_perm(O[1], O[2], 0x5432);
-    uint32_t s01 = e12 + e34 + 6u * E[1] + 4u * (o12 + O[1]);
-    uint32_t s23 = e34 + e56 + 6u * E[2] + 4u * (o34 + O[2]);
-    uint32_t r01 = (s01 >> 8) & 0x00FF00FFu, r23 = (s23 >> 8) & 0x00FF00FFu;
-    uint32_t packed = __byte_perm(r01, r23, 0x6420);
+    pd_hsum(a16, b, c8, h01, h23);
+}
 
-    const int ox = ox0 + 4 * q, oy = oy0 + ry;
-    if (oy < oh && ox < ow) {
-        uint8_t* o = dst + (size_t)oy * out_stride + ox;
-        if (ox + 4 <= ow && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+template <bool FAST>
+__device__ __forceinline__ void pd_strip(const uint8_t* __restrict__ src, int64_t in_stride, int iw, int ih,
+                                         uint8_t* __restrict__ dst, int64_t out_stride, int ow, int oh, int x4, int y0, bool store_word)
+{
+    uint32_t a01, a23, b01, b23, c01, c23;
+    pd_load_row<FAST>(src, in_stride, iw, ih, 2 * y0 - 2, x4, a01, a23);
+    pd_load_row<FAST>(src, in_stride, iw, ih, 2 * y0 - 1, x4, b01, b23);
+    pd_load_row<FAST>(src, in_stride, iw, ih, 2 * y0, x4, c01, c23);
+#pragma unroll
+    for (int i = 0; i < PD_ROWS; i++) {
+        const int y = y0 + i;
+        if (y >= oh) break;
+        uint32_t d01, d23, e01, e23;
+        pd_load_row<FAST>(src, in_stride, iw, ih, 2 * y + 1, x4, d01, d23);
+        pd_load_row<FAST>(src, in_stride, iw, ih, 2 * y + 2, x4, e01, e23);
+        const uint32_t v01 = a01 + e01 + 4u * (b01 + d01) + 6u * c01;
+        const uint32_t v23 = a23 + e23 + 4u * (b23 + d23) + 6u * c23;
+        const uint32_t packed = __byte_perm(v01, v23, 0x7531);   // (v >> 8) of the four 16-bit lanes
+        uint8_t* o = dst + (size_t)y * out_stride + x4;
+        if (store_word) {
             *reinterpret_cast<uint32_t*>(o) = packed;
         } else {
-            for (int i = 0; i < 4 && ox + i < ow; i++) o[i] = (uint8_t)(packed >> (8 * i));
+            for (int k = 0; k < 4 && x4 + k < ow; k++) o[k] = (uint8_t)(packed >> (8 * k));
         }
+        a01 = c01; a23 = c23; b01 = d01; b23 = d23; c01 = e01; c23 = e23;
     }
+}
+
+__global__ void __launch_bounds__(128)
+k_pyr_down(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, int iw, int ih,
+           uint8_t* __restrict__ out, int64_t out_stride, int64_t out_bs, int ow, int oh, int in_al8, int out_al4)
+{
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y0 = (blockIdx.y * 4 + threadIdx.y) * PD_ROWS;
+    if (x4 >= ow || y0 >= oh) return;
+    const uint8_t* src = in + (size_t)blockIdx.z * in_bs;
+    uint8_t* dst = out + (size_t)blockIdx.z * out_bs;
+    const bool store_word = out_al4 && x4 + 4 <= ow;
+    if (in_al8 && 2 * x4 + 8 <= iw)
+        pd_strip<true>(src, in_stride, iw, ih, dst, out_stride, ow, oh, x4, y0, store_word);
+    else
+        pd_strip<false>(src, in_stride, iw, ih, dst, out_stride, ow, oh, x4, y0, store_word);
 }
 
 // ------------------------------------------------------------------ grad_xy
@@ -542,12 +561,13 @@ int vsk_pyr_down(vs_ctx* ctx, const VsDevImg& in, const VsDevImg& out)
     VS_REQUIRE(ctx, in.batch == out.batch, "pyr_down: batch mismatch");
     VS_REQUIRE(ctx, in.w > 0 && in.h > 0, "pyr_down: empty input");
     if (out.w <= 0 || out.h <= 0) return VS_OK;
-    VS_REQUIRE(ctx, out.batch <= 65535 && vs_cdiv(out.h, PD_TOH) <= 65535, "pyr_down: grid too large");
-    int in_al = aligned_to(in.data, 4) && in.stride % 4 == 0 && in.batch_stride % 4 == 0;
-    dim3 block(256), grid(vs_cdiv(out.w, PD_TOW), vs_cdiv(out.h, PD_TOH), out.batch);
+    VS_REQUIRE(ctx, out.batch <= 65535 && vs_cdiv(out.h, 4 * PD_ROWS) <= 65535, "pyr_down: grid too large");
+    int in_al8 = aligned_to(in.data, 8) && in.stride % 8 == 0 && in.batch_stride % 8 == 0;
+    int out_al4 = aligned_to(out.data, 4) && out.stride % 4 == 0 && out.batch_stride % 4 == 0;
+    dim3 block(32, 4), grid(vs_cdiv(vs_cdiv(out.w, 4), 32), vs_cdiv(out.h, 4 * PD_ROWS), out.batch);
     VS_LAUNCH_BEGIN(ctx, VSK_PYR_DOWN);
     k_pyr_down<<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
-                                                (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h, in_al);
+                                                (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h, in_al8, out_al4);
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }

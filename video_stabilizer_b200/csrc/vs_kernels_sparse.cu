@@ -96,8 +96,8 @@ k_sparse_jac(const float* __restrict__ gx, int64_t gxs, const float* __restrict_
 // all levels and all requested slots in one launch.  2|g| = |I(+1) - I(-1)| is an integer in
 // [0,255], so key = 2|g| << 16 | (N*N-1 - scan index) reproduces Halide's first-maximum rule.
 __global__ void __launch_bounds__(256)
-k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t* __restrict__ slots,
-                    uint32_t* __restrict__ kp, float4* __restrict__ jac)
+k_keyframe_features_generic(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t* __restrict__ slots,
+                            uint32_t* __restrict__ kp, float4* __restrict__ jac)
 {
     const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -140,6 +140,132 @@ k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t
             J = jac_y(gval, x, y, L.w, L.h);
         }
         size_t o = ((size_t)slot * 2 + axis) * g.total_tiles + wid;
+        kp[o] = ((uint32_t)y << 16) | (uint32_t)x;
+        jac[o] = J;
+    }
+}
+
+// ------------------------------------------------------------- keyframe features (banded)
+// Same result as k_keyframe_features_generic, organised for bandwidth: one CTA owns one tile
+// row (a band of N image rows, full width) of one level of one slot.  A thread streams down
+// the band on a 16-pixel column group: one 16-byte load per row (+ two halo bytes), a
+// three-row register window, |I(x+1)-I(x-1)| and |I(y+1)-I(y-1)| four pixels at a time with
+// funnel shifts and VABSDIFF4, and a running per-column maximum of (2|g| << 8 | 255 - ry),
+// one PRMT + one max per pixel and axis.  After the band the 16 column maxima are merged per
+// tile in registers, pushed to shared-memory accumulators with atomicMax on the full key
+// (2|g| << 16 | N*N-1 - scan index: the maximum is Halide's first maximum in (ry, rx) order),
+// and one thread per tile emits keypoint + Jacobian.
+constexpr int KF_THREADS = 128;
+constexpr int KF_MAX_TW = 512;     // tiles per band the shared accumulators hold
+
+__device__ __forceinline__ uint32_t kf_word(const uint4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+// replicate pixel (nvalid-1) into bytes nvalid..15 (repeat-edge for the last column group of a row)
+__device__ __forceinline__ void kf_clamp_tail(uint4& v, int nvalid)
+{
+    if (nvalid >= 16) return;
+    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    const int last = nvalid - 1;
+    const uint32_t edge = (wv[last >> 2] >> (8 * (last & 3))) & 0xffu;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        if (i >= nvalid) wv[i >> 2] = (wv[i >> 2] & ~(0xffu << (8 * (i & 3)))) | (edge << (8 * (i & 3)));
+    v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+}
+
+__device__ __forceinline__ uint4 kf_load_row(const uint8_t* __restrict__ img, int pitch, int w, int h, int y, int x0)
+{
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)vs_clampi(y, 0, h - 1) * pitch + x0));
+    kf_clamp_tail(v, w - x0);
+    return v;
+}
+
+__global__ void __launch_bounds__(KF_THREADS)
+k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t* __restrict__ slots,
+                    uint32_t* __restrict__ kp, float4* __restrict__ jac)
+{
+    __shared__ uint32_t acc[2][KF_MAX_TW];
+    // which (level, band) is this CTA?  band_off is the running sum of th over levels
+    int lvl = 0, band = blockIdx.x;
+    while (band >= g.lv[lvl].th) { band -= g.lv[lvl].th; lvl++; }
+    const VsLevel L = g.lv[lvl];
+    const int slot = slots[blockIdx.y];
+    const uint8_t* img = pyr + (size_t)slot * g.pyr_slot_bytes + L.img_off;
+    const int N = L.tile, NN1 = N * N - 1;
+    const int y0 = band * N;
+    const int wtiles = L.tw * N;                      // columns that belong to a tile
+    for (int i = threadIdx.x; i < L.tw; i += KF_THREADS) { acc[0][i] = 0u; acc[1][i] = 0u; }
+    __syncthreads();
+
+    for (int x0 = threadIdx.x * 16; x0 < wtiles; x0 += KF_THREADS * 16) {
+        uint32_t mx[16], my[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { mx[i] = 0u; my[i] = 0u; }
+        uint4 prev = kf_load_row(img, L.pitch, L.w, L.h, y0 - 1, x0);
+        uint4 cur = kf_load_row(img, L.pitch, L.w, L.h, y0, x0);
+        for (int ry = 0; ry < N; ry++) {
+            const int y = y0 + ry;
+            const uint4 next = kf_load_row(img, L.pitch, L.w, L.h, y + 1, x0);
+            const uint8_t* row = img + (size_t)y * L.pitch;
+            const uint32_t lb = x0 > 0 ? (uint32_t)__ldg(row + x0 - 1) : (cur.x & 0xffu);
+            const uint32_t rb = x0 + 16 < L.w ? (uint32_t)__ldg(row + x0 + 16) : (cur.w >> 24);
+            const uint32_t crow = 255u - (uint32_t)ry;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t wc = kf_word(cur, k);
+                const uint32_t wl = k == 0 ? (lb << 24) : kf_word(cur, k - 1);
+                const uint32_t wr = k == 3 ? rb : kf_word(cur, k + 1);
+                const uint32_t left = __funnelshift_r(wl, wc, 24);     // pixels x-1 .. x+2
+                const uint32_t right = __funnelshift_r(wc, wr, 8);     // pixels x+1 .. x+4
+                const uint32_t gx4 = __vabsdiffu4(right, left);
+                const uint32_t gy4 = __vabsdiffu4(kf_word(next, k), kf_word(prev, k));
+                // key' = 2|g| << 8 | 255 - ry : bytes (crow, g_byte, 0, 0)
+                mx[4 * k + 0] = max(mx[4 * k + 0], __byte_perm(gx4, crow, 0x5504));
+                mx[4 * k + 1] = max(mx[4 * k + 1], __byte_perm(gx4, crow, 0x5514));
+                mx[4 * k + 2] = max(mx[4 * k + 2], __byte_perm(gx4, crow, 0x5524));
+                mx[4 * k + 3] = max(mx[4 * k + 3], __byte_perm(gx4, crow, 0x5534));
+                my[4 * k + 0] = max(my[4 * k + 0], __byte_perm(gy4, crow, 0x5504));
+                my[4 * k + 1] = max(my[4 * k + 1], __byte_perm(gy4, crow, 0x5514));
+                my[4 * k + 2] = max(my[4 * k + 2], __byte_perm(gy4, crow, 0x5524));
+                my[4 * k + 3] = max(my[4 * k + 3], __byte_perm(gy4, crow, 0x5534));
+            }
+            prev = cur; cur = next;
+        }
+        // merge the 16 columns per tile, then one shared atomic per (tile, axis)
+        int tile = x0 / N;
+        int rx = x0 - tile * N;
+        uint32_t bx = 0u, by = 0u;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (x0 + i < wtiles) {
+                const uint32_t kx = ((mx[i] >> 8) << 16) | (uint32_t)(NN1 - (int)(255u - (mx[i] & 0xffu)) * N - rx);
+                const uint32_t ky = ((my[i] >> 8) << 16) | (uint32_t)(NN1 - (int)(255u - (my[i] & 0xffu)) * N - rx);
+                bx = max(bx, kx); by = max(by, ky);
+            }
+            rx++;
+            if (rx == N || i == 15) {
+                if (bx | by) { atomicMax(&acc[0][tile], bx); atomicMax(&acc[1][tile], by); }
+                bx = by = 0u; rx = 0; tile++;
+            }
+        }
+    }
+    __syncthreads();
+
+    for (int i = threadIdx.x; i < 2 * L.tw; i += KF_THREADS) {
+        const int axis = i >= L.tw, tx = i - axis * L.tw;
+        const int p = NN1 - (int)(acc[axis][tx] & 0xffffu);
+        const int x = tx * N + p % N, y = y0 + p / N;
+        float4 J;
+        if (axis == 0) {
+            const uint8_t* row = img + (size_t)y * L.pitch;
+            const float gval = __fmul_rn(0.5f, __fsub_rn((float)__ldg(row + min(x + 1, L.w - 1)), (float)__ldg(row + max(x - 1, 0))));
+            J = jac_x(gval, x, y, L.w, L.h);
+        } else {
+            const float gval = __fmul_rn(0.5f, __fsub_rn((float)__ldg(img + (size_t)min(y + 1, L.h - 1) * L.pitch + x),
+                                                         (float)__ldg(img + (size_t)max(y - 1, 0) * L.pitch + x)));
+            J = jac_y(gval, x, y, L.w, L.h);
+        }
+        const size_t o = ((size_t)slot * 2 + axis) * g.total_tiles + L.tile_off + (size_t)band * L.tw + tx;
         kp[o] = ((uint32_t)y << 16) | (uint32_t)x;
         jac[o] = J;
     }
@@ -475,9 +601,21 @@ int vsk_keyframe_features(vs_ctx* ctx, const VsClipGeom& g, const uint8_t* d_pyr
 {
     if (n_slots <= 0) return VS_OK;
     VS_REQUIRE(ctx, n_slots <= 65535, "keyframe: too many slots in one call");
-    dim3 grid(vs_cdiv(g.total_tiles, 8), n_slots);
+    // banded kernel: needs 16-byte aligned rows and a band's tiles in its shared accumulators
+    bool banded = (reinterpret_cast<uintptr_t>(d_pyr) % 16 == 0) && g.pyr_slot_bytes % 16 == 0;
+    int bands = 0;
+    for (int l = 0; l < g.levels; l++) {
+        banded = banded && g.lv[l].pitch % 16 == 0 && g.lv[l].img_off % 16 == 0 && g.lv[l].tw <= KF_MAX_TW;
+        bands += g.lv[l].th;
+    }
     VS_LAUNCH_BEGIN(ctx, VSK_KEYFRAME);
-    k_keyframe_features<<<grid, 256, 0, ctx->stream>>>(g, d_pyr, d_slots, d_kp, d_jac);
+    if (banded) {
+        dim3 grid(bands, n_slots);
+        k_keyframe_features<<<grid, KF_THREADS, 0, ctx->stream>>>(g, d_pyr, d_slots, d_kp, d_jac);
+    } else {
+        dim3 grid(vs_cdiv(g.total_tiles, 8), n_slots);
+        k_keyframe_features_generic<<<grid, 256, 0, ctx->stream>>>(g, d_pyr, d_slots, d_kp, d_jac);
+    }
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
