@@ -74,7 +74,7 @@ def build_host(force: bool = False) -> str | None:
     if not force and _newer(LIB_HOST, deps):
         return LIB_HOST
     cxx = shutil.which("g++") or "g++"
-    _run([cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-pthread",
+    _run([cxx, "-std=c++17", "-O2", "-mavx2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-pthread",
           "-I", INCLUDE, "-I", host_dir, "-idirafter", os.path.join(INCLUDE, "compat"),
           "-o", LIB_HOST] + srcs + ["-L", PKG_DIR, "-lvstab", "-Wl,-rpath,$ORIGIN"])
     return LIB_HOST

@@ -3,6 +3,7 @@
 // reference bit for bit.
 #include "smoother.hpp"
 
+#include <immintrin.h>
 #include <math.h>
 
 #include <algorithm>
@@ -31,6 +32,69 @@ void tvl1_relax(const double* data, int n, double lambda, int iterations, double
     }
 }
 
+namespace {
+
+// The four transform parameters are smoothed independently with identical control flow
+// apart from the per-pair branch, so they run as the four lanes of one vector: every lane
+// performs exactly the scalar operations above (both branch results are formed and the
+// lane's own one is kept), which keeps the trajectory bit-identical to the scalar code.
+typedef double v4d __attribute__((vector_size(32)));
+typedef long long v4i __attribute__((vector_size(32)));
+
+inline v4d v4_abs(v4d a)
+{
+    v4i bits = (v4i)a & (v4i){0x7fffffffffffffffLL, 0x7fffffffffffffffLL, 0x7fffffffffffffffLL, 0x7fffffffffffffffLL};
+    return (v4d)bits;
+}
+
+inline v4d v4_select(v4i mask, v4d a, v4d b) { return (v4d)(((v4i)a & mask) | ((v4i)b & ~mask)); }
+
+// data, x: n vectors (A, B, TX, TY).
+// The scalar loop nest is a chain of iterations x (n-1) dependent pair updates, each with a
+// divide: pure latency.  Pair i of iteration t only needs pair i-1 of iteration t and pair
+// i+1 of iteration t-1, so all pairs with the same 2t+i are independent; walking those
+// wavefronts in place performs exactly the same operations on the same values in a
+// dependency-respecting order (bit-identical result) with up to (n-1)/2 divides in flight.
+void tvl1_relax4(const v4d* data, int n, double lambda, int iterations, v4d* x)
+{
+    const v4d half = {0.5, 0.5, 0.5, 0.5};
+    const v4d lam = {lambda, lambda, lambda, lambda};
+    for (int i = 0; i < n; i++) x[i] = data[i];
+    if (n < 2 || iterations <= 0) return;   // a lone sample relaxes onto itself: 0.5 d + 0.5 d == d
+    const int pairs = n - 1;
+    const int waves = 2 * (iterations - 1) + pairs;
+    for (int w = 0; w < waves; w++) {
+        // iterations t with 0 <= w - 2t <= pairs - 1
+        int t_lo = (w - (pairs - 1) + 1) / 2;
+        if (t_lo < 0) t_lo = 0;
+        int t_hi = w / 2;
+        if (t_hi > iterations - 1) t_hi = iterations - 1;
+        for (int t = t_lo; t <= t_hi; t++) {
+            const int i = w - 2 * t;
+            // the relaxation step of iteration t, applied where each value is first used:
+            // x[i+1] always, x[i] only for the first pair (later pairs inherit it from pair i-1)
+            const v4d a = i == 0 ? half * x[0] + half * data[0] : x[i];
+            const v4d b = half * x[i + 1] + half * data[i + 1];
+            const v4d diff = b - a;
+            const v4d mag = v4_abs(diff);
+            const v4i shrink_lane = mag > lam;
+            const v4d mid = half * (a + b);
+            if (!_mm256_movemask_pd((__m256d)shrink_lane)) {
+                // no lane exceeds lambda (the common case for sub-lambda jitter): skip the divide
+                x[i] = mid;
+                x[i + 1] = mid;
+                continue;
+            }
+            const v4d shrink = (mag - lam) / mag * half;
+            const v4d step = diff * shrink;
+            x[i] = v4_select(shrink_lane, a + step, mid);
+            x[i + 1] = v4_select(shrink_lane, b - step, mid);
+        }
+    }
+}
+
+}  // namespace
+
 }  // namespace vstab
 
 L1SmootherCenter::L1SmootherCenter(int lagBehind, int lagAhead, double lambda)
@@ -47,21 +111,18 @@ bool L1SmootherCenter::update(const SimilarityTransform& meas, SimilarityTransfo
     const int first = std::max(0, m_nextToFinalize - m_lagBehind);
     const int last = m_nextToFinalize + m_lagAhead;
     const int n = last - first + 1;
-    // one window per parameter, smoothed independently
-    std::vector<double> window(4 * (size_t)n), smooth(4 * (size_t)n);
+    // one window, the four parameters as the four lanes of a vector
+    std::vector<vstab::v4d> window(n), smooth(n);
     for (int i = 0; i < n; i++) {
         const SimilarityTransform& m = m_measurements[first + i];
-        window[0 * n + i] = m.A;
-        window[1 * n + i] = m.B;
-        window[2 * n + i] = m.TX;
-        window[3 * n + i] = m.TY;
+        window[i] = (vstab::v4d){m.A, m.B, m.TX, m.TY};
     }
-    for (int c = 0; c < 4; c++) vstab::tvl1_relax(&window[(size_t)c * n], n, m_lambda, 100, &smooth[(size_t)c * n]);
+    vstab::tvl1_relax4(window.data(), n, m_lambda, 100, smooth.data());
     const int mid = m_nextToFinalize - first;
-    outFinalized.A = smooth[0 * n + mid];
-    outFinalized.B = smooth[1 * n + mid];
-    outFinalized.TX = smooth[2 * n + mid];
-    outFinalized.TY = smooth[3 * n + mid];
+    outFinalized.A = smooth[mid][0];
+    outFinalized.B = smooth[mid][1];
+    outFinalized.TX = smooth[mid][2];
+    outFinalized.TY = smooth[mid][3];
     m_nextToFinalize++;
     return true;
 }
