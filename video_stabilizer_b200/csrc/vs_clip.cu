@@ -31,6 +31,7 @@ struct vs_clip {
     uint16_t* d_dbg_wd = nullptr;
     uint16_t* d_dbg_order = nullptr;
     int32_t* d_dbg_count = nullptr;
+    uint16_t* d_pos_scratch = nullptr; // [max_pairs][4][max_tiles] candidate lists of the parallel selection
     uint8_t* d_warp_out = nullptr;    // staging for VS_MEM_HOST warps, grown on demand
     size_t warp_out_bytes = 0;
     int last_pairs = 0;
@@ -55,7 +56,7 @@ void free_all(vs_clip* c)
 {
     cudaFree(c->d_bgr); cudaFree(c->d_pyr); cudaFree(c->d_kp); cudaFree(c->d_jac); cudaFree(c->d_pairs);
     cudaFree(c->d_T); cudaFree(c->d_status); cudaFree(c->d_iters); cudaFree(c->d_slots); cudaFree(c->d_coef);
-    cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_warp_out);
+    cudaFree(c->d_pos_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_warp_out);
 }
 
 }  // namespace
@@ -129,6 +130,7 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_iters, (size_t)max_pairs * g.levels);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_slots, (size_t)nslots);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_coef, (size_t)capacity);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_pos_scratch, (size_t)max_pairs * 4 * g.max_tiles);
     if (r == VS_OK && (flags & VS_CLIP_DEBUG_TAPS)) {
         r = dev_alloc(ctx, &c->d_dbg_wd, (size_t)max_pairs * 2 * g.total_tiles);
         if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_order, (size_t)max_pairs * 2 * g.total_tiles);
@@ -251,6 +253,7 @@ int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_
     a.out_status = dev_out ? out_status : c->d_status;
     a.out_iters = dev_out ? out_iters : (out_iters ? c->d_iters : nullptr);
     a.dbg_warpdiff = c->d_dbg_wd; a.dbg_order = c->d_dbg_order; a.dbg_count = c->d_dbg_count;
+    a.pos_scratch = c->d_pos_scratch;
     if (c->d_dbg_count)   // -1 marks levels a pair never reached
         VS_CUDA(ctx, cudaMemsetAsync(c->d_dbg_count, 0xFF, (size_t)c->max_pairs * 2 * c->g.levels * sizeof(int32_t), ctx->stream));
     VS_TRY(vsk_solve_pairs(ctx, c->g, a));

@@ -337,6 +337,182 @@ struct SolveShared {
     int status;
 };
 
+// ---- block-parallel exact replay of std::nth_element (libstdc++ introselect) ------------
+// The serial algorithm (vs_introselect.cuh) is: loop { median-of-3 pivot to `first`;
+// unguarded Hoare partition of [first+1,last); keep the side that holds nth } until the range
+// is <= 3 long, then insertion sort.  Only the Hoare partition is long, and it is
+// order-independent enough to run in parallel while producing the identical permutation:
+//   the left pointer stops at the successive positions a_0 < a_1 < ... whose value is >= pivot,
+//   the right pointer at the successive positions b_0 > b_1 > ... whose value is <= pivot
+//   (both in the array as it was when the partition started), and swap k exchanges a_k and b_k
+//   as long as a_k < b_k.  With m such swaps the function returns min(a_m, b_{m-1}): the first
+//   position past a_{m-1} that now holds a value >= pivot.
+// So a round is: every thread counts the candidates of its slice, a block scan turns counts
+// into ranks, candidates are scattered to posL[rank] / posR[rank], m is a block-wide count of
+// a_k < b_k, and the m swaps touch disjoint positions.  Median-of-3, the bookkeeping and the
+// tail (ranges <= SEL_SERIAL long, or an exhausted depth limit -> heap select) run on one thread
+// per axis with the serial code, so every comparison-dependent choice is libstdc++'s own.
+// Both keypoint axes are processed in the same rounds.
+constexpr int SEL_SERIAL = 96;
+
+struct SelAxis {
+    int first, last, depth, done;
+    uint32_t pivot;
+    int nL, nR, m;
+};
+
+struct SelShared {
+    SelAxis ax[2];
+    uint32_t warp_tot[2][SOLVE_WARPS];
+    int warp_cnt[2][SOLVE_WARPS];
+};
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+
+// keys[a]: n packed keys of axis a; pos[a]: 2*n u16 (posL then posR).  nth < n.
+__device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1, uint16_t* const pos0, uint16_t* const pos1,
+                                   const int n, const int nth, SelShared& ss)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n == 0 || nth == n) return;
+    if (tid < 2) {
+        ss.ax[tid].first = 0; ss.ax[tid].last = n; ss.ax[tid].depth = vs_sel::lg(n) * 2; ss.ax[tid].done = 0;
+    }
+    __syncthreads();
+    while (true) {
+        // ---- per-axis serial step: finish, or pick the pivot of the next round
+        if (tid == 0 || tid == 32) {
+            const int a = tid >> 5;
+            SelAxis& st = ss.ax[a];
+            uint32_t* v = a ? keys1 : keys0;
+            if (!st.done) {
+                if (st.last - st.first <= SEL_SERIAL || st.depth == 0) {
+                    vs_sel::introselect_from(v, st.first, nth, st.last, st.depth);
+                    st.done = 1;
+                } else {
+                    --st.depth;
+                    const int mid = st.first + (st.last - st.first) / 2;
+                    vs_sel::move_median_to_first(v, st.first, st.first + 1, mid, st.last - 1);
+                    st.pivot = v[st.first];
+                }
+            }
+        }
+        __syncthreads();
+        const bool act0 = !ss.ax[0].done, act1 = !ss.ax[1].done;
+        if (!act0 && !act1) break;
+
+        // ---- count the candidates of this thread's slice, both axes
+        int c0[2], c1[2];
+        uint32_t cnt[2] = {0u, 0u};          // nL | nR << 16
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            c0[a] = c1[a] = 0;
+            if (!(a ? act1 : act0)) continue;
+            const SelAxis& st = ss.ax[a];
+            const uint32_t* v = a ? keys1 : keys0;
+            const int f0 = st.first + 1, len = st.last - f0;
+            const int chunk = (len + SOLVE_THREADS - 1) / SOLVE_THREADS;
+            c0[a] = min(f0 + tid * chunk, st.last);
+            c1[a] = min(c0[a] + chunk, st.last);
+            const uint32_t pv = st.pivot;
+            uint32_t c = 0;
+            for (int i = c0[a]; i < c1[a]; i++) {
+                const uint32_t e = v[i];
+                c += (vs_sel::less(e, pv) ? 0u : 1u) + (vs_sel::less(pv, e) ? 0u : 0x10000u);
+            }
+            cnt[a] = c;
+        }
+        uint32_t incl[2];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            incl[a] = warp_incl_scan_u32(cnt[a]);
+            if (lane == 31) ss.warp_tot[a][warp] = incl[a];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < SOLVE_WARPS; w++) {
+                const uint32_t t = ss.warp_tot[a][w];
+                if (w < warp) before += t;
+                total += t;
+            }
+            incl[a] += before;
+            if (!(a ? act1 : act0)) continue;
+            const uint32_t* v = a ? keys1 : keys0;
+            uint16_t* posL = a ? pos1 : pos0;
+            uint16_t* posR = posL + n;
+            const uint32_t pv = ss.ax[a].pivot;
+            const int nL = (int)(total & 0xffffu), nR = (int)(total >> 16);
+            int offL = (int)((incl[a] - cnt[a]) & 0xffffu);            // candidates in lower slices
+            int offR = nR - (int)(incl[a] >> 16);                      // candidates in higher slices
+            for (int i = c0[a]; i < c1[a]; i++)
+                if (!vs_sel::less(v[i], pv)) posL[offL++] = (uint16_t)i;
+            for (int i = c1[a] - 1; i >= c0[a]; i--)
+                if (!vs_sel::less(pv, v[i])) posR[offR++] = (uint16_t)i;
+            if (tid == 0) { ss.ax[a].nL = nL; ss.ax[a].nR = nR; }
+        }
+        __syncthreads();
+
+        // ---- m = number of swaps = #{k : a_k < b_k}
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            int c = 0;
+            if (a ? act1 : act0) {
+                const uint16_t* posL = a ? pos1 : pos0;
+                const uint16_t* posR = posL + n;
+                const int lim = min(ss.ax[a].nL, ss.ax[a].nR);
+                for (int k = tid; k < lim; k += SOLVE_THREADS) c += posL[k] < posR[k] ? 1 : 0;
+            }
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0) ss.warp_cnt[a][warp] = c;
+        }
+        __syncthreads();
+
+        // ---- the swaps, then the bookkeeping of __introselect
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            if (!(a ? act1 : act0)) continue;
+            uint32_t* v = a ? keys1 : keys0;
+            const uint16_t* posL = a ? pos1 : pos0;
+            const uint16_t* posR = posL + n;
+            int m = 0;
+#pragma unroll
+            for (int w = 0; w < SOLVE_WARPS; w++) m += ss.warp_cnt[a][w];
+            for (int k = tid; k < m; k += SOLVE_THREADS) {
+                const int i = posL[k], j = posR[k];
+                const uint32_t t = v[i]; v[i] = v[j]; v[j] = t;
+            }
+            if (tid == 32 * a) ss.ax[a].m = m;
+        }
+        __syncthreads();
+        if (tid == 0 || tid == 32) {
+            const int a = tid >> 5;
+            SelAxis& st = ss.ax[a];
+            if (!st.done) {
+                const uint16_t* posL = a ? pos1 : pos0;
+                const uint16_t* posR = posL + n;
+                const int m = st.m;
+                int cut = st.last;
+                if (m < st.nL) cut = posL[m];
+                if (m > 0) cut = min(cut, (int)posR[m - 1]);
+                if (cut <= nth) st.first = cut; else st.last = cut;
+            }
+        }
+        // the next iteration's serial step runs on the same threads (0 and 32): no barrier needed here
+    }
+}
+
 template <int N>
 __device__ __forceinline__ void block_reduce(double* v, SolveShared& sh, double* total)
 {
@@ -366,8 +542,9 @@ __device__ __forceinline__ double dist2d(const double* a, const double* b)
 __global__ void __launch_bounds__(SOLVE_THREADS)
 k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 {
-    extern __shared__ uint32_t dyn_keys[];   // keys[2][max_tiles]: abs_delta << 16 | tile
+    extern __shared__ uint32_t dyn_keys[];   // keys[2][max_tiles]: abs_delta << 16 | tile, then (optionally) pos[2][2*max_tiles] u16
     __shared__ SolveShared sh;
+    __shared__ SelShared sel;
     const int tid = threadIdx.x;
     const int pair = blockIdx.x;
     if (pair >= a.n_pairs) return;
@@ -377,6 +554,10 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
     const size_t feat = (size_t)pr.keyframe_slot * 2 * g.total_tiles;
     uint32_t* const keys0 = dyn_keys;
     uint32_t* const keys1 = dyn_keys + g.max_tiles;
+    // candidate position lists of the parallel selection: shared memory when they fit, else a global scratch slice
+    uint16_t* const pos0 = a.pos_scratch ? a.pos_scratch + (size_t)pair * 4 * g.max_tiles
+                                         : reinterpret_cast<uint16_t*>(dyn_keys + 2 * g.max_tiles);
+    uint16_t* const pos1 = pos0 + 2 * g.max_tiles;
 
     if (tid == 0) {
         sh.T[0] = sh.T[1] = sh.T[2] = sh.T[3] = 0.0;
@@ -414,8 +595,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         __syncthreads();
 
         // ---- keep the k smallest: exact replay of std::nth_element (alignment.cpp:460-486)
-        if (tid == 0) vs_sel::nth_element_serial(keys0, nt, k);
-        if (tid == 32) vs_sel::nth_element_serial(keys1, nt, k);
+        block_nth_element2(keys0, keys1, pos0, pos1, nt, k, sel);
         __syncthreads();
 
         if (a.dbg_order) {
@@ -623,13 +803,23 @@ int vsk_keyframe_features(vs_ctx* ctx, const VsClipGeom& g, const uint8_t* d_pyr
 int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
 {
     if (a.n_pairs <= 0) return VS_OK;
-    size_t smem = (size_t)2 * g.max_tiles * sizeof(uint32_t);
+    // keys (8 B per tile) always live in shared memory; the candidate position lists of the
+    // parallel selection (another 8 B per tile) join them when the total stays small enough
+    // for three CTAs per SM, else they come from the caller's global scratch
+    const size_t key_bytes = (size_t)2 * g.max_tiles * sizeof(uint32_t);
+    const size_t pos_bytes = (size_t)4 * g.max_tiles * sizeof(uint16_t);
     VS_REQUIRE(ctx, g.max_tiles <= 65535, "solve: more than 65535 tiles per level");
-    VS_REQUIRE(ctx, smem <= 200 * 1024, "solve: level too large for the shared-memory selection");
-    if (smem > 48 * 1024)
-        VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_REQUIRE(ctx, key_bytes <= 200 * 1024, "solve: level too large for the shared-memory selection");
+    size_t smem = key_bytes;
+    VsSolveArgs args = a;
+    if (key_bytes + pos_bytes <= 72 * 1024 || !a.pos_scratch) {
+        VS_REQUIRE(ctx, key_bytes + pos_bytes <= 220 * 1024, "solve: level too large and no selection scratch given");
+        smem += pos_bytes;
+        args.pos_scratch = nullptr;
+    }
+    VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);
-    k_solve_pairs<<<a.n_pairs, SOLVE_THREADS, smem, ctx->stream>>>(g, a);
+    k_solve_pairs<<<a.n_pairs, SOLVE_THREADS, smem, ctx->stream>>>(g, args);
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
