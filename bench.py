@@ -246,6 +246,8 @@ def run_gpu_arm(args):
     p = host.stab_params_default()
     p.crop_pixels = crop
     cs = host.ClipStabilizer(W, H, F, p, device=local)
+    if args.pipeline_frames:
+        cs.set_pipeline_frames(args.pipeline_frames)
     # a real (non-default) torch stream, borrowed by the library: the CUDA events of the timed
     # region are recorded on the stream the kernels are launched on
     stream = torch.cuda.Stream()
@@ -395,7 +397,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
@@ -405,6 +407,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=16, help="frames per CPU worker thread in the CPU arm / baseline")
     ap.add_argument("--cpu-threads", type=int, default=0, help="CPU worker threads (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-frames", type=int, default=0, help="sub-chunk of the host-to-host pipeline (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -201,6 +201,22 @@ int vs_clip_align(vs_clip*, const vs_pair* pairs, int n,
 int vs_clip_warp(vs_clip*, const int32_t* slots, int n, const double* transforms,
                  int mode, int border, int crop, uint8_t* out, int64_t out_frame_stride, int mem);
 
+/* ---- asynchronous host <-> device transfers for pipelined feeding (ClipStabilizer::feed with
+ * host buffers): uploads run on the clip's copy-in stream and downloads on its copy-out stream,
+ * so PCIe traffic in both directions overlaps the kernels of neighbouring chunks.  Host buffers
+ * should be pinned (vs_host_alloc_pinned / cudaHostRegister) for the copies to be truly
+ * asynchronous; pageable memory works but serialises. */
+/* like vs_clip_upload(VS_MEM_HOST) on the copy-in stream; ordered after all compute enqueued so far */
+int vs_clip_upload_async(vs_clip*, int slot0, int n, const uint8_t* bgr, int64_t row_stride, int64_t frame_stride);
+/* compute enqueued after this call waits for every upload issued so far */
+int vs_clip_wait_uploads(vs_clip*);
+/* like vs_clip_warp(VS_MEM_HOST) but returns as soon as the warp is enqueued; the frames land in
+ * `out` on the copy-out stream.  out must stay valid until vs_clip_sync_transfers(). */
+int vs_clip_warp_to_host_async(vs_clip*, const int32_t* slots, int n, const double* transforms,
+                               int mode, int border, int crop, uint8_t* out, int64_t out_frame_stride);
+/* blocks until every asynchronous upload and download issued so far has completed */
+int vs_clip_sync_transfers(vs_clip*);
+
 /* inspection taps (host outputs, synchronous) used by the bit-exact parity tests */
 int vs_clip_get_bgr(vs_clip*, int slot, uint8_t* out /* w*h*3 dense */);
 int vs_clip_get_gray(vs_clip*, int slot, int level, uint8_t* out /* w*h dense */);

@@ -86,6 +86,8 @@ int   vsh_stabilizer_process(void*, const uint8_t* bgr, int w, int h, int64_t ro
 void* vsh_clipstab_create(int device, int width, int height, int chunk_frames, const vsh_stab_params* p);
 void  vsh_clipstab_destroy(void*);
 int   vsh_clipstab_reset(void*);
+/* sub-chunk (frames) of the host-to-host transfer/compute pipeline inside feed(); default 32 */
+int   vsh_clipstab_set_pipeline_frames(void*, int frames);
 /* returns the number of stabilized frames written to out (>= 0) or -1 */
 int   vsh_clipstab_feed(void*, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, int mem,
                         uint8_t* out, int64_t out_frame_stride, int out_mem);

@@ -81,6 +81,10 @@ SYMBOLS = {
     "vs_clip_build_keyframes": (C.c_int, [_P, _P, C.c_int]),
     "vs_clip_align": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int]),
     "vs_clip_warp": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64, C.c_int]),
+    "vs_clip_upload_async": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64, C.c_int64]),
+    "vs_clip_wait_uploads": (C.c_int, [_P]),
+    "vs_clip_warp_to_host_async": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64]),
+    "vs_clip_sync_transfers": (C.c_int, [_P]),
     "vs_clip_get_bgr": (C.c_int, [_P, C.c_int, _P]),
     "vs_clip_get_gray": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "vs_clip_get_keypoints": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),

@@ -72,21 +72,48 @@ int ClipStabilizer::feed(const uint8_t* frames, int n, int64_t row_stride, int64
                          uint8_t* out, int64_t out_frame_stride, int out_mem)
 {
     if (n < 0 || n > m_chunk) throw std::runtime_error("ClipStabilizer: feed() takes at most chunk_frames frames");
+    if (mem == VS_MEM_HOST && out_mem == VS_MEM_HOST && n > m_sub)
+        return feed_pipelined(frames, n, row_stride, frame_stride, out, out_frame_stride);
     upload_only(m_fed, frames, n, row_stride, frame_stride, mem);
-    return process(n, out, out_frame_stride, out_mem);
+    return process(n, out, out_frame_stride, out_mem, false, false);
+}
+
+int ClipStabilizer::feed_pipelined(const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride,
+                                   uint8_t* out, int64_t out_frame_stride)
+{
+    // NOTE: m_fed advances inside process(); uploads address frames by their position in this call
+    const long base = m_fed;
+    auto upload_chunk = [&](int first, int count) {
+        for_slot_runs(base + first, count, [&](int slot, int done, int run) {
+            check(vs_clip_upload_async(m_clip, slot, run, frames + (size_t)frame_stride * (first + done), row_stride, frame_stride),
+                  "upload");
+        });
+    };
+    int produced = 0;
+    upload_chunk(0, std::min(m_sub, n));
+    for (int first = 0; first < n; first += m_sub) {
+        const int count = std::min(m_sub, n - first);
+        check(vs_clip_wait_uploads(m_clip), "wait for uploads");          // compute of this sub-chunk waits for its frames only
+        if (first + count < n) upload_chunk(first + count, std::min(m_sub, n - first - count));   // overlaps the kernels below
+        produced += process(count, out ? out + (size_t)out_frame_stride * produced : nullptr, out_frame_stride, VS_MEM_HOST,
+                            first > 0, true);
+    }
+    check(vs_clip_sync_transfers(m_clip), "transfers");
+    return produced;
 }
 
 int ClipStabilizer::feed_resident(int n, uint8_t* out, int64_t out_frame_stride, int out_mem)
 {
     if (n < 0 || n > m_chunk) throw std::runtime_error("ClipStabilizer: feed_resident() takes at most chunk_frames frames");
-    return process(n, out, out_frame_stride, out_mem);
+    return process(n, out, out_frame_stride, out_mem, false, false);
 }
 
-int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int out_mem)
+int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int out_mem, bool append_records, bool async_to_host)
 {
-    m_meas.assign(n, SimilarityTransform());
-    m_ok.assign(n, 0);
-    m_corr.clear();
+    const size_t rec0 = append_records ? m_meas.size() : 0;
+    m_meas.resize(rec0 + n);
+    m_ok.resize(rec0 + n);
+    if (!append_records) m_corr.clear();
     if (n == 0) return 0;
     const long f0 = m_fed;
 
@@ -121,8 +148,8 @@ int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int o
             meas.A = m_T[4 * p]; meas.B = m_T[4 * p + 1]; meas.TX = m_T[4 * p + 2]; meas.TY = m_T[4 * p + 3];
             ok = m_status[p] != 0;
         }
-        m_meas[i] = meas;
-        m_ok[i] = ok ? 1 : 0;
+        m_meas[rec0 + i] = meas;
+        m_ok[rec0 + i] = ok ? 1 : 0;
         SimilarityTransform corr;
         if (m_trajectory.push(meas, ok, m_w, m_h, corr)) {
             m_corr.push_back(corr);
@@ -136,8 +163,12 @@ int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int o
     const int produced = (int)due_slots.size();
     if (produced) {
         if (!out) throw std::runtime_error("ClipStabilizer: output buffer is NULL");
-        check(vs_clip_warp(m_clip, due_slots.data(), produced, due_T.data(), VS_WARP_CV_EXACT_BILINEAR, VS_BORDER_CONSTANT0,
-                           m_crop, out, out_frame_stride, out_mem), "warp");
+        if (async_to_host)
+            check(vs_clip_warp_to_host_async(m_clip, due_slots.data(), produced, due_T.data(), VS_WARP_CV_EXACT_BILINEAR,
+                                             VS_BORDER_CONSTANT0, m_crop, out, out_frame_stride), "warp");
+        else
+            check(vs_clip_warp(m_clip, due_slots.data(), produced, due_T.data(), VS_WARP_CV_EXACT_BILINEAR, VS_BORDER_CONSTANT0,
+                               m_crop, out, out_frame_stride, out_mem), "warp");
     }
     m_emitted += produced;
     return produced;

@@ -37,8 +37,15 @@ public:
     // frame_stride in bytes, in host (VS_MEM_HOST) or device (VS_MEM_DEVICE) memory.
     // Stabilized frames that became due are written densely ((w-2c) x (h-2c) x 3 each,
     // out_frame_stride bytes apart) to `out` in `out_mem`; returns how many (<= n).
+    // With host input AND host output the call is software-pipelined over sub-chunks of
+    // pipeline_frames(): the H2D copy of sub-chunk k+1 (copy-in stream) and the D2H copy of
+    // the frames warped for sub-chunk k-1 (copy-out stream) overlap the kernels of sub-chunk k,
+    // so a PCIe-fed clip runs at the speed of the slower PCIe direction rather than the sum of
+    // both copies and the compute.  Pinned host buffers are needed for that overlap.
     int feed(const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, int mem,
              uint8_t* out, int64_t out_frame_stride, int out_mem);
+    int pipeline_frames() const { return m_sub; }
+    void set_pipeline_frames(int frames) { m_sub = frames < 1 ? 1 : frames; }
 
     // Same, for frames that are already in the ring: slots are assigned in feed order,
     // frame f of the video lives in slot f % ring_capacity(); upload_only() places frames
@@ -61,6 +68,7 @@ public:
 
 private:
     int m_w, m_h, m_chunk, m_capacity, m_crop;
+    int m_sub = 32;        // sub-chunk of the host-to-host pipeline
     VideoStabilizerParams m_params;
     vs_ctx* m_ctx = nullptr;
     vs_clip* m_clip = nullptr;
@@ -75,7 +83,8 @@ private:
 
     void check(int rc, const char* what) const;
     template <typename F> void for_slot_runs(long first_frame, int n, F f) const;
-    int process(int n, uint8_t* out, int64_t out_frame_stride, int out_mem);
+    int process(int n, uint8_t* out, int64_t out_frame_stride, int out_mem, bool append_records, bool async_to_host);
+    int feed_pipelined(const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, uint8_t* out, int64_t out_frame_stride);
 };
 
 }  // namespace vstab

@@ -34,6 +34,18 @@ struct vs_clip {
     uint16_t* d_pos_scratch = nullptr; // [max_pairs][4][max_tiles] candidate lists of the parallel selection
     uint8_t* d_warp_out = nullptr;    // staging for VS_MEM_HOST warps, grown on demand
     size_t warp_out_bytes = 0;
+    // asynchronous transfer pipeline (vs_clip_upload_async / vs_clip_warp_to_host_async)
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaEvent_t ev_compute = nullptr, ev_upload = nullptr;
+    static const int kOutRing = 3;
+    uint8_t* d_out_ring[kOutRing] = {nullptr, nullptr, nullptr};
+    size_t out_ring_bytes[kOutRing] = {0, 0, 0};
+    cudaEvent_t ev_warp[kOutRing] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_down[kOutRing] = {nullptr, nullptr, nullptr};
+    bool out_ring_used[kOutRing] = {false, false, false};
+    VsWarpCoef* d_coef_ring = nullptr;  // kOutRing * capacity
+    int32_t* d_slot_ring = nullptr;     // kOutRing * capacity
+    int out_ring_next = 0;
     int last_pairs = 0;
 };
 
@@ -56,6 +68,16 @@ void free_all(vs_clip* c)
 {
     cudaFree(c->d_bgr); cudaFree(c->d_pyr); cudaFree(c->d_kp); cudaFree(c->d_jac); cudaFree(c->d_pairs);
     cudaFree(c->d_T); cudaFree(c->d_status); cudaFree(c->d_iters); cudaFree(c->d_slots); cudaFree(c->d_coef);
+    for (int i = 0; i < vs_clip::kOutRing; i++) {
+        cudaFree(c->d_out_ring[i]);
+        if (c->ev_warp[i]) cudaEventDestroy(c->ev_warp[i]);
+        if (c->ev_down[i]) cudaEventDestroy(c->ev_down[i]);
+    }
+    cudaFree(c->d_coef_ring); cudaFree(c->d_slot_ring);
+    if (c->ev_compute) cudaEventDestroy(c->ev_compute);
+    if (c->ev_upload) cudaEventDestroy(c->ev_upload);
+    if (c->up_stream) cudaStreamDestroy(c->up_stream);
+    if (c->down_stream) cudaStreamDestroy(c->down_stream);
     cudaFree(c->d_pos_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_warp_out);
 }
 
@@ -148,7 +170,9 @@ int vs_clip_destroy(vs_clip* c)
 {
     if (!c) return VS_OK;
     cudaSetDevice(c->ctx->device);
+    if (c->up_stream) cudaStreamSynchronize(c->up_stream);
     cudaStreamSynchronize(c->ctx->stream);
+    if (c->down_stream) cudaStreamSynchronize(c->down_stream);
     free_all(c);
     delete c;
     return VS_OK;
@@ -313,6 +337,125 @@ int vs_clip_warp(vs_clip* c, const int32_t* slots, int n, const double* transfor
                                        cudaMemcpyDeviceToHost, ctx->stream));
         VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------ asynchronous transfers
+static int ensure_async(vs_clip* c)
+{
+    vs_ctx* ctx = c->ctx;
+    if (c->up_stream) return VS_OK;
+    VS_CUDA(ctx, cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+    VS_CUDA(ctx, cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
+    VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming));
+    VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming));
+    for (int i = 0; i < vs_clip::kOutRing; i++) {
+        VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_warp[i], cudaEventDisableTiming));
+        VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_down[i], cudaEventDisableTiming));
+    }
+    VS_TRY(dev_alloc(ctx, &c->d_coef_ring, (size_t)vs_clip::kOutRing * c->capacity));
+    VS_TRY(dev_alloc(ctx, &c->d_slot_ring, (size_t)vs_clip::kOutRing * c->capacity));
+    return VS_OK;
+}
+
+int vs_clip_upload_async(vs_clip* c, int slot0, int n, const uint8_t* bgr, int64_t row_stride, int64_t frame_stride)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, slot0 >= 0 && n >= 0 && slot0 + n <= c->capacity, "clip_upload_async: slot range out of bounds");
+    VS_REQUIRE(ctx, n == 0 || bgr, "clip_upload_async: source is NULL");
+    VS_REQUIRE(ctx, row_stride >= (int64_t)c->w * 3, "clip_upload_async: row_stride smaller than a row");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_TRY(ensure_async(c));
+    if (n == 0) return VS_OK;
+    // the slots being overwritten may still be read by compute enqueued earlier
+    VS_CUDA(ctx, cudaEventRecord(c->ev_compute, ctx->stream));
+    VS_CUDA(ctx, cudaStreamWaitEvent(c->up_stream, c->ev_compute, 0));
+    if (frame_stride == row_stride * c->h) {
+        VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)slot0 * c->bgr_slot_bytes, c->bgr_pitch, bgr, (size_t)row_stride,
+                                       (size_t)c->w * 3, (size_t)c->h * n, cudaMemcpyHostToDevice, c->up_stream));
+    } else {
+        for (int i = 0; i < n; i++)
+            VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)(slot0 + i) * c->bgr_slot_bytes, c->bgr_pitch,
+                                           bgr + (size_t)frame_stride * i, (size_t)row_stride, (size_t)c->w * 3, c->h,
+                                           cudaMemcpyHostToDevice, c->up_stream));
+    }
+    return VS_OK;
+}
+
+int vs_clip_wait_uploads(vs_clip* c)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    if (!c->up_stream) return VS_OK;
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaEventRecord(c->ev_upload, c->up_stream));
+    VS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_upload, 0));
+    return VS_OK;
+}
+
+int vs_clip_warp_to_host_async(vs_clip* c, const int32_t* slots, int n, const double* transforms, int mode, int border, int crop,
+                               uint8_t* out, int64_t out_frame_stride)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, n >= 0 && n <= c->capacity, "clip_warp_to_host_async: more frames than capacity");
+    if (n == 0) return VS_OK;
+    VS_REQUIRE(ctx, slots && transforms && out, "clip_warp_to_host_async: NULL pointer");
+    VS_REQUIRE(ctx, crop >= 0 && 2 * crop < c->w && 2 * crop < c->h, "clip_warp_to_host_async: crop too large");
+    const int ow = c->w - 2 * crop, oh = c->h - 2 * crop;
+    const size_t frame_bytes = (size_t)ow * oh * 3;
+    VS_REQUIRE(ctx, out_frame_stride >= (int64_t)frame_bytes, "clip_warp_to_host_async: out_frame_stride smaller than a frame");
+    for (int i = 0; i < n; i++) VS_REQUIRE(ctx, slots[i] >= 0 && slots[i] < c->capacity, "clip_warp_to_host_async: slot out of range");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_TRY(ensure_async(c));
+
+    const int b = c->out_ring_next;
+    c->out_ring_next = (b + 1) % vs_clip::kOutRing;
+    // this staging buffer (and its coefficient / slot arrays) may still be draining to the host
+    if (c->out_ring_used[b]) VS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_down[b], 0));
+    const size_t need = frame_bytes * n;
+    if (need > c->out_ring_bytes[b]) {
+        if (c->out_ring_used[b]) VS_CUDA(ctx, cudaEventSynchronize(c->ev_down[b]));
+        cudaFree(c->d_out_ring[b]); c->d_out_ring[b] = nullptr; c->out_ring_bytes[b] = 0;
+        VS_TRY(dev_alloc(ctx, &c->d_out_ring[b], need));
+        c->out_ring_bytes[b] = need;
+    }
+    std::vector<VsWarpCoef> coef(n);
+    for (int i = 0; i < n; i++) {
+        double M[6];
+        vs_forward_matrix_from_transform(transforms + 4 * i, c->w, c->h, M);
+        vs_warp_coef_from_forward(M, &coef[i]);
+    }
+    VsWarpCoef* d_coef = c->d_coef_ring + (size_t)b * c->capacity;
+    int32_t* d_slots = c->d_slot_ring + (size_t)b * c->capacity;
+    // pageable sources: both copies complete (staged) before the call returns
+    VS_CUDA(ctx, cudaMemcpyAsync(d_coef, coef.data(), (size_t)n * sizeof(VsWarpCoef), cudaMemcpyHostToDevice, ctx->stream));
+    VS_CUDA(ctx, cudaMemcpyAsync(d_slots, slots, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    VsDevImg src{c->d_bgr, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
+    VsDevImg dst{c->d_out_ring[b], ow, oh, (int64_t)ow * 3, n, (int64_t)frame_bytes};
+    VS_TRY(vsk_bgr_warp_slots(ctx, src, d_slots, d_coef, dst, crop, crop, mode, border));
+    VS_CUDA(ctx, cudaEventRecord(c->ev_warp[b], ctx->stream));
+    VS_CUDA(ctx, cudaStreamWaitEvent(c->down_stream, c->ev_warp[b], 0));
+    if (out_frame_stride == (int64_t)frame_bytes)
+        VS_CUDA(ctx, cudaMemcpyAsync(out, c->d_out_ring[b], need, cudaMemcpyDeviceToHost, c->down_stream));
+    else
+        VS_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)out_frame_stride, c->d_out_ring[b], frame_bytes, frame_bytes, n,
+                                       cudaMemcpyDeviceToHost, c->down_stream));
+    VS_CUDA(ctx, cudaEventRecord(c->ev_down[b], c->down_stream));
+    c->out_ring_used[b] = true;
+    return VS_OK;
+}
+
+int vs_clip_sync_transfers(vs_clip* c)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    if (!c->up_stream) return VS_OK;
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaStreamSynchronize(c->up_stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(c->down_stream));
     return VS_OK;
 }
 

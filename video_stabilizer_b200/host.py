@@ -61,6 +61,7 @@ SYMBOLS = {
     "vsh_clipstab_create": (_P, [_I, _I, _I, _I, _SP]),
     "vsh_clipstab_destroy": (None, [_P]),
     "vsh_clipstab_reset": (_I, [_P]),
+    "vsh_clipstab_set_pipeline_frames": (_I, [_P, _I]),
     "vsh_clipstab_feed": (_I, [_P, _P, _I, _I64, _I64, _I, _P, _I64, _I]),
     "vsh_clipstab_upload_only": (_I, [_P, _I64, _P, _I, _I64, _I64, _I]),
     "vsh_clipstab_feed_resident": (_I, [_P, _I, _P, _I64, _I]),
@@ -340,6 +341,9 @@ class ClipStabilizer(_Handle):
     def reset(self):
         if load().vsh_clipstab_reset(self.h) < 0:
             _raise("reset")
+
+    def set_pipeline_frames(self, frames: int):
+        load().vsh_clipstab_set_pipeline_frames(self.h, int(frames))
 
     def feed(self, frames: np.ndarray) -> np.ndarray:
         """frames: (n,h,w,3) u8 host array; returns the (k,oh,ow,3) stabilized frames that became due."""
