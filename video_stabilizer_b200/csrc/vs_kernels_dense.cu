@@ -437,79 +437,87 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
     const bool staged = (long long)pitch * nrows <= WT_SRC_ENTRIES;
 
     if (staged) {
-        // task / ngran == umulhi(task, magic) for task < 2^16 (ngran == 1 would overflow the magic number)
-        const uint32_t magic = ngran > 1 ? 0xffffffffu / (uint32_t)ngran + 1u : 0u;
+        // task = (row, 4-pixel granule); a thread takes tasks tid, tid + 128, ...  The (row, granule)
+        // pair advances incrementally (no division per task), all loads of a batch are issued before
+        // the first conversion, and each task remembers where its entries go.
+        const int dq = WT_THREADS % ngran, dr = WT_THREADS / ngran;
+        int r = tid / ngran, q = tid - r * ngran;
         for (int base = 0; base < ntask; base += WT_THREADS * WT_PREFETCH) {
             uint32_t wq[WT_PREFETCH][4];
-            bool fast[WT_PREFETCH];
+            int dstoff[WT_PREFETCH];                 // entry offset in S, or -1: no task, or ~offset: slow path
 #pragma unroll
             for (int k = 0; k < WT_PREFETCH; k++) {
                 const int task = base + k * WT_THREADS + tid;
-                const int r = ngran > 1 ? (int)__umulhi((uint32_t)task, magic) : task, q = task - r * ngran;
                 const int y = by0 + r, x = bx0 + 4 * q;
-                fast[k] = task < ntask && src_al4 && x >= 0 && x + 5 < w && y >= 0 && y < h;   // the 4th word ends inside the row
-                if (fast[k]) {
+                const int off = r * pitch + 4 * q;
+                const bool inside = (unsigned)y < (unsigned)h && x >= 0 && x + 5 < w;   // the 4th word ends inside the row
+                if (task >= ntask) {
+                    dstoff[k] = -1;
+                } else if (src_al4 && inside) {
                     const uint32_t* g = reinterpret_cast<const uint32_t*>(src + (size_t)y * src_stride + 3 * x);
                     wq[k][0] = __ldg(g); wq[k][1] = __ldg(g + 1); wq[k][2] = __ldg(g + 2); wq[k][3] = __ldg(g + 3);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < WT_PREFETCH; k++) {
-                const int task = base + k * WT_THREADS + tid;
-                if (task >= ntask) break;
-                const int r = ngran > 1 ? (int)__umulhi((uint32_t)task, magic) : task, q = task - r * ngran;
-                uint2 e0, e1, e2, e3;
-                if (fast[k]) {
-                    const uint32_t w0 = wq[k][0], w1 = wq[k][1], w2 = wq[k][2], w3 = wq[k][3];
-                    // stream bytes of pixel j start at 3j; entry j = (b[3j], b[3j+3], b[3j+1], b[3j+4]), (b[3j+2], b[3j+5])
-                    e0 = make_uint2(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x0052) & 0xffffu);
-                    e1 = make_uint2(__byte_perm(w0, w1, 0x7463), __byte_perm(w1, w2, 0x0041) & 0xffffu);
-                    e2 = make_uint2(__byte_perm(w1, w2, 0x6352), __byte_perm(w2, w2, 0x0030) & 0xffffu);
-                    e3 = make_uint2(__byte_perm(w2, w3, 0x5241), __byte_perm(w2, w3, 0x0063) & 0xffffu);
+                    dstoff[k] = off;
                 } else {
-                    const int y = by0 + r, x = bx0 + 4 * q;
+                    // border or unaligned source: texel by texel (clamped / zero-filled), converted right away
                     const uint32_t p0 = bgr_texel_word<BORDER>(src, src_stride, w, h, x, y);
                     const uint32_t p1 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 1, y);
                     const uint32_t p2 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 2, y);
                     const uint32_t p3 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 3, y);
                     const uint32_t p4 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 4, y);
-                    e0 = wt_entry(p0, p1); e1 = wt_entry(p1, p2); e2 = wt_entry(p2, p3); e3 = wt_entry(p3, p4);
+                    const uint2 e0 = wt_entry(p0, p1), e1 = wt_entry(p1, p2), e2 = wt_entry(p2, p3), e3 = wt_entry(p3, p4);
+                    uint4* d = reinterpret_cast<uint4*>(S + off);
+                    d[0] = make_uint4(e0.x, e0.y, e1.x, e1.y);
+                    d[1] = make_uint4(e2.x, e2.y, e3.x, e3.y);
+                    dstoff[k] = -1;
                 }
-                uint4* d = reinterpret_cast<uint4*>(S + (size_t)r * pitch + 4 * q);
-                d[0] = make_uint4(e0.x, e0.y, e1.x, e1.y);
-                d[1] = make_uint4(e2.x, e2.y, e3.x, e3.y);
+                q += dq; r += dr;
+                if (q >= ngran) { q -= ngran; r++; }
+            }
+#pragma unroll
+            for (int k = 0; k < WT_PREFETCH; k++) {
+                if (dstoff[k] < 0) continue;
+                const uint32_t w0 = wq[k][0], w1 = wq[k][1], w2 = wq[k][2], w3 = wq[k][3];
+                // stream bytes of pixel j start at 3j; entry j = (b[3j], b[3j+3], b[3j+1], b[3j+4]), (b[3j+2], b[3j+5])
+                uint4* d = reinterpret_cast<uint4*>(S + dstoff[k]);
+                d[0] = make_uint4(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x0052) & 0xffffu,
+                                  __byte_perm(w0, w1, 0x7463), __byte_perm(w1, w2, 0x0041) & 0xffffu);
+                d[1] = make_uint4(__byte_perm(w1, w2, 0x6352), __byte_perm(w2, w2, 0x0030) & 0xffffu,
+                                  __byte_perm(w2, w3, 0x5241), __byte_perm(w2, w3, 0x0063) & 0xffffu);
             }
         }
         __syncthreads();
     }
 
-    {
-        // every thread runs the loop (columns beyond the tile edge repeat the last column) so the
-        // warp shuffles below are always executed by full warps
+    // every thread runs the loops below (columns beyond the tile edge repeat the last column) so the
+    // warp shuffles are always executed by full warps
+    const int k4 = tid & 3;
+    // lane 4j+k (k<3) assembles packed word k of the 12 bytes of pixels 4j..4j+3 from its own
+    // BGRX word and its right neighbour's: B0G0R0B1 | G1R1B2G2 | R2B3G3R3
+    const uint32_t sel = k4 == 0 ? 0x4210u : (k4 == 1 ? 0x5421u : 0x6542u);
+    uint32_t* const Orow = O + 3 * (tid >> 2) + k4;
+    if (staged) {
         const uint2* const Sorg = S + (-by0 * pitch - bx0);
-        const int k4 = tid & 3;
-        // lane 4j+k (k<3) assembles packed word k of the 12 bytes of pixels 4j..4j+3 from its own
-        // BGRX word and its right neighbour's: B0G0R0B1 | G1R1B2G2 | R2B3G3R3
-        const uint32_t sel = k4 == 0 ? 0x4210u : (k4 == 1 ? 0x5421u : 0x6542u);
-        uint32_t* const Orow = O + 3 * (tid >> 2) + k4;
 #pragma unroll 4
         for (int r = 0; r < WT_H; r++) {
             if (r >= th) break;
             const int2 xy0 = sXY0[r];
             const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
+            const int fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
+            const uint2* p = Sorg + ((sfy >> 10) * pitch + (sfx >> 10));
+            const uint32_t px = cv_blend(p[0], p[pitch], fx, fy);
+            const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
+            if (k4 < 3) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
+        }
+    } else {
+        for (int r = 0; r < th; r++) {
+            const int2 xy0 = sXY0[r];
+            const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
             const int sx = sfx >> 10, sy = sfy >> 10, fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
-            uint2 top, bot;
-            if (staged) {
-                const uint2* p = Sorg + (sy * pitch + sx);
-                top = p[0]; bot = p[pitch];
-            } else {
-                const uint32_t t00 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx, sy);
-                const uint32_t t10 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx + 1, sy);
-                const uint32_t t01 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx, sy + 1);
-                const uint32_t t11 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx + 1, sy + 1);
-                top = wt_entry(t00, t10); bot = wt_entry(t01, t11);
-            }
-            const uint32_t px = cv_blend(top, bot, fx, fy);
+            const uint32_t t00 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx, sy);
+            const uint32_t t10 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx + 1, sy);
+            const uint32_t t01 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx, sy + 1);
+            const uint32_t t11 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx + 1, sy + 1);
+            const uint32_t px = cv_blend(wt_entry(t00, t10), wt_entry(t01, t11), fx, fy);
             const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
             if (k4 < 3) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
         }
@@ -518,7 +526,14 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
 
     // write the tile: 16-byte vectors when the destination rows allow it
     const int row_bytes = tw * 3;
-    if (dst_al16 && (row_bytes & 15) == 0) {
+    if (dst_al16 && tw == WT_W) {
+        constexpr int VPR = WT_W * 3 / 16;            // 24 vectors per full row
+        uint8_t* const drow0 = dst + (size_t)oy0 * dst_stride + (size_t)ox0 * 3;
+        for (int i = tid; i < th * VPR; i += WT_THREADS) {
+            const int r = i / VPR, v = i - r * VPR;
+            *(reinterpret_cast<uint4*>(drow0 + (size_t)r * dst_stride) + v) = *reinterpret_cast<const uint4*>(O + r * WT_OUT_ROW_WORDS + 4 * v);
+        }
+    } else if (dst_al16 && (row_bytes & 15) == 0) {
         const int vec_per_row = row_bytes >> 4;
         for (int i = tid; i < th * vec_per_row; i += WT_THREADS) {
             const int r = i / vec_per_row, v = i - r * vec_per_row;

@@ -539,7 +539,7 @@ __device__ __forceinline__ double dist2d(const double* a, const double* b)
     return sqrt(dx * dx + dy * dy);
 }
 
-__global__ void __launch_bounds__(SOLVE_THREADS)
+__global__ void __launch_bounds__(SOLVE_THREADS, 3)
 k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 {
     extern __shared__ uint32_t dyn_keys[];   // keys[2][max_tiles]: abs_delta << 16 | tile, then (optionally) pos[2][2*max_tiles] u16
