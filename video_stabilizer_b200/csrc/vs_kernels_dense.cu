@@ -337,28 +337,32 @@ k_bgr_warp(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src
 
 // ------------------------------------------------------------------ BGR warp, cv-exact, tiled
 // The production form of mode 0 (the warp VideoStabilizer runs on every output frame).
-// A CTA of 128 threads produces a 128 x 16 pixel output tile:
+// A CTA of 128 threads produces a 120 x 16 pixel output tile (120 px = 360 B = 45 8-byte
+// stores per row; 1920 and 3840 are multiples of 120; the source box of a tile is then at
+// most 32 four-pixel granules wide, one per lane):
 //   1. thread t owns output column t: its two column terms adelta/bdelta (the only f64 work)
 //      are computed once and reused for the 16 rows; the 16 row terms X0/Y0 go to shared memory.
 //   2. the source bounding box of the tile follows from its four corners (the fixed-point
-//      map is a sum of a monotone function of x and a monotone function of y).  It is staged
-//      in shared memory with coalesced 32-bit loads (all of a thread's loads are issued before
-//      the first is consumed) as one 8-byte entry per source pixel x:
+//      map is a sum of a monotone function of x and a monotone function of y).  Warp w stages
+//      box rows w, w+4, ...: lane l loads the 12 bytes of granule l (+4 bytes of look-ahead) of
+//      each of its rows with 32-bit loads, all issued before the first is consumed, and writes
+//      one 8-byte entry per source pixel x:
 //          .x = (B[x], B[x+1], G[x], G[x+1])      .y = (R[x], R[x+1], 0, 0)
 //      i.e. the two horizontal taps of every channel sit in adjacent bytes.  Texels outside
 //      the image are staged as the border value (0, or the clamped edge texel), so sampling
 //      needs no border logic.
 //   3. a pixel is then two conflict-free 8-byte shared loads (top and bottom row) and six
 //      IDP.2A dot products against the packed 16-bit weight pairs (w00|w10<<16, w01|w11<<16);
-//      results are collected in a shared tile and written out as 16-byte vectors.
+//      four lanes' pixels are packed into 12 bytes with one shuffle + PRMT per lane and
+//      collected in a shared tile that is written out with 8-byte stores.
 // A tile whose bounding box does not fit (large rotations or scales) takes the direct
 // global-memory path, decided per CTA.
-constexpr int WT_W = 128, WT_H = 16, WT_THREADS = 128;
-constexpr int WT_SRC_ENTRIES = 2560;                     // staged source capacity (20 KB): (128+8) x 18 fits
-constexpr int WT_OUT_ROW_WORDS = WT_W * 3 / 4;           // packed BGR bytes of one output row
-constexpr int WT_OUT_WORDS = WT_OUT_ROW_WORDS * WT_H;    // 6 KB
+constexpr int WT_W = 120, WT_H = 16, WT_THREADS = 128, WT_WARPS = WT_THREADS / 32;
+constexpr int WT_SRC_ENTRIES = 2560;                     // staged source capacity (20 KB): 32 granules x 20 rows
+constexpr int WT_OUT_ROW_WORDS = WT_W * 3 / 4;           // 90 words: packed BGR bytes of one output row
+constexpr int WT_OUT_WORDS = WT_OUT_ROW_WORDS * WT_H;    // 5.6 KB
 constexpr int WT_SMEM_BYTES = WT_SRC_ENTRIES * 8 + WT_OUT_WORDS * 4;
-constexpr int WT_PREFETCH = 5;                           // staging tasks per thread kept in flight
+constexpr int WT_ROWS_PER_WARP = 5;                      // staged rows per warp kept in flight (covers 20 rows)
 
 template <int BORDER>
 __device__ __forceinline__ uint32_t bgr_texel_word(const uint8_t* __restrict__ src, int64_t stride, int w, int h, int x, int y)
@@ -395,14 +399,17 @@ __global__ void __launch_bounds__(WT_THREADS)
 k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
                     const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
                     uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
-                    int dst_x0, int dst_y0, int src_al4, int dst_al16)
+                    int dst_x0, int dst_y0, int src_al4, int dst_al8)
 {
     extern __shared__ __align__(16) uint32_t wt_smem[];
-    uint2* const S = reinterpret_cast<uint2*>(wt_smem);
+    // staged entries as two planes (SX: .x words, SY: .y words): a lane's four entries are then 16
+    // contiguous bytes per plane, so the staging stores of a warp are conflict-free
+    uint32_t* const SX = wt_smem;
+    uint32_t* const SY = wt_smem + WT_SRC_ENTRIES;
     uint32_t* const O = wt_smem + WT_SRC_ENTRIES * 2;
     __shared__ int2 sXY0[WT_H];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const int ox0 = blockIdx.x * WT_W, oy0 = blockIdx.y * WT_H;
     const int tw = min(WT_W, dw - ox0), th = min(WT_H, dh - oy0);
@@ -422,67 +429,73 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
     }
     __syncthreads();
 
-    // source bounding box from the four corners (each term is monotone in its variable)
-    const int xl = ox0 + dst_x0, xr = ox0 + tw - 1 + dst_x0;
-    const int aL = __double2int_rn(cf.i00 * (double)xl * 1024.0), aR = __double2int_rn(cf.i00 * (double)xr * 1024.0);
-    const int bL = __double2int_rn(cf.i10 * (double)xl * 1024.0), bR = __double2int_rn(cf.i10 * (double)xr * 1024.0);
-    const int X0t = sXY0[0].x, X0b = sXY0[th - 1].x, Y0t = sXY0[0].y, Y0b = sXY0[th - 1].y;
-    const int sxmin = (min(X0t, X0b) + min(aL, aR)) >> 10, sxmax = (max(X0t, X0b) + max(aL, aR)) >> 10;
-    const int symin = (min(Y0t, Y0b) + min(bL, bR)) >> 10, symax = (max(Y0t, Y0b) + max(bL, bR)) >> 10;
+    // source bounding box from the four corners (each term is monotone in its variable): the
+    // column terms of the first and last column are those of threads 0 and tw-1
+    const int xr = ox0 + tw - 1 + dst_x0;
+    const int aL = __shfl_sync(0xffffffffu, adelta, 0), bL = __shfl_sync(0xffffffffu, bdelta, 0);
+    const int aL0 = warp == 0 ? aL : __double2int_rn(cf.i00 * (double)(ox0 + dst_x0) * 1024.0);
+    const int bL0 = warp == 0 ? bL : __double2int_rn(cf.i10 * (double)(ox0 + dst_x0) * 1024.0);
+    const int aR = __double2int_rn(cf.i00 * (double)xr * 1024.0), bR = __double2int_rn(cf.i10 * (double)xr * 1024.0);
+    const int2 xyT = sXY0[0], xyB = sXY0[th - 1];
+    const int sxmin = (min(xyT.x, xyB.x) + min(aL0, aR)) >> 10, sxmax = (max(xyT.x, xyB.x) + max(aL0, aR)) >> 10;
+    const int symin = (min(xyT.y, xyB.y) + min(bL0, bR)) >> 10, symax = (max(xyT.y, xyB.y) + max(bL0, bR)) >> 10;
     const int bx0 = (sxmin >> 2) * 4;                            // 4-pixel (12-byte, 3-word) staging granules
     const int ngran = ((sxmax - bx0) >> 2) + 1;                  // entries bx0 .. sxmax (entry x also carries x+1)
     const int pitch = ngran * 4;                                 // entries per staged row
     const int by0 = symin, nrows = symax + 1 - symin + 1;
-    const int ntask = nrows * ngran;
-    const bool staged = (long long)pitch * nrows <= WT_SRC_ENTRIES;
+    const bool staged = pitch * nrows <= WT_SRC_ENTRIES && nrows <= 4096;
 
     if (staged) {
-        // task = (row, 4-pixel granule); a thread takes tasks tid, tid + 128, ...  The (row, granule)
-        // pair advances incrementally (no division per task), all loads of a batch are issued before
-        // the first conversion, and each task remembers where its entries go.
-        const int dq = WT_THREADS % ngran, dr = WT_THREADS / ngran;
-        int r = tid / ngran, q = tid - r * ngran;
-        for (int base = 0; base < ntask; base += WT_THREADS * WT_PREFETCH) {
-            uint32_t wq[WT_PREFETCH][4];
-            int dstoff[WT_PREFETCH];                 // entry offset in S, or -1: no task, or ~offset: slow path
+        // rows of the box inside the image: by0 + r in [0, h)  <=>  r - rlo < rspan (unsigned)
+        const int rlo = -by0;
+        const unsigned rspan = (unsigned)h;
+        for (int q = lane; q < ngran; q += 32) {
+            const int x = bx0 + 4 * q;
+            const bool xfast = src_al4 && x >= 0 && x + 5 < w;   // the 4th word ends inside the row
+            for (int r0 = warp; r0 < nrows; r0 += WT_WARPS * WT_ROWS_PER_WARP) {
+                uint32_t wq[WT_ROWS_PER_WARP][4];
+                // one pointer and one shared-memory offset, advanced by 4 rows per step
+                const uint8_t* g = src + (ptrdiff_t)(by0 + r0) * src_stride + 3 * x;
+                const ptrdiff_t gstep = (ptrdiff_t)WT_WARPS * src_stride;
 #pragma unroll
-            for (int k = 0; k < WT_PREFETCH; k++) {
-                const int task = base + k * WT_THREADS + tid;
-                const int y = by0 + r, x = bx0 + 4 * q;
-                const int off = r * pitch + 4 * q;
-                const bool inside = (unsigned)y < (unsigned)h && x >= 0 && x + 5 < w;   // the 4th word ends inside the row
-                if (task >= ntask) {
-                    dstoff[k] = -1;
-                } else if (src_al4 && inside) {
-                    const uint32_t* g = reinterpret_cast<const uint32_t*>(src + (size_t)y * src_stride + 3 * x);
-                    wq[k][0] = __ldg(g); wq[k][1] = __ldg(g + 1); wq[k][2] = __ldg(g + 2); wq[k][3] = __ldg(g + 3);
-                    dstoff[k] = off;
-                } else {
-                    // border or unaligned source: texel by texel (clamped / zero-filled), converted right away
-                    const uint32_t p0 = bgr_texel_word<BORDER>(src, src_stride, w, h, x, y);
-                    const uint32_t p1 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 1, y);
-                    const uint32_t p2 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 2, y);
-                    const uint32_t p3 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 3, y);
-                    const uint32_t p4 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 4, y);
-                    const uint2 e0 = wt_entry(p0, p1), e1 = wt_entry(p1, p2), e2 = wt_entry(p2, p3), e3 = wt_entry(p3, p4);
-                    uint4* d = reinterpret_cast<uint4*>(S + off);
-                    d[0] = make_uint4(e0.x, e0.y, e1.x, e1.y);
-                    d[1] = make_uint4(e2.x, e2.y, e3.x, e3.y);
-                    dstoff[k] = -1;
+                for (int k = 0; k < WT_ROWS_PER_WARP; k++) {
+                    const int r = r0 + k * WT_WARPS;
+                    if (xfast && r < nrows && (unsigned)(r - rlo) < rspan) {
+                        const uint32_t* gw = reinterpret_cast<const uint32_t*>(g);
+                        wq[k][0] = __ldg(gw); wq[k][1] = __ldg(gw + 1); wq[k][2] = __ldg(gw + 2); wq[k][3] = __ldg(gw + 3);
+                    }
+                    g += gstep;
                 }
-                q += dq; r += dr;
-                if (q >= ngran) { q -= ngran; r++; }
-            }
+                int off = r0 * pitch + 4 * q;
 #pragma unroll
-            for (int k = 0; k < WT_PREFETCH; k++) {
-                if (dstoff[k] < 0) continue;
-                const uint32_t w0 = wq[k][0], w1 = wq[k][1], w2 = wq[k][2], w3 = wq[k][3];
-                // stream bytes of pixel j start at 3j; entry j = (b[3j], b[3j+3], b[3j+1], b[3j+4]), (b[3j+2], b[3j+5])
-                uint4* d = reinterpret_cast<uint4*>(S + dstoff[k]);
-                d[0] = make_uint4(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x0052) & 0xffffu,
-                                  __byte_perm(w0, w1, 0x7463), __byte_perm(w1, w2, 0x0041) & 0xffffu);
-                d[1] = make_uint4(__byte_perm(w1, w2, 0x6352), __byte_perm(w2, w2, 0x0030) & 0xffffu,
-                                  __byte_perm(w2, w3, 0x5241), __byte_perm(w2, w3, 0x0063) & 0xffffu);
+                for (int k = 0; k < WT_ROWS_PER_WARP; k++) {
+                    const int r = r0 + k * WT_WARPS;
+                    if (r >= nrows) break;
+                    uint4 ex, ey;
+                    if (xfast && (unsigned)(r - rlo) < rspan) {
+                        const uint32_t w0 = wq[k][0], w1 = wq[k][1], w2 = wq[k][2], w3 = wq[k][3];
+                        // stream bytes of pixel j start at 3j; entry j = (b[3j], b[3j+3], b[3j+1], b[3j+4]), (b[3j+2], b[3j+5]);
+                        // the .y words keep two don't-care upper bytes: IDP.2A.LO only reads the lower two
+                        ex = make_uint4(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x7463),
+                                        __byte_perm(w1, w2, 0x6352), __byte_perm(w2, w3, 0x5241));
+                        ey = make_uint4(__byte_perm(w0, w1, 0x0052), __byte_perm(w1, w2, 0x0041),
+                                        __byte_perm(w2, w2, 0x0030), __byte_perm(w2, w3, 0x0063));
+                    } else {
+                        // border or unaligned source: texel by texel (clamped / zero-filled)
+                        const int y = by0 + r;
+                        const uint32_t p0 = bgr_texel_word<BORDER>(src, src_stride, w, h, x, y);
+                        const uint32_t p1 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 1, y);
+                        const uint32_t p2 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 2, y);
+                        const uint32_t p3 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 3, y);
+                        const uint32_t p4 = bgr_texel_word<BORDER>(src, src_stride, w, h, x + 4, y);
+                        const uint2 e0 = wt_entry(p0, p1), e1 = wt_entry(p1, p2), e2 = wt_entry(p2, p3), e3 = wt_entry(p3, p4);
+                        ex = make_uint4(e0.x, e1.x, e2.x, e3.x);
+                        ey = make_uint4(e0.y, e1.y, e2.y, e3.y);
+                    }
+                    *reinterpret_cast<uint4*>(SX + off) = ex;
+                    *reinterpret_cast<uint4*>(SY + off) = ey;
+                    off += WT_WARPS * pitch;
+                }
             }
         }
         __syncthreads();
@@ -495,18 +508,19 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
     // BGRX word and its right neighbour's: B0G0R0B1 | G1R1B2G2 | R2B3G3R3
     const uint32_t sel = k4 == 0 ? 0x4210u : (k4 == 1 ? 0x5421u : 0x6542u);
     uint32_t* const Orow = O + 3 * (tid >> 2) + k4;
+    const bool keep = k4 < 3 && tid < WT_W;
     if (staged) {
-        const uint2* const Sorg = S + (-by0 * pitch - bx0);
+        const int sorg = -by0 * pitch - bx0;
 #pragma unroll 4
         for (int r = 0; r < WT_H; r++) {
             if (r >= th) break;
             const int2 xy0 = sXY0[r];
             const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
             const int fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
-            const uint2* p = Sorg + ((sfy >> 10) * pitch + (sfx >> 10));
-            const uint32_t px = cv_blend(p[0], p[pitch], fx, fy);
+            const int e = sorg + (sfy >> 10) * pitch + (sfx >> 10);
+            const uint32_t px = cv_blend(make_uint2(SX[e], SY[e]), make_uint2(SX[e + pitch], SY[e + pitch]), fx, fy);
             const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
-            if (k4 < 3) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
+            if (keep) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
         }
     } else {
         for (int r = 0; r < th; r++) {
@@ -519,32 +533,30 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
             const uint32_t t11 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx + 1, sy + 1);
             const uint32_t px = cv_blend(wt_entry(t00, t10), wt_entry(t01, t11), fx, fy);
             const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
-            if (k4 < 3) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
+            if (keep) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
         }
     }
     __syncthreads();
 
-    // write the tile: 16-byte vectors when the destination rows allow it
+    // write the tile: 8-byte vectors when the destination rows allow it.  A full row is 45 of them:
+    // warp w writes rows w, w+4, ... with lanes 0..31 and then lanes 0..12
     const int row_bytes = tw * 3;
-    if (dst_al16 && tw == WT_W) {
-        constexpr int VPR = WT_W * 3 / 16;            // 24 vectors per full row
-        uint8_t* const drow0 = dst + (size_t)oy0 * dst_stride + (size_t)ox0 * 3;
-        for (int i = tid; i < th * VPR; i += WT_THREADS) {
-            const int r = i / VPR, v = i - r * VPR;
-            *(reinterpret_cast<uint4*>(drow0 + (size_t)r * dst_stride) + v) = *reinterpret_cast<const uint4*>(O + r * WT_OUT_ROW_WORDS + 4 * v);
-        }
-    } else if (dst_al16 && (row_bytes & 15) == 0) {
-        const int vec_per_row = row_bytes >> 4;
-        for (int i = tid; i < th * vec_per_row; i += WT_THREADS) {
-            const int r = i / vec_per_row, v = i - r * vec_per_row;
-            const uint4 val = *reinterpret_cast<const uint4*>(O + r * WT_OUT_ROW_WORDS + 4 * v);
-            *(reinterpret_cast<uint4*>(dst + (size_t)(oy0 + r) * dst_stride + (size_t)ox0 * 3) + v) = val;
+    uint8_t* const drow0 = dst + (size_t)oy0 * dst_stride + (size_t)ox0 * 3;
+    if (dst_al8 && tw == WT_W) {
+        constexpr int VPR = WT_W * 3 / 8;
+        uint2* d = reinterpret_cast<uint2*>(drow0 + (size_t)warp * dst_stride) + lane;
+        const uint2* o = reinterpret_cast<const uint2*>(O + warp * WT_OUT_ROW_WORDS) + lane;
+        for (int r = warp; r < th; r += WT_WARPS) {
+            d[0] = o[0];
+            if (lane < VPR - 32) d[32] = o[32];
+            d = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(d) + (size_t)WT_WARPS * dst_stride);
+            o += WT_WARPS * WT_OUT_ROW_WORDS / 2;
         }
     } else {
         const uint8_t* Ob = reinterpret_cast<const uint8_t*>(O);
         for (int i = tid; i < th * row_bytes; i += WT_THREADS) {
             const int r = i / row_bytes, c = i - r * row_bytes;
-            dst[(size_t)(oy0 + r) * dst_stride + (size_t)ox0 * 3 + c] = Ob[r * (WT_OUT_ROW_WORDS * 4) + c];
+            drow0[(size_t)r * dst_stride + c] = Ob[r * (WT_OUT_ROW_WORDS * 4) + c];
         }
     }
 }
@@ -670,17 +682,17 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
         else
             VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tiled<VS_BORDER_CONSTANT0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
         const int src_al4 = aligned_to(src.data, 4) && src.stride % 4 == 0 && src.batch_stride % 4 == 0;
-        const int dst_al16 = aligned_to(dst.data, 16) && dst.stride % 16 == 0 && dst.batch_stride % 16 == 0;
+        const int dst_al8 = aligned_to(dst.data, 8) && dst.stride % 8 == 0 && dst.batch_stride % 8 == 0;
         dim3 tgrid(vs_cdiv(dst.w, WT_W), vs_cdiv(dst.h, WT_H), dst.batch);
         VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
         if (border == VS_BORDER_REPEAT_EDGE)
             k_bgr_warp_cv_tiled<VS_BORDER_REPEAT_EDGE><<<tgrid, WT_THREADS, WT_SMEM_BYTES, ctx->stream>>>(
                 (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
-                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al16);
+                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al8);
         else
             k_bgr_warp_cv_tiled<VS_BORDER_CONSTANT0><<<tgrid, WT_THREADS, WT_SMEM_BYTES, ctx->stream>>>(
                 (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
-                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al16);
+                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al8);
         VS_LAUNCH_CHECK(ctx);
         return VS_OK;
     }
