@@ -150,3 +150,39 @@ def test_synth_gpu_renderer_is_bit_identical_to_numpy(gpu):
     a, pa = synth.make_clip_numpy(320, 180, 3, 4)
     b, pb = synth.make_clip_gpu(gpu, 320, 180, 3, 4)
     assert np.array_equal(pa, pb) and np.array_equal(a, b)
+
+
+def test_frame_chunk_partition_equals_single_run(gpu):
+    """A video split into even-aligned chunks with a one-frame halo (one chunk per GPU in
+    production; here the chunks run one after the other on one device) gives bit-identical
+    transforms to the single run: pairs are independent and the keyframe parity is global."""
+    from video_stabilizer_b200 import _capi as capi
+    from video_stabilizer_b200 import partition, synth
+    from video_stabilizer_b200.clip import Clip, pairs_for_frames
+    w, h, n = 320, 180, 21
+    frames, _ = synth.make_clip_numpy(w, h, n, 13)
+    clip = Clip(w, h, n, ctx=gpu)
+    clip.upload(0, frames)
+    clip.build_pyramids(0, n)
+    pairs, keys = pairs_for_frames(0, n)
+    clip.build_keyframes(keys)
+    T_all, st_all, it_all = clip.align(pairs)
+    clip.close()
+    for world in (2, 3):
+        T_parts, st_parts = [], []
+        for rank, chunk in enumerate(partition.frame_chunks(n, world)):
+            up0, up1 = partition.chunk_upload_range(chunk, rank)
+            plist, kslots = partition.chunk_pairs(chunk, rank)
+            if not plist:
+                continue
+            c = Clip(w, h, up1 - up0, ctx=gpu)
+            c.upload(0, frames[up0:up1])
+            c.build_pyramids(0, up1 - up0)
+            c.build_keyframes(kslots)
+            arr = (capi.VsPair * len(plist))(*[capi.VsPair(*p) for p in plist])
+            T, st, _ = c.align(arr)
+            T_parts.append(T)
+            st_parts.append(st)
+            c.close()
+        assert np.array_equal(np.concatenate(T_parts), T_all)
+        assert np.array_equal(np.concatenate(st_parts), st_all)
