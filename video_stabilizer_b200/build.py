@@ -80,6 +80,27 @@ def build_host(force: bool = False) -> str | None:
     return LIB_HOST
 
 
+def build_tools(force: bool = False) -> list[str]:
+    """align_test / video_test: the reference's driver programs rebuilt against the drop-in
+    host library, from the public headers only."""
+    host_dir = os.path.join(CSRC, "host")
+    tools_dir = os.path.join(host_dir, "tools")
+    bin_dir = os.path.join(PKG_DIR, "bin")
+    os.makedirs(bin_dir, exist_ok=True)
+    outs = []
+    cxx = shutil.which("g++") or "g++"
+    for name in ("align_test", "video_test"):
+        src = os.path.join(tools_dir, name + ".cpp")
+        out = os.path.join(bin_dir, name)
+        deps = [src, LIB_HOST, LIB_CUDA] + glob.glob(os.path.join(tools_dir, "*.hpp")) + glob.glob(os.path.join(host_dir, "*.hpp"))
+        if force or not _newer(out, deps):
+            _run([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-pthread", "-I", INCLUDE, "-I", host_dir, "-I", tools_dir,
+                  "-idirafter", os.path.join(INCLUDE, "compat"), "-o", out, src,
+                  "-L", PKG_DIR, "-lvstab_host", "-lvstab", "-Wl,-rpath,$ORIGIN/.."])
+        outs.append(out)
+    return outs
+
+
 def build_oracle() -> None:
     _run(["make", "-s", "-C", os.path.join(REPO, "oracle")])
     if os.path.isdir("/root/reference") and os.path.exists(os.path.join(REPO, "oracle", "ref_shim")):
@@ -89,6 +110,7 @@ def build_oracle() -> None:
 def build_all(force: bool = False) -> None:
     build_cuda(force)
     build_host(force)
+    build_tools(force)
     build_oracle()
 
 
