@@ -186,3 +186,12 @@ def test_frame_chunk_partition_equals_single_run(gpu):
             c.close()
         assert np.array_equal(np.concatenate(T_parts), T_all)
         assert np.array_equal(np.concatenate(st_parts), st_all)
+
+
+def test_clip_alignment_4k(gpu, ob):
+    """BASELINE.json configs[2] shape: 3840x2160, 7 pyramid levels, 20736 tiles at L0 — the
+    selection's candidate lists no longer fit in shared memory and come from global scratch."""
+    from video_stabilizer_b200 import synth
+    frames, poses = synth.make_clip_gpu(gpu, 3840, 2160, 3, 17)
+    worst, T, status, ref = check_clip_against_oracle(gpu, ob, frames, deep=False)
+    assert status.all() and worst < 1e-6
