@@ -12,14 +12,18 @@ import subprocess
 import sys
 
 
-def launches(path):
+def launches(path, skip=0, count=None):
     rows = [r for r in csv.reader(open(path)) if len(r) > 5]
     hdr, agg = None, collections.OrderedDict()
+    seen = 0
     for r in rows:
         if r[0] == "ID":
             hdr = r
             continue
         if hdr is None:
+            continue
+        seen += 1
+        if seen <= skip or (count is not None and seen > skip + count):
             continue
         d = dict(zip(hdr, r))
         v = float(d["Metric Value"].replace(",", ""))
@@ -70,7 +74,9 @@ def full(path, traffic_json=None):
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
-        launches(sys.argv[2])
+        skip = int(sys.argv[sys.argv.index("--skip") + 1]) if "--skip" in sys.argv else 0
+        count = int(sys.argv[sys.argv.index("--count") + 1]) if "--count" in sys.argv else None
+        launches(sys.argv[2], skip, count)
     else:
         tj = sys.argv[sys.argv.index("--traffic-json") + 1] if "--traffic-json" in sys.argv else None
         full(sys.argv[2], tj)
