@@ -4,6 +4,7 @@
 #include "vs_internal.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -62,7 +63,7 @@ k_bgr2gray(const uint8_t* __restrict__ bgr, int64_t in_stride, int64_t in_bs,
 // sums <= 65280: no carry between lanes).  The truncating >> 8 and the packing of the four
 // output bytes are one PRMT.  No shared memory, no barriers; the 3-row halo of a strip is
 // re-read from L1/L2.
-constexpr int PD_ROWS = 8;
+constexpr int PD_ROWS_DEFAULT = 8;
 
 // horizontal sums of outputs x..x+3 (x = first output column) from
 //   a16 = in[2x-2], in[2x-1] (low two bytes)   b = in[2x .. 2x+7]   c8 = in[2x+8]
@@ -100,15 +101,35 @@ __device__ __forceinline__ void pd_load_row(const uint8_t* __restrict__ src, int
     pd_hsum(a16, b, c8, h01, h23);
 }
 
-template <bool FAST>
+template <bool FAST, int PD_ROWS, bool FULL>
 __device__ __forceinline__ void pd_strip(const uint8_t* __restrict__ src, int64_t in_stride, int iw, int ih,
                                          uint8_t* __restrict__ dst, int64_t out_stride, int ow, int oh, int x4, int y0, bool store_word)
 {
+    // FULL strips (all PD_ROWS outputs exist) have no exit inside the unrolled loop, so the loads of
+    // all 2*PD_ROWS+3 input rows can be scheduled ahead of the arithmetic: that memory-level
+    // parallelism is what a latency-bound streaming kernel lives on
+    uint32_t h01[2 * PD_ROWS + 3], h23[2 * PD_ROWS + 3];
+    if (FULL) {
+#pragma unroll
+        for (int j = 0; j < 2 * PD_ROWS + 3; j++) pd_load_row<FAST>(src, in_stride, iw, ih, 2 * y0 - 2 + j, x4, h01[j], h23[j]);
+#pragma unroll
+        for (int i = 0; i < PD_ROWS; i++) {
+            const uint32_t v01 = h01[2 * i] + h01[2 * i + 4] + 4u * (h01[2 * i + 1] + h01[2 * i + 3]) + 6u * h01[2 * i + 2];
+            const uint32_t v23 = h23[2 * i] + h23[2 * i + 4] + 4u * (h23[2 * i + 1] + h23[2 * i + 3]) + 6u * h23[2 * i + 2];
+            const uint32_t packed = __byte_perm(v01, v23, 0x7531);   // (v >> 8) of the four 16-bit lanes
+            uint8_t* o = dst + (size_t)(y0 + i) * out_stride + x4;
+            if (store_word) {
+                *reinterpret_cast<uint32_t*>(o) = packed;
+            } else {
+                for (int k = 0; k < 4 && x4 + k < ow; k++) o[k] = (uint8_t)(packed >> (8 * k));
+            }
+        }
+        return;
+    }
     uint32_t a01, a23, b01, b23, c01, c23;
     pd_load_row<FAST>(src, in_stride, iw, ih, 2 * y0 - 2, x4, a01, a23);
     pd_load_row<FAST>(src, in_stride, iw, ih, 2 * y0 - 1, x4, b01, b23);
     pd_load_row<FAST>(src, in_stride, iw, ih, 2 * y0, x4, c01, c23);
-#pragma unroll
     for (int i = 0; i < PD_ROWS; i++) {
         const int y = y0 + i;
         if (y >= oh) break;
@@ -117,7 +138,7 @@ __device__ __forceinline__ void pd_strip(const uint8_t* __restrict__ src, int64_
         pd_load_row<FAST>(src, in_stride, iw, ih, 2 * y + 2, x4, e01, e23);
         const uint32_t v01 = a01 + e01 + 4u * (b01 + d01) + 6u * c01;
         const uint32_t v23 = a23 + e23 + 4u * (b23 + d23) + 6u * c23;
-        const uint32_t packed = __byte_perm(v01, v23, 0x7531);   // (v >> 8) of the four 16-bit lanes
+        const uint32_t packed = __byte_perm(v01, v23, 0x7531);
         uint8_t* o = dst + (size_t)y * out_stride + x4;
         if (store_word) {
             *reinterpret_cast<uint32_t*>(o) = packed;
@@ -128,20 +149,24 @@ __device__ __forceinline__ void pd_strip(const uint8_t* __restrict__ src, int64_
     }
 }
 
-__global__ void __launch_bounds__(128)
+template <int PD_ROWS, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_pyr_down(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, int iw, int ih,
            uint8_t* __restrict__ out, int64_t out_stride, int64_t out_bs, int ow, int oh, int in_al8, int out_al4)
 {
-    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y0 = (blockIdx.y * 4 + threadIdx.y) * PD_ROWS;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * PD_ROWS;
     if (x4 >= ow || y0 >= oh) return;
     const uint8_t* src = in + (size_t)blockIdx.z * in_bs;
     uint8_t* dst = out + (size_t)blockIdx.z * out_bs;
     const bool store_word = out_al4 && x4 + 4 <= ow;
-    if (in_al8 && 2 * x4 + 8 <= iw)
-        pd_strip<true>(src, in_stride, iw, ih, dst, out_stride, ow, oh, x4, y0, store_word);
+    const bool fast = in_al8 && 2 * x4 + 8 <= iw;
+    if (fast && y0 + PD_ROWS <= oh)
+        pd_strip<true, PD_ROWS, true>(src, in_stride, iw, ih, dst, out_stride, ow, oh, x4, y0, store_word);
+    else if (fast)
+        pd_strip<true, PD_ROWS, false>(src, in_stride, iw, ih, dst, out_stride, ow, oh, x4, y0, store_word);
     else
-        pd_strip<false>(src, in_stride, iw, ih, dst, out_stride, ow, oh, x4, y0, store_word);
+        pd_strip<false, PD_ROWS, false>(src, in_stride, iw, ih, dst, out_stride, ow, oh, x4, y0, store_word);
 }
 
 // ------------------------------------------------------------------ grad_xy
@@ -588,13 +613,22 @@ int vsk_pyr_down(vs_ctx* ctx, const VsDevImg& in, const VsDevImg& out)
     VS_REQUIRE(ctx, in.batch == out.batch, "pyr_down: batch mismatch");
     VS_REQUIRE(ctx, in.w > 0 && in.h > 0, "pyr_down: empty input");
     if (out.w <= 0 || out.h <= 0) return VS_OK;
-    VS_REQUIRE(ctx, out.batch <= 65535 && vs_cdiv(out.h, 4 * PD_ROWS) <= 65535, "pyr_down: grid too large");
     int in_al8 = aligned_to(in.data, 8) && in.stride % 8 == 0 && in.batch_stride % 8 == 0;
     int out_al4 = aligned_to(out.data, 4) && out.stride % 4 == 0 && out.batch_stride % 4 == 0;
-    dim3 block(32, 4), grid(vs_cdiv(vs_cdiv(out.w, 4), 32), vs_cdiv(out.h, 4 * PD_ROWS), out.batch);
+    static const int variant = getenv("VSTAB_PD_VARIANT") ? atoi(getenv("VSTAB_PD_VARIANT")) : 0;
+    const int rows = variant == 2 ? 4 : (variant == 3 ? 16 : PD_ROWS_DEFAULT);
+    VS_REQUIRE(ctx, out.batch <= 65535 && vs_cdiv(out.h, rows) <= 65535, "pyr_down: grid too large");
+    const int bx = variant == 5 ? 128 : (variant == 6 ? 64 : 32), by = 128 / bx;
+    dim3 block(bx, by), grid(vs_cdiv(vs_cdiv(out.w, 4), bx), vs_cdiv(out.h, by * rows), out.batch);
     VS_LAUNCH_BEGIN(ctx, VSK_PYR_DOWN);
-    k_pyr_down<<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
-                                                (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h, in_al8, out_al4);
+#define VS_PD_LAUNCH(R, B) k_pyr_down<R, B><<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h, \
+                                                (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h, in_al8, out_al4)
+    if (variant == 1) VS_PD_LAUNCH(8, 12);
+    else if (variant == 2) VS_PD_LAUNCH(4, 12);
+    else if (variant == 3) VS_PD_LAUNCH(16, 6);
+    else if (variant == 4) VS_PD_LAUNCH(8, 10);
+    else VS_PD_LAUNCH(8, 7);
+#undef VS_PD_LAUNCH
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
