@@ -131,6 +131,69 @@ __device__ __forceinline__ float vs_lanczos_sample(const uint8_t* __restrict__ i
     return __fdiv_rn(num, den);
 }
 
+// The same sample, split so that the loads of the next keypoint can be in flight while the
+// current one is evaluated (the solver's loops are latency-bound gathers).  vs_lz_fetch gathers
+// the 4x4 window as four 32-bit rows (bytes = columns ix-1 .. ix+2 of rows iy-1 .. iy+2, each
+// clamped to the image): two aligned 32-bit loads + a funnel shift per row when the window and
+// the second word lie inside the row, byte loads with clamping otherwise.  vs_lz_eval performs
+// exactly the operations of vs_lanczos_sample on those values, in the same order.
+// Requires a 4-byte aligned image base and pitch.
+struct VsLzTaps {
+    float rx, ry;
+    uint32_t row[4];
+};
+
+__device__ __forceinline__ void vs_lz_fetch(const uint8_t* __restrict__ img, int w, int h, int pitch, float ox, float oy,
+                                            float A, float B, float TX, float TY, VsLzTaps& t)
+{
+    const float onepA = __fadd_rn(1.0f, A);
+    const float Wx = __fadd_rn(__fsub_rn(__fmul_rn(onepA, ox), __fmul_rn(B, oy)), TX);
+    const float Wy = __fadd_rn(__fadd_rn(__fmul_rn(B, ox), __fmul_rn(onepA, oy)), TY);
+    const float fWx = floorf(Wx), fWy = floorf(Wy);
+    t.rx = __fsub_rn(Wx, fWx);
+    t.ry = __fsub_rn(Wy, fWy);
+    const int ix = (int)fWx, iy = (int)fWy;
+    if (ix >= 1 && ix + 6 < w && iy >= 1 && iy + 2 < h) {
+        const int off = (iy - 1) * pitch + ix - 1;
+        const uint8_t* p = img + (off & ~3);
+        const int sh = (off & 3) * 8;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(p + j * pitch));
+            const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(p + j * pitch + 4));
+            t.row[j] = __funnelshift_r(w0, w1, sh);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint8_t* r = img + (size_t)vs_clampi(iy - 1 + j, 0, h - 1) * pitch;
+            t.row[j] = (uint32_t)__ldg(r + vs_clampi(ix - 1, 0, w - 1)) | ((uint32_t)__ldg(r + vs_clampi(ix, 0, w - 1)) << 8) |
+                       ((uint32_t)__ldg(r + vs_clampi(ix + 1, 0, w - 1)) << 16) | ((uint32_t)__ldg(r + vs_clampi(ix + 2, 0, w - 1)) << 24);
+        }
+    }
+}
+
+__device__ __forceinline__ float vs_lz_eval(const VsLzTaps& t)
+{
+    float wx[4], wy[4];
+#pragma unroll
+    for (int u = 1; u < 5; u++) {
+        wx[u - 1] = vs_lanczos2(__fsub_rn((float)(u - 2), t.rx));
+        wy[u - 1] = vs_lanczos2(__fsub_rn((float)(u - 2), t.ry));
+    }
+    float num = 0.0f, den = 0.0f;
+#pragma unroll
+    for (int ty = 0; ty < 4; ty++) {
+#pragma unroll
+        for (int tx = 0; tx < 4; tx++) {
+            const float w2 = __fmul_rn(wx[tx], wy[ty]);
+            num = __fadd_rn(num, __fmul_rn(w2, (float)((t.row[ty] >> (8 * tx)) & 0xffu)));
+            den = __fadd_rn(den, w2);
+        }
+    }
+    return __fdiv_rn(num, den);
+}
+
 __device__ __forceinline__ double vs_warp_reduce_sum(double v)
 {
 #pragma unroll

@@ -354,6 +354,9 @@ struct SolveShared {
 // per axis with the serial code, so every comparison-dependent choice is libstdc++'s own.
 // Both keypoint axes are processed in the same rounds.
 constexpr int SEL_SERIAL = 96;
+#ifndef VS_SOLVE_PREFETCH
+#define VS_SOLVE_PREFETCH 0
+#endif
 
 struct SelAxis {
     int first, last, depth, done;
@@ -580,17 +583,35 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         // ---- SparseWarpDiff for both keypoint sets with the incoming transform (alignment.cpp:409-431)
         float P[4];
         vs_ul_params_half(sh.T, L.w, L.h, P);
-        for (int i = tid; i < 2 * nt; i += SOLVE_THREADS) {
-            const int axis = i >= nt, t = i - axis * nt;
-            uint32_t kv = __ldg((axis ? kpl1 : kpl0) + t);
-            int px = min((int)(kv & 0xffffu), L.w - 1), py = min((int)(kv >> 16), L.h - 1);
-            float s = vs_lanczos_sample(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3]);
-            float d = fabsf(__fsub_rn(s, (float)__ldg(timg + (size_t)py * L.pitch + px)));
-            d = fmaxf(fminf(d, 65535.0f), 0.0f);
-            uint32_t u = (uint32_t)d;
-            (axis ? keys1 : keys0)[t] = (u << 16) | (uint32_t)t;
-            if (a.dbg_warpdiff)
-                a.dbg_warpdiff[((size_t)pair * 2 + axis) * g.total_tiles + L.tile_off + t] = (uint16_t)u;
+        {
+            // software-pipelined over this thread's keypoints: the gather of keypoint i+256 is issued
+            // before keypoint i is evaluated
+            VsLzTaps cur, nxt;
+            uint32_t tb_cur = 0, tb_nxt = 0;
+            auto fetch = [&](int i, VsLzTaps& taps, uint32_t& tb) {
+                const int axis = i >= nt, t = i - axis * nt;
+                const uint32_t kv = __ldg((axis ? kpl1 : kpl0) + t);
+                const int px = min((int)(kv & 0xffffu), L.w - 1), py = min((int)(kv >> 16), L.h - 1);
+                vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3], taps);
+                tb = __ldg(timg + (size_t)py * L.pitch + px);
+            };
+            int i = tid;
+            if (VS_SOLVE_PREFETCH && i < 2 * nt) fetch(i, cur, tb_cur);
+            while (i < 2 * nt) {
+                const int inext = i + SOLVE_THREADS;
+                if (!VS_SOLVE_PREFETCH) fetch(i, cur, tb_cur);
+                else if (inext < 2 * nt) fetch(inext, nxt, tb_nxt);
+                const int axis = i >= nt, t = i - axis * nt;
+                const float s = vs_lz_eval(cur);
+                float d = fabsf(__fsub_rn(s, (float)tb_cur));
+                d = fmaxf(fminf(d, 65535.0f), 0.0f);
+                const uint32_t u = (uint32_t)d;
+                (axis ? keys1 : keys0)[t] = (u << 16) | (uint32_t)t;
+                if (a.dbg_warpdiff)
+                    a.dbg_warpdiff[((size_t)pair * 2 + axis) * g.total_tiles + L.tile_off + t] = (uint16_t)u;
+                if (VS_SOLVE_PREFETCH) { cur = nxt; tb_cur = tb_nxt; }
+                i = inext;
+            }
         }
         __syncthreads();
 
@@ -647,19 +668,33 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
             iters++;
             vs_ul_params_half(sh.T, L.w, L.h, P);
             double b[4] = {0, 0, 0, 0};
-            for (int i = tid; i < 2 * k; i += SOLVE_THREADS) {
-                const int axis = i >= k, j = i - axis * k;
-                const int t = (int)((axis ? keys1 : keys0)[j] & 0xffffu);
-                uint32_t kv = __ldg((axis ? kpl1 : kpl0) + t);
-                int px = (int)(kv & 0xffffu), py = (int)(kv >> 16);
-                float4 J = __ldg((axis ? jcl1 : jcl0) + t);
-                float warped = vs_lanczos_sample(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3]);
-                int qx = min(px, L.w - 1), qy = min(py, L.h - 1);
-                float r = __fsub_rn((float)__ldg(timg + (size_t)qy * L.pitch + qx), warped);
-                b[0] += (double)__fmul_rn(J.x, r);
-                b[1] += (double)__fmul_rn(J.y, r);
-                if (axis == 0) b[2] += (double)__fmul_rn(J.z, r);
-                else           b[3] += (double)__fmul_rn(J.w, r);
+            {
+                VsLzTaps cur, nxt;
+                uint32_t tb_cur = 0, tb_nxt = 0;
+                float4 J_cur = make_float4(0, 0, 0, 0), J_nxt = J_cur;
+                auto fetch = [&](int i, VsLzTaps& taps, uint32_t& tb, float4& J) {
+                    const int axis = i >= k, j = i - axis * k;
+                    const int t = (int)((axis ? keys1 : keys0)[j] & 0xffffu);
+                    const uint32_t kv = __ldg((axis ? kpl1 : kpl0) + t);
+                    const int px = (int)(kv & 0xffffu), py = (int)(kv >> 16);
+                    J = __ldg((axis ? jcl1 : jcl0) + t);
+                    vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3], taps);
+                    tb = __ldg(timg + (size_t)min(py, L.h - 1) * L.pitch + min(px, L.w - 1));
+                };
+                int i = tid;
+                if (VS_SOLVE_PREFETCH && i < 2 * k) fetch(i, cur, tb_cur, J_cur);
+                while (i < 2 * k) {
+                    const int inext = i + SOLVE_THREADS;
+                    if (!VS_SOLVE_PREFETCH) fetch(i, cur, tb_cur, J_cur);
+                    else if (inext < 2 * k) fetch(inext, nxt, tb_nxt, J_nxt);
+                    const float r = __fsub_rn((float)tb_cur, vs_lz_eval(cur));
+                    b[0] += (double)__fmul_rn(J_cur.x, r);
+                    b[1] += (double)__fmul_rn(J_cur.y, r);
+                    if (i < k) b[2] += (double)__fmul_rn(J_cur.z, r);
+                    else       b[3] += (double)__fmul_rn(J_cur.w, r);
+                    if (VS_SOLVE_PREFETCH) { cur = nxt; tb_cur = tb_nxt; J_cur = J_nxt; }
+                    i = inext;
+                }
             }
             double tot[4];
             block_reduce<4>(b, sh, tot);
