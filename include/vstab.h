@@ -225,6 +225,9 @@ int vs_clip_get_jacobians(vs_clip*, int slot, int level, int axis, float* out /*
 /* need VS_CLIP_DEBUG_TAPS; pair = index within the last vs_clip_align call */
 int vs_clip_get_warpdiff(vs_clip*, int pair, int level, int axis, uint16_t* out /* (tw,th) */);
 int vs_clip_get_selected(vs_clip*, int pair, int level, int axis, uint32_t* out_order, int* out_k);
+/* SM cycles pair `pair` of the last vs_clip_align spent per phase, summed over levels:
+ * {warp-diff, selection, Hessian + SVD, Gauss-Newton gathers, Gauss-Newton reduce + update, 0} */
+int vs_clip_get_solver_cycles(vs_clip*, int pair, long long* out6);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,7 @@ SYMBOLS = {
     "vs_clip_get_keypoints": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "vs_clip_get_jacobians": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "vs_clip_get_warpdiff": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "vs_clip_get_solver_cycles": (C.c_int, [_P, C.c_int, _P]),
     "vs_clip_get_selected": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
 }
 

@@ -31,6 +31,7 @@ struct vs_clip {
     uint16_t* d_dbg_wd = nullptr;
     uint16_t* d_dbg_order = nullptr;
     int32_t* d_dbg_count = nullptr;
+    long long* d_dbg_clock = nullptr;   // [max_pairs][8]
     uint16_t* d_pos_scratch = nullptr; // [max_pairs][4][max_tiles] candidate lists of the parallel selection
     uint8_t* d_warp_out = nullptr;    // staging for VS_MEM_HOST warps, grown on demand
     size_t warp_out_bytes = 0;
@@ -78,7 +79,7 @@ void free_all(vs_clip* c)
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
-    cudaFree(c->d_pos_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_warp_out);
+    cudaFree(c->d_pos_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
 }
 
 }  // namespace
@@ -157,6 +158,7 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
         r = dev_alloc(ctx, &c->d_dbg_wd, (size_t)max_pairs * 2 * g.total_tiles);
         if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_order, (size_t)max_pairs * 2 * g.total_tiles);
         if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_count, (size_t)max_pairs * 2 * g.levels);
+        if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_clock, (size_t)max_pairs * 8);
     }
     if (r != VS_OK) { free_all(c); delete c; return r; }
     // padding bytes of the pyramid rows are never read as pixels, but keep them defined
@@ -278,6 +280,7 @@ int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_
     a.out_iters = dev_out ? out_iters : (out_iters ? c->d_iters : nullptr);
     a.dbg_warpdiff = c->d_dbg_wd; a.dbg_order = c->d_dbg_order; a.dbg_count = c->d_dbg_count;
     a.pos_scratch = c->d_pos_scratch;
+    a.dbg_clock = c->d_dbg_clock;
     if (c->d_dbg_count)   // -1 marks levels a pair never reached
         VS_CUDA(ctx, cudaMemsetAsync(c->d_dbg_count, 0xFF, (size_t)c->max_pairs * 2 * c->g.levels * sizeof(int32_t), ctx->stream));
     VS_TRY(vsk_solve_pairs(ctx, c->g, a));
@@ -531,6 +534,18 @@ int vs_clip_get_warpdiff(vs_clip* c, int pair, int level, int axis, uint16_t* ou
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
     VS_CUDA(ctx, cudaMemcpyAsync(out, c->d_dbg_wd + ((size_t)pair * 2 + axis) * c->g.total_tiles + L.tile_off,
                                  (size_t)L.ntiles * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VS_OK;
+}
+
+int vs_clip_get_solver_cycles(vs_clip* c, int pair, long long* out6)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, c->d_dbg_clock, "clip_get_solver_cycles: clip was created without VS_CLIP_DEBUG_TAPS");
+    VS_REQUIRE(ctx, pair >= 0 && pair < c->last_pairs && out6, "clip_get_solver_cycles: bad arguments");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpyAsync(out6, c->d_dbg_clock + (size_t)pair * 8, 6 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VS_OK;
 }

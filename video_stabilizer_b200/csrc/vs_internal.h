@@ -84,6 +84,7 @@ struct VsSolveArgs {
     uint16_t* dbg_warpdiff;   // [pair][axis][total_tiles] or null
     uint16_t* dbg_order;      // [pair][axis][total_tiles] or null
     int32_t* dbg_count;       // [pair][axis][levels] or null
+    long long* dbg_clock;     // [pair][8] cycles per phase (debug taps only), or null
     uint16_t* pos_scratch;    // [pair][4][max_tiles] selection scratch in global memory, or null (shared memory)
 };
 

@@ -353,7 +353,7 @@ struct SolveShared {
 // tail (ranges <= SEL_SERIAL long, or an exhausted depth limit -> heap select) run on one thread
 // per axis with the serial code, so every comparison-dependent choice is libstdc++'s own.
 // Both keypoint axes are processed in the same rounds.
-constexpr int SEL_SERIAL = 96;
+constexpr int SEL_SERIAL = 32;
 #ifndef VS_SOLVE_PREFETCH
 #define VS_SOLVE_PREFETCH 0
 #endif
@@ -568,6 +568,9 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         if (a.out_iters) for (int l = 0; l < g.levels; l++) a.out_iters[(size_t)pair * g.levels + l] = 0;
     }
 
+    long long clk[6] = {0, 0, 0, 0, 0, 0};   // warpdiff, select, hessian+svd, gn gather, gn reduce+update, (unused)
+    long long t_prev = a.dbg_clock ? clock64() : 0;
+#define VS_CLK(slot) do { if (a.dbg_clock && tid == 0) { long long _t = clock64(); clk[slot] += _t - t_prev; t_prev = _t; } } while (0)
     for (int lvl = g.levels - 1; lvl >= 0; lvl--) {
         const VsLevel L = g.lv[lvl];
         const uint8_t* timg = tpyr + L.img_off;
@@ -615,9 +618,11 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         }
         __syncthreads();
 
+        VS_CLK(0);
         // ---- keep the k smallest: exact replay of std::nth_element (alignment.cpp:460-486)
         block_nth_element2(keys0, keys1, pos0, pos1, nt, k, sel);
         __syncthreads();
+        VS_CLK(1);
 
         if (a.dbg_order) {
             for (int i = tid; i < 2 * k; i += SOLVE_THREADS) {
@@ -661,6 +666,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         }
         __syncthreads();
 
+        VS_CLK(2);
         // ---- inverse-compositional Gauss-Newton iterations (alignment.cpp:600-668)
         int iters = 0;
         int flag = FLAG_CONTINUE;
@@ -696,6 +702,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
                     i = inext;
                 }
             }
+            VS_CLK(3);
             double tot[4];
             block_reduce<4>(b, sh, tot);
             if (tid == 0) {
@@ -727,6 +734,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
                 sh.flag = f;
             }
             __syncthreads();
+            VS_CLK(4);
             flag = sh.flag;
             if (flag != FLAG_CONTINUE) break;
         }
@@ -755,6 +763,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         }
         for (int c = 0; c < 4; c++) a.out_T[(size_t)pair * 4 + c] = T[c];
         a.out_status[pair] = sh.status;
+        if (a.dbg_clock) for (int c = 0; c < 6; c++) a.dbg_clock[(size_t)pair * 8 + c] = clk[c];
     }
 }
 

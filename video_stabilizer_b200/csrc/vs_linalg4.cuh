@@ -114,8 +114,10 @@ VS_LA_HD double vs_condition_and_invert(double* H, double* Hinv)
         double lambda = 1e-6 * w[0];
         for (int d = 0; d < 4; d++) H[d * 4 + d] += lambda;
     }
-    // H.inv(DECOMP_SVD) decomposes (the possibly regularised) H again
-    vs_svd4(H, w, u, vt);
+    // H.inv(DECOMP_SVD) decomposes H again.  When H was not regularised that second
+    // decomposition is the same deterministic computation on the same input, so its result is
+    // reused instead of recomputed (identical bits, half the serial work).
+    if (cond > 1e6) vs_svd4(H, w, u, vt);
     vs_inv4_from_svd(w, u, vt, Hinv);
     return cond;
 }
