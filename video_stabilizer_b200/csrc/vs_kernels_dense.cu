@@ -149,6 +149,54 @@ __device__ __forceinline__ void pd_strip(const uint8_t* __restrict__ src, int64_
     }
 }
 
+// Wide variant: 8 adjacent outputs per thread from one 16-byte load per input row (+ the same
+// 2 + 1 halo bytes): twice the bytes in flight per load instruction.
+//   a16 = in[2x-2], in[2x-1]   b = in[2x .. 2x+15]   c8 = in[2x+16]
+__device__ __forceinline__ void pd_hsum8(uint32_t a16, uint4 b, uint32_t c8, uint32_t h[4])
+{
+    const uint32_t h0 = __dp4a(b.x, 0x00010406u, __dp4a(a16, 0x00000401u, 0u));
+    const uint32_t h1 = __dp4a(b.y, 0x00000001u, __dp4a(b.x, 0x04060401u, 0u));
+    const uint32_t h2 = __dp4a(b.y, 0x00010406u, __dp4a(b.x, 0x04010000u, 0u));
+    const uint32_t h3 = __dp4a(b.z, 0x00000001u, __dp4a(b.y, 0x04060401u, 0u));
+    const uint32_t h4 = __dp4a(b.z, 0x00010406u, __dp4a(b.y, 0x04010000u, 0u));
+    const uint32_t h5 = __dp4a(b.w, 0x00000001u, __dp4a(b.z, 0x04060401u, 0u));
+    const uint32_t h6 = __dp4a(b.w, 0x00010406u, __dp4a(b.z, 0x04010000u, 0u));
+    const uint32_t h7 = __dp4a(b.w, 0x04060401u, c8);
+    h[0] = h0 | (h1 << 16); h[1] = h2 | (h3 << 16); h[2] = h4 | (h5 << 16); h[3] = h6 | (h7 << 16);
+}
+
+template <int PD_ROWS>
+__global__ void __launch_bounds__(128)
+k_pyr_down_wide(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, int iw, int ih,
+                uint8_t* __restrict__ out, int64_t out_stride, int64_t out_bs, int ow, int oh)
+{
+    // launched only when rows are 16-byte aligned, ow % 8 == 0 and 2*ow <= iw (every 16-byte load inside the row)
+    const int x8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * PD_ROWS;
+    if (x8 >= ow || y0 >= oh) return;
+    const uint8_t* src = in + (size_t)blockIdx.z * in_bs;
+    uint8_t* dst = out + (size_t)blockIdx.z * out_bs;
+    uint32_t h[2 * PD_ROWS + 3][4];
+#pragma unroll
+    for (int j = 0; j < 2 * PD_ROWS + 3; j++) {
+        const uint8_t* r = src + (size_t)vs_clampi(2 * y0 - 2 + j, 0, ih - 1) * in_stride;
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(r + 2 * x8));
+        const uint32_t a16 = x8 > 0 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(r + 2 * x8 - 2)) : (b.x & 0xffu) * 0x0101u;
+        const uint32_t c8 = __ldg(r + min(2 * x8 + 16, iw - 1));
+        pd_hsum8(a16, b, c8, h[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < PD_ROWS; i++) {
+        if (y0 + i >= oh) break;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            v[k] = h[2 * i][k] + h[2 * i + 4][k] + 4u * (h[2 * i + 1][k] + h[2 * i + 3][k]) + 6u * h[2 * i + 2][k];
+        *reinterpret_cast<uint2*>(dst + (size_t)(y0 + i) * out_stride + x8) =
+            make_uint2(__byte_perm(v[0], v[1], 0x7531), __byte_perm(v[2], v[3], 0x7531));
+    }
+}
+
 template <int PD_ROWS, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_pyr_down(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, int iw, int ih,
@@ -615,9 +663,29 @@ int vsk_pyr_down(vs_ctx* ctx, const VsDevImg& in, const VsDevImg& out)
     if (out.w <= 0 || out.h <= 0) return VS_OK;
     int in_al8 = aligned_to(in.data, 8) && in.stride % 8 == 0 && in.batch_stride % 8 == 0;
     int out_al4 = aligned_to(out.data, 4) && out.stride % 4 == 0 && out.batch_stride % 4 == 0;
-    static const int variant = getenv("VSTAB_PD_VARIANT") ? atoi(getenv("VSTAB_PD_VARIANT")) : 0;
+    // default: the wide kernel (8 outputs per thread, 4 rows) whenever alignment and sizes allow it;
+    // VSTAB_PD_VARIANT selects the tuning variants (0-6: narrow kernel shapes, 7/8: wide)
+    static const int variant = getenv("VSTAB_PD_VARIANT") ? atoi(getenv("VSTAB_PD_VARIANT")) : 7;
     const int rows = variant == 2 ? 4 : (variant == 3 ? 16 : PD_ROWS_DEFAULT);
     VS_REQUIRE(ctx, out.batch <= 65535 && vs_cdiv(out.h, rows) <= 65535, "pyr_down: grid too large");
+    if (variant >= 7) {
+        const bool ok16 = aligned_to(in.data, 16) && in.stride % 16 == 0 && in.batch_stride % 16 == 0 &&
+                          aligned_to(out.data, 8) && out.stride % 8 == 0 && out.batch_stride % 8 == 0 &&
+                          out.w % 8 == 0 && 2 * out.w <= in.w;
+        if (ok16) {
+            const int wr = variant == 8 ? 8 : 4;
+            dim3 wblock(32, 4), wgrid(vs_cdiv(out.w / 8, 32), vs_cdiv(out.h, 4 * wr), out.batch);
+            VS_LAUNCH_BEGIN(ctx, VSK_PYR_DOWN);
+            if (wr == 8)
+                k_pyr_down_wide<8><<<wgrid, wblock, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
+                                                                      (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h);
+            else
+                k_pyr_down_wide<4><<<wgrid, wblock, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
+                                                                      (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h);
+            VS_LAUNCH_CHECK(ctx);
+            return VS_OK;
+        }
+    }
     const int bx = variant == 5 ? 128 : (variant == 6 ? 64 : 32), by = 128 / bx;
     dim3 block(bx, by), grid(vs_cdiv(vs_cdiv(out.w, 4), bx), vs_cdiv(out.h, by * rows), out.batch);
     VS_LAUNCH_BEGIN(ctx, VSK_PYR_DOWN);
