@@ -335,32 +335,34 @@ def run_gpu_arm(args):
     alg = algorithmic_bytes(W, H, crop, F, n_key, F - 1, n_out)
     steps_profiled = args.steps + 1
     per_kernel = {}
+    lv = level_table(W, H)
+    px = [L["w"] * L["h"] for L in lv]
+    # algorithmic bytes of one STEP per kernel (a kernel may be launched several times per step:
+    # pyr_down once per level, bgr_warp in batches that overlap the host trajectory)
+    alg_step = dict(alg)
+    alg_step["pyr_down"] = sum(px[i] + px[i + 1] for i in range(len(px) - 1)) * F
     for name, (n, tot) in kernels.items():
-        per_launch_ms = tot / n
         launches_per_step = n / steps_profiled
-        b = alg.get(name)
-        if name == "pyr_down":   # several launches (one per level) per step: account all levels' bytes
-            lv = level_table(W, H)
-            px = [L["w"] * L["h"] for L in lv]
-            b_step = sum(px[i] + px[i + 1] for i in range(len(px) - 1)) * F
-            gbs = b_step / (tot / steps_profiled / 1e3) / 1e9
-        else:
-            gbs = (b / (per_launch_ms / 1e3) / 1e9) if b else None
-        per_kernel[name] = {"launches_per_step": launches_per_step, "ms_per_step": tot / steps_profiled,
-                            "ms_per_launch": per_launch_ms, "algorithmic_gbs": gbs,
+        ms_step = tot / steps_profiled
+        b = alg_step.get(name)
+        gbs = (b / (ms_step / 1e3) / 1e9) if b else None
+        per_kernel[name] = {"launches_per_step": launches_per_step, "ms_per_step": ms_step,
+                            "ms_per_launch": tot / n, "algorithmic_bytes_per_step": b, "algorithmic_gbs": gbs,
                             "frac_of_hbm_peak": (gbs / peak) if gbs else None}
     dominant = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
     d = per_kernel[dominant]
     traffic = None
-    tpath = os.path.join(REPO, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(REPO, "profiles", "traffic.json")   # dram bytes per step from the committed ncu --set full capture
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dominant)
+            t = json.load(open(tpath)).get(dominant)
+            traffic = t / d["launches_per_step"] if t else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": d["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": d["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg.get(dominant), "ms_per_launch": d["ms_per_launch"],
+                "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_step"] / d["launches_per_step"],
+                "launches_per_step": d["launches_per_step"], "ms_per_launch": d["ms_per_launch"],
                 "kernel_share_of_step": d["ms_per_step"] / max(prof_ms, 1e-9)}
 
     # ---- CPU baseline on this box's cores (N=1 only)

@@ -136,9 +136,27 @@ int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int o
     const int np = (int)m_pairs.size();
     if (np) check(vs_clip_align(m_clip, m_pairs.data(), np, m_T.data(), m_status.data(), nullptr, VS_MEM_HOST), "align");
 
-    // ---- sequential host trajectory
+    // ---- sequential host trajectory, with the warps of the frames already decided launched in
+    //      batches while the host is still smoothing the later ones (asynchronous outputs only)
     std::vector<int32_t> due_slots;
     std::vector<double> due_T;
+    const bool overlap = async_to_host || out_mem == VS_MEM_DEVICE;
+    const size_t out_frame_bytes = (size_t)out_width() * out_height() * 3;
+    (void)out_frame_bytes;
+    int launched = 0;
+    auto launch_warps = [&](int upto) {
+        const int cnt = upto - launched;
+        if (cnt <= 0) return;
+        if (!out) throw std::runtime_error("ClipStabilizer: output buffer is NULL");
+        uint8_t* dst = out + (size_t)out_frame_stride * launched;
+        if (async_to_host)
+            check(vs_clip_warp_to_host_async(m_clip, due_slots.data() + launched, cnt, due_T.data() + 4 * (size_t)launched,
+                                             VS_WARP_CV_EXACT_BILINEAR, VS_BORDER_CONSTANT0, m_crop, dst, out_frame_stride), "warp");
+        else
+            check(vs_clip_warp(m_clip, due_slots.data() + launched, cnt, due_T.data() + 4 * (size_t)launched,
+                               VS_WARP_CV_EXACT_BILINEAR, VS_BORDER_CONSTANT0, m_crop, dst, out_frame_stride, out_mem), "warp");
+        launched = upto;
+    };
     const int first_pair_frame = (int)(std::max(f0, 1L) - f0);
     for (int i = 0; i < n; i++) {
         SimilarityTransform meas;
@@ -155,21 +173,14 @@ int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int o
             m_corr.push_back(corr);
             due_slots.push_back((int32_t)((m_emitted + (long)due_slots.size()) % m_capacity));
             due_T.insert(due_T.end(), {corr.A, corr.B, corr.TX, corr.TY});
+            if (overlap && (int)due_slots.size() - launched >= m_warp_batch) launch_warps((int)due_slots.size());
         }
     }
     m_fed = f0 + n;
 
-    // ---- one warp launch over the frames that became due (crop fused)
+    // ---- the remaining (or, for synchronous host output, all) due frames in one launch (crop fused)
     const int produced = (int)due_slots.size();
-    if (produced) {
-        if (!out) throw std::runtime_error("ClipStabilizer: output buffer is NULL");
-        if (async_to_host)
-            check(vs_clip_warp_to_host_async(m_clip, due_slots.data(), produced, due_T.data(), VS_WARP_CV_EXACT_BILINEAR,
-                                             VS_BORDER_CONSTANT0, m_crop, out, out_frame_stride), "warp");
-        else
-            check(vs_clip_warp(m_clip, due_slots.data(), produced, due_T.data(), VS_WARP_CV_EXACT_BILINEAR, VS_BORDER_CONSTANT0,
-                               m_crop, out, out_frame_stride, out_mem), "warp");
-    }
+    launch_warps(produced);
     m_emitted += produced;
     return produced;
 }
