@@ -10,9 +10,16 @@
 //   dbg_*    optional (VS_CLIP_DEBUG_TAPS)               warpdiff and selection order per pair
 #include "vs_internal.h"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 struct vs_clip {
+    // TMA descriptor of the BGR store viewed as u32 [slot][row][pitch/4], box {108 words, 20 rows, 1}:
+    // the cv-exact warp fetches a tile's source box with one cp.async.bulk.tensor (first member: 64-byte aligned)
+    CUtensorMap bgr_map;
+    bool bgr_map_ok = false;
     vs_ctx* ctx = nullptr;
     int w = 0, h = 0, capacity = 0, max_pairs = 0, flags = 0;
     vs_align_params params;
@@ -80,6 +87,51 @@ void free_all(vs_clip* c)
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
     cudaFree(c->d_pos_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
+}
+
+// cuTensorMapEncodeTiled lives in the driver library; resolve it through the runtime so that
+// libvstab.so keeps linking against cudart only
+PFN_cuTensorMapEncodeTiled tensor_map_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+void build_bgr_tensor_map(vs_clip* c)
+{
+    c->bgr_map_ok = false;
+    const char* env = getenv("VSTAB_WARP_TMA");
+    if (env && atoi(env) == 0) return;
+    PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc || c->bgr_pitch % 16 != 0 || c->bgr_slot_bytes % 16 != 0) return;
+    if ((int)(c->bgr_pitch / 4) < VS_WARP_TMA_BOX_WORDS || c->h < VS_WARP_TMA_BOX_ROWS) return;
+    const cuuint64_t dims[3] = {(cuuint64_t)(c->bgr_pitch / 4), (cuuint64_t)c->h, (cuuint64_t)c->capacity};
+    const cuuint64_t strides[2] = {(cuuint64_t)c->bgr_pitch, (cuuint64_t)c->bgr_slot_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)VS_WARP_TMA_BOX_WORDS, (cuuint32_t)VS_WARP_TMA_BOX_ROWS, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&c->bgr_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->d_bgr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    c->bgr_map_ok = (r == CUDA_SUCCESS);
+}
+
+// the BGR warp of a clip: TMA-staged kernel for the production mode, generic kernels otherwise
+int clip_warp_launch(vs_clip* c, const int32_t* d_slots, const VsWarpCoef* d_coef, const VsDevImg& dst, int crop, int mode, int border, int n)
+{
+    VsDevImg src{c->d_bgr, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
+    if (mode == VS_WARP_CV_EXACT_BILINEAR && border == VS_BORDER_CONSTANT0 && c->bgr_map_ok)
+        return vsk_bgr_warp_slots_tma(c->ctx, &c->bgr_map, src, d_slots, d_coef, dst, crop, crop);
+    return vsk_bgr_warp_slots(c->ctx, src, d_slots, d_coef, dst, crop, crop, mode, border);
 }
 
 }  // namespace
@@ -164,6 +216,7 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
     // padding bytes of the pyramid rows are never read as pixels, but keep them defined
     cudaMemsetAsync(c->d_pyr, 0, g.pyr_slot_bytes * capacity, ctx->stream);
     cudaMemsetAsync(c->d_bgr, 0, c->bgr_slot_bytes * capacity, ctx->stream);
+    build_bgr_tensor_map(c);
     *out = c;
     return VS_OK;
 }
@@ -332,9 +385,8 @@ int vs_clip_warp(vs_clip* c, const int32_t* slots, int n, const double* transfor
         d_out = c->d_warp_out;
         d_stride = (int64_t)ow * oh * 3;
     }
-    VsDevImg src{c->d_bgr, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
     VsDevImg dst{d_out, ow, oh, (int64_t)ow * 3, n, d_stride};
-    VS_TRY(vsk_bgr_warp_slots(ctx, src, c->d_slots, c->d_coef, dst, crop, crop, mode, border));
+    VS_TRY(clip_warp_launch(c, c->d_slots, c->d_coef, dst, crop, mode, border, n));
     if (mem == VS_MEM_HOST) {
         VS_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)out_frame_stride, d_out, (size_t)d_stride, (size_t)ow * oh * 3, n,
                                        cudaMemcpyDeviceToHost, ctx->stream));
@@ -435,9 +487,8 @@ int vs_clip_warp_to_host_async(vs_clip* c, const int32_t* slots, int n, const do
     // pageable sources: both copies complete (staged) before the call returns
     VS_CUDA(ctx, cudaMemcpyAsync(d_coef, coef.data(), (size_t)n * sizeof(VsWarpCoef), cudaMemcpyHostToDevice, ctx->stream));
     VS_CUDA(ctx, cudaMemcpyAsync(d_slots, slots, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    VsDevImg src{c->d_bgr, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
     VsDevImg dst{c->d_out_ring[b], ow, oh, (int64_t)ow * 3, n, (int64_t)frame_bytes};
-    VS_TRY(vsk_bgr_warp_slots(ctx, src, d_slots, d_coef, dst, crop, crop, mode, border));
+    VS_TRY(clip_warp_launch(c, d_slots, d_coef, dst, crop, mode, border, n));
     VS_CUDA(ctx, cudaEventRecord(c->ev_warp[b], ctx->stream));
     VS_CUDA(ctx, cudaStreamWaitEvent(c->down_stream, c->ev_warp[b], 0));
     if (out_frame_stride == (int64_t)frame_bytes)

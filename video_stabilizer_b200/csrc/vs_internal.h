@@ -41,6 +41,12 @@ int vsk_bgr_warp(vs_ctx*, const VsDevImg& src, const VsWarpCoef* d_coef, const V
 int vsk_bgr_warp_slots(vs_ctx*, const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
                        const VsDevImg& dst, int dst_x0, int dst_y0, int mode, int border);
 
+// TMA-staged form for clip-resident frames: tensor_map points to a CUtensorMap over the BGR store viewed as
+// u32 [slot][row][pitch/4] with box {108, 20, 1} (built by vs_clip.cu); mode 0, BORDER_CONSTANT0 only
+int vsk_bgr_warp_slots_tma(vs_ctx*, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,
+                           const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0);
+constexpr int VS_WARP_TMA_BOX_WORDS = 108, VS_WARP_TMA_BOX_ROWS = 20;
+
 // ---- sparse kernels (vs_kernels_sparse.cu)
 int vsk_grad_argmax(vs_ctx*, const VsDevImg& gx, const VsDevImg& gy, int tile,
                     uint16_t* d_lmx, uint16_t* d_lmy);

@@ -3,6 +3,7 @@
 // arithmetic where the math allows it, no tensor cores (nothing here is a contraction).
 #include "vs_internal.h"
 
+#include <cuda.h>   // CUtensorMap (type only; the encoder is resolved at run time in vs_clip.cu)
 #include <math.h>
 #include <stdlib.h>
 
@@ -634,6 +635,156 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
     }
 }
 
+// ------------------------------------------------------------------ BGR warp, cv-exact, TMA-staged
+// Same tile, same sampling and the same bits as k_bgr_warp_cv_tiled, for frames that live in a
+// vs_clip (zero-padded 128-byte-pitch rows, one tensor map over [slot][row][word]): the source
+// box of a tile is fetched by ONE cp.async.bulk.tensor (TMA) instruction issued by one thread —
+// no per-thread address arithmetic, bounds tests or load instructions — and elements outside the
+// frame arrive as zeros, which is exactly BORDER_CONSTANT(0), on every edge.  The box is a fixed
+// 108 words (= 144 pixels) x 20 rows whose first pixel is a multiple of 16 (the start of a TMA box
+// must be 16-byte aligned in global memory: 16 pixels = 48 bytes); the raw bytes are then expanded
+// in shared memory into the paired-tap planes (task = box row x 4-pixel granule: 4 word loads,
+// 8 PRMT, 2 16-byte stores).  A tile whose box does not fit 144 x 20 falls back to direct loads.
+constexpr int WTM_BOX_WORDS = 108, WTM_BOX_ROWS = 20, WTM_PITCH = 144;     // pitch in staged entries (pixels)
+constexpr int WTM_GRANULES = WTM_PITCH / 4;                                 // 36 four-pixel granules per box row
+constexpr int WTM_RAW_BYTES = WTM_BOX_WORDS * 4 * WTM_BOX_ROWS;            // 7680: the TMA transaction size
+constexpr int WTM_PLANE_WORDS = WTM_PITCH * WTM_BOX_ROWS;                  // 2560 entries per plane
+constexpr int WTM_SMEM_BYTES = WTM_RAW_BYTES + 2 * WTM_PLANE_WORDS * 4;    // raw box (reused as the output tile) + SX + SY
+static_assert(WT_OUT_WORDS * 4 <= WTM_RAW_BYTES, "the packed output tile reuses the raw box");
+
+__global__ void __launch_bounds__(WT_THREADS)
+k_bgr_warp_cv_tma(const __grid_constant__ CUtensorMap src_map, const uint8_t* __restrict__ src_base, int64_t src_stride,
+                  int64_t src_bs, int w, int h, const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
+                  uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
+                  int dst_x0, int dst_y0, int dst_al8)
+{
+    extern __shared__ __align__(128) uint32_t wtm_smem[];
+    uint32_t* const RAW = wtm_smem;                               // [WTM_BOX_ROWS][WTM_BOX_WORDS], later the output tile
+    uint32_t* const SX = wtm_smem + WTM_RAW_BYTES / 4;
+    uint32_t* const SY = SX + WTM_PLANE_WORDS;
+    uint32_t* const O = RAW;
+    __shared__ int2 sXY0[WT_H];
+    __shared__ __align__(8) unsigned long long tma_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int ox0 = blockIdx.x * WT_W, oy0 = blockIdx.y * WT_H;
+    const int tw = min(WT_W, dw - ox0), th = min(WT_H, dh - oy0);
+    const int slot = slots ? slots[b] : b;
+    const uint8_t* src = src_base + (size_t)slot * src_bs;
+    uint8_t* dst = dst_base + (size_t)b * dst_bs;
+    const VsWarpCoef cf = coefs[b];
+
+    const int xcol = ox0 + min(tid, tw - 1) + dst_x0;
+    const int adelta = __double2int_rn(cf.i00 * (double)xcol * 1024.0);
+    const int bdelta = __double2int_rn(cf.i10 * (double)xcol * 1024.0);
+    if (tid < WT_H) {
+        const int y = oy0 + min(tid, th - 1) + dst_y0;
+        sXY0[tid] = make_int2(__double2int_rn((cf.i01 * (double)y + cf.i02) * 1024.0) + 16,
+                              __double2int_rn((cf.i11 * (double)y + cf.i12) * 1024.0) + 16);
+    }
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int xl = ox0 + dst_x0, xr = ox0 + tw - 1 + dst_x0;
+    const int aL = __double2int_rn(cf.i00 * (double)xl * 1024.0), aR = __double2int_rn(cf.i00 * (double)xr * 1024.0);
+    const int bL = __double2int_rn(cf.i10 * (double)xl * 1024.0), bR = __double2int_rn(cf.i10 * (double)xr * 1024.0);
+    const int2 xyT = sXY0[0], xyB = sXY0[th - 1];
+    const int sxmin = (min(xyT.x, xyB.x) + min(aL, aR)) >> 10, sxmax = (max(xyT.x, xyB.x) + max(aL, aR)) >> 10;
+    const int symin = (min(xyT.y, xyB.y) + min(bL, bR)) >> 10, symax = (max(xyT.y, xyB.y) + max(bL, bR)) >> 10;
+    const int bx0 = (sxmin >> 4) * 16;                            // 16 pixels = 48 bytes = 12 words: a 16-byte aligned box start
+    const int by0 = symin, nrows = symax + 1 - symin + 1;
+    // entries bx0 .. sxmax are needed, entry x also carries pixel x+1: pixels bx0 .. sxmax+1 must be in the 144-pixel box
+    const bool staged = sxmax + 1 - bx0 < WTM_PITCH && nrows <= WTM_BOX_ROWS;
+
+    if (staged) {
+        if (tid == 0) {
+            const uint32_t dstsm = (uint32_t)__cvta_generic_to_shared(RAW);
+            const int c0 = (bx0 >> 4) * 12;                       // first 32-bit word of pixel bx0 (a multiple of 4 words), may be negative
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WTM_RAW_BYTES) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(dstsm), "l"(reinterpret_cast<uint64_t>(&src_map)), "r"(c0), "r"(by0), "r"(slot), "r"(bar)
+                : "memory");
+        }
+        // everyone waits for the box (phase 0 of the barrier)
+        uint32_t done = 0, spins = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar) : "memory");
+            if (!done && ++spins > (1u << 24)) __trap();   // a lost transaction must fail loudly, not hang the GPU
+        }
+        // raw bytes -> paired-tap planes: entry j = (b[3j], b[3j+3], b[3j+1], b[3j+4]), (b[3j+2], b[3j+5])
+        for (int t = tid; t < nrows * WTM_GRANULES; t += WT_THREADS) {
+            const int r = t / WTM_GRANULES, q = t - r * WTM_GRANULES;
+            const uint32_t* g = RAW + r * WTM_BOX_WORDS + 3 * q;
+            const uint32_t w0 = g[0], w1 = g[1], w2 = g[2], w3 = g[3];   // g[3] of the last granule: next row's first word, feeds only the unused last entry
+            *reinterpret_cast<uint4*>(SX + r * WTM_PITCH + 4 * q) =
+                make_uint4(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x7463), __byte_perm(w1, w2, 0x6352), __byte_perm(w2, w3, 0x5241));
+            *reinterpret_cast<uint4*>(SY + r * WTM_PITCH + 4 * q) =
+                make_uint4(__byte_perm(w0, w1, 0x0052), __byte_perm(w1, w2, 0x0041), __byte_perm(w2, w2, 0x0030), __byte_perm(w2, w3, 0x0063));
+        }
+        __syncthreads();     // planes complete; the raw box is dead and becomes the output tile
+    }
+
+    const int k4 = tid & 3;
+    const uint32_t sel = k4 == 0 ? 0x4210u : (k4 == 1 ? 0x5421u : 0x6542u);
+    uint32_t* const Orow = O + 3 * (tid >> 2) + k4;
+    const bool keep = k4 < 3 && tid < WT_W;
+    if (staged) {
+        const int sorg = -by0 * WTM_PITCH - bx0;
+#pragma unroll 4
+        for (int r = 0; r < WT_H; r++) {
+            if (r >= th) break;
+            const int2 xy0 = sXY0[r];
+            const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
+            const int fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
+            const int e = sorg + (sfy >> 10) * WTM_PITCH + (sfx >> 10);
+            const uint32_t px = cv_blend(make_uint2(SX[e], SY[e]), make_uint2(SX[e + WTM_PITCH], SY[e + WTM_PITCH]), fx, fy);
+            const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
+            if (keep) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
+        }
+    } else {
+        for (int r = 0; r < th; r++) {
+            const int2 xy0 = sXY0[r];
+            const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
+            const int sx = sfx >> 10, sy = sfy >> 10, fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
+            const uint32_t t00 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx, sy);
+            const uint32_t t10 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx + 1, sy);
+            const uint32_t t01 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx, sy + 1);
+            const uint32_t t11 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx + 1, sy + 1);
+            const uint32_t px = cv_blend(wt_entry(t00, t10), wt_entry(t01, t11), fx, fy);
+            const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
+            if (keep) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
+        }
+    }
+    __syncthreads();
+
+    const int row_bytes = tw * 3;
+    uint8_t* const drow0 = dst + (size_t)oy0 * dst_stride + (size_t)ox0 * 3;
+    if (dst_al8 && tw == WT_W) {
+        constexpr int VPR = WT_W * 3 / 8;
+        uint2* d = reinterpret_cast<uint2*>(drow0 + (size_t)warp * dst_stride) + lane;
+        const uint2* o = reinterpret_cast<const uint2*>(O + warp * WT_OUT_ROW_WORDS) + lane;
+        for (int r = warp; r < th; r += WT_WARPS) {
+            d[0] = o[0];
+            if (lane < VPR - 32) d[32] = o[32];
+            d = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(d) + (size_t)WT_WARPS * dst_stride);
+            o += WT_WARPS * WT_OUT_ROW_WORDS / 2;
+        }
+    } else {
+        const uint8_t* Ob = reinterpret_cast<const uint8_t*>(O);
+        for (int i = tid; i < th * row_bytes; i += WT_THREADS) {
+            const int r = i / row_bytes, c = i - r * row_bytes;
+            drow0[(size_t)r * dst_stride + c] = Ob[r * (WT_OUT_ROW_WORDS * 4) + c];
+        }
+    }
+}
+
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 }  // namespace
@@ -806,6 +957,24 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
         launch_bgr_warp<VS_WARP_FLOAT_BILINEAR>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
     else
         launch_bgr_warp<VS_WARP_LANCZOS2>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+// clip-resident sources with a tensor map over [slot][row][word] (vs_clip.cu): mode 0, constant border
+int vsk_bgr_warp_slots_tma(vs_ctx* ctx, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,
+                           const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0)
+{
+    VS_REQUIRE(ctx, tensor_map && src.w > 0 && src.h > 0, "bgr_warp_tma: bad source");
+    if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
+    VS_REQUIRE(ctx, vs_cdiv(dst.h, WT_H) <= 65535 && dst.batch <= 65535, "bgr_warp_tma: grid too large");
+    VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, WTM_SMEM_BYTES));
+    const int dst_al8 = aligned_to(dst.data, 8) && dst.stride % 8 == 0 && dst.batch_stride % 8 == 0;
+    dim3 tgrid(vs_cdiv(dst.w, WT_W), vs_cdiv(dst.h, WT_H), dst.batch);
+    VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
+    k_bgr_warp_cv_tma<<<tgrid, WT_THREADS, WTM_SMEM_BYTES, ctx->stream>>>(
+        *reinterpret_cast<const CUtensorMap*>(tensor_map), (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
+        d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, dst_al8);
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
