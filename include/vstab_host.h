@@ -100,6 +100,13 @@ int   vsh_clipstab_out_size(void*, int* w, int* h);
 vs_ctx*  vsh_clipstab_context(void*);
 vs_clip* vsh_clipstab_clip(void*);
 
+/* ---- MultiGpuStabilizer: one video partitioned by frame chunk over several GPUs (multi_gpu.hpp) */
+void* vsh_multigpu_create(const int32_t* devices, int n_devices, int width, int height, int max_frames, const vsh_stab_params* p);
+void  vsh_multigpu_destroy(void*);
+/* returns the number of stabilized frames written to out (>= 0) or -1; meas (n x 4) / ok (n) may be NULL */
+int   vsh_multigpu_stabilize(void*, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride,
+                             uint8_t* out, int64_t out_frame_stride, double* meas, uint8_t* ok);
+
 #ifdef __cplusplus
 }
 #endif

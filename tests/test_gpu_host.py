@@ -180,3 +180,32 @@ def test_clip_stabilizer_records(host, ob):
         assert bool(ok[i]) == ok_o
         assert corner_displacement(meas[i], T_o, w, h) <= TOL_PX
     assert len(corr) == len(out) == n - 10
+
+
+@pytest.mark.parametrize("workers", [1, 2, 3])
+def test_multi_gpu_stabilizer_equals_single_stream(host, workers):
+    """Frame-chunk partition of one video over several workers (here: contexts on one device; on a
+    multi-GPU box, one per device) with the transforms gathered to the host and the sequential
+    smoother run there: the output equals the single-stream ClipStabilizer bit for bit."""
+    from video_stabilizer_b200 import _capi as capi
+    w, h, n = 320, 180, 45
+    frames = _clip(w, h, n, 31, step=3.0)
+    p = host.stab_params_default()
+    p.crop_pixels = 8
+    cs = host.ClipStabilizer(w, h, n, p, 0)
+    want = cs.feed(frames)
+    meas_want, ok_want, _ = cs.last_records(n)
+    ndev = max(1, capi.load().vs_device_count())
+    devices = [i % ndev for i in range(workers)]
+    mg = host.MultiGpuStabilizer(devices, w, h, n, p)
+    got, meas, ok = mg.stabilize(frames)
+    assert np.array_equal(meas, meas_want) and np.array_equal(ok, ok_want)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    # a shorter second video through the same object
+    got2, _, _ = mg.stabilize(frames[:20])
+    assert np.array_equal(got2, cs_feed_fresh(host, frames[:20], p))
+
+
+def cs_feed_fresh(host, frames, p):
+    n, h, w, _ = frames.shape
+    return host.ClipStabilizer(w, h, n, p, 0).feed(frames)

@@ -8,6 +8,7 @@
 
 #include "aligner_impl.hpp"
 #include "clip_stabilizer.hpp"
+#include "multi_gpu.hpp"
 #include "stabilizer.hpp"
 
 namespace {
@@ -295,6 +296,28 @@ int vsh_clipstab_out_size(void* c, int* w, int* h)
     *w = s->out_width(); *h = s->out_height();
     return 0;
 }
+void* vsh_multigpu_create(const int32_t* devices, int n_devices, int width, int height, int max_frames, const vsh_stab_params* p)
+{
+    vstab::MultiGpuStabilizer* m = nullptr;
+    guarded([&] {
+        m = new vstab::MultiGpuStabilizer(std::vector<int>(devices, devices + n_devices), width, height, max_frames, stab_params(p));
+        return 0;
+    });
+    return m;
+}
+void vsh_multigpu_destroy(void* m) { delete (vstab::MultiGpuStabilizer*)m; }
+int vsh_multigpu_stabilize(void* m, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, uint8_t* out,
+                           int64_t out_frame_stride, double* meas, uint8_t* ok)
+{
+    return guarded([&] {
+        auto* s = (vstab::MultiGpuStabilizer*)m;
+        int k = s->stabilize(frames, n, row_stride, frame_stride, out, out_frame_stride);
+        if (meas) for (size_t i = 0; i < s->measurements().size(); i++) put(s->measurements()[i], meas + 4 * i);
+        if (ok) for (size_t i = 0; i < s->successes().size(); i++) ok[i] = s->successes()[i];
+        return k;
+    });
+}
+
 vs_ctx* vsh_clipstab_context(void* c) { return ((vstab::ClipStabilizer*)c)->context(); }
 vs_clip* vsh_clipstab_clip(void* c) { return ((vstab::ClipStabilizer*)c)->clip(); }
 

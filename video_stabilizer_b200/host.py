@@ -68,6 +68,9 @@ SYMBOLS = {
     "vsh_clipstab_last_records": (_I, [_P, _P, _P, _P]),
     "vsh_clipstab_out_size": (_I, [_P, _PI, _PI]),
     "vsh_clipstab_context": (_P, [_P]),
+    "vsh_multigpu_create": (_P, [_P, _I, _I, _I, _I, _SP]),
+    "vsh_multigpu_destroy": (None, [_P]),
+    "vsh_multigpu_stabilize": (_I, [_P, _P, _I, _I64, _I64, _P, _I64, _P, _P]),
     "vsh_clipstab_clip": (_P, [_P]),
 }
 
@@ -387,3 +390,30 @@ class ClipStabilizer(_Handle):
 
     def synchronize(self):
         capi.check(self.ctx_handle, capi.load().vs_ctx_synchronize(self.ctx_handle), "vs_ctx_synchronize")
+
+
+class MultiGpuStabilizer(_Handle):
+    """One video partitioned by frame chunk over several GPUs of one box (multi_gpu.hpp)."""
+    _destroy = "vsh_multigpu_destroy"
+
+    def __init__(self, devices, width, height, max_frames, params: VshStabParams | None = None):
+        self.params = params or stab_params_default()
+        self.width, self.height = width, height
+        dev = np.asarray(list(devices), np.int32)
+        self.h = C.c_void_p(load().vsh_multigpu_create(_p(dev), len(dev), width, height, max_frames, C.byref(self.params)))
+        if not self.h:
+            _raise("MultiGpuStabilizer")
+        crop = max(0, self.params.crop_pixels)
+        self.out_w, self.out_h = width - 2 * crop, height - 2 * crop
+
+    def stabilize(self, frames: np.ndarray):
+        """frames (n,h,w,3) u8 -> (stabilized (n-lag,oh,ow,3), meas (n,4), ok (n,))."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = frames.shape[0]
+        out = np.empty((n, self.out_h, self.out_w, 3), np.uint8)
+        meas, ok = np.zeros((n, 4)), np.zeros(n, np.uint8)
+        k = load().vsh_multigpu_stabilize(self.h, _p(frames), n, frames.strides[1], frames.strides[0], _p(out),
+                                          self.out_w * self.out_h * 3, _p(meas), _p(ok))
+        if k < 0:
+            _raise("stabilize")
+        return out[:k], meas, ok.astype(bool)
