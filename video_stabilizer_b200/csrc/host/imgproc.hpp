@@ -12,25 +12,34 @@
 
 #include <string>
 
+// Shorthand for the buffer types of the signatures below (aliases: the functions take exactly
+// Halide::Runtime::Buffer<T>&, as the reference's do).
+namespace vstab {
+using BufU8 = Halide::Runtime::Buffer<uint8_t>;
+using BufU16 = Halide::Runtime::Buffer<uint16_t>;
+using BufF32 = Halide::Runtime::Buffer<float>;
+using BufF64 = Halide::Runtime::Buffer<double>;
+}  // namespace vstab
+
 // ---- keyframe feature operators -------------------------------------------------------
 // sparse_jac (reference imgproc.hpp:8-14, imgproc.cpp:26-44): outputs are (re)allocated to
 // (tw, th, 4) when their shape does not match local_max_x.
-bool SparseJacobian(Halide::Runtime::Buffer<float>& grad_x, Halide::Runtime::Buffer<float>& grad_y,
-                    Halide::Runtime::Buffer<uint16_t>& local_max_x, Halide::Runtime::Buffer<uint16_t>& local_max_y,
-                    Halide::Runtime::Buffer<float>& output_x, Halide::Runtime::Buffer<float>& output_y);
+bool SparseJacobian(vstab::BufF32& grad_x, vstab::BufF32& grad_y,
+                    vstab::BufU16& local_max_x, vstab::BufU16& local_max_y,
+                    vstab::BufF32& output_x, vstab::BufF32& output_y);
 
 // pyr_down (imgproc.hpp:16-18): caller allocates `output`; its extent is the work domain.
-bool PyrDown(Halide::Runtime::Buffer<uint8_t>& input, Halide::Runtime::Buffer<uint8_t>& output);
+bool PyrDown(vstab::BufU8& input, vstab::BufU8& output);
 
 // grad_xy (imgproc.hpp:20-23): caller allocates both outputs.
-bool GradXY(Halide::Runtime::Buffer<uint8_t>& input, Halide::Runtime::Buffer<float>& output_x,
-            Halide::Runtime::Buffer<float>& output_y);
+bool GradXY(vstab::BufU8& input, vstab::BufF32& output_x,
+            vstab::BufF32& output_y);
 
 // grad_argmax (imgproc.hpp:25-32): picks tile_size (largest even value in [2,20] that keeps
 // at least 1000 tiles), (re)allocates the outputs to (w/tile, h/tile, 2) and writes, per tile,
 // the pixel position of the first maximum of |grad|.
-bool GradArgMax(Halide::Runtime::Buffer<float>& grad_x, Halide::Runtime::Buffer<float>& grad_y, int& tile_size,
-                Halide::Runtime::Buffer<uint16_t>& local_max_x, Halide::Runtime::Buffer<uint16_t>& local_max_y);
+bool GradArgMax(vstab::BufF32& grad_x, vstab::BufF32& grad_y, int& tile_size,
+                vstab::BufU16& local_max_x, vstab::BufU16& local_max_y);
 
 // ---- transform algebra (imgproc.hpp:34-65) ----------------------------------------------
 struct Point {
@@ -54,27 +63,27 @@ struct SimilarityTransform {
 
 // image_warp (imgproc.hpp:67-70): out(x,y) = bilinear(input, W(x,y)), repeat-edge, f32 output
 // allocated by the caller.
-bool ImageWarp(Halide::Runtime::Buffer<uint8_t>& input, const SimilarityTransform& transform,
-               Halide::Runtime::Buffer<float>& output);
+bool ImageWarp(vstab::BufU8& input, const SimilarityTransform& transform,
+               vstab::BufF32& output);
 
 // ---- cv::Mat <-> Buffer converters (imgproc.hpp:72-76); throw std::runtime_error on misuse
-Halide::Runtime::Buffer<uint8_t> mat_to_halide_buffer_u8(const cv::Mat& mat);
-Halide::Runtime::Buffer<uint8_t> bgr_mat_to_halide_buffer_u8(const cv::Mat& mat);
-cv::Mat halide_buffer_to_mat(const Halide::Runtime::Buffer<uint8_t>& buffer);
-cv::Mat halide_buffer_to_mat(const Halide::Runtime::Buffer<float>& buffer);
-cv::Mat halide_vec4_to_mat(const Halide::Runtime::Buffer<double>& vec4);
+vstab::BufU8 mat_to_halide_buffer_u8(const cv::Mat& mat);
+vstab::BufU8 bgr_mat_to_halide_buffer_u8(const cv::Mat& mat);
+cv::Mat halide_buffer_to_mat(const vstab::BufU8& buffer);
+cv::Mat halide_buffer_to_mat(const vstab::BufF32& buffer);
+cv::Mat halide_vec4_to_mat(const vstab::BufF64& vec4);
 
 // ---- sparse solver operators ------------------------------------------------------------
 // sparse_ica (imgproc.hpp:78-88): output(4) = 0.5 * sum_i J_i (template(p_i) - keyframe(W(p_i)))
-bool SparseICA(Halide::Runtime::Buffer<uint8_t>& input_template, Halide::Runtime::Buffer<uint8_t>& input_keyframe,
-               Halide::Runtime::Buffer<uint16_t>& selected_pixels_x, Halide::Runtime::Buffer<uint16_t>& selected_pixels_y,
-               Halide::Runtime::Buffer<float>& selected_jacobians_x, Halide::Runtime::Buffer<float>& selected_jacobians_y,
-               const SimilarityTransform& transform, Halide::Runtime::Buffer<double>& output);
+bool SparseICA(vstab::BufU8& input_template, vstab::BufU8& input_keyframe,
+               vstab::BufU16& selected_pixels_x, vstab::BufU16& selected_pixels_y,
+               vstab::BufF32& selected_jacobians_x, vstab::BufF32& selected_jacobians_y,
+               const SimilarityTransform& transform, vstab::BufF64& output);
 
 // sparse_warpdiff (imgproc.hpp:90-95): output(tw,th) = trunc |keyframe(W(p)) - template(p)|
-bool SparseWarpDiff(Halide::Runtime::Buffer<uint8_t>& input_template, Halide::Runtime::Buffer<uint8_t>& input_keyframe,
-                    Halide::Runtime::Buffer<uint16_t>& local_max, const SimilarityTransform& transform,
-                    Halide::Runtime::Buffer<uint16_t>& output);
+bool SparseWarpDiff(vstab::BufU8& input_template, vstab::BufU8& input_keyframe,
+                    vstab::BufU16& local_max, const SimilarityTransform& transform,
+                    vstab::BufU16& output);
 
 // imgproc.hpp:97 — the BGR warp of the stabilizer: bit-exact with
 // cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT) of the forward matrix built from `transform`.
