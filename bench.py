@@ -137,10 +137,11 @@ def _cpu_frames(width, height, n, seed):
 _CPU_CLIPS = {}
 
 
-def cpu_reference(width, height, frames_per_thread, threads, crop, repeat=1):
-    """Frames/s of the reference CPU implementation: `threads` workers, one stabilizer each
-    over its own clip (the reference's scale-out recipe, grid_search_align.cpp:105-118,159-210).
-    Returns (frames_per_s, kind, seconds)."""
+def cpu_reference(width, height, frames_per_thread, threads, crop, passes=1, clip=None):
+    """Frames/s of the reference CPU implementation: `threads` workers, one stabilizer each (the
+    reference's scale-out recipe, grid_search_align.cpp:105-118,159-210).  Every worker plays the
+    clip forwards, then backwards, ... `passes` times (the turn-around keeps the motion continuous),
+    so the sample is threads x frames_per_thread x passes frames.  Returns (frames_per_s, kind, seconds)."""
     from oracle import binding as ob
     use_ref = ob.ref_available()
     if use_ref:
@@ -149,30 +150,34 @@ def cpu_reference(width, height, frames_per_thread, threads, crop, repeat=1):
         except Exception:
             use_ref = False
     kind = "reference" if use_ref else "port"
-    key = (width, height, frames_per_thread)
-    if key not in _CPU_CLIPS:
-        _CPU_CLIPS[key] = _cpu_frames(width, height, frames_per_thread, 4242)
-    base = _CPU_CLIPS[key]
-    clips = [base] * threads          # read-only input shared by the workers; every worker owns its stabilizer
+    if clip is None:
+        key = (width, height, frames_per_thread)
+        if key not in _CPU_CLIPS:
+            _CPU_CLIPS[key] = _cpu_frames(width, height, frames_per_thread, 4242)
+        clip = _CPU_CLIPS[key]
     p = ob.stab_params_default()
     p.crop_pixels = crop
 
     def work(t):
         st = ob.RefStabilizer(p, fast=True) if use_ref else ob.Stabilizer(p, fast=True)
-        for f in clips[t]:
-            st.process(f)
+        for k in range(passes):
+            for f in (clip if k % 2 == 0 else clip[::-1]):      # read-only input shared by the workers
+                st.process(f)
 
-    best = None
-    for _ in range(repeat):
-        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-        t0 = time.perf_counter()
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return threads * frames_per_thread / best, kind, best
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    return threads * len(clip) * passes / dt, kind, dt
+
+
+def cpu_passes_for(width, height, frames_per_thread, threads, crop, target_seconds, clip=None):
+    """One calibration pass, then how many passes make the sample last about target_seconds."""
+    _, _, dt = cpu_reference(width, height, frames_per_thread, threads, crop, 1, clip)
+    return int(max(1, min(200, round(target_seconds / max(dt, 1e-3)))))
 
 
 def run_reference_arm(args):
@@ -182,21 +187,25 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, args.cpu_threads or cores))
     per_thread = args.cpu_frames
+    # each step is a bounded sample sized so that the whole --steps/--warmup run stays around 2-3 minutes
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    passes = cpu_passes_for(args.width, args.height, per_thread, threads, args.crop, min(budget, 20.0))
     times = []
     kind = "port"
     for i in range(args.warmup + args.steps):
-        fps, kind, dt = cpu_reference(args.width, args.height, per_thread, threads, args.crop)
+        fps, kind, dt = cpu_reference(args.width, args.height, per_thread, threads, args.crop, passes)
         if i >= args.warmup:
             times.append(dt)
     ms = 1000.0 * float(np.mean(times))
-    value = threads * per_thread / (ms / 1000.0)
-    sample = "%d threads x one %d-frame %dx%d clip each per step (one VideoStabilizer per thread)" % (
-        threads, per_thread, args.width, args.height)
+    frames_per_step = threads * per_thread * passes
+    value = frames_per_step / (ms / 1000.0)
+    sample = "%d threads x a %d-frame %dx%d clip played %d times (forwards/backwards) per step, one VideoStabilizer per thread" % (
+        threads, per_thread, args.width, args.height, passes)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32/f64", "data": "synthetic",
-        "config": workload_config(args, frames=threads * per_thread),
+        "config": workload_config(args, frames=frames_per_step),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -370,10 +379,12 @@ def run_gpu_arm(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         threads = max(1, min(cores, args.cpu_threads or cores))
-        fps, kind, dt = cpu_reference(W, H, args.cpu_frames, threads, crop)
+        cpu_clip = frames[: args.cpu_frames]          # the first frames of the very clip the GPU arm stabilizes
+        passes = cpu_passes_for(W, H, args.cpu_frames, threads, crop, 12.0, cpu_clip)
+        fps, kind, dt = cpu_reference(W, H, args.cpu_frames, threads, crop, passes, cpu_clip)
         cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": "%d threads x one %d-frame %dx%d clip each (one VideoStabilizer per thread), %.1f s" % (
-                   threads, args.cpu_frames, W, H, dt)}
+               "sample": "%d threads x the first %d frames of the %dx%d clip played %d times (forwards/backwards), one VideoStabilizer per thread, %.1f s" % (
+                   threads, args.cpu_frames, W, H, passes, dt)}
 
     value = world * F / (ms / 1e3)
     line = {
