@@ -295,10 +295,9 @@ k_image_warp(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, i
 }
 
 // ------------------------------------------------------------------ BGR warp
-// warpBySimilarityTransform (imgproc.cpp:446-484).  Mode 0 is bit-exact with
-// cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT): 10-bit fixed-point coordinates rounded to
-// 1/32 px, integer weights; (sum w p + 16384) >> 15 with w = wx*wy*32 equals
-// (sum wx*wy*p + 512) >> 10.
+// Float-bilinear and Lanczos-2 modes of the BGR warp (BASELINE.json configs[4] sweep; they have no
+// counterpart in the reference, whose stabilizer uses cv::warpAffine): one thread per pixel, direct
+// loads.  The cv-exact mode (imgproc.cpp:446-484) has its own tiled kernels further down.
 template <int MODE, int BORDER>
 __device__ __forceinline__ float bgr_tap_f(const uint8_t* __restrict__ src, int64_t stride, int w, int h,
                                            int x, int y, int c)
@@ -327,40 +326,6 @@ k_bgr_warp(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src
     uint8_t* d = dst_base + (size_t)b * dst_bs + (size_t)yo * dst_stride + 3 * xo;
     const VsWarpCoef cf = coefs[b];
     const int x = xo + dst_x0, y = yo + dst_y0;
-
-    if (MODE == VS_WARP_CV_EXACT_BILINEAR) {
-        int adelta = __double2int_rn(cf.i00 * (double)x * 1024.0);
-        int bdelta = __double2int_rn(cf.i10 * (double)x * 1024.0);
-        int X0 = __double2int_rn((cf.i01 * (double)y + cf.i02) * 1024.0) + 16;
-        int Y0 = __double2int_rn((cf.i11 * (double)y + cf.i12) * 1024.0) + 16;
-        int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
-        int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
-        int w00 = (32 - fx) * (32 - fy), w10 = fx * (32 - fy), w01 = (32 - fx) * fy, w11 = fx * fy;
-        int x1 = sx + 1, y1 = sy + 1;
-        bool in00, in10, in01, in11;
-        int cx0 = sx, cx1 = x1, cy0 = sy, cy1 = y1;
-        if (BORDER == VS_BORDER_REPEAT_EDGE) {
-            cx0 = vs_clampi(sx, 0, w - 1); cx1 = vs_clampi(x1, 0, w - 1);
-            cy0 = vs_clampi(sy, 0, h - 1); cy1 = vs_clampi(y1, 0, h - 1);
-            in00 = in10 = in01 = in11 = true;
-        } else {
-            bool xin0 = sx >= 0 && sx < w, xin1 = x1 >= 0 && x1 < w;
-            bool yin0 = sy >= 0 && sy < h, yin1 = y1 >= 0 && y1 < h;
-            in00 = xin0 && yin0; in10 = xin1 && yin0; in01 = xin0 && yin1; in11 = xin1 && yin1;
-        }
-        const uint8_t* r0 = src + (size_t)cy0 * src_stride;
-        const uint8_t* r1 = src + (size_t)cy1 * src_stride;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            int p00 = in00 ? (int)__ldg(r0 + 3 * cx0 + c) : 0;
-            int p10 = in10 ? (int)__ldg(r0 + 3 * cx1 + c) : 0;
-            int p01 = in01 ? (int)__ldg(r1 + 3 * cx0 + c) : 0;
-            int p11 = in11 ? (int)__ldg(r1 + 3 * cx1 + c) : 0;
-            int v = w00 * p00 + w10 * p10 + w01 * p01 + w11 * p11;
-            d[c] = (uint8_t)((v + 512) >> 10);
-        }
-        return;
-    }
 
     const float f00 = (float)cf.i00, f01 = (float)cf.i01, f02 = (float)cf.i02;
     const float f10 = (float)cf.i10, f11 = (float)cf.i11, f12 = (float)cf.i12;
@@ -1129,9 +1094,7 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
     }
     dim3 block(256), grid(vs_cdiv(dst.w, 256), dst.h, dst.batch);
     VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
-    if (mode == VS_WARP_CV_EXACT_BILINEAR)
-        launch_bgr_warp<VS_WARP_CV_EXACT_BILINEAR>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
-    else if (mode == VS_WARP_FLOAT_BILINEAR)
+    if (mode == VS_WARP_FLOAT_BILINEAR)
         launch_bgr_warp<VS_WARP_FLOAT_BILINEAR>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
     else
         launch_bgr_warp<VS_WARP_LANCZOS2>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
