@@ -180,7 +180,7 @@ __device__ __forceinline__ uint4 kf_load_row(const uint8_t* __restrict__ img, in
     return v;
 }
 
-__global__ void __launch_bounds__(KF_THREADS)
+__global__ void __launch_bounds__(KF_THREADS, 8)
 k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t* __restrict__ slots,
                     uint32_t* __restrict__ kp, float4* __restrict__ jac)
 {
@@ -203,6 +203,7 @@ k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t
         for (int i = 0; i < 16; i++) { mx[i] = 0u; my[i] = 0u; }
         uint4 prev = kf_load_row(img, L.pitch, L.w, L.h, y0 - 1, x0);
         uint4 cur = kf_load_row(img, L.pitch, L.w, L.h, y0, x0);
+#pragma unroll 2
         for (int ry = 0; ry < N; ry++) {
             const int y = y0 + ry;
             const uint4 next = kf_load_row(img, L.pitch, L.w, L.h, y + 1, x0);
