@@ -145,6 +145,34 @@ def test_clip_warp_matches_oracle(gpu, ob):
     clip.close()
 
 
+@pytest.mark.parametrize("w,h", [(640, 360), (650, 187), (161, 40)])
+def test_clip_warp_row_group_kernel_every_path(gpu, ob, w, h):
+    """The production warp (k_bgr_warp_cv_rows) against the oracle on transforms that exercise each of its paths:
+    regular groups (near identity), fx = fy = 0 everywhere (identity, integer shifts), irregular groups (moderate
+    rotation / scale: the per-pixel list), tiles whose source box does not fit (large rotation / scale: global
+    path), content leaving the frame on every side, widths and crops that are not multiples of 4 or 128."""
+    from video_stabilizer_b200.clip import Clip
+    rng = np.random.default_rng(w * 7 + h)
+    frames = rng.integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+    clip = Clip(w, h, 3, ctx=gpu)
+    clip.upload(0, frames)
+    Ts = [[0, 0, 0, 0], [0, 0, 7, -3], [0, 0, -33, 18], [0.0007, -0.0004, 1.37, -2.61], [-0.002, 0.0015, -9.8, 4.4],
+          [0.001, 0.02, 3.3, 2.2], [0.03, -0.015, -4.1, 0.7], [-0.04, 0.0, 0.25, 0.25], [0.0, 0.2, 5.5, -7.5],
+          [-0.3, 0.05, 2.0, 1.0], [0.5, -0.4, 0.0, 0.0], [0.001, 0.001, w * 0.9, 0.0], [0.001, -0.001, 0.0, -h * 0.95],
+          [0.0, 0.0, 3.0 * w, 0.0], [0, 0, 0.5, 0.5], [0, 0, 1.0 / 32, 0], [1e-13, 0, 0.49999, 0.0]]
+    for crop in (0, 5, 32):
+        if w - 2 * crop < 8 or h - 2 * crop < 8:
+            continue
+        for i in range(0, len(Ts), 3):
+            T = np.array(Ts[i:i + 3], np.float64)
+            slots = [(i + k) % 3 for k in range(len(T))]
+            out = clip.warp(slots, T, crop=crop)
+            for k in range(len(T)):
+                want = ob.warp_bgr(frames[slots[k]], T[k], 0, 0, crop)
+                assert np.array_equal(out[k], want), (crop, Ts[i + k], int(np.abs(out[k].astype(int) - want).max()))
+    clip.close()
+
+
 def test_synth_gpu_renderer_is_bit_identical_to_numpy(gpu):
     from video_stabilizer_b200 import synth
     a, pa = synth.make_clip_numpy(320, 180, 3, 4)

@@ -19,7 +19,9 @@ struct vs_clip {
     // TMA descriptor of the BGR store viewed as u32 [slot][row][pitch/4], box {108 words, 20 rows, 1}:
     // the cv-exact warp fetches a tile's source box with one cp.async.bulk.tensor (first member: 64-byte aligned)
     CUtensorMap bgr_map;
-    bool bgr_map_ok = false;
+    CUtensorMap bgr_map_rows;         // box of the row-group kernel (160 pixels x 28 rows)
+    bool bgr_map_ok = false, bgr_map_rows_ok = false;
+    int32_t* d_warp_tab = nullptr;    // fixed-point column / row tables of the row-group warp, capacity images
     vs_ctx* ctx = nullptr;
     int w = 0, h = 0, capacity = 0, max_pairs = 0, flags = 0;
     vs_align_params params;
@@ -87,6 +89,7 @@ void free_all(vs_clip* c)
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
     cudaFree(c->d_pos_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
+    cudaFree(c->d_warp_tab);
 }
 
 // cuTensorMapEncodeTiled lives in the driver library; resolve it through the runtime so that
@@ -123,12 +126,30 @@ void build_bgr_tensor_map(vs_clip* c)
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     c->bgr_map_ok = (r == CUDA_SUCCESS);
+
+    // VSTAB_WARP_KERNEL=tma selects the previous (expanded-plane) kernel for A/B measurements
+    const char* kenv = getenv("VSTAB_WARP_KERNEL");
+    if (kenv && strcmp(kenv, "tma") == 0) return;
+    if ((int)(c->bgr_pitch / 4) < VS_WARP_ROWS_BOX_WORDS || c->h < VS_WARP_ROWS_BOX_ROWS) return;
+    if (cudaMalloc((void**)&c->d_warp_tab, vs_warp_rows_tab_ints(c->w, c->h) * c->capacity * sizeof(int32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        c->d_warp_tab = nullptr;
+        return;
+    }
+    const cuuint32_t box_rows[3] = {(cuuint32_t)VS_WARP_ROWS_BOX_WORDS, (cuuint32_t)VS_WARP_ROWS_BOX_ROWS, 1};
+    r = enc(&c->bgr_map_rows, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->d_bgr, dims, strides, box_rows, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    c->bgr_map_rows_ok = (r == CUDA_SUCCESS);
 }
 
 // the BGR warp of a clip: TMA-staged kernel for the production mode, generic kernels otherwise
 int clip_warp_launch(vs_clip* c, const int32_t* d_slots, const VsWarpCoef* d_coef, const VsDevImg& dst, int crop, int mode, int border, int n)
 {
     VsDevImg src{c->d_bgr, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
+    if (mode == VS_WARP_CV_EXACT_BILINEAR && border == VS_BORDER_CONSTANT0 && c->bgr_map_rows_ok && n <= c->capacity &&
+        dst.w <= c->w && dst.h <= c->h)
+        return vsk_bgr_warp_slots_rows(c->ctx, &c->bgr_map_rows, src, d_slots, d_coef, dst, crop, crop, c->d_warp_tab);
     if (mode == VS_WARP_CV_EXACT_BILINEAR && border == VS_BORDER_CONSTANT0 && c->bgr_map_ok)
         return vsk_bgr_warp_slots_tma(c->ctx, &c->bgr_map, src, d_slots, d_coef, dst, crop, crop);
     return vsk_bgr_warp_slots(c->ctx, src, d_slots, d_coef, dst, crop, crop, mode, border);

@@ -750,6 +750,239 @@ k_bgr_warp_cv_tma(const __grid_constant__ CUtensorMap src_map, const uint8_t* __
     }
 }
 
+// ------------------------------------------------------------------ BGR warp, cv-exact, row groups on the raw box
+// Same bits as the two kernels above, about half their instructions and a third of their shared-memory
+// traffic: no expanded copy of the source is built.  A thread owns four consecutive output pixels
+// (12 output bytes = three whole words) of one row.  For the near-identity similarity transforms of a
+// stabiliser those four pixels almost always read four consecutive source pixels of ONE source row pair
+// ("regular group"): then the 15 source bytes of a row are five aligned shared-memory words of the
+// TMA-fetched raw box, brought to byte alignment by four funnel shifts, and the paired taps
+// (B,B',G,G') / (R,R') of all four pixels are eight PRMTs with fixed selectors.  Weights are scaled by 64
+// so that every blended channel lands in byte 2 of its accumulator ((64 S + 32768) >> 16 == (S + 512) >> 10)
+// and the 12 output bytes are assembled by nine PRMTs, stored as three words (lane stride 3 words:
+// conflict-free) and written out with 16-byte vectors.  (The scaled top-left weight is 65536 when
+// fx = fy = 0; 65535 is substituted, which yields the same byte.)  Groups whose pixels do not share one
+// source row or consecutive source columns, and groups cut by the right image edge, are pushed to a list
+// and redone pixel by pixel from the same raw box after the main loop — same arithmetic, nothing
+// approximated.  The fixed-point column and row terms (cv::warpAffine's adelta/bdelta, X0/Y0: the only
+// f64 work) come from a small table kernel that runs once per launch instead of once per tile.
+constexpr int WG_W = 128, WG_H = 24, WG_THREADS = 128, WG_WARPS = 4, WG_ROWS_PER_WARP = WG_H / WG_WARPS;
+constexpr int WG_BOX_WORDS = VS_WARP_ROWS_BOX_WORDS, WG_BOX_ROWS = VS_WARP_ROWS_BOX_ROWS;   // 160 pixels x 28 rows
+constexpr int WG_BOX_PIXELS = WG_BOX_WORDS * 4 / 3;
+constexpr int WG_RAW_PITCH = WG_BOX_WORDS * 4;                       // bytes per box row
+constexpr int WG_RAW_BYTES = WG_RAW_PITCH * WG_BOX_ROWS;             // 13440: the TMA transaction size
+constexpr int WG_OUT_OFF = (WG_RAW_BYTES + 64 + 127) / 128 * 128;    // raw box + over-read pad of the last lane's window
+constexpr int WG_OUT_ROW_WORDS = WG_W * 3 / 4;                       // 96 words = 384 bytes per output row
+constexpr int WG_LIST_OFF = WG_OUT_OFF + WG_OUT_ROW_WORDS * 4 * WG_H;
+constexpr int WG_SMEM_BYTES = WG_LIST_OFF + WG_H * 32 * 2;           // one list entry per group at most
+static_assert(WG_BOX_PIXELS == 160 && WG_H % WG_WARPS == 0, "box / tile geometry");
+
+// per launch: image b has AD[dwp], BD[dwp] (column terms) and XY0[dhp] (row terms, rounding offset included)
+__global__ void __launch_bounds__(256)
+k_warp_tables(const VsWarpCoef* __restrict__ coefs, int dwp, int dhp, int dst_x0, int dst_y0, int32_t* __restrict__ tab)
+{
+    const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    const VsWarpCoef cf = coefs[b];
+    int32_t* const t = tab + (size_t)b * (2 * dwp + 2 * dhp);
+    if (i < dwp) {
+        const int x = i + dst_x0;
+        t[i] = __double2int_rn(cf.i00 * (double)x * 1024.0);
+        t[dwp + i] = __double2int_rn(cf.i10 * (double)x * 1024.0);
+    } else if (i < dwp + dhp) {
+        const int y = i - dwp + dst_y0;
+        reinterpret_cast<int2*>(t + 2 * dwp)[i - dwp] = make_int2(__double2int_rn((cf.i01 * (double)y + cf.i02) * 1024.0) + 16,
+                                                                  __double2int_rn((cf.i11 * (double)y + cf.i12) * 1024.0) + 16);
+    }
+}
+
+// packed 16-bit weight pairs of one pixel scaled by 64: wt = 64 w00 | 64 w10 << 16, wb = 64 w01 | 64 w11 << 16
+// (w = (32 - fx | fx) (32 - fy | fy))
+__device__ __forceinline__ void wg_weights(int sfx, int sfy, uint32_t& wt, uint32_t& wb)
+{
+    const uint32_t hp = (uint32_t)(sfx & 0x3e0) * 65535u + 1024u;    // 32 (32 - fx) | 32 fx << 16
+    const uint32_t fy2 = ((uint32_t)sfy >> 4) & 0x3eu;               // 2 fy
+    wb = fy2 * hp;
+    wt = hp * 64u - wb;
+    // fx == fy == 0: 64 w00 = 65536 is not a 16-bit value; 65535 gives the same byte 2 (65535 p + 32768 = 65536 p + (32768 - p))
+    if (((sfx | sfy) & 0x3e0) == 0) wt = 0xffffu;
+}
+
+__device__ __forceinline__ void wg_blend(uint32_t wt, uint32_t wb, uint32_t tx, uint32_t ty, uint32_t bx, uint32_t by,
+                                         uint32_t& b, uint32_t& g, uint32_t& r)
+{
+    b = __dp2a_lo(wt, tx, 32768u); g = __dp2a_hi(wt, tx, 32768u); r = __dp2a_lo(wt, ty, 32768u);
+    b = __dp2a_lo(wb, bx, b); g = __dp2a_hi(wb, bx, g); r = __dp2a_lo(wb, by, r);
+}
+
+// byte 2 of four accumulators -> one output word
+__device__ __forceinline__ uint32_t wg_pack(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return __byte_perm(__byte_perm(a, b, 0x0062), __byte_perm(c, d, 0x0062), 0x5410);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 8)
+k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const uint8_t* __restrict__ src_base, int64_t src_stride,
+                   int64_t src_bs, int w, int h, const int32_t* __restrict__ slots, const int32_t* __restrict__ tab,
+                   int dwp, int dhp, uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
+                   int dst_al16)
+{
+    extern __shared__ __align__(128) uint32_t wg_smem[];
+    uint32_t* const RAW = wg_smem;                                 // [WG_BOX_ROWS][WG_BOX_WORDS]
+    uint32_t* const O = wg_smem + WG_OUT_OFF / 4;                  // [WG_H][WG_OUT_ROW_WORDS]
+    uint16_t* const LIST = reinterpret_cast<uint16_t*>(wg_smem + WG_LIST_OFF / 4);
+    __shared__ int2 sXY0[WG_H];                                    // row terms relative to the box origin
+    __shared__ int sCount;
+    __shared__ __align__(8) unsigned long long tma_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int ox0 = blockIdx.x * WG_W, oy0 = blockIdx.y * WG_H;
+    const int tw = min(WG_W, dw - ox0), th = min(WG_H, dh - oy0);
+    const int slot = slots ? slots[b] : b;
+    const int32_t* const AD = tab + (size_t)b * (2 * dwp + 2 * dhp) + ox0;
+    const int32_t* const BD = AD + dwp;
+    const int2* const XY = reinterpret_cast<const int2*>(tab + (size_t)b * (2 * dwp + 2 * dhp) + 2 * dwp) + oy0;
+
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+    if (tid == 0) {
+        sCount = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    // source bounding box of the tile from its four corners (column and row terms are monotone)
+    const int aL = __ldg(AD), aR = __ldg(AD + tw - 1), bL = __ldg(BD), bR = __ldg(BD + tw - 1);
+    const int2 xyT = __ldg(XY), xyB = __ldg(XY + th - 1);
+    const int sxmin = (min(xyT.x, xyB.x) + min(aL, aR)) >> 10, sxmax = (max(xyT.x, xyB.x) + max(aL, aR)) >> 10;
+    const int symin = (min(xyT.y, xyB.y) + min(bL, bR)) >> 10, symax = (max(xyT.y, xyB.y) + max(bL, bR)) >> 10;
+    const int bx0 = (sxmin >> 4) * 16;                            // a TMA box starts 16-byte aligned: 16 pixels = 48 bytes
+    const int by0 = symin;
+    // pixels bx0 .. sxmax + 1 and rows symin .. symax + 1 must be inside the box
+    const bool staged = sxmax + 1 - bx0 < WG_BOX_PIXELS && symax + 1 - symin < WG_BOX_ROWS &&
+                        sxmin > -(1 << 20) && sxmax < (1 << 20) && symin > -(1 << 20) && symax < (1 << 20);
+    const int orgx = staged ? bx0 << 10 : 0, orgy = staged ? by0 << 10 : 0;
+    if (tid < WG_H) {
+        const int2 xy = __ldg(XY + min(tid, th - 1));
+        sXY0[tid] = make_int2(xy.x - orgx, xy.y - orgy);
+    }
+    const int4 ad4 = __ldg(reinterpret_cast<const int4*>(AD) + lane);
+    const int4 bd4 = __ldg(reinterpret_cast<const int4*>(BD) + lane);
+    __syncthreads();
+
+    uint8_t* const Ob = reinterpret_cast<uint8_t*>(O);
+    if (staged) {
+        if (tid == 0) {
+            const uint32_t dstsm = (uint32_t)__cvta_generic_to_shared(RAW);
+            const int c0 = (bx0 >> 4) * 12;                       // first 32-bit word of pixel bx0, may be negative
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WG_RAW_BYTES) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(dstsm), "l"(reinterpret_cast<uint64_t>(&src_map)), "r"(c0), "r"(by0), "r"(slot), "r"(bar)
+                : "memory");
+        }
+        // column terms with the pixel's offset inside the group taken out: a regular group has one integer part
+        const int a0 = ad4.x, a1 = ad4.y - 1024, a2 = ad4.z - 2048, a3 = ad4.w - 3072;
+        const bool whole = 4 * lane + 3 < tw;
+        uint32_t done = 0, spins = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar) : "memory");
+            if (!done && ++spins > (1u << 24)) __trap();   // a lost transaction must fail loudly, not hang the GPU
+        }
+#pragma unroll 1
+        for (int k = 0; k < WG_ROWS_PER_WARP; k++) {
+            const int r = warp * WG_ROWS_PER_WARP + k;
+            if (r >= th) break;
+            const int2 xy0 = sXY0[r];
+            const int x0 = xy0.x + a0, x1 = xy0.x + a1, x2 = xy0.x + a2, x3 = xy0.x + a3;
+            const int y0 = xy0.y + bd4.x, y1 = xy0.y + bd4.y, y2 = xy0.y + bd4.z, y3 = xy0.y + bd4.w;
+            uint32_t wt0, wb0, wt1, wb1, wt2, wb2, wt3, wb3;
+            wg_weights(x0, y0, wt0, wb0); wg_weights(x1, y1, wt1, wb1);
+            wg_weights(x2, y2, wt2, wb2); wg_weights(x3, y3, wt3, wb3);
+            // one source row pair (the row term is monotone in x: the ends decide) and consecutive source columns
+            const uint32_t spread = (uint32_t)((x1 ^ x0) | (x2 ^ x0) | (x3 ^ x0) | (y3 ^ y0));
+            if (whole && spread < 1024u) {
+                const uint32_t byte = (uint32_t)(y0 >> 10) * (uint32_t)WG_RAW_PITCH + (uint32_t)(x0 >> 10) * 3u;
+                const uint32_t* const p = RAW + (byte >> 2);
+                const uint32_t sh = byte << 3;                    // funnel shifts use the low five bits: 8 (byte & 3)
+                const uint32_t t0 = p[0], t1 = p[1], t2 = p[2], t3 = p[3], t4 = p[4];
+                const uint32_t c0 = p[WG_BOX_WORDS], c1 = p[WG_BOX_WORDS + 1], c2 = p[WG_BOX_WORDS + 2],
+                               c3 = p[WG_BOX_WORDS + 3], c4 = p[WG_BOX_WORDS + 4];
+                const uint32_t u0 = __funnelshift_r(t0, t1, sh), u1 = __funnelshift_r(t1, t2, sh),
+                               u2 = __funnelshift_r(t2, t3, sh), u3 = __funnelshift_r(t3, t4, sh);
+                const uint32_t v0 = __funnelshift_r(c0, c1, sh), v1 = __funnelshift_r(c1, c2, sh),
+                               v2 = __funnelshift_r(c2, c3, sh), v3 = __funnelshift_r(c3, c4, sh);
+                // stream bytes of pixel j start at 3j: taps (s[3j], s[3j+3], s[3j+1], s[3j+4]) and (s[3j+2], s[3j+5])
+                uint32_t b0, g0, r0, b1, g1, r1, b2, g2, r2, b3, g3, r3;
+                wg_blend(wt0, wb0, __byte_perm(u0, u1, 0x4130), __byte_perm(u0, u1, 0x0052),
+                         __byte_perm(v0, v1, 0x4130), __byte_perm(v0, v1, 0x0052), b0, g0, r0);
+                wg_blend(wt1, wb1, __byte_perm(u0, u1, 0x7463), __byte_perm(u1, u2, 0x0041),
+                         __byte_perm(v0, v1, 0x7463), __byte_perm(v1, v2, 0x0041), b1, g1, r1);
+                wg_blend(wt2, wb2, __byte_perm(u1, u2, 0x6352), __byte_perm(u2, u2, 0x0030),
+                         __byte_perm(v1, v2, 0x6352), __byte_perm(v2, v2, 0x0030), b2, g2, r2);
+                wg_blend(wt3, wb3, __byte_perm(u2, u3, 0x5241), __byte_perm(u2, u3, 0x0063),
+                         __byte_perm(v2, v3, 0x5241), __byte_perm(v2, v3, 0x0063), b3, g3, r3);
+                uint32_t* const o = O + r * WG_OUT_ROW_WORDS + 3 * lane;
+                o[0] = wg_pack(b0, g0, r0, b1);
+                o[1] = wg_pack(g1, r1, b2, g2);
+                o[2] = wg_pack(r2, b3, g3, r3);
+            } else if (4 * lane < tw) {
+                LIST[atomicAdd(&sCount, 1)] = (uint16_t)(r * 32 + lane);
+            }
+        }
+        __syncthreads();
+        // irregular groups, pixel by pixel from the raw box (every tap of the tile is inside it)
+        const int nfix = sCount * 4;
+        const uint8_t* const Rb = reinterpret_cast<const uint8_t*>(RAW);
+        for (int i = tid; i < nfix; i += WG_THREADS) {
+            const int e = LIST[i >> 2], r = e >> 5, x = 4 * (e & 31) + (i & 3);
+            if (x >= tw) continue;
+            const int2 xy0 = sXY0[r];
+            const int sfx = xy0.x + __ldg(AD + x), sfy = xy0.y + __ldg(BD + x);
+            const uint8_t* const q = Rb + (sfy >> 10) * WG_RAW_PITCH + (sfx >> 10) * 3;
+            const uint32_t t00 = q[0] | (q[1] << 8) | (q[2] << 16), t10 = q[3] | (q[4] << 8) | (q[5] << 16);
+            const uint32_t t01 = q[WG_RAW_PITCH] | (q[WG_RAW_PITCH + 1] << 8) | (q[WG_RAW_PITCH + 2] << 16),
+                           t11 = q[WG_RAW_PITCH + 3] | (q[WG_RAW_PITCH + 4] << 8) | (q[WG_RAW_PITCH + 5] << 16);
+            const uint32_t px = cv_blend(wt_entry(t00, t10), wt_entry(t01, t11), (sfx >> 5) & 31, (sfy >> 5) & 31);
+            uint8_t* const o = Ob + r * (WG_OUT_ROW_WORDS * 4) + 3 * x;
+            o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+        }
+    } else {
+        // the box does not fit (large rotation or scale): every pixel straight from global memory
+        const uint8_t* const src = src_base + (size_t)slot * src_bs;
+        for (int i = tid; i < tw * th; i += WG_THREADS) {
+            const int r = i / tw, x = i - r * tw;
+            const int2 xy0 = sXY0[r];
+            const int sfx = xy0.x + __ldg(AD + x), sfy = xy0.y + __ldg(BD + x);
+            const int sx = sfx >> 10, sy = sfy >> 10;
+            const uint32_t t00 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx, sy);
+            const uint32_t t10 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx + 1, sy);
+            const uint32_t t01 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx, sy + 1);
+            const uint32_t t11 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx + 1, sy + 1);
+            const uint32_t px = cv_blend(wt_entry(t00, t10), wt_entry(t01, t11), (sfx >> 5) & 31, (sfy >> 5) & 31);
+            uint8_t* const o = Ob + r * (WG_OUT_ROW_WORDS * 4) + 3 * x;
+            o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+        }
+    }
+    __syncthreads();
+
+    // write the tile: 16-byte vectors when the destination allows it (24 per full row)
+    uint8_t* const drow0 = dst_base + (size_t)b * dst_bs + (size_t)oy0 * dst_stride + (size_t)ox0 * 3;
+    if (dst_al16 && tw == WG_W) {
+        constexpr int VPR = WG_W * 3 / 16;
+        for (int i = tid; i < th * VPR; i += WG_THREADS) {
+            const int r = i / VPR, c = i - r * VPR;
+            reinterpret_cast<uint4*>(drow0 + (size_t)r * dst_stride)[c] = reinterpret_cast<const uint4*>(O + r * WG_OUT_ROW_WORDS)[c];
+        }
+    } else {
+        const int row_bytes = tw * 3;
+        for (int i = tid; i < th * row_bytes; i += WG_THREADS) {
+            const int r = i / row_bytes, c = i - r * row_bytes;
+            drow0[(size_t)r * dst_stride + c] = Ob[r * (WG_OUT_ROW_WORDS * 4) + c];
+        }
+    }
+}
+
 // ------------------------------------------------------------------ BGR warp, cv-exact, TMA-staged, persistent
 // k_bgr_warp_cv_tma as a persistent kernel: a CTA walks tiles t, t + gridDim.x, ... and keeps two raw
 // boxes in flight, so the TMA fetch of the next tile (issued by thread 0 right after the barrier that
@@ -1132,6 +1365,27 @@ int vsk_bgr_warp_slots_tma(vs_ctx* ctx, const void* tensor_map, const VsDevImg& 
             *reinterpret_cast<const CUtensorMap*>(tensor_map), (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
             d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, dst_al8);
     }
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+// clip-resident sources, row-group kernel: table kernel + warp kernel on the same stream
+int vsk_bgr_warp_slots_rows(vs_ctx* ctx, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,
+                            const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0, int32_t* d_tab)
+{
+    VS_REQUIRE(ctx, tensor_map && d_tab && src.w > 0 && src.h > 0, "bgr_warp_rows: bad source");
+    if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
+    VS_REQUIRE(ctx, vs_cdiv(dst.h, WG_H) <= 65535 && dst.batch <= 65535, "bgr_warp_rows: grid too large");
+    const int dwp = vs_cdiv(dst.w, WG_W) * WG_W, dhp = vs_cdiv(dst.h, WG_H) * WG_H;
+    const int dst_al16 = aligned_to(dst.data, 16) && dst.stride % 16 == 0 && dst.batch_stride % 16 == 0;
+    VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
+    VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
+    k_warp_tables<<<dim3(vs_cdiv(dwp + dhp, 256), dst.batch), 256, 0, ctx->stream>>>(d_coef, dwp, dhp, dst_x0, dst_y0, d_tab);
+    ctx->launches++;
+    dim3 tgrid(vs_cdiv(dst.w, WG_W), vs_cdiv(dst.h, WG_H), dst.batch);
+    k_bgr_warp_cv_rows<<<tgrid, WG_THREADS, WG_SMEM_BYTES, ctx->stream>>>(
+        *reinterpret_cast<const CUtensorMap*>(tensor_map), (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
+        d_slots, d_tab, dwp, dhp, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_al16);
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
