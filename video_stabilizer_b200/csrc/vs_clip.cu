@@ -92,22 +92,9 @@ void free_all(vs_clip* c)
     cudaFree(c->d_warp_tab);
 }
 
-// cuTensorMapEncodeTiled lives in the driver library; resolve it through the runtime so that
-// libvstab.so keeps linking against cudart only
 PFN_cuTensorMapEncodeTiled tensor_map_encoder()
 {
-    static PFN_cuTensorMapEncodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
-        else
-            cudaGetLastError();
-    }
-    return fn;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(vs_tensor_map_encoder());
 }
 
 void build_bgr_tensor_map(vs_clip* c)

@@ -51,11 +51,14 @@ constexpr int VS_WARP_TMA_BOX_WORDS = 108, VS_WARP_TMA_BOX_ROWS = 20;
 // d_tab is scratch for the per-launch fixed-point tables, vs_warp_rows_tab_ints(dst.w, dst.h) int32 per image
 int vsk_bgr_warp_slots_rows(vs_ctx*, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,
                             const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0, int32_t* d_tab);
-constexpr int VS_WARP_ROWS_BOX_WORDS = 120, VS_WARP_ROWS_BOX_ROWS = 28;
+constexpr int VS_WARP_ROWS_BOX_WORDS = 120, VS_WARP_ROWS_BOX_ROWS = 28, VS_WARP_ROWS_TILE_W = 128, VS_WARP_ROWS_TILE_H = 24;
 static inline size_t vs_warp_rows_tab_ints(int dw, int dh)
 {
-    return 2 * (size_t)((dw + 127) / 128 * 128) + 2 * (size_t)((dh + 23) / 24 * 24);
+    const size_t tx = (dw + VS_WARP_ROWS_TILE_W - 1) / VS_WARP_ROWS_TILE_W, ty = (dh + VS_WARP_ROWS_TILE_H - 1) / VS_WARP_ROWS_TILE_H;
+    return 2 * tx * VS_WARP_ROWS_TILE_W + 2 * ty * VS_WARP_ROWS_TILE_H + 4 * tx * ty;
 }
+// cuTensorMapEncodeTiled resolved through the runtime (PFN_cuTensorMapEncodeTiled), or null
+void* vs_tensor_map_encoder();
 
 // ---- sparse kernels (vs_kernels_sparse.cu)
 int vsk_grad_argmax(vs_ctx*, const VsDevImg& gx, const VsDevImg& gy, int tile,

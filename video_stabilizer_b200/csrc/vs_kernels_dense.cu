@@ -3,9 +3,11 @@
 // arithmetic where the math allows it, no tensor cores (nothing here is a contraction).
 #include "vs_internal.h"
 
-#include <cuda.h>   // CUtensorMap (type only; the encoder is resolved at run time in vs_clip.cu)
+#include <cuda.h>   // CUtensorMap; the encoder is resolved at run time (vs_tensor_map_encoder)
+#include <cudaTypedefs.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -757,15 +759,17 @@ k_bgr_warp_cv_tma(const __grid_constant__ CUtensorMap src_map, const uint8_t* __
 // stabiliser those four pixels almost always read four consecutive source pixels of ONE source row pair
 // ("regular group"): then the 15 source bytes of a row are five aligned shared-memory words of the
 // TMA-fetched raw box, brought to byte alignment by four funnel shifts, and the paired taps
-// (B,B',G,G') / (R,R') of all four pixels are eight PRMTs with fixed selectors.  Weights are scaled by 64
-// so that every blended channel lands in byte 2 of its accumulator ((64 S + 32768) >> 16 == (S + 512) >> 10)
-// and the 12 output bytes are assembled by nine PRMTs, stored as three words (lane stride 3 words:
-// conflict-free) and written out with 16-byte vectors.  (The scaled top-left weight is 65536 when
-// fx = fy = 0; 65535 is substituted, which yields the same byte.)  Groups whose pixels do not share one
-// source row or consecutive source columns, and groups cut by the right image edge, are pushed to a list
-// and redone pixel by pixel from the same raw box after the main loop — same arithmetic, nothing
-// approximated.  The fixed-point column and row terms (cv::warpAffine's adelta/bdelta, X0/Y0: the only
-// f64 work) come from a small table kernel that runs once per launch instead of once per tile.
+// (B,B',G,G') / (R,R') of all four pixels are eight PRMTs with fixed selectors.  A warp walks down six
+// consecutive rows, and the bottom taps of one row are normally the top taps of the next: they stay in
+// registers.  Weights are scaled by 64 so that every blended channel lands in byte 2 of its accumulator
+// ((64 S + 32768) >> 16 == (S + 512) >> 10) and the 12 output bytes are assembled by nine PRMTs, stored as
+// three words (lane stride 3 words: conflict-free); the finished 128 x 24 tile leaves through one TMA
+// store.  Groups whose pixels do not share one source row or consecutive source columns, groups with a
+// pixel at fx = fy = 0 (scaled top-left weight 65536: not a 16-bit value) and groups cut by the right image
+// edge are pushed to a list and redone pixel by pixel from the same raw box after the main loop — same
+// arithmetic, nothing approximated.  The fixed-point column and row terms (cv::warpAffine's adelta/bdelta,
+// X0/Y0: the only f64 work) and each tile's source box come from a small table kernel that runs once per
+// launch instead of once per tile.
 constexpr int WG_W = 128, WG_H = 24, WG_THREADS = 128, WG_WARPS = 4, WG_ROWS_PER_WARP = WG_H / WG_WARPS;
 constexpr int WG_BOX_WORDS = VS_WARP_ROWS_BOX_WORDS, WG_BOX_ROWS = VS_WARP_ROWS_BOX_ROWS;   // 160 pixels x 28 rows
 constexpr int WG_BOX_PIXELS = WG_BOX_WORDS * 4 / 3;
@@ -776,35 +780,58 @@ constexpr int WG_OUT_ROW_WORDS = WG_W * 3 / 4;                       // 96 words
 constexpr int WG_LIST_OFF = WG_OUT_OFF + WG_OUT_ROW_WORDS * 4 * WG_H;
 constexpr int WG_SMEM_BYTES = WG_LIST_OFF + WG_H * 32 * 2;           // one list entry per group at most
 static_assert(WG_BOX_PIXELS == 160 && WG_H % WG_WARPS == 0, "box / tile geometry");
+static_assert(WG_W == VS_WARP_ROWS_TILE_W && WG_H == VS_WARP_ROWS_TILE_H, "vs_warp_rows_tab_ints sizes the tables by tile");
 
-// per launch: image b has AD[dwp], BD[dwp] (column terms) and XY0[dhp] (row terms, rounding offset included)
+// Per launch and image b (vs_warp_rows_tab_ints int32 each): AD[dwp], BD[dwp] (column terms), XY0[dhp] (row terms,
+// rounding offset included), TILE[tiles_y][tiles_x] = {first TMA word, first source row, first source pixel, box fits}.
 __global__ void __launch_bounds__(256)
-k_warp_tables(const VsWarpCoef* __restrict__ coefs, int dwp, int dhp, int dst_x0, int dst_y0, int32_t* __restrict__ tab)
+k_warp_tables(const VsWarpCoef* __restrict__ coefs, int dw, int dh, int dwp, int dhp, int per, int dst_x0, int dst_y0,
+              int32_t* __restrict__ tab)
 {
     const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
     const VsWarpCoef cf = coefs[b];
-    int32_t* const t = tab + (size_t)b * (2 * dwp + 2 * dhp);
+    int32_t* const t = tab + (size_t)b * per;
+    auto colx = [&](int x) { return __double2int_rn(cf.i00 * (double)(x + dst_x0) * 1024.0); };
+    auto coly = [&](int x) { return __double2int_rn(cf.i10 * (double)(x + dst_x0) * 1024.0); };
+    auto rowx = [&](int y) { return __double2int_rn((cf.i01 * (double)(y + dst_y0) + cf.i02) * 1024.0) + 16; };
+    auto rowy = [&](int y) { return __double2int_rn((cf.i11 * (double)(y + dst_y0) + cf.i12) * 1024.0) + 16; };
+    const int tiles_x = dwp / WG_W, tiles_y = dhp / WG_H;
     if (i < dwp) {
-        const int x = i + dst_x0;
-        t[i] = __double2int_rn(cf.i00 * (double)x * 1024.0);
-        t[dwp + i] = __double2int_rn(cf.i10 * (double)x * 1024.0);
+        t[i] = colx(i);
+        t[dwp + i] = coly(i);
     } else if (i < dwp + dhp) {
-        const int y = i - dwp + dst_y0;
-        reinterpret_cast<int2*>(t + 2 * dwp)[i - dwp] = make_int2(__double2int_rn((cf.i01 * (double)y + cf.i02) * 1024.0) + 16,
-                                                                  __double2int_rn((cf.i11 * (double)y + cf.i12) * 1024.0) + 16);
+        reinterpret_cast<int2*>(t + 2 * dwp)[i - dwp] = make_int2(rowx(i - dwp), rowy(i - dwp));
+    } else if (i < dwp + dhp + tiles_x * tiles_y) {
+        // source bounding box of the tile from its four corners (column and row terms are monotone)
+        const int q = i - dwp - dhp, ty = q / tiles_x, tx = q - ty * tiles_x;
+        const int xl = tx * WG_W, xr = min(xl + WG_W, dw) - 1, yt = ty * WG_H, yb = min(yt + WG_H, dh) - 1;
+        const int aL = colx(xl), aR = colx(xr), bL = coly(xl), bR = coly(xr);
+        const int XT = rowx(yt), XB = rowx(yb), YT = rowy(yt), YB = rowy(yb);
+        const int sxmin = (min(XT, XB) + min(aL, aR)) >> 10, sxmax = (max(XT, XB) + max(aL, aR)) >> 10;
+        const int symin = (min(YT, YB) + min(bL, bR)) >> 10, symax = (max(YT, YB) + max(bL, bR)) >> 10;
+        const int bx0 = (sxmin >> 4) * 16;                        // a TMA box starts 16-byte aligned: 16 pixels = 48 bytes
+        // pixels bx0 .. sxmax + 1 and rows symin .. symax + 1 must be inside the box
+        const bool fits = sxmax + 1 - bx0 < WG_BOX_PIXELS && symax + 1 - symin < WG_BOX_ROWS &&
+                          sxmin > -(1 << 20) && sxmax < (1 << 20) && symin > -(1 << 20) && symax < (1 << 20);
+        reinterpret_cast<int4*>(t + 2 * dwp + 2 * dhp)[q] = make_int4((bx0 >> 4) * 12, symin, bx0, fits ? 1 : 0);
     }
 }
 
 // packed 16-bit weight pairs of one pixel scaled by 64: wt = 64 w00 | 64 w10 << 16, wb = 64 w01 | 64 w11 << 16
-// (w = (32 - fx | fx) (32 - fy | fy))
+// (w = (32 - fx | fx) (32 - fy | fy)).  64 w00 = 65536 when fx == fy == 0: then wt == 0x10000 (bit 16 is never set
+// otherwise, the upper half being a multiple of 64) and the caller takes the pixel-by-pixel path.  Written so that
+// most of the work is multiply-adds: the shift / logic pipe is the busy one in this kernel.
 __device__ __forceinline__ void wg_weights(int sfx, int sfy, uint32_t& wt, uint32_t& wb)
 {
-    const uint32_t hp = (uint32_t)(sfx & 0x3e0) * 65535u + 1024u;    // 32 (32 - fx) | 32 fx << 16
-    const uint32_t fy2 = ((uint32_t)sfy >> 4) & 0x3eu;               // 2 fy
-    wb = fy2 * hp;
-    wt = hp * 64u - wb;
-    // fx == fy == 0: 64 w00 = 65536 is not a 16-bit value; 65535 gives the same byte 2 (65535 p + 32768 = 65536 p + (32768 - p))
-    if (((sfx | sfy) & 0x3e0) == 0) wt = 0xffffu;
+    const uint32_t gx = (uint32_t)sfx & 0x3e0u;                        // 32 fx
+    const uint32_t hp2 = gx * 131070u + 2048u;                         // 64 (32 - fx) | 64 fx << 16
+    const uint32_t nhp2 = gx * (0u - 131070u) - 2048u;                 // -hp2 and 32 hp2 as multiply-adds of their own, so that
+    const uint32_t hp64 = gx * (131070u * 32u) + 65536u;               // wt = 32 hp2 - fy hp2 needs no subtraction on the logic pipe
+    uint32_t t, fy;
+    asm("shl.b32 %0, %1, 22;" : "=r"(t) : "r"(sfy));                  // two shifts, not shift + mask: the left one can be a multiply
+    asm("shr.u32 %0, %1, 27;" : "=r"(fy) : "r"(t));
+    wb = fy * hp2;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(wt) : "r"(fy), "r"(nhp2), "r"(hp64));
 }
 
 __device__ __forceinline__ void wg_blend(uint32_t wt, uint32_t wb, uint32_t tx, uint32_t ty, uint32_t bx, uint32_t by,
@@ -821,10 +848,10 @@ __device__ __forceinline__ uint32_t wg_pack(uint32_t a, uint32_t b, uint32_t c, 
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 8)
-k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const uint8_t* __restrict__ src_base, int64_t src_stride,
-                   int64_t src_bs, int w, int h, const int32_t* __restrict__ slots, const int32_t* __restrict__ tab,
-                   int dwp, int dhp, uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
-                   int dst_al16)
+k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map,
+                   const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
+                   const int32_t* __restrict__ slots, const int32_t* __restrict__ tab, int dwp, int dhp, int per,
+                   uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh, int dst_tma, int dst_al16)
 {
     extern __shared__ __align__(128) uint32_t wg_smem[];
     uint32_t* const RAW = wg_smem;                                 // [WG_BOX_ROWS][WG_BOX_WORDS]
@@ -838,29 +865,28 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const uint8_t* _
     const int b = blockIdx.z;
     const int ox0 = blockIdx.x * WG_W, oy0 = blockIdx.y * WG_H;
     const int tw = min(WG_W, dw - ox0), th = min(WG_H, dh - oy0);
-    const int slot = slots ? slots[b] : b;
-    const int32_t* const AD = tab + (size_t)b * (2 * dwp + 2 * dhp) + ox0;
+    const int32_t* const T = tab + (size_t)b * per;
+    const int32_t* const AD = T + ox0;
     const int32_t* const BD = AD + dwp;
-    const int2* const XY = reinterpret_cast<const int2*>(tab + (size_t)b * (2 * dwp + 2 * dhp) + 2 * dwp) + oy0;
-
+    const int2* const XY = reinterpret_cast<const int2*>(T + 2 * dwp) + oy0;
+    const int4 tile = __ldg(reinterpret_cast<const int4*>(T + 2 * dwp + 2 * dhp) + blockIdx.y * gridDim.x + blockIdx.x);
+    const bool staged = tile.w != 0;
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
     if (tid == 0) {
         sCount = 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (staged) {
+            const int slot = slots ? __ldg(slots + b) : b;
+            const uint32_t dstsm = (uint32_t)__cvta_generic_to_shared(RAW);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WG_RAW_BYTES) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(dstsm), "l"(reinterpret_cast<uint64_t>(&src_map)), "r"(tile.x), "r"(tile.y), "r"(slot), "r"(bar)
+                : "memory");
+        }
     }
-
-    // source bounding box of the tile from its four corners (column and row terms are monotone)
-    const int aL = __ldg(AD), aR = __ldg(AD + tw - 1), bL = __ldg(BD), bR = __ldg(BD + tw - 1);
-    const int2 xyT = __ldg(XY), xyB = __ldg(XY + th - 1);
-    const int sxmin = (min(xyT.x, xyB.x) + min(aL, aR)) >> 10, sxmax = (max(xyT.x, xyB.x) + max(aL, aR)) >> 10;
-    const int symin = (min(xyT.y, xyB.y) + min(bL, bR)) >> 10, symax = (max(xyT.y, xyB.y) + max(bL, bR)) >> 10;
-    const int bx0 = (sxmin >> 4) * 16;                            // a TMA box starts 16-byte aligned: 16 pixels = 48 bytes
-    const int by0 = symin;
-    // pixels bx0 .. sxmax + 1 and rows symin .. symax + 1 must be inside the box
-    const bool staged = sxmax + 1 - bx0 < WG_BOX_PIXELS && symax + 1 - symin < WG_BOX_ROWS &&
-                        sxmin > -(1 << 20) && sxmax < (1 << 20) && symin > -(1 << 20) && symax < (1 << 20);
-    const int orgx = staged ? bx0 << 10 : 0, orgy = staged ? by0 << 10 : 0;
+    const int orgx = staged ? tile.z << 10 : 0, orgy = staged ? tile.y << 10 : 0;
     if (tid < WG_H) {
         const int2 xy = __ldg(XY + min(tid, th - 1));
         sXY0[tid] = make_int2(xy.x - orgx, xy.y - orgy);
@@ -871,15 +897,6 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const uint8_t* _
 
     uint8_t* const Ob = reinterpret_cast<uint8_t*>(O);
     if (staged) {
-        if (tid == 0) {
-            const uint32_t dstsm = (uint32_t)__cvta_generic_to_shared(RAW);
-            const int c0 = (bx0 >> 4) * 12;                       // first 32-bit word of pixel bx0, may be negative
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WG_RAW_BYTES) : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                ::"r"(dstsm), "l"(reinterpret_cast<uint64_t>(&src_map)), "r"(c0), "r"(by0), "r"(slot), "r"(bar)
-                : "memory");
-        }
         // column terms with the pixel's offset inside the group taken out: a regular group has one integer part
         const int a0 = ad4.x, a1 = ad4.y - 1024, a2 = ad4.z - 2048, a3 = ad4.w - 3072;
         const bool whole = 4 * lane + 3 < tw;
@@ -889,7 +906,12 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const uint8_t* _
                          : "=r"(done) : "r"(bar) : "memory");
             if (!done && ++spins > (1u << 24)) __trap();   // a lost transaction must fail loudly, not hang the GPU
         }
-#pragma unroll 1
+        // A warp walks down six consecutive output rows.  From one row to the next a regular group normally moves
+        // down by exactly one source row at the same source column: its top taps are then the previous row's bottom
+        // taps, already aligned and paired in registers.  The test is warp-uniform (every regular lane must agree).
+        uint32_t pbyte = 0xffffffffu;                                 // raw-box byte offset of the paired bottom taps held in p*
+        uint32_t px0 = 0, px1 = 0, px2 = 0, px3 = 0, py0 = 0, py1 = 0, py2 = 0, py3 = 0;
+#pragma unroll
         for (int k = 0; k < WG_ROWS_PER_WARP; k++) {
             const int r = warp * WG_ROWS_PER_WARP + k;
             if (r >= th) break;
@@ -899,35 +921,50 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const uint8_t* _
             uint32_t wt0, wb0, wt1, wb1, wt2, wb2, wt3, wb3;
             wg_weights(x0, y0, wt0, wb0); wg_weights(x1, y1, wt1, wb1);
             wg_weights(x2, y2, wt2, wb2); wg_weights(x3, y3, wt3, wb3);
-            // one source row pair (the row term is monotone in x: the ends decide) and consecutive source columns
+            // one source row pair (the row term is monotone in x: the ends decide), consecutive source columns,
+            // no pixel at fx == fy == 0
             const uint32_t spread = (uint32_t)((x1 ^ x0) | (x2 ^ x0) | (x3 ^ x0) | (y3 ^ y0));
-            if (whole && spread < 1024u) {
-                const uint32_t byte = (uint32_t)(y0 >> 10) * (uint32_t)WG_RAW_PITCH + (uint32_t)(x0 >> 10) * 3u;
+            const uint32_t ovf = (wt0 | wt1 | wt2 | wt3) & 0x10000u;
+            const bool regular = whole && spread < 1024u && ovf == 0u;
+            const uint32_t byte = (uint32_t)(y0 >> 10) * (uint32_t)WG_RAW_PITCH + (uint32_t)(x0 >> 10) * 3u;
+            const bool reuse = __all_sync(0xffffffffu, !regular || byte == pbyte);
+            if (regular) {
                 const uint32_t* const p = RAW + (byte >> 2);
-                const uint32_t sh = byte << 3;                    // funnel shifts use the low five bits: 8 (byte & 3)
-                const uint32_t t0 = p[0], t1 = p[1], t2 = p[2], t3 = p[3], t4 = p[4];
+                const uint32_t sh = byte << 3;                        // funnel shifts use the low five bits: 8 (byte & 3)
+                uint32_t tx0, tx1, tx2, tx3, ty0, ty1, ty2, ty3;
+                if (reuse) {
+                    tx0 = px0; tx1 = px1; tx2 = px2; tx3 = px3; ty0 = py0; ty1 = py1; ty2 = py2; ty3 = py3;
+                } else {
+                    const uint32_t t0 = p[0], t1 = p[1], t2 = p[2], t3 = p[3], t4 = p[4];
+                    const uint32_t u0 = __funnelshift_r(t0, t1, sh), u1 = __funnelshift_r(t1, t2, sh),
+                                   u2 = __funnelshift_r(t2, t3, sh), u3 = __funnelshift_r(t3, t4, sh);
+                    // stream bytes of pixel j start at 3j: taps (s[3j], s[3j+3], s[3j+1], s[3j+4]) and (s[3j+2], s[3j+5])
+                    tx0 = __byte_perm(u0, u1, 0x4130); tx1 = __byte_perm(u0, u1, 0x7463);
+                    tx2 = __byte_perm(u1, u2, 0x6352); tx3 = __byte_perm(u2, u3, 0x5241);
+                    ty0 = __byte_perm(u0, u1, 0x0052); ty1 = __byte_perm(u1, u2, 0x0041);
+                    ty2 = __byte_perm(u2, u2, 0x0030); ty3 = __byte_perm(u2, u3, 0x0063);
+                }
                 const uint32_t c0 = p[WG_BOX_WORDS], c1 = p[WG_BOX_WORDS + 1], c2 = p[WG_BOX_WORDS + 2],
                                c3 = p[WG_BOX_WORDS + 3], c4 = p[WG_BOX_WORDS + 4];
-                const uint32_t u0 = __funnelshift_r(t0, t1, sh), u1 = __funnelshift_r(t1, t2, sh),
-                               u2 = __funnelshift_r(t2, t3, sh), u3 = __funnelshift_r(t3, t4, sh);
                 const uint32_t v0 = __funnelshift_r(c0, c1, sh), v1 = __funnelshift_r(c1, c2, sh),
                                v2 = __funnelshift_r(c2, c3, sh), v3 = __funnelshift_r(c3, c4, sh);
-                // stream bytes of pixel j start at 3j: taps (s[3j], s[3j+3], s[3j+1], s[3j+4]) and (s[3j+2], s[3j+5])
+                px0 = __byte_perm(v0, v1, 0x4130); px1 = __byte_perm(v0, v1, 0x7463);
+                px2 = __byte_perm(v1, v2, 0x6352); px3 = __byte_perm(v2, v3, 0x5241);
+                py0 = __byte_perm(v0, v1, 0x0052); py1 = __byte_perm(v1, v2, 0x0041);
+                py2 = __byte_perm(v2, v2, 0x0030); py3 = __byte_perm(v2, v3, 0x0063);
+                pbyte = byte + WG_RAW_PITCH;
                 uint32_t b0, g0, r0, b1, g1, r1, b2, g2, r2, b3, g3, r3;
-                wg_blend(wt0, wb0, __byte_perm(u0, u1, 0x4130), __byte_perm(u0, u1, 0x0052),
-                         __byte_perm(v0, v1, 0x4130), __byte_perm(v0, v1, 0x0052), b0, g0, r0);
-                wg_blend(wt1, wb1, __byte_perm(u0, u1, 0x7463), __byte_perm(u1, u2, 0x0041),
-                         __byte_perm(v0, v1, 0x7463), __byte_perm(v1, v2, 0x0041), b1, g1, r1);
-                wg_blend(wt2, wb2, __byte_perm(u1, u2, 0x6352), __byte_perm(u2, u2, 0x0030),
-                         __byte_perm(v1, v2, 0x6352), __byte_perm(v2, v2, 0x0030), b2, g2, r2);
-                wg_blend(wt3, wb3, __byte_perm(u2, u3, 0x5241), __byte_perm(u2, u3, 0x0063),
-                         __byte_perm(v2, v3, 0x5241), __byte_perm(v2, v3, 0x0063), b3, g3, r3);
+                wg_blend(wt0, wb0, tx0, ty0, px0, py0, b0, g0, r0);
+                wg_blend(wt1, wb1, tx1, ty1, px1, py1, b1, g1, r1);
+                wg_blend(wt2, wb2, tx2, ty2, px2, py2, b2, g2, r2);
+                wg_blend(wt3, wb3, tx3, ty3, px3, py3, b3, g3, r3);
                 uint32_t* const o = O + r * WG_OUT_ROW_WORDS + 3 * lane;
                 o[0] = wg_pack(b0, g0, r0, b1);
                 o[1] = wg_pack(g1, r1, b2, g2);
                 o[2] = wg_pack(r2, b3, g3, r3);
-            } else if (4 * lane < tw) {
-                LIST[atomicAdd(&sCount, 1)] = (uint16_t)(r * 32 + lane);
+            } else {
+                pbyte = 0xffffffffu;
+                if (4 * lane < tw) LIST[atomicAdd(&sCount, 1)] = (uint16_t)(r * 32 + lane);
             }
         }
         __syncthreads();
@@ -949,7 +986,7 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const uint8_t* _
         }
     } else {
         // the box does not fit (large rotation or scale): every pixel straight from global memory
-        const uint8_t* const src = src_base + (size_t)slot * src_bs;
+        const uint8_t* const src = src_base + (size_t)(slots ? __ldg(slots + b) : b) * src_bs;
         for (int i = tid; i < tw * th; i += WG_THREADS) {
             const int r = i / tw, x = i - r * tw;
             const int2 xy0 = sXY0[r];
@@ -964,9 +1001,23 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const uint8_t* _
             o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
         }
     }
-    __syncthreads();
 
-    // write the tile: 16-byte vectors when the destination allows it (24 per full row)
+    if (dst_tma) {
+        // the tile leaves through one TMA store (rows / words beyond the image are clipped by the tensor map)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t srcsm = (uint32_t)__cvta_generic_to_shared(O);
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         ::"l"(reinterpret_cast<uint64_t>(&dst_map)), "r"(blockIdx.x * WG_OUT_ROW_WORDS), "r"(oy0), "r"(b), "r"(srcsm)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        return;
+    }
+    __syncthreads();
+    // destinations a tensor map cannot describe: 16-byte vectors when possible (24 per full row), else bytes
     uint8_t* const drow0 = dst_base + (size_t)b * dst_bs + (size_t)oy0 * dst_stride + (size_t)ox0 * 3;
     if (dst_al16 && tw == WG_W) {
         constexpr int VPR = WG_W * 3 / 16;
@@ -1369,6 +1420,24 @@ int vsk_bgr_warp_slots_tma(vs_ctx* ctx, const void* tensor_map, const VsDevImg& 
     return VS_OK;
 }
 
+// cuTensorMapEncodeTiled lives in the driver library; resolve it through the runtime so that
+// libvstab.so keeps linking against cudart only
+void* vs_tensor_map_encoder()
+{
+    static void* fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
 // clip-resident sources, row-group kernel: table kernel + warp kernel on the same stream
 int vsk_bgr_warp_slots_rows(vs_ctx* ctx, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,
                             const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0, int32_t* d_tab)
@@ -1377,15 +1446,33 @@ int vsk_bgr_warp_slots_rows(vs_ctx* ctx, const void* tensor_map, const VsDevImg&
     if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
     VS_REQUIRE(ctx, vs_cdiv(dst.h, WG_H) <= 65535 && dst.batch <= 65535, "bgr_warp_rows: grid too large");
     const int dwp = vs_cdiv(dst.w, WG_W) * WG_W, dhp = vs_cdiv(dst.h, WG_H) * WG_H;
+    const int ntiles = (dwp / WG_W) * (dhp / WG_H);
+    const int per = (int)vs_warp_rows_tab_ints(dst.w, dst.h);
     const int dst_al16 = aligned_to(dst.data, 16) && dst.stride % 16 == 0 && dst.batch_stride % 16 == 0;
+    // the destination as a u32 [image][row][word] tensor for the TMA store: needs whole words per row and 16-byte strides
+    CUtensorMap dst_map;
+    memset(&dst_map, 0, sizeof(dst_map));
+    int dst_tma = 0;
+    static const int no_tma_store = getenv("VSTAB_WARP_TMA_STORE") ? atoi(getenv("VSTAB_WARP_TMA_STORE")) == 0 : 0;
+    if (!no_tma_store && dst_al16 && dst.w % 4 == 0 && vs_tensor_map_encoder()) {
+        const cuuint64_t dims[3] = {(cuuint64_t)(dst.w * 3 / 4), (cuuint64_t)dst.h, (cuuint64_t)dst.batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)dst.stride, (cuuint64_t)(dst.batch > 1 ? dst.batch_stride : dst.stride * dst.h)};
+        const cuuint32_t box[3] = {(cuuint32_t)WG_OUT_ROW_WORDS, (cuuint32_t)WG_H, 1}, estr[3] = {1, 1, 1};
+        CUresult r = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(vs_tensor_map_encoder())(
+            &dst_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, dst.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        dst_tma = (r == CUDA_SUCCESS);
+    }
     VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
     VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
-    k_warp_tables<<<dim3(vs_cdiv(dwp + dhp, 256), dst.batch), 256, 0, ctx->stream>>>(d_coef, dwp, dhp, dst_x0, dst_y0, d_tab);
+    k_warp_tables<<<dim3(vs_cdiv(dwp + dhp + ntiles, 256), dst.batch), 256, 0, ctx->stream>>>(
+        d_coef, dst.w, dst.h, dwp, dhp, per, dst_x0, dst_y0, d_tab);
     ctx->launches++;
-    dim3 tgrid(vs_cdiv(dst.w, WG_W), vs_cdiv(dst.h, WG_H), dst.batch);
+    dim3 tgrid(dwp / WG_W, dhp / WG_H, dst.batch);
     k_bgr_warp_cv_rows<<<tgrid, WG_THREADS, WG_SMEM_BYTES, ctx->stream>>>(
-        *reinterpret_cast<const CUtensorMap*>(tensor_map), (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
-        d_slots, d_tab, dwp, dhp, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_al16);
+        *reinterpret_cast<const CUtensorMap*>(tensor_map), dst_map, (const uint8_t*)src.data, src.stride, src.batch_stride,
+        src.w, src.h, d_slots, d_tab, dwp, dhp, per, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h,
+        dst_tma, dst_al16);
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
