@@ -35,8 +35,11 @@ void vs_warp_coef_from_forward(const double* M6, VsWarpCoef* out);
 // imgproc.cpp:458-466 — centre-based similarity -> forward 2x3 matrix
 void vs_forward_matrix_from_transform(const double* T4, int cols, int rows, double* M6);
 // d_coef: device array of `src.batch` VsWarpCoef
+// d_tab: optional scratch of vs_warp_rows_tab_ints(dst.w, dst.h) int32 per image; with it the cv-exact / constant-border
+// mode runs the row-group kernel whenever the source can be described by a tensor map (vs_warp_rows_usable)
 int vsk_bgr_warp(vs_ctx*, const VsDevImg& src, const VsWarpCoef* d_coef, const VsDevImg& dst,
-                 int dst_x0, int dst_y0, int mode, int border);
+                 int dst_x0, int dst_y0, int mode, int border, int32_t* d_tab = nullptr);
+bool vs_warp_rows_usable(const VsDevImg& src, int mode, int border);
 // same, but image b of the batch reads slot d_slots[b] of `src` (src.batch_stride apart)
 int vsk_bgr_warp_slots(vs_ctx*, const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
                        const VsDevImg& dst, int dst_x0, int dst_y0, int mode, int border);

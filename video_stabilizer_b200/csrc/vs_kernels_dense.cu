@@ -1034,184 +1034,6 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
     }
 }
 
-// ------------------------------------------------------------------ BGR warp, cv-exact, TMA-staged, persistent
-// k_bgr_warp_cv_tma as a persistent kernel: a CTA walks tiles t, t + gridDim.x, ... and keeps two raw
-// boxes in flight, so the TMA fetch of the next tile (issued by thread 0 right after the barrier that
-// frees its buffer) overlaps the expansion, sampling and write-back of the current one.
-struct WtTile {
-    int b, ox0, oy0, tw, th;
-};
-
-__device__ __forceinline__ WtTile wt_tile(int t, int tiles_x, int tiles_y, int dw, int dh)
-{
-    WtTile T;
-    const int per = tiles_x * tiles_y;
-    T.b = t / per;
-    const int r = t - T.b * per;
-    const int ty = r / tiles_x, tx = r - ty * tiles_x;
-    T.ox0 = tx * WT_W; T.oy0 = ty * WT_H;
-    T.tw = min(WT_W, dw - T.ox0); T.th = min(WT_H, dh - T.oy0);
-    return T;
-}
-
-// source box of a tile from its four corners: {bx0, by0, sxmax + 1 - bx0 (last needed pixel), nrows}
-__device__ __forceinline__ int4 wt_box(const VsWarpCoef& cf, const WtTile& T, int dst_x0, int dst_y0)
-{
-    const int xl = T.ox0 + dst_x0, xr = T.ox0 + T.tw - 1 + dst_x0, yt = T.oy0 + dst_y0, yb = T.oy0 + T.th - 1 + dst_y0;
-    const int aL = __double2int_rn(cf.i00 * (double)xl * 1024.0), aR = __double2int_rn(cf.i00 * (double)xr * 1024.0);
-    const int bL = __double2int_rn(cf.i10 * (double)xl * 1024.0), bR = __double2int_rn(cf.i10 * (double)xr * 1024.0);
-    const int XT = __double2int_rn((cf.i01 * (double)yt + cf.i02) * 1024.0) + 16, XB = __double2int_rn((cf.i01 * (double)yb + cf.i02) * 1024.0) + 16;
-    const int YT = __double2int_rn((cf.i11 * (double)yt + cf.i12) * 1024.0) + 16, YB = __double2int_rn((cf.i11 * (double)yb + cf.i12) * 1024.0) + 16;
-    const int sxmin = (min(XT, XB) + min(aL, aR)) >> 10, sxmax = (max(XT, XB) + max(aL, aR)) >> 10;
-    const int symin = (min(YT, YB) + min(bL, bR)) >> 10, symax = (max(YT, YB) + max(bL, bR)) >> 10;
-    const int bx0 = (sxmin >> 4) * 16;
-    return make_int4(bx0, symin, sxmax + 1 - bx0, symax + 1 - symin + 1);
-}
-
-constexpr int WTP_RAW_STRIDE = (WTM_RAW_BYTES + 127) / 128 * 128;   // a TMA destination must be 128-byte aligned
-constexpr int WTP_SMEM_BYTES = 2 * WTP_RAW_STRIDE + 2 * WTM_PLANE_WORDS * 4 + WT_OUT_WORDS * 4;
-
-__global__ void __launch_bounds__(WT_THREADS)
-k_bgr_warp_cv_tma_persistent(const __grid_constant__ CUtensorMap src_map, const uint8_t* __restrict__ src_base, int64_t src_stride,
-                             int64_t src_bs, int w, int h, const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
-                             uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
-                             int dst_x0, int dst_y0, int dst_al8, int tiles_x, int tiles_y, int total_tiles)
-{
-    extern __shared__ __align__(128) uint32_t wtp_smem[];
-    uint32_t* const RAW0 = wtp_smem;                              // two raw boxes
-    uint32_t* const SX = wtp_smem + 2 * (WTP_RAW_STRIDE / 4);
-    uint32_t* const SY = SX + WTM_PLANE_WORDS;
-    uint32_t* const O = SY + WTM_PLANE_WORDS;
-    __shared__ int2 sXY0[WT_H];
-    __shared__ __align__(8) unsigned long long tma_bar[2];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&tma_bar[0]);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // thread 0: request the box of tile t into buffer `buf` (nothing to do for a tile that will not be staged)
-    auto request = [&](int t, int buf) {
-        const WtTile T = wt_tile(t, tiles_x, tiles_y, dw, dh);
-        const int slot = slots ? slots[T.b] : T.b;
-        const int4 box = wt_box(coefs[T.b], T, dst_x0, dst_y0);
-        if (box.z < WTM_PITCH && box.w <= WTM_BOX_ROWS) {
-            const uint32_t bar = bar0 + 8 * buf;
-            const uint32_t dstsm = (uint32_t)__cvta_generic_to_shared(RAW0 + buf * (WTP_RAW_STRIDE / 4));
-            const int c0 = (box.x >> 4) * 12;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WTM_RAW_BYTES) : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                ::"r"(dstsm), "l"(reinterpret_cast<uint64_t>(&src_map)), "r"(c0), "r"(box.y), "r"(slot), "r"(bar)
-                : "memory");
-        }
-    };
-    if (tid == 0 && (int)blockIdx.x < total_tiles) request(blockIdx.x, 0);
-
-    const int k4 = tid & 3;
-    const uint32_t sel = k4 == 0 ? 0x4210u : (k4 == 1 ? 0x5421u : 0x6542u);
-    uint32_t* const Orow = O + 3 * (tid >> 2) + k4;
-    const bool keep = k4 < 3 && tid < WT_W;
-    uint32_t uses[2] = {0u, 0u};      // how often each buffer's barrier has been waited on: its parity bit
-
-    int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
-        const int buf = it & 1;
-        const WtTile T = wt_tile(t, tiles_x, tiles_y, dw, dh);
-        const int slot = slots ? slots[T.b] : T.b;
-        const uint8_t* src = src_base + (size_t)slot * src_bs;
-        uint8_t* dst = dst_base + (size_t)T.b * dst_bs;
-        const VsWarpCoef cf = coefs[T.b];
-        const int xcol = T.ox0 + min(tid, T.tw - 1) + dst_x0;
-        const int adelta = __double2int_rn(cf.i00 * (double)xcol * 1024.0);
-        const int bdelta = __double2int_rn(cf.i10 * (double)xcol * 1024.0);
-        if (tid < WT_H) {
-            const int y = T.oy0 + min(tid, T.th - 1) + dst_y0;
-            sXY0[tid] = make_int2(__double2int_rn((cf.i01 * (double)y + cf.i02) * 1024.0) + 16,
-                                  __double2int_rn((cf.i11 * (double)y + cf.i12) * 1024.0) + 16);
-        }
-        const int4 box = wt_box(cf, T, dst_x0, dst_y0);
-        const int bx0 = box.x, by0 = box.y, nrows = box.w;
-        const bool staged = box.z < WTM_PITCH && nrows <= WTM_BOX_ROWS;
-        // barrier: sXY0 visible; every thread has left the previous tile, so the other raw buffer, the planes and O are free
-        __syncthreads();
-        if (tid == 0 && t + (int)gridDim.x < total_tiles) request(t + gridDim.x, buf ^ 1);
-
-        if (staged) {
-            const uint32_t bar = bar0 + 8 * buf;
-            const uint32_t parity = uses[buf] & 1u;
-            uses[buf]++;
-            uint32_t done = 0, spins = 0;
-            while (!done) {
-                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-                if (!done && ++spins > (1u << 24)) __trap();   // a lost transaction must fail loudly, not hang the GPU
-            }
-            const uint32_t* RAW = RAW0 + buf * (WTP_RAW_STRIDE / 4);
-            for (int q0 = tid; q0 < nrows * WTM_GRANULES; q0 += WT_THREADS) {
-                const int r = q0 / WTM_GRANULES, q = q0 - r * WTM_GRANULES;
-                const uint32_t* g = RAW + r * WTM_BOX_WORDS + 3 * q;
-                const uint32_t w0 = g[0], w1 = g[1], w2 = g[2], w3 = g[3];
-                *reinterpret_cast<uint4*>(SX + r * WTM_PITCH + 4 * q) =
-                    make_uint4(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x7463), __byte_perm(w1, w2, 0x6352), __byte_perm(w2, w3, 0x5241));
-                *reinterpret_cast<uint4*>(SY + r * WTM_PITCH + 4 * q) =
-                    make_uint4(__byte_perm(w0, w1, 0x0052), __byte_perm(w1, w2, 0x0041), __byte_perm(w2, w2, 0x0030), __byte_perm(w2, w3, 0x0063));
-            }
-            __syncthreads();
-            const int sorg = -by0 * WTM_PITCH - bx0;
-#pragma unroll 4
-            for (int r = 0; r < WT_H; r++) {
-                if (r >= T.th) break;
-                const int2 xy0 = sXY0[r];
-                const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
-                const int fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
-                const int e = sorg + (sfy >> 10) * WTM_PITCH + (sfx >> 10);
-                const uint32_t px = cv_blend(make_uint2(SX[e], SY[e]), make_uint2(SX[e + WTM_PITCH], SY[e + WTM_PITCH]), fx, fy);
-                const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
-                if (keep) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
-            }
-        } else {
-            for (int r = 0; r < T.th; r++) {
-                const int2 xy0 = sXY0[r];
-                const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
-                const int sx = sfx >> 10, sy = sfy >> 10, fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
-                const uint32_t t00 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx, sy);
-                const uint32_t t10 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx + 1, sy);
-                const uint32_t t01 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx, sy + 1);
-                const uint32_t t11 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx + 1, sy + 1);
-                const uint32_t px = cv_blend(wt_entry(t00, t10), wt_entry(t01, t11), fx, fy);
-                const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
-                if (keep) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
-            }
-        }
-        __syncthreads();
-
-        const int row_bytes = T.tw * 3;
-        uint8_t* const drow0 = dst + (size_t)T.oy0 * dst_stride + (size_t)T.ox0 * 3;
-        if (dst_al8 && T.tw == WT_W) {
-            constexpr int VPR = WT_W * 3 / 8;
-            uint2* d = reinterpret_cast<uint2*>(drow0 + (size_t)warp * dst_stride) + lane;
-            const uint2* o = reinterpret_cast<const uint2*>(O + warp * WT_OUT_ROW_WORDS) + lane;
-            for (int r = warp; r < T.th; r += WT_WARPS) {
-                d[0] = o[0];
-                if (lane < VPR - 32) d[32] = o[32];
-                d = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(d) + (size_t)WT_WARPS * dst_stride);
-                o += WT_WARPS * WT_OUT_ROW_WORDS / 2;
-            }
-        } else {
-            const uint8_t* Ob = reinterpret_cast<const uint8_t*>(O);
-            for (int i = tid; i < T.th * row_bytes; i += WT_THREADS) {
-                const int r = i / row_bytes, c = i - r * row_bytes;
-                drow0[(size_t)r * dst_stride + c] = Ob[r * (WT_OUT_ROW_WORDS * 4) + c];
-            }
-        }
-    }
-}
-
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 }  // namespace
@@ -1394,28 +1216,12 @@ int vsk_bgr_warp_slots_tma(vs_ctx* ctx, const void* tensor_map, const VsDevImg& 
     if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
     VS_REQUIRE(ctx, vs_cdiv(dst.h, WT_H) <= 65535 && dst.batch <= 65535, "bgr_warp_tma: grid too large");
     const int dst_al8 = aligned_to(dst.data, 8) && dst.stride % 8 == 0 && dst.batch_stride % 8 == 0;
-    // measured on B200 (1080p x 290 frames): one-shot CTAs 1.41 ms, persistent two-box pipeline 1.99 ms — seven resident
-    // one-shot CTAs per SM hide the TMA latency better than four persistent ones; the persistent form stays selectable
-    static const int persistent = getenv("VSTAB_WARP_PERSISTENT") ? atoi(getenv("VSTAB_WARP_PERSISTENT")) : 0;
     VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
-    if (persistent) {
-        // persistent: one wave of CTAs (as many as fit: 4 per SM by shared memory), each walking tiles with a two-box TMA pipeline
-        VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tma_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, WTP_SMEM_BYTES));
-        const int tiles_x = vs_cdiv(dst.w, WT_W), tiles_y = vs_cdiv(dst.h, WT_H);
-        const long long total = (long long)tiles_x * tiles_y * dst.batch;
-        VS_REQUIRE(ctx, total < (1ll << 31), "bgr_warp_tma: too many tiles");
-        const int ctas = (int)(total < (long long)ctx->sm_count * persistent * 4 ? total : (long long)ctx->sm_count * 4);
-        k_bgr_warp_cv_tma_persistent<<<ctas, WT_THREADS, WTP_SMEM_BYTES, ctx->stream>>>(
-            *reinterpret_cast<const CUtensorMap*>(tensor_map), (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
-            d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, dst_al8,
-            tiles_x, tiles_y, (int)total);
-    } else {
-        VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, WTM_SMEM_BYTES));
-        dim3 tgrid(vs_cdiv(dst.w, WT_W), vs_cdiv(dst.h, WT_H), dst.batch);
-        k_bgr_warp_cv_tma<<<tgrid, WT_THREADS, WTM_SMEM_BYTES, ctx->stream>>>(
-            *reinterpret_cast<const CUtensorMap*>(tensor_map), (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
-            d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, dst_al8);
-    }
+    VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, WTM_SMEM_BYTES));
+    dim3 tgrid(vs_cdiv(dst.w, WT_W), vs_cdiv(dst.h, WT_H), dst.batch);
+    k_bgr_warp_cv_tma<<<tgrid, WT_THREADS, WTM_SMEM_BYTES, ctx->stream>>>(
+        *reinterpret_cast<const CUtensorMap*>(tensor_map), (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
+        d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, dst_al8);
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
@@ -1477,9 +1283,29 @@ int vsk_bgr_warp_slots_rows(vs_ctx* ctx, const void* tensor_map, const VsDevImg&
     return VS_OK;
 }
 
+bool vs_warp_rows_usable(const VsDevImg& src, int mode, int border)
+{
+    // whole words per row (elements past 3w/4 words are out of bounds = zero-filled = BORDER_CONSTANT(0)), a box that fits
+    return mode == VS_WARP_CV_EXACT_BILINEAR && border == VS_BORDER_CONSTANT0 && vs_tensor_map_encoder() != nullptr &&
+           aligned_to(src.data, 16) && src.stride % 16 == 0 && (src.batch <= 1 || src.batch_stride % 16 == 0) &&
+           src.w % 4 == 0 && src.w * 3 / 4 >= VS_WARP_ROWS_BOX_WORDS && src.h >= VS_WARP_ROWS_BOX_ROWS;
+}
+
 int vsk_bgr_warp(vs_ctx* ctx, const VsDevImg& src, const VsWarpCoef* d_coef, const VsDevImg& dst,
-                 int dst_x0, int dst_y0, int mode, int border)
+                 int dst_x0, int dst_y0, int mode, int border, int32_t* d_tab)
 {
     VS_REQUIRE(ctx, src.batch == dst.batch, "bgr_warp: batch mismatch");
+    if (d_tab && vs_warp_rows_usable(src, mode, border)) {
+        // any device image as a u32 [image][row][word] tensor
+        CUtensorMap map;
+        const cuuint64_t dims[3] = {(cuuint64_t)(src.w * 3 / 4), (cuuint64_t)src.h, (cuuint64_t)src.batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)src.stride, (cuuint64_t)(src.batch > 1 ? src.batch_stride : src.stride * src.h)};
+        const cuuint32_t box[3] = {(cuuint32_t)VS_WARP_ROWS_BOX_WORDS, (cuuint32_t)VS_WARP_ROWS_BOX_ROWS, 1}, estr[3] = {1, 1, 1};
+        CUresult r = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(vs_tensor_map_encoder())(
+            &map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+            return vsk_bgr_warp_slots_rows(ctx, &map, src, nullptr, d_coef, dst, dst_x0, dst_y0, d_tab);
+    }
     return vsk_bgr_warp_slots(ctx, src, nullptr, d_coef, dst, dst_x0, dst_y0, mode, border);
 }

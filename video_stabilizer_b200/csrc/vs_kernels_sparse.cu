@@ -325,14 +325,16 @@ k_sparse_ica(const uint8_t* __restrict__ tmpl, int64_t ts, const uint8_t* __rest
 }
 
 // ------------------------------------------------------------- per-pair solver
-constexpr int SOLVE_THREADS = 256;
-constexpr int SOLVE_WARPS = SOLVE_THREADS / 32;
+// CTA size is a template parameter; three CTAs per SM so that the 299 pairs of a 300-frame clip run as one wave
+constexpr int SOLVE_MAX_WARPS = 12;
+constexpr int SOLVE_WARPS = SOLVE_MAX_WARPS;   // array extents only
 enum { FLAG_CONTINUE = 0, FLAG_CONVERGED = 1, FLAG_FAIL = 2 };
 
 struct SolveShared {
     double T[4];
     double Hinv[16];
-    double red[SOLVE_WARPS][12];
+    double red[SOLVE_WARPS][12];      // Hessian partial sums
+    double red4[SOLVE_WARPS][4];      // Gauss-Newton partial sums (a buffer of their own: thread 0 may still be busy after the Hessian reduce)
     double c0[4][2], c1[4][2];
     int flag;
     int status;
@@ -355,9 +357,6 @@ struct SolveShared {
 // per axis with the serial code, so every comparison-dependent choice is libstdc++'s own.
 // Both keypoint axes are processed in the same rounds.
 constexpr int SEL_SERIAL = 32;
-#ifndef VS_SOLVE_PREFETCH
-#define VS_SOLVE_PREFETCH 0
-#endif
 
 struct SelAxis {
     int first, last, depth, done;
@@ -383,9 +382,11 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v)
 }
 
 // keys[a]: n packed keys of axis a; pos[a]: 2*n u16 (posL then posR).  nth < n.
+template <int SOLVE_THREADS>
 __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1, uint16_t* const pos0, uint16_t* const pos1,
                                    const int n, const int nth, SelShared& ss)
 {
+    constexpr int NWARPS = SOLVE_THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (n == 0 || nth == n) return;
     if (tid < 2) {
@@ -446,7 +447,7 @@ __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1,
         for (int a = 0; a < 2; a++) {
             uint32_t before = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < SOLVE_WARPS; w++) {
+            for (int w = 0; w < NWARPS; w++) {
                 const uint32_t t = ss.warp_tot[a][w];
                 if (w < warp) before += t;
                 total += t;
@@ -492,7 +493,7 @@ __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1,
             const uint16_t* posR = posL + n;
             int m = 0;
 #pragma unroll
-            for (int w = 0; w < SOLVE_WARPS; w++) m += ss.warp_cnt[a][w];
+            for (int w = 0; w < NWARPS; w++) m += ss.warp_cnt[a][w];
             for (int k = tid; k < m; k += SOLVE_THREADS) {
                 const int i = posL[k], j = posR[k];
                 const uint32_t t = v[i]; v[i] = v[j]; v[j] = t;
@@ -517,21 +518,21 @@ __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1,
     }
 }
 
-template <int N>
-__device__ __forceinline__ void block_reduce(double* v, SolveShared& sh, double* total)
+template <int N, int NWARPS, int STRIDE>
+__device__ __forceinline__ void block_reduce(double* v, double (*red)[STRIDE], double* total)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < N; i++) {
         double r = vs_warp_reduce_sum(v[i]);
-        if (lane == 0) sh.red[warp][i] = r;
+        if (lane == 0) red[warp][i] = r;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < N; i++) {
             double s = 0;
-            for (int w = 0; w < SOLVE_WARPS; w++) s += sh.red[w][i];
+            for (int w = 0; w < NWARPS; w++) s += red[w][i];
             total[i] = s;
         }
     }
@@ -543,9 +544,11 @@ __device__ __forceinline__ double dist2d(const double* a, const double* b)
     return sqrt(dx * dx + dy * dy);
 }
 
+template <int SOLVE_THREADS, int VS_SOLVE_PREFETCH>
 __global__ void __launch_bounds__(SOLVE_THREADS, 3)
 k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 {
+    constexpr int NWARPS = SOLVE_THREADS / 32;
     extern __shared__ uint32_t dyn_keys[];   // keys[2][max_tiles]: abs_delta << 16 | tile, then (optionally) pos[2][2*max_tiles] u16
     __shared__ SolveShared sh;
     __shared__ SelShared sel;
@@ -587,14 +590,21 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         // ---- SparseWarpDiff for both keypoint sets with the incoming transform (alignment.cpp:409-431)
         float P[4];
         vs_ul_params_half(sh.T, L.w, L.h, P);
+        // the keypoint words go to the key arrays first (coalesced, all in flight together): a sample is then one
+        // dependent round trip to L2 (key word in shared memory -> taps) instead of two (keypoint -> taps)
+        for (int t = tid; t < nt; t += SOLVE_THREADS) {
+            keys0[t] = __ldg(kpl0 + t);
+            keys1[t] = __ldg(kpl1 + t);
+        }
+        __syncthreads();
         {
-            // software-pipelined over this thread's keypoints: the gather of keypoint i+256 is issued
-            // before keypoint i is evaluated
+            // optionally software-pipelined over this thread's keypoints: the gather of keypoint i+256 is issued
+            // before keypoint i is evaluated.  keys[t] is read before the same thread overwrites it with the result.
             VsLzTaps cur, nxt;
             uint32_t tb_cur = 0, tb_nxt = 0;
             auto fetch = [&](int i, VsLzTaps& taps, uint32_t& tb) {
                 const int axis = i >= nt, t = i - axis * nt;
-                const uint32_t kv = __ldg((axis ? kpl1 : kpl0) + t);
+                const uint32_t kv = (axis ? keys1 : keys0)[t];
                 const int px = min((int)(kv & 0xffffu), L.w - 1), py = min((int)(kv >> 16), L.h - 1);
                 vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3], taps);
                 tb = __ldg(timg + (size_t)py * L.pitch + px);
@@ -621,7 +631,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 
         VS_CLK(0);
         // ---- keep the k smallest: exact replay of std::nth_element (alignment.cpp:460-486)
-        block_nth_element2(keys0, keys1, pos0, pos1, nt, k, sel);
+        block_nth_element2<SOLVE_THREADS>(keys0, keys1, pos0, pos1, nt, k, sel);
         __syncthreads();
         VS_CLK(1);
 
@@ -635,18 +645,29 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 
         // ---- H = sum j j^T in f64 (alignment.cpp:278-332); X rows are (a,b,c,0), Y rows (a,b,0,c)
         {
+            // The same pass rewrites the selected keys as tile column | tile row << 10 | x offset << 20 | y offset << 25:
+            // the keypoint position of every Gauss-Newton sample then follows from shared memory alone.
             double hs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
             for (int i = tid; i < 2 * k; i += SOLVE_THREADS) {
                 const int axis = i >= k, j = i - axis * k;
-                const int t = (int)((axis ? keys1 : keys0)[j] & 0xffffu);
+                uint32_t* const kj = (axis ? keys1 : keys0) + j;
+                const int t = (int)(*kj & 0xffffu);
+                const uint32_t kv = __ldg((axis ? kpl1 : kpl0) + t);
                 float4 J = __ldg((axis ? jcl1 : jcl0) + t);
+                const int ty = t / L.tw, tx = t - ty * L.tw;
+                *kj = (uint32_t)tx | ((uint32_t)ty << 10) | (((kv & 0xffffu) - (uint32_t)(tx * L.tile)) << 20) |
+                      (((kv >> 16) - (uint32_t)(ty * L.tile)) << 25);
                 double ja = J.x, jb = J.y, jc = axis == 0 ? J.z : J.w;
                 hs[0] += ja * ja; hs[1] += ja * jb; hs[2] += jb * jb;
                 if (axis == 0) { hs[3] += ja * jc; hs[4] += jb * jc; hs[5] += jc * jc; }
                 else           { hs[6] += ja * jc; hs[7] += jb * jc; hs[8] += jc * jc; }
             }
             double tot[9];
-            block_reduce<9>(hs, sh, tot);
+            block_reduce<9, NWARPS, 12>(hs, sh.red, tot);
+            VS_CLK(2);
+            // thread 0: conditioning + inverse (a serial f64 Jacobi SVD, ~20 us).  Meanwhile warps 1.. run the gather of
+            // the first Gauss-Newton iteration, which needs only the incoming transform and the selected keypoints.
             if (tid == 0) {
                 double H[16];
                 H[0] = tot[0]; H[1] = tot[1]; H[2] = tot[3]; H[3] = tot[6];
@@ -665,47 +686,49 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
                 sh.flag = FLAG_CONTINUE;
             }
         }
-        __syncthreads();
 
-        VS_CLK(2);
         // ---- inverse-compositional Gauss-Newton iterations (alignment.cpp:600-668)
+        // sum over the selected keypoints of J * (template - keyframe(W(p))), threads first .. first + count - 1
+        auto gather = [&](int first, int count, double* b) {
+            float Pg[4];
+            vs_ul_params_half(sh.T, L.w, L.h, Pg);
+            VsLzTaps cur, nxt;
+            uint32_t tb_cur = 0, tb_nxt = 0;
+            float4 J_cur = make_float4(0, 0, 0, 0), J_nxt = J_cur;
+            auto fetch = [&](int i, VsLzTaps& taps, uint32_t& tb, float4& J) {
+                const int axis = i >= k, j = i - axis * k;
+                const uint32_t key = (axis ? keys1 : keys0)[j];
+                const int tx = (int)(key & 0x3ffu), ty = (int)((key >> 10) & 0x3ffu);
+                const int px = tx * L.tile + (int)((key >> 20) & 31u), py = ty * L.tile + (int)((key >> 25) & 31u);
+                J = __ldg((axis ? jcl1 : jcl0) + ty * L.tw + tx);
+                vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, Pg[0], Pg[1], Pg[2], Pg[3], taps);
+                tb = __ldg(timg + (size_t)min(py, L.h - 1) * L.pitch + min(px, L.w - 1));
+            };
+            int i = tid - first;
+            if (VS_SOLVE_PREFETCH && i < 2 * k) fetch(i, cur, tb_cur, J_cur);
+            while (i < 2 * k) {
+                const int inext = i + count;
+                if (!VS_SOLVE_PREFETCH) fetch(i, cur, tb_cur, J_cur);
+                else if (inext < 2 * k) fetch(inext, nxt, tb_nxt, J_nxt);
+                const float r = __fsub_rn((float)tb_cur, vs_lz_eval(cur));
+                b[0] += (double)__fmul_rn(J_cur.x, r);
+                b[1] += (double)__fmul_rn(J_cur.y, r);
+                if (i < k) b[2] += (double)__fmul_rn(J_cur.z, r);
+                else       b[3] += (double)__fmul_rn(J_cur.w, r);
+                if (VS_SOLVE_PREFETCH) { cur = nxt; tb_cur = tb_nxt; J_cur = J_nxt; }
+                i = inext;
+            }
+        };
         int iters = 0;
         int flag = FLAG_CONTINUE;
         for (int iter = 0; iter < a.max_iters; iter++) {
             iters++;
-            vs_ul_params_half(sh.T, L.w, L.h, P);
             double b[4] = {0, 0, 0, 0};
-            {
-                VsLzTaps cur, nxt;
-                uint32_t tb_cur = 0, tb_nxt = 0;
-                float4 J_cur = make_float4(0, 0, 0, 0), J_nxt = J_cur;
-                auto fetch = [&](int i, VsLzTaps& taps, uint32_t& tb, float4& J) {
-                    const int axis = i >= k, j = i - axis * k;
-                    const int t = (int)((axis ? keys1 : keys0)[j] & 0xffffu);
-                    const uint32_t kv = __ldg((axis ? kpl1 : kpl0) + t);
-                    const int px = (int)(kv & 0xffffu), py = (int)(kv >> 16);
-                    J = __ldg((axis ? jcl1 : jcl0) + t);
-                    vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3], taps);
-                    tb = __ldg(timg + (size_t)min(py, L.h - 1) * L.pitch + min(px, L.w - 1));
-                };
-                int i = tid;
-                if (VS_SOLVE_PREFETCH && i < 2 * k) fetch(i, cur, tb_cur, J_cur);
-                while (i < 2 * k) {
-                    const int inext = i + SOLVE_THREADS;
-                    if (!VS_SOLVE_PREFETCH) fetch(i, cur, tb_cur, J_cur);
-                    else if (inext < 2 * k) fetch(inext, nxt, tb_nxt, J_nxt);
-                    const float r = __fsub_rn((float)tb_cur, vs_lz_eval(cur));
-                    b[0] += (double)__fmul_rn(J_cur.x, r);
-                    b[1] += (double)__fmul_rn(J_cur.y, r);
-                    if (i < k) b[2] += (double)__fmul_rn(J_cur.z, r);
-                    else       b[3] += (double)__fmul_rn(J_cur.w, r);
-                    if (VS_SOLVE_PREFETCH) { cur = nxt; tb_cur = tb_nxt; J_cur = J_nxt; }
-                    i = inext;
-                }
-            }
+            if (iter > 0) gather(0, SOLVE_THREADS, b);
+            else if (tid >= 32) gather(32, SOLVE_THREADS - 32, b);
             VS_CLK(3);
             double tot[4];
-            block_reduce<4>(b, sh, tot);
+            block_reduce<4, NWARPS, 4>(b, sh.red4, tot);
             if (tid == 0) {
                 double bb[4], dt[4];
                 for (int c = 0; c < 4; c++) bb[c] = tot[c] * 0.5;
@@ -862,9 +885,20 @@ int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
         smem += pos_bytes;
         args.pos_scratch = nullptr;
     }
-    VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);
-    k_solve_pairs<<<a.n_pairs, SOLVE_THREADS, smem, ctx->stream>>>(g, args);
+    // Measured on B200 (1080p, 299 pairs in flight), all rejected: CTAs of 320 / 384 threads (registers capped at 64 / 56:
+    // 0.88 / 1.09 ms mean per pair against 0.85), register software pipelining of the gathers (1.00 ms), L2 prefetch of
+    // the samples 1 / 2 / 4 iterations ahead (0.91 / 1.00 / 1.15 ms).  More loads in flight make it slower: the gathers
+    // are bound by the rate of random 32-byte sector reads from DRAM (L2 hit rate 27 %), not by their latency.
+    static const int prefetch = getenv("VSTAB_SOLVE_PREFETCH") ? atoi(getenv("VSTAB_SOLVE_PREFETCH")) : 0;
+    if (prefetch) {
+        VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);
+        k_solve_pairs<256, 1><<<a.n_pairs, 256, smem, ctx->stream>>>(g, args);
+    } else {
+        VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);
+        k_solve_pairs<256, 0><<<a.n_pairs, 256, smem, ctx->stream>>>(g, args);
+    }
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }

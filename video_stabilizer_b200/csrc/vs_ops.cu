@@ -290,19 +290,24 @@ int vs_bgr_warp_u8(vs_ctx* ctx, const vs_img* src, const double* M6, const vs_im
     for (int b = 0; b < batch; b++) vs_warp_coef_from_forward(M6 + 6 * b, &coef[b]);
     Stage st(ctx);
     st.want_raw(coef.size() * sizeof(VsWarpCoef));
+    // fixed-point tables of the row-group kernel (cv-exact mode, constant border)
+    const size_t tab_bytes = mode == VS_WARP_CV_EXACT_BILINEAR && border == VS_BORDER_CONSTANT0
+                                 ? vs_warp_rows_tab_ints(dst->width, dst->height) * sizeof(int32_t) * batch : 0;
+    st.want_raw(tab_bytes);
     if (mem == VS_MEM_HOST) { st.want_img(src, 3); st.want_img(dst, 3); }
     VS_TRY(st.reserve());
-    void* dcoef;
+    void *dcoef, *dtab = nullptr;
     // pageable source: the copy is complete when cudaMemcpyAsync returns, so `coef` may go away
     VS_TRY(st.raw(coef.data(), coef.size() * sizeof(VsWarpCoef), true, &dcoef));
+    if (tab_bytes) VS_TRY(st.raw(nullptr, tab_bytes, false, &dtab));
     if (mem == VS_MEM_DEVICE) {
-        int r = vsk_bgr_warp(ctx, vs_dev_img(src), (const VsWarpCoef*)dcoef, vs_dev_img(dst), dst_x0, dst_y0, mode, border);
+        int r = vsk_bgr_warp(ctx, vs_dev_img(src), (const VsWarpCoef*)dcoef, vs_dev_img(dst), dst_x0, dst_y0, mode, border, (int32_t*)dtab);
         return r;
     }
     VsDevImg dsrc, ddst;
     VS_TRY(st.img(src, 3, 1, true, &dsrc));
     VS_TRY(st.img(dst, 3, 1, false, &ddst));
-    VS_TRY(vsk_bgr_warp(ctx, dsrc, (const VsWarpCoef*)dcoef, ddst, dst_x0, dst_y0, mode, border));
+    VS_TRY(vsk_bgr_warp(ctx, dsrc, (const VsWarpCoef*)dcoef, ddst, dst_x0, dst_y0, mode, border, (int32_t*)dtab));
     VS_TRY(st.img_out(ddst, dst, 3, 1));
     return st.finish();
 }
