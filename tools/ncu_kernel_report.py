@@ -29,17 +29,22 @@ for h, u, v in zip(hdr, units, r):
         print("%-90s %-10s %s" % (h, u, v[:80]))
 
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
-blocks, cur, h = [], None, None
-for row in rows:
+srows = list(csv.reader(io.StringIO(src)))
+blocks, names, cur, h = [], [], None, None
+for row in srows:
     if row and row[0] == "Kernel Name":
         cur = []
         blocks.append(cur)
+        names.append(row[1] if len(row) > 1 else "")
     elif row and row[0] == "Address":
         h = row
     elif cur is not None and len(row) > 10:
         cur.append(row)
-b = blocks[idx]
+# the SASS section is only trusted for single-kernel captures (ncu -k regex:<kernel>): block idx of the source page
+if len({x[hdr.index("Kernel Name")] for x in rows[2:]}) != 1:
+    print("\n(SASS runs are printed for captures of a single kernel only: use ncu -k regex:<name>)")
+    sys.exit(0)
+b = blocks[min(idx, len(blocks) - 1)]
 iS, iE, iM = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
 tot = sum(int(x[iE]) for x in b)
 print("\nSASS runs (>= 0.3%% of %d executed warp instructions, %d SASS lines):" % (tot, len(b)))
