@@ -42,6 +42,7 @@ struct vs_clip {
     int32_t* d_dbg_count = nullptr;
     long long* d_dbg_clock = nullptr;   // [max_pairs][8]
     uint16_t* d_pos_scratch = nullptr; // [max_pairs][4][max_tiles] candidate lists of the parallel selection
+    float* d_res_scratch = nullptr;    // [max_pairs][2][max_tiles] warp-diff residuals reused by the first Gauss-Newton iteration
     uint8_t* d_warp_out = nullptr;    // staging for VS_MEM_HOST warps, grown on demand
     size_t warp_out_bytes = 0;
     // asynchronous transfer pipeline (vs_clip_upload_async / vs_clip_warp_to_host_async)
@@ -88,7 +89,7 @@ void free_all(vs_clip* c)
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
-    cudaFree(c->d_pos_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
+    cudaFree(c->d_pos_scratch); cudaFree(c->d_res_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
     cudaFree(c->d_warp_tab);
 }
 
@@ -214,6 +215,7 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_slots, (size_t)nslots);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_coef, (size_t)capacity);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_pos_scratch, (size_t)max_pairs * 4 * g.max_tiles);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_res_scratch, (size_t)max_pairs * 2 * g.max_tiles);
     if (r == VS_OK && (flags & VS_CLIP_DEBUG_TAPS)) {
         r = dev_alloc(ctx, &c->d_dbg_wd, (size_t)max_pairs * 2 * g.total_tiles);
         if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_order, (size_t)max_pairs * 2 * g.total_tiles);
@@ -341,6 +343,7 @@ int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_
     a.out_iters = dev_out ? out_iters : (out_iters ? c->d_iters : nullptr);
     a.dbg_warpdiff = c->d_dbg_wd; a.dbg_order = c->d_dbg_order; a.dbg_count = c->d_dbg_count;
     a.pos_scratch = c->d_pos_scratch;
+    a.res_scratch = c->d_res_scratch;
     a.dbg_clock = c->d_dbg_clock;
     if (c->d_dbg_count)   // -1 marks levels a pair never reached
         VS_CUDA(ctx, cudaMemsetAsync(c->d_dbg_count, 0xFF, (size_t)c->max_pairs * 2 * c->g.levels * sizeof(int32_t), ctx->stream));

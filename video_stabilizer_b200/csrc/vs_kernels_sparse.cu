@@ -565,6 +565,9 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
     uint16_t* const pos0 = a.pos_scratch ? a.pos_scratch + (size_t)pair * 4 * g.max_tiles
                                          : reinterpret_cast<uint16_t*>(dyn_keys + 2 * g.max_tiles);
     uint16_t* const pos1 = pos0 + 2 * g.max_tiles;
+    // signed residual template - keyframe(W(p)) of every tile from the warp-diff pass: the first Gauss-Newton iteration of a
+    // level evaluates exactly these samples again (same transform), so it reads them back instead of the images
+    float* const res = a.res_scratch ? a.res_scratch + (size_t)pair * 2 * g.max_tiles : nullptr;
 
     if (tid == 0) {
         sh.T[0] = sh.T[1] = sh.T[2] = sh.T[3] = 0.0;
@@ -617,6 +620,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
                 else if (inext < 2 * nt) fetch(inext, nxt, tb_nxt);
                 const int axis = i >= nt, t = i - axis * nt;
                 const float s = vs_lz_eval(cur);
+                if (res) res[axis * g.max_tiles + t] = __fsub_rn((float)tb_cur, s);
                 float d = fabsf(__fsub_rn(s, (float)tb_cur));
                 d = fmaxf(fminf(d, 65535.0f), 0.0f);
                 const uint32_t u = (uint32_t)d;
@@ -719,13 +723,31 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
                 i = inext;
             }
         };
+        // first iteration: residuals of the warp-diff pass (bit-identical: same samples, same transform)
+        auto gather_cached = [&](int first, int count, double* b) {
+#pragma unroll 2
+            for (int i = tid - first; i < 2 * k; i += count) {
+                const int axis = i >= k, j = i - axis * k;
+                const uint32_t key = (axis ? keys1 : keys0)[j];
+                const int t = (int)((key >> 10) & 0x3ffu) * L.tw + (int)(key & 0x3ffu);
+                const float4 J = __ldg((axis ? jcl1 : jcl0) + t);
+                const float r = __ldcg(res + axis * g.max_tiles + t);
+                b[0] += (double)__fmul_rn(J.x, r);
+                b[1] += (double)__fmul_rn(J.y, r);
+                if (i < k) b[2] += (double)__fmul_rn(J.z, r);
+                else       b[3] += (double)__fmul_rn(J.w, r);
+            }
+        };
         int iters = 0;
         int flag = FLAG_CONTINUE;
         for (int iter = 0; iter < a.max_iters; iter++) {
             iters++;
             double b[4] = {0, 0, 0, 0};
             if (iter > 0) gather(0, SOLVE_THREADS, b);
-            else if (tid >= 32) gather(32, SOLVE_THREADS - 32, b);
+            else if (tid >= 32) {
+                if (res) gather_cached(32, SOLVE_THREADS - 32, b);
+                else gather(32, SOLVE_THREADS - 32, b);
+            }
             VS_CLK(3);
             double tot[4];
             block_reduce<4, NWARPS, 4>(b, sh.red4, tot);
