@@ -228,6 +228,10 @@ int vs_clip_get_selected(vs_clip*, int pair, int level, int axis, uint32_t* out_
 /* SM cycles pair `pair` of the last vs_clip_align spent per phase, summed over levels:
  * {warp-diff, selection, Hessian + SVD, Gauss-Newton gathers, Gauss-Newton reduce + update, 0} */
 int vs_clip_get_solver_cycles(vs_clip*, int pair, long long* out6);
+/* Debug tap for the solver's 4x4 conditioning + SVD pseudo-inverse (alignment.cpp:554-583) as it runs on the device:
+ * n row-major 4x4 f64 matrices from host memory -> the inverse computed by the lane-parallel form the solver uses
+ * (out_quad) and by the serial restatement (out_serial), plus the condition number; the two must agree bit for bit. */
+int vs_debug_invert4(vs_ctx*, const double* H, int n, double* out_quad, double* out_serial, double* out_cond);
 
 #ifdef __cplusplus
 }

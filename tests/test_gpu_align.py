@@ -223,3 +223,37 @@ def test_clip_alignment_4k(gpu, ob):
     frames, poses = synth.make_clip_gpu(gpu, 3840, 2160, 3, 17)
     worst, T, status, ref = check_clip_against_oracle(gpu, ob, frames, deep=False)
     assert status.all() and worst < 1e-6
+
+
+def test_lane_parallel_svd_inverse_equals_the_serial_one_bit_for_bit(gpu, ob):
+    """The solver inverts its 4x4 Hessian with a Jacobi SVD spread over four lanes; it must reproduce the serial
+    restatement of cv::SVD + Mat::inv(DECOMP_SVD) bit for bit (same operations, same order), on well-conditioned
+    Hessians, on the regularised branch (cond > 1e6, alignment.cpp:566-571) and on singular input."""
+    from video_stabilizer_b200 import _capi as capi
+    rng = np.random.default_rng(5)
+    mats = []
+    for i in range(200):
+        n = int(rng.integers(8, 4000))
+        J = rng.normal(size=(n, 4)) * rng.uniform(0.1, 300, size=4)
+        if i % 3 == 0:
+            J[:, 3] = 0 if i % 2 else J[:, 2] * (1 + 1e-9 * rng.normal(size=n))     # singular / nearly dependent columns
+        if i % 7 == 0:
+            J[:, 0] *= 1e-5
+        mats.append(J.T @ J)
+    mats.append(np.zeros((4, 4)))
+    mats.append(np.eye(4))
+    H = np.ascontiguousarray(np.stack(mats), np.float64)
+    n = H.shape[0]
+    quad, serial, cond = np.zeros_like(H), np.zeros_like(H), np.zeros(n)
+    capi.check(gpu.handle, gpu.lib.vs_debug_invert4(gpu.handle, capi.ptr(H), n, capi.ptr(quad), capi.ptr(serial), capi.ptr(cond)),
+               "vs_debug_invert4")
+    assert np.array_equal(quad.view(np.uint64), serial.view(np.uint64))
+    assert (cond > 1e6).sum() > 10 and (cond < 1e6).sum() > 10
+    for i in range(n):
+        w, _, _ = ob.svd4(H[i])
+        Hi = H[i].copy()
+        if w[0] / (w[3] + 1e-10) > 1e6:
+            Hi[np.arange(4), np.arange(4)] += 1e-6 * w[0]
+        want = ob.inv4_svd(Hi)
+        scale = np.abs(want).max() + 1e-300
+        assert np.abs(quad[i] - want).max() <= 1e-9 * scale, i

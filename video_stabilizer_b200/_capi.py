@@ -91,6 +91,7 @@ SYMBOLS = {
     "vs_clip_get_jacobians": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "vs_clip_get_warpdiff": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "vs_clip_get_solver_cycles": (C.c_int, [_P, C.c_int, _P]),
+    "vs_debug_invert4": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "vs_clip_get_selected": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
 }
 

@@ -144,6 +144,7 @@ int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int o
     const size_t out_frame_bytes = (size_t)out_width() * out_height() * 3;
     (void)out_frame_bytes;
     int launched = 0;
+    int batch = std::min(16, m_warp_batch);   // first launch early (the GPU idles until then), later ones grow to m_warp_batch
     auto launch_warps = [&](int upto) {
         const int cnt = upto - launched;
         if (cnt <= 0) return;
@@ -173,7 +174,10 @@ int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int o
             m_corr.push_back(corr);
             due_slots.push_back((int32_t)((m_emitted + (long)due_slots.size()) % m_capacity));
             due_T.insert(due_T.end(), {corr.A, corr.B, corr.TX, corr.TY});
-            if (overlap && (int)due_slots.size() - launched >= m_warp_batch) launch_warps((int)due_slots.size());
+            if (overlap && (int)due_slots.size() - launched >= batch) {
+                launch_warps((int)due_slots.size());
+                batch = std::min(2 * batch, m_warp_batch);
+            }
         }
     }
     m_fed = f0 + n;

@@ -69,7 +69,7 @@ public:
 private:
     int m_w, m_h, m_chunk, m_capacity, m_crop;
     int m_sub = 32;        // sub-chunk of the host-to-host pipeline
-    int m_warp_batch = 64; // due frames per warp launch while the host trajectory is still running
+    int m_warp_batch = 96; // largest batch of due frames per warp launch while the host trajectory is still running (16, 32, 64, 96, 96 ...)
     VideoStabilizerParams m_params;
     vs_ctx* m_ctx = nullptr;
     vs_clip* m_clip = nullptr;

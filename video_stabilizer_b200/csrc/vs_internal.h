@@ -114,3 +114,4 @@ struct VsSolveArgs {
 int vsk_keyframe_features(vs_ctx*, const VsClipGeom& g, const uint8_t* d_pyr, const int32_t* d_slots,
                           int n_slots, uint32_t* d_kp, float4* d_jac);
 int vsk_solve_pairs(vs_ctx*, const VsClipGeom& g, const VsSolveArgs& a);
+int vsk_debug_invert4(vs_ctx*, const double* d_H, int n, double* d_quad, double* d_serial, double* d_cond);

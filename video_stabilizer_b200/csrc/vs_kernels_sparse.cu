@@ -332,6 +332,7 @@ enum { FLAG_CONTINUE = 0, FLAG_CONVERGED = 1, FLAG_FAIL = 2 };
 
 struct SolveShared {
     double T[4];
+    double H[16];
     double Hinv[16];
     double red[SOLVE_WARPS][12];      // Hessian partial sums
     double red4[SOLVE_WARPS][4];      // Gauss-Newton partial sums (a buffer of their own: thread 0 may still be busy after the Hessian reduce)
@@ -361,7 +362,8 @@ constexpr int SEL_SERIAL = 32;
 struct SelAxis {
     int first, last, depth, done;
     uint32_t pivot;
-    int nL, nR, m;
+    int nL, nR;
+    int cutL, cutR;     // posL[m] and posR[m-1] of the current round (see the swap phase)
 };
 
 struct SelShared {
@@ -405,6 +407,7 @@ __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1,
                     st.done = 1;
                 } else {
                     --st.depth;
+                    st.cutL = st.cutR = 0x7fffffff;
                     const int mid = st.first + (st.last - st.first) / 2;
                     vs_sel::move_median_to_first(v, st.first, st.first + 1, mid, st.last - 1);
                     st.pivot = v[st.first];
@@ -469,48 +472,51 @@ __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1,
         }
         __syncthreads();
 
-        // ---- m = number of swaps = #{k : a_k < b_k}
+        // ---- the swaps.  a_k increases and b_k decreases with k, so "a_k < b_k" holds exactly for k < m: every thread
+        //      decides its own swaps without knowing m, m is the block-wide count, and the two positions the bookkeeping
+        //      needs (posL[m], posR[m-1]) are the smallest a_k not swapped and the smallest b_k swapped.
 #pragma unroll
         for (int a = 0; a < 2; a++) {
             int c = 0;
             if (a ? act1 : act0) {
+                uint32_t* v = a ? keys1 : keys0;
                 const uint16_t* posL = a ? pos1 : pos0;
                 const uint16_t* posR = posL + n;
-                const int lim = min(ss.ax[a].nL, ss.ax[a].nR);
-                for (int k = tid; k < lim; k += SOLVE_THREADS) c += posL[k] < posR[k] ? 1 : 0;
+                const int nL = ss.ax[a].nL, lim = min(nL, ss.ax[a].nR);
+                int minL = 0x7fffffff, minR = 0x7fffffff;
+                for (int k = tid; k <= lim; k += SOLVE_THREADS) {
+                    if (k == lim) { if (k < nL) minL = min(minL, (int)posL[k]); break; }
+                    const int i = posL[k], j = posR[k];
+                    if (i < j) {
+                        const uint32_t t = v[i]; v[i] = v[j]; v[j] = t;
+                        c++;
+                        minR = min(minR, j);
+                    } else {
+                        minL = min(minL, i);
+                    }
+                }
+                minL = __reduce_min_sync(0xffffffffu, minL);
+                minR = __reduce_min_sync(0xffffffffu, minR);
+                if (lane == 0) {
+                    if (minL != 0x7fffffff) atomicMin(&ss.ax[a].cutL, minL);
+                    if (minR != 0x7fffffff) atomicMin(&ss.ax[a].cutR, minR);
+                }
             }
             c = __reduce_add_sync(0xffffffffu, c);
             if (lane == 0) ss.warp_cnt[a][warp] = c;
         }
         __syncthreads();
-
-        // ---- the swaps, then the bookkeeping of __introselect
-#pragma unroll
-        for (int a = 0; a < 2; a++) {
-            if (!(a ? act1 : act0)) continue;
-            uint32_t* v = a ? keys1 : keys0;
-            const uint16_t* posL = a ? pos1 : pos0;
-            const uint16_t* posR = posL + n;
-            int m = 0;
-#pragma unroll
-            for (int w = 0; w < NWARPS; w++) m += ss.warp_cnt[a][w];
-            for (int k = tid; k < m; k += SOLVE_THREADS) {
-                const int i = posL[k], j = posR[k];
-                const uint32_t t = v[i]; v[i] = v[j]; v[j] = t;
-            }
-            if (tid == 32 * a) ss.ax[a].m = m;
-        }
-        __syncthreads();
+        // ---- the bookkeeping of __introselect
         if (tid == 0 || tid == 32) {
             const int a = tid >> 5;
             SelAxis& st = ss.ax[a];
             if (!st.done) {
-                const uint16_t* posL = a ? pos1 : pos0;
-                const uint16_t* posR = posL + n;
-                const int m = st.m;
+                int m = 0;
+#pragma unroll
+                for (int w = 0; w < NWARPS; w++) m += ss.warp_cnt[a][w];
                 int cut = st.last;
-                if (m < st.nL) cut = posL[m];
-                if (m > 0) cut = min(cut, (int)posR[m - 1]);
+                if (m < st.nL) cut = st.cutL;                       // posL[m]
+                if (m > 0) cut = min(cut, st.cutR);                  // posR[m - 1]
                 if (cut <= nth) st.first = cut; else st.last = cut;
             }
         }
@@ -670,24 +676,37 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
             double tot[9];
             block_reduce<9, NWARPS, 12>(hs, sh.red, tot);
             VS_CLK(2);
-            // thread 0: conditioning + inverse (a serial f64 Jacobi SVD, ~20 us).  Meanwhile warps 1.. run the gather of
-            // the first Gauss-Newton iteration, which needs only the incoming transform and the selected keypoints.
-            if (tid == 0) {
-                double H[16];
-                H[0] = tot[0]; H[1] = tot[1]; H[2] = tot[3]; H[3] = tot[6];
-                H[4] = tot[1]; H[5] = tot[2]; H[6] = tot[4]; H[7] = tot[7];
-                H[8] = tot[3]; H[9] = tot[4]; H[10] = tot[5]; H[11] = 0.0;
-                H[12] = tot[6]; H[13] = tot[7]; H[14] = 0.0; H[15] = tot[8];
-                vs_condition_and_invert(H, sh.Hinv);
-                // corner bookkeeping (alignment.cpp:585-598)
-                const double cx = L.w * 0.5, cy = L.h * 0.5;
-                const double xr = (double)((float)L.w - 1.f), yb = (double)((float)L.h - 1.f);
-                const double cr[4][2] = {{0.0, 0.0}, {xr, 0.0}, {0.0, yb}, {xr, yb}};
-                for (int c = 0; c < 4; c++) {
-                    vs_tf_warp_center(sh.T, cr[c][0], cr[c][1], cx, cy, sh.c0[c]);
-                    sh.c1[c][0] = sh.c0[c][0]; sh.c1[c][1] = sh.c0[c][1];
+            // warp 0: conditioning + inverse (f64 Jacobi SVD spread over the lanes of a quad, bit-identical to the serial
+            // vs_condition_and_invert).  Meanwhile warps 1.. run the first Gauss-Newton iteration, which needs only the
+            // incoming transform and the selected keypoints.
+            if (tid < 32) {
+                if (tid == 0) {
+                    double* H = sh.H;
+                    H[0] = tot[0]; H[1] = tot[1]; H[2] = tot[3]; H[3] = tot[6];
+                    H[4] = tot[1]; H[5] = tot[2]; H[6] = tot[4]; H[7] = tot[7];
+                    H[8] = tot[3]; H[9] = tot[4]; H[10] = tot[5]; H[11] = 0.0;
+                    H[12] = tot[6]; H[13] = tot[7]; H[14] = 0.0; H[15] = tot[8];
                 }
-                sh.flag = FLAG_CONTINUE;
+                __syncwarp();
+                double hrow[4], hinv[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) hrow[c] = sh.H[(tid & 3) * 4 + c];
+                vs_condition_and_invert_quad(hrow, hinv);
+                if (tid < 4) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) sh.Hinv[tid * 4 + c] = hinv[c];
+                }
+                if (tid == 0) {
+                    // corner bookkeeping (alignment.cpp:585-598)
+                    const double cx = L.w * 0.5, cy = L.h * 0.5;
+                    const double xr = (double)((float)L.w - 1.f), yb = (double)((float)L.h - 1.f);
+                    const double cr[4][2] = {{0.0, 0.0}, {xr, 0.0}, {0.0, yb}, {xr, yb}};
+                    for (int c = 0; c < 4; c++) {
+                        vs_tf_warp_center(sh.T, cr[c][0], cr[c][1], cx, cy, sh.c0[c]);
+                        sh.c1[c][0] = sh.c0[c][0]; sh.c1[c][1] = sh.c0[c][1];
+                    }
+                    sh.flag = FLAG_CONTINUE;
+                }
             }
         }
 
@@ -813,9 +832,40 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
     }
 }
 
+// debug tap: one warp per matrix, quad form on all lanes and the serial form on lane 0
+__global__ void __launch_bounds__(32)
+k_debug_invert4(const double* __restrict__ H, double* __restrict__ out_quad, double* __restrict__ out_serial, double* __restrict__ out_cond)
+{
+    const int m = blockIdx.x, lane = threadIdx.x;
+    double hrow[4], hinv[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) hrow[c] = H[m * 16 + (lane & 3) * 4 + c];
+    const double cond = vs_condition_and_invert_quad(hrow, hinv);
+    if (lane < 4) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) out_quad[m * 16 + lane * 4 + c] = hinv[c];
+    }
+    if (lane == 0) {
+        double Hs[16], Hi[16];
+        for (int i = 0; i < 16; i++) Hs[i] = H[m * 16 + i];
+        vs_condition_and_invert(Hs, Hi);
+        for (int i = 0; i < 16; i++) out_serial[m * 16 + i] = Hi[i];
+        out_cond[m] = cond;
+    }
+}
+
 }  // namespace
 
 // ================================================================== launchers
+
+int vsk_debug_invert4(vs_ctx* ctx, const double* d_H, int n, double* d_quad, double* d_serial, double* d_cond)
+{
+    if (n <= 0) return VS_OK;
+    VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);
+    k_debug_invert4<<<n, 32, 0, ctx->stream>>>(d_H, d_quad, d_serial, d_cond);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
 
 int vsk_grad_argmax(vs_ctx* ctx, const VsDevImg& gx, const VsDevImg& gy, int tile, uint16_t* d_lmx, uint16_t* d_lmy)
 {

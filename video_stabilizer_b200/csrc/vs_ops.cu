@@ -312,4 +312,25 @@ int vs_bgr_warp_u8(vs_ctx* ctx, const vs_img* src, const double* M6, const vs_im
     return st.finish();
 }
 
+int vs_debug_invert4(vs_ctx* ctx, const double* H, int n, double* out_quad, double* out_serial, double* out_cond)
+{
+    if (!ctx) return VS_ERR_INVALID;
+    VS_REQUIRE(ctx, H && out_quad && out_serial && out_cond && n >= 0, "debug_invert4: bad arguments");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t mb = (size_t)n * 16 * sizeof(double);
+    Stage st(ctx);
+    st.want_raw(mb); st.want_raw(mb); st.want_raw(mb); st.want_raw((size_t)n * sizeof(double));
+    VS_TRY(st.reserve());
+    void *dH, *dq, *ds, *dc;
+    VS_TRY(st.raw(H, mb, true, &dH));
+    VS_TRY(st.raw(nullptr, mb, false, &dq));
+    VS_TRY(st.raw(nullptr, mb, false, &ds));
+    VS_TRY(st.raw(nullptr, (size_t)n * sizeof(double), false, &dc));
+    VS_TRY(vsk_debug_invert4(ctx, (const double*)dH, n, (double*)dq, (double*)ds, (double*)dc));
+    VS_TRY(st.raw_out(out_quad, dq, mb));
+    VS_TRY(st.raw_out(out_serial, ds, mb));
+    VS_TRY(st.raw_out(out_cond, dc, (size_t)n * sizeof(double)));
+    return st.finish();
+}
+
 }  // extern "C"
