@@ -368,11 +368,16 @@ def run_gpu_arm(args):
             traffic = t / d["launches_per_step"] if t else None
         except Exception:
             traffic = None
+    second = sorted(per_kernel, key=lambda k: -per_kernel[k]["ms_per_step"])[1] if len(per_kernel) > 1 else None
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": d["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": d["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_step"] / d["launches_per_step"],
                 "launches_per_step": d["launches_per_step"], "ms_per_launch": d["ms_per_launch"],
                 "kernel_share_of_step": d["ms_per_step"] / max(prof_ms, 1e-9)}
+    if second:
+        d2 = per_kernel[second]
+        roofline["runner_up"] = {"kernel": second, "achieved": d2["algorithmic_gbs"], "frac": d2["frac_of_hbm_peak"],
+                                 "ms_per_step": d2["ms_per_step"], "kernel_share_of_step": d2["ms_per_step"] / max(prof_ms, 1e-9)}
 
     # ---- CPU baseline on this box's cores (N=1 only)
     cpu = None
