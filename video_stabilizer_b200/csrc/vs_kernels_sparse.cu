@@ -326,7 +326,7 @@ k_sparse_ica(const uint8_t* __restrict__ tmpl, int64_t ts, const uint8_t* __rest
 
 // ------------------------------------------------------------- per-pair solver
 // CTA size is a template parameter; three CTAs per SM so that the 299 pairs of a 300-frame clip run as one wave
-constexpr int SOLVE_MAX_WARPS = 12;
+constexpr int SOLVE_MAX_WARPS = 32;
 constexpr int SOLVE_WARPS = SOLVE_MAX_WARPS;   // array extents only
 enum { FLAG_CONTINUE = 0, FLAG_CONVERGED = 1, FLAG_FAIL = 2 };
 
@@ -550,8 +550,8 @@ __device__ __forceinline__ double dist2d(const double* a, const double* b)
     return sqrt(dx * dx + dy * dy);
 }
 
-template <int SOLVE_THREADS, int VS_SOLVE_PREFETCH>
-__global__ void __launch_bounds__(SOLVE_THREADS, 3)
+template <int SOLVE_THREADS, int VS_SOLVE_PREFETCH, int MIN_CTAS>
+__global__ void __launch_bounds__(SOLVE_THREADS, MIN_CTAS)
 k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 {
     constexpr int NWARPS = SOLVE_THREADS / 32;
@@ -961,16 +961,25 @@ int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
     // 0.88 / 1.09 ms mean per pair against 0.85), register software pipelining of the gathers (1.00 ms), L2 prefetch of
     // the samples 1 / 2 / 4 iterations ahead (0.91 / 1.00 / 1.15 ms).  More loads in flight make it slower: the gathers
     // are bound by the rate of random 32-byte sector reads from DRAM (L2 hit rate 27 %), not by their latency.
+    // CTA size by how many pairs are in flight: every pair must be resident at once (a second wave would double the
+    // time: the kernel lasts as long as its slowest pair), and within that the largest CTA wins because the gathers
+    // of a pair are independent.  256 x 3 per SM (444 pairs), 512 x 1 (148 pairs, registers uncapped), 1024 x 1 for
+    // the big shared-memory footprints of 4K where only one CTA fits anyway.
     static const int prefetch = getenv("VSTAB_SOLVE_PREFETCH") ? atoi(getenv("VSTAB_SOLVE_PREFETCH")) : 0;
-    if (prefetch) {
-        VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);
-        k_solve_pairs<256, 1><<<a.n_pairs, 256, smem, ctx->stream>>>(g, args);
-    } else {
-        VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);
-        k_solve_pairs<256, 0><<<a.n_pairs, 256, smem, ctx->stream>>>(g, args);
-    }
+    static const int force = getenv("VSTAB_SOLVE_THREADS") ? atoi(getenv("VSTAB_SOLVE_THREADS")) : 0;
+#define VS_SOLVE_LAUNCH(NT, PF, MINB)                                                                                             \
+    do {                                                                                                                          \
+        VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<NT, PF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);                                                                                          \
+        k_solve_pairs<NT, PF, MINB><<<a.n_pairs, NT, smem, ctx->stream>>>(g, args);                                               \
+    } while (0)
+    int threads = a.n_pairs <= ctx->sm_count ? 512 : 256;
+    if (force == 256 || force == 512 || force == 1024) threads = force;
+    if (prefetch) VS_SOLVE_LAUNCH(256, 1, 3);
+    else if (threads == 1024) VS_SOLVE_LAUNCH(1024, 0, 1);
+    else if (threads == 512) VS_SOLVE_LAUNCH(512, 0, 1);
+    else VS_SOLVE_LAUNCH(256, 0, 3);
+#undef VS_SOLVE_LAUNCH
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
