@@ -180,24 +180,46 @@ __device__ __forceinline__ uint4 kf_load_row(const uint8_t* __restrict__ img, in
     return v;
 }
 
+// bands one CTA handles on a level: a band of the narrow levels keeps only one or two warps busy (16 pixels per
+// thread), and a CTA lasts as long as the band is tall whatever its width, so the narrow levels put several bands
+// side by side in one CTA (a team of 1, 2 or 4 warps per band).  Shared by the kernel and its launcher.
+__host__ __device__ inline int kf_bands_per_cta(const VsLevel& L)
+{
+    const int groups = (L.tw * L.tile + 15) / 16;
+    int b = groups <= 32 ? 4 : (groups <= 64 ? 2 : 1);
+    while (b > 1 && L.tw * b > KF_MAX_TW) b >>= 1;
+    return b;
+}
+
 __global__ void __launch_bounds__(KF_THREADS, 8)
 k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t* __restrict__ slots,
                     uint32_t* __restrict__ kp, float4* __restrict__ jac)
 {
-    __shared__ uint32_t acc[2][KF_MAX_TW];
-    // which (level, band) is this CTA?  band_off is the running sum of th over levels
-    int lvl = 0, band = blockIdx.x;
-    while (band >= g.lv[lvl].th) { band -= g.lv[lvl].th; lvl++; }
+    __shared__ uint32_t acc_all[2 * KF_MAX_TW];
+    // which (level, band group) is this CTA?
+    int lvl = 0, grp = blockIdx.x;
+    int bpc = kf_bands_per_cta(g.lv[0]);
+    while (grp >= (g.lv[lvl].th + bpc - 1) / bpc) {
+        grp -= (g.lv[lvl].th + bpc - 1) / bpc;
+        lvl++;
+        bpc = kf_bands_per_cta(g.lv[lvl]);
+    }
     const VsLevel L = g.lv[lvl];
+    const int team_size = KF_THREADS / bpc, team = threadIdx.x / team_size, ttid = threadIdx.x - team * team_size;
+    const int band = grp * bpc + team;
+    const bool live = band < L.th;
+    // accumulators of this team: [axis][KF_MAX_TW / bpc]
+    uint32_t* const acc0 = acc_all + team * (2 * KF_MAX_TW / bpc);
+    uint32_t* const acc1 = acc0 + KF_MAX_TW / bpc;
     const int slot = slots[blockIdx.y];
     const uint8_t* img = pyr + (size_t)slot * g.pyr_slot_bytes + L.img_off;
     const int N = L.tile, NN1 = N * N - 1;
     const int y0 = band * N;
-    const int wtiles = L.tw * N;                      // columns that belong to a tile
-    for (int i = threadIdx.x; i < L.tw; i += KF_THREADS) { acc[0][i] = 0u; acc[1][i] = 0u; }
+    const int wtiles = live ? L.tw * N : 0;           // columns that belong to a tile
+    for (int i = ttid; i < L.tw; i += team_size) { acc0[i] = 0u; acc1[i] = 0u; }
     __syncthreads();
 
-    for (int x0 = threadIdx.x * 16; x0 < wtiles; x0 += KF_THREADS * 16) {
+    for (int x0 = ttid * 16; x0 < wtiles; x0 += team_size * 16) {
         uint32_t mx[16], my[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) { mx[i] = 0u; my[i] = 0u; }
@@ -245,16 +267,16 @@ k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t
             }
             rx++;
             if (rx == N || i == 15) {
-                if (bx | by) { atomicMax(&acc[0][tile], bx); atomicMax(&acc[1][tile], by); }
+                if (bx | by) { atomicMax(&acc0[tile], bx); atomicMax(&acc1[tile], by); }
                 bx = by = 0u; rx = 0; tile++;
             }
         }
     }
     __syncthreads();
 
-    for (int i = threadIdx.x; i < 2 * L.tw; i += KF_THREADS) {
+    for (int i = ttid; i < (live ? 2 * L.tw : 0); i += team_size) {
         const int axis = i >= L.tw, tx = i - axis * L.tw;
-        const int p = NN1 - (int)(acc[axis][tx] & 0xffffu);
+        const int p = NN1 - (int)((axis ? acc1 : acc0)[tx] & 0xffffu);
         const int x = tx * N + p % N, y = y0 + p / N;
         float4 J;
         if (axis == 0) {
@@ -926,7 +948,8 @@ int vsk_keyframe_features(vs_ctx* ctx, const VsClipGeom& g, const uint8_t* d_pyr
     int bands = 0;
     for (int l = 0; l < g.levels; l++) {
         banded = banded && g.lv[l].pitch % 16 == 0 && g.lv[l].img_off % 16 == 0 && g.lv[l].tw <= KF_MAX_TW;
-        bands += g.lv[l].th;
+        const int bpc = kf_bands_per_cta(g.lv[l]);
+        bands += (g.lv[l].th + bpc - 1) / bpc;
     }
     VS_LAUNCH_BEGIN(ctx, VSK_KEYFRAME);
     if (banded) {
