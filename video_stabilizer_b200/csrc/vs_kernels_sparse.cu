@@ -220,9 +220,9 @@ k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t
     __syncthreads();
 
     for (int x0 = ttid * 16; x0 < wtiles; x0 += team_size * 16) {
-        uint32_t mx[16], my[16];
+        uint32_t mx[8], my[8];          // running column maxima, two 16-bit keys per register (VIMNMX.U16x2)
 #pragma unroll
-        for (int i = 0; i < 16; i++) { mx[i] = 0u; my[i] = 0u; }
+        for (int i = 0; i < 8; i++) { mx[i] = 0u; my[i] = 0u; }
         uint4 prev = kf_load_row(img, L.pitch, L.w, L.h, y0 - 1, x0);
         uint4 cur = kf_load_row(img, L.pitch, L.w, L.h, y0, x0);
 #pragma unroll 2
@@ -242,15 +242,11 @@ k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t
                 const uint32_t right = __funnelshift_r(wc, wr, 8);     // pixels x+1 .. x+4
                 const uint32_t gx4 = __vabsdiffu4(right, left);
                 const uint32_t gy4 = __vabsdiffu4(kf_word(next, k), kf_word(prev, k));
-                // key' = 2|g| << 8 | 255 - ry : bytes (crow, g_byte, 0, 0)
-                mx[4 * k + 0] = max(mx[4 * k + 0], __byte_perm(gx4, crow, 0x5504));
-                mx[4 * k + 1] = max(mx[4 * k + 1], __byte_perm(gx4, crow, 0x5514));
-                mx[4 * k + 2] = max(mx[4 * k + 2], __byte_perm(gx4, crow, 0x5524));
-                mx[4 * k + 3] = max(mx[4 * k + 3], __byte_perm(gx4, crow, 0x5534));
-                my[4 * k + 0] = max(my[4 * k + 0], __byte_perm(gy4, crow, 0x5504));
-                my[4 * k + 1] = max(my[4 * k + 1], __byte_perm(gy4, crow, 0x5514));
-                my[4 * k + 2] = max(my[4 * k + 2], __byte_perm(gy4, crow, 0x5524));
-                my[4 * k + 3] = max(my[4 * k + 3], __byte_perm(gy4, crow, 0x5534));
+                // key' = 2|g| << 8 | 255 - ry, 16 bits per pixel: bytes (crow, g_a, crow, g_b) hold two pixels
+                mx[2 * k + 0] = __vmaxu2(mx[2 * k + 0], __byte_perm(gx4, crow, 0x1404));
+                mx[2 * k + 1] = __vmaxu2(mx[2 * k + 1], __byte_perm(gx4, crow, 0x3424));
+                my[2 * k + 0] = __vmaxu2(my[2 * k + 0], __byte_perm(gy4, crow, 0x1404));
+                my[2 * k + 1] = __vmaxu2(my[2 * k + 1], __byte_perm(gy4, crow, 0x3424));
             }
             prev = cur; cur = next;
         }
@@ -261,8 +257,9 @@ k_keyframe_features(VsClipGeom g, const uint8_t* __restrict__ pyr, const int32_t
 #pragma unroll
         for (int i = 0; i < 16; i++) {
             if (x0 + i < wtiles) {
-                const uint32_t kx = ((mx[i] >> 8) << 16) | (uint32_t)(NN1 - (int)(255u - (mx[i] & 0xffu)) * N - rx);
-                const uint32_t ky = ((my[i] >> 8) << 16) | (uint32_t)(NN1 - (int)(255u - (my[i] & 0xffu)) * N - rx);
+                const uint32_t mxi = (mx[i >> 1] >> (16 * (i & 1))) & 0xffffu, myi = (my[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                const uint32_t kx = ((mxi >> 8) << 16) | (uint32_t)(NN1 - (int)(255u - (mxi & 0xffu)) * N - rx);
+                const uint32_t ky = ((myi >> 8) << 16) | (uint32_t)(NN1 - (int)(255u - (myi & 0xffu)) * N - rx);
                 bx = max(bx, kx); by = max(by, ky);
             }
             rx++;
