@@ -1230,17 +1230,15 @@ int vsk_bgr_warp_slots_tma(vs_ctx* ctx, const void* tensor_map, const VsDevImg& 
 // libvstab.so keeps linking against cudart only
 void* vs_tensor_map_encoder()
 {
-    static void* fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // a function-local static is initialised once even when several host threads (one VideoStabilizer each) arrive together
+    static void* const fn = []() -> void* {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = p;
-        else
-            cudaGetLastError();
-    }
+            return p;
+        cudaGetLastError();
+        return nullptr;
+    }();
     return fn;
 }
 
