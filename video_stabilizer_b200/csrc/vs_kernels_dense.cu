@@ -825,13 +825,12 @@ __device__ __forceinline__ void wg_weights(int sfx, int sfy, uint32_t& wt, uint3
 {
     const uint32_t gx = (uint32_t)sfx & 0x3e0u;                        // 32 fx
     const uint32_t hp2 = gx * 131070u + 2048u;                         // 64 (32 - fx) | 64 fx << 16
-    const uint32_t nhp2 = gx * (0u - 131070u) - 2048u;                 // -hp2 and 32 hp2 as multiply-adds of their own, so that
-    const uint32_t hp64 = gx * (131070u * 32u) + 65536u;               // wt = 32 hp2 - fy hp2 needs no subtraction on the logic pipe
-    uint32_t t, fy;
+    const uint32_t hp64 = gx * (131070u * 32u) + 65536u;               // 32 hp2 as a multiply-add of its own: wt = 32 hp2 - fy hp2
+    uint32_t t, fy;                                                    // then is one subtraction, not (32 - fy) on the logic pipe + a multiply
     asm("shl.b32 %0, %1, 22;" : "=r"(t) : "r"(sfy));                  // two shifts, not shift + mask: the left one can be a multiply
     asm("shr.u32 %0, %1, 27;" : "=r"(fy) : "r"(t));
     wb = fy * hp2;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(wt) : "r"(fy), "r"(nhp2), "r"(hp64));
+    wt = hp64 - wb;
 }
 
 __device__ __forceinline__ void wg_blend(uint32_t wt, uint32_t wb, uint32_t tx, uint32_t ty, uint32_t bx, uint32_t by,
@@ -963,7 +962,9 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
                 o[1] = wg_pack(g1, r1, b2, g2);
                 o[2] = wg_pack(r2, b3, g3, r3);
             } else {
+                // (the held taps are dead: defining them here lets the register moves of the merge land on this rare path)
                 pbyte = 0xffffffffu;
+                px0 = px1 = px2 = px3 = py0 = py1 = py2 = py3 = 0u;
                 if (4 * lane < tw) LIST[atomicAdd(&sCount, 1)] = (uint16_t)(r * 32 + lane);
             }
         }
