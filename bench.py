@@ -262,6 +262,8 @@ def run_gpu_arm(args):
     stream = torch.cuda.Stream()
     assert stream.cuda_stream != 0
     cs.set_stream(stream.cuda_stream)
+    SOLVER_LANES = int(os.environ.get("VSTAB_LANES", "3"))
+    cs.set_solver_lanes(SOLVER_LANES)
     lib = capi.load()
     n_out = F - p.lag
     out_dev = torch.empty((n_out, cs.out_h, cs.out_w, 3), dtype=torch.uint8, device="cuda")
@@ -315,10 +317,13 @@ def run_gpu_arm(args):
     clocks = sampler.stop(t0, t1) if sampler else None
     meas, ok, corr = cs.last_records(F)
 
-    # ---- per-kernel CUDA-event times over a second timed region of the same steps
+    # ---- per-kernel CUDA-event times over a second timed region of the same steps, with the stages back to back on one
+    #      stream (one solver lane): with the lanes of the timed run a kernel's events also span the kernels beside it
+    cs.set_solver_lanes(1)
     lib.vs_ctx_profile_enable(cs.ctx_handle, 1)
     lib.vs_ctx_profile_reset(cs.ctx_handle)
     prof_ms, _, _ = timed(step_resident, args.steps, 1)
+    cs.set_solver_lanes(SOLVER_LANES)
     kernels = {}
     for k in range(capi.VS_KERNEL_COUNT):
         n, tot = C.c_int64(), C.c_double()
@@ -395,7 +400,10 @@ def run_gpu_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/f32/f64", "data": "synthetic", "config": workload_config(args, F),
+        "dtype": "u8/f32/f64", "data": "synthetic",
+        "config": dict(workload_config(args, F), solver_lanes=SOLVER_LANES,
+                       kernel_times="`kernels` and `roofline` come from a second timed region with the stages back to back on one "
+                                    "stream (one solver lane); `value` runs the chunk as %d pieces whose solves overlap the other stages" % SOLVER_LANES),
         "e2e": {"value": world * F / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": F * frame_bytes,
                 "d2h_bytes_per_step": n_out * cs.out_frame_bytes + (F - 1) * 36, "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),

@@ -195,6 +195,14 @@ int vs_clip_build_keyframes(vs_clip*, const int32_t* slots, int n);
  * (may be NULL).  Outputs live in `mem`. */
 int vs_clip_align(vs_clip*, const vs_pair* pairs, int n,
                   double* out_transform, int32_t* out_status, int32_t* out_iters, int mem);
+#define VS_CLIP_SOLVER_LANES 4
+/* The same solve, enqueued on one of the clip's solver streams (lane 0 .. VS_CLIP_SOLVER_LANES-1) behind everything
+ * enqueued on the context stream so far, without waiting: the pyramids / keyframe features of the next frames and the warps of frames
+ * already decided then run beside it.  The pairs of one call use the per-pair scratch [base, base + n): calls in
+ * flight together must not overlap there (base + n <= max_pairs).  vs_clip_align_wait blocks until the call of that
+ * lane has finished and copies its transforms / status to host memory. */
+int vs_clip_align_async(vs_clip*, const vs_pair* pairs, int n, int base, int lane);
+int vs_clip_align_wait(vs_clip*, int lane, double* out_transform, int32_t* out_status);
 /* warpBySimilarityTransform (imgproc.cpp:446-484) + crop (stabilizer.cpp:102-109) for the
  * listed slots.  transforms: 4 doubles per frame (centre-based correction), host array.
  * out: (w-2crop)x(h-2crop) BGR frames, dense, out_frame_stride bytes apart, in `mem`. */

@@ -88,6 +88,9 @@ void  vsh_clipstab_destroy(void*);
 int   vsh_clipstab_reset(void*);
 /* sub-chunk (frames) of the host-to-host transfer/compute pipeline inside feed(); default 32 */
 int   vsh_clipstab_set_pipeline_frames(void*, int frames);
+/* pieces a device-resident chunk of >= 128 pairs is cut into, each solved on a stream of its own beside the other
+ * stages (1 = every stage back to back on one stream); default 3 */
+int   vsh_clipstab_set_solver_lanes(void*, int lanes);
 /* returns the number of stabilized frames written to out (>= 0) or -1 */
 int   vsh_clipstab_feed(void*, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, int mem,
                         uint8_t* out, int64_t out_frame_stride, int out_mem);

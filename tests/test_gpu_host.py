@@ -168,6 +168,33 @@ def test_clip_stabilizer_equals_frame_by_frame(host, ob, chunks):
         assert np.array_equal(again[0], got[0])
 
 
+@pytest.mark.parametrize("chunks", [(160,), (139, 150), (130, 129, 131), (300,)])
+def test_clip_stabilizer_solver_lanes_equal_frame_by_frame(host, chunks):
+    """Device-resident chunks of >= 128 pairs run as 2-4 pieces on the clip's solver lanes (the solve of one piece
+    beside the pyramids / warps of the others): the frames must still be those of n processFrame() calls, bit for bit,
+    whatever the parity of the chunk's first frame."""
+    import torch
+    from video_stabilizer_b200 import _capi as capi
+    w, h, n = 320, 180, sum(chunks)
+    frames = _clip(w, h, n, 5, step=2.0)
+    p = host.stab_params_default()
+    seq = host.VideoStabilizer(p, 0)
+    want = [f for f in (seq.processFrame(f) for f in frames) if f is not None]
+    cs = host.ClipStabilizer(w, h, max(chunks), p, 0)
+    got = []
+    pos = 0
+    for c in chunks:
+        part = np.ascontiguousarray(frames[pos:pos + c])
+        out = torch.empty((c, cs.out_h, cs.out_w, 3), dtype=torch.uint8, device="cuda")
+        k = cs.feed_ptr(part.ctypes.data, c, part.strides[1], part.strides[0], capi.VS_MEM_HOST, out.data_ptr(), capi.VS_MEM_DEVICE)
+        cs.synchronize()
+        got.extend(list(out[:k].cpu().numpy()))
+        pos += c
+    assert len(got) == len(want) == n - p.lag
+    for i, (g, s) in enumerate(zip(got, want)):
+        assert np.array_equal(g, s), i
+
+
 def test_clip_stabilizer_records(host, ob):
     w, h, n = 320, 180, 16
     frames = _clip(w, h, n, 3)

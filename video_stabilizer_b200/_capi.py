@@ -80,6 +80,8 @@ SYMBOLS = {
     "vs_clip_build_pyramids": (C.c_int, [_P, C.c_int, C.c_int]),
     "vs_clip_build_keyframes": (C.c_int, [_P, _P, C.c_int]),
     "vs_clip_align": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int]),
+    "vs_clip_align_async": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
+    "vs_clip_align_wait": (C.c_int, [_P, C.c_int, _P, _P]),
     "vs_clip_warp": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64, C.c_int]),
     "vs_clip_upload_async": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64, C.c_int64]),
     "vs_clip_wait_uploads": (C.c_int, [_P]),

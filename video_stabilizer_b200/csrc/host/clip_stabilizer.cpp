@@ -2,6 +2,7 @@
 #include "clip_stabilizer.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -27,6 +28,7 @@ ClipStabilizer::ClipStabilizer(int device, int width, int height, int chunk_fram
         throw std::runtime_error(msg);
     }
     m_pairs.reserve(chunk_frames); m_T.resize((size_t)chunk_frames * 4); m_status.resize(chunk_frames); m_slots.reserve(chunk_frames);
+    if (const char* e = getenv("VSTAB_LANES")) m_lanes = std::max(1, atoi(e));   // A/B measurements
 }
 
 ClipStabilizer::~ClipStabilizer()
@@ -117,14 +119,7 @@ int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int o
     if (n == 0) return 0;
     const long f0 = m_fed;
 
-    // ---- pyramids of the new frames, keyframe features of the odd ones
-    for_slot_runs(f0, n, [&](int slot, int, int run) { check(vs_clip_build_pyramids(m_clip, slot, run), "pyramids"); });
-    m_slots.clear();
-    for (long f = f0; f < f0 + n; f++)
-        if (f & 1) m_slots.push_back((int32_t)(f % m_capacity));
-    if (!m_slots.empty()) check(vs_clip_build_keyframes(m_clip, m_slots.data(), (int)m_slots.size()), "keyframes");
-
-    // ---- one solver launch over every pair (f-1 -> f); roles as reference alignment.cpp:357,396-397,690-693
+    // ---- every pair (f-1 -> f); roles as reference alignment.cpp:357,396-397,690-693
     m_pairs.clear();
     for (long f = std::max(f0, 1L); f < f0 + n; f++) {
         vs_pair p;
@@ -134,13 +129,45 @@ int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int o
         m_pairs.push_back(p);
     }
     const int np = (int)m_pairs.size();
-    if (np) check(vs_clip_align(m_clip, m_pairs.data(), np, m_T.data(), m_status.data(), nullptr, VS_MEM_HOST), "align");
+    const long first_pair = std::max(f0, 1L);
+
+    // pyramids of frames [a, b), keyframe features of the odd ones
+    auto ingest = [&](long a, long b) {
+        if (b <= a) return;
+        for_slot_runs(a, (int)(b - a), [&](int slot, int, int run) { check(vs_clip_build_pyramids(m_clip, slot, run), "pyramids"); });
+        m_slots.clear();
+        for (long f = a; f < b; f++)
+            if (f & 1) m_slots.push_back((int32_t)(f % m_capacity));
+        if (!m_slots.empty()) check(vs_clip_build_keyframes(m_clip, m_slots.data(), (int)m_slots.size()), "keyframes");
+    };
+
+    // Large device-resident chunks run as up to four pieces on the clip's solver lanes.  A solve lasts as long as its
+    // slowest pair (~0.9 ms) however many pairs it has and is bound by gather latency; the other stages are bound by
+    // bandwidth.  So the solve of a piece runs beside the pyramids / keyframe features of the next pieces and beside the
+    // warps of the previous ones, and the chunk takes about ingest + one solve + the last piece's warps.
+    const bool overlap = async_to_host || out_mem == VS_MEM_DEVICE;
+    int lanes = 1;
+    if (m_lanes > 1 && overlap && !async_to_host && np >= 128) lanes = std::min({m_lanes, VS_CLIP_SOLVER_LANES, np / 64});
+    int lane_first[VS_CLIP_SOLVER_LANES + 1] = {0};   // first pair of each piece; piece l = pairs [lane_first[l], lane_first[l+1])
+    if (lanes > 1) {
+        long a = f0;
+        for (int l = 0; l < lanes; l++) {
+            const long b = l + 1 == lanes ? f0 + n : (f0 + (long)n * (l + 1) / lanes) & ~1L;   // pieces end on even frames
+            lane_first[l + 1] = (int)(std::max(b, first_pair) - first_pair);
+            ingest(a, b);
+            check(vs_clip_align_async(m_clip, m_pairs.data() + lane_first[l], lane_first[l + 1] - lane_first[l], lane_first[l], l), "align");
+            a = b;
+        }
+    } else {
+        ingest(f0, f0 + n);
+        if (np) check(vs_clip_align(m_clip, m_pairs.data(), np, m_T.data(), m_status.data(), nullptr, VS_MEM_HOST), "align");
+    }
+    int lane_waited = 0;              // pieces whose results are on the host
 
     // ---- sequential host trajectory, with the warps of the frames already decided launched in
     //      batches while the host is still smoothing the later ones (asynchronous outputs only)
     std::vector<int32_t> due_slots;
     std::vector<double> due_T;
-    const bool overlap = async_to_host || out_mem == VS_MEM_DEVICE;
     const size_t out_frame_bytes = (size_t)out_width() * out_height() * 3;
     (void)out_frame_bytes;
     int launched = 0;
@@ -164,6 +191,11 @@ int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int o
         bool ok = false;
         if (i >= first_pair_frame) {
             const int p = i - first_pair_frame;
+            while (lanes > 1 && lane_waited < lanes && p >= lane_first[lane_waited]) {
+                check(vs_clip_align_wait(m_clip, lane_waited, m_T.data() + 4 * (size_t)lane_first[lane_waited],
+                                         m_status.data() + lane_first[lane_waited]), "align");
+                lane_waited++;
+            }
             meas.A = m_T[4 * p]; meas.B = m_T[4 * p + 1]; meas.TX = m_T[4 * p + 2]; meas.TY = m_T[4 * p + 3];
             ok = m_status[p] != 0;
         }

@@ -46,6 +46,9 @@ public:
              uint8_t* out, int64_t out_frame_stride, int out_mem);
     int pipeline_frames() const { return m_sub; }
     void set_pipeline_frames(int frames) { m_sub = frames < 1 ? 1 : frames; }
+    // pieces a device-resident chunk of >= 128 pairs is cut into (one solver stream each); 1 = all stages back to back
+    int solver_lanes() const { return m_lanes; }
+    void set_solver_lanes(int lanes) { m_lanes = lanes < 1 ? 1 : lanes; }
 
     // Same, for frames that are already in the ring: slots are assigned in feed order,
     // frame f of the video lives in slot f % ring_capacity(); upload_only() places frames
@@ -68,6 +71,7 @@ public:
 
 private:
     int m_w, m_h, m_chunk, m_capacity, m_crop;
+    int m_lanes = 3;       // device-resident chunks of >= 128 pairs: up to this many pieces on the clip's solver lanes
     int m_sub = 32;        // sub-chunk of the host-to-host pipeline
     int m_warp_batch = 96; // largest batch of due frames per warp launch while the host trajectory is still running (16, 32, 64, 96, 96 ...)
     VideoStabilizerParams m_params;

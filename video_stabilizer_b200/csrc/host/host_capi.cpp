@@ -269,6 +269,7 @@ void* vsh_clipstab_create(int device, int width, int height, int chunk_frames, c
 void vsh_clipstab_destroy(void* c) { delete (vstab::ClipStabilizer*)c; }
 int vsh_clipstab_reset(void* c) { return guarded([&] { ((vstab::ClipStabilizer*)c)->reset(); return 0; }); }
 int vsh_clipstab_set_pipeline_frames(void* c, int frames) { ((vstab::ClipStabilizer*)c)->set_pipeline_frames(frames); return 0; }
+int vsh_clipstab_set_solver_lanes(void* c, int lanes) { ((vstab::ClipStabilizer*)c)->set_solver_lanes(lanes); return 0; }
 int vsh_clipstab_feed(void* c, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, int mem,
                       uint8_t* out, int64_t out_frame_stride, int out_mem)
 {

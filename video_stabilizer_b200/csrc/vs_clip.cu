@@ -58,6 +58,13 @@ struct vs_clip {
     int32_t* d_slot_ring = nullptr;     // kOutRing * capacity
     int out_ring_next = 0;
     int last_pairs = 0;
+    // asynchronous solver lanes (vs_clip_align_async / vs_clip_align_wait)
+    static const int kLanes = VS_CLIP_SOLVER_LANES;
+    cudaStream_t solve_stream[kLanes] = {};
+    cudaEvent_t ev_ready[kLanes] = {}, ev_solved[kLanes] = {};
+    double* h_T = nullptr;            // pinned, max_pairs * 4
+    int32_t* h_status = nullptr;      // pinned, max_pairs
+    int lane_base[kLanes] = {}, lane_n[kLanes] = {};
 };
 
 namespace {
@@ -91,6 +98,13 @@ void free_all(vs_clip* c)
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
     cudaFree(c->d_pos_scratch); cudaFree(c->d_res_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
     cudaFree(c->d_warp_tab);
+    for (int l = 0; l < vs_clip::kLanes; l++) {
+        if (c->solve_stream[l]) { cudaStreamSynchronize(c->solve_stream[l]); cudaStreamDestroy(c->solve_stream[l]); }
+        if (c->ev_ready[l]) cudaEventDestroy(c->ev_ready[l]);
+        if (c->ev_solved[l]) cudaEventDestroy(c->ev_solved[l]);
+    }
+    if (c->h_T) cudaFreeHost(c->h_T);
+    if (c->h_status) cudaFreeHost(c->h_status);
 }
 
 PFN_cuTensorMapEncodeTiled tensor_map_encoder()
@@ -344,6 +358,7 @@ int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_
     a.dbg_warpdiff = c->d_dbg_wd; a.dbg_order = c->d_dbg_order; a.dbg_count = c->d_dbg_count;
     a.pos_scratch = c->d_pos_scratch;
     a.res_scratch = c->d_res_scratch;
+    a.force_threads = 0;
     a.dbg_clock = c->d_dbg_clock;
     if (c->d_dbg_count)   // -1 marks levels a pair never reached
         VS_CUDA(ctx, cudaMemsetAsync(c->d_dbg_count, 0xFF, (size_t)c->max_pairs * 2 * c->g.levels * sizeof(int32_t), ctx->stream));
@@ -356,6 +371,72 @@ int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_
             VS_CUDA(ctx, cudaMemcpyAsync(out_iters, c->d_iters, (size_t)n * c->g.levels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return VS_OK;
+}
+
+int vs_clip_align_async(vs_clip* c, const vs_pair* pairs, int n, int base, int lane)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, lane >= 0 && lane < vs_clip::kLanes, "clip_align_async: lane out of range");
+    VS_REQUIRE(ctx, n >= 0 && base >= 0 && base + n <= c->max_pairs, "clip_align_async: pair range exceeds max_pairs");
+    c->lane_base[lane] = base; c->lane_n[lane] = n;
+    if (n == 0) return VS_OK;
+    VS_REQUIRE(ctx, pairs, "clip_align_async: NULL pointer");
+    for (int i = 0; i < n; i++)
+        VS_REQUIRE(ctx, pairs[i].template_slot >= 0 && pairs[i].template_slot < c->capacity &&
+                        pairs[i].keyframe_slot >= 0 && pairs[i].keyframe_slot < c->capacity, "clip_align_async: slot out of range");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!c->solve_stream[lane]) {
+        VS_CUDA(ctx, cudaStreamCreateWithFlags(&c->solve_stream[lane], cudaStreamNonBlocking));
+        VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_ready[lane], cudaEventDisableTiming));
+        VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_solved[lane], cudaEventDisableTiming));
+    }
+    if (!c->h_T) {
+        VS_CUDA(ctx, cudaMallocHost((void**)&c->h_T, (size_t)c->max_pairs * 4 * sizeof(double)));
+        VS_CUDA(ctx, cudaMallocHost((void**)&c->h_status, (size_t)c->max_pairs * sizeof(int32_t)));
+    }
+    cudaStream_t s = c->solve_stream[lane];
+    // the solve follows everything enqueued on the context stream so far (pyramids, keyframe features, the pair list)
+    VS_CUDA(ctx, cudaMemcpyAsync(c->d_pairs + base, pairs, (size_t)n * sizeof(vs_pair), cudaMemcpyHostToDevice, ctx->stream));
+    VS_CUDA(ctx, cudaEventRecord(c->ev_ready[lane], ctx->stream));
+    VS_CUDA(ctx, cudaStreamWaitEvent(s, c->ev_ready[lane], 0));
+    VsSolveArgs a;
+    a.pyr = c->d_pyr; a.kp = c->d_kp; a.jac = c->d_jac; a.pairs = c->d_pairs + base; a.n_pairs = n;
+    a.threshold = c->params.threshold; a.fraction = c->params.smallest_fraction;
+    a.max_iters = c->params.max_iters; a.max_displacement = c->params.max_displacement;
+    a.out_T = c->d_T + (size_t)base * 4;
+    a.out_status = c->d_status + base;
+    a.out_iters = nullptr;
+    a.dbg_warpdiff = nullptr; a.dbg_order = nullptr; a.dbg_count = nullptr; a.dbg_clock = nullptr;
+    a.pos_scratch = c->d_pos_scratch ? c->d_pos_scratch + (size_t)base * 4 * c->g.max_tiles : nullptr;
+    a.res_scratch = c->d_res_scratch ? c->d_res_scratch + (size_t)base * 2 * c->g.max_tiles : nullptr;
+    a.force_threads = 256;            // all lanes must fit on the GPU together: three CTAs per SM
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = s;
+    int r = vsk_solve_pairs(ctx, c->g, a);
+    ctx->stream = main_stream;
+    VS_TRY(r);
+    VS_CUDA(ctx, cudaMemcpyAsync(c->h_T + (size_t)base * 4, c->d_T + (size_t)base * 4, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    VS_CUDA(ctx, cudaMemcpyAsync(c->h_status + base, c->d_status + base, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    VS_CUDA(ctx, cudaEventRecord(c->ev_solved[lane], s));
+    c->last_pairs = base + n;
+    return VS_OK;
+}
+
+int vs_clip_align_wait(vs_clip* c, int lane, double* out_T, int32_t* out_status)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, lane >= 0 && lane < vs_clip::kLanes, "clip_align_wait: lane out of range");
+    const int n = c->lane_n[lane], base = c->lane_base[lane];
+    if (n == 0) return VS_OK;
+    VS_REQUIRE(ctx, out_T && out_status && c->ev_solved[lane], "clip_align_wait: nothing in flight on this lane / NULL pointer");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaEventSynchronize(c->ev_solved[lane]));
+    memcpy(out_T, c->h_T + (size_t)base * 4, (size_t)n * 4 * sizeof(double));
+    memcpy(out_status, c->h_status + base, (size_t)n * sizeof(int32_t));
+    c->lane_n[lane] = 0;
     return VS_OK;
 }
 

@@ -84,6 +84,7 @@ static void prof_resolve(vs_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto& s : p->pending) {
         float ms = 0;
+        cudaEventSynchronize(s.b);      // launches on another stream of the owner (the clip's solver lanes)
         if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { p->ms[s.id] += ms; p->n[s.id]++; }
         p->pool.push_back(s.a); p->pool.push_back(s.b);
     }

@@ -109,6 +109,7 @@ struct VsSolveArgs {
     long long* dbg_clock;     // [pair][8] cycles per phase (debug taps only), or null
     uint16_t* pos_scratch;    // [pair][4][max_tiles] selection scratch in global memory, or null (shared memory)
     float* res_scratch;       // [pair][2][max_tiles] signed residual of every tile from the warp-diff pass, or null
+    int force_threads;        // 0 = CTA size by pair count; 256 when several launches must be resident together
 };
 
 int vsk_keyframe_features(vs_ctx*, const VsClipGeom& g, const uint8_t* d_pyr, const int32_t* d_slots,

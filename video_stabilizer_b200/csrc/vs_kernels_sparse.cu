@@ -994,6 +994,7 @@ int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
         k_solve_pairs<NT, PF, MINB><<<a.n_pairs, NT, smem, ctx->stream>>>(g, args);                                               \
     } while (0)
     int threads = a.n_pairs <= ctx->sm_count ? 512 : 256;
+    if (a.force_threads == 256 || a.force_threads == 512) threads = a.force_threads;
     if (force == 256 || force == 512 || force == 1024) threads = force;
     if (prefetch) VS_SOLVE_LAUNCH(256, 1, 3);
     else if (threads == 1024) VS_SOLVE_LAUNCH(1024, 0, 1);

@@ -62,6 +62,7 @@ SYMBOLS = {
     "vsh_clipstab_destroy": (None, [_P]),
     "vsh_clipstab_reset": (_I, [_P]),
     "vsh_clipstab_set_pipeline_frames": (_I, [_P, _I]),
+    "vsh_clipstab_set_solver_lanes": (_I, [_P, _I]),
     "vsh_clipstab_feed": (_I, [_P, _P, _I, _I64, _I64, _I, _P, _I64, _I]),
     "vsh_clipstab_upload_only": (_I, [_P, _I64, _P, _I, _I64, _I64, _I]),
     "vsh_clipstab_feed_resident": (_I, [_P, _I, _P, _I64, _I]),
@@ -347,6 +348,9 @@ class ClipStabilizer(_Handle):
 
     def set_pipeline_frames(self, frames: int):
         load().vsh_clipstab_set_pipeline_frames(self.h, int(frames))
+
+    def set_solver_lanes(self, lanes: int):
+        load().vsh_clipstab_set_solver_lanes(self.h, int(lanes))
 
     def feed(self, frames: np.ndarray) -> np.ndarray:
         """frames: (n,h,w,3) u8 host array; returns the (k,oh,ow,3) stabilized frames that became due."""
