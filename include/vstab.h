@@ -234,7 +234,8 @@ int vs_clip_get_jacobians(vs_clip*, int slot, int level, int axis, float* out /*
 int vs_clip_get_warpdiff(vs_clip*, int pair, int level, int axis, uint16_t* out /* (tw,th) */);
 int vs_clip_get_selected(vs_clip*, int pair, int level, int axis, uint32_t* out_order, int* out_k);
 /* SM cycles pair `pair` of the last vs_clip_align spent per phase, summed over levels:
- * {warp-diff, selection, Hessian + SVD, Gauss-Newton gathers, Gauss-Newton reduce + update, 0} */
+ * {warp-diff, selection, Hessian sums, SVD beside the first iteration + Gauss-Newton gathers, Gauss-Newton reduce + update,
+ *  number of parallel partition rounds of the selection (a count, not cycles)} */
 int vs_clip_get_solver_cycles(vs_clip*, int pair, long long* out6);
 /* Debug tap for the solver's 4x4 conditioning + SVD pseudo-inverse (alignment.cpp:554-583) as it runs on the device:
  * n row-major 4x4 f64 matrices from host memory -> the inverse computed by the lane-parallel form the solver uses

@@ -25,9 +25,12 @@ for _ in range(2):
 cyc = np.zeros((n - 1, 6), np.int64)
 for p in range(n - 1):
     capi.check(ctx.handle, ctx.lib.vs_clip_get_solver_cycles(clip.handle, p, capi.ptr(cyc[p:p + 1])), "cycles")
+rounds = cyc[:, 5].copy()       # slot 5 counts the partition rounds of the selection (both axes share a round)
+cyc[:, 5] = 0
 tot = cyc.sum(1)
 names = ["warpdiff", "select", "hessian sums", "svd || first gather, gn gathers", "gn reduce+update", "-"]
 print("pairs %d, converged %d, mean iterations per level %s" % (n - 1, st.sum(), np.round(it.mean(0), 2)))
 print("mean cycles per pair %.0f (max %.0f) = %.3f ms at 1.965 GHz" % (tot.mean(), tot.max(), tot.mean() / 1.965e6))
+print("selection: %.1f parallel partition rounds per pair (all levels), %.0f cycles per round" % (rounds.mean(), cyc[:, 1].sum() / max(rounds.sum(), 1)))
 for i, nm in enumerate(names[:5]):
     print("  %-32s %9.0f cycles  %5.1f%%" % (nm, cyc[:, i].mean(), 100 * cyc[:, i].sum() / tot.sum()))

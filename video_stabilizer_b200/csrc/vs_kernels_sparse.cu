@@ -349,12 +349,13 @@ constexpr int SOLVE_MAX_WARPS = 32;
 constexpr int SOLVE_WARPS = SOLVE_MAX_WARPS;   // array extents only
 enum { FLAG_CONTINUE = 0, FLAG_CONVERGED = 1, FLAG_FAIL = 2 };
 
+// (sized by the CTA's own warp count: every KB of shared memory is a KB of L1 taken from the gathers)
+template <int NWARPS>
 struct SolveShared {
     double T[4];
-    double H[16];
     double Hinv[16];
-    double red[SOLVE_WARPS][12];      // Hessian partial sums
-    double red4[SOLVE_WARPS][4];      // Gauss-Newton partial sums (a buffer of their own: thread 0 may still be busy after the Hessian reduce)
+    double red[NWARPS][12];           // Hessian partial sums; its first 16 doubles then carry H to the lanes of warp 0
+    double red4[NWARPS][4];           // Gauss-Newton partial sums (a buffer of their own: thread 0 may still be busy after the Hessian reduce)
     double c0[4][2], c1[4][2];
     int flag;
     int status;
@@ -385,10 +386,11 @@ struct SelAxis {
     int cutL, cutR;     // posL[m] and posR[m-1] of the current round (see the swap phase)
 };
 
+template <int NWARPS>
 struct SelShared {
     SelAxis ax[2];
-    uint32_t warp_tot[2][SOLVE_WARPS];
-    int warp_cnt[2][SOLVE_WARPS];
+    uint32_t warp_tot[2][NWARPS];
+    int warp_cnt[2][NWARPS];
 };
 
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v)
@@ -405,7 +407,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v)
 // keys[a]: n packed keys of axis a; pos[a]: 2*n u16 (posL then posR).  nth < n.
 template <int SOLVE_THREADS>
 __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1, uint16_t* const pos0, uint16_t* const pos1,
-                                   const int n, const int nth, SelShared& ss)
+                                   const int n, const int nth, SelShared<SOLVE_THREADS / 32>& ss, long long* rounds = nullptr)
 {
     constexpr int NWARPS = SOLVE_THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -436,6 +438,7 @@ __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1,
         __syncthreads();
         const bool act0 = !ss.ax[0].done, act1 = !ss.ax[1].done;
         if (!act0 && !act1) break;
+        if (rounds) ++*rounds;
 
         // ---- count the candidates of this thread's slice, both axes
         int c0[2], c1[2];
@@ -575,8 +578,8 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 {
     constexpr int NWARPS = SOLVE_THREADS / 32;
     extern __shared__ uint32_t dyn_keys[];   // keys[2][max_tiles]: abs_delta << 16 | tile, then (optionally) pos[2][2*max_tiles] u16
-    __shared__ SolveShared sh;
-    __shared__ SelShared sel;
+    __shared__ SolveShared<SOLVE_THREADS / 32> sh;
+    __shared__ SelShared<SOLVE_THREADS / 32> sel;
     const int tid = threadIdx.x;
     const int pair = blockIdx.x;
     if (pair >= a.n_pairs) return;
@@ -660,7 +663,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 
         VS_CLK(0);
         // ---- keep the k smallest: exact replay of std::nth_element (alignment.cpp:460-486)
-        block_nth_element2<SOLVE_THREADS>(keys0, keys1, pos0, pos1, nt, k, sel);
+        block_nth_element2<SOLVE_THREADS>(keys0, keys1, pos0, pos1, nt, k, sel, a.dbg_clock ? &clk[5] : nullptr);
         __syncthreads();
         VS_CLK(1);
 
@@ -699,8 +702,9 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
             // vs_condition_and_invert).  Meanwhile warps 1.. run the first Gauss-Newton iteration, which needs only the
             // incoming transform and the selected keypoints.
             if (tid < 32) {
+                double* const H = &sh.red[0][0];              // the partial sums are dead once thread 0 holds the totals
+                static_assert(NWARPS * 12 >= 16, "H aliases the Hessian partial sums");
                 if (tid == 0) {
-                    double* H = sh.H;
                     H[0] = tot[0]; H[1] = tot[1]; H[2] = tot[3]; H[3] = tot[6];
                     H[4] = tot[1]; H[5] = tot[2]; H[6] = tot[4]; H[7] = tot[7];
                     H[8] = tot[3]; H[9] = tot[4]; H[10] = tot[5]; H[11] = 0.0;
@@ -709,7 +713,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
                 __syncwarp();
                 double hrow[4], hinv[4];
 #pragma unroll
-                for (int c = 0; c < 4; c++) hrow[c] = sh.H[(tid & 3) * 4 + c];
+                for (int c = 0; c < 4; c++) hrow[c] = H[(tid & 3) * 4 + c];
                 vs_condition_and_invert_quad(hrow, hinv);
                 if (tid < 4) {
 #pragma unroll
@@ -972,6 +976,9 @@ int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
     VS_REQUIRE(ctx, key_bytes <= 200 * 1024, "solve: level too large for the shared-memory selection");
     size_t smem = key_bytes;
     VsSolveArgs args = a;
+    // (Measured: keeping the lists of the shorter rounds in a shared-memory part next to the keys makes a round cheaper,
+    // 9.5k -> 8.3k cycles, but every KB of shared memory is a KB of L1 taken from the gathers, which lose more: mean
+    // 0.67 -> 0.97 ms per pair at 68 KB per CTA.  The keys stay alone in shared memory unless everything fits.)
     if (key_bytes + pos_bytes <= 72 * 1024 || !a.pos_scratch) {
         VS_REQUIRE(ctx, key_bytes + pos_bytes <= 220 * 1024, "solve: level too large and no selection scratch given");
         smem += pos_bytes;
@@ -987,9 +994,21 @@ int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
     // the big shared-memory footprints of 4K where only one CTA fits anyway.
     static const int prefetch = getenv("VSTAB_SOLVE_PREFETCH") ? atoi(getenv("VSTAB_SOLVE_PREFETCH")) : 0;
     static const int force = getenv("VSTAB_SOLVE_THREADS") ? atoi(getenv("VSTAB_SOLVE_THREADS")) : 0;
+    // shared-memory carve-out: just enough for the CTAs that must be resident (the rest of the 256 KB is L1 for the gathers)
+    // (B200, 1080p, 299 pairs: 0.857 ms with the minimal carve-out, 0.88 with the driver's default, 0.95 at 72 %, 1.43 at 86 %;
+    // VSTAB_SOLVE_CARVEOUT = percentage, -1 = minimal (default), -2 = leave it to the driver)
+    static const int carve_env = getenv("VSTAB_SOLVE_CARVEOUT") ? atoi(getenv("VSTAB_SOLVE_CARVEOUT")) : -1;
 #define VS_SOLVE_LAUNCH(NT, PF, MINB)                                                                                             \
     do {                                                                                                                          \
         VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<NT, PF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        if (carve_env != -2) {                                                                                                    \
+            cudaFuncAttributes fa;                                                                                                \
+            VS_CUDA(ctx, cudaFuncGetAttributes(&fa, k_solve_pairs<NT, PF, MINB>));                                                \
+            const size_t need = (size_t)MINB * (smem + fa.sharedSizeBytes + 1024);                                                \
+            const int pct = carve_env >= 0 ? carve_env : (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));                     \
+            VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<NT, PF, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,         \
+                                              pct > 100 ? 100 : pct));                                                            \
+        }                                                                                                                         \
         VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);                                                                                          \
         k_solve_pairs<NT, PF, MINB><<<a.n_pairs, NT, smem, ctx->stream>>>(g, args);                                               \
     } while (0)
