@@ -8,6 +8,7 @@
 //   jac      [capacity][2 axes][total_tiles] float4       Jacobian per keypoint (reference channel order)
 //   pairs / out_T / out_status / out_iters               per vs_clip_align call, max_pairs entries
 //   dbg_*    optional (VS_CLIP_DEBUG_TAPS)               warpdiff and selection order per pair
+//   pos_scratch / res_scratch / warp_tab                  per-pair selection lists and warp-diff residuals, per-launch warp tables
 #include "vs_internal.h"
 
 #include <cuda.h>
@@ -145,7 +146,8 @@ void build_bgr_tensor_map(vs_clip* c)
     c->bgr_map_rows_ok = (r == CUDA_SUCCESS);
 }
 
-// the BGR warp of a clip: TMA-staged kernel for the production mode, generic kernels otherwise
+// the BGR warp of a clip: row-group kernel for the mode the stabiliser uses (cv-exact, constant border); the earlier
+// TMA-staged kernel when the clip is too small for its box; generic kernels for the other modes / borders
 int clip_warp_launch(vs_clip* c, const int32_t* d_slots, const VsWarpCoef* d_coef, const VsDevImg& dst, int crop, int mode, int border, int n)
 {
     VsDevImg src{c->d_bgr, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};

@@ -377,7 +377,8 @@ k_bgr_warp(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src
 }
 
 // ------------------------------------------------------------------ BGR warp, cv-exact, tiled
-// The production form of mode 0 (the warp VideoStabilizer runs on every output frame).
+// Mode 0 (the warp VideoStabilizer runs on every output frame), first tiled generation; k_bgr_warp_cv_rows below is
+// the form used whenever the source can be described by a tensor map.
 // A CTA of 128 threads produces a 120 x 16 pixel output tile (120 px = 360 B = 45 8-byte
 // stores per row; 1920 and 3840 are multiples of 120; the source box of a tile is then at
 // most 32 four-pixel granules wide, one per lane):
