@@ -96,8 +96,19 @@ int MultiGpuStabilizer::stabilize(const uint8_t* frames, int n, int64_t row_stri
         up_first[r] = up0;
         const int cnt = last - up0;
         if (cnt > wk.capacity) throw std::runtime_error("MultiGpuStabilizer: chunk larger than the worker's ring");
-        check(wk, vs_clip_upload(wk.clip, 0, cnt, frames + (size_t)frame_stride * up0, row_stride, frame_stride, VS_MEM_HOST), "upload");
-        check(wk, vs_clip_build_pyramids(wk.clip, 0, cnt), "pyramids");
+        // asynchronous copies on the clip's copy-in stream (PCIe rate when the caller's frames are pinned); the pyramids of
+        // a sub-chunk are built while the next one is still arriving
+        const int sub = 32;
+        auto upload = [&](int s0) {
+            check(wk, vs_clip_upload_async(wk.clip, s0, std::min(sub, cnt - s0), frames + (size_t)frame_stride * (up0 + s0),
+                                           row_stride, frame_stride), "upload");
+        };
+        upload(0);
+        for (int s0 = 0; s0 < cnt; s0 += sub) {
+            check(wk, vs_clip_wait_uploads(wk.clip), "wait for uploads");     // covers sub-chunk s0: the next one is not issued yet
+            if (s0 + sub < cnt) upload(s0 + sub);
+            check(wk, vs_clip_build_pyramids(wk.clip, s0, std::min(sub, cnt - s0)), "pyramids");
+        }
         std::vector<int32_t> keys;
         std::vector<vs_pair> pairs;
         for (int f = std::max(first, 1); f < last; f++) {
@@ -142,8 +153,15 @@ int MultiGpuStabilizer::stabilize(const uint8_t* frames, int n, int64_t row_stri
             slots.push_back(f - up_first[r]);
             T.insert(T.end(), {corr[f].A, corr[f].B, corr[f].TX, corr[f].TY});
         }
-        check(wk, vs_clip_warp(wk.clip, slots.data(), (int)slots.size(), T.data(), VS_WARP_CV_EXACT_BILINEAR, VS_BORDER_CONSTANT0,
-                               m_crop, out + (size_t)out_frame_stride * first, out_frame_stride, VS_MEM_HOST), "warp");
+        // warps in batches, each batch's frames copied out on the copy-out stream while the next batch is warped
+        const int batch = 32, cnt = (int)slots.size();
+        for (int b0 = 0; b0 < cnt; b0 += batch) {
+            const int bc = std::min(batch, cnt - b0);
+            check(wk, vs_clip_warp_to_host_async(wk.clip, slots.data() + b0, bc, T.data() + 4 * (size_t)b0, VS_WARP_CV_EXACT_BILINEAR,
+                                                 VS_BORDER_CONSTANT0, m_crop, out + (size_t)out_frame_stride * (first + b0),
+                                                 out_frame_stride), "warp");
+        }
+        check(wk, vs_clip_sync_transfers(wk.clip), "transfers");
     });
     return produced;
 }

@@ -410,11 +410,14 @@ class MultiGpuStabilizer(_Handle):
         crop = max(0, self.params.crop_pixels)
         self.out_w, self.out_h = width - 2 * crop, height - 2 * crop
 
-    def stabilize(self, frames: np.ndarray):
-        """frames (n,h,w,3) u8 -> (stabilized (n-lag,oh,ow,3), meas (n,4), ok (n,))."""
+    def stabilize(self, frames: np.ndarray, out: np.ndarray | None = None):
+        """frames (n,h,w,3) u8 -> (stabilized (n-lag,oh,ow,3), meas (n,4), ok (n,)).  The copies run at the PCIe rate
+        when `frames` and `out` (optional, (n,oh,ow,3) u8, C-contiguous) are pinned host memory."""
         frames = np.ascontiguousarray(frames, np.uint8)
         n = frames.shape[0]
-        out = np.empty((n, self.out_h, self.out_w, 3), np.uint8)
+        if out is None:
+            out = np.empty((n, self.out_h, self.out_w, 3), np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == (n, self.out_h, self.out_w, 3)
         meas, ok = np.zeros((n, 4)), np.zeros(n, np.uint8)
         k = load().vsh_multigpu_stabilize(self.h, _p(frames), n, frames.strides[1], frames.strides[0], _p(out),
                                           self.out_w * self.out_h * 3, _p(meas), _p(ok))
