@@ -63,6 +63,8 @@ def bench_warp(args):
     if args.mode is not None:
         modes = [m for m in modes if m[0] == args.mode]
     T = np.array([0.0013, -0.0021, 6.37, -3.81])
+    if args.transform:
+        T = np.array([float(v) for v in args.transform.split(",")])   # e.g. 0,0,0,0 (a camera standing still) or 0,0,5,-3
     for (w, h) in sizes:
         batch = max(1, int(np.ceil(512e6 / (6 * w * h))))
         pitch = (3 * w + 127) // 128 * 128
@@ -78,8 +80,9 @@ def bench_warp(args):
                                                           capi.VS_BORDER_CONSTANT0, capi.VS_MEM_DEVICE), "vs_bgr_warp_u8")
             ms = time_launches(torch, fn, args.iters)
             gbs = 6.0 * w * h * batch / (ms / 1e3) / 1e9
-            print(json.dumps({"kernel": "bgr_warp", "mode": name, "size": "%dx%d" % (w, h), "batch": batch, "ms_per_launch": ms,
-                              "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak(), "frames_per_s": batch / (ms / 1e3)}), flush=True)
+            print(json.dumps({"kernel": "bgr_warp", "mode": name, "size": "%dx%d" % (w, h), "batch": batch, "transform": T.tolist(),
+                              "ms_per_launch": ms, "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak(),
+                              "frames_per_s": batch / (ms / 1e3)}), flush=True)
         del src, dst
 
 
@@ -129,6 +132,7 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--size", default=None)
     ap.add_argument("--mode", type=int, default=None)
+    ap.add_argument("--transform", default=None, help="A,B,TX,TY of the similarity transform of the warp sweep")
     a = ap.parse_args()
     if a.what in ("warp", "all"):
         bench_warp(a)

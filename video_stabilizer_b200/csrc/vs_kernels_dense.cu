@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 namespace {
 
@@ -814,7 +815,9 @@ k_warp_tables(const VsWarpCoef* __restrict__ coefs, int dw, int dh, int dwp, int
         // pixels bx0 .. sxmax + 1 and rows symin .. symax + 1 must be inside the box
         const bool fits = sxmax + 1 - bx0 < WG_BOX_PIXELS && symax + 1 - symin < WG_BOX_ROWS &&
                           sxmin > -(1 << 20) && sxmax < (1 << 20) && symin > -(1 << 20) && symax < (1 << 20);
-        reinterpret_cast<int4*>(t + 2 * dwp + 2 * dhp)[q] = make_int4((bx0 >> 4) * 12, symin, bx0, fits ? 1 : 0);
+        // bit 1: fx == fy == 0 at all four corners of the tile (then, for a near-identity transform, almost everywhere in it)
+        const int fr = ((XT + aL) | (XT + aR) | (XB + aL) | (XB + aR) | (YT + bL) | (YT + bR) | (YB + bL) | (YB + bR)) & 0x3e0;
+        reinterpret_cast<int4*>(t + 2 * dwp + 2 * dhp)[q] = make_int4((bx0 >> 4) * 12, symin, bx0, (fits ? 1 : 0) | (fr == 0 ? 2 : 0));
     }
 }
 
@@ -870,7 +873,7 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
     const int32_t* const BD = AD + dwp;
     const int2* const XY = reinterpret_cast<const int2*>(T + 2 * dwp) + oy0;
     const int4 tile = __ldg(reinterpret_cast<const int4*>(T + 2 * dwp + 2 * dhp) + blockIdx.y * gridDim.x + blockIdx.x);
-    const bool staged = tile.w != 0;
+    const bool staged = (tile.w & 1) != 0;
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
     if (tid == 0) {
         sCount = 0;
@@ -906,69 +909,82 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
                          : "=r"(done) : "r"(bar) : "memory");
             if (!done && ++spins > (1u << 24)) __trap();   // a lost transaction must fail loudly, not hang the GPU
         }
-        // A warp walks down six consecutive output rows.  From one row to the next a regular group normally moves
-        // down by exactly one source row at the same source column: its top taps are then the previous row's bottom
-        // taps, already aligned and paired in registers.  The test is warp-uniform (every regular lane must agree).
-        uint32_t pbyte = 0xffffffffu;                                 // raw-box byte offset of the paired bottom taps held in p*
-        uint32_t px0 = 0, px1 = 0, px2 = 0, px3 = 0, py0 = 0, py1 = 0, py2 = 0, py3 = 0;
-#pragma unroll
-        for (int k = 0; k < WG_ROWS_PER_WARP; k++) {
-            const int r = warp * WG_ROWS_PER_WARP + k;
-            if (r >= th) break;
-            const int2 xy0 = sXY0[r];
-            const int x0 = xy0.x + a0, x1 = xy0.x + a1, x2 = xy0.x + a2, x3 = xy0.x + a3;
-            const int y0 = xy0.y + bd4.x, y1 = xy0.y + bd4.y, y2 = xy0.y + bd4.z, y3 = xy0.y + bd4.w;
-            uint32_t wt0, wb0, wt1, wb1, wt2, wb2, wt3, wb3;
-            wg_weights(x0, y0, wt0, wb0); wg_weights(x1, y1, wt1, wb1);
-            wg_weights(x2, y2, wt2, wb2); wg_weights(x3, y3, wt3, wb3);
-            // one source row pair (the row term is monotone in x: the ends decide), consecutive source columns,
-            // no pixel at fx == fy == 0
-            const uint32_t spread = (uint32_t)((x1 ^ x0) | (x2 ^ x0) | (x3 ^ x0) | (y3 ^ y0));
-            const uint32_t ovf = (wt0 | wt1 | wt2 | wt3) & 0x10000u;
-            const bool regular = whole && spread < 1024u && ovf == 0u;
-            const uint32_t byte = (uint32_t)(y0 >> 10) * (uint32_t)WG_RAW_PITCH + (uint32_t)(x0 >> 10) * 3u;
-            const bool reuse = __all_sync(0xffffffffu, !regular || byte == pbyte);
-            if (regular) {
-                const uint32_t* const p = RAW + (byte >> 2);
-                const uint32_t sh = byte << 3;                        // funnel shifts use the low five bits: 8 (byte & 3)
-                uint32_t tx0, tx1, tx2, tx3, ty0, ty1, ty2, ty3;
-                if (reuse) {
-                    tx0 = px0; tx1 = px1; tx2 = px2; tx3 = px3; ty0 = py0; ty1 = py1; ty2 = py2; ty3 = py3;
-                } else {
-                    const uint32_t t0 = p[0], t1 = p[1], t2 = p[2], t3 = p[3], t4 = p[4];
-                    const uint32_t u0 = __funnelshift_r(t0, t1, sh), u1 = __funnelshift_r(t1, t2, sh),
-                                   u2 = __funnelshift_r(t2, t3, sh), u3 = __funnelshift_r(t3, t4, sh);
-                    // stream bytes of pixel j start at 3j: taps (s[3j], s[3j+3], s[3j+1], s[3j+4]) and (s[3j+2], s[3j+5])
-                    tx0 = __byte_perm(u0, u1, 0x4130); tx1 = __byte_perm(u0, u1, 0x7463);
-                    tx2 = __byte_perm(u1, u2, 0x6352); tx3 = __byte_perm(u2, u3, 0x5241);
-                    ty0 = __byte_perm(u0, u1, 0x0052); ty1 = __byte_perm(u1, u2, 0x0041);
-                    ty2 = __byte_perm(u2, u2, 0x0030); ty3 = __byte_perm(u2, u3, 0x0063);
+        auto rows = [&](auto fix_tag) {
+            constexpr bool FIX = decltype(fix_tag)::value;
+            // A warp walks down six consecutive output rows.  From one row to the next a regular group normally moves
+            // down by exactly one source row at the same source column: its top taps are then the previous row's bottom
+            // taps, already aligned and paired in registers.  The test is warp-uniform (every regular lane must agree).
+            uint32_t pbyte = 0xffffffffu;                                 // raw-box byte offset of the paired bottom taps held in p*
+            uint32_t px0 = 0, px1 = 0, px2 = 0, px3 = 0, py0 = 0, py1 = 0, py2 = 0, py3 = 0;
+    #pragma unroll
+            for (int k = 0; k < WG_ROWS_PER_WARP; k++) {
+                const int r = warp * WG_ROWS_PER_WARP + k;
+                if (r >= th) break;
+                const int2 xy0 = sXY0[r];
+                const int x0 = xy0.x + a0, x1 = xy0.x + a1, x2 = xy0.x + a2, x3 = xy0.x + a3;
+                const int y0 = xy0.y + bd4.x, y1 = xy0.y + bd4.y, y2 = xy0.y + bd4.z, y3 = xy0.y + bd4.w;
+                uint32_t wt0, wb0, wt1, wb1, wt2, wb2, wt3, wb3;
+                wg_weights(x0, y0, wt0, wb0); wg_weights(x1, y1, wt1, wb1);
+                wg_weights(x2, y2, wt2, wb2); wg_weights(x3, y3, wt3, wb3);
+                // one source row pair (the row term is monotone in x: the ends decide), consecutive source columns,
+                // no pixel at fx == fy == 0
+                const uint32_t spread = (uint32_t)((x1 ^ x0) | (x2 ^ x0) | (x3 ^ x0) | (y3 ^ y0));
+                // FIX (tiles whose corners all have fx == fy == 0: whole-pixel shifts, a camera standing still): 65535 in place
+                // of the unrepresentable 65536 gives the same byte 2 (65535 p + 32768 = 65536 p + (32768 - p)), two more
+                // instructions per pixel; elsewhere such a pixel is one in 1024 and its group goes to the list
+                if (FIX) {
+                    if (wt0 == 0x10000u) wt0 = 0xffffu;
+                    if (wt1 == 0x10000u) wt1 = 0xffffu;
+                    if (wt2 == 0x10000u) wt2 = 0xffffu;
+                    if (wt3 == 0x10000u) wt3 = 0xffffu;
                 }
-                const uint32_t c0 = p[WG_BOX_WORDS], c1 = p[WG_BOX_WORDS + 1], c2 = p[WG_BOX_WORDS + 2],
-                               c3 = p[WG_BOX_WORDS + 3], c4 = p[WG_BOX_WORDS + 4];
-                const uint32_t v0 = __funnelshift_r(c0, c1, sh), v1 = __funnelshift_r(c1, c2, sh),
-                               v2 = __funnelshift_r(c2, c3, sh), v3 = __funnelshift_r(c3, c4, sh);
-                px0 = __byte_perm(v0, v1, 0x4130); px1 = __byte_perm(v0, v1, 0x7463);
-                px2 = __byte_perm(v1, v2, 0x6352); px3 = __byte_perm(v2, v3, 0x5241);
-                py0 = __byte_perm(v0, v1, 0x0052); py1 = __byte_perm(v1, v2, 0x0041);
-                py2 = __byte_perm(v2, v2, 0x0030); py3 = __byte_perm(v2, v3, 0x0063);
-                pbyte = byte + WG_RAW_PITCH;
-                uint32_t b0, g0, r0, b1, g1, r1, b2, g2, r2, b3, g3, r3;
-                wg_blend(wt0, wb0, tx0, ty0, px0, py0, b0, g0, r0);
-                wg_blend(wt1, wb1, tx1, ty1, px1, py1, b1, g1, r1);
-                wg_blend(wt2, wb2, tx2, ty2, px2, py2, b2, g2, r2);
-                wg_blend(wt3, wb3, tx3, ty3, px3, py3, b3, g3, r3);
-                uint32_t* const o = O + r * WG_OUT_ROW_WORDS + 3 * lane;
-                o[0] = wg_pack(b0, g0, r0, b1);
-                o[1] = wg_pack(g1, r1, b2, g2);
-                o[2] = wg_pack(r2, b3, g3, r3);
-            } else {
-                // (the held taps are dead: defining them here lets the register moves of the merge land on this rare path)
-                pbyte = 0xffffffffu;
-                px0 = px1 = px2 = px3 = py0 = py1 = py2 = py3 = 0u;
-                if (4 * lane < tw) LIST[atomicAdd(&sCount, 1)] = (uint16_t)(r * 32 + lane);
+                const uint32_t ovf = FIX ? 0u : (wt0 | wt1 | wt2 | wt3) & 0x10000u;
+                const bool regular = whole && spread < 1024u && ovf == 0u;
+                const uint32_t byte = (uint32_t)(y0 >> 10) * (uint32_t)WG_RAW_PITCH + (uint32_t)(x0 >> 10) * 3u;
+                const bool reuse = __all_sync(0xffffffffu, !regular || byte == pbyte);
+                if (regular) {
+                    const uint32_t* const p = RAW + (byte >> 2);
+                    const uint32_t sh = byte << 3;                        // funnel shifts use the low five bits: 8 (byte & 3)
+                    uint32_t tx0, tx1, tx2, tx3, ty0, ty1, ty2, ty3;
+                    if (reuse) {
+                        tx0 = px0; tx1 = px1; tx2 = px2; tx3 = px3; ty0 = py0; ty1 = py1; ty2 = py2; ty3 = py3;
+                    } else {
+                        const uint32_t t0 = p[0], t1 = p[1], t2 = p[2], t3 = p[3], t4 = p[4];
+                        const uint32_t u0 = __funnelshift_r(t0, t1, sh), u1 = __funnelshift_r(t1, t2, sh),
+                                       u2 = __funnelshift_r(t2, t3, sh), u3 = __funnelshift_r(t3, t4, sh);
+                        // stream bytes of pixel j start at 3j: taps (s[3j], s[3j+3], s[3j+1], s[3j+4]) and (s[3j+2], s[3j+5])
+                        tx0 = __byte_perm(u0, u1, 0x4130); tx1 = __byte_perm(u0, u1, 0x7463);
+                        tx2 = __byte_perm(u1, u2, 0x6352); tx3 = __byte_perm(u2, u3, 0x5241);
+                        ty0 = __byte_perm(u0, u1, 0x0052); ty1 = __byte_perm(u1, u2, 0x0041);
+                        ty2 = __byte_perm(u2, u2, 0x0030); ty3 = __byte_perm(u2, u3, 0x0063);
+                    }
+                    const uint32_t c0 = p[WG_BOX_WORDS], c1 = p[WG_BOX_WORDS + 1], c2 = p[WG_BOX_WORDS + 2],
+                                   c3 = p[WG_BOX_WORDS + 3], c4 = p[WG_BOX_WORDS + 4];
+                    const uint32_t v0 = __funnelshift_r(c0, c1, sh), v1 = __funnelshift_r(c1, c2, sh),
+                                   v2 = __funnelshift_r(c2, c3, sh), v3 = __funnelshift_r(c3, c4, sh);
+                    px0 = __byte_perm(v0, v1, 0x4130); px1 = __byte_perm(v0, v1, 0x7463);
+                    px2 = __byte_perm(v1, v2, 0x6352); px3 = __byte_perm(v2, v3, 0x5241);
+                    py0 = __byte_perm(v0, v1, 0x0052); py1 = __byte_perm(v1, v2, 0x0041);
+                    py2 = __byte_perm(v2, v2, 0x0030); py3 = __byte_perm(v2, v3, 0x0063);
+                    pbyte = byte + WG_RAW_PITCH;
+                    uint32_t b0, g0, r0, b1, g1, r1, b2, g2, r2, b3, g3, r3;
+                    wg_blend(wt0, wb0, tx0, ty0, px0, py0, b0, g0, r0);
+                    wg_blend(wt1, wb1, tx1, ty1, px1, py1, b1, g1, r1);
+                    wg_blend(wt2, wb2, tx2, ty2, px2, py2, b2, g2, r2);
+                    wg_blend(wt3, wb3, tx3, ty3, px3, py3, b3, g3, r3);
+                    uint32_t* const o = O + r * WG_OUT_ROW_WORDS + 3 * lane;
+                    o[0] = wg_pack(b0, g0, r0, b1);
+                    o[1] = wg_pack(g1, r1, b2, g2);
+                    o[2] = wg_pack(r2, b3, g3, r3);
+                } else {
+                    // (the held taps are dead: defining them here lets the register moves of the merge land on this rare path)
+                    pbyte = 0xffffffffu;
+                    px0 = px1 = px2 = px3 = py0 = py1 = py2 = py3 = 0u;
+                    if (4 * lane < tw) LIST[atomicAdd(&sCount, 1)] = (uint16_t)(r * 32 + lane);
+                }
             }
-        }
+        };
+        if (tile.w & 2) rows(std::true_type{}); else rows(std::false_type{});
         __syncthreads();
         // irregular groups, pixel by pixel from the raw box (every tap of the tile is inside it)
         const int nfix = sCount * 4;
