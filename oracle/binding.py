@@ -82,6 +82,9 @@ def load(fast: bool = False):
     lib.vo_image_warp.argtypes = [P, I, I, P, P, I, I]
     lib.vo_warp_bgr.argtypes = [P, I, I, P, P, I, I, I]
     lib.vo_tf_inverse.argtypes = [P, P]
+    lib.vo_optimal_dft_size.argtypes = [I]
+    lib.vo_phase_correlate_u8.argtypes = [P, P, I, I, P]
+    lib.vo_aligner_phase.argtypes = [P, P]
     lib.vo_tf_compose.argtypes = [P, P, P]
     lib.vo_svd4.argtypes = [P, P, P, P]
     lib.vo_inv4_svd.argtypes = [P, P]
@@ -115,6 +118,15 @@ def bgr2gray(bgr, fast=False):
     h, w, _ = bgr.shape
     out = np.empty((h, w), np.uint8)
     load(fast).vo_bgr2gray(_p(bgr), w, h, _p(out))
+    return out
+
+
+def phase_correlate_u8(a, b, fast=False):
+    """cv::phaseCorrelate (alignment.cpp:374) of two u8 images taken as f32: (shift x, shift y, response)."""
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    assert a.shape == b.shape and a.ndim == 2
+    out = np.zeros(3)
+    load(fast).vo_phase_correlate_u8(_p(a), _p(b), a.shape[1], a.shape[0], _p(out))
     return out
 
 

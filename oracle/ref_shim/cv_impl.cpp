@@ -113,10 +113,16 @@ Mat operator*(const Mat& a, const Mat& b)
     return out;
 }
 
-// default-off in the reference (alignment.hpp:11); not restated
-Point2d phaseCorrelate(const Mat&, const Mat&, _NoArray, double*)
+// alignment.cpp:374 — the oracle's restatement of cv::phaseCorrelate (direct f64 DFT, see vs_oracle.cpp)
+Point2d phaseCorrelate(const Mat& src1, const Mat& src2, _NoArray, double* response)
 {
-    throw std::runtime_error("oracle cv shim: phaseCorrelate is not restated (VideoAlignerParams::phase_correlate is off by default)");
+    if (src1.type() != CV_32F || src2.type() != CV_32F || src1.rows != src2.rows || src1.cols != src2.cols)
+        throw std::runtime_error("oracle cv shim: phaseCorrelate needs two CV_32F images of one size");
+    if (src1.step[0] != src2.step[0]) throw std::runtime_error("oracle cv shim: phaseCorrelate needs equal row steps");
+    double out[3];
+    vo_phase_correlate(src1.ptr<float>(0), src2.ptr<float>(0), src1.cols, src1.rows, (int64_t)(src1.step[0] / sizeof(float)), out);
+    if (response) *response = out[2];
+    return Point2d(out[0], out[1]);
 }
 
 }  // namespace cv

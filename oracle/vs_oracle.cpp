@@ -19,6 +19,7 @@
 #include "vs_oracle.h"
 
 #include <algorithm>
+#include <cfloat>
 #include <array>
 #include <cmath>
 #include <cstdlib>
@@ -624,6 +625,159 @@ int vo_introselect_depth(const uint16_t* abs_delta, int n, int nth, int depth, u
 }
 
 //------------------------------------------------------------------------------
+// cv::phaseCorrelate (alignment.cpp:374; OpenCV imgproc/src/phasecorr.cpp, not under /root/reference) restated
+// as a direct, separable DFT in f64 with every sum taken serially in ascending index order and no FMA — the
+// canonical order the CUDA kernels reproduce bit for bit.  OpenCV runs its own f32 mixed-radix FFT: its ulps are
+// not reproduced, its result is (tests/golden/phase_correlate.npz pins shift and response against cv2 4.13 to 1e-4):
+//   M, N = getOptimalDFTSize(rows), (cols); zero padding on the right / bottom (copyMakeBorder);
+//   P = F1 conj(F2) (mulSpectrums conjB), C = P |P| / (|P|^2 + FLT_EPSILON) (magSpectrums, divSpectrums),
+//   R = unnormalised inverse DFT of C, fftShift, first maximum (minMaxLoc), 5x5 weighted centroid clamped to the
+//   array (response = window sum / (M N)), shift = (N/2, M/2) - centroid.
+int vo_optimal_dft_size(int n)
+{
+    for (;; n++) {
+        int m = n;
+        while (m % 2 == 0) m /= 2;
+        while (m % 3 == 0) m /= 3;
+        while (m % 5 == 0) m /= 5;
+        if (m == 1) return n;
+    }
+}
+
+static void pc_twiddles(int n, std::vector<double>& c, std::vector<double>& s)
+{
+    c.resize(n); s.resize(n);
+    for (int j = 0; j < n; j++) {
+        const double a = 2.0 * M_PI * (double)j / (double)n;
+        c[j] = cos(a); s[j] = -sin(a);
+    }
+}
+
+// forward transform of a real w x h image padded to N x M: G[m][k], k < N/2+1 (interleaved re, im)
+static void pc_forward(const float* img, int64_t stride, int w, int h, int M, int N,
+                       const std::vector<double>& cN, const std::vector<double>& sN,
+                       const std::vector<double>& cM, const std::vector<double>& sM, std::vector<double>& G)
+{
+    const int Kh = N / 2 + 1;
+    std::vector<double> F((size_t)h * Kh * 2);
+    for (int r = 0; r < h; r++)
+        for (int k = 0; k < Kh; k++) {
+            double re = 0.0, im = 0.0;
+            int j = 0;
+            for (int n = 0; n < w; n++) {
+                const double x = (double)img[(size_t)r * stride + n];
+                re = re + x * cN[j];
+                im = im + x * sN[j];
+                j += k; if (j >= N) j -= N;
+            }
+            F[((size_t)r * Kh + k) * 2] = re; F[((size_t)r * Kh + k) * 2 + 1] = im;
+        }
+    G.assign((size_t)M * Kh * 2, 0.0);
+    for (int m = 0; m < M; m++)
+        for (int k = 0; k < Kh; k++) {
+            double re = 0.0, im = 0.0;
+            int j = 0;
+            for (int r = 0; r < h; r++) {
+                const double ar = F[((size_t)r * Kh + k) * 2], ai = F[((size_t)r * Kh + k) * 2 + 1];
+                const double t1 = ar * cM[j], t2 = ai * sM[j], t3 = ar * sM[j], t4 = ai * cM[j];
+                re = re + (t1 - t2);
+                im = im + (t3 + t4);
+                j += m; if (j >= M) j -= M;
+            }
+            G[((size_t)m * Kh + k) * 2] = re; G[((size_t)m * Kh + k) * 2 + 1] = im;
+        }
+}
+
+void vo_phase_correlate(const float* img1, const float* img2, int w, int h, int64_t stride, double out[3])
+{
+    const int M = vo_optimal_dft_size(h), N = vo_optimal_dft_size(w), Kh = N / 2 + 1;
+    std::vector<double> cN, sN, cM, sM, G1, G2;
+    pc_twiddles(N, cN, sN);
+    pc_twiddles(M, cM, sM);
+    pc_forward(img1, stride, w, h, M, N, cN, sN, cM, sM, G1);
+    pc_forward(img2, stride, w, h, M, N, cN, sN, cM, sM, G2);
+    // cross-power spectrum
+    std::vector<double> C((size_t)M * Kh * 2), D((size_t)M * Kh * 2);
+    for (size_t i = 0; i < (size_t)M * Kh; i++) {
+        const double ar = G1[2 * i], ai = G1[2 * i + 1], br = G2[2 * i], bi = G2[2 * i + 1];
+        const double pr = ar * br + ai * bi, pi = ai * br - ar * bi;
+        const double mag = sqrt(pr * pr + pi * pi);
+        const double den = mag * mag + (double)FLT_EPSILON;
+        C[2 * i] = (pr * mag) / den; C[2 * i + 1] = (pi * mag) / den;
+    }
+    // inverse along the columns (conjugate twiddles)
+    for (int r = 0; r < M; r++)
+        for (int k = 0; k < Kh; k++) {
+            double re = 0.0, im = 0.0;
+            int j = 0;
+            for (int m = 0; m < M; m++) {
+                const double ar = C[((size_t)m * Kh + k) * 2], ai = C[((size_t)m * Kh + k) * 2 + 1];
+                const double t1 = ar * cM[j], t2 = ai * sM[j], t3 = ai * cM[j], t4 = ar * sM[j];
+                re = re + (t1 + t2);
+                im = im + (t3 - t4);
+                j += r; if (j >= M) j -= M;
+            }
+            D[((size_t)r * Kh + k) * 2] = re; D[((size_t)r * Kh + k) * 2 + 1] = im;
+        }
+    // inverse along the rows to a real surface (Hermitian halves folded), then the first maximum of the shifted surface
+    std::vector<double> R((size_t)M * N);
+    const int kfull = (N - 1) / 2;
+    for (int r = 0; r < M; r++)
+        for (int n = 0; n < N; n++) {
+            const double* d = &D[(size_t)r * Kh * 2];
+            double acc = d[0];
+            int j = 0;
+            for (int k = 1; k <= kfull; k++) {
+                j += n; if (j >= N) j -= N;
+                const double t = d[2 * k] * cN[j] + d[2 * k + 1] * sN[j];
+                acc = acc + 2.0 * t;
+            }
+            if (N % 2 == 0) {
+                j += n; if (j >= N) j -= N;
+                acc = acc + d[2 * (N / 2)] * cN[j];
+            }
+            R[(size_t)r * N + n] = acc;
+        }
+    auto shifted = [&](int y, int x) {   // fftShift: element (r, n) moves to ((r + M/2) % M, (n + N/2) % N)
+        const int r = (y - M / 2 + M) % M, n = (x - N / 2 + N) % N;
+        return R[(size_t)r * N + n];
+    };
+    int py = 0, px = 0;
+    double best = shifted(0, 0);
+    for (int y = 0; y < M; y++)
+        for (int x = 0; x < N; x++) {
+            const double v = shifted(y, x);
+            if (v > best) { best = v; py = y; px = x; }
+        }
+    int minr = py - 2, maxr = py + 2, minc = px - 2, maxc = px + 2;
+    if (minr < 0) minr = 0;
+    if (minc < 0) minc = 0;
+    if (maxr > M - 1) maxr = M - 1;
+    if (maxc > N - 1) maxc = N - 1;
+    double cx = 0.0, cy = 0.0, sum = 0.0;
+    for (int y = minr; y <= maxr; y++)
+        for (int x = minc; x <= maxc; x++) {
+            const double v = shifted(y, x);
+            cx = cx + (double)x * v;
+            cy = cy + (double)y * v;
+            sum = sum + v;
+        }
+    const double response = sum / (double)(M * N);
+    sum = sum + DBL_EPSILON;
+    cx = cx / sum; cy = cy / sum;
+    out[0] = (double)N / 2.0 - cx;
+    out[1] = (double)M / 2.0 - cy;
+    out[2] = response;
+}
+
+void vo_phase_correlate_u8(const uint8_t* img1, const uint8_t* img2, int w, int h, double out[3])
+{
+    std::vector<float> a((size_t)w * h), b((size_t)w * h);
+    for (size_t i = 0; i < (size_t)w * h; i++) { a[i] = (float)img1[i]; b[i] = (float)img2[i]; }
+    vo_phase_correlate(a.data(), b.data(), w, h, w, out);
+}
+
+//------------------------------------------------------------------------------
 // VideoAligner — alignment.cpp:149-704.
 
 void vo_align_params_default(vo_align_params* p)   // alignment.hpp:5-41
@@ -653,6 +807,7 @@ struct vo_aligner {
         int iters = 0;
     };
     std::vector<Level> lv;
+    double phase[3] = {0, 0, 0};                  // last cv::phaseCorrelate shift (x, y) and response
 };
 
 vo_aligner* vo_aligner_create(void) { return new vo_aligner(); }
@@ -688,7 +843,7 @@ static bool compute_pyramid(vo_aligner* a, const uint8_t* bgr, int width, int he
     for (int i = 1; i < a->levels; i++)
         vo_pyr_down(a->lv[i - 1].img[a->curr].data(), a->lv[i - 1].w, a->lv[i - 1].h,
                     a->lv[i].img[a->curr].data(), a->lv[i].w, a->lv[i].h);
-    // alignment.cpp:225-229 (PhaseImage conversion) has no effect when phase_correlate is off.
+    // alignment.cpp:225-229: PhaseImage = level 2 as f32 — u8 values are exact in f32, vo_phase_correlate_u8 converts on use.
     if (a->accumulated >= 2) return true;
     return ++a->accumulated >= 2;
 }
@@ -722,7 +877,21 @@ int vo_aligner_align(vo_aligner* a, const uint8_t* bgr, int w, int h,
 
     if (!compute_pyramid(a, bgr, w, h, params)) return 0;
     if (a->curr == KeyframeIndex) compute_keyframe(a);
-    // params->phase_correlate (alignment.cpp:369-388) is not restated: default off.
+    // alignment.cpp:369-388 — translation seeded from cv::phaseCorrelate of the level-2 images
+    if (params->phase_correlate) {
+        const int PhaseLevel = 2;                          // alignment.hpp:69
+        if (a->levels <= PhaseLevel) return 0;             // (the reference indexes past its pyramid here)
+        auto& PL = a->lv[PhaseLevel];
+        double pc[3];
+        vo_phase_correlate_u8(PL.img[a->prev].data(), PL.img[a->curr].data(), PL.w, PL.h, pc);
+        a->phase[0] = pc[0]; a->phase[1] = pc[1]; a->phase[2] = pc[2];
+        if (pc[2] > params->phase_correlate_threshold) {
+            const float phase_layer_scale = (1 << PhaseLevel) / float(1 << a->levels);
+            T[2] = pc[0] * phase_layer_scale;
+            T[3] = pc[1] * phase_layer_scale;
+            if (a->curr == KeyframeIndex) { T[2] = -T[2]; T[3] = -T[3]; }
+        }
+    }
 
     std::vector<DeltaPixel> dpx, dpy;
     for (int i = a->levels - 1; i >= 0; i--) {
@@ -845,6 +1014,7 @@ int vo_aligner_align(vo_aligner* a, const uint8_t* bgr, int w, int h,
     return 1;
 }
 
+void vo_aligner_phase(const vo_aligner* a, double out[3]) { out[0] = a->phase[0]; out[1] = a->phase[1]; out[2] = a->phase[2]; }
 int vo_aligner_levels(const vo_aligner* a) { return a->levels; }
 int vo_aligner_curr_index(const vo_aligner* a) { return a->curr; }
 void vo_aligner_level_info(const vo_aligner* a, int level, int* w, int* h, int* tile, int* tw, int* th)

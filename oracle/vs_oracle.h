@@ -87,6 +87,11 @@ int vo_select_smallest(const uint16_t* abs_delta, int n, float fraction, uint32_
 int vo_introselect_depth(const uint16_t* abs_delta, int n, int nth, int depth, uint32_t* order);
 
 /* ---- aligner (alignment.cpp:149-704) ---- */
+/* cv::phaseCorrelate (alignment.cpp:374) on f32 images: out = shift x, shift y, response */
+int  vo_optimal_dft_size(int n);
+void vo_phase_correlate(const float* img1, const float* img2, int w, int h, int64_t stride, double out[3]);
+void vo_phase_correlate_u8(const uint8_t* img1, const uint8_t* img2, int w, int h, double out[3]);
+
 typedef struct vo_align_params {
     int    phase_correlate;          /* must be 0: not restated (default off in the reference) */
     double phase_correlate_threshold;
@@ -106,6 +111,7 @@ void        vo_aligner_destroy(vo_aligner*);
 int  vo_aligner_align(vo_aligner*, const uint8_t* bgr, int w, int h,
                       const vo_align_params* params, double T[4]);
 /* debug taps */
+void vo_aligner_phase(const vo_aligner*, double out[3]);   /* phaseCorrelate result of the last align */
 int  vo_aligner_levels(const vo_aligner*);
 int  vo_aligner_curr_index(const vo_aligner*);
 void vo_aligner_level_info(const vo_aligner*, int level, int* w, int* h, int* tile, int* tw, int* th);

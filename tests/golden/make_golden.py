@@ -70,4 +70,30 @@ b = np.zeros((64, 64), np.float32); b[27:37, 25:35] = 255
 out["phase_shift"] = np.array([sx, sy, resp])
 
 np.savez_compressed(os.path.join(HERE, "cv2_golden.npz"), **out)
+
+# --- phaseCorrelate on u8-valued textures the way the aligner calls it (alignment.cpp:225-229, 374: level-2 image as
+#     CV_32F, no window): even, odd and padded (non-5-smooth) sizes, translations, a small rotation + translation,
+#     and two unrelated images (low response).  Written to a second file so cv2_golden.npz stays byte-stable.
+prng = np.random.default_rng(20261019)
+pc = {"cv2_version": np.array(cv2.__version__)}
+cases = []
+for i, (h, w) in enumerate([(64, 96), (45, 75), (67, 120), (90, 160), (61, 83), (135, 240)]):
+    big = cv2.GaussianBlur(prng.random((h + 48, w + 48)).astype(np.float32), (0, 0), 1.5 + 0.5 * (i % 3))
+    big = ((big - big.min()) / (big.max() - big.min()) * 255).astype(np.uint8)
+    shifts = [(0, 0), (3, -5), (-7, 2), (11, 9)]
+    for (dy, dx) in shifts:
+        cases.append((big[24:24 + h, 24:24 + w], big[24 + dy:24 + dy + h, 24 + dx:24 + dx + w]))
+    R = cv2.getRotationMatrix2D((big.shape[1] / 2, big.shape[0] / 2), 0.4, 1.002); R[:, 2] += (2.3, -1.6)
+    rot = cv2.warpAffine(big, R, (big.shape[1], big.shape[0]), flags=cv2.INTER_LINEAR)
+    cases.append((big[24:24 + h, 24:24 + w], rot[24:24 + h, 24:24 + w]))
+    other = prng.integers(0, 256, (h, w), dtype=np.uint8)
+    cases.append((big[24:24 + h, 24:24 + w], other))
+res = []
+for k, (a, b) in enumerate(cases):
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    (sx, sy), resp = cv2.phaseCorrelate(a.astype(np.float32), b.astype(np.float32))
+    pc["a%d" % k] = a; pc["b%d" % k] = b
+    res.append([sx, sy, resp])
+pc["result"] = np.array(res)
+np.savez_compressed(os.path.join(HERE, "phase_correlate.npz"), **pc)
 print("wrote", os.path.join(HERE, "cv2_golden.npz"), {k: getattr(v, "shape", None) for k, v in out.items()})
