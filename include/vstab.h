@@ -141,11 +141,14 @@ int vs_image_warp_u8_f32(vs_ctx*, const vs_img* in, const float* params4, const 
  * (x+dst_x0, y+dst_y0) of the full-size warp (stabilizer.cpp:102-109 crop fused). */
 int vs_bgr_warp_u8(vs_ctx*, const vs_img* src, const double* M6, const vs_img* dst,
                    int dst_x0, int dst_y0, int mode, int border, int mem);
+/* cv::phaseCorrelate(src1, src2, noArray(), &response) (alignment.cpp:374, align_test.cpp:190,386) on two u8 images of
+ * one size taken as CV_32F: out3 = shift x, shift y, response (host memory).  Direct f64 DFT on the device. */
+int vs_phase_correlate_u8(vs_ctx*, const vs_img* src1, const vs_img* src2, double* out3, int mem);
 
 /* ------------------------------------------- fused, batched, device-resident */
 /* VideoAlignerParams, alignment.hpp:5-41 */
 typedef struct vs_align_params {
-    int32_t phase_correlate;          /* nonzero -> VS_ERR_UNSUPPORTED (default off upstream) */
+    int32_t phase_correlate;          /* alignment.cpp:369-388: seed the translation from the phase correlation of the level-2 images */
     double  phase_correlate_threshold;
     double  threshold;
     float   smallest_fraction;
@@ -233,6 +236,9 @@ int vs_clip_get_jacobians(vs_clip*, int slot, int level, int axis, float* out /*
 /* need VS_CLIP_DEBUG_TAPS; pair = index within the last vs_clip_align call */
 int vs_clip_get_warpdiff(vs_clip*, int pair, int level, int axis, uint16_t* out /* (tw,th) */);
 int vs_clip_get_selected(vs_clip*, int pair, int level, int axis, uint32_t* out_order, int* out_k);
+/* cv::phaseCorrelate result (shift x, shift y, response) of pair `pair` of the last vs_clip_align call made with
+ * params.phase_correlate set (alignment.cpp:374) */
+int vs_clip_get_phase(vs_clip*, int pair, double* out3);
 /* SM cycles pair `pair` of the last vs_clip_align spent per phase, summed over levels:
  * {warp-diff, selection, Hessian sums, SVD beside the first iteration + Gauss-Newton gathers, Gauss-Newton reduce + update,
  *  number of parallel partition rounds of the selection (a count, not cycles)} */

@@ -312,6 +312,12 @@ class Aligner:
     def levels(self):
         return self.lib.vo_aligner_levels(self.h)
 
+    def phase(self):
+        """cv::phaseCorrelate result (shift x, shift y, response) of the last align (params.phase_correlate on)."""
+        out = np.zeros(3)
+        self.lib.vo_aligner_phase(self.h, _p(out))
+        return out
+
     def level_info(self, level):
         v = [C.c_int() for _ in range(5)]
         self.lib.vo_aligner_level_info(self.h, level, *[C.byref(x) for x in v])

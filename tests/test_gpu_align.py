@@ -19,7 +19,7 @@ def run_oracle(ob, frames, params=None):
     res = []
     for i, f in enumerate(frames):
         ok, T = al.align(f)
-        rec = dict(ok=ok, T=T.copy(), curr=al.lib.vo_aligner_curr_index(al.h))
+        rec = dict(ok=ok, T=T.copy(), curr=al.lib.vo_aligner_curr_index(al.h), phase=al.phase())
         if i > 0:
             L = al.levels
             rec["iters"] = [al.iterations(l) for l in range(L)]
@@ -69,6 +69,9 @@ def check_clip_against_oracle(gpu, ob, frames, deep=True, **param_overrides):
                 for a in range(2):
                     assert np.array_equal(clip.get_keypoints(kf, l, a), r["kp"][l][a]), ("keypoints", i, l, a)
                     assert np.array_equal(clip.get_jacobians(kf, l, a), r["jac"][l][a]), ("jacobians", i, l, a)
+        if param_overrides.get("phase_correlate"):
+            # shift and response of cv::phaseCorrelate (alignment.cpp:374): same serial f64 sums, bit for bit
+            assert np.array_equal(clip.get_phase(p), r["phase"]), ("phase", i, clip.get_phase(p), r["phase"])
         assert list(iters[p]) == r["iters"], ("iterations", i, list(iters[p]), r["iters"])
         assert bool(status[p]) == r["ok"], ("status", i)
         for l in range(clip.levels):
@@ -124,6 +127,48 @@ def test_failure_paths_match_oracle(gpu, ob):
     check_clip_against_oracle(gpu, ob, noise, deep=False)
     flat = np.full((3, h, w, 3), 77, np.uint8)                      # zero gradients, singular Hessian
     check_clip_against_oracle(gpu, ob, flat, deep=False)
+
+
+def test_phase_correlate_operator(gpu, ob):
+    """cv::phaseCorrelate on the device: bit-identical to the restatement (same serial f64 sums) on even, odd and
+    padded sizes, and within 1e-4 of the cv2 4.13 fixtures."""
+    import os
+    from video_stabilizer_b200 import imgproc as ip
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "phase_correlate.npz"))
+    ref = g["result"]
+    for k in range(len(ref)):
+        a, b = g["a%d" % k], g["b%d" % k]
+        (sx, sy), resp = ip.PhaseCorrelate(a, b, gpu)
+        got = np.array([sx, sy, resp])
+        assert np.array_equal(got, ob.phase_correlate_u8(a, b)), (k, got, ob.phase_correlate_u8(a, b))
+        assert np.abs(got - ref[k]).max() < 1e-4, (k, got, ref[k])
+    # the reference's own shift pattern (align_test.cpp:358-400): (5, 7) within half a pixel
+    a = np.zeros((64, 64), np.uint8); a[20:30, 20:30] = 255
+    b = np.zeros((64, 64), np.uint8); b[27:37, 25:35] = 255
+    (sx, sy), resp = ip.PhaseCorrelate(a, b, gpu)
+    assert abs(sx - 5) <= 0.5 and abs(sy - 7) <= 0.5
+    # strided views and a level-2 sized image (480 x 270: the size the 1080p path runs)
+    rng = np.random.default_rng(3)
+    big = rng.integers(0, 256, (300, 520), dtype=np.uint8)
+    a, b = big[10:280, 20:500], big[13:283, 15:495]
+    (sx, sy), resp = ip.PhaseCorrelate(a, b, gpu)
+    assert np.array_equal(np.array([sx, sy, resp]), ob.phase_correlate_u8(a, b))
+    assert abs(sx - (-5)) < 0.01 and abs(sy - 3) < 0.01 and resp > 0.9
+
+
+@pytest.mark.parametrize("w,h,n,seed,step", [(320, 180, 8, 0, 2.0), (640, 360, 6, 1, 9.0), (250, 141, 5, 2, 5.0)])
+def test_clip_alignment_with_phase_correlate_matches_oracle(gpu, ob, w, h, n, seed, step):
+    """VideoAlignerParams::phase_correlate (alignment.cpp:369-388): the seed, and everything the solver derives from
+    it (warp-diffs, selections, iteration counts, status), identical to the restated aligner."""
+    from video_stabilizer_b200 import synth
+    frames, _ = synth.make_clip_numpy(w, h, n, seed, step=step, limit=40.0)
+    worst, T, status, ref = check_clip_against_oracle(gpu, ob, frames, deep=False, phase_correlate=1)
+    assert worst < 1e-6
+    assert any(r["phase"][2] > 0.5 for r in ref[1:]), "the seed should be accepted on some pairs"
+    # a threshold nobody passes: the seed is computed and ignored, results equal the plain run
+    worst, T2, status2, _ = check_clip_against_oracle(gpu, ob, frames, deep=False, phase_correlate=1, phase_correlate_threshold=1e9)
+    _, T0, status0, _ = check_clip_against_oracle(gpu, ob, frames, deep=False)
+    assert np.array_equal(T2, T0) and np.array_equal(status2, status0)
 
 
 def test_clip_warp_matches_oracle(gpu, ob):

@@ -89,6 +89,24 @@ def test_video_aligner_class_matches_oracle(host, ob, w, h, n, seed):
     assert ok == ok_o and corner_displacement(T, T_o, w, h) <= TOL_PX
 
 
+def test_video_aligner_class_with_phase_correlate(host, ob):
+    """AlignNextFrame with VideoAlignerParams::phase_correlate through the drop-in class, against the restated
+    aligner; the flag can be switched per call (alignment.hpp:55-58)."""
+    from video_stabilizer_b200 import _capi as capi
+    w, h = 320, 180
+    frames = _clip(w, h, 9, 4, step=8.0, limit=40.0)
+    p = capi.VsAlignParams()
+    capi.load().vs_align_params_default(p)
+    po = ob.align_params_default()
+    a, o = host.VideoAligner(0), ob.Aligner(po)
+    for i, f in enumerate(frames):
+        p.phase_correlate = po.phase_correlate = 0 if i in (4, 5) else 1
+        ok, T = a.AlignNextFrame(f, p)
+        ok_o, T_o = o.align(f)
+        assert ok == ok_o, i
+        assert corner_displacement(T, T_o, w, h) <= 1e-6, (i, T, T_o)
+
+
 def test_video_aligner_size_change_resets(host, ob):
     a, o = host.VideoAligner(0), ob.Aligner()
     seq = list(_clip(320, 180, 3, 1)) + list(_clip(256, 144, 3, 2)) + list(_clip(320, 180, 2, 3))

@@ -71,6 +71,19 @@ def test_failure_paths_equal_reference_sources(ref):
     _compare_aligners(ref, np.full((3, 180, 320, 3), 77, np.uint8))
 
 
+def test_phase_correlate_initialisation_equals_reference_sources(ref):
+    """VideoAlignerParams::phase_correlate: the reference's own alignment.cpp:369-388 (seed scaling, threshold,
+    negation on keyframes) over the restated cv::phaseCorrelate, against the restated aligner."""
+    for (w, h, n, seed, step) in ((320, 180, 6, 0, 2.0), (320, 180, 6, 4, 9.0)):
+        frames = _clip(w, h, n, seed, step=step, limit=40.0)
+        p = ref.align_params_default()
+        p.phase_correlate = 1
+        oks = _compare_aligners(ref, frames, p)
+        assert sum(oks) >= (n - 2 if step < 5 else 2)   # large steps fail with or without the seed, like upstream
+        p.phase_correlate_threshold = 1e9          # computed, never accepted
+        _compare_aligners(ref, frames, p)
+
+
 def test_size_change_resets_like_reference_sources(ref):
     a, r = ref.Aligner(), ref.RefAligner()
     seq = list(_clip(320, 180, 3, 1)) + list(_clip(256, 144, 3, 2)) + list(_clip(320, 180, 2, 3))

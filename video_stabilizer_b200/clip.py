@@ -152,6 +152,12 @@ class Clip:
         self._chk(self.lib.vs_clip_get_warpdiff(self.handle, pair, level, axis, capi.ptr(out)), "vs_clip_get_warpdiff")
         return out
 
+    def get_phase(self, pair: int) -> np.ndarray:
+        """cv::phaseCorrelate result (shift x, shift y, response) of a pair of the last align call (phase_correlate on)."""
+        out = np.zeros(3, np.float64)
+        self._chk(self.lib.vs_clip_get_phase(self.handle, pair, capi.ptr(out)), "vs_clip_get_phase")
+        return out
+
     def get_selected(self, pair: int, level: int, axis: int) -> np.ndarray:
         li = self.level_info(level)
         out = np.empty(li["th"] * li["tw"], np.uint32)

@@ -55,7 +55,6 @@ bool VideoAligner::Impl::ensure_clip(int w, int h, const VideoAlignerParams& par
 {
     vs_align_params cp;
     vstab::to_c_params(params, &cp);
-    cp.phase_correlate = 0;   // handled (refused) by the caller
     if (clip && w == width && h == height) return vs_clip_set_params(clip, &cp) == VS_OK;
     destroy_clip();
     width = w; height = h;
@@ -108,11 +107,6 @@ bool VideoAligner::AlignNextFrame(const cv::Mat& frame, SimilarityTransform& tra
             s.width = s.height = -1;   // force re-initialisation, like upstream's LastWidth = -1
             return false;
         }
-    }
-    if (params.phase_correlate) {
-        std::cerr << "VideoAligner: phase_correlate initialisation is not implemented on the GPU path" << std::endl;
-        vs_ctx_synchronize(s.ctx);
-        return false;
     }
 
     vs_pair pair;

@@ -16,7 +16,6 @@ ClipStabilizer::ClipStabilizer(int device, int width, int height, int chunk_fram
 {
     if (width <= 0 || height <= 0 || chunk_frames <= 0) throw std::runtime_error("ClipStabilizer: bad geometry");
     if (2 * m_crop >= width || 2 * m_crop >= height) throw std::runtime_error("ClipStabilizer: crop_pixels removes the whole frame");
-    if (params.aligner.phase_correlate) throw std::runtime_error("ClipStabilizer: phase_correlate initialisation is not implemented on the GPU path");
     if (vs_ctx_create(device, &m_ctx) != VS_OK)
         throw std::runtime_error(std::string("ClipStabilizer: cannot create a GPU context: ") + vs_last_error(nullptr));
     vs_align_params cp;

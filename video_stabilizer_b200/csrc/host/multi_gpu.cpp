@@ -28,7 +28,6 @@ MultiGpuStabilizer::MultiGpuStabilizer(const std::vector<int>& devices, int widt
 {
     if (devices.empty() || width <= 0 || height <= 0 || max_frames <= 0) throw std::runtime_error("MultiGpuStabilizer: bad arguments");
     if (2 * m_crop >= width || 2 * m_crop >= height) throw std::runtime_error("MultiGpuStabilizer: crop_pixels removes the whole frame");
-    if (params.aligner.phase_correlate) throw std::runtime_error("MultiGpuStabilizer: phase_correlate initialisation is not implemented on the GPU path");
     vs_align_params cp;
     to_c_params(params.aligner, &cp);
     const int workers = (int)devices.size();

@@ -15,6 +15,7 @@
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 struct vs_clip {
     // TMA descriptor of the BGR store viewed as u32 [slot][row][pitch/4], box {108 words, 20 rows, 1}:
@@ -66,6 +67,13 @@ struct vs_clip {
     double* h_T = nullptr;            // pinned, max_pairs * 4
     int32_t* h_status = nullptr;      // pinned, max_pairs
     int lane_base[kLanes] = {}, lane_n[kLanes] = {};
+    // phase-correlation initialiser (params.phase_correlate): allocated on first use
+    VsPhasePlan pc;
+    bool pc_ready = false;
+    std::vector<char> pc_valid;       // per slot: the spectrum matches the pyramid in the slot
+    int32_t* d_pc_slots = nullptr;    // capacity
+    double* d_pc_init = nullptr;      // [max_pairs][2] seed (TX, TY) of the solver
+    double* d_pc_phase = nullptr;     // [max_pairs][3] shift x, shift y, response
 };
 
 namespace {
@@ -99,6 +107,8 @@ void free_all(vs_clip* c)
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
     cudaFree(c->d_pos_scratch); cudaFree(c->d_res_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
     cudaFree(c->d_warp_tab);
+    cudaFree(c->pc.d_tw); cudaFree(c->pc.d_rows); cudaFree(c->pc.d_spec); cudaFree(c->pc.d_cross); cudaFree(c->pc.d_inv);
+    cudaFree(c->pc.d_surf); cudaFree(c->d_pc_slots); cudaFree(c->d_pc_init); cudaFree(c->d_pc_phase);
     for (int l = 0; l < vs_clip::kLanes; l++) {
         if (c->solve_stream[l]) { cudaStreamSynchronize(c->solve_stream[l]); cudaStreamDestroy(c->solve_stream[l]); }
         if (c->ev_ready[l]) cudaEventDestroy(c->ev_ready[l]);
@@ -159,6 +169,67 @@ int clip_warp_launch(vs_clip* c, const int32_t* d_slots, const VsWarpCoef* d_coe
     return vsk_bgr_warp_slots(c->ctx, src, d_slots, d_coef, dst, crop, crop, mode, border);
 }
 
+constexpr int kPhaseLevel = 2;   // alignment.hpp:69
+
+int phase_prepare(vs_clip* c)
+{
+    if (c->pc_ready) return VS_OK;
+    vs_ctx* ctx = c->ctx;
+    const VsClipGeom& g = c->g;
+    if (g.levels <= kPhaseLevel)
+        return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "phase_correlate needs pyramid level %d, this clip has %d levels", kPhaseLevel, g.levels);
+    VsPhasePlan& p = c->pc;
+    const VsLevel& L = g.lv[kPhaseLevel];
+    p.w = L.w; p.h = L.h; p.pitch = L.pitch;
+    p.M = vs_optimal_dft_size(L.h); p.N = vs_optimal_dft_size(L.w); p.Kh = p.N / 2 + 1;
+    const size_t spec = (size_t)p.M * p.Kh * 2;
+    int r = dev_alloc(ctx, &p.d_tw, (size_t)(p.N + p.M) * 2);
+    if (r == VS_OK) r = dev_alloc(ctx, &p.d_rows, (size_t)c->capacity * p.h * p.Kh * 2);
+    if (r == VS_OK) r = dev_alloc(ctx, &p.d_spec, (size_t)c->capacity * spec);
+    if (r == VS_OK) r = dev_alloc(ctx, &p.d_cross, (size_t)c->max_pairs * spec);
+    if (r == VS_OK) r = dev_alloc(ctx, &p.d_inv, (size_t)c->max_pairs * spec);
+    if (r == VS_OK) r = dev_alloc(ctx, &p.d_surf, (size_t)c->max_pairs * p.M * p.N);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_pc_slots, (size_t)c->capacity);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_pc_init, (size_t)c->max_pairs * 2);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_pc_phase, (size_t)c->max_pairs * 3);
+    if (r != VS_OK) return r;
+    std::vector<double> tw((size_t)(p.N + p.M) * 2);
+    vs_phase_twiddles(p.N, tw.data());
+    vs_phase_twiddles(p.M, tw.data() + (size_t)p.N * 2);
+    VS_CUDA(ctx, cudaMemcpyAsync(p.d_tw, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // tw is a local
+    c->pc_valid.assign(c->capacity, 0);
+    c->pc_ready = true;
+    return VS_OK;
+}
+
+// Enqueues, on the context stream, the spectra of the frames of `pairs` that do not have one yet and the phase
+// correlation of every pair; d_pairs is the device copy of `pairs`, [base, base + n) the pairs' scratch range.
+// *init receives the device array of seeds for the solver.
+int phase_seed(vs_clip* c, const vs_pair* pairs, const vs_pair* d_pairs, int n, int base, const double** init)
+{
+    vs_ctx* ctx = c->ctx;
+    VS_TRY(phase_prepare(c));
+    std::vector<int32_t> todo;
+    for (int i = 0; i < n; i++)
+        for (int s : {pairs[i].template_slot, pairs[i].keyframe_slot})
+            if (!c->pc_valid[s]) { c->pc_valid[s] = 1; todo.push_back(s); }
+    if (!todo.empty()) {
+        // pageable source: the copy is staged before the call returns
+        VS_CUDA(ctx, cudaMemcpyAsync(c->d_pc_slots, todo.data(), todo.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        VS_TRY(vsk_phase_forward(ctx, c->pc, c->d_pyr + c->g.lv[kPhaseLevel].img_off, c->g.pyr_slot_bytes, c->d_pc_slots, (int)todo.size()));
+    }
+    // alignment.cpp:380: the seed is expressed at the coarsest level
+    const float scale = (float)(1 << kPhaseLevel) / float(1 << c->g.levels);
+    VsPhasePlan p = c->pc;
+    const size_t spec = (size_t)p.M * p.Kh * 2;
+    p.d_cross += (size_t)base * spec; p.d_inv += (size_t)base * spec; p.d_surf += (size_t)base * p.M * p.N;
+    VS_TRY(vsk_phase_pairs(ctx, p, d_pairs, n, c->params.phase_correlate_threshold, scale,
+                           c->d_pc_phase + (size_t)base * 3, c->d_pc_init + (size_t)base * 2));
+    *init = c->d_pc_init + (size_t)base * 2;
+    return VS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -172,8 +243,6 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
     VS_REQUIRE(ctx, width <= 65535 && height <= 65535, "clip_create: keypoint coordinates must fit in u16");
     vs_align_params P;
     if (params) P = *params; else vs_align_params_default(&P);
-    if (P.phase_correlate)
-        return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "phase_correlate initialisation (alignment.cpp:369-388) is not implemented");
     VS_REQUIRE(ctx, P.max_iters >= 1, "clip_create: max_iters must be >= 1");
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
 
@@ -263,8 +332,6 @@ int vs_clip_set_params(vs_clip* c, const vs_align_params* params)
 {
     if (!c || !params) return VS_ERR_INVALID;
     vs_ctx* ctx = c->ctx;
-    if (params->phase_correlate)
-        return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "phase_correlate initialisation (alignment.cpp:369-388) is not implemented");
     VS_REQUIRE(ctx, params->max_iters >= 1, "clip_set_params: max_iters must be >= 1");
     const int mw = c->params.pyramid_min_width, mh = c->params.pyramid_min_height;
     c->params = *params;
@@ -315,6 +382,7 @@ int vs_clip_build_pyramids(vs_clip* c, int slot0, int n)
     VsDevImg bgr{c->d_bgr + (size_t)slot0 * c->bgr_slot_bytes, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
     uint8_t* pyr0 = c->d_pyr + (size_t)slot0 * g.pyr_slot_bytes;
     VsDevImg prev{pyr0 + g.lv[0].img_off, g.lv[0].w, g.lv[0].h, g.lv[0].pitch, n, (int64_t)g.pyr_slot_bytes};
+    if (c->pc_ready) for (int i = 0; i < n; i++) c->pc_valid[slot0 + i] = 0;   // the spectra follow the pyramids
     VS_TRY(vsk_bgr2gray(ctx, bgr, prev));
     for (int l = 1; l < g.levels; l++) {
         VsDevImg cur{pyr0 + g.lv[l].img_off, g.lv[l].w, g.lv[l].h, g.lv[l].pitch, n, (int64_t)g.pyr_slot_bytes};
@@ -362,6 +430,7 @@ int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_
     a.res_scratch = c->d_res_scratch;
     a.force_threads = 0;
     a.dbg_clock = c->d_dbg_clock;
+    if (c->params.phase_correlate) VS_TRY(phase_seed(c, pairs, c->d_pairs, n, 0, &a.init_T));
     if (c->d_dbg_count)   // -1 marks levels a pair never reached
         VS_CUDA(ctx, cudaMemsetAsync(c->d_dbg_count, 0xFF, (size_t)c->max_pairs * 2 * c->g.levels * sizeof(int32_t), ctx->stream));
     VS_TRY(vsk_solve_pairs(ctx, c->g, a));
@@ -401,6 +470,8 @@ int vs_clip_align_async(vs_clip* c, const vs_pair* pairs, int n, int base, int l
     cudaStream_t s = c->solve_stream[lane];
     // the solve follows everything enqueued on the context stream so far (pyramids, keyframe features, the pair list)
     VS_CUDA(ctx, cudaMemcpyAsync(c->d_pairs + base, pairs, (size_t)n * sizeof(vs_pair), cudaMemcpyHostToDevice, ctx->stream));
+    const double* init_T = nullptr;
+    if (c->params.phase_correlate) VS_TRY(phase_seed(c, pairs, c->d_pairs + base, n, base, &init_T));
     VS_CUDA(ctx, cudaEventRecord(c->ev_ready[lane], ctx->stream));
     VS_CUDA(ctx, cudaStreamWaitEvent(s, c->ev_ready[lane], 0));
     VsSolveArgs a;
@@ -414,6 +485,7 @@ int vs_clip_align_async(vs_clip* c, const vs_pair* pairs, int n, int base, int l
     a.pos_scratch = c->d_pos_scratch ? c->d_pos_scratch + (size_t)base * 4 * c->g.max_tiles : nullptr;
     a.res_scratch = c->d_res_scratch ? c->d_res_scratch + (size_t)base * 2 * c->g.max_tiles : nullptr;
     a.force_threads = 256;            // all lanes must fit on the GPU together: three CTAs per SM
+    a.init_T = init_T;
     cudaStream_t main_stream = ctx->stream;
     ctx->stream = s;
     int r = vsk_solve_pairs(ctx, c->g, a);
@@ -679,6 +751,18 @@ int vs_clip_get_warpdiff(vs_clip* c, int pair, int level, int axis, uint16_t* ou
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
     VS_CUDA(ctx, cudaMemcpyAsync(out, c->d_dbg_wd + ((size_t)pair * 2 + axis) * c->g.total_tiles + L.tile_off,
                                  (size_t)L.ntiles * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VS_OK;
+}
+
+int vs_clip_get_phase(vs_clip* c, int pair, double* out3)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, c->pc_ready && c->params.phase_correlate, "clip_get_phase: the last align call did not use phase_correlate");
+    VS_REQUIRE(ctx, pair >= 0 && pair < c->last_pairs && out3, "clip_get_phase: bad arguments");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpyAsync(out3, c->d_pc_phase + (size_t)pair * 3, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VS_OK;
 }

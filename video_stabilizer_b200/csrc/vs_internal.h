@@ -110,7 +110,28 @@ struct VsSolveArgs {
     uint16_t* pos_scratch;    // [pair][4][max_tiles] selection scratch in global memory, or null (shared memory)
     float* res_scratch;       // [pair][2][max_tiles] signed residual of every tile from the warp-diff pass, or null
     int force_threads;        // 0 = CTA size by pair count; 256 when several launches must be resident together
+    const double* init_T = nullptr;   // [pair][2] initial (TX, TY) at the coarsest level (phase-correlation seed), or null
 };
+
+// ---- phase-correlation initialiser (vs_phasecorr.cu; alignment.cpp:225-229, 369-388)
+struct VsPhasePlan {
+    int w = 0, h = 0, pitch = 0;      // the level-2 image
+    int M = 0, N = 0, Kh = 0;         // DFT size (getOptimalDFTSize of h, w) and N/2+1
+    double* d_tw = nullptr;           // N + M twiddles (cos, -sin), interleaved
+    double* d_rows = nullptr;         // [slot][h][Kh] complex: row transforms
+    double* d_spec = nullptr;         // [slot][M][Kh] complex: spectrum of the padded image
+    double* d_cross = nullptr;        // [pair][M][Kh] complex: normalised cross-power spectrum
+    double* d_inv = nullptr;          // [pair][M][Kh] complex: after the inverse column pass
+    double* d_surf = nullptr;         // [pair][M][N]: correlation surface (unshifted)
+};
+int vs_optimal_dft_size(int n);
+void vs_phase_twiddles(int n, double* out2);
+// spectra of the listed slots (images at d_img_base + slot * slot_bytes, rows plan.pitch bytes apart)
+int vsk_phase_forward(vs_ctx*, const VsPhasePlan& p, const uint8_t* d_img_base, size_t slot_bytes,
+                      const int32_t* d_slots, int nslots);
+// d_phase [n][3] = shift x, shift y, response (or null); d_init [n][2] = the seed (TX, TY) of the solver (or null)
+int vsk_phase_pairs(vs_ctx*, const VsPhasePlan& p, const vs_pair* d_pairs, int n, double threshold, float scale,
+                    double* d_phase, double* d_init);
 
 int vsk_keyframe_features(vs_ctx*, const VsClipGeom& g, const uint8_t* d_pyr, const int32_t* d_slots,
                           int n_slots, uint32_t* d_kp, float4* d_jac);

@@ -599,6 +599,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 
     if (tid == 0) {
         sh.T[0] = sh.T[1] = sh.T[2] = sh.T[3] = 0.0;
+        if (a.init_T) { sh.T[2] = a.init_T[(size_t)pair * 2]; sh.T[3] = a.init_T[(size_t)pair * 2 + 1]; }   // alignment.cpp:379-387
         sh.status = 1;
         if (a.out_iters) for (int l = 0; l < g.levels; l++) a.out_iters[(size_t)pair * g.levels + l] = 0;
     }

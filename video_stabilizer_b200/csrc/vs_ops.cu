@@ -4,6 +4,8 @@
 // the result back before returning; with VS_MEM_DEVICE it only enqueues the kernel.
 #include "vs_internal.h"
 
+#include <vector>
+
 int vs_scratch_reserve_public(vs_ctx* ctx, size_t bytes);
 
 namespace {
@@ -99,6 +101,52 @@ int vs_bgr2gray_u8(vs_ctx* ctx, const vs_img* bgr, const vs_img* gray, int mem)
     VS_TRY(vsk_bgr2gray(ctx, din, dout));
     VS_TRY(st.img_out(dout, gray, 1, 1));
     return st.finish();
+}
+
+int vs_phase_correlate_u8(vs_ctx* ctx, const vs_img* src1, const vs_img* src2, double* out3, int mem)
+{
+    if (!ctx) return VS_ERR_INVALID;
+    VS_TRY(check_mem(ctx, mem)); VS_TRY(check_img(ctx, src1, "phase_correlate src1")); VS_TRY(check_img(ctx, src2, "phase_correlate src2"));
+    VS_REQUIRE(ctx, out3, "phase_correlate: out3 is NULL");
+    VS_REQUIRE(ctx, src1->width == src2->width && src1->height == src2->height && src1->width > 0 && src1->height > 0,
+               "phase_correlate: the images must have one non-empty size");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int w = src1->width, h = src1->height;
+    VsPhasePlan p;
+    p.w = w; p.h = h; p.pitch = w;
+    p.M = vs_optimal_dft_size(h); p.N = vs_optimal_dft_size(w); p.Kh = p.N / 2 + 1;
+    const size_t spec = (size_t)p.M * p.Kh * 2 * sizeof(double);
+    // one allocation: twiddles | row transforms x2 | spectra x2 | cross | inverse | surface | result | images | slots, pair
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += vs_align_up(bytes, 256); return o; };
+    const size_t o_tw = take((size_t)(p.N + p.M) * 16), o_rows = take((size_t)2 * h * p.Kh * 16), o_spec = take(2 * spec),
+                 o_cross = take(spec), o_inv = take(spec), o_surf = take((size_t)p.M * p.N * 8), o_res = take(3 * 8),
+                 o_img = take((size_t)2 * w * h), o_idx = take(64);
+    uint8_t* base = nullptr;
+    VS_CUDA(ctx, cudaMalloc((void**)&base, off));
+    p.d_tw = (double*)(base + o_tw); p.d_rows = (double*)(base + o_rows); p.d_spec = (double*)(base + o_spec);
+    p.d_cross = (double*)(base + o_cross); p.d_inv = (double*)(base + o_inv); p.d_surf = (double*)(base + o_surf);
+    std::vector<double> tw((size_t)(p.N + p.M) * 2);
+    vs_phase_twiddles(p.N, tw.data());
+    vs_phase_twiddles(p.M, tw.data() + (size_t)p.N * 2);
+    struct { int32_t slots[2]; vs_pair pair; } idx = {{0, 1}, {0, 1, 0}};   // previous = template slot 0, current = keyframe slot 1
+    const cudaMemcpyKind kind = mem == VS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaError_t e = cudaMemcpyAsync(p.d_tw, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_idx, &idx, sizeof(idx), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(base + o_img, w, src1->data, (size_t)src1->stride, w, h, kind, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(base + o_img + (size_t)w * h, w, src2->data, (size_t)src2->stride, w, h, kind, ctx->stream);
+    int r = e == cudaSuccess ? VS_OK : vs_set_error(ctx, VS_ERR_CUDA, "phase_correlate: copy failed: %s", cudaGetErrorString(e));
+    if (r == VS_OK) r = vsk_phase_forward(ctx, p, base + o_img, (size_t)w * h, (const int32_t*)(base + o_idx), 2);
+    if (r == VS_OK) r = vsk_phase_pairs(ctx, p, (const vs_pair*)(base + o_idx + 8), 1, 0.0, 1.0f, (double*)(base + o_res), nullptr);
+    if (r == VS_OK) {
+        e = cudaMemcpyAsync(out3, base + o_res, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) r = vs_set_error(ctx, VS_ERR_CUDA, "phase_correlate: %s", cudaGetErrorString(e));
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(base);
+    return r;
 }
 
 int vs_pyr_down_u8(vs_ctx* ctx, const vs_img* in, const vs_img* out, int mem)

@@ -149,6 +149,18 @@ def BGR2Gray(bgr: np.ndarray, ctx: Context | None = None) -> np.ndarray:
     return out
 
 
+def PhaseCorrelate(src1: np.ndarray, src2: np.ndarray, ctx: Context | None = None):
+    """cv::phaseCorrelate(src1, src2, noArray(), &response) as called at alignment.cpp:374 (u8-valued images taken
+    as CV_32F): returns ((shift_x, shift_y), response)."""
+    ctx = ctx or default_context()
+    a = _u8(src1)
+    b = _u8(src2)
+    out = np.zeros(3, np.float64)
+    capi.check(ctx.handle, ctx.lib.vs_phase_correlate_u8(ctx.handle, C.byref(capi.img_of(a)), C.byref(capi.img_of(b)),
+                                                         capi.ptr(out), capi.VS_MEM_HOST), "vs_phase_correlate_u8")
+    return (float(out[0]), float(out[1])), float(out[2])
+
+
 # NOTE: arrays are bound to locals before their address is taken: a descriptor only holds
 # the raw pointer, so a temporary contiguous copy must outlive the call.
 def PyrDown(input: np.ndarray, output: np.ndarray, ctx: Context | None = None) -> bool:
