@@ -153,7 +153,7 @@ def test_phase_correlate_operator(gpu, ob):
     a, b = big[10:280, 20:500], big[13:283, 15:495]
     (sx, sy), resp = ip.PhaseCorrelate(a, b, gpu)
     assert np.array_equal(np.array([sx, sy, resp]), ob.phase_correlate_u8(a, b))
-    assert abs(sx - (-5)) < 0.01 and abs(sy - 3) < 0.01 and resp > 0.9
+    assert abs(sx - 5) < 0.01 and abs(sy + 3) < 0.01 and resp > 0.9   # content moved by (+5, -3)
 
 
 @pytest.mark.parametrize("w,h,n,seed,step", [(320, 180, 8, 0, 2.0), (640, 360, 6, 1, 9.0), (250, 141, 5, 2, 5.0)])
