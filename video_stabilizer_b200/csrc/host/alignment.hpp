@@ -10,8 +10,8 @@
 #include "imgproc.hpp"
 
 struct VideoAlignerParams {
-    // Initialise from cv::phaseCorrelate on pyramid level 2.  Off by default upstream; this
-    // implementation does not provide it: AlignNextFrame returns false when it is set.
+    // Initialise from cv::phaseCorrelate on pyramid level 2 (alignment.cpp:369-388).  Off by default
+    // upstream; here it runs on the device (vs_phasecorr.cu).
     bool phase_correlate = false;
     double phase_correlate_threshold = 0.5;
 
