@@ -186,8 +186,8 @@ def test_clip_stabilizer_equals_frame_by_frame(host, ob, chunks):
         assert np.array_equal(again[0], got[0])
 
 
-@pytest.mark.parametrize("chunks", [(160,), (139, 150), (130, 129, 131), (300,)])
-def test_clip_stabilizer_solver_lanes_equal_frame_by_frame(host, chunks):
+@pytest.mark.parametrize("chunks,phase", [((160,), 0), ((139, 150), 0), ((130, 129, 131), 0), ((300,), 0), ((139, 150), 1), ((40, 7), 1)])
+def test_clip_stabilizer_solver_lanes_equal_frame_by_frame(host, chunks, phase):
     """Device-resident chunks of >= 128 pairs run as 2-4 pieces on the clip's solver lanes (the solve of one piece
     beside the pyramids / warps of the others): the frames must still be those of n processFrame() calls, bit for bit,
     whatever the parity of the chunk's first frame."""
@@ -196,6 +196,7 @@ def test_clip_stabilizer_solver_lanes_equal_frame_by_frame(host, chunks):
     w, h, n = 320, 180, sum(chunks)
     frames = _clip(w, h, n, 5, step=2.0)
     p = host.stab_params_default()
+    p.aligner.phase_correlate = phase      # the seed kernels run on the context stream ahead of each lane's solve
     seq = host.VideoStabilizer(p, 0)
     want = [f for f in (seq.processFrame(f) for f in frames) if f is not None]
     cs = host.ClipStabilizer(w, h, max(chunks), p, 0)
@@ -227,8 +228,8 @@ def test_clip_stabilizer_records(host, ob):
     assert len(corr) == len(out) == n - 10
 
 
-@pytest.mark.parametrize("workers", [1, 2, 3])
-def test_multi_gpu_stabilizer_equals_single_stream(host, workers):
+@pytest.mark.parametrize("workers,phase", [(1, 0), (2, 0), (3, 0), (2, 1)])
+def test_multi_gpu_stabilizer_equals_single_stream(host, workers, phase):
     """Frame-chunk partition of one video over several workers (here: contexts on one device; on a
     multi-GPU box, one per device) with the transforms gathered to the host and the sequential
     smoother run there: the output equals the single-stream ClipStabilizer bit for bit."""
@@ -237,6 +238,7 @@ def test_multi_gpu_stabilizer_equals_single_stream(host, workers):
     frames = _clip(w, h, n, 31, step=3.0)
     p = host.stab_params_default()
     p.crop_pixels = 8
+    p.aligner.phase_correlate = phase
     cs = host.ClipStabilizer(w, h, n, p, 0)
     want = cs.feed(frames)
     meas_want, ok_want, _ = cs.last_records(n)
