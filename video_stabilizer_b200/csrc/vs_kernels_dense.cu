@@ -447,7 +447,8 @@ k_bgr_warp(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src
            int dst_x0, int dst_y0, int src_al4, int dst_al4)
 {
     const int xo = 4 * (blockIdx.x * WQ_THREADS + threadIdx.x);
-    if (xo >= dw) return;
+    const int lane = threadIdx.x & 31;
+    const int npx = max(0, min(4, dw - xo));                          // threads past the row stay for the warp-wide steps below
     const int b = blockIdx.z;
     const int slot = slots ? slots[b] : b;
     const uint8_t* src = src_base + (size_t)slot * src_bs;
@@ -461,7 +462,6 @@ k_bgr_warp(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src
         fx[j] = __fmul_rn(f00, xf);
         gx[j] = __fmul_rn(f10, xf);
     }
-    const int npx = min(4, dw - xo);
     constexpr int C0 = MODE == VS_WARP_FLOAT_BILINEAR ? 0 : -1;       // first tap column / row relative to (ix, iy)
     constexpr int NT = MODE == VS_WARP_FLOAT_BILINEAR ? 2 : 4;        // taps per axis
     constexpr int NB = 3 * (NT + 3);                                  // source bytes of a row of a regular group
@@ -544,10 +544,29 @@ k_bgr_warp(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src
                 px[j] = wq_pack_bgr(bits[0], bits[1], bits[2]);
             }
 #undef VS_TAPF
-        } else {
-            for (int j = 0; j < npx; j++)
-                px[j] = bgr_warp_pixel<MODE, BORDER>(src, src_stride, w, h, ix[j], iy[j], rx[j], ry[j]);
         }
+        // Groups that are not regular (typically one per warp where the row of taps changes, a few at the image borders) are
+        // done by the whole warp, one group at a time: lane l takes pixel l & 3 of the group (eight lanes compute the same
+        // pixel — same instructions, no divergence), so such a group costs the warp one general pixel instead of four.
+        unsigned todo = __ballot_sync(0xffffffffu, !regular && npx > 0);
+        while (todo) {
+            const int owner = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int j = lane & 3;
+            int gix = 0, giy = 0;
+            float grx = 0.0f, gry = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int tix = __shfl_sync(0xffffffffu, ix[q], owner), tiy = __shfl_sync(0xffffffffu, iy[q], owner);
+                const float trx = __shfl_sync(0xffffffffu, rx[q], owner), try_ = __shfl_sync(0xffffffffu, ry[q], owner);
+                if (q == j) { gix = tix; giy = tiy; grx = trx; gry = try_; }
+            }
+            const uint32_t res = bgr_warp_pixel<MODE, BORDER>(src, src_stride, w, h, gix, giy, grx, gry);
+            const uint32_t r0 = __shfl_sync(0xffffffffu, res, 0), r1 = __shfl_sync(0xffffffffu, res, 1),
+                           r2 = __shfl_sync(0xffffffffu, res, 2), r3 = __shfl_sync(0xffffffffu, res, 3);
+            if (lane == owner) { px[0] = r0; px[1] = r1; px[2] = r2; px[3] = r3; }
+        }
+        if (npx == 0) continue;
         uint8_t* d = dst_base + (size_t)b * dst_bs + (size_t)yo * dst_stride + 3 * xo;
         if (npx == 4 && dst_al4) {
             uint32_t* dw32 = reinterpret_cast<uint32_t*>(d);
