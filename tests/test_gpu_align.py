@@ -156,6 +156,37 @@ def test_phase_correlate_operator(gpu, ob):
     assert abs(sx - 5) < 0.01 and abs(sy + 3) < 0.01 and resp > 0.9   # content moved by (+5, -3)
 
 
+def test_phase_correlate_errors_are_reported(gpu):
+    import ctypes as C
+    from video_stabilizer_b200 import _capi as capi
+    from video_stabilizer_b200.clip import Clip, pairs_for_frames
+    lib = gpu.lib
+    a, b = np.zeros((16, 24), np.uint8), np.zeros((16, 20), np.uint8)
+    out = np.zeros(3)
+    r = lib.vs_phase_correlate_u8(gpu.handle, C.byref(capi.img_of(a)), C.byref(capi.img_of(b)), capi.ptr(out), capi.VS_MEM_HOST)
+    assert r == -1 and b"one non-empty size" in lib.vs_last_error(gpu.handle)
+    r = lib.vs_phase_correlate_u8(gpu.handle, C.byref(capi.img_of(a)), C.byref(capi.img_of(a)), None, capi.VS_MEM_HOST)
+    assert r == -1
+    # the tap needs an align call made with phase_correlate on
+    clip = Clip(64, 48, 2, debug=True, ctx=gpu)
+    assert lib.vs_clip_get_phase(clip.handle, 0, capi.ptr(out)) == -1
+    clip.close()
+    # level 2 must exist (alignment.hpp:69 indexes it unconditionally): a 2-level pyramid is refused, not read out of bounds
+    pg = capi.VsAlignParams()
+    capi.load().vs_align_params_default(pg)
+    pg.phase_correlate = 1
+    pg.pyramid_min_width, pg.pyramid_min_height = 40, 30
+    clip = Clip(96, 64, 2, params=pg, ctx=gpu)
+    assert clip.levels == 2
+    clip.upload(0, np.zeros((2, 64, 96, 3), np.uint8))
+    clip.build_pyramids(0, 2)
+    pairs, keys = pairs_for_frames(0, 2)
+    clip.build_keyframes(keys)
+    with pytest.raises(Exception, match="level 2"):
+        clip.align(pairs)
+    clip.close()
+
+
 @pytest.mark.parametrize("w,h,n,seed,step", [(320, 180, 8, 0, 2.0), (640, 360, 6, 1, 9.0), (250, 141, 5, 2, 5.0)])
 def test_clip_alignment_with_phase_correlate_matches_oracle(gpu, ob, w, h, n, seed, step):
     """VideoAlignerParams::phase_correlate (alignment.cpp:369-388): the seed, and everything the solver derives from
