@@ -154,6 +154,13 @@ def test_phase_correlate_operator(gpu, ob):
     (sx, sy), resp = ip.PhaseCorrelate(a, b, gpu)
     assert np.array_equal(np.array([sx, sy, resp]), ob.phase_correlate_u8(a, b))
     assert abs(sx - 5) < 0.01 and abs(sy + 3) < 0.01 and resp > 0.9   # content moved by (+5, -3)
+    # very wide / very tall images: twiddle and row tables beyond the default 48 KB of dynamic shared memory
+    for (hh, ww) in ((48, 1536), (3072, 32)):
+        big = rng.integers(0, 256, (hh + 8, ww + 8), dtype=np.uint8)
+        a, b = np.ascontiguousarray(big[2:2 + hh, 3:3 + ww]), np.ascontiguousarray(big[4:4 + hh, 1:1 + ww])
+        (sx, sy), resp = ip.PhaseCorrelate(a, b, gpu)
+        assert np.array_equal(np.array([sx, sy, resp]), ob.phase_correlate_u8(a, b)), (hh, ww)
+        assert abs(sx - 2) < 0.1 and abs(sy + 2) < 0.1
 
 
 def test_phase_correlate_errors_are_reported(gpu):
