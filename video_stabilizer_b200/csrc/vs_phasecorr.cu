@@ -16,7 +16,6 @@
 
 #include <float.h>
 #include <math.h>
-#include <vector>
 
 namespace {
 
