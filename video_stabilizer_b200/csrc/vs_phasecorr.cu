@@ -20,9 +20,9 @@
 namespace {
 
 constexpr int PC_THREADS = 256;
-constexpr int PC_FWD_ROWS = 4;     // image rows per CTA of the forward row pass (they share every twiddle load)
-constexpr int PC_INV_ROWS = 2;     // surface rows per CTA of the inverse row pass
-constexpr int PC_COL_M = 2;        // outputs per thread of a column pass (they share every load of the input column)
+constexpr int PC_FWD_ROWS = 8;     // image rows per CTA of the forward row pass (they share every twiddle load)
+constexpr int PC_INV_ROWS = 4;     // surface rows per CTA of the inverse row pass
+constexpr int PC_COL_M = 4;        // outputs per thread of a column pass (they share every load of the input column)
 
 // forward row pass: F[slot][r][k] = sum_{n<w} x[r][n] tw_N[(k n) mod N], k < N/2+1 (real input, Hermitian half)
 __global__ void __launch_bounds__(PC_THREADS)
