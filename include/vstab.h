@@ -96,6 +96,12 @@ int vs_memcpy_d2h(vs_ctx* ctx, void* dst, const void* src, size_t bytes);  /* as
  * stride in bytes.  gray: u8. */
 int vs_bgr2gray_u8(vs_ctx*, const vs_img* bgr, const vs_img* gray, int mem);
 
+/* Fused ingest: cv::cvtColor(BGR2GRAY) (alignment.cpp:212) and the first PyrDown
+ * (alignment.cpp:220-223) in ONE pass over the interleaved frame: gray0 = BGR2GRAY(bgr), gray1 = pyr_down(gray0),
+ * bit-identical to vs_bgr2gray_u8 followed by vs_pyr_down_u8.  The single fused kernel runs when width % 16 == 0,
+ * gray1 is (width/2) x (height/2) and the rows are 16-byte aligned; other geometries run the two kernels. */
+int vs_ingest_bgr_u8(vs_ctx*, const vs_img* bgr, const vs_img* gray0, const vs_img* gray1, int mem);
+
 /* pyr_down(), generators.cpp:56-92 via PyrDown(), imgproc.cpp:108-114.  The output
  * extent defines the work; input is read through repeat-edge. */
 int vs_pyr_down_u8(vs_ctx*, const vs_img* in, const vs_img* out, int mem);

@@ -17,6 +17,37 @@ def test_bgr2gray(gpu, ob, h, w):
     assert np.array_equal(ip.BGR2Gray(bgr, gpu), ob.bgr2gray(bgr))
 
 
+# the fused kernel runs for widths that are multiples of 16 (strips of 72 rows: sizes around the strip boundaries, odd
+# heights, one and several column warps, partial warps); the other sizes take the two-kernel path behind the same entry
+INGEST_SIZES = [(2, 16), (3, 16), (72, 32), (73, 48), (74, 512), (75, 528), (143, 1040), (144, 16), (145, 64), (146, 80),
+                (180, 320), (360, 640), (720, 1280), (1080, 1920), (1081, 1936), (2160, 3840), (135, 240), (131, 97), (67, 120)]
+
+
+@pytest.mark.parametrize("h,w", INGEST_SIZES)
+def test_ingest_bgr_gray_l1(gpu, ob, h, w):
+    """BGR -> gray + first pyramid level in one kernel == cvtColor then pyr_down of the oracle, bit for bit."""
+    from video_stabilizer_b200 import imgproc as ip
+    rng = np.random.default_rng(h * 4099 + w)
+    bgr = noise_image(rng, h, w, 3)
+    g0, g1 = ip.IngestBGR(bgr, gpu)
+    want0 = ob.bgr2gray(bgr)
+    assert np.array_equal(g0, want0)
+    assert np.array_equal(g1, ob.pyr_down(want0, w // 2, h // 2))
+
+
+def test_ingest_extreme_values(gpu, ob):
+    """saturated channels exercise the top of the 24-bit gray accumulator and of the 16-bit pyramid sums"""
+    from video_stabilizer_b200 import imgproc as ip
+    h, w = 150, 96
+    for fill in ((255, 255, 255), (0, 0, 0), (255, 0, 0), (0, 255, 0), (0, 0, 255)):
+        bgr = np.empty((h, w, 3), np.uint8)
+        bgr[:] = fill
+        bgr[::7, ::5] = 255 - np.array(fill, np.uint8)
+        g0, g1 = ip.IngestBGR(bgr, gpu)
+        want0 = ob.bgr2gray(bgr)
+        assert np.array_equal(g0, want0) and np.array_equal(g1, ob.pyr_down(want0, w // 2, h // 2))
+
+
 @pytest.mark.parametrize("h,w", SIZES)
 def test_pyr_down(gpu, ob, h, w):
     from video_stabilizer_b200 import imgproc as ip

@@ -59,6 +59,7 @@ SYMBOLS = {
     "vs_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "vs_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "vs_bgr2gray_u8": (C.c_int, [_P, _IMG, _IMG, C.c_int]),
+    "vs_ingest_bgr_u8": (C.c_int, [_P, _IMG, _IMG, _IMG, C.c_int]),
     "vs_pyr_down_u8": (C.c_int, [_P, _IMG, _IMG, C.c_int]),
     "vs_grad_xy_u8_f32": (C.c_int, [_P, _IMG, _IMG, _IMG, C.c_int]),
     "vs_grad_argmax_tile_size": (C.c_int, [C.c_int, C.c_int]),

@@ -15,6 +15,7 @@ struct VideoAligner::Impl {
     long frames_since_reset = 0;   // frame n sits in slot n % capacity; odd n are keyframes
     int last_slot = -1;
     int generation = 0;            // bumped whenever the ring is re-created
+    bool force_reinit = false;     // a keyframe / device failure: the next frame re-creates the ring (upstream's LastWidth = -1)
 
     ~Impl();
     void ensure_context();

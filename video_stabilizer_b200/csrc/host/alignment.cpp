@@ -55,8 +55,9 @@ bool VideoAligner::Impl::ensure_clip(int w, int h, const VideoAlignerParams& par
 {
     vs_align_params cp;
     vstab::to_c_params(params, &cp);
-    if (clip && w == width && h == height) return vs_clip_set_params(clip, &cp) == VS_OK;
+    if (clip && !force_reinit && w == width && h == height) return vs_clip_set_params(clip, &cp) == VS_OK;
     destroy_clip();
+    force_reinit = false;
     width = w; height = h;
     frames_since_reset = 0;
     last_slot = -1;
@@ -90,6 +91,8 @@ bool VideoAligner::AlignNextFrame(const cv::Mat& frame, SimilarityTransform& tra
     if (vs_clip_upload(s.clip, slot, 1, frame.data, (int64_t)frame.step[0], (int64_t)frame.step[0] * frame.rows, VS_MEM_HOST) != VS_OK ||
         vs_clip_build_pyramids(s.clip, slot, 1) != VS_OK) {
         std::cerr << "VideoAligner: " << vs_last_error(s.ctx) << std::endl;
+        s.last_slot = -1;          // this frame is not in the ring: VideoStabilizer keeps a host copy of it
+        s.force_reinit = true;
         return false;
     }
     const int prev = s.last_slot;
@@ -104,7 +107,7 @@ bool VideoAligner::AlignNextFrame(const cv::Mat& frame, SimilarityTransform& tra
         const int32_t ks = slot;
         if (vs_clip_build_keyframes(s.clip, &ks, 1) != VS_OK) {
             std::cerr << "VideoAligner: " << vs_last_error(s.ctx) << std::endl;
-            s.width = s.height = -1;   // force re-initialisation, like upstream's LastWidth = -1
+            s.force_reinit = true;     // force re-initialisation, like upstream's LastWidth = -1 (the ring keeps its true size)
             return false;
         }
     }

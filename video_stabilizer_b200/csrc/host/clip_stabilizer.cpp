@@ -27,7 +27,6 @@ ClipStabilizer::ClipStabilizer(int device, int width, int height, int chunk_fram
         throw std::runtime_error(msg);
     }
     m_pairs.reserve(chunk_frames); m_T.resize((size_t)chunk_frames * 4); m_status.resize(chunk_frames); m_slots.reserve(chunk_frames);
-    if (const char* e = getenv("VSTAB_LANES")) m_lanes = std::max(1, atoi(e));   // A/B measurements
 }
 
 ClipStabilizer::~ClipStabilizer()

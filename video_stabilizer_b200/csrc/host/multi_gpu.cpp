@@ -34,24 +34,33 @@ MultiGpuStabilizer::MultiGpuStabilizer(const std::vector<int>& devices, int widt
     // a chunk holds at most ceil(n / workers) + 2 frames (even alignment) plus the halo frame
     const int capacity = (max_frames + workers - 1) / workers + 3;
     m_workers.resize(workers);
-    for (int i = 0; i < workers; i++) {
-        Worker& wk = m_workers[i];
-        wk.device = devices[i];
-        wk.capacity = capacity;
-        if (vs_ctx_create(wk.device, &wk.ctx) != VS_OK)
-            throw std::runtime_error(std::string("MultiGpuStabilizer: cannot create a GPU context: ") + vs_last_error(nullptr));
-        if (vs_clip_create(wk.ctx, width, height, capacity, capacity, &cp, 0, &wk.clip) != VS_OK)
-            throw std::runtime_error(std::string("MultiGpuStabilizer: ") + vs_last_error(wk.ctx));
+    try {
+        for (int i = 0; i < workers; i++) {
+            Worker& wk = m_workers[i];
+            wk.device = devices[i];
+            wk.capacity = capacity;
+            if (vs_ctx_create(wk.device, &wk.ctx) != VS_OK)
+                throw std::runtime_error(std::string("MultiGpuStabilizer: cannot create a GPU context: ") + vs_last_error(nullptr));
+            if (vs_clip_create(wk.ctx, width, height, capacity, capacity, &cp, 0, &wk.clip) != VS_OK)
+                throw std::runtime_error(std::string("MultiGpuStabilizer: ") + vs_last_error(wk.ctx));
+        }
+    } catch (...) {
+        release();      // the destructor does not run for a partially constructed object
+        throw;
     }
 }
 
-MultiGpuStabilizer::~MultiGpuStabilizer()
+void MultiGpuStabilizer::release()
 {
     for (Worker& wk : m_workers) {
         if (wk.clip) vs_clip_destroy(wk.clip);
         if (wk.ctx) vs_ctx_destroy(wk.ctx);
+        wk.clip = nullptr;
+        wk.ctx = nullptr;
     }
 }
+
+MultiGpuStabilizer::~MultiGpuStabilizer() { release(); }
 
 int MultiGpuStabilizer::stabilize(const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, uint8_t* out,
                                   int64_t out_frame_stride)

@@ -58,6 +58,7 @@ private:
     std::vector<Worker> m_workers;
     std::vector<SimilarityTransform> m_meas;
     std::vector<uint8_t> m_ok;
+    void release();
 };
 
 }  // namespace vstab

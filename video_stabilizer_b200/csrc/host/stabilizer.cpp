@@ -70,8 +70,10 @@ cv::Mat VideoStabilizer::processFrame(const cv::Mat& inputFrame)
     ++m_frameIndex;
     VideoAligner::Impl& ring = *aligner.impl_;
 
-    // A frame-size change re-creates the ring: rescue the frames still waiting in it first.
-    if (ring.clip && (inputFrame.cols != ring.width || inputFrame.rows != ring.height)) {
+    // A frame-size change (or a forced re-initialisation after a failure) re-creates the ring: rescue the frames still
+    // waiting in it first.  ring.width / ring.height are always the true size of the frames in the ring.
+    if (ring.clip && ring.width > 0 && ring.height > 0 &&
+        (ring.force_reinit || inputFrame.cols != ring.width || inputFrame.rows != ring.height)) {
         for (Pending& p : m_frameBuffer) {
             if (p.generation != ring.generation || !p.host.empty()) continue;
             p.host = cv::Mat(ring.height, ring.width, CV_8UC3);
@@ -86,7 +88,8 @@ cv::Mat VideoStabilizer::processFrame(const cv::Mat& inputFrame)
     Pending incoming;
     incoming.slot = ring.last_slot;
     incoming.generation = ring.generation;
-    if (!ring.clip) incoming.host = inputFrame.clone();   // device error: keep a host copy so the stream continues
+    // device error (no ring, or this frame never reached it): keep a host copy so the stream continues
+    if (!ring.clip || incoming.slot < 0) incoming.host = inputFrame.clone();
     m_frameBuffer.push_back(incoming);
 
     SimilarityTransform correction;

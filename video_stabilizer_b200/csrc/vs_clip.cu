@@ -18,11 +18,10 @@
 #include <vector>
 
 struct vs_clip {
-    // TMA descriptor of the BGR store viewed as u32 [slot][row][pitch/4], box {108 words, 20 rows, 1}:
-    // the cv-exact warp fetches a tile's source box with one cp.async.bulk.tensor (first member: 64-byte aligned)
-    CUtensorMap bgr_map;
-    CUtensorMap bgr_map_rows;         // box of the row-group kernel (160 pixels x 28 rows)
-    bool bgr_map_ok = false, bgr_map_rows_ok = false;
+    // TMA descriptor of the BGR store viewed as u32 [slot][row][pitch/4], box {120 words = 160 pixels, 28 rows, 1}: the
+    // cv-exact warp fetches a tile's source box with one cp.async.bulk.tensor (first member: 64-byte aligned)
+    CUtensorMap bgr_map_rows;
+    bool bgr_map_rows_ok = false;
     int32_t* d_warp_tab = nullptr;    // fixed-point column / row tables of the row-group warp, capacity images
     vs_ctx* ctx = nullptr;
     int w = 0, h = 0, capacity = 0, max_pairs = 0, flags = 0;
@@ -125,47 +124,33 @@ PFN_cuTensorMapEncodeTiled tensor_map_encoder()
 
 void build_bgr_tensor_map(vs_clip* c)
 {
-    c->bgr_map_ok = false;
-    const char* env = getenv("VSTAB_WARP_TMA");
-    if (env && atoi(env) == 0) return;
+    c->bgr_map_rows_ok = false;
     PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
     if (!enc || c->bgr_pitch % 16 != 0 || c->bgr_slot_bytes % 16 != 0) return;
-    if ((int)(c->bgr_pitch / 4) < VS_WARP_TMA_BOX_WORDS || c->h < VS_WARP_TMA_BOX_ROWS) return;
-    const cuuint64_t dims[3] = {(cuuint64_t)(c->bgr_pitch / 4), (cuuint64_t)c->h, (cuuint64_t)c->capacity};
-    const cuuint64_t strides[2] = {(cuuint64_t)c->bgr_pitch, (cuuint64_t)c->bgr_slot_bytes};
-    const cuuint32_t box[3] = {(cuuint32_t)VS_WARP_TMA_BOX_WORDS, (cuuint32_t)VS_WARP_TMA_BOX_ROWS, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&c->bgr_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->d_bgr, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    c->bgr_map_ok = (r == CUDA_SUCCESS);
-
-    // VSTAB_WARP_KERNEL=tma selects the previous (expanded-plane) kernel for A/B measurements
-    const char* kenv = getenv("VSTAB_WARP_KERNEL");
-    if (kenv && strcmp(kenv, "tma") == 0) return;
     if ((int)(c->bgr_pitch / 4) < VS_WARP_ROWS_BOX_WORDS || c->h < VS_WARP_ROWS_BOX_ROWS) return;
     if (cudaMalloc((void**)&c->d_warp_tab, vs_warp_rows_tab_ints(c->w, c->h) * c->capacity * sizeof(int32_t)) != cudaSuccess) {
         cudaGetLastError();
         c->d_warp_tab = nullptr;
         return;
     }
+    const cuuint64_t dims[3] = {(cuuint64_t)(c->bgr_pitch / 4), (cuuint64_t)c->h, (cuuint64_t)c->capacity};
+    const cuuint64_t strides[2] = {(cuuint64_t)c->bgr_pitch, (cuuint64_t)c->bgr_slot_bytes};
     const cuuint32_t box_rows[3] = {(cuuint32_t)VS_WARP_ROWS_BOX_WORDS, (cuuint32_t)VS_WARP_ROWS_BOX_ROWS, 1};
-    r = enc(&c->bgr_map_rows, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->d_bgr, dims, strides, box_rows, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&c->bgr_map_rows, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->d_bgr, dims, strides, box_rows, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     c->bgr_map_rows_ok = (r == CUDA_SUCCESS);
 }
 
-// the BGR warp of a clip: row-group kernel for the mode the stabiliser uses (cv-exact, constant border); the earlier
-// TMA-staged kernel when the clip is too small for its box; generic kernels for the other modes / borders
+// the BGR warp of a clip: row-group kernel for the mode the stabiliser uses (cv-exact, constant border); the tiled kernel
+// when the clip is too small for its TMA box; generic kernels for the other modes / borders
 int clip_warp_launch(vs_clip* c, const int32_t* d_slots, const VsWarpCoef* d_coef, const VsDevImg& dst, int crop, int mode, int border, int n)
 {
     VsDevImg src{c->d_bgr, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
     if (mode == VS_WARP_CV_EXACT_BILINEAR && border == VS_BORDER_CONSTANT0 && c->bgr_map_rows_ok && n <= c->capacity &&
         dst.w <= c->w && dst.h <= c->h)
         return vsk_bgr_warp_slots_rows(c->ctx, &c->bgr_map_rows, src, d_slots, d_coef, dst, crop, crop, c->d_warp_tab);
-    if (mode == VS_WARP_CV_EXACT_BILINEAR && border == VS_BORDER_CONSTANT0 && c->bgr_map_ok)
-        return vsk_bgr_warp_slots_tma(c->ctx, &c->bgr_map, src, d_slots, d_coef, dst, crop, crop);
     return vsk_bgr_warp_slots(c->ctx, src, d_slots, d_coef, dst, crop, crop, mode, border);
 }
 
@@ -244,6 +229,7 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
     vs_align_params P;
     if (params) P = *params; else vs_align_params_default(&P);
     VS_REQUIRE(ctx, P.max_iters >= 1, "clip_create: max_iters must be >= 1");
+    VS_REQUIRE(ctx, P.smallest_fraction >= 0.f && P.smallest_fraction <= 1.f, "clip_create: smallest_fraction must be in [0, 1]");
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
 
     vs_clip* c = new vs_clip();
@@ -274,6 +260,8 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
             toff += L.ntiles;
             g.max_tiles = L.ntiles > g.max_tiles ? L.ntiles : g.max_tiles;
             if (L.ntiles < 1) { delete c; return vs_set_error(ctx, VS_ERR_INVALID, "pyramid level %d has no tiles", l); }
+            // the solver packs a selected keypoint as tile column | tile row << 10 | offsets
+            if (L.tw > 1023 || L.th > 1023) { delete c; return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "pyramid level %d has more than 1023 tiles along an axis", l); }
         }
         g.total_tiles = toff;
         g.pyr_slot_bytes = vs_align_up(off, 256);
@@ -333,6 +321,8 @@ int vs_clip_set_params(vs_clip* c, const vs_align_params* params)
     if (!c || !params) return VS_ERR_INVALID;
     vs_ctx* ctx = c->ctx;
     VS_REQUIRE(ctx, params->max_iters >= 1, "clip_set_params: max_iters must be >= 1");
+    VS_REQUIRE(ctx, params->smallest_fraction >= 0.f && params->smallest_fraction <= 1.f,
+               "clip_set_params: smallest_fraction must be in [0, 1]");
     const int mw = c->params.pyramid_min_width, mh = c->params.pyramid_min_height;
     c->params = *params;
     c->params.pyramid_min_width = mw; c->params.pyramid_min_height = mh;
@@ -383,8 +373,16 @@ int vs_clip_build_pyramids(vs_clip* c, int slot0, int n)
     uint8_t* pyr0 = c->d_pyr + (size_t)slot0 * g.pyr_slot_bytes;
     VsDevImg prev{pyr0 + g.lv[0].img_off, g.lv[0].w, g.lv[0].h, g.lv[0].pitch, n, (int64_t)g.pyr_slot_bytes};
     if (c->pc_ready) for (int i = 0; i < n; i++) c->pc_valid[slot0 + i] = 0;   // the spectra follow the pyramids
-    VS_TRY(vsk_bgr2gray(ctx, bgr, prev));
-    for (int l = 1; l < g.levels; l++) {
+    // gray + level 1 in one pass over the BGR frame when the geometry allows it (every 16-aligned width: 720p, 1080p, 4K ...)
+    int l0 = 1;
+    if (g.levels > 1) {
+        VsDevImg lv1{pyr0 + g.lv[1].img_off, g.lv[1].w, g.lv[1].h, g.lv[1].pitch, n, (int64_t)g.pyr_slot_bytes};
+        bool fused = false;
+        VS_TRY(vsk_ingest_bgr_gray_l1(ctx, bgr, prev, lv1, &fused));
+        if (fused) { prev = lv1; l0 = 2; }
+    }
+    if (l0 == 1) VS_TRY(vsk_bgr2gray(ctx, bgr, prev));
+    for (int l = l0; l < g.levels; l++) {
         VsDevImg cur{pyr0 + g.lv[l].img_off, g.lv[l].w, g.lv[l].h, g.lv[l].pitch, n, (int64_t)g.pyr_slot_bytes};
         VS_TRY(vsk_pyr_down(ctx, prev, cur));
         prev = cur;

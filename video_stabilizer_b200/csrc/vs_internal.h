@@ -23,6 +23,9 @@ static inline VsDevImg vs_dev_img(const vs_img* im)
 // ---- dense kernels (vs_kernels_dense.cu)
 int vsk_bgr2gray(vs_ctx*, const VsDevImg& bgr, const VsDevImg& gray);
 int vsk_pyr_down(vs_ctx*, const VsDevImg& in, const VsDevImg& out);
+// fused BGR -> gray + first pyramid level (one pass over the frame); *fused = false when the geometry needs the two
+// separate kernels (width not a multiple of 16, unaligned rows, level 1 not the floor half of level 0)
+int vsk_ingest_bgr_gray_l1(vs_ctx*, const VsDevImg& bgr, const VsDevImg& gray0, const VsDevImg& gray1, bool* fused);
 int vsk_grad_xy(vs_ctx*, const VsDevImg& in, const VsDevImg& gx, const VsDevImg& gy);
 int vsk_image_warp(vs_ctx*, const VsDevImg& in, const float* d_params4, const VsDevImg& out);
 
@@ -43,12 +46,6 @@ bool vs_warp_rows_usable(const VsDevImg& src, int mode, int border);
 // same, but image b of the batch reads slot d_slots[b] of `src` (src.batch_stride apart)
 int vsk_bgr_warp_slots(vs_ctx*, const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
                        const VsDevImg& dst, int dst_x0, int dst_y0, int mode, int border);
-
-// TMA-staged form for clip-resident frames: tensor_map points to a CUtensorMap over the BGR store viewed as
-// u32 [slot][row][pitch/4] with box {108, 20, 1} (built by vs_clip.cu); mode 0, BORDER_CONSTANT0 only
-int vsk_bgr_warp_slots_tma(vs_ctx*, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,
-                           const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0);
-constexpr int VS_WARP_TMA_BOX_WORDS = 108, VS_WARP_TMA_BOX_ROWS = 20;
 
 // row-group form (the production kernel): tensor map with box {120, 28, 1} (160 pixels x 28 rows) over the same view;
 // d_tab is scratch for the per-launch fixed-point tables, vs_warp_rows_tab_ints(dst.w, dst.h) int32 per image

@@ -158,6 +158,12 @@ VS_SEL_HD void nth_element_serial(uint32_t* v, int n, int nth)
 }
 
 // selected count of alignment.cpp:464-465: (size_t)(size * fraction), float product
-VS_SEL_HD int selected_count(int n, float fraction) { return (int)(size_t)((float)n * fraction); }
+// alignment.cpp:464-465: (size_t)(N * fraction) in float; callers validate 0 <= fraction <= 1, the clamp keeps an
+// out-of-contract value from indexing past the keys
+VS_SEL_HD int selected_count(int n, float fraction)
+{
+    const int k = (int)(size_t)((float)n * fraction);
+    return k < 0 ? 0 : (k > n ? n : k);
+}
 
 }  // namespace vs_sel

@@ -221,6 +221,136 @@ k_pyr_down(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, int
         pd_strip<false, PD_ROWS, false>(src, in_stride, iw, ih, dst, out_stride, ow, oh, x4, y0, store_word);
 }
 
+// ------------------------------------------------------------------ fused ingest: BGR -> gray L0 + pyramid L1
+// cv::cvtColor(BGR2GRAY) (alignment.cpp:212) and the first PyrDown (alignment.cpp:220-223, generators.cpp:56-92) in one
+// pass over the interleaved frame: the gray level is written once and never read back (unfused, 1080p: 2.07 MB written by
+// BGR->gray and read again by pyr_down, per frame).  Register streaming, no shared memory, no barriers: a thread owns 16
+// level-0 columns (48 BGR bytes = three 16-byte loads per row, one 16-byte gray store) = 8 level-1 columns (one 8-byte
+// store per level-1 row) and walks down a strip of IG_L1_ROWS level-1 rows with a five-row window of horizontal
+// [1 4 6 4 1] sums (IDP.4A, two 16-bit sums per register, exactly as k_pyr_down_wide).  The three gray pixels a thread
+// needs from its neighbours (two on the left, one on the right) come by warp shuffle; only the first / last lane of a
+// warp fetches them from the BGR frame itself.  The loads of the next two rows are issued before the current two are
+// converted.  Gray: t = 2 (3735 B + 19235 G + 9798 R) + 32768 as two IDP.4A (weights split into high and low bytes) and one
+// multiply-add per pixel; the gray value is byte 2 of t, so four pixels are packed by three PRMTs.
+constexpr int IG_L1_ROWS = 36;          // level-1 rows per strip: 72 level-0 rows + 3 halo rows (4 % re-read)
+
+__device__ __forceinline__ uint32_t ig_t(uint32_t p)
+{
+    return __dp4a(p, 0x004C961Du, 0u) * 256u + __dp4a(p, 0x008C462Eu, 32768u);
+}
+
+// four gray pixels from 12 interleaved bytes (three words)
+__device__ __forceinline__ uint32_t ig_gray4(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    const uint32_t t0 = ig_t(w0), t1 = ig_t(__byte_perm(w0, w1, 0x0543)), t2 = ig_t(__byte_perm(w1, w2, 0x0432)), t3 = ig_t(w2 >> 8);
+    return __byte_perm(__byte_perm(t0, t1, 0x0062), __byte_perm(t2, t3, 0x0062), 0x5410);
+}
+
+struct IgRow {
+    uint4 a, b, c;      // the 48 BGR bytes of this thread's 16 pixels
+    uint2 l;            // the 8 bytes before them (first lane of a warp, not at the image edge)
+    uint32_t r;         // the 4 bytes after them (last lane of a warp, not at the image edge)
+};
+
+__device__ __forceinline__ void ig_load(const uint8_t* __restrict__ src, int64_t stride, int h, int row, int xb,
+                                        bool need_l, bool need_r, IgRow& o)
+{
+    const uint8_t* p = src + (size_t)vs_clampi(row, 0, h - 1) * stride + xb;
+    const uint4* p4 = reinterpret_cast<const uint4*>(p);
+    o.a = __ldg(p4); o.b = __ldg(p4 + 1); o.c = __ldg(p4 + 2);
+    o.l = need_l ? __ldg(reinterpret_cast<const uint2*>(p - 8)) : make_uint2(0u, 0u);
+    o.r = need_r ? __ldg(reinterpret_cast<const uint32_t*>(p + 48)) : 0u;
+}
+
+// gray of the 16 pixels (g) and the horizontal sums of the 8 level-1 outputs (hs)
+__device__ __forceinline__ void ig_convert(const IgRow& in, bool first_col, bool last_col, bool need_l, bool need_r,
+                                           uint4& g, uint32_t hs[4])
+{
+    g.x = ig_gray4(in.a.x, in.a.y, in.a.z);
+    g.y = ig_gray4(in.a.w, in.b.x, in.b.y);
+    g.z = ig_gray4(in.b.z, in.b.w, in.c.x);
+    g.w = ig_gray4(in.c.y, in.c.z, in.c.w);
+    uint32_t a16 = __shfl_up_sync(0xffffffffu, g.w, 1) >> 16;        // pixels x0-2, x0-1 of the lane to the left
+    uint32_t c8 = __shfl_down_sync(0xffffffffu, g.x, 1) & 0xffu;     // pixel x0+16 of the lane to the right
+    if (need_l) {
+        const uint32_t t0 = ig_t(__byte_perm(in.l.x, in.l.y, 0x0432)), t1 = ig_t(in.l.y >> 8);
+        a16 = __byte_perm(t0, t1, 0x0062) & 0xffffu;
+    }
+    if (need_r) c8 = ig_t(in.r) >> 16;
+    if (first_col) a16 = (g.x & 0xffu) * 0x0101u;                      // repeat-edge
+    if (last_col) c8 = g.w >> 24;
+    pd_hsum8(a16, g, c8, hs);
+}
+
+__global__ void __launch_bounds__(128)
+k_ingest_bgr_gray_l1(const uint8_t* __restrict__ bgr, int64_t bgr_stride, int64_t bgr_bs,
+                     uint8_t* __restrict__ g0, int64_t g0_stride, int64_t g0_bs,
+                     uint8_t* __restrict__ g1, int64_t g1_stride, int64_t g1_bs, int w, int h, int ow, int oh)
+{
+    // launched only when w % 16 == 0, ow == w / 2, oh == h / 2 and all rows are 16-byte (level 1: 8-byte) aligned
+    const int lane = threadIdx.x;
+    const int col = blockIdx.x * 32 + lane;                      // 16-pixel column group
+    const int ncols = w >> 4;
+    const bool live = col < ncols;
+    const int x0 = min(col, ncols - 1) << 4;                    // lanes past the row shadow the last group (shuffles need them)
+    const int strip = blockIdx.y * blockDim.y + threadIdx.y;
+    const int Y0 = strip * IG_L1_ROWS;
+    if (Y0 >= oh) return;                                        // a whole warp leaves together (one strip per warp)
+    const int Y1 = min(Y0 + IG_L1_ROWS, oh);
+    const bool last_strip = Y1 >= oh;
+    const uint8_t* src = bgr + (size_t)blockIdx.z * bgr_bs;
+    uint8_t* d0 = g0 + (size_t)blockIdx.z * g0_bs + x0;
+    uint8_t* d1 = g1 + (size_t)blockIdx.z * g1_bs + (x0 >> 1);
+    const bool first_col = x0 == 0, last_col = x0 + 16 >= w;
+    const bool need_l = lane == 0 && !first_col, need_r = lane == 31 && !last_col;
+    const int xb = x0 * 3;
+
+    // level-0 row r is written by the strip whose range [2 Y0, 2 Y1) holds it; the last strip also owns the rows below
+    // 2 oh (one row when h is odd)
+    auto store0 = [&](int r, const uint4& g) {
+        if (live && r >= 2 * Y0 && r < h && (r < 2 * Y1 || last_strip))
+            *reinterpret_cast<uint4*>(d0 + (size_t)r * g0_stride) = g;
+    };
+
+    uint32_t hA[4], hB[4], hC[4];
+    {
+        IgRow ra, rb, rc;
+        ig_load(src, bgr_stride, h, 2 * Y0 - 2, xb, need_l, need_r, ra);
+        ig_load(src, bgr_stride, h, 2 * Y0 - 1, xb, need_l, need_r, rb);
+        ig_load(src, bgr_stride, h, 2 * Y0, xb, need_l, need_r, rc);
+        uint4 g;
+        ig_convert(ra, first_col, last_col, need_l, need_r, g, hA);
+        ig_convert(rb, first_col, last_col, need_l, need_r, g, hB);
+        ig_convert(rc, first_col, last_col, need_l, need_r, g, hC);
+        store0(2 * Y0, g);
+    }
+    IgRow nd, ne;
+    ig_load(src, bgr_stride, h, 2 * Y0 + 1, xb, need_l, need_r, nd);
+    ig_load(src, bgr_stride, h, 2 * Y0 + 2, xb, need_l, need_r, ne);
+#pragma unroll 1
+    for (int y = Y0; y < Y1; y++) {
+        const IgRow rd = nd, re = ne;
+        if (y + 1 < Y1) {                                        // rows of the next iteration: in flight during this one
+            ig_load(src, bgr_stride, h, 2 * y + 3, xb, need_l, need_r, nd);
+            ig_load(src, bgr_stride, h, 2 * y + 4, xb, need_l, need_r, ne);
+        }
+        uint32_t hD[4], hE[4];
+        uint4 gd, ge;
+        ig_convert(rd, first_col, last_col, need_l, need_r, gd, hD);
+        ig_convert(re, first_col, last_col, need_l, need_r, ge, hE);
+        store0(2 * y + 1, gd);
+        store0(2 * y + 2, ge);
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = hA[k] + hE[k] + 4u * (hB[k] + hD[k]) + 6u * hC[k];
+        if (live)
+            *reinterpret_cast<uint2*>(d1 + (size_t)y * g1_stride) =
+                make_uint2(__byte_perm(v[0], v[1], 0x7531), __byte_perm(v[2], v[3], 0x7531));
+#pragma unroll
+        for (int k = 0; k < 4; k++) { hA[k] = hC[k]; hB[k] = hD[k]; hC[k] = hE[k]; }
+    }
+}
+
 // ------------------------------------------------------------------ grad_xy
 // generators.cpp:202-224: 0.5*(I(x+1,y)-I(x-1,y)), 0.5*(I(x,y+1)-I(x,y-1)), repeat-edge.
 __global__ void __launch_bounds__(128)
@@ -808,158 +938,8 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
     }
 }
 
-// ------------------------------------------------------------------ BGR warp, cv-exact, TMA-staged
-// Same tile, same sampling and the same bits as k_bgr_warp_cv_tiled, for frames that live in a
-// vs_clip (zero-padded 128-byte-pitch rows, one tensor map over [slot][row][word]): the source
-// box of a tile is fetched by ONE cp.async.bulk.tensor (TMA) instruction issued by one thread —
-// no per-thread address arithmetic, bounds tests or load instructions — and elements outside the
-// frame arrive as zeros, which is exactly BORDER_CONSTANT(0), on every edge.  The box is a fixed
-// 108 words (= 144 pixels) x 20 rows whose first pixel is a multiple of 16 (the start of a TMA box
-// must be 16-byte aligned in global memory: 16 pixels = 48 bytes); the raw bytes are then expanded
-// in shared memory into the paired-tap planes (task = box row x 4-pixel granule: 4 word loads,
-// 8 PRMT, 2 16-byte stores).  A tile whose box does not fit 144 x 20 falls back to direct loads.
-constexpr int WTM_BOX_WORDS = 108, WTM_BOX_ROWS = 20, WTM_PITCH = 144;     // pitch in staged entries (pixels)
-constexpr int WTM_GRANULES = WTM_PITCH / 4;                                 // 36 four-pixel granules per box row
-constexpr int WTM_RAW_BYTES = WTM_BOX_WORDS * 4 * WTM_BOX_ROWS;            // 7680: the TMA transaction size
-constexpr int WTM_PLANE_WORDS = WTM_PITCH * WTM_BOX_ROWS;                  // 2560 entries per plane
-constexpr int WTM_SMEM_BYTES = WTM_RAW_BYTES + 2 * WTM_PLANE_WORDS * 4;    // raw box (reused as the output tile) + SX + SY
-static_assert(WT_OUT_WORDS * 4 <= WTM_RAW_BYTES, "the packed output tile reuses the raw box");
-
-__global__ void __launch_bounds__(WT_THREADS)
-k_bgr_warp_cv_tma(const __grid_constant__ CUtensorMap src_map, const uint8_t* __restrict__ src_base, int64_t src_stride,
-                  int64_t src_bs, int w, int h, const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
-                  uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
-                  int dst_x0, int dst_y0, int dst_al8)
-{
-    extern __shared__ __align__(128) uint32_t wtm_smem[];
-    uint32_t* const RAW = wtm_smem;                               // [WTM_BOX_ROWS][WTM_BOX_WORDS], later the output tile
-    uint32_t* const SX = wtm_smem + WTM_RAW_BYTES / 4;
-    uint32_t* const SY = SX + WTM_PLANE_WORDS;
-    uint32_t* const O = RAW;
-    __shared__ int2 sXY0[WT_H];
-    __shared__ __align__(8) unsigned long long tma_bar;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.z;
-    const int ox0 = blockIdx.x * WT_W, oy0 = blockIdx.y * WT_H;
-    const int tw = min(WT_W, dw - ox0), th = min(WT_H, dh - oy0);
-    const int slot = slots ? slots[b] : b;
-    const uint8_t* src = src_base + (size_t)slot * src_bs;
-    uint8_t* dst = dst_base + (size_t)b * dst_bs;
-    const VsWarpCoef cf = coefs[b];
-
-    const int xcol = ox0 + min(tid, tw - 1) + dst_x0;
-    const int adelta = __double2int_rn(cf.i00 * (double)xcol * 1024.0);
-    const int bdelta = __double2int_rn(cf.i10 * (double)xcol * 1024.0);
-    if (tid < WT_H) {
-        const int y = oy0 + min(tid, th - 1) + dst_y0;
-        sXY0[tid] = make_int2(__double2int_rn((cf.i01 * (double)y + cf.i02) * 1024.0) + 16,
-                              __double2int_rn((cf.i11 * (double)y + cf.i12) * 1024.0) + 16);
-    }
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const int xl = ox0 + dst_x0, xr = ox0 + tw - 1 + dst_x0;
-    const int aL = __double2int_rn(cf.i00 * (double)xl * 1024.0), aR = __double2int_rn(cf.i00 * (double)xr * 1024.0);
-    const int bL = __double2int_rn(cf.i10 * (double)xl * 1024.0), bR = __double2int_rn(cf.i10 * (double)xr * 1024.0);
-    const int2 xyT = sXY0[0], xyB = sXY0[th - 1];
-    const int sxmin = (min(xyT.x, xyB.x) + min(aL, aR)) >> 10, sxmax = (max(xyT.x, xyB.x) + max(aL, aR)) >> 10;
-    const int symin = (min(xyT.y, xyB.y) + min(bL, bR)) >> 10, symax = (max(xyT.y, xyB.y) + max(bL, bR)) >> 10;
-    const int bx0 = (sxmin >> 4) * 16;                            // 16 pixels = 48 bytes = 12 words: a 16-byte aligned box start
-    const int by0 = symin, nrows = symax + 1 - symin + 1;
-    // entries bx0 .. sxmax are needed, entry x also carries pixel x+1: pixels bx0 .. sxmax+1 must be in the 144-pixel box
-    const bool staged = sxmax + 1 - bx0 < WTM_PITCH && nrows <= WTM_BOX_ROWS;
-
-    if (staged) {
-        if (tid == 0) {
-            const uint32_t dstsm = (uint32_t)__cvta_generic_to_shared(RAW);
-            const int c0 = (bx0 >> 4) * 12;                       // first 32-bit word of pixel bx0 (a multiple of 4 words), may be negative
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WTM_RAW_BYTES) : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                ::"r"(dstsm), "l"(reinterpret_cast<uint64_t>(&src_map)), "r"(c0), "r"(by0), "r"(slot), "r"(bar)
-                : "memory");
-        }
-        // everyone waits for the box (phase 0 of the barrier)
-        uint32_t done = 0, spins = 0;
-        while (!done) {
-            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
-                         : "=r"(done) : "r"(bar) : "memory");
-            if (!done && ++spins > (1u << 24)) __trap();   // a lost transaction must fail loudly, not hang the GPU
-        }
-        // raw bytes -> paired-tap planes: entry j = (b[3j], b[3j+3], b[3j+1], b[3j+4]), (b[3j+2], b[3j+5])
-        for (int t = tid; t < nrows * WTM_GRANULES; t += WT_THREADS) {
-            const int r = t / WTM_GRANULES, q = t - r * WTM_GRANULES;
-            const uint32_t* g = RAW + r * WTM_BOX_WORDS + 3 * q;
-            const uint32_t w0 = g[0], w1 = g[1], w2 = g[2], w3 = g[3];   // g[3] of the last granule: next row's first word, feeds only the unused last entry
-            *reinterpret_cast<uint4*>(SX + r * WTM_PITCH + 4 * q) =
-                make_uint4(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x7463), __byte_perm(w1, w2, 0x6352), __byte_perm(w2, w3, 0x5241));
-            *reinterpret_cast<uint4*>(SY + r * WTM_PITCH + 4 * q) =
-                make_uint4(__byte_perm(w0, w1, 0x0052), __byte_perm(w1, w2, 0x0041), __byte_perm(w2, w2, 0x0030), __byte_perm(w2, w3, 0x0063));
-        }
-        __syncthreads();     // planes complete; the raw box is dead and becomes the output tile
-    }
-
-    const int k4 = tid & 3;
-    const uint32_t sel = k4 == 0 ? 0x4210u : (k4 == 1 ? 0x5421u : 0x6542u);
-    uint32_t* const Orow = O + 3 * (tid >> 2) + k4;
-    const bool keep = k4 < 3 && tid < WT_W;
-    if (staged) {
-        const int sorg = -by0 * WTM_PITCH - bx0;
-#pragma unroll 4
-        for (int r = 0; r < WT_H; r++) {
-            if (r >= th) break;
-            const int2 xy0 = sXY0[r];
-            const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
-            const int fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
-            const int e = sorg + (sfy >> 10) * WTM_PITCH + (sfx >> 10);
-            const uint32_t px = cv_blend(make_uint2(SX[e], SY[e]), make_uint2(SX[e + WTM_PITCH], SY[e + WTM_PITCH]), fx, fy);
-            const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
-            if (keep) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
-        }
-    } else {
-        for (int r = 0; r < th; r++) {
-            const int2 xy0 = sXY0[r];
-            const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
-            const int sx = sfx >> 10, sy = sfy >> 10, fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
-            const uint32_t t00 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx, sy);
-            const uint32_t t10 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx + 1, sy);
-            const uint32_t t01 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx, sy + 1);
-            const uint32_t t11 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx + 1, sy + 1);
-            const uint32_t px = cv_blend(wt_entry(t00, t10), wt_entry(t01, t11), fx, fy);
-            const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
-            if (keep) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
-        }
-    }
-    __syncthreads();
-
-    const int row_bytes = tw * 3;
-    uint8_t* const drow0 = dst + (size_t)oy0 * dst_stride + (size_t)ox0 * 3;
-    if (dst_al8 && tw == WT_W) {
-        constexpr int VPR = WT_W * 3 / 8;
-        uint2* d = reinterpret_cast<uint2*>(drow0 + (size_t)warp * dst_stride) + lane;
-        const uint2* o = reinterpret_cast<const uint2*>(O + warp * WT_OUT_ROW_WORDS) + lane;
-        for (int r = warp; r < th; r += WT_WARPS) {
-            d[0] = o[0];
-            if (lane < VPR - 32) d[32] = o[32];
-            d = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(d) + (size_t)WT_WARPS * dst_stride);
-            o += WT_WARPS * WT_OUT_ROW_WORDS / 2;
-        }
-    } else {
-        const uint8_t* Ob = reinterpret_cast<const uint8_t*>(O);
-        for (int i = tid; i < th * row_bytes; i += WT_THREADS) {
-            const int r = i / row_bytes, c = i - r * row_bytes;
-            drow0[(size_t)r * dst_stride + c] = Ob[r * (WT_OUT_ROW_WORDS * 4) + c];
-        }
-    }
-}
-
 // ------------------------------------------------------------------ BGR warp, cv-exact, row groups on the raw box
-// Same bits as the two kernels above, about half their instructions and a third of their shared-memory
+// Same bits as the tiled kernel above, about half its instructions and a third of its shared-memory
 // traffic: no expanded copy of the source is built.  A thread owns four consecutive output pixels
 // (12 output bytes = three whole words) of one row.  For the near-identity similarity transforms of a
 // stabiliser those four pixels almost always read four consecutive source pixels of ONE source row pair
@@ -1278,47 +1258,52 @@ int vsk_bgr2gray(vs_ctx* ctx, const VsDevImg& bgr, const VsDevImg& gray)
     return VS_OK;
 }
 
+// BGR -> gray level 0 + level 1 in one pass when the geometry allows the fused kernel; returns VS_OK and sets *fused
+int vsk_ingest_bgr_gray_l1(vs_ctx* ctx, const VsDevImg& bgr, const VsDevImg& g0, const VsDevImg& g1, bool* fused)
+{
+    *fused = false;
+    VS_REQUIRE(ctx, bgr.w == g0.w && bgr.h == g0.h && bgr.batch == g0.batch && bgr.batch == g1.batch, "ingest: shape mismatch");
+    if (bgr.w <= 0 || bgr.h <= 0) return VS_OK;
+    const bool ok = bgr.w % 16 == 0 && bgr.h >= 2 && g1.w == bgr.w / 2 && g1.h == bgr.h / 2 &&
+                    aligned_to(bgr.data, 16) && bgr.stride % 16 == 0 && bgr.batch_stride % 16 == 0 &&
+                    aligned_to(g0.data, 16) && g0.stride % 16 == 0 && g0.batch_stride % 16 == 0 &&
+                    aligned_to(g1.data, 8) && g1.stride % 8 == 0 && g1.batch_stride % 8 == 0 &&
+                    bgr.batch <= 65535 && vs_cdiv(g1.h, IG_L1_ROWS * 4) <= 65535;
+    if (!ok) return VS_OK;
+    dim3 block(32, 4), grid(vs_cdiv(bgr.w / 16, 32), vs_cdiv(vs_cdiv(g1.h, IG_L1_ROWS), 4), bgr.batch);
+    VS_LAUNCH_BEGIN(ctx, VSK_INGEST);
+    k_ingest_bgr_gray_l1<<<grid, block, 0, ctx->stream>>>((const uint8_t*)bgr.data, bgr.stride, bgr.batch_stride,
+                                                          (uint8_t*)g0.data, g0.stride, g0.batch_stride,
+                                                          (uint8_t*)g1.data, g1.stride, g1.batch_stride, bgr.w, bgr.h, g1.w, g1.h);
+    VS_LAUNCH_CHECK(ctx);
+    *fused = true;
+    return VS_OK;
+}
+
 int vsk_pyr_down(vs_ctx* ctx, const VsDevImg& in, const VsDevImg& out)
 {
     VS_REQUIRE(ctx, in.batch == out.batch, "pyr_down: batch mismatch");
     VS_REQUIRE(ctx, in.w > 0 && in.h > 0, "pyr_down: empty input");
     if (out.w <= 0 || out.h <= 0) return VS_OK;
-    int in_al8 = aligned_to(in.data, 8) && in.stride % 8 == 0 && in.batch_stride % 8 == 0;
-    int out_al4 = aligned_to(out.data, 4) && out.stride % 4 == 0 && out.batch_stride % 4 == 0;
-    // default: the wide kernel (8 outputs per thread, 4 rows) whenever alignment and sizes allow it;
-    // VSTAB_PD_VARIANT selects the tuning variants (0-6: narrow kernel shapes, 7/8: wide)
-    static const int variant = getenv("VSTAB_PD_VARIANT") ? atoi(getenv("VSTAB_PD_VARIANT")) : 7;
-    const int rows = variant == 2 ? 4 : (variant == 3 ? 16 : PD_ROWS_DEFAULT);
-    VS_REQUIRE(ctx, out.batch <= 65535 && vs_cdiv(out.h, rows) <= 65535, "pyr_down: grid too large");
-    if (variant >= 7) {
-        const bool ok16 = aligned_to(in.data, 16) && in.stride % 16 == 0 && in.batch_stride % 16 == 0 &&
-                          aligned_to(out.data, 8) && out.stride % 8 == 0 && out.batch_stride % 8 == 0 &&
-                          out.w % 8 == 0 && 2 * out.w <= in.w;
-        if (ok16) {
-            const int wr = variant == 8 ? 8 : 4;
-            dim3 wblock(32, 4), wgrid(vs_cdiv(out.w / 8, 32), vs_cdiv(out.h, 4 * wr), out.batch);
-            VS_LAUNCH_BEGIN(ctx, VSK_PYR_DOWN);
-            if (wr == 8)
-                k_pyr_down_wide<8><<<wgrid, wblock, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
-                                                                      (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h);
-            else
-                k_pyr_down_wide<4><<<wgrid, wblock, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
-                                                                      (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h);
-            VS_LAUNCH_CHECK(ctx);
-            return VS_OK;
-        }
-    }
-    const int bx = variant == 5 ? 128 : (variant == 6 ? 64 : 32), by = 128 / bx;
-    dim3 block(bx, by), grid(vs_cdiv(vs_cdiv(out.w, 4), bx), vs_cdiv(out.h, by * rows), out.batch);
+    const int in_al8 = aligned_to(in.data, 8) && in.stride % 8 == 0 && in.batch_stride % 8 == 0;
+    const int out_al4 = aligned_to(out.data, 4) && out.stride % 4 == 0 && out.batch_stride % 4 == 0;
+    VS_REQUIRE(ctx, out.batch <= 65535 && vs_cdiv(out.h, PD_ROWS_DEFAULT) <= 65535, "pyr_down: grid too large");
+    // the wide kernel (8 outputs per thread, 4 rows) whenever alignment and sizes allow it, else the 4-column kernel that
+    // takes any alignment and size (the other shapes that were measured are in profiles/r01_v5_kernel_bench.jsonl)
+    const bool ok16 = aligned_to(in.data, 16) && in.stride % 16 == 0 && in.batch_stride % 16 == 0 &&
+                      aligned_to(out.data, 8) && out.stride % 8 == 0 && out.batch_stride % 8 == 0 &&
+                      out.w % 8 == 0 && 2 * out.w <= in.w;
     VS_LAUNCH_BEGIN(ctx, VSK_PYR_DOWN);
-#define VS_PD_LAUNCH(R, B) k_pyr_down<R, B><<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h, \
-                                                (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h, in_al8, out_al4)
-    if (variant == 1) VS_PD_LAUNCH(8, 12);
-    else if (variant == 2) VS_PD_LAUNCH(4, 12);
-    else if (variant == 3) VS_PD_LAUNCH(16, 6);
-    else if (variant == 4) VS_PD_LAUNCH(8, 10);
-    else VS_PD_LAUNCH(8, 7);
-#undef VS_PD_LAUNCH
+    if (ok16) {
+        dim3 wblock(32, 4), wgrid(vs_cdiv(out.w / 8, 32), vs_cdiv(out.h, 4 * 4), out.batch);
+        k_pyr_down_wide<4><<<wgrid, wblock, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
+                                                              (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h);
+    } else {
+        dim3 block(32, 4), grid(vs_cdiv(vs_cdiv(out.w, 4), 32), vs_cdiv(out.h, 4 * PD_ROWS_DEFAULT), out.batch);
+        k_pyr_down<PD_ROWS_DEFAULT, 7><<<grid, block, 0, ctx->stream>>>((const uint8_t*)in.data, in.stride, in.batch_stride, in.w, in.h,
+                                                                        (uint8_t*)out.data, out.stride, out.batch_stride, out.w, out.h,
+                                                                        in_al8, out_al4);
+    }
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
@@ -1445,24 +1430,6 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
     return VS_OK;
 }
 
-// clip-resident sources with a tensor map over [slot][row][word] (vs_clip.cu): mode 0, constant border
-int vsk_bgr_warp_slots_tma(vs_ctx* ctx, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,
-                           const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0)
-{
-    VS_REQUIRE(ctx, tensor_map && src.w > 0 && src.h > 0, "bgr_warp_tma: bad source");
-    if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
-    VS_REQUIRE(ctx, vs_cdiv(dst.h, WT_H) <= 65535 && dst.batch <= 65535, "bgr_warp_tma: grid too large");
-    const int dst_al8 = aligned_to(dst.data, 8) && dst.stride % 8 == 0 && dst.batch_stride % 8 == 0;
-    VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
-    VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, WTM_SMEM_BYTES));
-    dim3 tgrid(vs_cdiv(dst.w, WT_W), vs_cdiv(dst.h, WT_H), dst.batch);
-    k_bgr_warp_cv_tma<<<tgrid, WT_THREADS, WTM_SMEM_BYTES, ctx->stream>>>(
-        *reinterpret_cast<const CUtensorMap*>(tensor_map), (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
-        d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, dst_al8);
-    VS_LAUNCH_CHECK(ctx);
-    return VS_OK;
-}
-
 // cuTensorMapEncodeTiled lives in the driver library; resolve it through the runtime so that
 // libvstab.so keeps linking against cudart only
 void* vs_tensor_map_encoder()
@@ -1494,8 +1461,7 @@ int vsk_bgr_warp_slots_rows(vs_ctx* ctx, const void* tensor_map, const VsDevImg&
     CUtensorMap dst_map;
     memset(&dst_map, 0, sizeof(dst_map));
     int dst_tma = 0;
-    static const int no_tma_store = getenv("VSTAB_WARP_TMA_STORE") ? atoi(getenv("VSTAB_WARP_TMA_STORE")) == 0 : 0;
-    if (!no_tma_store && dst_al16 && dst.w % 4 == 0 && vs_tensor_map_encoder()) {
+    if (dst_al16 && dst.w % 4 == 0 && vs_tensor_map_encoder()) {
         const cuuint64_t dims[3] = {(cuuint64_t)(dst.w * 3 / 4), (cuuint64_t)dst.h, (cuuint64_t)dst.batch};
         const cuuint64_t strides[2] = {(cuuint64_t)dst.stride, (cuuint64_t)(dst.batch > 1 ? dst.batch_stride : dst.stride * dst.h)};
         const cuuint32_t box[3] = {(cuuint32_t)WG_OUT_ROW_WORDS, (cuuint32_t)WG_H, 1}, estr[3] = {1, 1, 1};

@@ -572,7 +572,7 @@ __device__ __forceinline__ double dist2d(const double* a, const double* b)
     return sqrt(dx * dx + dy * dy);
 }
 
-template <int SOLVE_THREADS, int VS_SOLVE_PREFETCH, int MIN_CTAS>
+template <int SOLVE_THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(SOLVE_THREADS, MIN_CTAS)
 k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 {
@@ -629,36 +629,22 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
             keys1[t] = __ldg(kpl1 + t);
         }
         __syncthreads();
-        {
-            // optionally software-pipelined over this thread's keypoints: the gather of keypoint i+256 is issued
-            // before keypoint i is evaluated.  keys[t] is read before the same thread overwrites it with the result.
-            VsLzTaps cur, nxt;
-            uint32_t tb_cur = 0, tb_nxt = 0;
-            auto fetch = [&](int i, VsLzTaps& taps, uint32_t& tb) {
-                const int axis = i >= nt, t = i - axis * nt;
-                const uint32_t kv = (axis ? keys1 : keys0)[t];
-                const int px = min((int)(kv & 0xffffu), L.w - 1), py = min((int)(kv >> 16), L.h - 1);
-                vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3], taps);
-                tb = __ldg(timg + (size_t)py * L.pitch + px);
-            };
-            int i = tid;
-            if (VS_SOLVE_PREFETCH && i < 2 * nt) fetch(i, cur, tb_cur);
-            while (i < 2 * nt) {
-                const int inext = i + SOLVE_THREADS;
-                if (!VS_SOLVE_PREFETCH) fetch(i, cur, tb_cur);
-                else if (inext < 2 * nt) fetch(inext, nxt, tb_nxt);
-                const int axis = i >= nt, t = i - axis * nt;
-                const float s = vs_lz_eval(cur);
-                if (res) res[axis * g.max_tiles + t] = __fsub_rn((float)tb_cur, s);
-                float d = fabsf(__fsub_rn(s, (float)tb_cur));
-                d = fmaxf(fminf(d, 65535.0f), 0.0f);
-                const uint32_t u = (uint32_t)d;
-                (axis ? keys1 : keys0)[t] = (u << 16) | (uint32_t)t;
-                if (a.dbg_warpdiff)
-                    a.dbg_warpdiff[((size_t)pair * 2 + axis) * g.total_tiles + L.tile_off + t] = (uint16_t)u;
-                if (VS_SOLVE_PREFETCH) { cur = nxt; tb_cur = tb_nxt; }
-                i = inext;
-            }
+        // keys[t] is read before the same thread overwrites it with the result
+        for (int i = tid; i < 2 * nt; i += SOLVE_THREADS) {
+            const int axis = i >= nt, t = i - axis * nt;
+            const uint32_t kv = (axis ? keys1 : keys0)[t];
+            const int px = min((int)(kv & 0xffffu), L.w - 1), py = min((int)(kv >> 16), L.h - 1);
+            VsLzTaps taps;
+            vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3], taps);
+            const uint32_t tb = __ldg(timg + (size_t)py * L.pitch + px);
+            const float s = vs_lz_eval(taps);
+            if (res) res[axis * g.max_tiles + t] = __fsub_rn((float)tb, s);
+            float d = fabsf(__fsub_rn(s, (float)tb));
+            d = fmaxf(fminf(d, 65535.0f), 0.0f);
+            const uint32_t u = (uint32_t)d;
+            (axis ? keys1 : keys0)[t] = (u << 16) | (uint32_t)t;
+            if (a.dbg_warpdiff)
+                a.dbg_warpdiff[((size_t)pair * 2 + axis) * g.total_tiles + L.tile_off + t] = (uint16_t)u;
         }
         __syncthreads();
 
@@ -739,31 +725,20 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         auto gather = [&](int first, int count, double* b) {
             float Pg[4];
             vs_ul_params_half(sh.T, L.w, L.h, Pg);
-            VsLzTaps cur, nxt;
-            uint32_t tb_cur = 0, tb_nxt = 0;
-            float4 J_cur = make_float4(0, 0, 0, 0), J_nxt = J_cur;
-            auto fetch = [&](int i, VsLzTaps& taps, uint32_t& tb, float4& J) {
+            for (int i = tid - first; i < 2 * k; i += count) {
                 const int axis = i >= k, j = i - axis * k;
                 const uint32_t key = (axis ? keys1 : keys0)[j];
                 const int tx = (int)(key & 0x3ffu), ty = (int)((key >> 10) & 0x3ffu);
                 const int px = tx * L.tile + (int)((key >> 20) & 31u), py = ty * L.tile + (int)((key >> 25) & 31u);
-                J = __ldg((axis ? jcl1 : jcl0) + ty * L.tw + tx);
+                const float4 J = __ldg((axis ? jcl1 : jcl0) + ty * L.tw + tx);
+                VsLzTaps taps;
                 vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, Pg[0], Pg[1], Pg[2], Pg[3], taps);
-                tb = __ldg(timg + (size_t)min(py, L.h - 1) * L.pitch + min(px, L.w - 1));
-            };
-            int i = tid - first;
-            if (VS_SOLVE_PREFETCH && i < 2 * k) fetch(i, cur, tb_cur, J_cur);
-            while (i < 2 * k) {
-                const int inext = i + count;
-                if (!VS_SOLVE_PREFETCH) fetch(i, cur, tb_cur, J_cur);
-                else if (inext < 2 * k) fetch(inext, nxt, tb_nxt, J_nxt);
-                const float r = __fsub_rn((float)tb_cur, vs_lz_eval(cur));
-                b[0] += (double)__fmul_rn(J_cur.x, r);
-                b[1] += (double)__fmul_rn(J_cur.y, r);
-                if (i < k) b[2] += (double)__fmul_rn(J_cur.z, r);
-                else       b[3] += (double)__fmul_rn(J_cur.w, r);
-                if (VS_SOLVE_PREFETCH) { cur = nxt; tb_cur = tb_nxt; J_cur = J_nxt; }
-                i = inext;
+                const uint32_t tb = __ldg(timg + (size_t)min(py, L.h - 1) * L.pitch + min(px, L.w - 1));
+                const float r = __fsub_rn((float)tb, vs_lz_eval(taps));
+                b[0] += (double)__fmul_rn(J.x, r);
+                b[1] += (double)__fmul_rn(J.y, r);
+                if (i < k) b[2] += (double)__fmul_rn(J.z, r);
+                else       b[3] += (double)__fmul_rn(J.w, r);
             }
         };
         // first iteration: residuals of the warp-diff pass (bit-identical: same samples, same transform)
@@ -985,41 +960,33 @@ int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
         smem += pos_bytes;
         args.pos_scratch = nullptr;
     }
-    // Measured on B200 (1080p, 299 pairs in flight), all rejected: CTAs of 320 / 384 threads (registers capped at 64 / 56:
-    // 0.88 / 1.09 ms mean per pair against 0.85), register software pipelining of the gathers (1.00 ms), L2 prefetch of
-    // the samples 1 / 2 / 4 iterations ahead (0.91 / 1.00 / 1.15 ms).  More loads in flight make it slower: the gathers
+    // Measured on B200 (1080p, 299 pairs in flight), all rejected (profiles/r01_*): CTAs of 320 / 384 threads (registers
+    // capped at 64 / 56: 0.88 / 1.09 ms mean per pair against 0.85), register software pipelining of the gathers (1.00 ms),
+    // L2 prefetch of the samples 1 / 2 / 4 iterations ahead (0.91 / 1.00 / 1.15 ms).  More loads in flight make it slower: the gathers
     // are bound by the rate of random 32-byte sector reads from DRAM (L2 hit rate 27 %), not by their latency.
     // CTA size by how many pairs are in flight: every pair must be resident at once (a second wave would double the
     // time: the kernel lasts as long as its slowest pair), and within that the largest CTA wins because the gathers
     // of a pair are independent.  256 x 3 per SM (444 pairs), 512 x 1 (148 pairs, registers uncapped), 1024 x 1 for
     // the big shared-memory footprints of 4K where only one CTA fits anyway.
-    static const int prefetch = getenv("VSTAB_SOLVE_PREFETCH") ? atoi(getenv("VSTAB_SOLVE_PREFETCH")) : 0;
-    static const int force = getenv("VSTAB_SOLVE_THREADS") ? atoi(getenv("VSTAB_SOLVE_THREADS")) : 0;
-    // shared-memory carve-out: just enough for the CTAs that must be resident (the rest of the 256 KB is L1 for the gathers)
-    // (B200, 1080p, 299 pairs: 0.857 ms with the minimal carve-out, 0.88 with the driver's default, 0.95 at 72 %, 1.43 at 86 %;
-    // VSTAB_SOLVE_CARVEOUT = percentage, -1 = minimal (default), -2 = leave it to the driver)
-    static const int carve_env = getenv("VSTAB_SOLVE_CARVEOUT") ? atoi(getenv("VSTAB_SOLVE_CARVEOUT")) : -1;
-#define VS_SOLVE_LAUNCH(NT, PF, MINB)                                                                                             \
+    // shared-memory carve-out: just enough for the CTAs that must be resident (the rest of the 256 KB is L1 for the gathers;
+    // B200, 1080p, 299 pairs: 0.857 ms with the minimal carve-out, 0.88 with the driver's default, 0.95 at 72 %, 1.43 at 86 %)
+#define VS_SOLVE_LAUNCH(NT, MINB)                                                                                                 \
     do {                                                                                                                          \
-        VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<NT, PF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        if (carve_env != -2) {                                                                                                    \
-            cudaFuncAttributes fa;                                                                                                \
-            VS_CUDA(ctx, cudaFuncGetAttributes(&fa, k_solve_pairs<NT, PF, MINB>));                                                \
-            const size_t need = (size_t)MINB * (smem + fa.sharedSizeBytes + 1024);                                                \
-            const int pct = carve_env >= 0 ? carve_env : (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));                     \
-            VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<NT, PF, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,         \
-                                              pct > 100 ? 100 : pct));                                                            \
-        }                                                                                                                         \
+        VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        cudaFuncAttributes fa;                                                                                                    \
+        VS_CUDA(ctx, cudaFuncGetAttributes(&fa, k_solve_pairs<NT, MINB>));                                                        \
+        const size_t need = (size_t)MINB * (smem + fa.sharedSizeBytes + 1024);                                                    \
+        const int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));                                                      \
+        VS_CUDA(ctx, cudaFuncSetAttribute(k_solve_pairs<NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,                \
+                                          pct > 100 ? 100 : pct));                                                                \
         VS_LAUNCH_BEGIN(ctx, VSK_SOLVE);                                                                                          \
-        k_solve_pairs<NT, PF, MINB><<<a.n_pairs, NT, smem, ctx->stream>>>(g, args);                                               \
+        k_solve_pairs<NT, MINB><<<a.n_pairs, NT, smem, ctx->stream>>>(g, args);                                                   \
     } while (0)
     int threads = a.n_pairs <= ctx->sm_count ? 512 : 256;
-    if (a.force_threads == 256 || a.force_threads == 512) threads = a.force_threads;
-    if (force == 256 || force == 512 || force == 1024) threads = force;
-    if (prefetch) VS_SOLVE_LAUNCH(256, 1, 3);
-    else if (threads == 1024) VS_SOLVE_LAUNCH(1024, 0, 1);
-    else if (threads == 512) VS_SOLVE_LAUNCH(512, 0, 1);
-    else VS_SOLVE_LAUNCH(256, 0, 3);
+    if (a.force_threads == 256 || a.force_threads == 512 || a.force_threads == 1024) threads = a.force_threads;
+    if (threads == 1024) VS_SOLVE_LAUNCH(1024, 1);
+    else if (threads == 512) VS_SOLVE_LAUNCH(512, 1);
+    else VS_SOLVE_LAUNCH(256, 3);
 #undef VS_SOLVE_LAUNCH
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;

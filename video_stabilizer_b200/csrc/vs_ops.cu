@@ -103,6 +103,33 @@ int vs_bgr2gray_u8(vs_ctx* ctx, const vs_img* bgr, const vs_img* gray, int mem)
     return st.finish();
 }
 
+int vs_ingest_bgr_u8(vs_ctx* ctx, const vs_img* bgr, const vs_img* gray0, const vs_img* gray1, int mem)
+{
+    if (!ctx) return VS_ERR_INVALID;
+    VS_TRY(check_mem(ctx, mem)); VS_TRY(check_img(ctx, bgr, "ingest input"));
+    VS_TRY(check_img(ctx, gray0, "ingest gray level 0")); VS_TRY(check_img(ctx, gray1, "ingest gray level 1"));
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto run = [&](const VsDevImg& din, const VsDevImg& d0, const VsDevImg& d1) -> int {
+        bool fused = false;
+        VS_TRY(vsk_ingest_bgr_gray_l1(ctx, din, d0, d1, &fused));
+        if (fused) return VS_OK;
+        VS_TRY(vsk_bgr2gray(ctx, din, d0));
+        return vsk_pyr_down(ctx, d0, d1);
+    };
+    if (mem == VS_MEM_DEVICE) return run(vs_dev_img(bgr), vs_dev_img(gray0), vs_dev_img(gray1));
+    Stage st(ctx);
+    st.want_img(bgr, 3); st.want_img(gray0, 1); st.want_img(gray1, 1);
+    VS_TRY(st.reserve());
+    VsDevImg din, d0, d1;
+    VS_TRY(st.img(bgr, 3, 1, true, &din));
+    VS_TRY(st.img(gray0, 1, 1, false, &d0));
+    VS_TRY(st.img(gray1, 1, 1, false, &d1));
+    VS_TRY(run(din, d0, d1));
+    VS_TRY(st.img_out(d0, gray0, 1, 1));
+    VS_TRY(st.img_out(d1, gray1, 1, 1));
+    return st.finish();
+}
+
 int vs_phase_correlate_u8(vs_ctx* ctx, const vs_img* src1, const vs_img* src2, double* out3, int mem)
 {
     if (!ctx) return VS_ERR_INVALID;

@@ -149,6 +149,19 @@ def BGR2Gray(bgr: np.ndarray, ctx: Context | None = None) -> np.ndarray:
     return out
 
 
+def IngestBGR(bgr: np.ndarray, ctx: Context | None = None):
+    """Fused ingest (alignment.cpp:212 + the first PyrDown of :220-223): returns (gray level 0, gray level 1) with
+    level 1 = (w // 2) x (h // 2), computed in one pass over the BGR frame when its geometry allows."""
+    ctx = ctx or default_context()
+    bgr = _u8(bgr)
+    h, w = bgr.shape[:2]
+    g0 = np.empty((h, w), np.uint8)
+    g1 = np.empty((max(h // 2, 0), max(w // 2, 0)), np.uint8)
+    capi.check(ctx.handle, ctx.lib.vs_ingest_bgr_u8(ctx.handle, C.byref(capi.img_of(bgr)), C.byref(capi.img_of(g0)),
+                                                    C.byref(capi.img_of(g1)), capi.VS_MEM_HOST), "vs_ingest_bgr_u8")
+    return g0, g1
+
+
 def PhaseCorrelate(src1: np.ndarray, src2: np.ndarray, ctx: Context | None = None):
     """cv::phaseCorrelate(src1, src2, noArray(), &response) as called at alignment.cpp:374 (u8-valued images taken
     as CV_32F): returns ((shift_x, shift_y), response)."""
