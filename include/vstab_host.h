@@ -110,6 +110,35 @@ void  vsh_multigpu_destroy(void*);
 int   vsh_multigpu_stabilize(void*, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride,
                              uint8_t* out, int64_t out_frame_stride, double* meas, uint8_t* ok);
 
+/* ---- one video partitioned by frame chunk over several workers (partitioned.hpp): one worker per GPU, processes or
+ * threads; the workers share a per-frame table in POSIX shared memory (exchange_name = "/name"; rank 0 creates it).
+ * Sub-chunks of sub_frames (even) frames, `block` consecutive sub-chunks per chunk, chunks round-robin over the workers. */
+/* host half only (no GPU): runs one video's trajectory from a full measurement table (total x 4, total) the partitioned way;
+ * writes this worker's corrections (outputs x 4) and their frame indices; returns the number of outputs or -1 */
+void* vsh_parttraj_create(int rank, int world, int width, int height, int64_t total_frames, int sub_frames, int block,
+                          const vsh_stab_params* p, const char* exchange_name, int host_threads);
+void  vsh_parttraj_destroy(void*);
+int   vsh_parttraj_output_count(void*);
+int   vsh_parttraj_run(void*, const double* meas_all, const uint8_t* ok_all, double* corrections, int64_t* frames);
+/* the full worker.  resident != 0: all local frames live in the ring (upload_resident, then stabilize(frames = NULL)) */
+void* vsh_partstab_create(int device, int rank, int world, int width, int height, int64_t total_frames, int sub_frames,
+                          int block, const vsh_stab_params* p, const char* exchange_name, int resident, int host_threads);
+void  vsh_partstab_destroy(void*);
+/* local frame list of the worker: own frames in video order, each foreign-preceded run headed by its halo frame */
+int     vsh_partstab_local_count(void*);
+int64_t vsh_partstab_local_frame(void*, int i);
+int     vsh_partstab_local_is_halo(void*, int i);
+int     vsh_partstab_output_count(void*);            /* frames stabilize() writes */
+int     vsh_partstab_output_frame(void*, int k);     /* video frame index of output k */
+int     vsh_partstab_upload_resident(void*, const uint8_t* frames, int64_t row_stride, int64_t frame_stride, int mem);
+/* frames: the local frames (host; NULL when resident); out: output_count() dense frames; returns their number or -1 */
+int     vsh_partstab_stabilize(void*, const uint8_t* frames, int64_t row_stride, int64_t frame_stride, uint8_t* out,
+                               int64_t out_frame_stride, int out_mem);
+/* after stabilize: corrections (outputs x 4), the measurements / status of the frames this worker has seen; returns how many */
+int64_t vsh_partstab_records(void*, double* corrections, double* meas, uint8_t* ok);
+int     vsh_partstab_out_size(void*, int* w, int* h);
+vs_ctx* vsh_partstab_context(void*);
+
 #ifdef __cplusplus
 }
 #endif

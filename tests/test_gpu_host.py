@@ -1,6 +1,8 @@
 """The C++ host layer (VideoAligner, VideoStabilizer, ClipStabilizer, imgproc.hpp operators)
 on the GPU against the oracle: the reference-facing classes are the thing under test, called
 through libvstab_host.so exactly as a C++ caller would call them."""
+import os
+
 import numpy as np
 import pytest
 
@@ -256,3 +258,68 @@ def test_multi_gpu_stabilizer_equals_single_stream(host, workers, phase):
 def cs_feed_fresh(host, frames, p):
     n, h, w, _ = frames.shape
     return host.ClipStabilizer(w, h, n, p, 0).feed(frames)
+
+
+# ---------------------------------------------------------------- one video partitioned over several workers (partitioned.hpp)
+def _partitioned_run(host, frames, p, world, sub, block, resident, name):
+    """`world` workers as threads of this process (one context each; on a multi-GPU box one per device), the table in POSIX
+    shared memory exactly as between processes.  Returns {frame: stabilized frame}, and the last worker's records."""
+    import threading
+    from video_stabilizer_b200 import _capi as capi
+    n, h, w, _ = frames.shape
+    ndev = max(1, capi.load().vs_device_count())
+    workers = [host.PartitionedStabilizer(r, world, w, h, n, sub, block, p, name, resident, device=r % ndev, host_threads=2)
+               for r in range(world)]          # rank 0 first: it creates the segment
+    out, errors = {}, []
+
+    def run(r):
+        try:
+            ps = workers[r]
+            local = np.ascontiguousarray(frames[ps.local_frames])
+            for video in range(2):          # twice: the second video uses the other copy of the table
+                if resident:
+                    if video == 0:
+                        ps.upload_resident(local.ctypes.data, local.strides[1], local.strides[0])
+                    got = ps.stabilize(None)
+                else:
+                    got = ps.stabilize(local)
+                assert len(got) == ps.outputs
+                if video == 1:
+                    for f, g in zip(ps.output_frames, got):
+                        out[int(f)] = g
+        except Exception as e:       # noqa: BLE001
+            errors.append((r, repr(e)))
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors
+    return out, workers[-1].records(n)
+
+
+@pytest.mark.parametrize("world,sub,block,resident", [(1, 16, 3, True), (1, 12, 1, False), (2, 12, 2, True), (2, 12, 1, False),
+                                                      (3, 10, 1, True), (3, 16, 1, False)])
+def test_partitioned_stabilizer_equals_single_stream(host, world, sub, block, resident):
+    """ONE video, frame-chunk partitioned over `world` workers (contiguous chunks when block * sub covers a worker's share,
+    interleaved sub-chunks otherwise), device-resident and host-streamed: measurements, status and every stabilized frame
+    equal the single-stream pipeline bit for bit; no collective, 65 bytes per frame through the shared host table."""
+    w, h, n = 320, 180, 50
+    frames = _clip(w, h, n, 41, step=3.0)
+    p = host.stab_params_default()
+    p.crop_pixels = 8
+    cs = host.ClipStabilizer(w, h, n, p, 0)
+    want = cs.feed(frames)
+    meas_want, ok_want, corr_want = cs.last_records(n)
+    name = "/vstab_gputest_%d_%d%d%d%d" % (os.getpid(), world, sub, block, int(resident))
+    got, (corr, meas, ok) = _partitioned_run(host, frames, p, world, sub, block, resident, name if world > 1 else "")
+    assert sorted(got) == list(range(n - p.lag))
+    for f in range(n - p.lag):
+        assert np.array_equal(got[f], want[f]), f
+    seen = len(meas)
+    assert seen >= n - 2 * sub
+    assert np.array_equal(ok, ok_want[:seen])
+    # the solver's f64 sums follow its CTA size (pairs in flight): ~1e-9 px, selections and iteration counts are identical
+    for f in range(seen):
+        assert corner_displacement(meas[f], meas_want[f], w, h) <= 1e-6, f

@@ -81,3 +81,66 @@ def test_two_rank_gather_and_trajectory_equal_single_process(tmp_path):
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / ("table_%d.npy" % r)), table)
         assert np.array_equal(np.load(tmp_path / ("corr_%d.npy" % r)), want)
+
+
+# ---------------------------------------------------------------- the C++ partitioned trajectory (host/partitioned.hpp)
+def _sequential_corrections(table, w, h, params=None):
+    """frame-by-frame StabilizerTrajectory (stabilizer.cpp:19-88) over a measurement table -> {frame: correction}"""
+    from video_stabilizer_b200 import host
+    tr = host.StabilizerTrajectory(params)
+    lag = tr.params.lag
+    out = {}
+    for n in range(len(table)):
+        due, corr = tr.push(table[n, :4], table[n, 4] != 0, w, h)
+        if due:
+            out[n - lag] = corr
+    return out
+
+
+def _part_worker(rank, world, name, n_frames, sub, block, videos, threads, out_dir):
+    from video_stabilizer_b200 import host
+    host.load()
+    pt = host.PartitionedTrajectory(rank, world, 1920, 1080, n_frames, sub, block, None, name, threads)
+    for v in range(videos):
+        table = np.stack([_fake_measurement(f + 1000 * v) for f in range(n_frames)])
+        table[0] = 0.0
+        frames, corr = pt.run(table[:, :4], table[:, 4] != 0)
+        np.save(os.path.join(out_dir, "pf_%d_%d.npy" % (rank, v)), frames)
+        np.save(os.path.join(out_dir, "pc_%d_%d.npy" % (rank, v)), corr)
+
+
+@pytest.mark.parametrize("n_frames,sub,block", [(300, 100, 3), (300, 32, 1), (123, 10, 1), (57, 20, 2), (11, 12, 1)])
+def test_partitioned_trajectory_single_worker_equals_frame_by_frame(tmp_path, n_frames, sub, block):
+    """world = 1: smoothing on a worker pool + the chain == StabilizerTrajectory::push frame by frame, bit for bit."""
+    _part_worker(0, 1, "", n_frames, sub, block, 2, 3, str(tmp_path))
+    for v in range(2):
+        table = np.stack([_fake_measurement(f + 1000 * v) for f in range(n_frames)])
+        table[0] = 0.0
+        want = _sequential_corrections(table, 1920, 1080)
+        frames, corr = np.load(tmp_path / ("pf_0_%d.npy" % v)), np.load(tmp_path / ("pc_0_%d.npy" % v))
+        assert list(frames) == sorted(want)
+        for f, c in zip(frames, corr):
+            assert np.array_equal(c, want[int(f)]), f
+
+
+@pytest.mark.parametrize("n_frames,sub,block,world", [(600, 100, 3, 2), (600, 32, 1, 2), (250, 10, 1, 3), (64, 32, 1, 2)])
+def test_partitioned_trajectory_processes_equal_frame_by_frame(tmp_path, n_frames, sub, block, world):
+    """Several worker PROCESSES sharing the table in POSIX shared memory (no collective): every output frame's correction
+    equals the frame-by-frame trajectory bit for bit, over three videos in a row (the table alternates between two copies)."""
+    import torch.multiprocessing as mp
+    name = "/vstab_test_%d_%d" % (os.getpid(), n_frames * 100 + sub)
+    videos = 3
+    mp.spawn(_part_worker, args=(world, name, n_frames, sub, block, videos, 2, str(tmp_path)), nprocs=world, join=True)
+    for v in range(videos):
+        table = np.stack([_fake_measurement(f + 1000 * v) for f in range(n_frames)])
+        table[0] = 0.0
+        want = _sequential_corrections(table, 1920, 1080)
+        got = {}
+        for r in range(world):
+            frames, corr = np.load(tmp_path / ("pf_%d_%d.npy" % (r, v))), np.load(tmp_path / ("pc_%d_%d.npy" % (r, v)))
+            for f, c in zip(frames, corr):
+                assert int(f) not in got
+                got[int(f)] = c
+        assert sorted(got) == sorted(want)
+        for f in want:
+            assert np.array_equal(got[f], want[f]), (v, f)

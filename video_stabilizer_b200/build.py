@@ -76,7 +76,7 @@ def build_host(force: bool = False) -> str | None:
     cxx = shutil.which("g++") or "g++"
     _run([cxx, "-std=c++17", "-O2", "-mavx2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-pthread",
           "-I", INCLUDE, "-I", host_dir, "-idirafter", os.path.join(INCLUDE, "compat"),
-          "-o", LIB_HOST] + srcs + ["-L", PKG_DIR, "-lvstab", "-Wl,-rpath,$ORIGIN"])
+          "-o", LIB_HOST] + srcs + ["-L", PKG_DIR, "-lvstab", "-lrt", "-Wl,-rpath,$ORIGIN"])
     return LIB_HOST
 
 

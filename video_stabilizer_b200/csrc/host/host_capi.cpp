@@ -5,10 +5,13 @@
 
 #include <exception>
 #include <string>
+#include <vector>
+#include <algorithm>
 
 #include "aligner_impl.hpp"
 #include "clip_stabilizer.hpp"
 #include "multi_gpu.hpp"
+#include "partitioned.hpp"
 #include "stabilizer.hpp"
 
 namespace {
@@ -318,6 +321,91 @@ int vsh_multigpu_stabilize(void* m, const uint8_t* frames, int n, int64_t row_st
         return k;
     });
 }
+
+// ---- partitioned video: host half (no GPU) and the full worker
+void* vsh_parttraj_create(int rank, int world, int width, int height, int64_t total_frames, int sub_frames, int block,
+                          const vsh_stab_params* p, const char* exchange_name, int host_threads)
+{
+    vstab::PartitionedTrajectory* t = nullptr;
+    guarded([&] {
+        t = new vstab::PartitionedTrajectory(rank, world, width, height, (long)total_frames, sub_frames, block, stab_params(p),
+                                             exchange_name ? exchange_name : "", host_threads);
+        return 0;
+    });
+    return t;
+}
+void vsh_parttraj_destroy(void* t) { delete (vstab::PartitionedTrajectory*)t; }
+int vsh_parttraj_run(void* tp, const double* meas_all, const uint8_t* ok_all, double* corrections, int64_t* frames)
+{
+    return guarded([&] {
+        auto* t = (vstab::PartitionedTrajectory*)tp;
+        t->begin_video();
+        std::vector<double> T;
+        std::vector<int32_t> st;
+        for (size_t i = 0; i < t->subs().size(); i++) {
+            const auto& s = t->subs()[i];
+            T.clear(); st.clear();
+            for (long f = std::max(s.a, 1L); f < s.b; f++) {
+                T.insert(T.end(), meas_all + 4 * f, meas_all + 4 * f + 4);
+                st.push_back(ok_all[f] ? 1 : 0);
+            }
+            t->submit((int)i, T.data(), st.data());
+        }
+        t->flush();
+        t->end_video();
+        for (int k = 0; k < t->output_count(); k++) {
+            if (corrections) put(t->correction(k), corrections + 4 * k);
+            if (frames) frames[k] = t->local_frame(t->local_of_own(k));
+        }
+        return t->due();
+    });
+}
+int vsh_parttraj_output_count(void* t) { return ((vstab::PartitionedTrajectory*)t)->output_count(); }
+
+void* vsh_partstab_create(int device, int rank, int world, int width, int height, int64_t total_frames, int sub_frames,
+                          int block, const vsh_stab_params* p, const char* exchange_name, int resident, int host_threads)
+{
+    vstab::PartitionedStabilizer* s = nullptr;
+    guarded([&] {
+        s = new vstab::PartitionedStabilizer(device, rank, world, width, height, (long)total_frames, sub_frames, block, stab_params(p),
+                                             exchange_name ? exchange_name : "", resident != 0, host_threads);
+        return 0;
+    });
+    return s;
+}
+void vsh_partstab_destroy(void* s) { delete (vstab::PartitionedStabilizer*)s; }
+int vsh_partstab_local_count(void* s) { return ((vstab::PartitionedStabilizer*)s)->trajectory().local_count(); }
+int64_t vsh_partstab_local_frame(void* s, int i) { return ((vstab::PartitionedStabilizer*)s)->trajectory().local_frame(i); }
+int vsh_partstab_local_is_halo(void* s, int i) { return ((vstab::PartitionedStabilizer*)s)->trajectory().local_is_halo(i) ? 1 : 0; }
+int vsh_partstab_output_count(void* s) { return ((vstab::PartitionedStabilizer*)s)->trajectory().output_count(); }
+int vsh_partstab_output_frame(void* s, int k)
+{
+    const auto& t = ((vstab::PartitionedStabilizer*)s)->trajectory();
+    return (int)t.local_frame(t.local_of_own(k));
+}
+int vsh_partstab_upload_resident(void* s, const uint8_t* frames, int64_t row_stride, int64_t frame_stride, int mem)
+{
+    return guarded([&] { ((vstab::PartitionedStabilizer*)s)->upload_resident(frames, row_stride, frame_stride, mem); return 0; });
+}
+int vsh_partstab_stabilize(void* s, const uint8_t* frames, int64_t row_stride, int64_t frame_stride, uint8_t* out,
+                           int64_t out_frame_stride, int out_mem)
+{
+    return guarded([&] { return ((vstab::PartitionedStabilizer*)s)->stabilize(frames, row_stride, frame_stride, out, out_frame_stride, out_mem); });
+}
+int64_t vsh_partstab_records(void* sp, double* corrections, double* meas, uint8_t* ok)
+{
+    const auto& t = ((vstab::PartitionedStabilizer*)sp)->trajectory();
+    if (corrections) for (int k = 0; k < t.output_count(); k++) put(t.correction(k), corrections + 4 * k);
+    if (meas) for (size_t i = 0; i < t.measurements().size(); i++) put(t.measurements()[i], meas + 4 * i);
+    if (ok) for (size_t i = 0; i < t.successes().size(); i++) ok[i] = t.successes()[i];
+    return (int64_t)t.measurements().size();
+}
+int vsh_partstab_out_size(void* s, int* w, int* h)
+{
+    *w = ((vstab::PartitionedStabilizer*)s)->out_width(); *h = ((vstab::PartitionedStabilizer*)s)->out_height();
+    return 0;
+}
+vs_ctx* vsh_partstab_context(void* s) { return ((vstab::PartitionedStabilizer*)s)->context(); }
 
 vs_ctx* vsh_clipstab_context(void* c) { return ((vstab::ClipStabilizer*)c)->context(); }
 vs_clip* vsh_clipstab_clip(void* c) { return ((vstab::ClipStabilizer*)c)->clip(); }

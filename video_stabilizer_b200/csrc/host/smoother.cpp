@@ -102,27 +102,45 @@ L1SmootherCenter::L1SmootherCenter(int lagBehind, int lagAhead, double lambda)
 {
 }
 
+namespace vstab {
+
+SimilarityTransform smoother_finalize(const SimilarityTransform* meas, long s, int lagBehind, int lagAhead, double lambda)
+{
+    const long first = std::max(0L, s - lagBehind);
+    const long last = s + lagAhead;
+    const int n = (int)(last - first + 1);
+    // one window, the four parameters as the four lanes of a vector
+    v4d stack_window[64], stack_smooth[64];
+    std::vector<v4d> heap;
+    v4d* window = stack_window;
+    v4d* smooth = stack_smooth;
+    if (n > 64) {
+        heap.resize((size_t)2 * n);
+        window = heap.data();
+        smooth = heap.data() + n;
+    }
+    for (int i = 0; i < n; i++) {
+        const SimilarityTransform& m = meas[first + i];
+        window[i] = (v4d){m.A, m.B, m.TX, m.TY};
+    }
+    tvl1_relax4(window, n, lambda, 100, smooth);
+    const int mid = (int)(s - first);
+    SimilarityTransform out;
+    out.A = smooth[mid][0];
+    out.B = smooth[mid][1];
+    out.TX = smooth[mid][2];
+    out.TY = smooth[mid][3];
+    return out;
+}
+
+}  // namespace vstab
+
 bool L1SmootherCenter::update(const SimilarityTransform& meas, SimilarityTransform& outFinalized)
 {
     m_measurements.push_back(meas);
     const int newest = (int)m_measurements.size() - 1;
     if (m_nextToFinalize + m_lagAhead > newest) return false;
-
-    const int first = std::max(0, m_nextToFinalize - m_lagBehind);
-    const int last = m_nextToFinalize + m_lagAhead;
-    const int n = last - first + 1;
-    // one window, the four parameters as the four lanes of a vector
-    std::vector<vstab::v4d> window(n), smooth(n);
-    for (int i = 0; i < n; i++) {
-        const SimilarityTransform& m = m_measurements[first + i];
-        window[i] = (vstab::v4d){m.A, m.B, m.TX, m.TY};
-    }
-    vstab::tvl1_relax4(window.data(), n, m_lambda, 100, smooth.data());
-    const int mid = m_nextToFinalize - first;
-    outFinalized.A = smooth[mid][0];
-    outFinalized.B = smooth[mid][1];
-    outFinalized.TX = smooth[mid][2];
-    outFinalized.TY = smooth[mid][3];
+    outFinalized = vstab::smoother_finalize(m_measurements.data(), m_nextToFinalize, m_lagBehind, m_lagAhead, m_lambda);
     m_nextToFinalize++;
     return true;
 }

@@ -28,4 +28,8 @@ namespace vstab {
 // sweeps of (a) a half step of every sample back towards its datum and (b) a sequential
 // pass over neighbouring pairs that shrinks |x[i+1]-x[i]| by lambda or merges the pair.
 void tvl1_relax(const double* data, int n, double lambda, int iterations, double* x);
+// The value L1SmootherCenter::update finalises for measurement s (smoother.cpp:84-125 upstream): the relaxation of the raw
+// window [max(0, s - lagBehind), s + lagAhead], read from `meas` (measurement 0 first).  A pure function of the raw
+// measurements: values of different s are independent of each other.
+SimilarityTransform smoother_finalize(const SimilarityTransform* meas, long s, int lagBehind, int lagAhead, double lambda);
 }  // namespace vstab

@@ -9,12 +9,13 @@
 #include <stdexcept>
 
 #include "aligner_impl.hpp"
+#include "trajectory.hpp"
 
 namespace vstab {
 
 StabilizerTrajectory::StabilizerTrajectory(const VideoStabilizerParams& params)
     // upstream passes (lag, smoother_memory) as (lagBehind, lagAhead): reference stabilizer.cpp:4
-    : m_params(params), m_smoother(params.lag, params.smoother_memory, params.lambda)
+    : m_params(params), m_smoother(params.lag, params.smoother_memory, params.lambda), m_chain(params)
 {
 }
 
@@ -26,33 +27,14 @@ bool StabilizerTrajectory::push(const SimilarityTransform& measurement, bool suc
     // upstream, and that is reproduced here, not repaired.
     SimilarityTransform smoothed;
     if (m_params.enable_smoother) m_smoother.update(measurement, smoothed);
-    if (!success) m_accum = SimilarityTransform();
     m_measurements.push_back(measurement);
-    if (m_measurements.size() <= (size_t)m_params.lag) return false;
-
-    const SimilarityTransform oldest = m_measurements.front();
-    m_measurements.pop_front();
-    const SimilarityTransform jitter = m_params.enable_smoother ? oldest.compose(smoothed.inverse()) : oldest;
-    SimilarityTransform next = m_accum.compose(jitter);
-
-    const double displacement = next.maxCornerDisplacement(frame_width, frame_height);
-    double decay;
-    if (displacement > m_params.max_disp) {
-        decay = m_params.max_decay;
-    } else if (displacement > m_params.min_disp) {
-        double f = (displacement - m_params.min_disp) / (m_params.max_disp - m_params.min_disp);
-        f = std::max(0.0, std::min(1.0, f));
-        decay = m_params.min_decay * (1.0 - f) + m_params.max_decay * f;
-    } else {
-        decay = m_params.min_decay;
+    const long n = m_pushes++;
+    SimilarityTransform oldest;
+    if (m_measurements.size() > (size_t)std::max(0, m_params.lag)) {
+        oldest = m_measurements.front();
+        m_measurements.pop_front();
     }
-    next.TX *= decay;
-    next.TY *= decay;
-    next.A *= decay;
-    next.B *= decay;
-    m_accum = next;
-    correction = next.inverse();
-    return true;
+    return m_chain.step(n, success, oldest, smoothed, frame_width, frame_height, correction);
 }
 
 }  // namespace vstab

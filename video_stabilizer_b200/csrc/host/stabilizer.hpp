@@ -27,6 +27,23 @@ struct VideoStabilizerParams {
 
 namespace vstab {
 
+// The sequential part of the trajectory for one push (reference stabilizer.cpp:39-88): reset on failure, accumulate the
+// jitter of the frame `lag` pushes back, decay, invert.  See trajectory.hpp for the smoothed value it takes.
+class TrajectoryChain {
+public:
+    explicit TrajectoryChain(const VideoStabilizerParams& params) : m_params(params) {}
+    // push n: `success` is AlignNextFrame's return value for frame n; when n >= lag, `oldest` is the measurement of frame
+    // n - lag and `smoothed` the smoother's output at this push (identity while it has none); returns true and the
+    // correction of frame n - lag then.
+    bool step(long n, bool success, const SimilarityTransform& oldest, const SimilarityTransform& smoothed,
+              int frame_width, int frame_height, SimilarityTransform& correction);
+    const SimilarityTransform& accumulated() const { return m_accum; }
+
+private:
+    VideoStabilizerParams m_params;
+    SimilarityTransform m_accum;
+};
+
 // The sequential, host-side half of the stabilizer (reference stabilizer.cpp:19-88):
 // measurement in, correction for the frame `lag` frames back out.  Shared by
 // VideoStabilizer::processFrame and the batched clip pipeline so both produce the same
@@ -39,13 +56,14 @@ public:
     // transform to warp it by (inverse of the decayed accumulated jitter).
     bool push(const SimilarityTransform& measurement, bool success, int frame_width, int frame_height,
               SimilarityTransform& correction);
-    const SimilarityTransform& accumulated() const { return m_accum; }
+    const SimilarityTransform& accumulated() const { return m_chain.accumulated(); }
 
 private:
     VideoStabilizerParams m_params;
     L1SmootherCenter m_smoother;
+    TrajectoryChain m_chain;
     std::deque<SimilarityTransform> m_measurements;
-    SimilarityTransform m_accum;
+    long m_pushes = 0;
 };
 
 }  // namespace vstab

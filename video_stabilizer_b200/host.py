@@ -73,6 +73,22 @@ SYMBOLS = {
     "vsh_multigpu_destroy": (None, [_P]),
     "vsh_multigpu_stabilize": (_I, [_P, _P, _I, _I64, _I64, _P, _I64, _P, _P]),
     "vsh_clipstab_clip": (_P, [_P]),
+    "vsh_parttraj_create": (_P, [_I, _I, _I, _I, _I64, _I, _I, _SP, C.c_char_p, _I]),
+    "vsh_parttraj_destroy": (None, [_P]),
+    "vsh_parttraj_output_count": (_I, [_P]),
+    "vsh_parttraj_run": (_I, [_P, _P, _P, _P, _P]),
+    "vsh_partstab_create": (_P, [_I, _I, _I, _I, _I, _I64, _I, _I, _SP, C.c_char_p, _I, _I]),
+    "vsh_partstab_destroy": (None, [_P]),
+    "vsh_partstab_local_count": (_I, [_P]),
+    "vsh_partstab_local_frame": (_I64, [_P, _I]),
+    "vsh_partstab_local_is_halo": (_I, [_P, _I]),
+    "vsh_partstab_output_count": (_I, [_P]),
+    "vsh_partstab_output_frame": (_I, [_P, _I]),
+    "vsh_partstab_upload_resident": (_I, [_P, _P, _I64, _I64, _I]),
+    "vsh_partstab_stabilize": (_I, [_P, _P, _I64, _I64, _P, _I64, _I]),
+    "vsh_partstab_records": (_I64, [_P, _P, _P, _P]),
+    "vsh_partstab_out_size": (_I, [_P, _PI, _PI]),
+    "vsh_partstab_context": (_P, [_P]),
 }
 
 _lib = None
@@ -424,3 +440,89 @@ class MultiGpuStabilizer(_Handle):
         if k < 0:
             _raise("stabilize")
         return out[:k], meas, ok.astype(bool)
+
+
+class PartitionedTrajectory(_Handle):
+    """Host half of a worker of a partitioned video (partitioned.hpp): no GPU involved."""
+    _destroy = "vsh_parttraj_destroy"
+
+    def __init__(self, rank, world, width, height, total_frames, sub_frames, block, params: VshStabParams | None = None,
+                 exchange_name: str = "", host_threads: int = 2):
+        self.params = params or stab_params_default()
+        self.h = C.c_void_p(load().vsh_parttraj_create(rank, world, width, height, total_frames, sub_frames, block,
+                                                       C.byref(self.params), exchange_name.encode(), host_threads))
+        if not self.h:
+            _raise("PartitionedTrajectory")
+        self.outputs = load().vsh_parttraj_output_count(self.h)
+
+    def run(self, meas_all, ok_all):
+        """One video from its full measurement table: returns (frame indices, corrections) of this worker's outputs."""
+        m = np.ascontiguousarray(meas_all, np.float64)
+        o = np.ascontiguousarray(ok_all, np.uint8)
+        corr, frames = np.zeros((self.outputs, 4)), np.zeros(self.outputs, np.int64)
+        k = load().vsh_parttraj_run(self.h, _p(m), _p(o), _p(corr), _p(frames))
+        if k < 0:
+            _raise("PartitionedTrajectory.run")
+        assert k == self.outputs, (k, self.outputs)
+        return frames, corr
+
+
+class PartitionedStabilizer(_Handle):
+    """One worker (GPU) of ONE video partitioned by frame chunk over several workers (partitioned.hpp)."""
+    _destroy = "vsh_partstab_destroy"
+
+    def __init__(self, rank, world, width, height, total_frames, sub_frames, block, params: VshStabParams | None = None,
+                 exchange_name: str = "", resident: bool = True, device: int = 0, host_threads: int = 4):
+        self.params = params or stab_params_default()
+        self.width, self.height = width, height
+        self.h = C.c_void_p(load().vsh_partstab_create(device, rank, world, width, height, total_frames, sub_frames, block,
+                                                       C.byref(self.params), exchange_name.encode(), int(resident), host_threads))
+        if not self.h:
+            _raise("PartitionedStabilizer")
+        lib = load()
+        ow, oh = C.c_int(), C.c_int()
+        lib.vsh_partstab_out_size(self.h, C.byref(ow), C.byref(oh))
+        self.out_w, self.out_h = ow.value, oh.value
+        self.out_frame_bytes = self.out_w * self.out_h * 3
+        self.ctx_handle = C.c_void_p(lib.vsh_partstab_context(self.h))
+        n = lib.vsh_partstab_local_count(self.h)
+        self.local_frames = np.array([lib.vsh_partstab_local_frame(self.h, i) for i in range(n)], np.int64)
+        self.local_is_halo = np.array([lib.vsh_partstab_local_is_halo(self.h, i) for i in range(n)], bool)
+        self.outputs = lib.vsh_partstab_output_count(self.h)
+        self.output_frames = np.array([lib.vsh_partstab_output_frame(self.h, k) for k in range(self.outputs)], np.int64)
+
+    def upload_resident(self, ptr: int, row_stride: int, frame_stride: int, mem: int = capi.VS_MEM_HOST):
+        if load().vsh_partstab_upload_resident(self.h, C.c_void_p(ptr), row_stride, frame_stride, mem) < 0:
+            _raise("upload_resident")
+
+    def stabilize_ptr(self, frames_ptr: int | None, row_stride: int, frame_stride: int, out_ptr: int, out_mem: int) -> int:
+        k = load().vsh_partstab_stabilize(self.h, C.c_void_p(frames_ptr or 0), row_stride, frame_stride, C.c_void_p(out_ptr),
+                                          self.out_frame_bytes, out_mem)
+        if k < 0:
+            _raise("stabilize")
+        return k
+
+    def stabilize(self, local_frames: np.ndarray | None) -> np.ndarray:
+        """local_frames: (local_count,h,w,3) u8 host array (None when resident); returns this worker's stabilized frames."""
+        out = np.empty((max(self.outputs, 1), self.out_h, self.out_w, 3), np.uint8)
+        if local_frames is None:
+            k = self.stabilize_ptr(None, 0, 0, out.ctypes.data, capi.VS_MEM_HOST)
+        else:
+            f = np.ascontiguousarray(local_frames, np.uint8)
+            k = self.stabilize_ptr(f.ctypes.data, f.strides[1], f.strides[0], out.ctypes.data, capi.VS_MEM_HOST)
+        return out[:k]
+
+    def records(self, total_frames: int):
+        corr, meas, ok = np.zeros((max(self.outputs, 1), 4)), np.zeros((total_frames, 4)), np.zeros(total_frames, np.uint8)
+        seen = load().vsh_partstab_records(self.h, _p(corr), _p(meas), _p(ok))
+        return corr[: self.outputs], meas[:seen], ok[:seen].astype(bool)
+
+    @property
+    def launches(self) -> int:
+        return int(capi.load().vs_ctx_launch_count(self.ctx_handle))
+
+    def set_stream(self, stream: int | None):
+        capi.check(self.ctx_handle, capi.load().vs_ctx_set_stream(self.ctx_handle, C.c_void_p(stream or 0)), "vs_ctx_set_stream")
+
+    def synchronize(self):
+        capi.check(self.ctx_handle, capi.load().vs_ctx_synchronize(self.ctx_handle), "vs_ctx_synchronize")
