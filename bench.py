@@ -1,20 +1,26 @@
 #!/usr/bin/env python
 """bench.py — stabilized frames/s of the alignment-and-warp hot path on B200.
 
-Workload (BASELINE.json configs[1], "video_test"): a 1920x1080 synthetic, procedurally
-jittered 300-frame BGR clip through the full pipeline — BGR->gray + pyramid, keyframe
-features, batched sparse Lucas-Kanade solve, the sequential host L1 smoother, cv-exact BGR
-warp — with VideoStabilizerParams as video_test.cpp:53-54 sets them (crop_pixels = 0).
-One step = one pass of the whole clip.  With N GPUs every rank stabilizes its own clip
-(independent clips, no collective on the data path): weak scaling, value = all frames / max
-step time over ranks.
+Workload (BASELINE.json configs[1], "video_test"): ONE 1920x1080 synthetic, procedurally jittered BGR video of
+300 frames PER GPU through the full pipeline — fused BGR->gray + pyramid ingest, keyframe features, batched sparse
+Lucas-Kanade solve, the host L1 smoother, cv-exact BGR warp — with VideoStabilizerParams as video_test.cpp:53-54 sets
+them (crop_pixels = 0).  With N GPUs the video is N x 300 frames long and is partitioned by frame chunk (north_star):
+rank r owns the contiguous frames [300 r, 300 r + 300) plus one halo frame, the 40 bytes per pair go to a table in host
+shared memory, every rank runs its share of the smoothing and the (cheap, sequential) accumulate chain and warps its own
+frames.  No collective on the data path (NCCL only carries the barrier and the MAX of the step time): weak scaling,
+value = all frames / max step time over ranks.  One step = `--passes` videos back to back (so that the timed region of
+the default --steps is about a second).
 
-  value  frames/s with the clip already resident in HBM (CUDA events, max over ranks)
-  e2e    frames/s through ClipStabilizer::feed() with HOST buffers: pinned H2D of every
-         frame and D2H of every stabilized frame inside the timed region
+  value  frames/s with the frames already resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e    frames/s through PartitionedStabilizer::stabilize() with HOST buffers: pinned H2D of every frame and D2H of
+         every stabilized frame inside the timed region; here the video is interleaved over the ranks in 32-frame
+         sub-chunks so that every GPU uploads, computes and downloads all the time.  `host_ceiling` is the box's own
+         pinned-copy rate with all N GPUs copying both ways at once, measured in the same run.
   roofline      dominant kernel of the timed region: algorithmic bytes / its CUDA-event time
-  cpu_baseline  the reference's own host sources (oracle/_ref) or the oracle port, timed on
-                this box's cores on a bounded sample of the same workload (rank 0, N=1)
+  cpu_baseline  the reference's own host sources (oracle/_ref) or the oracle port, timed on this box's cores on a
+                bounded sample of the same workload (rank 0, N=1)
+  extra         4K (120 frames per GPU) through the same partitioned pipeline at every N; at N=1 also configs[3]
+                (64 x 720p clips in shared launches) and the configs[4] BGR warp sweep
 
 `--impl reference` times the reference CPU implementation instead (rank 0 only).
 """
@@ -28,6 +34,7 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 import numpy as np
 
@@ -37,6 +44,7 @@ if REPO not in sys.path:
 
 METRIC = "stabilized_frames_per_sec_1080p"
 UNIT = "frames/s"
+CLIP_SEED = 100
 
 
 def level_table(w, h, min_w=20, min_h=20):
@@ -65,17 +73,17 @@ def level_table(w, h, min_w=20, min_h=20):
 
 
 def algorithmic_bytes(w, h, crop, n_frames, n_keyframes, n_pairs, n_warped):
-    """Compulsory HBM traffic per launch of each kernel (each input byte read once, each
-    output byte written once), BASELINE.md section 4 / DESIGN.md."""
+    """Compulsory HBM traffic per video of each kernel (each input byte read once, each output byte written once),
+    BASELINE.md section 4 / DESIGN.md.  pyr_down: the levels below level 1 when the ingest is fused (16-aligned widths)."""
     lv = level_table(w, h)
     px = [L["w"] * L["h"] for L in lv]
     tiles = sum(L["tiles"] for L in lv)
     ow, oh = w - 2 * crop, h - 2 * crop
+    fused = w % 16 == 0 and len(px) > 1
     return {
         "bgr2gray": 4 * w * h * n_frames,
         "ingest_bgr_gray_l1": (3 * w * h + px[0] + px[1]) * n_frames,
-        # one launch per level; the per-launch figure reported is the L0->L1 launch (3/4 of the bytes)
-        "pyr_down": (px[0] + px[1]) * n_frames,
+        "pyr_down": sum(px[i] + px[i + 1] for i in range(1 if fused else 0, len(px) - 1)) * n_frames,
         "keyframe_features": (sum(px) + 40 * tiles) * n_keyframes,
         # both pyramids of a pair read once + keypoints/Jacobians of the keyframe + 40 B out
         "solve_pairs": (2 * sum(px) + 2 * tiles * 20 + 40) * n_pairs,
@@ -127,21 +135,44 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(args, world=None):
+    """The workload both arms are quoted on (the CPU arm times a bounded sample of it and says which)."""
+    world = world or args.gpus
+    return {
+        "workload": "video_test: one %dx%d synthetic procedurally-jittered BGR video of %d frames per GPU, full pipeline "
+                    "(BGR->gray pyramid, keyframe features, sparse LK solve, host L1 smoother, cv-exact BGR warp), "
+                    "VideoStabilizerParams of video_test.cpp:53-54 (crop_pixels=%d, lag=10)" % (args.width, args.height, args.frames, args.crop),
+        "frames_per_video_per_gpu": args.frames, "width": args.width, "height": args.height,
+        "partition": "frame-chunk of one video: rank r owns frames [%d r, %d r + %d) + 1 halo frame; 40 B per pair to a table "
+                     "in host shared memory; no collective on the data path" % (args.frames, args.frames, args.frames),
+        "l2": "inputs larger than L2: %.2f GB of frames read per video per GPU vs 126 MB L2" % (args.frames * args.width * args.height * 3 / 1e9),
+    }
+
+
 # ----------------------------------------------------------------------------- CPU reference
-def _cpu_frames(width, height, n, seed):
-    """A short clip of the same synthetic workload for the CPU arm (numpy renderer: no GPU needed)."""
+def _cpu_clip(width, height, n, seed):
+    """The first n frames of the very clip rank 0 of the GPU arm stabilizes (same canvas, same poses, same bytes: the
+    renderer is the cv-exact integer warp), rendered on the host by the oracle's C restatement of cv::warpAffine."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import binding as ob
     from video_stabilizer_b200 import synth
-    return synth.make_clip_numpy(width, height, n, seed)[0]
+    ob.load(fast=True)
+    canvas = synth.make_canvas(width, height, 1000 + seed)
+    poses = synth.jitter_path(max(n, 1), 1001 + seed)
+    frames = np.empty((n, height, width, 3), np.uint8)
+
+    def one(t):
+        ob.warp_bgr_matrix(canvas, synth.forward_matrix_for_pose(poses[t], width, height), width, height, fast=True, out=frames[t])
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        list(ex.map(one, range(n)))
+    return frames
 
 
-_CPU_CLIPS = {}
-
-
-def cpu_reference(width, height, frames_per_thread, threads, crop, passes=1, clip=None):
-    """Frames/s of the reference CPU implementation: `threads` workers, one stabilizer each (the
-    reference's scale-out recipe, grid_search_align.cpp:105-118,159-210).  Every worker plays the
-    clip forwards, then backwards, ... `passes` times (the turn-around keeps the motion continuous),
-    so the sample is threads x frames_per_thread x passes frames.  Returns (frames_per_s, kind, seconds)."""
+def cpu_reference(clip, threads, crop):
+    """Frames/s of the reference CPU implementation: `threads` workers, one VideoStabilizer each (the reference's own
+    scale-out recipe, grid_search_align.cpp:105-118,159-210), every worker stabilizing `clip` from its first frame.
+    Returns (frames_per_s, kind, seconds)."""
     from oracle import binding as ob
     use_ref = ob.ref_available()
     if use_ref:
@@ -150,19 +181,13 @@ def cpu_reference(width, height, frames_per_thread, threads, crop, passes=1, cli
         except Exception:
             use_ref = False
     kind = "reference" if use_ref else "port"
-    if clip is None:
-        key = (width, height, frames_per_thread)
-        if key not in _CPU_CLIPS:
-            _CPU_CLIPS[key] = _cpu_frames(width, height, frames_per_thread, 4242)
-        clip = _CPU_CLIPS[key]
     p = ob.stab_params_default()
     p.crop_pixels = crop
 
-    def work(t):
+    def work(_):
         st = ob.RefStabilizer(p, fast=True) if use_ref else ob.Stabilizer(p, fast=True)
-        for k in range(passes):
-            for f in (clip if k % 2 == 0 else clip[::-1]):      # read-only input shared by the workers
-                st.process(f)
+        for f in clip:      # read-only input shared by the workers
+            st.process(f)
 
     ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
     t0 = time.perf_counter()
@@ -171,13 +196,15 @@ def cpu_reference(width, height, frames_per_thread, threads, crop, passes=1, cli
     for th in ths:
         th.join()
     dt = time.perf_counter() - t0
-    return threads * len(clip) * passes / dt, kind, dt
+    return threads * len(clip) / dt, kind, dt
 
 
-def cpu_passes_for(width, height, frames_per_thread, threads, crop, target_seconds, clip=None):
-    """One calibration pass, then how many passes make the sample last about target_seconds."""
-    _, _, dt = cpu_reference(width, height, frames_per_thread, threads, crop, 1, clip)
-    return int(max(1, min(200, round(target_seconds / max(dt, 1e-3)))))
+def cpu_sample_frames(width, height, threads, crop, target_seconds, max_frames):
+    """How many leading frames of the clip make one sample last about target_seconds (calibrated on 12 frames)."""
+    clip = _cpu_clip(width, height, 12, CLIP_SEED)
+    fps, _, _ = cpu_reference(clip, threads, crop)
+    per_thread = fps / threads
+    return int(max(12, min(max_frames, round(target_seconds * per_thread))))
 
 
 def run_reference_arm(args):
@@ -186,26 +213,25 @@ def run_reference_arm(args):
         return 0
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, args.cpu_threads or cores))
-    per_thread = args.cpu_frames
-    # each step is a bounded sample sized so that the whole --steps/--warmup run stays around 2-3 minutes
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    passes = cpu_passes_for(args.width, args.height, per_thread, threads, args.crop, min(budget, 20.0))
+    # each step is a bounded sample of the workload, sized so that the whole --steps/--warmup run stays around 2-3 minutes
+    budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
+    n = cpu_sample_frames(args.width, args.height, threads, args.crop, budget, args.frames)
+    clip = _cpu_clip(args.width, args.height, n, CLIP_SEED)
     times = []
     kind = "port"
     for i in range(args.warmup + args.steps):
-        fps, kind, dt = cpu_reference(args.width, args.height, per_thread, threads, args.crop, passes)
+        fps, kind, dt = cpu_reference(clip, threads, args.crop)
         if i >= args.warmup:
             times.append(dt)
     ms = 1000.0 * float(np.mean(times))
-    frames_per_step = threads * per_thread * passes
-    value = frames_per_step / (ms / 1000.0)
-    sample = "%d threads x a %d-frame %dx%d clip played %d times (forwards/backwards) per step, one VideoStabilizer per thread" % (
-        threads, per_thread, args.width, args.height, passes)
+    value = threads * n / (ms / 1000.0)
+    sample = ("%d threads, one VideoStabilizer each, every thread stabilizes the first %d frames of the %d-frame %dx%d video of the "
+              "GPU arm (same bytes) per step" % (threads, n, args.frames, args.width, args.height))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32/f64", "data": "synthetic",
-        "config": workload_config(args, frames=frames_per_step),
+        "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -214,237 +240,389 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config(args, frames):
-    return {
-        "workload": "video_test: %dx%d synthetic procedurally-jittered BGR clip, full pipeline (BGR->gray pyramid, "
-                    "keyframe features, sparse LK solve, host L1 smoother, cv-exact BGR warp), "
-                    "VideoStabilizerParams of video_test.cpp:53-54 (crop_pixels=%d, lag=10)" % (args.width, args.height, args.crop),
-        "frames_per_step_per_gpu": frames, "width": args.width, "height": args.height,
-        "partition": "one independent clip per GPU, no collective on the data path",
-        "l2": "inputs larger than L2: %.2f GB of frames read per step vs 126 MB L2" % (frames * args.width * args.height * 3 / 1e9),
-    }
-
-
 # ----------------------------------------------------------------------------- GPU arm
-def run_gpu_arm(args):
-    import torch
-    import torch.distributed as dist
+class Ranks:
+    """torch.distributed plumbing: barrier and MAX only."""
 
-    from video_stabilizer_b200 import _capi as capi
-    from video_stabilizer_b200 import host, synth
-    from video_stabilizer_b200.imgproc import Context
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        # NCCL prints its version banner on stdout when the communicator is created: keep stdout to the one JSON line
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            # NCCL prints its version banner on stdout when the communicator is created: keep stdout to the one JSON line
             sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
-    W, H, F, crop = args.width, args.height, args.frames, args.crop
-    frame_bytes = W * H * 3
+            saved_stdout = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved_stdout, 1)
+                os.close(saved_stdout)
+            self.dist = dist
 
-    # ---- synthetic clip in pinned host memory, rendered on the GPU through vs_bgr_warp_u8
-    pinned = torch.empty((F, H, W, 3), dtype=torch.uint8, pin_memory=True)
-    frames = pinned.numpy()
-    gen_ctx = Context(local)
-    synth.make_clip_gpu(gen_ctx, W, H, F, seed=100 + rank, out=frames, chunk=50)
-    gen_ctx.close()
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    p = host.stab_params_default()
-    p.crop_pixels = crop
-    cs = host.ClipStabilizer(W, H, F, p, device=local)
-    if args.pipeline_frames:
-        cs.set_pipeline_frames(args.pipeline_frames)
-    # a real (non-default) torch stream, borrowed by the library: the CUDA events of the timed
-    # region are recorded on the stream the kernels are launched on
-    stream = torch.cuda.Stream()
-    assert stream.cuda_stream != 0
-    cs.set_stream(stream.cuda_stream)
-    SOLVER_LANES = int(os.environ.get("VSTAB_LANES", "3"))
-    cs.set_solver_lanes(SOLVER_LANES)
+    def reduce(self, v, op="max"):
+        if not self.dist:
+            return float(v)
+        t = self.torch.tensor([v], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def exchange_name(tag):
+    """POSIX shared-memory name of one video's table: the same on every rank of this job, distinct between jobs."""
+    job = os.environ.get("TORCHELASTIC_RUN_ID", "") + "_" + os.environ.get("MASTER_PORT", "0")
+    return "/vstab_%s_%s_%d" % (tag, "".join(c for c in job if c.isalnum() or c == "_")[-24:], os.getuid())
+
+
+class PartitionedVideo:
+    """One rank's share of a synthetic N x F-frame video in a given partition, with its pinned host frames."""
+
+    def __init__(self, R, args, W, H, F, sub, block, resident, tag, seed=CLIP_SEED):
+        import torch
+        from video_stabilizer_b200 import host, synth
+        from video_stabilizer_b200.imgproc import Context
+        self.R, self.W, self.H, self.F = R, W, H, F
+        self.total = R.world * F
+        p = host.stab_params_default()
+        p.crop_pixels = args.crop
+        self.params = p
+        threads = max(1, min(8, (os.cpu_count() or 1) // max(1, R.world)))
+        name = exchange_name(tag) if R.world > 1 else ""
+        # rank 0 creates the shared table; the others attach once it exists
+        if R.rank == 0:
+            self.ps = host.PartitionedStabilizer(R.rank, R.world, W, H, self.total, sub, block, p, name, resident,
+                                                 device=R.local, host_threads=threads)
+        R.barrier()
+        if R.rank != 0:
+            self.ps = host.PartitionedStabilizer(R.rank, R.world, W, H, self.total, sub, block, p, name, resident,
+                                                 device=R.local, host_threads=threads)
+        R.barrier()
+        self.host_threads = threads
+        ps = self.ps
+        n_local = len(ps.local_frames)
+        self.pinned = torch.empty((n_local, H, W, 3), dtype=torch.uint8, pin_memory=True)
+        self.frames = self.pinned.numpy()
+        ctx = Context(R.local)
+        canvas = synth.make_canvas(W, H, 1000 + seed)
+        poses = synth.jitter_path(self.total, 1001 + seed)
+        synth.render_frames_gpu(ctx, canvas, poses, ps.local_frames, W, H, self.frames, chunk=32 if W <= 1920 else 8)
+        ctx.close()
+        self.frame_bytes = W * H * 3
+        self.stream = torch.cuda.Stream()
+        assert self.stream.cuda_stream != 0
+        # a real (non-default) torch stream, borrowed by the library: the CUDA events of the timed region are recorded on
+        # the stream the kernels are launched on
+        ps.set_stream(self.stream.cuda_stream)
+        self.h2d_bytes = n_local * self.frame_bytes
+        self.d2h_bytes = ps.outputs * ps.out_frame_bytes
+
+
+def timed(R, stream, fn, steps, warmup, launches_of=None):
+    torch = R.torch
+    for _ in range(warmup):
+        fn()
+    R.barrier()
+    n0 = launches_of() if launches_of else 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    R.barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1) / steps
+    timed.launches = (launches_of() - n0) if launches_of else 0
+    return R.reduce(ms, "max"), t0, t1
+
+
+def host_copy_ceiling(R, seconds=0.4, mbytes=256):
+    """Pinned host <-> device copy rate of THIS box with every rank copying both ways at once: the denominator of the
+    end-to-end number.  Returns GB/s summed over ranks: (h2d, d2h) together, and h2d alone."""
+    torch = R.torch
+    n = mbytes << 20
+    hin = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    hout = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    din = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dout = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(both):
+        reps = 0
+        for phase in (0, 1):
+            R.barrier()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            k = 2 if phase == 0 else max(2, reps)
+            e[0].record(s_up)
+            e[2].record(s_down)
+            for _ in range(k):
+                with torch.cuda.stream(s_up):
+                    din.copy_(hin, non_blocking=True)
+                if both:
+                    with torch.cuda.stream(s_down):
+                        hout.copy_(dout, non_blocking=True)
+            e[1].record(s_up)
+            e[3].record(s_down)
+            R.barrier()
+            ms_up, ms_down = e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])
+            if phase == 0:      # the same repeat count on every rank: they must all be copying for the whole measurement
+                reps = int(R.reduce(max(2, seconds * 1e3 / max(ms_up / k, 1e-3)), "max"))
+        up = n * k / (ms_up / 1e3) / 1e9
+        down = n * k / (ms_down / 1e3) / 1e9 if both else 0.0
+        return up, down
+
+    up1, _ = run(False)
+    up2, down2 = run(True)
+    return {"h2d_alone_gbs": R.reduce(up1, "sum"), "h2d_duplex_gbs": R.reduce(up2, "sum"), "d2h_duplex_gbs": R.reduce(down2, "sum")}
+
+
+def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_sub, profile, tag, seed=CLIP_SEED):
+    """value (resident, contiguous chunk per rank) and e2e (host-streamed, interleaved sub-chunks) of one video size."""
+    import torch
+    from video_stabilizer_b200 import _capi as capi
     lib = capi.load()
-    n_out = F - p.lag
-    out_dev = torch.empty((n_out, cs.out_h, cs.out_w, 3), dtype=torch.uint8, device="cuda")
-    out_host = torch.empty((n_out, cs.out_h, cs.out_w, 3), dtype=torch.uint8, pin_memory=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        n0 = cs.launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.time()
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        barrier()
-        t1 = time.time()
-        ms = e0.elapsed_time(e1) / steps
-        timed.launches = cs.launches - n0
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, t0, t1
-
-    # ---- device-resident: frames already in the ring; a step = pyramids + features + solve +
-    #      D2H of the transforms + host trajectory + warp, outputs stay in HBM
-    cs.upload_only(0, frames.ctypes.data, F, W * 3, frame_bytes, capi.VS_MEM_HOST)
-    cs.synchronize()
+    res = {}
+    # ---- device-resident: each rank's contiguous chunk as three sub-chunks (the solve of one beside the pyramids of the next)
+    sub = F // 3 if (F // 3) % 2 == 0 and F % 3 == 0 else F
+    block = F // sub
+    if sub % 2 or F % sub or sub < 10:
+        raise SystemExit("bench.py: --frames must be even (and at least 10)")
+    pv = PartitionedVideo(R, args, W, H, F, sub, block, True, tag + "r", seed)
+    ps = pv.ps
+    ps.upload_resident(pv.frames.ctypes.data, W * 3, pv.frame_bytes)
+    ps.synchronize()
+    out_dev = torch.empty((max(ps.outputs, 1), ps.out_h, ps.out_w, 3), dtype=torch.uint8, device="cuda")
 
     def step_resident():
-        cs.reset()
-        k = cs.feed_resident(F, out_dev.data_ptr(), capi.VS_MEM_DEVICE)
-        assert k == n_out, k
+        for _ in range(passes):
+            k = ps.stabilize_ptr(None, 0, 0, out_dev.data_ptr(), capi.VS_MEM_DEVICE)
+            assert k == ps.outputs, k
 
-    # ---- end to end: host frames in, host frames out, copies inside the timed region
-    def step_e2e():
-        cs.reset()
-        k = cs.feed_ptr(frames.ctypes.data, F, W * 3, frame_bytes, capi.VS_MEM_HOST, out_host.data_ptr(), capi.VS_MEM_HOST)
-        assert k == n_out, k
+    sampler = ClockSampler(R.local) if (R.rank == 0 and profile) else None
+    ms, t0, t1 = timed(R, pv.stream, step_resident, steps, warmup, lambda: ps.launches)
+    res["ms_per_step"] = ms
+    res["launches"] = timed.launches
+    res["clocks"] = sampler.stop(t0, t1) if sampler else None
+    res["frames_per_step"] = R.world * F * passes
+    res["value"] = res["frames_per_step"] / (ms / 1e3)
+    res["sub"], res["block"], res["host_threads"] = sub, block, pv.host_threads
+    corr, meas, ok = ps.records(pv.total)
+    res["pairs_seen"] = int(len(ok) - 1)
+    res["pairs_converged"] = int(ok[1:].sum())
+    res["outputs_per_rank"] = int(ps.outputs)
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    ms, t0, t1 = timed(step_resident, args.steps, args.warmup)
-    launches = timed.launches
-    clocks = sampler.stop(t0, t1) if sampler else None
-    meas, ok, corr = cs.last_records(F)
+    # ---- per-kernel CUDA-event times over a second timed region of the same steps, with the stages back to back on
+    #      one stream (one lane): with the lanes of the timed run a kernel's events also span the kernels beside it
+    if profile:
+        ps.set_lanes(1)
+        lib.vs_ctx_profile_enable(ps.ctx_handle, 1)
+        lib.vs_ctx_profile_reset(ps.ctx_handle)
+        psteps = max(1, min(steps, 4))
+        prof_ms, _, _ = timed(R, pv.stream, step_resident, psteps, 1)
+        kernels = {}
+        for k in range(capi.VS_KERNEL_COUNT):
+            n, tot = C.c_int64(), C.c_double()
+            lib.vs_ctx_profile_read(ps.ctx_handle, k, C.byref(n), C.byref(tot))
+            if n.value:
+                kernels[lib.vs_kernel_name(k).decode()] = (n.value, tot.value)
+        lib.vs_ctx_profile_enable(ps.ctx_handle, 0)
+        ps.set_lanes(3)
+        res["kernels_raw"] = kernels
+        res["prof_videos"] = (psteps + 1) * passes
+        res["prof_ms_per_video"] = prof_ms / passes
+    n_own, n_local, n_out = int((~ps.local_is_halo).sum()), len(ps.local_frames), int(ps.outputs)
+    res["per_rank"] = {"frames": n_local, "keyframes": int((ps.local_frames % 2 == 1).sum()),
+                       "pairs": n_own - (1 if R.rank == 0 else 0), "warped": n_out}
+    del out_dev
+    pv.ps.close()
+    del pv
+    torch.cuda.empty_cache()
 
-    # ---- per-kernel CUDA-event times over a second timed region of the same steps, with the stages back to back on one
-    #      stream (one solver lane): with the lanes of the timed run a kernel's events also span the kernels beside it
-    cs.set_solver_lanes(1)
-    lib.vs_ctx_profile_enable(cs.ctx_handle, 1)
-    lib.vs_ctx_profile_reset(cs.ctx_handle)
-    prof_ms, _, _ = timed(step_resident, args.steps, 1)
-    cs.set_solver_lanes(SOLVER_LANES)
-    kernels = {}
-    for k in range(capi.VS_KERNEL_COUNT):
-        n, tot = C.c_int64(), C.c_double()
-        lib.vs_ctx_profile_read(cs.ctx_handle, k, C.byref(n), C.byref(tot))
-        if n.value:
-            kernels[lib.vs_kernel_name(k).decode()] = (n.value, tot.value)
-    lib.vs_ctx_profile_enable(cs.ctx_handle, 0)
+    # ---- end to end: host frames in, host frames out, copies inside the timed region; sub-chunks interleaved over the ranks
+    if e2e_steps > 0:
+        pe = PartitionedVideo(R, args, W, H, F, e2e_sub, 1, False, tag + "s", seed)
+        out_host = torch.empty((max(pe.ps.outputs, 1), pe.ps.out_h, pe.ps.out_w, 3), dtype=torch.uint8, pin_memory=True)
 
-    e2e_ms, _, _ = timed(step_e2e, max(1, args.steps // 2), 1)
+        def step_e2e():
+            k = pe.ps.stabilize_ptr(pe.frames.ctypes.data, W * 3, pe.frame_bytes, out_host.data_ptr(), capi.VS_MEM_HOST)
+            assert k == pe.ps.outputs, k
+
+        e2e_ms, _, _ = timed(R, pe.stream, step_e2e, e2e_steps, 1)
+        h2d = R.reduce(pe.h2d_bytes, "sum")
+        d2h = R.reduce(pe.d2h_bytes + (len(pe.ps.local_frames)) * 36, "sum")
+        res["e2e"] = {"value": R.world * F / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                      "ms_per_step": e2e_ms, "frames_per_step": R.world * F, "sub_chunk_frames": e2e_sub,
+                      "h2d_gbs": h2d / (e2e_ms / 1e3) / 1e9, "d2h_gbs": d2h / (e2e_ms / 1e3) / 1e9}
+        del out_host
+        pe.ps.close()
+        del pe
+        torch.cuda.empty_cache()
+    return res
+
+
+def run_gpu_arm(args):
+    R = Ranks()
+    torch = R.torch
+    W, H, F, crop = args.width, args.height, args.frames, args.crop
+    world, rank = R.world, R.rank
+
+    main = measure_partitioned(R, args, W, H, F, args.steps, args.warmup, args.passes, max(1, args.steps // 2), args.e2e_sub, True, "m")
+    ceiling = host_copy_ceiling(R)
+
+    extra = {}
+    if not args.no_extra:
+        # 4K (BASELINE.json metric names 1080p AND 4K; configs[2]): 120 frames per GPU through the same partitioned pipeline
+        a4 = types.SimpleNamespace(**vars(args))
+        a4.width, a4.height, a4.frames = 3840, 2160, args.frames_4k
+        r4 = measure_partitioned(R, a4, 3840, 2160, args.frames_4k, max(2, args.steps // 4), 2, max(1, args.passes // 4),
+                                 2, args.e2e_sub, False, "k", seed=CLIP_SEED + 7)
+        extra["4k"] = {"metric": "stabilized_frames_per_sec_4k", "value": r4["value"], "unit": UNIT, "n_gpus": world,
+                       "ms_per_step": r4["ms_per_step"], "frames_per_step": r4["frames_per_step"],
+                       "frames_per_video_per_gpu": args.frames_4k, "pairs_converged": r4["pairs_converged"], "pairs_seen": r4["pairs_seen"],
+                       "e2e": r4.get("e2e")}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        R.close()
         return 0
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant kernel (rank 0's share: frames incl. the halo, its pairs, its warped frames)
     peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    n_key = F // 2
-    alg = algorithmic_bytes(W, H, crop, F, n_key, F - 1, n_out)
-    steps_profiled = args.steps + 1
+    pr = main["per_rank"]
+    alg = algorithmic_bytes(W, H, crop, pr["frames"], pr["keyframes"], pr["pairs"], pr["warped"])
+    videos = main["prof_videos"]
     per_kernel = {}
-    lv = level_table(W, H)
-    px = [L["w"] * L["h"] for L in lv]
-    # algorithmic bytes of one STEP per kernel (a kernel may be launched several times per step:
-    # pyr_down once per level, bgr_warp in batches that overlap the host trajectory)
-    alg_step = dict(alg)
-    alg_step["pyr_down"] = sum(px[i] + px[i + 1] for i in range(len(px) - 1)) * F
-    for name, (n, tot) in kernels.items():
-        launches_per_step = n / steps_profiled
-        ms_step = tot / steps_profiled
-        b = alg_step.get(name)
-        gbs = (b / (ms_step / 1e3) / 1e9) if b else None
-        per_kernel[name] = {"launches_per_step": launches_per_step, "ms_per_step": ms_step,
-                            "ms_per_launch": tot / n, "algorithmic_bytes_per_step": b, "algorithmic_gbs": gbs,
+    for name, (n, tot) in main["kernels_raw"].items():
+        b = alg.get(name)
+        ms_video = tot / videos
+        gbs = (b / (ms_video / 1e3) / 1e9) if b else None
+        per_kernel[name] = {"launches_per_video": n / videos, "ms_per_video": ms_video, "ms_per_launch": tot / n,
+                            "algorithmic_bytes_per_video": b, "algorithmic_gbs": gbs,
                             "frac_of_hbm_peak": (gbs / peak) if gbs else None}
-    dominant = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
+    dominant = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_video"])
     d = per_kernel[dominant]
     traffic = None
-    tpath = os.path.join(REPO, "profiles", "traffic.json")   # dram bytes per step from the committed ncu --set full capture
-    if os.path.exists(tpath):
+    tpath = os.path.join(REPO, "profiles", "traffic.json")   # dram bytes per video per kernel from the committed ncu --set full capture
+    if os.path.exists(tpath) and (W, H, F) == (1920, 1080, 300):      # the capture is of the default configuration only
         try:
             t = json.load(open(tpath)).get(dominant)
-            traffic = t / d["launches_per_step"] if t else None
+            traffic = t / d["launches_per_video"] if t else None
         except Exception:
             traffic = None
-    second = sorted(per_kernel, key=lambda k: -per_kernel[k]["ms_per_step"])[1] if len(per_kernel) > 1 else None
+    second = sorted(per_kernel, key=lambda k: -per_kernel[k]["ms_per_video"])[1] if len(per_kernel) > 1 else None
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": d["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": d["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_step"] / d["launches_per_step"],
-                "launches_per_step": d["launches_per_step"], "ms_per_launch": d["ms_per_launch"],
-                "kernel_share_of_step": d["ms_per_step"] / max(prof_ms, 1e-9)}
+                "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_video"] / d["launches_per_video"],
+                "launches_per_video": d["launches_per_video"], "ms_per_launch": d["ms_per_launch"],
+                "kernel_share_of_step": d["ms_per_video"] / max(main["prof_ms_per_video"], 1e-9)}
     if second:
         d2 = per_kernel[second]
         roofline["runner_up"] = {"kernel": second, "achieved": d2["algorithmic_gbs"], "frac": d2["frac_of_hbm_peak"],
-                                 "ms_per_step": d2["ms_per_step"], "kernel_share_of_step": d2["ms_per_step"] / max(prof_ms, 1e-9)}
+                                 "ms_per_video": d2["ms_per_video"],
+                                 "kernel_share_of_step": d2["ms_per_video"] / max(main["prof_ms_per_video"], 1e-9)}
+    step_bytes = sum(v["algorithmic_bytes_per_video"] or 0 for v in per_kernel.values())
+    whole = {"algorithmic_bytes_per_video": step_bytes, "ms_per_video": main["ms_per_step"] / args.passes,
+             "frac_of_hbm_peak": step_bytes / (main["ms_per_step"] / args.passes / 1e3) / 1e9 / peak}
 
-    # ---- CPU baseline on this box's cores (N=1 only)
+    # ---- CPU baseline on this box's cores (N=1 only), the same clip's leading frames
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         threads = max(1, min(cores, args.cpu_threads or cores))
-        cpu_clip = frames[: args.cpu_frames]          # the first frames of the very clip the GPU arm stabilizes
-        passes = cpu_passes_for(W, H, args.cpu_frames, threads, crop, 12.0, cpu_clip)
-        fps, kind, dt = cpu_reference(W, H, args.cpu_frames, threads, crop, passes, cpu_clip)
+        n = cpu_sample_frames(W, H, threads, crop, 12.0, F)
+        fps, kind, dt = cpu_reference(_cpu_clip(W, H, n, CLIP_SEED), threads, crop)
         cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": "%d threads x the first %d frames of the %dx%d clip played %d times (forwards/backwards), one VideoStabilizer per thread, %.1f s" % (
-                   threads, args.cpu_frames, W, H, passes, dt)}
+               "sample": "%d threads, one VideoStabilizer each, every thread stabilizes the first %d frames of the %d-frame %dx%d video "
+                         "(same bytes as the GPU arm), %.1f s" % (threads, n, F, W, H, dt)}
 
-    value = world * F / (ms / 1e3)
+    # ---- N=1 only: the other BASELINE.json configs as driver-run records
+    if world == 1 and not args.no_extra:
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        try:
+            import config_bench
+            import kernel_bench
+            q = types.SimpleNamespace(clips=64, clip_frames=32, iters=3, quiet=True)
+            extra["clips720"] = config_bench.clips720(q)
+            sweep = kernel_bench.bench_warp(types.SimpleNamespace(size=None, mode=None, transform=None, iters=5, quiet=True))
+            extra["warp_sweep"] = [{k: r[k] for k in ("mode", "size", "bytes_per_launch", "ms_per_launch", "algorithmic_gbs", "frac_of_hbm_peak")}
+                                   for r in sweep]
+        except Exception as e:      # noqa: BLE001  (an extra record must not take the headline down)
+            extra["error"] = repr(e)
+
+    e2e = main["e2e"]
+    achieved = e2e["h2d_gbs"] + e2e["d2h_gbs"]
+    ceil_sum = ceiling["h2d_duplex_gbs"] + ceiling["d2h_duplex_gbs"]
+    e2e["host_ceiling"] = dict(ceiling, note="pinned copies on every rank at once, both directions together; GB/s summed over ranks")
+    e2e["frac_of_host_ceiling"] = achieved / ceil_sum if ceil_sum > 0 else None
+    e2e["value_per_gpu"] = e2e["value"] / world
+    if "4k" in extra and extra["4k"].get("e2e"):
+        x = extra["4k"]["e2e"]
+        x["frac_of_host_ceiling"] = (x["h2d_gbs"] + x["d2h_gbs"]) / ceil_sum if ceil_sum > 0 else None
+
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32/f64", "data": "synthetic",
-        "config": dict(workload_config(args, F), solver_lanes=SOLVER_LANES,
+        "config": dict(workload_config(args, world), videos_per_step=args.passes, frames_per_step=main["frames_per_step"],
+                       sub_chunk_frames=main["sub"], sub_chunks_per_rank=main["block"], host_threads_per_rank=main["host_threads"],
                        kernel_times="`kernels` and `roofline` come from a second timed region with the stages back to back on one "
-                                    "stream (one solver lane); `value` runs the chunk as %d pieces whose solves overlap the other stages" % SOLVER_LANES),
-        "e2e": {"value": world * F / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": F * frame_bytes,
-                "d2h_bytes_per_step": n_out * cs.out_frame_bytes + (F - 1) * 36, "ms_per_step": e2e_ms},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+                                    "stream (one lane); `value` runs a rank's chunk as %d sub-chunks whose solves overlap the "
+                                    "other stages" % main["block"]),
+        "e2e": e2e,
+        "gpu_launches": int(main["launches"]),
+        "clocks": main["clocks"],
         "roofline": roofline,
         "cpu_baseline": cpu,
         "kernels": per_kernel,
-        "align_ms_per_pair": sum(per_kernel[k]["ms_per_step"] for k in per_kernel if k != "bgr_warp") / (F - 1),
-        "pairs_converged": int(ok.sum()), "pairs": F - 1,
+        "whole_step": whole,
+        "value_per_gpu": main["value"] / world,
+        "align_ms_per_pair": sum(per_kernel[k]["ms_per_video"] for k in per_kernel if k != "bgr_warp") / max(pr["pairs"], 1),
+        "pairs_converged": main["pairs_converged"], "pairs": main["pairs_seen"],
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    R.close()
     return 0
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--frames", type=int, default=300, help="frames of the video per GPU")
+    ap.add_argument("--frames-4k", type=int, default=120, help="frames per GPU of the 4K extra record")
     ap.add_argument("--crop", type=int, default=0)
-    ap.add_argument("--cpu-frames", type=int, default=16, help="frames per CPU worker thread in the CPU arm / baseline")
+    ap.add_argument("--passes", type=int, default=10, help="videos per step (device-resident number)")
+    ap.add_argument("--e2e-sub", type=int, default=32, help="sub-chunk (frames) of the host-streamed partition")
     ap.add_argument("--cpu-threads", type=int, default=0, help="CPU worker threads (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline-frames", type=int, default=0, help="sub-chunk of the host-to-host pipeline (0 = library default)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the 4K / configs[3] / warp-sweep records")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

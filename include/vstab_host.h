@@ -136,6 +136,8 @@ int     vsh_partstab_stabilize(void*, const uint8_t* frames, int64_t row_stride,
                                int64_t out_frame_stride, int out_mem);
 /* after stabilize: corrections (outputs x 4), the measurements / status of the frames this worker has seen; returns how many */
 int64_t vsh_partstab_records(void*, double* corrections, double* meas, uint8_t* ok);
+/* sub-chunks in flight on the GPU, one solver lane each (default 3 resident, 2 streamed); 1 = every stage back to back */
+int     vsh_partstab_set_lanes(void*, int lanes);
 int     vsh_partstab_out_size(void*, int* w, int* h);
 vs_ctx* vsh_partstab_context(void*);
 

@@ -81,6 +81,7 @@ def load(fast: bool = False):
     lib.vo_sparse_ica.argtypes = [P, P, I, I, P, I, P, I, P, P, P, P]
     lib.vo_image_warp.argtypes = [P, I, I, P, P, I, I]
     lib.vo_warp_bgr.argtypes = [P, I, I, P, P, I, I, I]
+    lib.vo_warp_bgr_matrix.argtypes = [P, I, I, P, P, I, I, I, I, I, I]
     lib.vo_tf_inverse.argtypes = [P, P]
     lib.vo_optimal_dft_size.argtypes = [I]
     lib.vo_phase_correlate_u8.argtypes = [P, P, I, I, P]
@@ -219,6 +220,18 @@ def warp_bgr(src, T, mode=0, border=0, crop=0, fast=False):
     out = np.empty((h - 2 * crop, w - 2 * crop, 3), np.uint8)
     T = _t(T)
     load(fast).vo_warp_bgr(_p(src), w, h, _p(T), _p(out), mode, border, crop)
+    return out
+
+
+def warp_bgr_matrix(src, M6, out_w, out_h, dx0=0, dy0=0, mode=0, border=0, fast=False, out=None):
+    """cv::warpAffine(src, M (forward 2x3), Size(out_w + dx0.., ..)) restated: window (dx0, dy0, out_w, out_h) of the output."""
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w, _ = src.shape
+    if out is None:
+        out = np.empty((out_h, out_w, 3), np.uint8)
+    assert out.flags.c_contiguous and out.shape == (out_h, out_w, 3)
+    M = np.ascontiguousarray(M6, np.float64)
+    load(fast).vo_warp_bgr_matrix(_p(src), w, h, _p(M), _p(out), out_w, out_h, dx0, dy0, mode, border)
     return out
 
 

@@ -318,13 +318,12 @@ void vo_image_warp(const uint8_t* in, int iw, int ih, const double T[4],
 // here for the interpolation sweep (BASELINE.json configs[4]).
 static inline long rint_he(double v) { return std::lrint(v); } // round-half-even (default FE mode)
 
-void vo_warp_bgr(const uint8_t* src, int w, int h, const double T[4],
-                 uint8_t* dst, int mode, int border, int crop)
+// General form: forward 2x3 matrix M (as cv::warpAffine takes it), source sw x sh, destination window dw x dh whose pixel
+// (x, y) is output pixel (x + dx0, y + dy0) of the warp.  vo_warp_bgr below and the synthetic-clip renderer use it.
+void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uint8_t* dst, int ow, int oh, int dx0, int dy0,
+                        int mode, int border)
 {
-    double A = T[0], B = T[1];
-    double cx = (w - 1) * 0.5, cy = (h - 1) * 0.5;
-    double m00 = 1.0 + A, m01 = -B, m02 = T[2] - A * cx + B * cy;
-    double m10 = B, m11 = 1.0 + A, m12 = T[3] - B * cx - A * cy;
+    const double m00 = M[0], m01 = M[1], m02 = M[2], m10 = M[3], m11 = M[4], m12 = M[5];
     // cv::warpAffine: invert the 2x3 matrix
     double D = m00 * m11 - m01 * m10;
     D = D != 0 ? 1.0 / D : 0;
@@ -332,25 +331,33 @@ void vo_warp_bgr(const uint8_t* src, int w, int h, const double T[4],
     double i02 = -i00 * m02 - i01 * m12;
     double i12 = -i10 * m02 - i11 * m12;
 
-    int ow = w - 2 * crop, oh = h - 2 * crop;
     if (mode == 0) {
-        std::vector<int> adelta(w), bdelta(w);
-        for (int x = 0; x < w; x++) {
-            adelta[x] = (int)rint_he(i00 * x * 1024);
-            bdelta[x] = (int)rint_he(i10 * x * 1024);
+        std::vector<int> adelta(ow), bdelta(ow);
+        for (int xo = 0; xo < ow; xo++) {
+            adelta[xo] = (int)rint_he(i00 * (xo + dx0) * 1024);
+            bdelta[xo] = (int)rint_he(i10 * (xo + dx0) * 1024);
         }
         for (int yo = 0; yo < oh; yo++) {
-            int y = yo + crop;
+            int y = yo + dy0;
             int X0 = (int)rint_he((i01 * y + i02) * 1024) + 16;
             int Y0 = (int)rint_he((i11 * y + i12) * 1024) + 16;
             for (int xo = 0; xo < ow; xo++) {
-                int x = xo + crop;
-                int X = (X0 + adelta[x]) >> 5, Y = (Y0 + bdelta[x]) >> 5;
+                int X = (X0 + adelta[xo]) >> 5, Y = (Y0 + bdelta[xo]) >> 5;
                 int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
                 // 15-bit weights: rint(32768 * (1-fy/32)(1-fx/32)) — exact, sum is 32768
                 int w00 = (32 - fx) * (32 - fy) * 32, w10 = fx * (32 - fy) * 32;
                 int w01 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
                 uint8_t* d = dst + ((size_t)yo * ow + xo) * 3;
+                const bool inside = sx >= 0 && sx + 1 < w && sy >= 0 && sy + 1 < h;
+                if (inside) {
+                    const uint8_t* p0 = src + ((size_t)sy * w + sx) * 3;
+                    const uint8_t* p1 = p0 + (size_t)w * 3;
+                    for (int c = 0; c < 3; c++) {
+                        int v = w00 * p0[c] + w10 * p0[3 + c] + w01 * p1[c] + w11 * p1[3 + c];
+                        d[c] = (uint8_t)((v + 16384) >> 15);
+                    }
+                    continue;
+                }
                 for (int c = 0; c < 3; c++) {
                     auto tap = [&](int xx, int yy) -> int {
                         if (border == 1) { xx = clampi(xx, 0, w - 1); yy = clampi(yy, 0, h - 1); }
@@ -369,9 +376,9 @@ void vo_warp_bgr(const uint8_t* src, int w, int h, const double T[4],
     float f00 = (float)i00, f01 = (float)i01, f02 = (float)i02;
     float f10 = (float)i10, f11 = (float)i11, f12 = (float)i12;
     for (int yo = 0; yo < oh; yo++) {
-        int y = yo + crop;
+        int y = yo + dy0;
         for (int xo = 0; xo < ow; xo++) {
-            int x = xo + crop;
+            int x = xo + dx0;
             float Wx = f00 * (float)x + f01 * (float)y + f02;
             float Wy = f10 * (float)x + f11 * (float)y + f12;
             float fWx = std::floor(Wx), fWy = std::floor(Wy);
@@ -413,6 +420,16 @@ void vo_warp_bgr(const uint8_t* src, int w, int h, const double T[4],
             }
         }
     }
+}
+
+// imgproc.cpp:458-466: centre-based similarity -> forward matrix, same-size output cropped by `crop` on every side
+void vo_warp_bgr(const uint8_t* src, int w, int h, const double T[4],
+                 uint8_t* dst, int mode, int border, int crop)
+{
+    double A = T[0], B = T[1];
+    double cx = (w - 1) * 0.5, cy = (h - 1) * 0.5;
+    const double M[6] = {1.0 + A, -B, T[2] - A * cx + B * cy, B, 1.0 + A, T[3] - B * cx - A * cy};
+    vo_warp_bgr_matrix(src, w, h, M, dst, w - 2 * crop, h - 2 * crop, crop, crop, mode, border);
 }
 
 //------------------------------------------------------------------------------

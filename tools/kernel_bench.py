@@ -51,6 +51,7 @@ def time_launches(torch, fn, iters):
 
 
 def bench_warp(args):
+    """Returns the list of records (and prints each as a JSON line unless args.quiet)."""
     import torch
     from video_stabilizer_b200 import _capi as capi
     from video_stabilizer_b200.imgproc import Context
@@ -62,6 +63,7 @@ def bench_warp(args):
     modes = [(0, "cv_exact_bilinear"), (1, "float_bilinear"), (2, "lanczos2")]
     if args.mode is not None:
         modes = [m for m in modes if m[0] == args.mode]
+    records = []
     T = np.array([0.0013, -0.0021, 6.37, -3.81])
     if args.transform:
         T = np.array([float(v) for v in args.transform.split(",")])   # e.g. 0,0,0,0 (a camera standing still) or 0,0,5,-3
@@ -80,10 +82,14 @@ def bench_warp(args):
                                                           capi.VS_BORDER_CONSTANT0, capi.VS_MEM_DEVICE), "vs_bgr_warp_u8")
             ms = time_launches(torch, fn, args.iters)
             gbs = 6.0 * w * h * batch / (ms / 1e3) / 1e9
-            print(json.dumps({"kernel": "bgr_warp", "mode": name, "size": "%dx%d" % (w, h), "batch": batch, "transform": T.tolist(),
-                              "ms_per_launch": ms, "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak(),
-                              "frames_per_s": batch / (ms / 1e3)}), flush=True)
+            rec = {"kernel": "bgr_warp", "mode": name, "size": "%dx%d" % (w, h), "batch": batch, "transform": T.tolist(),
+                   "bytes_per_launch": 6 * w * h * batch, "ms_per_launch": ms, "algorithmic_gbs": gbs,
+                   "frac_of_hbm_peak": gbs / peak(), "frames_per_s": batch / (ms / 1e3)}
+            records.append(rec)
+            if not getattr(args, "quiet", False):
+                print(json.dumps(rec), flush=True)
         del src, dst
+    return records
 
 
 def bench_pyramid(args):

@@ -405,6 +405,7 @@ int vsh_partstab_out_size(void* s, int* w, int* h)
     *w = ((vstab::PartitionedStabilizer*)s)->out_width(); *h = ((vstab::PartitionedStabilizer*)s)->out_height();
     return 0;
 }
+int vsh_partstab_set_lanes(void* s, int lanes) { ((vstab::PartitionedStabilizer*)s)->set_lanes(lanes); return 0; }
 vs_ctx* vsh_partstab_context(void* s) { return ((vstab::PartitionedStabilizer*)s)->context(); }
 
 vs_ctx* vsh_clipstab_context(void* c) { return ((vstab::ClipStabilizer*)c)->context(); }

@@ -140,14 +140,14 @@ PartitionedStabilizer::PartitionedStabilizer(int device, int rank, int world, in
       m_traj(rank, world, width, height, total_frames, sub_frames, block_subchunks, params, exchange_name, host_threads)
 {
     if (2 * m_crop >= width || 2 * m_crop >= height) throw std::runtime_error("PartitionedStabilizer: crop_pixels removes the whole frame");
-    m_lanes = resident ? 3 : 2;
+    m_lanes = m_max_lanes = resident ? 3 : 2;
     const int locals = m_traj.local_count();
-    m_capacity = std::max(2, resident ? locals : std::min(locals, (m_lanes + 1) * (sub_frames + 1)));
+    m_capacity = std::max(2, resident ? locals : std::min(locals, (m_max_lanes + 1) * (sub_frames + 1)));
     if (vs_ctx_create(device, &m_ctx) != VS_OK)
         throw std::runtime_error(std::string("PartitionedStabilizer: cannot create a GPU context: ") + vs_last_error(nullptr));
     vs_align_params cp;
     to_c_params(params.aligner, &cp);
-    if (vs_clip_create(m_ctx, width, height, m_capacity, m_lanes * sub_frames, &cp, 0, &m_clip) != VS_OK) {
+    if (vs_clip_create(m_ctx, width, height, m_capacity, m_max_lanes * sub_frames, &cp, 0, &m_clip) != VS_OK) {
         const std::string msg = std::string("PartitionedStabilizer: ") + vs_last_error(m_ctx);
         vs_ctx_destroy(m_ctx);
         m_ctx = nullptr;

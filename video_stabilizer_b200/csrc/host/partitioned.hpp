@@ -126,6 +126,9 @@ public:
     // bytes apart, in out_mem.  Returns output_count().
     int stabilize(const uint8_t* frames, int64_t row_stride, int64_t frame_stride, uint8_t* out, int64_t out_frame_stride, int out_mem);
 
+    // sub-chunks in flight on the GPU (one solver lane each), 1 .. lanes the ring was built for; 1 = every stage back to back
+    void set_lanes(int lanes) { m_lanes = std::max(1, std::min(lanes, m_max_lanes)); }
+    int lanes() const { return m_lanes; }
     int out_width() const { return m_w - 2 * m_crop; }
     int out_height() const { return m_h - 2 * m_crop; }
     vs_ctx* context() const { return m_ctx; }
@@ -134,7 +137,7 @@ public:
 private:
     int m_w, m_h, m_crop;
     bool m_resident;
-    int m_lanes = 3;
+    int m_lanes = 3, m_max_lanes = 3;
     VideoStabilizerParams m_params;
     PartitionedTrajectory m_traj;
     vs_ctx* m_ctx = nullptr;

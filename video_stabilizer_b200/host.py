@@ -88,6 +88,7 @@ SYMBOLS = {
     "vsh_partstab_stabilize": (_I, [_P, _P, _I64, _I64, _P, _I64, _I]),
     "vsh_partstab_records": (_I64, [_P, _P, _P, _P]),
     "vsh_partstab_out_size": (_I, [_P, _PI, _PI]),
+    "vsh_partstab_set_lanes": (_I, [_P, _I]),
     "vsh_partstab_context": (_P, [_P]),
 }
 
@@ -511,6 +512,9 @@ class PartitionedStabilizer(_Handle):
             f = np.ascontiguousarray(local_frames, np.uint8)
             k = self.stabilize_ptr(f.ctypes.data, f.strides[1], f.strides[0], out.ctypes.data, capi.VS_MEM_HOST)
         return out[:k]
+
+    def set_lanes(self, lanes: int):
+        load().vsh_partstab_set_lanes(self.h, int(lanes))
 
     def records(self, total_frames: int):
         corr, meas, ok = np.zeros((max(self.outputs, 1), 4)), np.zeros((total_frames, 4)), np.zeros(total_frames, np.uint8)

@@ -130,3 +130,22 @@ def make_clip_gpu(ctx, width: int, height: int, n_frames: int, seed: int, out: n
                                                       capi.VS_WARP_CV_EXACT_BILINEAR, capi.VS_BORDER_CONSTANT0,
                                                       capi.VS_MEM_HOST), "vs_bgr_warp_u8")
     return frames, poses
+
+
+def render_frames_gpu(ctx, canvas: np.ndarray, poses: np.ndarray, frame_indices, width: int, height: int,
+                      out: np.ndarray, chunk: int = 32) -> np.ndarray:
+    """Frames `frame_indices` of the clip (canvas, poses) into out[i] through vs_bgr_warp_u8: what make_clip_gpu does for a
+    whole clip, for any subset of it (a worker's share of a partitioned video)."""
+    from . import _capi as capi
+    ch, cw, _ = canvas.shape
+    idx = list(frame_indices)
+    for t0 in range(0, len(idx), chunk):
+        n = min(chunk, len(idx) - t0)
+        M = np.stack([forward_matrix_for_pose(poses[idx[t0 + i]], width, height) for i in range(n)])
+        src = capi.VsImg(canvas.ctypes.data, cw, ch, canvas.strides[0], n, 0)
+        dst_arr = out[t0:t0 + n]
+        dst = capi.VsImg(dst_arr.ctypes.data, width, height, dst_arr.strides[1], n, dst_arr.strides[0])
+        capi.check(ctx.handle, ctx.lib.vs_bgr_warp_u8(ctx.handle, C.byref(src), capi.ptr(M), C.byref(dst), 0, 0,
+                                                      capi.VS_WARP_CV_EXACT_BILINEAR, capi.VS_BORDER_CONSTANT0,
+                                                      capi.VS_MEM_HOST), "vs_bgr_warp_u8")
+    return out
