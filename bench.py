@@ -430,25 +430,6 @@ def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_
     res["pairs_converged"] = int(ok[1:].sum())
     res["outputs_per_rank"] = int(ps.outputs)
 
-    # ---- per-kernel CUDA-event times over a second timed region of the same steps, with the stages back to back on
-    #      one stream (one lane): with the lanes of the timed run a kernel's events also span the kernels beside it
-    if profile:
-        ps.set_lanes(1)
-        lib.vs_ctx_profile_enable(ps.ctx_handle, 1)
-        lib.vs_ctx_profile_reset(ps.ctx_handle)
-        psteps = max(1, min(steps, 4))
-        prof_ms, _, _ = timed(R, pv.stream, step_resident, psteps, 1)
-        kernels = {}
-        for k in range(capi.VS_KERNEL_COUNT):
-            n, tot = C.c_int64(), C.c_double()
-            lib.vs_ctx_profile_read(ps.ctx_handle, k, C.byref(n), C.byref(tot))
-            if n.value:
-                kernels[lib.vs_kernel_name(k).decode()] = (n.value, tot.value)
-        lib.vs_ctx_profile_enable(ps.ctx_handle, 0)
-        ps.set_lanes(3)
-        res["kernels_raw"] = kernels
-        res["prof_videos"] = (psteps + 1) * passes
-        res["prof_ms_per_video"] = prof_ms / passes
     n_own, n_local, n_out = int((~ps.local_is_halo).sum()), len(ps.local_frames), int(ps.outputs)
     res["per_rank"] = {"frames": n_local, "keyframes": int((ps.local_frames % 2 == 1).sum()),
                        "pairs": n_own - (1 if R.rank == 0 else 0), "warped": n_out}
@@ -456,6 +437,40 @@ def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_
     pv.ps.close()
     del pv
     torch.cuda.empty_cache()
+
+    # ---- per-kernel CUDA-event times over a second timed region: the rank's chunk as ONE sub-chunk, every stage one
+    #      launch, back to back on one stream (with the lanes of the timed run a kernel's events also span the kernels
+    #      beside it, and a solve lasts as long as its slowest pair however few pairs it has)
+    if profile:
+        pp = PartitionedVideo(R, args, W, H, F, F, 1, True, tag + "p", seed)
+        pp.ps.upload_resident(pp.frames.ctypes.data, W * 3, pp.frame_bytes)
+        pp.ps.set_lanes(1)
+        pp.ps.synchronize()
+        out_dev = torch.empty((max(pp.ps.outputs, 1), pp.ps.out_h, pp.ps.out_w, 3), dtype=torch.uint8, device="cuda")
+
+        def step_profile():
+            for _ in range(passes):
+                pp.ps.stabilize_ptr(None, 0, 0, out_dev.data_ptr(), capi.VS_MEM_DEVICE)
+
+        step_profile()
+        lib.vs_ctx_profile_enable(pp.ps.ctx_handle, 1)
+        lib.vs_ctx_profile_reset(pp.ps.ctx_handle)
+        psteps = max(1, min(steps, 4))
+        prof_ms, _, _ = timed(R, pp.stream, step_profile, psteps, 1)
+        kernels = {}
+        for k in range(capi.VS_KERNEL_COUNT):
+            n, tot = C.c_int64(), C.c_double()
+            lib.vs_ctx_profile_read(pp.ps.ctx_handle, k, C.byref(n), C.byref(tot))
+            if n.value:
+                kernels[lib.vs_kernel_name(k).decode()] = (n.value, tot.value)
+        lib.vs_ctx_profile_enable(pp.ps.ctx_handle, 0)
+        res["kernels_raw"] = kernels
+        res["prof_videos"] = (psteps + 1) * passes
+        res["prof_ms_per_video"] = prof_ms / passes
+        del out_dev
+        pp.ps.close()
+        del pp
+        torch.cuda.empty_cache()
 
     # ---- end to end: host frames in, host frames out, copies inside the timed region; sub-chunks interleaved over the ranks
     if e2e_steps > 0:
@@ -587,9 +602,9 @@ def run_gpu_arm(args):
         "dtype": "u8/f32/f64", "data": "synthetic",
         "config": dict(workload_config(args, world), videos_per_step=args.passes, frames_per_step=main["frames_per_step"],
                        sub_chunk_frames=main["sub"], sub_chunks_per_rank=main["block"], host_threads_per_rank=main["host_threads"],
-                       kernel_times="`kernels` and `roofline` come from a second timed region with the stages back to back on one "
-                                    "stream (one lane); `value` runs a rank's chunk as %d sub-chunks whose solves overlap the "
-                                    "other stages" % main["block"]),
+                       kernel_times="`kernels` and `roofline` come from a second timed region with a rank's chunk as one sub-chunk, "
+                                    "every stage one launch, back to back on one stream; `value` runs the chunk as %d sub-chunks "
+                                    "whose solves overlap the other stages" % main["block"]),
         "e2e": e2e,
         "gpu_launches": int(main["launches"]),
         "clocks": main["clocks"],
@@ -619,7 +634,7 @@ def main():
     ap.add_argument("--frames-4k", type=int, default=120, help="frames per GPU of the 4K extra record")
     ap.add_argument("--crop", type=int, default=0)
     ap.add_argument("--passes", type=int, default=10, help="videos per step (device-resident number)")
-    ap.add_argument("--e2e-sub", type=int, default=32, help="sub-chunk (frames) of the host-streamed partition")
+    ap.add_argument("--e2e-sub", type=int, default=16, help="sub-chunk (frames) of the host-streamed partition")
     ap.add_argument("--cpu-threads", type=int, default=0, help="CPU worker threads (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the 4K / configs[3] / warp-sweep records")

@@ -118,6 +118,15 @@ public:
         step[1] = elemSize();
         step[0] = step_bytes ? step_bytes : (size_t)c * elemSize();
     }
+    // wrap of external memory that the Mat (and its copies / ROIs) keeps alive through `owner` — what a custom
+    // cv::MatAllocator (e.g. cv::cuda::HostMem::getAllocator() for page-locked memory) does with real OpenCV
+    Mat(int r, int c, int type, void* ext, size_t step_bytes, std::shared_ptr<void> owner)
+    {
+        flags = type; rows = r; cols = c; data = (uint8_t*)ext;
+        step[1] = elemSize();
+        step[0] = step_bytes ? step_bytes : (size_t)c * elemSize();
+        owner_ = std::move(owner);
+    }
 
     void create(int r, int c, int type)
     {
@@ -125,8 +134,9 @@ public:
         flags = type; rows = r; cols = c;
         step[1] = elemSize();
         step[0] = (size_t)c * elemSize();
-        owner_ = std::make_shared<std::vector<uint8_t>>((size_t)r * step[0] + 64);
-        data = owner_->data();
+        auto buf = std::make_shared<std::vector<uint8_t>>((size_t)r * step[0] + 64);
+        data = buf->data();
+        owner_ = buf;
     }
     void create(Size sz, int type) { create(sz.height, sz.width, type); }
     void release() { owner_.reset(); data = nullptr; rows = cols = 0; }
@@ -237,9 +247,10 @@ public:
     Mat inv(int method = DECOMP_LU) const;
 
     bool ownsData() const { return (bool)owner_; }
+    const std::shared_ptr<void>& owner() const { return owner_; }
 
 private:
-    std::shared_ptr<std::vector<uint8_t>> owner_;
+    std::shared_ptr<void> owner_;
 };
 
 // cv::Mat_<T>(r,c) << a, b, c ... ; only what imgproc.cpp:467-469 needs

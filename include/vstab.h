@@ -88,6 +88,12 @@ int vs_dev_alloc(vs_ctx* ctx, size_t bytes, void** out);
 int vs_dev_free(vs_ctx* ctx, void* p);
 int vs_host_alloc_pinned(vs_ctx* ctx, size_t bytes, void** out);
 int vs_host_free_pinned(vs_ctx* ctx, void* p);
+/* page-locked host memory that is not tied to a context (frame pools that outlive the stabilizer that filled them), and
+ * whether a host pointer is page-locked (cudaMallocHost / cudaHostRegister): copies from and to such memory are DMA
+ * transfers at the PCIe rate, copies of pageable memory are staged by the driver */
+int vs_pinned_alloc(size_t bytes, void** out);
+int vs_pinned_free(void* p);
+int vs_host_is_pinned(const void* p);
 int vs_memcpy_h2d(vs_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async on stream */
 int vs_memcpy_d2h(vs_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async on stream */
 

@@ -56,6 +56,9 @@ SYMBOLS = {
     "vs_dev_free": (C.c_int, [_P, _P]),
     "vs_host_alloc_pinned": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "vs_host_free_pinned": (C.c_int, [_P, _P]),
+    "vs_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "vs_pinned_free": (C.c_int, [_P]),
+    "vs_host_is_pinned": (C.c_int, [_P]),
     "vs_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "vs_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "vs_bgr2gray_u8": (C.c_int, [_P, _IMG, _IMG, C.c_int]),

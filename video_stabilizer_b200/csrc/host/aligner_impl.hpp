@@ -16,6 +16,8 @@ struct VideoAligner::Impl {
     int last_slot = -1;
     int generation = 0;            // bumped whenever the ring is re-created
     bool force_reinit = false;     // a keyframe / device failure: the next frame re-creates the ring (upstream's LastWidth = -1)
+    uint8_t* staging = nullptr;    // page-locked copy of the incoming frame when the caller's memory is pageable (frame_io.hpp)
+    size_t staging_bytes = 0;
 
     ~Impl();
     void ensure_context();
@@ -23,6 +25,9 @@ struct VideoAligner::Impl {
     bool ensure_clip(int w, int h, const VideoAlignerParams& params);
     void destroy_clip();
     int slot_of(long frame) const { return (int)(frame % capacity); }
+    // enqueue the upload of a host frame into `slot`: DMA from the caller's memory when it is page-locked, else through the
+    // page-locked staging buffer; the caller may reuse its frame as soon as this returns
+    int upload(int slot, const uint8_t* data, size_t step, int w, int h);
 };
 
 namespace vstab {

@@ -5,6 +5,8 @@
 // itself is one kernel launch (vs_clip_align).
 #include "aligner_impl.hpp"
 
+#include "frame_io.hpp"
+
 #include <stdexcept>
 
 namespace vstab {
@@ -28,6 +30,26 @@ VideoAligner::Impl::~Impl()
 {
     destroy_clip();
     if (ctx) vs_ctx_destroy(ctx);
+    if (staging) vs_pinned_free(staging);
+}
+
+int VideoAligner::Impl::upload(int slot, const uint8_t* data, size_t step, int w, int h)
+{
+    const size_t row_bytes = (size_t)w * 3;
+    if (vs_host_is_pinned(data))
+        return vs_clip_upload(clip, slot, 1, data, (int64_t)step, (int64_t)step * h, VS_MEM_HOST);
+    if (staging_bytes < row_bytes * h) {
+        // the previous frame's DMA out of the old buffer has finished: every call ends with a synchronisation
+        if (staging) vs_pinned_free(staging);
+        staging = nullptr;
+        staging_bytes = 0;
+        void* p = nullptr;
+        if (vs_pinned_alloc(row_bytes * h, &p) != VS_OK) return VS_ERR_NOMEM;
+        staging = (uint8_t*)p;
+        staging_bytes = row_bytes * h;
+    }
+    vstab::copy_rows_parallel(staging, row_bytes, data, step, row_bytes, h);
+    return vs_clip_upload(clip, slot, 1, staging, (int64_t)row_bytes, (int64_t)row_bytes * h, VS_MEM_HOST);
 }
 
 void VideoAligner::Impl::ensure_context()
@@ -88,7 +110,7 @@ bool VideoAligner::AlignNextFrame(const cv::Mat& frame, SimilarityTransform& tra
     const long n = s.frames_since_reset;
     const int slot = s.slot_of(n);
     const bool is_keyframe = (n & 1) != 0;
-    if (vs_clip_upload(s.clip, slot, 1, frame.data, (int64_t)frame.step[0], (int64_t)frame.step[0] * frame.rows, VS_MEM_HOST) != VS_OK ||
+    if (s.upload(slot, frame.data, (size_t)frame.step[0], frame.cols, frame.rows) != VS_OK ||
         vs_clip_build_pyramids(s.clip, slot, 1) != VS_OK) {
         std::cerr << "VideoAligner: " << vs_last_error(s.ctx) << std::endl;
         s.last_slot = -1;          // this frame is not in the ring: VideoStabilizer keeps a host copy of it

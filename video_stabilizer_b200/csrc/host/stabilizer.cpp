@@ -9,6 +9,7 @@
 #include <stdexcept>
 
 #include "aligner_impl.hpp"
+#include "frame_io.hpp"
 #include "trajectory.hpp"
 
 namespace vstab {
@@ -84,7 +85,13 @@ cv::Mat VideoStabilizer::processFrame(const cv::Mat& inputFrame)
     if (oldest.host.empty() && oldest.generation == ring.generation && ring.clip) {
         const int ow = ring.width - 2 * crop, oh = ring.height - 2 * crop;
         if (ow <= 0 || oh <= 0) throw std::runtime_error("VideoStabilizer: crop_pixels removes the whole frame");
-        cv::Mat out(oh, ow, CV_8UC3);
+#ifdef CV_COMPAT_SHIM
+        // the frame the caller receives lives in a recycled page-locked buffer: the warp's output arrives by DMA
+        cv::Mat out(oh, ow, CV_8UC3, nullptr, (size_t)ow * 3, vstab::pinned_frame((size_t)ow * oh * 3));
+        out.data = (uint8_t*)out.owner().get();
+#else
+        cv::Mat out(oh, ow, CV_8UC3);       // real OpenCV: see INTEGRATION.md (cv::cuda::HostMem allocator)
+#endif
         const int32_t slot = oldest.slot;
         const double T[4] = {correction.A, correction.B, correction.TX, correction.TY};
         if (vs_clip_warp(ring.clip, &slot, 1, T, VS_WARP_CV_EXACT_BILINEAR, VS_BORDER_CONSTANT0, crop, out.data,

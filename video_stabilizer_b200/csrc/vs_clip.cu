@@ -482,7 +482,9 @@ int vs_clip_align_async(vs_clip* c, const vs_pair* pairs, int n, int base, int l
     a.dbg_warpdiff = nullptr; a.dbg_order = nullptr; a.dbg_count = nullptr; a.dbg_clock = nullptr;
     a.pos_scratch = c->d_pos_scratch ? c->d_pos_scratch + (size_t)base * 4 * c->g.max_tiles : nullptr;
     a.res_scratch = c->d_res_scratch ? c->d_res_scratch + (size_t)base * 2 * c->g.max_tiles : nullptr;
-    a.force_threads = 256;            // all lanes must fit on the GPU together: three CTAs per SM
+    // all lanes must be resident on the GPU together: an SM per pair (512 threads, registers uncapped: the shortest
+    // latency per pair) when every pair of every lane gets one, else three 256-thread CTAs per SM
+    a.force_threads = c->max_pairs <= ctx->sm_count ? 512 : 256;
     a.init_T = init_T;
     cudaStream_t main_stream = ctx->stream;
     ctx->stream = s;

@@ -241,6 +241,33 @@ int vs_host_free_pinned(vs_ctx* ctx, void* p)
     return VS_OK;
 }
 
+int vs_pinned_alloc(size_t bytes, void** out)
+{
+    if (!out) return VS_ERR_INVALID;
+    *out = nullptr;
+    if (bytes == 0) return VS_OK;
+    cudaError_t e = cudaMallocHost(out, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return vs_set_error(nullptr, VS_ERR_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return VS_OK;
+}
+
+int vs_pinned_free(void* p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return VS_ERR_CUDA; }
+    return VS_OK;
+}
+
+int vs_host_is_pinned(const void* p)
+{
+    if (!p) return 0;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 int vs_memcpy_h2d(vs_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     if (!ctx) return VS_ERR_INVALID;
