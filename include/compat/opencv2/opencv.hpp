@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <iostream>
 #include <memory>
+#include <random>      // the reference's align_test.cpp uses std::mt19937 with only OpenCV / Halide headers included
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -48,6 +49,7 @@ template <typename T> struct Point_ {
     Point_(T x_, T y_) : x(x_), y(y_) {}
 };
 typedef Point_<int> Point2i;
+typedef Point2i Point;
 typedef Point_<float> Point2f;
 typedef Point_<double> Point2d;
 
@@ -76,6 +78,11 @@ enum { INTER_NEAREST = 0, INTER_LINEAR = 1, WARP_INVERSE_MAP = 16 };
 enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1 };
 enum { COLOR_BGR2GRAY = 6 };
 enum { DECOMP_LU = 0, DECOMP_SVD = 1 };
+enum { IMREAD_GRAYSCALE = 0, IMREAD_COLOR = 1 };
+enum { NORM_MINMAX = 32 };
+enum { FILLED = -1 };
+enum { CAP_PROP_FRAME_WIDTH = 3, CAP_PROP_FRAME_HEIGHT = 4, CAP_PROP_FPS = 5, CAP_PROP_FRAME_COUNT = 7 };
+enum { VIDEOWRITER_PROP_QUALITY = 1 };
 
 inline size_t depth_bytes(int depth)
 {
@@ -300,6 +307,76 @@ public:
     Mat u, w, vt;
     SVD() {}
     explicit SVD(const Mat& src, int flags = 0);   // declared only
+};
+
+// ---- small host utilities the reference's drivers use (align_test.cpp:24,361): plain loops, nothing on the hot path
+// cv::normalize(src, dst, alpha, beta, NORM_MINMAX): affine map of [min, max] onto [alpha, beta], same depth
+inline void normalize(const Mat& src, Mat& dst, double alpha, double beta, int norm_type)
+{
+    if (norm_type != NORM_MINMAX || src.channels() != 1 || (src.depth() != CV_32F && src.depth() != CV_8U))
+        throw std::runtime_error("compat cv::normalize: NORM_MINMAX on single-channel 8U / 32F only");
+    double lo = 1e300, hi = -1e300;
+    for (int r = 0; r < src.rows; r++)
+        for (int c = 0; c < src.cols; c++) {
+            const double v = src.depth() == CV_32F ? (double)src.ptr<float>(r)[c] : (double)src.ptr<uint8_t>(r)[c];
+            lo = std::min(lo, v); hi = std::max(hi, v);
+        }
+    const double scale = hi > lo ? (beta - alpha) / (hi - lo) : 0.0;
+    Mat out(src.rows, src.cols, src.type());
+    for (int r = 0; r < src.rows; r++)
+        for (int c = 0; c < src.cols; c++) {
+            if (src.depth() == CV_32F) out.ptr<float>(r)[c] = (float)((src.ptr<float>(r)[c] - lo) * scale + alpha);
+            else out.ptr<uint8_t>(r)[c] = (uint8_t)std::min(255.0, std::max(0.0, nearbyint((src.ptr<uint8_t>(r)[c] - lo) * scale + alpha)));
+        }
+    dst = out;
+}
+
+// cv::rectangle(img, rect, color, FILLED) on 8-bit images
+inline void rectangle(Mat& img, Rect rc, const Scalar& color, int thickness = 1)
+{
+    if (img.depth() != CV_8U) throw std::runtime_error("compat cv::rectangle: 8-bit images only");
+    const int cn = img.channels();
+    for (int y = std::max(0, rc.y); y < std::min(img.rows, rc.y + rc.height); y++)
+        for (int x = std::max(0, rc.x); x < std::min(img.cols, rc.x + rc.width); x++) {
+            const bool edge = y == rc.y || y == rc.y + rc.height - 1 || x == rc.x || x == rc.x + rc.width - 1;
+            if (thickness != FILLED && !edge) continue;
+            for (int k = 0; k < cn; k++) img.ptr<uint8_t>(y)[x * cn + k] = (uint8_t)color.val[k < 4 ? k : 3];
+        }
+}
+
+// ---- image / video I/O of the reference's drivers (align_test.cpp:45,632,682; video_test.cpp:62-117): declared only.
+// The product never reads or writes files; a caller links OpenCV's own, the tests link oracle/ref_shim/cv_io.cpp.
+Mat imread(const std::string& filename, int flags = IMREAD_COLOR);
+bool imwrite(const std::string& filename, const Mat& img);
+
+class VideoCapture {
+public:
+    VideoCapture();
+    explicit VideoCapture(const std::string& filename);
+    ~VideoCapture();
+    bool open(const std::string& filename);
+    bool isOpened() const;
+    double get(int prop) const;
+    bool read(Mat& frame);
+    void release();
+private:
+    struct Impl;
+    std::shared_ptr<Impl> impl_;
+};
+
+class VideoWriter {
+public:
+    VideoWriter();
+    ~VideoWriter();
+    static int fourcc(char a, char b, char c, char d) { return (a & 255) | ((b & 255) << 8) | ((c & 255) << 16) | ((d & 255) << 24); }
+    bool open(const std::string& filename, int fourcc, double fps, Size frameSize, bool isColor = true);
+    bool isOpened() const;
+    bool set(int prop, double value);
+    void write(const Mat& frame);
+    void release();
+private:
+    struct Impl;
+    std::shared_ptr<Impl> impl_;
 };
 
 // ---- declared only: CPU definitions live in oracle/ref_shim/cv_impl.cpp (test infrastructure)

@@ -89,7 +89,7 @@ def build_tools(force: bool = False) -> list[str]:
     os.makedirs(bin_dir, exist_ok=True)
     outs = []
     cxx = shutil.which("g++") or "g++"
-    for name in ("align_test", "video_test"):
+    for name in ("align_test", "video_test", "stream_bench"):
         src = os.path.join(tools_dir, name + ".cpp")
         out = os.path.join(bin_dir, name)
         deps = [src, LIB_HOST, LIB_CUDA] + glob.glob(os.path.join(tools_dir, "*.hpp")) + glob.glob(os.path.join(host_dir, "*.hpp"))
@@ -105,6 +105,8 @@ def build_oracle() -> None:
     _run(["make", "-s", "-C", os.path.join(REPO, "oracle")])
     if os.path.isdir("/root/reference") and os.path.exists(os.path.join(REPO, "oracle", "ref_shim")):
         _run(["make", "-s", "-C", os.path.join(REPO, "oracle"), "ref"])
+        # the reference's own drivers against the product's headers and libraries
+        _run(["make", "-s", "-C", os.path.join(REPO, "oracle"), "ref_drivers"])
 
 
 def build_all(force: bool = False) -> None:

@@ -65,6 +65,7 @@ struct vs_clip {
     cudaEvent_t ev_ready[kLanes] = {}, ev_solved[kLanes] = {};
     double* h_T = nullptr;            // pinned, max_pairs * 4
     int32_t* h_status = nullptr;      // pinned, max_pairs
+    int32_t* h_iters = nullptr;       // pinned, max_pairs * levels (only when a caller asks for iteration counts)
     int lane_base[kLanes] = {}, lane_n[kLanes] = {};
     // phase-correlation initialiser (params.phase_correlate): allocated on first use
     VsPhasePlan pc;
@@ -115,6 +116,7 @@ void free_all(vs_clip* c)
     }
     if (c->h_T) cudaFreeHost(c->h_T);
     if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->h_iters) cudaFreeHost(c->h_iters);
 }
 
 PFN_cuTensorMapEncodeTiled tensor_map_encoder()
@@ -434,11 +436,22 @@ int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_
     VS_TRY(vsk_solve_pairs(ctx, c->g, a));
     c->last_pairs = n;
     if (!dev_out) {
-        VS_CUDA(ctx, cudaMemcpyAsync(out_T, c->d_T, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        VS_CUDA(ctx, cudaMemcpyAsync(out_status, c->d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        // results land in page-locked memory and are handed over after a stream synchronisation: a device-to-host copy
+        // into pageable memory is a blocking driver call, and host threads driving other clips queue up behind it
+        if (!c->h_T) {
+            VS_CUDA(ctx, cudaMallocHost((void**)&c->h_T, (size_t)c->max_pairs * 4 * sizeof(double)));
+            VS_CUDA(ctx, cudaMallocHost((void**)&c->h_status, (size_t)c->max_pairs * sizeof(int32_t)));
+        }
+        if (out_iters && !c->h_iters)
+            VS_CUDA(ctx, cudaMallocHost((void**)&c->h_iters, (size_t)c->max_pairs * c->g.levels * sizeof(int32_t)));
+        VS_CUDA(ctx, cudaMemcpyAsync(c->h_T, c->d_T, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        VS_CUDA(ctx, cudaMemcpyAsync(c->h_status, c->d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (out_iters)
-            VS_CUDA(ctx, cudaMemcpyAsync(out_iters, c->d_iters, (size_t)n * c->g.levels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            VS_CUDA(ctx, cudaMemcpyAsync(c->h_iters, c->d_iters, (size_t)n * c->g.levels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(out_T, c->h_T, (size_t)n * 4 * sizeof(double));
+        memcpy(out_status, c->h_status, (size_t)n * sizeof(int32_t));
+        if (out_iters) memcpy(out_iters, c->h_iters, (size_t)n * c->g.levels * sizeof(int32_t));
     }
     return VS_OK;
 }
