@@ -7,7 +7,10 @@
 // The tests write input.png / template.png / recordings/*.mp4 in that form and read the drivers' outputs back.
 #include <opencv2/opencv.hpp>
 
+#include <execinfo.h>
+#include <signal.h>
 #include <stdio.h>
+#include <unistd.h>
 
 #include <fstream>
 
@@ -27,6 +30,25 @@ bool read_header(FILE* f, RawHeader& hd)
     hd.data_offset = ftell(f);
     return hd.w > 0 && hd.h > 0 && (hd.c == 1 || hd.c == 3) && hd.n > 0;
 }
+
+// the drivers run as child processes of the tests: line-buffered output and a backtrace on a crash make a failure readable
+void on_crash(int sig)
+{
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "[cv_io] fatal signal, backtrace:\n";
+    (void)!write(2, msg, sizeof(msg) - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+struct CrashReport {
+    CrashReport()
+    {
+        signal(SIGSEGV, on_crash);
+        signal(SIGABRT, on_crash);
+        setvbuf(stdout, nullptr, _IOLBF, 0);
+    }
+} crash_report;
 
 void write_header(FILE* f, int w, int h, int c, int n) { fprintf(f, "VSRAW1\n%d %d %d %d\n", w, h, c, n); }
 
