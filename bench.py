@@ -583,6 +583,16 @@ def run_gpu_arm(args):
             sweep = kernel_bench.bench_warp(types.SimpleNamespace(size=None, mode=None, transform=None, iters=5, quiet=True))
             extra["warp_sweep"] = [{k: r[k] for k in ("mode", "size", "bytes_per_launch", "ms_per_launch", "algorithmic_gbs", "frac_of_hbm_peak")}
                                    for r in sweep]
+            # the drop-in per-frame API (VideoStabilizer::processFrame, pageable cv::Mat in and out) and the batched
+            # VideoAlignerParams sweep, as their C++ tools measure them
+            tool = os.path.join(REPO, "video_stabilizer_b200", "bin", "stream_bench")
+            if os.path.exists(tool):
+                out = subprocess.run([tool, "1920", "1080", "96", "1", "4", "8"], capture_output=True, text=True, timeout=120).stdout
+                extra["process_frame"] = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+            tool = os.path.join(REPO, "video_stabilizer_b200", "bin", "grid_search_align")
+            if os.path.exists(tool):
+                out = subprocess.run([tool, "1280", "720", "48"], capture_output=True, text=True, timeout=120).stdout
+                extra["grid_search_align"] = [l for l in out.splitlines() if l.startswith(("Input", "Best", "54 "))]
         except Exception as e:      # noqa: BLE001  (an extra record must not take the headline down)
             extra["error"] = repr(e)
 

@@ -210,6 +210,20 @@ int vs_clip_build_keyframes(vs_clip*, const int32_t* slots, int n);
  * (may be NULL).  Outputs live in `mem`. */
 int vs_clip_align(vs_clip*, const vs_pair* pairs, int n,
                   double* out_transform, int32_t* out_status, int32_t* out_iters, int mem);
+/* One parameter combination of a sweep over VideoAlignerParams (grid_search_align.cpp:134-146 sweeps phase_correlate,
+ * threshold, smallest_fraction and max_displacement). */
+typedef struct vs_sweep_params {
+    double  threshold;
+    double  max_displacement;
+    float   smallest_fraction;
+    int32_t max_iters;
+    int32_t phase_correlate;
+} vs_sweep_params;
+/* The alignment of n_pairs pairs under n_sets parameter combinations in ONE launch (n_pairs * n_sets <= max_pairs):
+ * out_transform [n_sets][n_pairs][4], out_status [n_sets][n_pairs], in `mem`.  Each (set, pair) result is the one
+ * vs_clip_align gives after vs_clip_set_params with that combination.  phase_correlate_threshold is the clip's. */
+int vs_clip_align_sweep(vs_clip*, const vs_pair* pairs, int n_pairs, const vs_sweep_params* sets, int n_sets,
+                        double* out_transform, int32_t* out_status, int mem);
 #define VS_CLIP_SOLVER_LANES 4
 /* The same solve, enqueued on one of the clip's solver streams (lane 0 .. VS_CLIP_SOLVER_LANES-1) behind everything
  * enqueued on the context stream so far, without waiting: the pyramids / keyframe features of the next frames and the warps of frames

@@ -110,6 +110,21 @@ void  vsh_multigpu_destroy(void*);
 int   vsh_multigpu_stabilize(void*, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride,
                              uint8_t* out, int64_t out_frame_stride, double* meas, uint8_t* ok);
 
+/* ---- quality tooling on the batched API (grid_search.hpp; reference eval_jitter.cpp:21-75, grid_search_align.cpp:27-60,
+ * 134-210).  A combination is 4 doubles {phase_correlate, threshold, smallest_fraction, max_displacement}. */
+void*  vsh_gridsearch_create(int device, int width, int height, int max_frames, int max_combos, int crop_pixels);
+void   vsh_gridsearch_destroy(void*);
+int    vsh_gridsearch_reference_grid(double* combos4, int capacity);      /* returns 54 */
+double vsh_flow_median_px(const double T[4], int w, int h);
+/* jitter of n host BGR frames: out3 = {median px, pairs, pairs the aligner could not align} */
+int    vsh_gridsearch_jitter(void*, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, double* out3);
+/* the sweep: all pairs under all combinations in one solver launch, trajectories (smoother off, lag 1) on the host, output
+ * sequences warped and scored in batched launches.  results5 per combination = {output jitter px, ratio to the input's,
+ * output pairs not aligned, input pairs not aligned, output pairs}; T [combos][n-1][4] and status [combos][n-1] optional.
+ * Returns the number of kernel launches so far (>= 0) or -1. */
+int    vsh_gridsearch_run(void*, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, const double* combos4,
+                          int n_combos, double* input3, double* results5, double* T, int32_t* status);
+
 /* ---- one video partitioned by frame chunk over several workers (partitioned.hpp): one worker per GPU, processes or
  * threads; the workers share a per-frame table in POSIX shared memory (exchange_name = "/name"; rank 0 creates it).
  * Sub-chunks of sub_frames (even) frames, `block` consecutive sub-chunks per chunk, chunks round-robin over the workers. */

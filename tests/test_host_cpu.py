@@ -140,3 +140,15 @@ def test_trajectory_matches_reference_stabilizer_glue(host, ob, enable, lag, mem
         else:
             assert not due
     assert dues == 120 - lag
+
+
+def test_flow_median_of_a_translation_and_a_rotation():
+    """jitter statistic (grid_search.hpp): median |W(p) - p| over a grid; a pure translation moves every point alike"""
+    from video_stabilizer_b200 import host
+    host.load()
+    assert abs(host.flow_median_px([0, 0, 3, 4], 1920, 1080) - 5.0) < 1e-12
+    assert host.flow_median_px([0, 0, 0, 0], 1920, 1080) == 0.0
+    r = host.flow_median_px([0, 0.001, 0, 0], 1920, 1080)       # small rotation about the centre: grows with the radius
+    assert 0.2 < r < 1.2
+    g = host.reference_grid()
+    assert g.shape == (54, 4) and g[0].tolist() == [0.0, 0.02, np.float32(0.3), 6.0] and g[-1, 0] == 1.0

@@ -32,6 +32,11 @@ class VsAlignParams(C.Structure):
                 ("max_displacement", C.c_double)]
 
 
+class VsSweepParams(C.Structure):
+    _fields_ = [("threshold", C.c_double), ("max_displacement", C.c_double), ("smallest_fraction", C.c_float),
+                ("max_iters", C.c_int32), ("phase_correlate", C.c_int32)]
+
+
 class VsPair(C.Structure):
     _fields_ = [("template_slot", C.c_int32), ("keyframe_slot", C.c_int32), ("invert", C.c_int32)]
 
@@ -84,6 +89,7 @@ SYMBOLS = {
     "vs_clip_build_pyramids": (C.c_int, [_P, C.c_int, C.c_int]),
     "vs_clip_build_keyframes": (C.c_int, [_P, _P, C.c_int]),
     "vs_clip_align": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int]),
+    "vs_clip_align_sweep": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int]),
     "vs_clip_align_async": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     "vs_clip_align_wait": (C.c_int, [_P, C.c_int, _P, _P]),
     "vs_clip_warp": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64, C.c_int]),

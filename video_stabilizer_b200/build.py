@@ -89,7 +89,7 @@ def build_tools(force: bool = False) -> list[str]:
     os.makedirs(bin_dir, exist_ok=True)
     outs = []
     cxx = shutil.which("g++") or "g++"
-    for name in ("align_test", "video_test", "stream_bench"):
+    for name in ("align_test", "video_test", "stream_bench", "grid_search_align"):
         src = os.path.join(tools_dir, name + ".cpp")
         out = os.path.join(bin_dir, name)
         deps = [src, LIB_HOST, LIB_CUDA] + glob.glob(os.path.join(tools_dir, "*.hpp")) + glob.glob(os.path.join(host_dir, "*.hpp"))

@@ -10,6 +10,7 @@
 
 #include "aligner_impl.hpp"
 #include "clip_stabilizer.hpp"
+#include "grid_search.hpp"
 #include "multi_gpu.hpp"
 #include "partitioned.hpp"
 #include "stabilizer.hpp"
@@ -319,6 +320,53 @@ int vsh_multigpu_stabilize(void* m, const uint8_t* frames, int n, int64_t row_st
         if (meas) for (size_t i = 0; i < s->measurements().size(); i++) put(s->measurements()[i], meas + 4 * i);
         if (ok) for (size_t i = 0; i < s->successes().size(); i++) ok[i] = s->successes()[i];
         return k;
+    });
+}
+
+// ---- quality tooling: jitter score and the batched VideoAlignerParams sweep (grid_search.hpp)
+void* vsh_gridsearch_create(int device, int width, int height, int max_frames, int max_combos, int crop_pixels)
+{
+    vstab::AlignerGridSearch* g = nullptr;
+    guarded([&] { g = new vstab::AlignerGridSearch(device, width, height, max_frames, max_combos, crop_pixels); return 0; });
+    return g;
+}
+void vsh_gridsearch_destroy(void* g) { delete (vstab::AlignerGridSearch*)g; }
+int vsh_gridsearch_reference_grid(double* combos4, int capacity)
+{
+    const auto grid = vstab::AlignerGridSearch::reference_grid();
+    for (size_t i = 0; i < grid.size() && (int)i < capacity; i++) {
+        combos4[4 * i] = grid[i].phase_correlate ? 1.0 : 0.0; combos4[4 * i + 1] = grid[i].threshold;
+        combos4[4 * i + 2] = grid[i].smallest_fraction; combos4[4 * i + 3] = grid[i].max_displacement;
+    }
+    return (int)grid.size();
+}
+double vsh_flow_median_px(const double T[4], int w, int h) { return vstab::flow_median_px(tf(T), w, h); }
+int vsh_gridsearch_jitter(void* g, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, double* out3)
+{
+    return guarded([&] {
+        const vstab::JitterScore s = ((vstab::AlignerGridSearch*)g)->measure_jitter(frames, n, row_stride, frame_stride);
+        out3[0] = s.median_px; out3[1] = s.pairs; out3[2] = s.failed;
+        return 0;
+    });
+}
+int vsh_gridsearch_run(void* gp, const uint8_t* frames, int n, int64_t row_stride, int64_t frame_stride, const double* combos4,
+                       int n_combos, double* input3, double* results5, double* T, int32_t* status)
+{
+    return guarded([&] {
+        auto* g = (vstab::AlignerGridSearch*)gp;
+        std::vector<vstab::AlignerGridSearch::Combo> combos(n_combos);
+        for (int i = 0; i < n_combos; i++)
+            combos[i] = {combos4[4 * i] != 0.0, combos4[4 * i + 1], (float)combos4[4 * i + 2], combos4[4 * i + 3]};
+        vstab::JitterScore in;
+        const auto res = g->run(frames, n, row_stride, frame_stride, combos, &in);
+        if (input3) { input3[0] = in.median_px; input3[1] = in.pairs; input3[2] = in.failed; }
+        for (int i = 0; i < n_combos; i++) {
+            results5[5 * i] = res[i].out.median_px; results5[5 * i + 1] = res[i].ratio; results5[5 * i + 2] = res[i].out.failed;
+            results5[5 * i + 3] = res[i].failed_alignments; results5[5 * i + 4] = res[i].out.pairs;
+        }
+        if (T) std::copy(g->sweep_transforms().begin(), g->sweep_transforms().end(), T);
+        if (status) std::copy(g->sweep_status().begin(), g->sweep_status().end(), status);
+        return (int)g->launches();
     });
 }
 

@@ -66,6 +66,8 @@ struct vs_clip {
     double* h_T = nullptr;            // pinned, max_pairs * 4
     int32_t* h_status = nullptr;      // pinned, max_pairs
     int32_t* h_iters = nullptr;       // pinned, max_pairs * levels (only when a caller asks for iteration counts)
+    VsSweepSet* d_sweep = nullptr;    // parameter sets of vs_clip_align_sweep
+    size_t sweep_capacity = 0;
     int lane_base[kLanes] = {}, lane_n[kLanes] = {};
     // phase-correlation initialiser (params.phase_correlate): allocated on first use
     VsPhasePlan pc;
@@ -107,6 +109,7 @@ void free_all(vs_clip* c)
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
     cudaFree(c->d_pos_scratch); cudaFree(c->d_res_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
     cudaFree(c->d_warp_tab);
+    cudaFree(c->d_sweep);
     cudaFree(c->pc.d_tw); cudaFree(c->pc.d_rows); cudaFree(c->pc.d_spec); cudaFree(c->pc.d_cross); cudaFree(c->pc.d_inv);
     cudaFree(c->pc.d_surf); cudaFree(c->d_pc_slots); cudaFree(c->d_pc_init); cudaFree(c->d_pc_phase);
     for (int l = 0; l < vs_clip::kLanes; l++) {
@@ -452,6 +455,74 @@ int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_
         memcpy(out_T, c->h_T, (size_t)n * 4 * sizeof(double));
         memcpy(out_status, c->h_status, (size_t)n * sizeof(int32_t));
         if (out_iters) memcpy(out_iters, c->h_iters, (size_t)n * c->g.levels * sizeof(int32_t));
+    }
+    return VS_OK;
+}
+
+// Batched parameter sweep (the reference sweeps VideoAlignerParams with one VideoStabilizer per
+// worker thread and parameter combination, grid_search_align.cpp:134-210): every pair is solved once per parameter set in
+// ONE launch.  Job (set s, pair p) uses scratch / output index s * n_pairs + p.
+int vs_clip_align_sweep(vs_clip* c, const vs_pair* pairs, int n_pairs, const vs_sweep_params* sets, int n_sets,
+                        double* out_T, int32_t* out_status, int mem)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, n_pairs >= 0 && n_sets >= 0 && (long long)n_pairs * n_sets <= c->max_pairs,
+               "clip_align_sweep: pairs x parameter sets exceeds max_pairs");
+    VS_REQUIRE(ctx, mem == VS_MEM_HOST || mem == VS_MEM_DEVICE, "clip_align_sweep: bad mem");
+    const int jobs = n_pairs * n_sets;
+    if (jobs == 0) return VS_OK;
+    VS_REQUIRE(ctx, pairs && sets && out_T && out_status, "clip_align_sweep: NULL pointer");
+    for (int i = 0; i < n_pairs; i++)
+        VS_REQUIRE(ctx, pairs[i].template_slot >= 0 && pairs[i].template_slot < c->capacity &&
+                        pairs[i].keyframe_slot >= 0 && pairs[i].keyframe_slot < c->capacity, "clip_align_sweep: slot out of range");
+    std::vector<VsSweepSet> hs(n_sets);
+    bool any_seed = false;
+    for (int i = 0; i < n_sets; i++) {
+        VS_REQUIRE(ctx, sets[i].max_iters >= 1, "clip_align_sweep: max_iters must be >= 1");
+        VS_REQUIRE(ctx, sets[i].smallest_fraction >= 0.f && sets[i].smallest_fraction <= 1.f,
+                   "clip_align_sweep: smallest_fraction must be in [0, 1]");
+        hs[i].threshold = sets[i].threshold; hs[i].max_displacement = sets[i].max_displacement;
+        hs[i].fraction = sets[i].smallest_fraction; hs[i].max_iters = sets[i].max_iters;
+        hs[i].use_seed = sets[i].phase_correlate ? 1 : 0; hs[i].pad = 0;
+        any_seed = any_seed || sets[i].phase_correlate;
+    }
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((size_t)n_sets > c->sweep_capacity) {
+        VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(c->d_sweep); c->d_sweep = nullptr; c->sweep_capacity = 0;
+        VS_TRY(dev_alloc(ctx, &c->d_sweep, (size_t)n_sets));
+        c->sweep_capacity = (size_t)n_sets;
+    }
+    VS_CUDA(ctx, cudaMemcpyAsync(c->d_pairs, pairs, (size_t)n_pairs * sizeof(vs_pair), cudaMemcpyHostToDevice, ctx->stream));
+    VS_CUDA(ctx, cudaMemcpyAsync(c->d_sweep, hs.data(), (size_t)n_sets * sizeof(VsSweepSet), cudaMemcpyHostToDevice, ctx->stream));
+    const bool dev_out = mem == VS_MEM_DEVICE;
+    VsSolveArgs a;
+    a.pyr = c->d_pyr; a.kp = c->d_kp; a.jac = c->d_jac; a.pairs = c->d_pairs; a.n_pairs = jobs;
+    a.threshold = c->params.threshold; a.fraction = c->params.smallest_fraction;
+    a.max_iters = c->params.max_iters; a.max_displacement = c->params.max_displacement;
+    a.out_T = dev_out ? out_T : c->d_T;
+    a.out_status = dev_out ? out_status : c->d_status;
+    a.out_iters = nullptr;
+    a.dbg_warpdiff = nullptr; a.dbg_order = nullptr; a.dbg_count = nullptr; a.dbg_clock = nullptr;
+    a.pos_scratch = c->d_pos_scratch;
+    a.res_scratch = c->d_res_scratch;
+    a.force_threads = 0;
+    a.sweep = c->d_sweep;
+    a.sweep_pairs = n_pairs;
+    if (any_seed) VS_TRY(phase_seed(c, pairs, c->d_pairs, n_pairs, 0, &a.init_T));   // alignment.cpp:369-388, once per pair
+    VS_TRY(vsk_solve_pairs(ctx, c->g, a));
+    c->last_pairs = jobs;
+    if (!dev_out) {
+        if (!c->h_T) {
+            VS_CUDA(ctx, cudaMallocHost((void**)&c->h_T, (size_t)c->max_pairs * 4 * sizeof(double)));
+            VS_CUDA(ctx, cudaMallocHost((void**)&c->h_status, (size_t)c->max_pairs * sizeof(int32_t)));
+        }
+        VS_CUDA(ctx, cudaMemcpyAsync(c->h_T, c->d_T, (size_t)jobs * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        VS_CUDA(ctx, cudaMemcpyAsync(c->h_status, c->d_status, (size_t)jobs * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(out_T, c->h_T, (size_t)jobs * 4 * sizeof(double));
+        memcpy(out_status, c->h_status, (size_t)jobs * sizeof(int32_t));
     }
     return VS_OK;
 }

@@ -87,6 +87,16 @@ struct VsClipGeom {
     VsLevel lv[VS_MAX_LEVELS];
 };
 
+// one parameter set of a batched sweep (vs_clip_align_sweep): job j of the launch aligns pair j % sweep_pairs with
+// parameter set j / sweep_pairs; scratch and outputs are indexed by job
+struct VsSweepSet {
+    double threshold, max_displacement;
+    float fraction;
+    int32_t max_iters;
+    int32_t use_seed;         // take the phase-correlation seed of the pair (init_T), else start from the identity
+    int32_t pad;
+};
+
 struct VsSolveArgs {
     const uint8_t* pyr;       // slot-major pyramid store
     const uint32_t* kp;       // [slot][axis][total_tiles] packed (y<<16 | x)
@@ -108,6 +118,8 @@ struct VsSolveArgs {
     float* res_scratch;       // [pair][2][max_tiles] signed residual of every tile from the warp-diff pass, or null
     int force_threads;        // 0 = CTA size by pair count; 256 when several launches must be resident together
     const double* init_T = nullptr;   // [pair][2] initial (TX, TY) at the coarsest level (phase-correlation seed), or null
+    const VsSweepSet* sweep = nullptr;   // device array of parameter sets, or null: n_pairs = sets * sweep_pairs jobs
+    int sweep_pairs = 0;
 };
 
 // ---- phase-correlation initialiser (vs_phasecorr.cu; alignment.cpp:225-229, 369-388)

@@ -581,9 +581,20 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
     __shared__ SolveShared<SOLVE_THREADS / 32> sh;
     __shared__ SelShared<SOLVE_THREADS / 32> sel;
     const int tid = threadIdx.x;
-    const int pair = blockIdx.x;
+    const int pair = blockIdx.x;          // the job: index of scratch and outputs
     if (pair >= a.n_pairs) return;
-    const vs_pair pr = a.pairs[pair];
+    // a parameter sweep runs every pair once per parameter set in the same launch
+    const int src_pair = a.sweep ? pair % a.sweep_pairs : pair;
+    double p_threshold = a.threshold, p_max_displacement = a.max_displacement;
+    float p_fraction = a.fraction;
+    int p_max_iters = a.max_iters;
+    bool p_seed = a.init_T != nullptr;
+    if (a.sweep) {
+        const VsSweepSet ss = a.sweep[pair / a.sweep_pairs];
+        p_threshold = ss.threshold; p_max_displacement = ss.max_displacement; p_fraction = ss.fraction;
+        p_max_iters = ss.max_iters; p_seed = p_seed && ss.use_seed != 0;
+    }
+    const vs_pair pr = a.pairs[src_pair];
     const uint8_t* tpyr = a.pyr + (size_t)pr.template_slot * g.pyr_slot_bytes;
     const uint8_t* kpyr = a.pyr + (size_t)pr.keyframe_slot * g.pyr_slot_bytes;
     const size_t feat = (size_t)pr.keyframe_slot * 2 * g.total_tiles;
@@ -599,7 +610,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 
     if (tid == 0) {
         sh.T[0] = sh.T[1] = sh.T[2] = sh.T[3] = 0.0;
-        if (a.init_T) { sh.T[2] = a.init_T[(size_t)pair * 2]; sh.T[3] = a.init_T[(size_t)pair * 2 + 1]; }   // alignment.cpp:379-387
+        if (p_seed) { sh.T[2] = a.init_T[(size_t)src_pair * 2]; sh.T[3] = a.init_T[(size_t)src_pair * 2 + 1]; }   // alignment.cpp:379-387
         sh.status = 1;
         if (a.out_iters) for (int l = 0; l < g.levels; l++) a.out_iters[(size_t)pair * g.levels + l] = 0;
     }
@@ -616,7 +627,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         const float4* const jcl0 = a.jac + feat + L.tile_off;
         const float4* const jcl1 = jcl0 + g.total_tiles;
         const int nt = L.ntiles;
-        const int k = vs_sel::selected_count(nt, a.fraction);
+        const int k = vs_sel::selected_count(nt, p_fraction);
         __syncthreads();   // sh.T of the previous level (or the initial identity) is visible
 
         // ---- SparseWarpDiff for both keypoint sets with the incoming transform (alignment.cpp:409-431)
@@ -758,7 +769,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         };
         int iters = 0;
         int flag = FLAG_CONTINUE;
-        for (int iter = 0; iter < a.max_iters; iter++) {
+        for (int iter = 0; iter < p_max_iters; iter++) {
             iters++;
             double b[4] = {0, 0, 0, 0};
             if (iter > 0) gather(0, SOLVE_THREADS, b);
@@ -793,8 +804,8 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
                     sh.c1[c][0] = c2[0]; sh.c1[c][1] = c2[1];
                 }
                 int f = FLAG_CONTINUE;
-                if (d12 < a.threshold) f = FLAG_CONVERGED;
-                else if (iter >= a.max_iters - 1) f = FLAG_FAIL;
+                if (d12 < p_threshold) f = FLAG_CONVERGED;
+                else if (iter >= p_max_iters - 1) f = FLAG_FAIL;
                 sh.flag = f;
             }
             __syncthreads();
@@ -810,7 +821,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
             } else {
                 double d01 = 0.0;
                 for (int c = 0; c < 4; c++) d01 = fmax(d01, dist2d(sh.c0[c], sh.c1[c]));
-                if (d01 > a.max_displacement) sh.status = 0;
+                if (d01 > p_max_displacement) sh.status = 0;
                 else if (lvl > 0) { sh.T[2] *= 2.0; sh.T[3] *= 2.0; }
             }
         }

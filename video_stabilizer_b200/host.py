@@ -73,6 +73,12 @@ SYMBOLS = {
     "vsh_multigpu_destroy": (None, [_P]),
     "vsh_multigpu_stabilize": (_I, [_P, _P, _I, _I64, _I64, _P, _I64, _P, _P]),
     "vsh_clipstab_clip": (_P, [_P]),
+    "vsh_gridsearch_create": (_P, [_I, _I, _I, _I, _I, _I]),
+    "vsh_gridsearch_destroy": (None, [_P]),
+    "vsh_gridsearch_reference_grid": (_I, [_P, _I]),
+    "vsh_flow_median_px": (_D, [_P, _I, _I]),
+    "vsh_gridsearch_jitter": (_I, [_P, _P, _I, _I64, _I64, _P]),
+    "vsh_gridsearch_run": (_I, [_P, _P, _I, _I64, _I64, _P, _I, _P, _P, _P, _P]),
     "vsh_parttraj_create": (_P, [_I, _I, _I, _I, _I64, _I, _I, _SP, C.c_char_p, _I]),
     "vsh_parttraj_destroy": (None, [_P]),
     "vsh_parttraj_output_count": (_I, [_P]),
@@ -530,3 +536,46 @@ class PartitionedStabilizer(_Handle):
 
     def synchronize(self):
         capi.check(self.ctx_handle, capi.load().vs_ctx_synchronize(self.ctx_handle), "vs_ctx_synchronize")
+
+
+def reference_grid() -> np.ndarray:
+    """The 54 VideoAlignerParams combinations of grid_search_align.cpp:134-146 as rows {phase_correlate, threshold,
+    smallest_fraction, max_displacement}."""
+    g = np.zeros((64, 4))
+    n = load().vsh_gridsearch_reference_grid(_p(g), 64)
+    return g[:n].copy()
+
+
+def flow_median_px(T, w, h) -> float:
+    a = _t(T)
+    return load().vsh_flow_median_px(_p(a), w, h)
+
+
+class AlignerGridSearch(_Handle):
+    """Jitter score and the batched parameter sweep (grid_search.hpp)."""
+    _destroy = "vsh_gridsearch_destroy"
+
+    def __init__(self, width, height, max_frames, max_combos=54, crop_pixels=32, device=0):
+        self.width, self.height = width, height
+        self.h = C.c_void_p(load().vsh_gridsearch_create(device, width, height, max_frames, max_combos, crop_pixels))
+        if not self.h:
+            _raise("AlignerGridSearch")
+
+    def measure_jitter(self, frames):
+        f = np.ascontiguousarray(frames, np.uint8)
+        out = np.zeros(3)
+        if load().vsh_gridsearch_jitter(self.h, _p(f), f.shape[0], f.strides[1], f.strides[0], _p(out)) < 0:
+            _raise("measure_jitter")
+        return {"median_px": float(out[0]), "pairs": int(out[1]), "failed": int(out[2])}
+
+    def run(self, frames, combos):
+        """Returns (input jitter dict, results (n_combos, 5), T (n_combos, n-1, 4), status (n_combos, n-1), launches)."""
+        f = np.ascontiguousarray(frames, np.uint8)
+        c = np.ascontiguousarray(combos, np.float64)
+        n, S = f.shape[0], c.shape[0]
+        inp, res = np.zeros(3), np.zeros((S, 5))
+        T, st = np.zeros((S, n - 1, 4)), np.zeros((S, n - 1), np.int32)
+        k = load().vsh_gridsearch_run(self.h, _p(f), n, f.strides[1], f.strides[0], _p(c), S, _p(inp), _p(res), _p(T), _p(st))
+        if k < 0:
+            _raise("AlignerGridSearch.run")
+        return {"median_px": float(inp[0]), "pairs": int(inp[1]), "failed": int(inp[2])}, res, T, st, k
