@@ -303,9 +303,50 @@ def test_clip_alignment_4k(gpu, ob):
     """BASELINE.json configs[2] shape: 3840x2160, 7 pyramid levels, 20736 tiles at L0 — the
     selection's candidate lists no longer fit in shared memory and come from global scratch."""
     from video_stabilizer_b200 import synth
-    frames, poses = synth.make_clip_gpu(gpu, 3840, 2160, 3, 17)
-    worst, T, status, ref = check_clip_against_oracle(gpu, ob, frames, deep=False)
+    frames, poses = synth.make_clip_gpu(gpu, 3840, 2160, 9, 17)
+    # 8 pairs, every stage compared: pyramids (the fused ingest at 4K), keypoints, Jacobians, warp-diffs, selections,
+    # iteration counts, status, transforms
+    worst, T, status, ref = check_clip_against_oracle(gpu, ob, frames, deep=True)
     assert status.all() and worst < 1e-6
+
+
+def test_clips_in_shared_launches_equal_each_clip_alone(gpu):
+    """BASELINE.json configs[3] (many independent 720p clips aligned and warped concurrently): the pyramids, keyframe
+    features, ONE solver launch and ONE warp launch over all clips give each clip exactly what it gets alone."""
+    from video_stabilizer_b200 import _capi as capi, synth
+    from video_stabilizer_b200.clip import Clip, pairs_for_frames
+    w, h, nclips, nf = 1280, 720, 6, 6
+    clips = [synth.make_clip_gpu(gpu, w, h, nf, 200 + c)[0] for c in range(nclips)]
+    T_corr = np.array([0.001, -0.002, 3.25, -1.5])
+    alone = []
+    for fr in clips:
+        c = Clip(w, h, nf, ctx=gpu)
+        c.upload(0, fr)
+        c.build_pyramids(0, nf)
+        pairs, keys = pairs_for_frames(0, nf)
+        c.build_keyframes(keys)
+        T, st, it = c.align(pairs)
+        warped = c.warp(list(range(nf)), np.tile(T_corr, (nf, 1)))
+        alone.append((T, st, it, warped))
+        c.close()
+    big = Clip(w, h, nclips * nf, max_pairs=nclips * (nf - 1), ctx=gpu)
+    allp, keys = [], []
+    for ci, fr in enumerate(clips):
+        big.upload(ci * nf, fr)
+        p, k = pairs_for_frames(0, nf, slot_of=lambda f, ci=ci: ci * nf + f)
+        allp.extend((q.template_slot, q.keyframe_slot, q.invert) for q in p)
+        keys.extend(ci * nf + f for f in k)
+    big.build_pyramids(0, nclips * nf)
+    big.build_keyframes(keys)
+    arr = (capi.VsPair * len(allp))(*[capi.VsPair(*q) for q in allp])
+    T, st, it = big.align(arr)
+    warped = big.warp(list(range(nclips * nf)), np.tile(T_corr, (nclips * nf, 1)))
+    for ci in range(nclips):
+        a = alone[ci]
+        sl = slice(ci * (nf - 1), (ci + 1) * (nf - 1))
+        assert np.array_equal(T[sl], a[0]) and np.array_equal(st[sl], a[1]) and np.array_equal(it[sl], a[2]), ci
+        assert np.array_equal(warped[ci * nf:(ci + 1) * nf], a[3]), ci
+    big.close()
 
 
 def test_lane_parallel_svd_inverse_equals_the_serial_one_bit_for_bit(gpu, ob):

@@ -193,3 +193,20 @@ def test_errors_are_reported_not_swallowed(gpu):
     out = np.zeros((4, 4), np.uint8)
     r = lib.vs_pyr_down_u8(gpu.handle, C.byref(bad), C.byref(capi.img_of(out)), capi.VS_MEM_HOST)
     assert r == -1 and b"NULL" in lib.vs_last_error(gpu.handle)
+
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 2160), (7680, 4320)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_bgr_warp_float_modes_full_size(gpu, ob, w, h, mode):
+    """BASELINE.json configs[4] sizes: the float-bilinear and Lanczos-2 BGR warps on whole 1080p / 4K / 8K frames, compared
+    with the oracle on bands of rows (top, bottom, and spread over the frame) — bit-exact."""
+    from video_stabilizer_b200 import imgproc as ip
+    rng = np.random.default_rng(w + mode)
+    src = noise_image(rng, h, w, 3)
+    T = (0.0013, -0.0021, 6.37, -3.81)
+    got = ip.warpBySimilarityTransform(src, ip.SimilarityTransform(*T), gpu, mode=mode, border=0)
+    M = ip.forward_matrix(ip.SimilarityTransform(*T), w, h)
+    bands = [0, 5, h // 3, h // 2 + 1, h - 24, h - 8]
+    for y0 in bands:
+        want = ob.warp_bgr_matrix(src, M, w, 8, dx0=0, dy0=y0, mode=mode, border=0, fast=False)
+        assert np.array_equal(got[y0:y0 + 8], want), (y0, int(np.abs(got[y0:y0 + 8].astype(int) - want.astype(int)).max()))
