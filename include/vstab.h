@@ -82,6 +82,10 @@ enum { VS_KERNEL_BGR2GRAY = 0, VS_KERNEL_PYR_DOWN, VS_KERNEL_GRAD_XY, VS_KERNEL_
 int vs_ctx_profile_enable(vs_ctx* ctx, int enable);
 int vs_ctx_profile_reset(vs_ctx* ctx);
 int vs_ctx_profile_read(vs_ctx* ctx, int kernel, int64_t* launches, double* total_ms);
+/* Timeline of the launches recorded since the last reset / read, oldest first: out3[i] = {kernel id, start ms, end ms}
+ * relative to the first launch's start (the events of launches on the clip's solver lanes included).  Returns how many.
+ * Call before vs_ctx_profile_read (which consumes the records). */
+int vs_ctx_profile_timeline(vs_ctx* ctx, double* out3, int capacity);
 const char* vs_kernel_name(int kernel);
 /* device memory helpers for callers without their own allocator (C++ host layer) */
 int vs_dev_alloc(vs_ctx* ctx, size_t bytes, void** out);
@@ -224,7 +228,7 @@ typedef struct vs_sweep_params {
  * vs_clip_align gives after vs_clip_set_params with that combination.  phase_correlate_threshold is the clip's. */
 int vs_clip_align_sweep(vs_clip*, const vs_pair* pairs, int n_pairs, const vs_sweep_params* sets, int n_sets,
                         double* out_transform, int32_t* out_status, int mem);
-#define VS_CLIP_SOLVER_LANES 4
+#define VS_CLIP_SOLVER_LANES 6
 /* The same solve, enqueued on one of the clip's solver streams (lane 0 .. VS_CLIP_SOLVER_LANES-1) behind everything
  * enqueued on the context stream so far, without waiting: the pyramids / keyframe features of the next frames and the warps of frames
  * already decided then run beside it.  The pairs of one call use the per-pair scratch [base, base + n): calls in

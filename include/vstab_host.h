@@ -135,9 +135,10 @@ void* vsh_parttraj_create(int rank, int world, int width, int height, int64_t to
 void  vsh_parttraj_destroy(void*);
 int   vsh_parttraj_output_count(void*);
 int   vsh_parttraj_run(void*, const double* meas_all, const uint8_t* ok_all, double* corrections, int64_t* frames);
-/* the full worker.  resident != 0: all local frames live in the ring (upload_resident, then stabilize(frames = NULL)) */
+/* the full worker.  resident != 0: all local frames live in the ring (upload_resident, then stabilize(frames = NULL));
+ * lanes: sub-chunks in flight on the GPU (0 = default) */
 void* vsh_partstab_create(int device, int rank, int world, int width, int height, int64_t total_frames, int sub_frames,
-                          int block, const vsh_stab_params* p, const char* exchange_name, int resident, int host_threads);
+                          int block, const vsh_stab_params* p, const char* exchange_name, int resident, int host_threads, int lanes);
 void  vsh_partstab_destroy(void*);
 /* local frame list of the worker: own frames in video order, each foreign-preceded run headed by its halo frame */
 int     vsh_partstab_local_count(void*);

@@ -312,10 +312,11 @@ void vo_image_warp(const uint8_t* in, int iw, int ih, const double T[4],
 // imgproc.cpp:446-484 — BGR warp.  Mode 0 restates cv::warpAffine(INTER_LINEAR,
 // BORDER_CONSTANT 0) without WARP_INVERSE_MAP: OpenCV inverts M in f64, walks the
 // destination with 10-bit fixed-point coordinates (AB_BITS=10), rounds to 1/32 px
-// (INTER_BITS=5) and blends with 15-bit integer weights.  Modes 1 and 2 keep the same
-// geometry (f64 inverse cast to f32) with float bilinear / Lanczos-2 sampling; they have
-// no counterpart in the reference (its bgr_image_warp generator is gone) and are defined
-// here for the interpolation sweep (BASELINE.json configs[4]).
+// (INTER_BITS=5) and blends with 15-bit integer weights.  Modes 1 and 2 have no counterpart
+// in the reference (its bgr_image_warp generator is gone): they are defined here, and in
+// the kernels alike, for the interpolation sweep (BASELINE.json configs[4]).  Mode 1 is the
+// same exact integer bilinear on a finer grid (16 position bits, 1/256-pixel weights); mode
+// 2 keeps the f64 inverse cast to f32 with Lanczos-2 sampling.
 static inline long rint_he(double v) { return std::lrint(v); } // round-half-even (default FE mode)
 
 // General form: forward 2x3 matrix M (as cv::warpAffine takes it), source sw x sh, destination window dw x dh whose pixel
@@ -331,22 +332,28 @@ void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uin
     double i02 = -i00 * m02 - i01 * m12;
     double i12 = -i10 * m02 - i11 * m12;
 
-    if (mode == 0) {
+    if (mode == 0 || mode == 1) {
+        // Both bilinear modes are exact integer arithmetic on a fixed-point grid with P fractional position bits of which
+        // the top W are the weight: mode 0 is cv::warpAffine's own (AB_BITS = 10, INTER_BITS = 5), mode 1 keeps 16
+        // position bits and 1/256-pixel weights (no counterpart upstream; defined here and in the kernels alike).
+        const int P = mode == 0 ? 10 : 16, W = mode == 0 ? 5 : 8;
+        const double SCALE = (double)(1 << P);
+        const int ROUND = 1 << (P - W - 1), one = 1 << W, half = 1 << (2 * W - 1);
         std::vector<int> adelta(ow), bdelta(ow);
         for (int xo = 0; xo < ow; xo++) {
-            adelta[xo] = (int)rint_he(i00 * (xo + dx0) * 1024);
-            bdelta[xo] = (int)rint_he(i10 * (xo + dx0) * 1024);
+            adelta[xo] = (int)rint_he(i00 * (xo + dx0) * SCALE);
+            bdelta[xo] = (int)rint_he(i10 * (xo + dx0) * SCALE);
         }
         for (int yo = 0; yo < oh; yo++) {
             int y = yo + dy0;
-            int X0 = (int)rint_he((i01 * y + i02) * 1024) + 16;
-            int Y0 = (int)rint_he((i11 * y + i12) * 1024) + 16;
+            int X0 = (int)rint_he((i01 * y + i02) * SCALE) + ROUND;
+            int Y0 = (int)rint_he((i11 * y + i12) * SCALE) + ROUND;
             for (int xo = 0; xo < ow; xo++) {
-                int X = (X0 + adelta[xo]) >> 5, Y = (Y0 + bdelta[xo]) >> 5;
-                int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
-                // 15-bit weights: rint(32768 * (1-fy/32)(1-fx/32)) — exact, sum is 32768
-                int w00 = (32 - fx) * (32 - fy) * 32, w10 = fx * (32 - fy) * 32;
-                int w01 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+                const int sfx = X0 + adelta[xo], sfy = Y0 + bdelta[xo];
+                const int sx = sfx >> P, sy = sfy >> P;
+                const int fx = (sfx >> (P - W)) & (one - 1), fy = (sfy >> (P - W)) & (one - 1);
+                // weights sum to 2^(2W); for mode 0 this equals cv's 15-bit weights and (v + 16384) >> 15
+                const int w00 = (one - fx) * (one - fy), w10 = fx * (one - fy), w01 = (one - fx) * fy, w11 = fx * fy;
                 uint8_t* d = dst + ((size_t)yo * ow + xo) * 3;
                 const bool inside = sx >= 0 && sx + 1 < w && sy >= 0 && sy + 1 < h;
                 if (inside) {
@@ -354,7 +361,7 @@ void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uin
                     const uint8_t* p1 = p0 + (size_t)w * 3;
                     for (int c = 0; c < 3; c++) {
                         int v = w00 * p0[c] + w10 * p0[3 + c] + w01 * p1[c] + w11 * p1[3 + c];
-                        d[c] = (uint8_t)((v + 16384) >> 15);
+                        d[c] = (uint8_t)((v + half) >> (2 * W));
                     }
                     continue;
                 }
@@ -366,7 +373,7 @@ void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uin
                     };
                     int v = w00 * tap(sx, sy) + w10 * tap(sx + 1, sy) +
                             w01 * tap(sx, sy + 1) + w11 * tap(sx + 1, sy + 1);
-                    d[c] = (uint8_t)((v + 16384) >> 15);
+                    d[c] = (uint8_t)((v + half) >> (2 * W));
                 }
             }
         }

@@ -56,6 +56,7 @@ SYMBOLS = {
     "vs_ctx_profile_enable": (C.c_int, [_P, C.c_int]),
     "vs_ctx_profile_reset": (C.c_int, [_P]),
     "vs_ctx_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "vs_ctx_profile_timeline": (C.c_int, [_P, _P, C.c_int]),
     "vs_kernel_name": (C.c_char_p, [C.c_int]),
     "vs_dev_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "vs_dev_free": (C.c_int, [_P, _P]),

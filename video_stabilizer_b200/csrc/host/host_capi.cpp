@@ -411,12 +411,12 @@ int vsh_parttraj_run(void* tp, const double* meas_all, const uint8_t* ok_all, do
 int vsh_parttraj_output_count(void* t) { return ((vstab::PartitionedTrajectory*)t)->output_count(); }
 
 void* vsh_partstab_create(int device, int rank, int world, int width, int height, int64_t total_frames, int sub_frames,
-                          int block, const vsh_stab_params* p, const char* exchange_name, int resident, int host_threads)
+                          int block, const vsh_stab_params* p, const char* exchange_name, int resident, int host_threads, int lanes)
 {
     vstab::PartitionedStabilizer* s = nullptr;
     guarded([&] {
         s = new vstab::PartitionedStabilizer(device, rank, world, width, height, (long)total_frames, sub_frames, block, stab_params(p),
-                                             exchange_name ? exchange_name : "", resident != 0, host_threads);
+                                             exchange_name ? exchange_name : "", resident != 0, host_threads, lanes);
         return 0;
     });
     return s;

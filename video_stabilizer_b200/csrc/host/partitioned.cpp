@@ -135,12 +135,13 @@ void PartitionedTrajectory::end_video()
 // ================================================================== GPU half
 PartitionedStabilizer::PartitionedStabilizer(int device, int rank, int world, int width, int height, long total_frames,
                                              int sub_frames, int block_subchunks, const VideoStabilizerParams& params,
-                                             const std::string& exchange_name, bool resident, int host_threads)
+                                             const std::string& exchange_name, bool resident, int host_threads, int lanes)
     : m_w(width), m_h(height), m_crop(std::max(0, params.crop_pixels)), m_resident(resident), m_params(params),
       m_traj(rank, world, width, height, total_frames, sub_frames, block_subchunks, params, exchange_name, host_threads)
 {
     if (2 * m_crop >= width || 2 * m_crop >= height) throw std::runtime_error("PartitionedStabilizer: crop_pixels removes the whole frame");
-    m_lanes = m_max_lanes = resident ? 3 : 2;
+    if (lanes <= 0) lanes = resident ? std::max(2, block_subchunks) : 2;
+    m_lanes = m_max_lanes = std::max(1, std::min(lanes, VS_CLIP_SOLVER_LANES));
     const int locals = m_traj.local_count();
     m_capacity = std::max(2, resident ? locals : std::min(locals, (m_max_lanes + 1) * (sub_frames + 1)));
     if (vs_ctx_create(device, &m_ctx) != VS_OK)

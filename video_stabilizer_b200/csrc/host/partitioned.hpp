@@ -111,9 +111,11 @@ class PartitionedStabilizer {
 public:
     // resident = true: the ring holds all of this worker's frames (upload_resident + stabilize(nullptr ...));
     // false: frames stream through a ring of (lanes + 1) sub-chunks.
+    // lanes: sub-chunks in flight on the GPU, one solver stream each (0 = default: the sub-chunks of a chunk, at most
+    // VS_CLIP_SOLVER_LANES, when resident; 2 when streamed)
     PartitionedStabilizer(int device, int rank, int world, int width, int height, long total_frames, int sub_frames,
                           int block_subchunks, const VideoStabilizerParams& params, const std::string& exchange_name,
-                          bool resident, int host_threads = 4);
+                          bool resident, int host_threads = 4, int lanes = 0);
     ~PartitionedStabilizer();
     PartitionedStabilizer(const PartitionedStabilizer&) = delete;
     PartitionedStabilizer& operator=(const PartitionedStabilizer&) = delete;

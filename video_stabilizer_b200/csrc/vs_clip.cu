@@ -153,9 +153,9 @@ void build_bgr_tensor_map(vs_clip* c)
 int clip_warp_launch(vs_clip* c, const int32_t* d_slots, const VsWarpCoef* d_coef, const VsDevImg& dst, int crop, int mode, int border, int n)
 {
     VsDevImg src{c->d_bgr, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
-    if (mode == VS_WARP_CV_EXACT_BILINEAR && border == VS_BORDER_CONSTANT0 && c->bgr_map_rows_ok && n <= c->capacity &&
-        dst.w <= c->w && dst.h <= c->h)
-        return vsk_bgr_warp_slots_rows(c->ctx, &c->bgr_map_rows, src, d_slots, d_coef, dst, crop, crop, c->d_warp_tab);
+    if ((mode == VS_WARP_CV_EXACT_BILINEAR || mode == VS_WARP_FLOAT_BILINEAR) && border == VS_BORDER_CONSTANT0 &&
+        c->bgr_map_rows_ok && n <= c->capacity && dst.w <= c->w && dst.h <= c->h)
+        return vsk_bgr_warp_slots_rows(c->ctx, &c->bgr_map_rows, src, d_slots, d_coef, dst, crop, crop, c->d_warp_tab, mode);
     return vsk_bgr_warp_slots(c->ctx, src, d_slots, d_coef, dst, crop, crop, mode, border);
 }
 

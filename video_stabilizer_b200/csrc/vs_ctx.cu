@@ -131,6 +131,25 @@ int vs_ctx_profile_read(vs_ctx* ctx, int kernel, int64_t* launches, double* tota
     return VS_OK;
 }
 
+int vs_ctx_profile_timeline(vs_ctx* ctx, double* out3, int capacity)
+{
+    if (!ctx || !ctx->prof) return 0;
+    VsProfiler* p = ctx->prof;
+    cudaStreamSynchronize(ctx->stream);
+    int n = 0;
+    cudaEvent_t base = p->pending.empty() ? nullptr : p->pending.front().a;
+    for (auto& s : p->pending) {
+        cudaEventSynchronize(s.b);
+        float t0 = 0, t1 = 0;
+        if (n < capacity && cudaEventElapsedTime(&t0, base, s.a) == cudaSuccess && cudaEventElapsedTime(&t1, base, s.b) == cudaSuccess) {
+            out3[3 * n] = s.id; out3[3 * n + 1] = t0; out3[3 * n + 2] = t1;
+            n++;
+        }
+    }
+    cudaGetLastError();
+    return n;
+}
+
 const char* vs_kernel_name(int kernel)
 {
     static const char* names[VSK_COUNT] = {"bgr2gray", "pyr_down", "grad_xy", "image_warp", "bgr_warp", "grad_argmax",

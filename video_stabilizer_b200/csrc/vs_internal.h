@@ -38,8 +38,8 @@ void vs_warp_coef_from_forward(const double* M6, VsWarpCoef* out);
 // imgproc.cpp:458-466 — centre-based similarity -> forward 2x3 matrix
 void vs_forward_matrix_from_transform(const double* T4, int cols, int rows, double* M6);
 // d_coef: device array of `src.batch` VsWarpCoef
-// d_tab: optional scratch of vs_warp_rows_tab_ints(dst.w, dst.h) int32 per image; with it the cv-exact / constant-border
-// mode runs the row-group kernel whenever the source can be described by a tensor map (vs_warp_rows_usable)
+// d_tab: optional scratch of vs_warp_rows_tab_ints(dst.w, dst.h) int32 per image; with it the two bilinear modes (constant
+// border) run the row-group kernel whenever the source can be described by a tensor map (vs_warp_rows_usable)
 int vsk_bgr_warp(vs_ctx*, const VsDevImg& src, const VsWarpCoef* d_coef, const VsDevImg& dst,
                  int dst_x0, int dst_y0, int mode, int border, int32_t* d_tab = nullptr);
 bool vs_warp_rows_usable(const VsDevImg& src, int mode, int border);
@@ -50,7 +50,8 @@ int vsk_bgr_warp_slots(vs_ctx*, const VsDevImg& src, const int32_t* d_slots, con
 // row-group form (the production kernel): tensor map with box {120, 28, 1} (160 pixels x 28 rows) over the same view;
 // d_tab is scratch for the per-launch fixed-point tables, vs_warp_rows_tab_ints(dst.w, dst.h) int32 per image
 int vsk_bgr_warp_slots_rows(vs_ctx*, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,
-                            const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0, int32_t* d_tab);
+                            const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0, int32_t* d_tab,
+                            int mode = VS_WARP_CV_EXACT_BILINEAR);
 constexpr int VS_WARP_ROWS_BOX_WORDS = 120, VS_WARP_ROWS_BOX_ROWS = 28, VS_WARP_ROWS_TILE_W = 128, VS_WARP_ROWS_TILE_H = 24;
 static inline size_t vs_warp_rows_tab_ints(int dw, int dh)
 {

@@ -567,148 +567,36 @@ k_bgr_warp_px(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t 
     d[0] = (uint8_t)px; d[1] = (uint8_t)(px >> 8); d[2] = (uint8_t)(px >> 16);
 }
 
-constexpr int WQ_THREADS = 96, WQ_ROWS = 4;      // 384 output pixels x 4 rows per CTA (1920 = 5 x 384, 3840 = 10 x 384)
+// ------------------------------------------------------------------ the two bilinear modes: one arithmetic, two grids
+// Both bilinear modes are exact integer arithmetic on a fixed-point grid:
+//   position of output pixel (x, y):  sfx = rint(i00 x 2^P) + rint((i01 y + i02) 2^P) + 2^(P-W-1)   (likewise sfy),
+//   source pixel (sfx >> P, sfy >> P), weight fractions fx, fy = the top W bits below the point,
+//   out = (sum of (2^W - fx | fx)(2^W - fy | fy) taps + 2^(2W-1)) >> 2W per channel.
+// VS_WARP_CV_EXACT_BILINEAR is cv::warpAffine's grid (AB_BITS = 10, INTER_BITS = 5: P = 10, W = 5; imgproc.cpp:446-484).
+// VS_WARP_FLOAT_BILINEAR (no counterpart upstream) keeps 16 fractional position bits and 1/256-pixel weights (P = 16,
+// W = 8): positions are good to 2^-16 px on frames up to 16384 pixels (an f32 coordinate is good to 2^-11 px at 8K), the
+// weights are as fine as the 8-bit output can show.  Same kernels, same instruction count: the weights of one pixel sum to
+// 2^(2W), and with the cv weights scaled by 64 both grids blend to byte 2 of a 32-bit accumulator.
+template <int MODE> struct WarpGrid;
+template <> struct WarpGrid<VS_WARP_CV_EXACT_BILINEAR> { static constexpr int P = 10, W = 5; };
+template <> struct WarpGrid<VS_WARP_FLOAT_BILINEAR> { static constexpr int P = 16, W = 8; };
 
-template <int MODE, int BORDER>
-__global__ void __launch_bounds__(WQ_THREADS)
-k_bgr_warp(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
-           const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
-           uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
-           int dst_x0, int dst_y0, int src_al4, int dst_al4)
+// one output pixel from four BGRX taps, any fractions: returns B | G << 8 | R << 16
+template <int MODE>
+__device__ __forceinline__ uint32_t warp_blend_taps(uint32_t t00, uint32_t t10, uint32_t t01, uint32_t t11, int sfx, int sfy)
 {
-    const int xo = 4 * (blockIdx.x * WQ_THREADS + threadIdx.x);
-    const int lane = threadIdx.x & 31;
-    const int npx = max(0, min(4, dw - xo));                          // threads past the row stay for the warp-wide steps below
-    const int b = blockIdx.z;
-    const int slot = slots ? slots[b] : b;
-    const uint8_t* src = src_base + (size_t)slot * src_bs;
-    const VsWarpCoef cf = coefs[b];
-    const float f00 = (float)cf.i00, f01 = (float)cf.i01, f02 = (float)cf.i02;
-    const float f10 = (float)cf.i10, f11 = (float)cf.i11, f12 = (float)cf.i12;
-    float fx[4], gx[4];
+    constexpr int P = WarpGrid<MODE>::P, W = WarpGrid<MODE>::W;
+    const uint32_t fx = ((uint32_t)sfx >> (P - W)) & ((1u << W) - 1u), fy = ((uint32_t)sfy >> (P - W)) & ((1u << W) - 1u);
+    const uint32_t one = 1u << W, half = 1u << (2 * W - 1);
+    const uint32_t w00 = (one - fx) * (one - fy), w10 = fx * (one - fy), w01 = (one - fx) * fy, w11 = fx * fy;
+    uint32_t out = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const float xf = (float)(xo + j + dst_x0);
-        fx[j] = __fmul_rn(f00, xf);
-        gx[j] = __fmul_rn(f10, xf);
+    for (int c = 0; c < 3; c++) {
+        const uint32_t v = w00 * ((t00 >> (8 * c)) & 0xffu) + w10 * ((t10 >> (8 * c)) & 0xffu) +
+                           w01 * ((t01 >> (8 * c)) & 0xffu) + w11 * ((t11 >> (8 * c)) & 0xffu);
+        out |= ((v + half) >> (2 * W)) << (8 * c);
     }
-    constexpr int C0 = MODE == VS_WARP_FLOAT_BILINEAR ? 0 : -1;       // first tap column / row relative to (ix, iy)
-    constexpr int NT = MODE == VS_WARP_FLOAT_BILINEAR ? 2 : 4;        // taps per axis
-    constexpr int NB = 3 * (NT + 3);                                  // source bytes of a row of a regular group
-    constexpr int NW = (NB + 3 + 3) / 4;                              // aligned words covering them at any alignment
-    constexpr int NU = (NB + 3) / 4;                                  // words of the byte-aligned stream
-
-    for (int r = 0; r < WQ_ROWS; r++) {
-        const int yo = blockIdx.y * WQ_ROWS + r;
-        if (yo >= dh) break;
-        const float yf = (float)(yo + dst_y0);
-        const float ay = __fmul_rn(f01, yf), by = __fmul_rn(f11, yf);
-        int ix[4], iy[4];
-        float rx[4], ry[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float Wx = __fadd_rn(__fadd_rn(fx[j], ay), f02);
-            const float Wy = __fadd_rn(__fadd_rn(gx[j], by), f12);
-            const float fWx = floorf(Wx), fWy = floorf(Wy);
-            rx[j] = __fsub_rn(Wx, fWx); ry[j] = __fsub_rn(Wy, fWy);
-            ix[j] = (int)fWx; iy[j] = (int)fWy;
-        }
-        const int off = 3 * (ix[0] + C0);
-        const bool regular = npx == 4 && src_al4 && ix[1] == ix[0] + 1 && ix[2] == ix[0] + 2 && ix[3] == ix[0] + 3 &&
-                             iy[1] == iy[0] && iy[2] == iy[0] && iy[3] == iy[0] &&
-                             ix[0] + C0 >= 0 && iy[0] + C0 >= 0 && iy[0] + C0 + NT <= h && (off & ~3) + 4 * NW <= 3 * w;
-        uint32_t px[4] = {0u, 0u, 0u, 0u};
-        if (regular) {
-            const uint32_t sh = (uint32_t)(off & 3) * 8u;
-            uint32_t u[NT][NU];
-#pragma unroll
-            for (int t = 0; t < NT; t++) {
-                const uint32_t* rowp = reinterpret_cast<const uint32_t*>(src + (size_t)(iy[0] + C0 + t) * src_stride + (off & ~3));
-                uint32_t wv[NW + 1];
-#pragma unroll
-                for (int k = 0; k < NW; k++) wv[k] = __ldg(rowp + k);
-                wv[NW] = 0u;
-#pragma unroll
-                for (int k = 0; k < NU; k++) u[t][k] = __funnelshift_r(wv[k], wv[k + 1], sh);
-            }
-            // byte i of the byte-aligned stream of tap row t as a float: source pixel ix[0] + C0 + i / 3, channel i % 3
-#define VS_TAPF(t, i) __fsub_rn(__uint_as_float(__byte_perm(u[t][(i) >> 2], 0x4B000000u, 0x7540u + ((i) & 3))), 8388608.0f)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint32_t bits[3];
-                if (MODE == VS_WARP_FLOAT_BILINEAR) {
-                    const float omx = __fsub_rn(1.0f, rx[j]), omy = __fsub_rn(1.0f, ry[j]);
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const float p00 = VS_TAPF(0, 3 * j + c), p10 = VS_TAPF(0, 3 * j + 3 + c);
-                        const float p01 = VS_TAPF(1, 3 * j + c), p11 = VS_TAPF(1, 3 * j + 3 + c);
-                        const float top = __fadd_rn(__fmul_rn(p00, omx), __fmul_rn(p10, rx[j]));
-                        const float bot = __fadd_rn(__fmul_rn(p01, omx), __fmul_rn(p11, rx[j]));
-                        const float v = __fadd_rn(__fmul_rn(top, omy), __fmul_rn(bot, ry[j]));
-                        // a convex combination of bytes: 0 <= v + 0.5 < 256, the clamp of the general path never acts
-                        bits[c] = wq_byte_bits(__fadd_rn(v, 0.5f));
-                    }
-                } else {
-                    float wx[5], wy[5];
-#pragma unroll
-                    for (int q = 1; q < 5; q++) {
-                        wx[q] = vs_lanczos2(__fsub_rn((float)(q - 2), rx[j]));
-                        wy[q] = vs_lanczos2(__fsub_rn((float)(q - 2), ry[j]));
-                    }
-                    float num0 = 0.0f, num1 = 0.0f, num2 = 0.0f, den = 0.0f;
-#pragma unroll
-                    for (int ty = 1; ty < 5; ty++) {
-#pragma unroll
-                        for (int tx = 1; tx < 5; tx++) {
-                            const float w2 = __fmul_rn(wx[tx], wy[ty]);
-                            num0 = __fadd_rn(num0, __fmul_rn(w2, VS_TAPF(ty - 1, 3 * (j + tx - 1))));
-                            num1 = __fadd_rn(num1, __fmul_rn(w2, VS_TAPF(ty - 1, 3 * (j + tx - 1) + 1)));
-                            num2 = __fadd_rn(num2, __fmul_rn(w2, VS_TAPF(ty - 1, 3 * (j + tx - 1) + 2)));
-                            den = __fadd_rn(den, w2);
-                        }
-                    }
-                    bits[0] = wq_byte_bits(wq_round_clamp(__fdiv_rn(num0, den)));
-                    bits[1] = wq_byte_bits(wq_round_clamp(__fdiv_rn(num1, den)));
-                    bits[2] = wq_byte_bits(wq_round_clamp(__fdiv_rn(num2, den)));
-                }
-                px[j] = wq_pack_bgr(bits[0], bits[1], bits[2]);
-            }
-#undef VS_TAPF
-        }
-        // Groups that are not regular (typically one per warp where the row of taps changes, a few at the image borders) are
-        // done by the whole warp, one group at a time: lane l takes pixel l & 3 of the group (eight lanes compute the same
-        // pixel — same instructions, no divergence), so such a group costs the warp one general pixel instead of four.
-        unsigned todo = __ballot_sync(0xffffffffu, !regular && npx > 0);
-        while (todo) {
-            const int owner = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int j = lane & 3;
-            int gix = 0, giy = 0;
-            float grx = 0.0f, gry = 0.0f;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int tix = __shfl_sync(0xffffffffu, ix[q], owner), tiy = __shfl_sync(0xffffffffu, iy[q], owner);
-                const float trx = __shfl_sync(0xffffffffu, rx[q], owner), try_ = __shfl_sync(0xffffffffu, ry[q], owner);
-                if (q == j) { gix = tix; giy = tiy; grx = trx; gry = try_; }
-            }
-            const uint32_t res = bgr_warp_pixel<MODE, BORDER>(src, src_stride, w, h, gix, giy, grx, gry);
-            const uint32_t r0 = __shfl_sync(0xffffffffu, res, 0), r1 = __shfl_sync(0xffffffffu, res, 1),
-                           r2 = __shfl_sync(0xffffffffu, res, 2), r3 = __shfl_sync(0xffffffffu, res, 3);
-            if (lane == owner) { px[0] = r0; px[1] = r1; px[2] = r2; px[3] = r3; }
-        }
-        if (npx == 0) continue;
-        uint8_t* d = dst_base + (size_t)b * dst_bs + (size_t)yo * dst_stride + 3 * xo;
-        if (npx == 4 && dst_al4) {
-            uint32_t* dw32 = reinterpret_cast<uint32_t*>(d);
-            dw32[0] = __byte_perm(px[0], px[1], 0x4210);
-            dw32[1] = __byte_perm(px[1], px[2], 0x5421);
-            dw32[2] = __byte_perm(px[2], px[3], 0x6542);
-        } else {
-            for (int j = 0; j < npx; j++) {
-                d[3 * j] = (uint8_t)px[j]; d[3 * j + 1] = (uint8_t)(px[j] >> 8); d[3 * j + 2] = (uint8_t)(px[j] >> 16);
-            }
-        }
-    }
+    return out;
 }
 
 // ------------------------------------------------------------------ BGR warp, cv-exact, tiled
@@ -771,13 +659,30 @@ __device__ __forceinline__ uint32_t cv_blend(uint2 top, uint2 bot, int fx, int f
     return (b >> 10) | ((g >> 10) << 8) | ((r >> 10) << 16);
 }
 
-template <int BORDER>
+// one pixel from two staged entries: the cv grid blends with IDP.2A (weights <= 1024); the fine grid's weights reach
+// 65536, so it unpacks the entry (this kernel is the fallback path: borders, small or unaligned images)
+template <int MODE>
+__device__ __forceinline__ uint32_t wt_blend(uint2 top, uint2 bot, int sfx, int sfy)
+{
+    if (MODE == VS_WARP_CV_EXACT_BILINEAR) return cv_blend(top, bot, (sfx >> 5) & 31, (sfy >> 5) & 31);
+    // entry = (B, B', G, G'), (R, R')
+    const uint32_t t00 = (top.x & 0xffu) | ((top.x >> 8) & 0xff00u) | ((top.y & 0xffu) << 16);
+    const uint32_t t10 = ((top.x >> 8) & 0xffu) | ((top.x >> 16) & 0xff00u) | ((top.y & 0xff00u) << 8);
+    const uint32_t t01 = (bot.x & 0xffu) | ((bot.x >> 8) & 0xff00u) | ((bot.y & 0xffu) << 16);
+    const uint32_t t11 = ((bot.x >> 8) & 0xffu) | ((bot.x >> 16) & 0xff00u) | ((bot.y & 0xff00u) << 8);
+    return warp_blend_taps<MODE>(t00, t10, t01, t11, sfx, sfy);
+}
+
+template <int MODE, int BORDER>
 __global__ void __launch_bounds__(WT_THREADS)
 k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
                     const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
                     uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
                     int dst_x0, int dst_y0, int src_al4, int dst_al8)
 {
+    constexpr int P = WarpGrid<MODE>::P;
+    constexpr double SCALE = (double)(1 << P);
+    constexpr int ROUND = 1 << (P - WarpGrid<MODE>::W - 1);
     extern __shared__ __align__(16) uint32_t wt_smem[];
     // staged entries as two planes (SX: .x words, SY: .y words): a lane's four entries are then 16
     // contiguous bytes per plane, so the staging stores of a warp are conflict-free
@@ -797,12 +702,12 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
 
     // column terms of this thread, row terms of the tile (cv::warpAffine's adelta/bdelta, X0/Y0)
     const int xcol = ox0 + min(tid, tw - 1) + dst_x0;
-    const int adelta = __double2int_rn(cf.i00 * (double)xcol * 1024.0);
-    const int bdelta = __double2int_rn(cf.i10 * (double)xcol * 1024.0);
+    const int adelta = __double2int_rn(cf.i00 * (double)xcol * SCALE);
+    const int bdelta = __double2int_rn(cf.i10 * (double)xcol * SCALE);
     if (tid < WT_H) {
         const int y = oy0 + min(tid, th - 1) + dst_y0;
-        sXY0[tid] = make_int2(__double2int_rn((cf.i01 * (double)y + cf.i02) * 1024.0) + 16,
-                              __double2int_rn((cf.i11 * (double)y + cf.i12) * 1024.0) + 16);
+        sXY0[tid] = make_int2(__double2int_rn((cf.i01 * (double)y + cf.i02) * SCALE) + ROUND,
+                              __double2int_rn((cf.i11 * (double)y + cf.i12) * SCALE) + ROUND);
     }
     __syncthreads();
 
@@ -810,12 +715,12 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
     // column terms of the first and last column are those of threads 0 and tw-1
     const int xr = ox0 + tw - 1 + dst_x0;
     const int aL = __shfl_sync(0xffffffffu, adelta, 0), bL = __shfl_sync(0xffffffffu, bdelta, 0);
-    const int aL0 = warp == 0 ? aL : __double2int_rn(cf.i00 * (double)(ox0 + dst_x0) * 1024.0);
-    const int bL0 = warp == 0 ? bL : __double2int_rn(cf.i10 * (double)(ox0 + dst_x0) * 1024.0);
-    const int aR = __double2int_rn(cf.i00 * (double)xr * 1024.0), bR = __double2int_rn(cf.i10 * (double)xr * 1024.0);
+    const int aL0 = warp == 0 ? aL : __double2int_rn(cf.i00 * (double)(ox0 + dst_x0) * SCALE);
+    const int bL0 = warp == 0 ? bL : __double2int_rn(cf.i10 * (double)(ox0 + dst_x0) * SCALE);
+    const int aR = __double2int_rn(cf.i00 * (double)xr * SCALE), bR = __double2int_rn(cf.i10 * (double)xr * SCALE);
     const int2 xyT = sXY0[0], xyB = sXY0[th - 1];
-    const int sxmin = (min(xyT.x, xyB.x) + min(aL0, aR)) >> 10, sxmax = (max(xyT.x, xyB.x) + max(aL0, aR)) >> 10;
-    const int symin = (min(xyT.y, xyB.y) + min(bL0, bR)) >> 10, symax = (max(xyT.y, xyB.y) + max(bL0, bR)) >> 10;
+    const int sxmin = (min(xyT.x, xyB.x) + min(aL0, aR)) >> P, sxmax = (max(xyT.x, xyB.x) + max(aL0, aR)) >> P;
+    const int symin = (min(xyT.y, xyB.y) + min(bL0, bR)) >> P, symax = (max(xyT.y, xyB.y) + max(bL0, bR)) >> P;
     const int bx0 = (sxmin >> 2) * 4;                            // 4-pixel (12-byte, 3-word) staging granules
     const int ngran = ((sxmax - bx0) >> 2) + 1;                  // entries bx0 .. sxmax (entry x also carries x+1)
     const int pitch = ngran * 4;                                 // entries per staged row
@@ -893,9 +798,8 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
             if (r >= th) break;
             const int2 xy0 = sXY0[r];
             const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
-            const int fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
-            const int e = sorg + (sfy >> 10) * pitch + (sfx >> 10);
-            const uint32_t px = cv_blend(make_uint2(SX[e], SY[e]), make_uint2(SX[e + pitch], SY[e + pitch]), fx, fy);
+            const int e = sorg + (sfy >> P) * pitch + (sfx >> P);
+            const uint32_t px = wt_blend<MODE>(make_uint2(SX[e], SY[e]), make_uint2(SX[e + pitch], SY[e + pitch]), sfx, sfy);
             const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
             if (keep) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
         }
@@ -903,12 +807,12 @@ k_bgr_warp_cv_tiled(const uint8_t* __restrict__ src_base, int64_t src_stride, in
         for (int r = 0; r < th; r++) {
             const int2 xy0 = sXY0[r];
             const int sfx = xy0.x + adelta, sfy = xy0.y + bdelta;
-            const int sx = sfx >> 10, sy = sfy >> 10, fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
+            const int sx = sfx >> P, sy = sfy >> P;
             const uint32_t t00 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx, sy);
             const uint32_t t10 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx + 1, sy);
             const uint32_t t01 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx, sy + 1);
             const uint32_t t11 = bgr_texel_word<BORDER>(src, src_stride, w, h, sx + 1, sy + 1);
-            const uint32_t px = cv_blend(wt_entry(t00, t10), wt_entry(t01, t11), fx, fy);
+            const uint32_t px = warp_blend_taps<MODE>(t00, t10, t01, t11, sfx, sfy);
             const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
             if (keep) Orow[r * WT_OUT_ROW_WORDS] = __byte_perm(px, nx, sel);
         }
@@ -970,17 +874,21 @@ static_assert(WG_W == VS_WARP_ROWS_TILE_W && WG_H == VS_WARP_ROWS_TILE_H, "vs_wa
 
 // Per launch and image b (vs_warp_rows_tab_ints int32 each): AD[dwp], BD[dwp] (column terms), XY0[dhp] (row terms,
 // rounding offset included), TILE[tiles_y][tiles_x] = {first TMA word, first source row, first source pixel, box fits}.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 k_warp_tables(const VsWarpCoef* __restrict__ coefs, int dw, int dh, int dwp, int dhp, int per, int dst_x0, int dst_y0,
               int32_t* __restrict__ tab)
 {
+    constexpr int P = WarpGrid<MODE>::P, W = WarpGrid<MODE>::W;
+    constexpr double SCALE = (double)(1 << P);
+    constexpr int ROUND = 1 << (P - W - 1);
     const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
     const VsWarpCoef cf = coefs[b];
     int32_t* const t = tab + (size_t)b * per;
-    auto colx = [&](int x) { return __double2int_rn(cf.i00 * (double)(x + dst_x0) * 1024.0); };
-    auto coly = [&](int x) { return __double2int_rn(cf.i10 * (double)(x + dst_x0) * 1024.0); };
-    auto rowx = [&](int y) { return __double2int_rn((cf.i01 * (double)(y + dst_y0) + cf.i02) * 1024.0) + 16; };
-    auto rowy = [&](int y) { return __double2int_rn((cf.i11 * (double)(y + dst_y0) + cf.i12) * 1024.0) + 16; };
+    auto colx = [&](int x) { return __double2int_rn(cf.i00 * (double)(x + dst_x0) * SCALE); };
+    auto coly = [&](int x) { return __double2int_rn(cf.i10 * (double)(x + dst_x0) * SCALE); };
+    auto rowx = [&](int y) { return __double2int_rn((cf.i01 * (double)(y + dst_y0) + cf.i02) * SCALE) + ROUND; };
+    auto rowy = [&](int y) { return __double2int_rn((cf.i11 * (double)(y + dst_y0) + cf.i12) * SCALE) + ROUND; };
     const int tiles_x = dwp / WG_W, tiles_y = dhp / WG_H;
     if (i < dwp) {
         t[i] = colx(i);
@@ -993,32 +901,48 @@ k_warp_tables(const VsWarpCoef* __restrict__ coefs, int dw, int dh, int dwp, int
         const int xl = tx * WG_W, xr = min(xl + WG_W, dw) - 1, yt = ty * WG_H, yb = min(yt + WG_H, dh) - 1;
         const int aL = colx(xl), aR = colx(xr), bL = coly(xl), bR = coly(xr);
         const int XT = rowx(yt), XB = rowx(yb), YT = rowy(yt), YB = rowy(yb);
-        const int sxmin = (min(XT, XB) + min(aL, aR)) >> 10, sxmax = (max(XT, XB) + max(aL, aR)) >> 10;
-        const int symin = (min(YT, YB) + min(bL, bR)) >> 10, symax = (max(YT, YB) + max(bL, bR)) >> 10;
+        const int sxmin = (min(XT, XB) + min(aL, aR)) >> P, sxmax = (max(XT, XB) + max(aL, aR)) >> P;
+        const int symin = (min(YT, YB) + min(bL, bR)) >> P, symax = (max(YT, YB) + max(bL, bR)) >> P;
         const int bx0 = (sxmin >> 4) * 16;                        // a TMA box starts 16-byte aligned: 16 pixels = 48 bytes
         // pixels bx0 .. sxmax + 1 and rows symin .. symax + 1 must be inside the box
         const bool fits = sxmax + 1 - bx0 < WG_BOX_PIXELS && symax + 1 - symin < WG_BOX_ROWS &&
-                          sxmin > -(1 << 20) && sxmax < (1 << 20) && symin > -(1 << 20) && symax < (1 << 20);
+                          sxmin > -(1 << 14) && sxmax < (1 << 14) && symin > -(1 << 14) && symax < (1 << 14);
         // bit 1: fx == fy == 0 at all four corners of the tile (then, for a near-identity transform, almost everywhere in it)
-        const int fr = ((XT + aL) | (XT + aR) | (XB + aL) | (XB + aR) | (YT + bL) | (YT + bR) | (YB + bL) | (YB + bR)) & 0x3e0;
+        const int fr = ((XT + aL) | (XT + aR) | (XB + aL) | (XB + aR) | (YT + bL) | (YT + bR) | (YB + bL) | (YB + bR)) & (((1 << W) - 1) << (P - W));
         reinterpret_cast<int4*>(t + 2 * dwp + 2 * dhp)[q] = make_int4((bx0 >> 4) * 12, symin, bx0, (fits ? 1 : 0) | (fr == 0 ? 2 : 0));
     }
 }
 
-// packed 16-bit weight pairs of one pixel scaled by 64: wt = 64 w00 | 64 w10 << 16, wb = 64 w01 | 64 w11 << 16
-// (w = (32 - fx | fx) (32 - fy | fy)).  64 w00 = 65536 when fx == fy == 0: then wt == 0x10000 (bit 16 is never set
-// otherwise, the upper half being a multiple of 64) and the caller takes the pixel-by-pixel path.  Written so that
-// most of the work is multiply-adds: the shift / logic pipe is the busy one in this kernel.
+// packed 16-bit weight pairs of one pixel, summing to 65536: wt = w00 | w10 << 16, wb = w01 | w11 << 16 — the cv grid's
+// (32 - fx | fx)(32 - fy | fy) scaled by 64, the fine grid's (256 - fx | fx)(256 - fy | fy).  w00 = 65536 when
+// fx == fy == 0: then wt == 0x10000 exactly, and the caller takes the pixel-by-pixel path (on the cv grid bit 16 is never
+// set otherwise, the upper half being a multiple of 64; on the fine grid it can be, so the test is an equality there).
+// Written so that most of the work is multiply-adds: the shift / logic pipe is the busy one in this kernel.
+template <int MODE>
 __device__ __forceinline__ void wg_weights(int sfx, int sfy, uint32_t& wt, uint32_t& wb)
 {
-    const uint32_t gx = (uint32_t)sfx & 0x3e0u;                        // 32 fx
-    const uint32_t hp2 = gx * 131070u + 2048u;                         // 64 (32 - fx) | 64 fx << 16
-    const uint32_t hp64 = gx * (131070u * 32u) + 65536u;               // 32 hp2 as a multiply-add of its own: wt = 32 hp2 - fy hp2
-    uint32_t t, fy;                                                    // then is one subtraction, not (32 - fy) on the logic pipe + a multiply
-    asm("shl.b32 %0, %1, 22;" : "=r"(t) : "r"(sfy));                  // two shifts, not shift + mask: the left one can be a multiply
-    asm("shr.u32 %0, %1, 27;" : "=r"(fy) : "r"(t));
-    wb = fy * hp2;
-    wt = hp64 - wb;
+    if (MODE == VS_WARP_CV_EXACT_BILINEAR) {
+        const uint32_t gx = (uint32_t)sfx & 0x3e0u;                        // 32 fx
+        const uint32_t hp2 = gx * 131070u + 2048u;                         // 64 (32 - fx) | 64 fx << 16
+        const uint32_t hp64 = gx * (131070u * 32u) + 65536u;               // 32 hp2 as a multiply-add of its own: wt = 32 hp2 - fy hp2
+        uint32_t t, fy;                                                    // then is one subtraction, not (32 - fy) on the logic pipe + a multiply
+        asm("shl.b32 %0, %1, 22;" : "=r"(t) : "r"(sfy));                  // two shifts, not shift + mask: the left one can be a multiply
+        asm("shr.u32 %0, %1, 27;" : "=r"(fy) : "r"(t));
+        wb = fy * hp2;
+        wt = hp64 - wb;
+    } else {
+        // 8-bit fractions: (256 - fx | fx << 16) times (256 - fy | fy); the products are 16-bit values except
+        // (256 - 0)(256 - 0) = 65536, which makes wt == 0x10000 exactly (and only then)
+        uint32_t t, fx, fy;
+        asm("shl.b32 %0, %1, 16;" : "=r"(t) : "r"(sfx));
+        asm("shr.u32 %0, %1, 24;" : "=r"(fx) : "r"(t));
+        asm("shl.b32 %0, %1, 16;" : "=r"(t) : "r"(sfy));
+        asm("shr.u32 %0, %1, 24;" : "=r"(fy) : "r"(t));
+        const uint32_t hp = fx * 65535u + 256u;                            // 256 - fx | fx << 16
+        const uint32_t hp256 = fx * (65535u * 256u) + 65536u;              // 256 hp
+        wb = fy * hp;
+        wt = hp256 - wb;
+    }
 }
 
 __device__ __forceinline__ void wg_blend(uint32_t wt, uint32_t wb, uint32_t tx, uint32_t ty, uint32_t bx, uint32_t by,
@@ -1034,12 +958,14 @@ __device__ __forceinline__ uint32_t wg_pack(uint32_t a, uint32_t b, uint32_t c, 
     return __byte_perm(__byte_perm(a, b, 0x0062), __byte_perm(c, d, 0x0062), 0x5410);
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(WG_THREADS, 8)
 k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map,
                    const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
                    const int32_t* __restrict__ slots, const int32_t* __restrict__ tab, int dwp, int dhp, int per,
                    uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh, int dst_tma, int dst_al16)
 {
+    constexpr int P = WarpGrid<MODE>::P;
     extern __shared__ __align__(128) uint32_t wg_smem[];
     uint32_t* const RAW = wg_smem;                                 // [WG_BOX_ROWS][WG_BOX_WORDS]
     uint32_t* const O = wg_smem + WG_OUT_OFF / 4;                  // [WG_H][WG_OUT_ROW_WORDS]
@@ -1073,7 +999,7 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
                 : "memory");
         }
     }
-    const int orgx = staged ? tile.z << 10 : 0, orgy = staged ? tile.y << 10 : 0;
+    const int orgx = staged ? tile.z << P : 0, orgy = staged ? tile.y << P : 0;
     if (tid < WG_H) {
         const int2 xy = __ldg(XY + min(tid, th - 1));
         sXY0[tid] = make_int2(xy.x - orgx, xy.y - orgy);
@@ -1085,7 +1011,7 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
     uint8_t* const Ob = reinterpret_cast<uint8_t*>(O);
     if (staged) {
         // column terms with the pixel's offset inside the group taken out: a regular group has one integer part
-        const int a0 = ad4.x, a1 = ad4.y - 1024, a2 = ad4.z - 2048, a3 = ad4.w - 3072;
+        const int a0 = ad4.x, a1 = ad4.y - (1 << P), a2 = ad4.z - (2 << P), a3 = ad4.w - (3 << P);
         const bool whole = 4 * lane + 3 < tw;
         uint32_t done = 0, spins = 0;
         while (!done) {
@@ -1108,8 +1034,8 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
                 const int x0 = xy0.x + a0, x1 = xy0.x + a1, x2 = xy0.x + a2, x3 = xy0.x + a3;
                 const int y0 = xy0.y + bd4.x, y1 = xy0.y + bd4.y, y2 = xy0.y + bd4.z, y3 = xy0.y + bd4.w;
                 uint32_t wt0, wb0, wt1, wb1, wt2, wb2, wt3, wb3;
-                wg_weights(x0, y0, wt0, wb0); wg_weights(x1, y1, wt1, wb1);
-                wg_weights(x2, y2, wt2, wb2); wg_weights(x3, y3, wt3, wb3);
+                wg_weights<MODE>(x0, y0, wt0, wb0); wg_weights<MODE>(x1, y1, wt1, wb1);
+                wg_weights<MODE>(x2, y2, wt2, wb2); wg_weights<MODE>(x3, y3, wt3, wb3);
                 // one source row pair (the row term is monotone in x: the ends decide), consecutive source columns,
                 // no pixel at fx == fy == 0
                 const uint32_t spread = (uint32_t)((x1 ^ x0) | (x2 ^ x0) | (x3 ^ x0) | (y3 ^ y0));
@@ -1122,9 +1048,13 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
                     if (wt2 == 0x10000u) wt2 = 0xffffu;
                     if (wt3 == 0x10000u) wt3 = 0xffffu;
                 }
-                const uint32_t ovf = FIX ? 0u : (wt0 | wt1 | wt2 | wt3) & 0x10000u;
-                const bool regular = whole && spread < 1024u && ovf == 0u;
-                const uint32_t byte = (uint32_t)(y0 >> 10) * (uint32_t)WG_RAW_PITCH + (uint32_t)(x0 >> 10) * 3u;
+                uint32_t ovf = 0u;
+                if (!FIX) {
+                    if (MODE == VS_WARP_CV_EXACT_BILINEAR) ovf = (wt0 | wt1 | wt2 | wt3) & 0x10000u;
+                    else ovf = (wt0 == 0x10000u) | (wt1 == 0x10000u) | (wt2 == 0x10000u) | (wt3 == 0x10000u);
+                }
+                const bool regular = whole && spread < (1u << P) && ovf == 0u;
+                const uint32_t byte = (uint32_t)(y0 >> P) * (uint32_t)WG_RAW_PITCH + (uint32_t)(x0 >> P) * 3u;
                 const bool reuse = __all_sync(0xffffffffu, !regular || byte == pbyte);
                 if (regular) {
                     const uint32_t* const p = RAW + (byte >> 2);
@@ -1178,11 +1108,11 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
             if (x >= tw) continue;
             const int2 xy0 = sXY0[r];
             const int sfx = xy0.x + __ldg(AD + x), sfy = xy0.y + __ldg(BD + x);
-            const uint8_t* const q = Rb + (sfy >> 10) * WG_RAW_PITCH + (sfx >> 10) * 3;
+            const uint8_t* const q = Rb + (sfy >> P) * WG_RAW_PITCH + (sfx >> P) * 3;
             const uint32_t t00 = q[0] | (q[1] << 8) | (q[2] << 16), t10 = q[3] | (q[4] << 8) | (q[5] << 16);
             const uint32_t t01 = q[WG_RAW_PITCH] | (q[WG_RAW_PITCH + 1] << 8) | (q[WG_RAW_PITCH + 2] << 16),
                            t11 = q[WG_RAW_PITCH + 3] | (q[WG_RAW_PITCH + 4] << 8) | (q[WG_RAW_PITCH + 5] << 16);
-            const uint32_t px = cv_blend(wt_entry(t00, t10), wt_entry(t01, t11), (sfx >> 5) & 31, (sfy >> 5) & 31);
+            const uint32_t px = warp_blend_taps<MODE>(t00, t10, t01, t11, sfx, sfy);
             uint8_t* const o = Ob + r * (WG_OUT_ROW_WORDS * 4) + 3 * x;
             o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
         }
@@ -1193,12 +1123,12 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
             const int r = i / tw, x = i - r * tw;
             const int2 xy0 = sXY0[r];
             const int sfx = xy0.x + __ldg(AD + x), sfy = xy0.y + __ldg(BD + x);
-            const int sx = sfx >> 10, sy = sfy >> 10;
+            const int sx = sfx >> P, sy = sfy >> P;
             const uint32_t t00 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx, sy);
             const uint32_t t10 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx + 1, sy);
             const uint32_t t01 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx, sy + 1);
             const uint32_t t11 = bgr_texel_word<VS_BORDER_CONSTANT0>(src, src_stride, w, h, sx + 1, sy + 1);
-            const uint32_t px = cv_blend(wt_entry(t00, t10), wt_entry(t01, t11), (sfx >> 5) & 31, (sfy >> 5) & 31);
+            const uint32_t px = warp_blend_taps<MODE>(t00, t10, t01, t11, sfx, sfy);
             uint8_t* const o = Ob + r * (WG_OUT_ROW_WORDS * 4) + 3 * x;
             o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
         }
@@ -1361,34 +1291,27 @@ void vs_forward_matrix_from_transform(const double* T, int cols, int rows, doubl
     M[3] = T[1]; M[4] = 1.0 + T[0]; M[5] = ty_ul;
 }
 
-template <int MODE>
-static void launch_bgr_warp(int border, dim3 grid, dim3 block, cudaStream_t s,
-                            const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
-                            const VsDevImg& dst, int dst_x0, int dst_y0)
+template <int MODE, int BORDER>
+static int launch_bgr_warp_tiled(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
+                                 const VsDevImg& dst, int dst_x0, int dst_y0)
 {
-    // rows start on word boundaries: regular groups read them as aligned words / write their 12 bytes as 3 words
-    const int src_al4 = ((uintptr_t)src.data % 4 == 0) && src.stride % 4 == 0 && src.batch_stride % 4 == 0;
-    const int dst_al4 = ((uintptr_t)dst.data % 4 == 0) && dst.stride % 4 == 0 && dst.batch_stride % 4 == 0;
-    if constexpr (MODE == VS_WARP_LANCZOS2) {
-        const dim3 pblock(256), pgrid(vs_cdiv(dst.w, 256), dst.h, dst.batch);
-        if (border == VS_BORDER_REPEAT_EDGE)
-            k_bgr_warp_px<MODE, VS_BORDER_REPEAT_EDGE><<<pgrid, pblock, 0, s>>>(
-                (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
-                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4);
-        else
-            k_bgr_warp_px<MODE, VS_BORDER_CONSTANT0><<<pgrid, pblock, 0, s>>>(
-                (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
-                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4);
-    } else {
-        if (border == VS_BORDER_REPEAT_EDGE)
-            k_bgr_warp<MODE, VS_BORDER_REPEAT_EDGE><<<grid, block, 0, s>>>(
-                (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
-                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al4);
-        else
-            k_bgr_warp<MODE, VS_BORDER_CONSTANT0><<<grid, block, 0, s>>>(
-                (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
-                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al4);
-    }
+    // per device, so set on every launch (multi-GPU processes drive several devices)
+    VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tiled<MODE, BORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
+    const int src_al4 = aligned_to(src.data, 4) && src.stride % 4 == 0 && src.batch_stride % 4 == 0;
+    const int dst_al8 = aligned_to(dst.data, 8) && dst.stride % 8 == 0 && dst.batch_stride % 8 == 0;
+    dim3 tgrid(vs_cdiv(dst.w, WT_W), vs_cdiv(dst.h, WT_H), dst.batch);
+    VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
+    k_bgr_warp_cv_tiled<MODE, BORDER><<<tgrid, WT_THREADS, WT_SMEM_BYTES, ctx->stream>>>(
+        (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
+        (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al8);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
+// the fine grid keeps 16 fractional bits in an int32: positions must stay below 2^14 pixels
+static bool warp_fits_fine_grid(const VsDevImg& src, const VsDevImg& dst, int dst_x0, int dst_y0)
+{
+    return src.w <= 16384 && src.h <= 16384 && dst.w + dst_x0 <= 16384 && dst.h + dst_y0 <= 16384 && dst_x0 >= 0 && dst_y0 >= 0;
 }
 
 int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
@@ -1398,34 +1321,30 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
     VS_REQUIRE(ctx, mode >= 0 && mode <= 2 && (border == 0 || border == 1), "bgr_warp: bad mode/border");
     if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
     VS_REQUIRE(ctx, dst.h <= 65535 && dst.batch <= 65535, "bgr_warp: grid too large");
-    if (mode == VS_WARP_CV_EXACT_BILINEAR) {
+    if (mode == VS_WARP_CV_EXACT_BILINEAR || mode == VS_WARP_FLOAT_BILINEAR) {
         VS_REQUIRE(ctx, vs_cdiv(dst.h, WT_H) <= 65535, "bgr_warp: grid too large");
-        // per device, so set on every launch (multi-GPU processes drive several devices)
-        if (border == VS_BORDER_REPEAT_EDGE)
-            VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tiled<VS_BORDER_REPEAT_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
-        else
-            VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_tiled<VS_BORDER_CONSTANT0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
-        const int src_al4 = aligned_to(src.data, 4) && src.stride % 4 == 0 && src.batch_stride % 4 == 0;
-        const int dst_al8 = aligned_to(dst.data, 8) && dst.stride % 8 == 0 && dst.batch_stride % 8 == 0;
-        dim3 tgrid(vs_cdiv(dst.w, WT_W), vs_cdiv(dst.h, WT_H), dst.batch);
-        VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
-        if (border == VS_BORDER_REPEAT_EDGE)
-            k_bgr_warp_cv_tiled<VS_BORDER_REPEAT_EDGE><<<tgrid, WT_THREADS, WT_SMEM_BYTES, ctx->stream>>>(
-                (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
-                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al8);
-        else
-            k_bgr_warp_cv_tiled<VS_BORDER_CONSTANT0><<<tgrid, WT_THREADS, WT_SMEM_BYTES, ctx->stream>>>(
-                (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
-                (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4, dst_al8);
-        VS_LAUNCH_CHECK(ctx);
-        return VS_OK;
+        if (mode == VS_WARP_FLOAT_BILINEAR)
+            VS_REQUIRE(ctx, warp_fits_fine_grid(src, dst, dst_x0, dst_y0), "bgr_warp: the 16.16 grid holds frames up to 16384 pixels");
+        if (mode == VS_WARP_CV_EXACT_BILINEAR)
+            return border == VS_BORDER_REPEAT_EDGE
+                       ? launch_bgr_warp_tiled<VS_WARP_CV_EXACT_BILINEAR, VS_BORDER_REPEAT_EDGE>(ctx, src, d_slots, d_coef, dst, dst_x0, dst_y0)
+                       : launch_bgr_warp_tiled<VS_WARP_CV_EXACT_BILINEAR, VS_BORDER_CONSTANT0>(ctx, src, d_slots, d_coef, dst, dst_x0, dst_y0);
+        return border == VS_BORDER_REPEAT_EDGE
+                   ? launch_bgr_warp_tiled<VS_WARP_FLOAT_BILINEAR, VS_BORDER_REPEAT_EDGE>(ctx, src, d_slots, d_coef, dst, dst_x0, dst_y0)
+                   : launch_bgr_warp_tiled<VS_WARP_FLOAT_BILINEAR, VS_BORDER_CONSTANT0>(ctx, src, d_slots, d_coef, dst, dst_x0, dst_y0);
     }
-    dim3 block(WQ_THREADS), grid(vs_cdiv(dst.w, 4 * WQ_THREADS), vs_cdiv(dst.h, WQ_ROWS), dst.batch);
+    // Lanczos-2: one pixel per thread
+    const int src_al4 = ((uintptr_t)src.data % 4 == 0) && src.stride % 4 == 0 && src.batch_stride % 4 == 0;
+    const dim3 pblock(256), pgrid(vs_cdiv(dst.w, 256), dst.h, dst.batch);
     VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
-    if (mode == VS_WARP_FLOAT_BILINEAR)
-        launch_bgr_warp<VS_WARP_FLOAT_BILINEAR>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
+    if (border == VS_BORDER_REPEAT_EDGE)
+        k_bgr_warp_px<VS_WARP_LANCZOS2, VS_BORDER_REPEAT_EDGE><<<pgrid, pblock, 0, ctx->stream>>>(
+            (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
+            (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4);
     else
-        launch_bgr_warp<VS_WARP_LANCZOS2>(border, grid, block, ctx->stream, src, d_slots, d_coef, dst, dst_x0, dst_y0);
+        k_bgr_warp_px<VS_WARP_LANCZOS2, VS_BORDER_CONSTANT0><<<pgrid, pblock, 0, ctx->stream>>>(
+            (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
+            (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4);
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
@@ -1447,9 +1366,24 @@ void* vs_tensor_map_encoder()
 }
 
 // clip-resident sources, row-group kernel: table kernel + warp kernel on the same stream
-int vsk_bgr_warp_slots_rows(vs_ctx* ctx, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,
-                            const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0, int32_t* d_tab)
+template <int MODE>
+static void launch_warp_rows(cudaStream_t s, dim3 tab_grid, dim3 tgrid, const CUtensorMap& src_map, const CUtensorMap& dst_map,
+                             const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef, const VsDevImg& dst,
+                             int dst_x0, int dst_y0, int32_t* d_tab, int dwp, int dhp, int per, int dst_tma, int dst_al16)
 {
+    cudaFuncSetAttribute(k_bgr_warp_cv_rows<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    k_warp_tables<MODE><<<tab_grid, 256, 0, s>>>(d_coef, dst.w, dst.h, dwp, dhp, per, dst_x0, dst_y0, d_tab);
+    k_bgr_warp_cv_rows<MODE><<<tgrid, WG_THREADS, WG_SMEM_BYTES, s>>>(
+        src_map, dst_map, (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_tab, dwp, dhp, per,
+        (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_tma, dst_al16);
+}
+
+int vsk_bgr_warp_slots_rows(vs_ctx* ctx, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,
+                            const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0, int32_t* d_tab, int mode)
+{
+    VS_REQUIRE(ctx, mode == VS_WARP_CV_EXACT_BILINEAR || mode == VS_WARP_FLOAT_BILINEAR, "bgr_warp_rows: bilinear modes only");
+    if (mode == VS_WARP_FLOAT_BILINEAR)
+        VS_REQUIRE(ctx, warp_fits_fine_grid(src, dst, dst_x0, dst_y0), "bgr_warp: the 16.16 grid holds frames up to 16384 pixels");
     VS_REQUIRE(ctx, tensor_map && d_tab && src.w > 0 && src.h > 0, "bgr_warp_rows: bad source");
     if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
     VS_REQUIRE(ctx, vs_cdiv(dst.h, WG_H) <= 65535 && dst.batch <= 65535, "bgr_warp_rows: grid too large");
@@ -1470,16 +1404,16 @@ int vsk_bgr_warp_slots_rows(vs_ctx* ctx, const void* tensor_map, const VsDevImg&
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         dst_tma = (r == CUDA_SUCCESS);
     }
-    VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_cv_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
     VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
-    k_warp_tables<<<dim3(vs_cdiv(dwp + dhp + ntiles, 256), dst.batch), 256, 0, ctx->stream>>>(
-        d_coef, dst.w, dst.h, dwp, dhp, per, dst_x0, dst_y0, d_tab);
-    ctx->launches++;
-    dim3 tgrid(dwp / WG_W, dhp / WG_H, dst.batch);
-    k_bgr_warp_cv_rows<<<tgrid, WG_THREADS, WG_SMEM_BYTES, ctx->stream>>>(
-        *reinterpret_cast<const CUtensorMap*>(tensor_map), dst_map, (const uint8_t*)src.data, src.stride, src.batch_stride,
-        src.w, src.h, d_slots, d_tab, dwp, dhp, per, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h,
-        dst_tma, dst_al16);
+    const dim3 tab_grid(vs_cdiv(dwp + dhp + ntiles, 256), dst.batch), tgrid(dwp / WG_W, dhp / WG_H, dst.batch);
+    const CUtensorMap& smap = *reinterpret_cast<const CUtensorMap*>(tensor_map);
+    if (mode == VS_WARP_CV_EXACT_BILINEAR)
+        launch_warp_rows<VS_WARP_CV_EXACT_BILINEAR>(ctx->stream, tab_grid, tgrid, smap, dst_map, src, d_slots, d_coef, dst, dst_x0,
+                                                    dst_y0, d_tab, dwp, dhp, per, dst_tma, dst_al16);
+    else
+        launch_warp_rows<VS_WARP_FLOAT_BILINEAR>(ctx->stream, tab_grid, tgrid, smap, dst_map, src, d_slots, d_coef, dst, dst_x0,
+                                                 dst_y0, d_tab, dwp, dhp, per, dst_tma, dst_al16);
+    ctx->launches++;            // the table kernel
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
@@ -1487,7 +1421,8 @@ int vsk_bgr_warp_slots_rows(vs_ctx* ctx, const void* tensor_map, const VsDevImg&
 bool vs_warp_rows_usable(const VsDevImg& src, int mode, int border)
 {
     // whole words per row (elements past 3w/4 words are out of bounds = zero-filled = BORDER_CONSTANT(0)), a box that fits
-    return mode == VS_WARP_CV_EXACT_BILINEAR && border == VS_BORDER_CONSTANT0 && vs_tensor_map_encoder() != nullptr &&
+    return (mode == VS_WARP_CV_EXACT_BILINEAR || mode == VS_WARP_FLOAT_BILINEAR) && border == VS_BORDER_CONSTANT0 &&
+           vs_tensor_map_encoder() != nullptr &&
            aligned_to(src.data, 16) && src.stride % 16 == 0 && (src.batch <= 1 || src.batch_stride % 16 == 0) &&
            src.w % 4 == 0 && src.w * 3 / 4 >= VS_WARP_ROWS_BOX_WORDS && src.h >= VS_WARP_ROWS_BOX_ROWS;
 }
@@ -1506,7 +1441,7 @@ int vsk_bgr_warp(vs_ctx* ctx, const VsDevImg& src, const VsWarpCoef* d_coef, con
             &map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r == CUDA_SUCCESS)
-            return vsk_bgr_warp_slots_rows(ctx, &map, src, nullptr, d_coef, dst, dst_x0, dst_y0, d_tab);
+            return vsk_bgr_warp_slots_rows(ctx, &map, src, nullptr, d_coef, dst, dst_x0, dst_y0, d_tab, mode);
     }
     return vsk_bgr_warp_slots(ctx, src, nullptr, d_coef, dst, dst_x0, dst_y0, mode, border);
 }

@@ -83,7 +83,7 @@ SYMBOLS = {
     "vsh_parttraj_destroy": (None, [_P]),
     "vsh_parttraj_output_count": (_I, [_P]),
     "vsh_parttraj_run": (_I, [_P, _P, _P, _P, _P]),
-    "vsh_partstab_create": (_P, [_I, _I, _I, _I, _I, _I64, _I, _I, _SP, C.c_char_p, _I, _I]),
+    "vsh_partstab_create": (_P, [_I, _I, _I, _I, _I, _I64, _I, _I, _SP, C.c_char_p, _I, _I, _I]),
     "vsh_partstab_destroy": (None, [_P]),
     "vsh_partstab_local_count": (_I, [_P]),
     "vsh_partstab_local_frame": (_I64, [_P, _I]),
@@ -479,11 +479,11 @@ class PartitionedStabilizer(_Handle):
     _destroy = "vsh_partstab_destroy"
 
     def __init__(self, rank, world, width, height, total_frames, sub_frames, block, params: VshStabParams | None = None,
-                 exchange_name: str = "", resident: bool = True, device: int = 0, host_threads: int = 4):
+                 exchange_name: str = "", resident: bool = True, device: int = 0, host_threads: int = 4, lanes: int = 0):
         self.params = params or stab_params_default()
         self.width, self.height = width, height
         self.h = C.c_void_p(load().vsh_partstab_create(device, rank, world, width, height, total_frames, sub_frames, block,
-                                                       C.byref(self.params), exchange_name.encode(), int(resident), host_threads))
+                                                       C.byref(self.params), exchange_name.encode(), int(resident), host_threads, lanes))
         if not self.h:
             _raise("PartitionedStabilizer")
         lib = load()
