@@ -316,8 +316,39 @@ void vo_image_warp(const uint8_t* in, int iw, int ih, const double T[4],
 // in the reference (its bgr_image_warp generator is gone): they are defined here, and in
 // the kernels alike, for the interpolation sweep (BASELINE.json configs[4]).  Mode 1 is the
 // same exact integer bilinear on a finer grid (16 position bits, 1/256-pixel weights); mode
-// 2 keeps the f64 inverse cast to f32 with Lanczos-2 sampling.
+// 2 is a 4 x 4 Lanczos-2 on that grid with tabulated Q14 weights (64 fractions), integer too.
 static inline long rint_he(double v) { return std::lrint(v); } // round-half-even (default FE mode)
+
+// Q14 Lanczos-2 weights of the 64 fractions q/64 for the taps at offsets -1, 0, 1, 2: lanczos2(t - f) with the reference's
+// polynomial (generators.cpp:31-47) in double, normalised; the rounding residue goes to the largest weight so that every
+// row sums to exactly 16384.
+void vo_lanczos_table(int16_t* tab /* [64][4] */)
+{
+    for (int q = 0; q < 64; q++) {
+        const double f = q / 64.0;
+        double wgt[4], sum = 0.0;
+        for (int t = 0; t < 4; t++) {
+            const double x = (double)(t - 1) - f, x2 = x * x;
+            double v = 0.000858519;
+            v = -0.0158853 + v * x2;
+            v = 0.128693 + v * x2;
+            v = -0.583468 + v * x2;
+            v = 1.52229 + v * x2;
+            v = -2.05238 + v * x2;
+            v = 0.999861 + v * x2;
+            wgt[t] = std::fabs(x) >= 2.0 ? 0.0 : v;
+            sum += wgt[t];
+        }
+        int iw[4], isum = 0, big = 0;
+        for (int t = 0; t < 4; t++) {
+            iw[t] = (int)std::lrint(wgt[t] / sum * 16384.0);
+            isum += iw[t];
+            if (iw[t] > iw[big]) big = t;
+        }
+        iw[big] += 16384 - isum;
+        for (int t = 0; t < 4; t++) tab[q * 4 + t] = (int16_t)iw[t];
+    }
+}
 
 // General form: forward 2x3 matrix M (as cv::warpAffine takes it), source sw x sh, destination window dw x dh whose pixel
 // (x, y) is output pixel (x + dx0, y + dy0) of the warp.  vo_warp_bgr below and the synthetic-clip renderer use it.
@@ -380,49 +411,38 @@ void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uin
         return;
     }
 
-    float f00 = (float)i00, f01 = (float)i01, f02 = (float)i02;
-    float f10 = (float)i10, f11 = (float)i11, f12 = (float)i12;
-    for (int yo = 0; yo < oh; yo++) {
-        int y = yo + dy0;
-        for (int xo = 0; xo < ow; xo++) {
-            int x = xo + dx0;
-            float Wx = f00 * (float)x + f01 * (float)y + f02;
-            float Wy = f10 * (float)x + f11 * (float)y + f12;
-            float fWx = std::floor(Wx), fWy = std::floor(Wy);
-            float rx = Wx - fWx, ry = Wy - fWy;
-            int ix = (int)fWx, iy = (int)fWy;
-            uint8_t* d = dst + ((size_t)yo * ow + xo) * 3;
-            auto tap = [&](int xx, int yy, int c) -> float {
-                if (border == 1) { xx = clampi(xx, 0, w - 1); yy = clampi(yy, 0, h - 1); }
-                else if (xx < 0 || xx >= w || yy < 0 || yy >= h) return 0.0f;
-                return (float)src[((size_t)yy * w + xx) * 3 + c];
-            };
-            if (mode == 1) {
+    // Mode 2: Lanczos-2 (4 x 4 taps) on the same 16.16 grid, weights from a table of 64 fractions in Q14 (the reference's
+    // lanczos2 polynomial, generators.cpp:31-47, normalised to sum 16384), exact integer arithmetic: the vertical sums of
+    // the four source columns first (Q14, then >> 7), the horizontal sum of those (Q21), rounded and clamped.
+    {
+        const int P = 16, W = 6;
+        const double SCALE = (double)(1 << P);
+        const int ROUND = 1 << (P - W - 1);
+        int16_t tab[64][4];
+        vo_lanczos_table(&tab[0][0]);
+        for (int yo = 0; yo < oh; yo++) {
+            const int y = yo + dy0;
+            const int X0 = (int)rint_he((i01 * y + i02) * SCALE) + ROUND;
+            const int Y0 = (int)rint_he((i11 * y + i12) * SCALE) + ROUND;
+            for (int xo = 0; xo < ow; xo++) {
+                const int sfx = X0 + (int)rint_he(i00 * (xo + dx0) * SCALE), sfy = Y0 + (int)rint_he(i10 * (xo + dx0) * SCALE);
+                const int ix = sfx >> P, iy = sfy >> P;
+                const int16_t* wx = tab[(sfx >> (P - W)) & 63];
+                const int16_t* wy = tab[(sfy >> (P - W)) & 63];
+                uint8_t* d = dst + ((size_t)yo * ow + xo) * 3;
                 for (int c = 0; c < 3; c++) {
-                    float top = tap(ix, iy, c) * (1.0f - rx) + tap(ix + 1, iy, c) * rx;
-                    float bot = tap(ix, iy + 1, c) * (1.0f - rx) + tap(ix + 1, iy + 1, c) * rx;
-                    float v = top * (1.0f - ry) + bot * ry;
-                    v = std::min(std::max(v + 0.5f, 0.0f), 255.0f);
-                    d[c] = (uint8_t)v;
-                }
-            } else {
-                float wx[5], wy[5];
-                for (int u = 0; u < 5; u++) {
-                    wx[u] = lanczos2((float)(u - 2) - rx);
-                    wy[u] = lanczos2((float)(u - 2) - ry);
-                }
-                float num[3] = {0, 0, 0}, den = 0.0f;
-                for (int ty = 0; ty < 5; ty++)
-                    for (int tx = 0; tx < 5; tx++) {
-                        float w2 = wx[tx] * wy[ty];
-                        for (int c = 0; c < 3; c++)
-                            num[c] = num[c] + w2 * tap(ix + tx - 2, iy + ty - 2, c);
-                        den = den + w2;
+                    int hsum = 1 << 20;
+                    for (int t = 0; t < 4; t++) {
+                        int v = 0;
+                        for (int r = 0; r < 4; r++) {
+                            int xx = ix - 1 + t, yy = iy - 1 + r, p = 0;
+                            if (border == 1) { xx = clampi(xx, 0, w - 1); yy = clampi(yy, 0, h - 1); p = src[((size_t)yy * w + xx) * 3 + c]; }
+                            else if (xx >= 0 && xx < w && yy >= 0 && yy < h) p = src[((size_t)yy * w + xx) * 3 + c];
+                            v += (int)wy[r] * p;
+                        }
+                        hsum += (int)wx[t] * (v >> 7);
                     }
-                for (int c = 0; c < 3; c++) {
-                    float v = num[c] / den;
-                    v = std::min(std::max(v + 0.5f, 0.0f), 255.0f);
-                    d[c] = (uint8_t)v;
+                    d[c] = (uint8_t)clampi(hsum >> 21, 0, 255);
                 }
             }
         }

@@ -64,6 +64,7 @@ void vo_k_image_warp(const uint8_t* in, int iw, int ih, float A, float B, float 
  * dst(M p) = src(p) with M built from the centre-based transform.
  * mode: 0 = OpenCV-exact fixed-point bilinear, 1 = float bilinear, 2 = Lanczos-2
  * border: 0 = constant 0, 1 = repeat edge.  crop: pixels removed on each side. */
+void vo_lanczos_table(int16_t* tab);
 void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uint8_t* dst, int ow, int oh, int dx0, int dy0,
                         int mode, int border);
 void vo_warp_bgr(const uint8_t* src, int w, int h, const double T[4],

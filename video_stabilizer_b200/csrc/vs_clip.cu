@@ -21,7 +21,8 @@ struct vs_clip {
     // TMA descriptor of the BGR store viewed as u32 [slot][row][pitch/4], box {120 words = 160 pixels, 28 rows, 1}: the
     // cv-exact warp fetches a tile's source box with one cp.async.bulk.tensor (first member: 64-byte aligned)
     CUtensorMap bgr_map_rows;
-    bool bgr_map_rows_ok = false;
+    CUtensorMap bgr_map_lz;           // the same view with the taller box of the Lanczos-2 warp
+    bool bgr_map_rows_ok = false, bgr_map_lz_ok = false;
     int32_t* d_warp_tab = nullptr;    // fixed-point column / row tables of the row-group warp, capacity images
     vs_ctx* ctx = nullptr;
     int w = 0, h = 0, capacity = 0, max_pairs = 0, flags = 0;
@@ -129,23 +130,33 @@ PFN_cuTensorMapEncodeTiled tensor_map_encoder()
 
 void build_bgr_tensor_map(vs_clip* c)
 {
-    c->bgr_map_rows_ok = false;
-    PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
-    if (!enc || c->bgr_pitch % 16 != 0 || c->bgr_slot_bytes % 16 != 0) return;
-    if ((int)(c->bgr_pitch / 4) < VS_WARP_ROWS_BOX_WORDS || c->h < VS_WARP_ROWS_BOX_ROWS) return;
+    c->bgr_map_rows_ok = c->bgr_map_lz_ok = false;
+    // per-launch fixed-point tables of the row-group warps
     if (cudaMalloc((void**)&c->d_warp_tab, vs_warp_rows_tab_ints(c->w, c->h) * c->capacity * sizeof(int32_t)) != cudaSuccess) {
         cudaGetLastError();
         c->d_warp_tab = nullptr;
         return;
     }
+    PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc || c->bgr_pitch % 16 != 0 || c->bgr_slot_bytes % 16 != 0) return;
+    if ((int)(c->bgr_pitch / 4) < VS_WARP_ROWS_BOX_WORDS) return;
     const cuuint64_t dims[3] = {(cuuint64_t)(c->bgr_pitch / 4), (cuuint64_t)c->h, (cuuint64_t)c->capacity};
     const cuuint64_t strides[2] = {(cuuint64_t)c->bgr_pitch, (cuuint64_t)c->bgr_slot_bytes};
-    const cuuint32_t box_rows[3] = {(cuuint32_t)VS_WARP_ROWS_BOX_WORDS, (cuuint32_t)VS_WARP_ROWS_BOX_ROWS, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&c->bgr_map_rows, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->d_bgr, dims, strides, box_rows, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    c->bgr_map_rows_ok = (r == CUDA_SUCCESS);
+    if (c->h >= VS_WARP_ROWS_BOX_ROWS) {
+        const cuuint32_t box_rows[3] = {(cuuint32_t)VS_WARP_ROWS_BOX_WORDS, (cuuint32_t)VS_WARP_ROWS_BOX_ROWS, 1};
+        CUresult r = enc(&c->bgr_map_rows, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->d_bgr, dims, strides, box_rows, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        c->bgr_map_rows_ok = (r == CUDA_SUCCESS);
+    }
+    if (c->h >= VS_WARP_LZ_BOX_ROWS) {
+        const cuuint32_t box_lz[3] = {(cuuint32_t)VS_WARP_ROWS_BOX_WORDS, (cuuint32_t)VS_WARP_LZ_BOX_ROWS, 1};
+        CUresult r = enc(&c->bgr_map_lz, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->d_bgr, dims, strides, box_lz, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        c->bgr_map_lz_ok = (r == CUDA_SUCCESS);
+    }
 }
 
 // the BGR warp of a clip: row-group kernel for the mode the stabiliser uses (cv-exact, constant border); the tiled kernel
@@ -156,6 +167,12 @@ int clip_warp_launch(vs_clip* c, const int32_t* d_slots, const VsWarpCoef* d_coe
     if ((mode == VS_WARP_CV_EXACT_BILINEAR || mode == VS_WARP_FLOAT_BILINEAR) && border == VS_BORDER_CONSTANT0 &&
         c->bgr_map_rows_ok && n <= c->capacity && dst.w <= c->w && dst.h <= c->h)
         return vsk_bgr_warp_slots_rows(c->ctx, &c->bgr_map_rows, src, d_slots, d_coef, dst, crop, crop, c->d_warp_tab, mode);
+    if (mode == VS_WARP_LANCZOS2) {
+        if (!c->d_warp_tab || n > c->capacity || dst.w > c->w || dst.h > c->h)
+            return vs_set_error(c->ctx, VS_ERR_NOMEM, "clip_warp: no table scratch for the Lanczos-2 warp");
+        return vsk_bgr_warp_lz(c->ctx, c->bgr_map_lz_ok ? &c->bgr_map_lz : nullptr, src, d_slots, d_coef, dst, crop, crop, border,
+                               c->d_warp_tab);
+    }
     return vsk_bgr_warp_slots(c->ctx, src, d_slots, d_coef, dst, crop, crop, mode, border);
 }
 

@@ -53,11 +53,15 @@ int vsk_bgr_warp_slots_rows(vs_ctx*, const void* tensor_map, const VsDevImg& src
                             const VsWarpCoef* d_coef, const VsDevImg& dst, int dst_x0, int dst_y0, int32_t* d_tab,
                             int mode = VS_WARP_CV_EXACT_BILINEAR);
 constexpr int VS_WARP_ROWS_BOX_WORDS = 120, VS_WARP_ROWS_BOX_ROWS = 28, VS_WARP_ROWS_TILE_W = 128, VS_WARP_ROWS_TILE_H = 24;
+constexpr int VS_WARP_LZ_BOX_ROWS = 32;     // the Lanczos-2 warp reads one row above and two below: a taller box
 static inline size_t vs_warp_rows_tab_ints(int dw, int dh)
 {
     const size_t tx = (dw + VS_WARP_ROWS_TILE_W - 1) / VS_WARP_ROWS_TILE_W, ty = (dh + VS_WARP_ROWS_TILE_H - 1) / VS_WARP_ROWS_TILE_H;
     return 2 * tx * VS_WARP_ROWS_TILE_W + 2 * ty * VS_WARP_ROWS_TILE_H + 4 * tx * ty;
 }
+// Lanczos-2 mode: row-group kernel on a TMA box of VS_WARP_LZ_BOX_ROWS rows (tensor_map) or direct loads (null)
+int vsk_bgr_warp_lz(vs_ctx*, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
+                    const VsDevImg& dst, int dst_x0, int dst_y0, int border, int32_t* d_tab);
 // cuTensorMapEncodeTiled resolved through the runtime (PFN_cuTensorMapEncodeTiled), or null
 void* vs_tensor_map_encoder();
 

@@ -427,146 +427,6 @@ k_image_warp(const uint8_t* __restrict__ in, int64_t in_stride, int64_t in_bs, i
     }
 }
 
-// ------------------------------------------------------------------ BGR warp
-// Float-bilinear and Lanczos-2 modes of the BGR warp (BASELINE.json configs[4] sweep; they have no
-// counterpart in the reference, whose stabilizer uses cv::warpAffine).  The cv-exact mode
-// (imgproc.cpp:446-484) has its own tiled kernels further down.
-// A thread owns 4 consecutive output pixels of WQ_ROWS consecutive rows: the coefficient conversions and the
-// column terms are computed once per thread, the 12 output bytes leave as three words.  For the near-identity
-// transforms of a stabiliser the 4 pixels read consecutive source pixels of the same rows ("regular group"): a row
-// of taps is then 5 (6) aligned word loads + funnel shifts shared by the 4 pixels, and a byte becomes a float by
-// PRMT into the mantissa of 2^23 + one subtraction.  Everything else (image borders, rotations, unaligned
-// sources) goes pixel by pixel through bounds-checked byte loads.  Both paths perform the same f32 operations on
-// the same values in the same order: bit-identical to the oracle.
-template <int MODE, int BORDER>
-__device__ __forceinline__ float bgr_tap_f(const uint8_t* __restrict__ src, int64_t stride, int w, int h,
-                                           int x, int y, int c)
-{
-    if (BORDER == VS_BORDER_REPEAT_EDGE) {
-        x = vs_clampi(x, 0, w - 1); y = vs_clampi(y, 0, h - 1);
-    } else if (x < 0 || x >= w || y < 0 || y >= h) {
-        return 0.0f;
-    }
-    return (float)__ldg(src + (size_t)y * stride + 3 * x + c);
-}
-
-// low byte = floor(t) for 0 <= t < 2^23 (round-toward-zero add into the mantissa of 2^23)
-__device__ __forceinline__ uint32_t wq_byte_bits(float t) { return __float_as_uint(__fadd_rz(t, 8388608.0f)); }
-__device__ __forceinline__ float wq_round_clamp(float v) { return fminf(fmaxf(__fadd_rn(v, 0.5f), 0.0f), 255.0f); }
-// B | G << 8 | R << 16 (byte 3 undefined) from three words whose low bytes hold the channels
-__device__ __forceinline__ uint32_t wq_pack_bgr(uint32_t bb, uint32_t gb, uint32_t rb)
-{
-    return __byte_perm(__byte_perm(bb, gb, 0x0040), rb, 0x4410);
-}
-
-// one pixel, any position: returns B | G << 8 | R << 16
-template <int MODE, int BORDER>
-__device__ __noinline__ uint32_t bgr_warp_pixel(const uint8_t* __restrict__ src, int64_t src_stride, int w, int h,
-                                                int ix, int iy, float rx, float ry)
-{
-    float v[3];
-    if (MODE == VS_WARP_FLOAT_BILINEAR) {
-        const float omx = __fsub_rn(1.0f, rx), omy = __fsub_rn(1.0f, ry);
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            float p00 = bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix, iy, c);
-            float p10 = bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix + 1, iy, c);
-            float p01 = bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix, iy + 1, c);
-            float p11 = bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix + 1, iy + 1, c);
-            float top = __fadd_rn(__fmul_rn(p00, omx), __fmul_rn(p10, rx));
-            float bot = __fadd_rn(__fmul_rn(p01, omx), __fmul_rn(p11, rx));
-            v[c] = __fadd_rn(__fmul_rn(top, omy), __fmul_rn(bot, ry));
-        }
-    } else {
-        float wx[5], wy[5];
-#pragma unroll
-        for (int u = 1; u < 5; u++) {       // column/row 0 weights are exactly 0
-            wx[u] = vs_lanczos2(__fsub_rn((float)(u - 2), rx));
-            wy[u] = vs_lanczos2(__fsub_rn((float)(u - 2), ry));
-        }
-        float num0 = 0.0f, num1 = 0.0f, num2 = 0.0f, den = 0.0f;
-#pragma unroll
-        for (int ty = 1; ty < 5; ty++) {
-#pragma unroll
-            for (int tx = 1; tx < 5; tx++) {
-                float w2 = __fmul_rn(wx[tx], wy[ty]);
-                num0 = __fadd_rn(num0, __fmul_rn(w2, bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix + tx - 2, iy + ty - 2, 0)));
-                num1 = __fadd_rn(num1, __fmul_rn(w2, bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix + tx - 2, iy + ty - 2, 1)));
-                num2 = __fadd_rn(num2, __fmul_rn(w2, bgr_tap_f<MODE, BORDER>(src, src_stride, w, h, ix + tx - 2, iy + ty - 2, 2)));
-                den = __fadd_rn(den, w2);
-            }
-        }
-        v[0] = __fdiv_rn(num0, den); v[1] = __fdiv_rn(num1, den); v[2] = __fdiv_rn(num2, den);
-    }
-    return wq_pack_bgr(wq_byte_bits(wq_round_clamp(v[0])), wq_byte_bits(wq_round_clamp(v[1])), wq_byte_bits(wq_round_clamp(v[2])));
-}
-
-// One pixel per thread with the same aligned-word fast path for interior pixels: the form the Lanczos-2 mode uses (its
-// 4 x 4 taps and ten weight polynomials per pixel leave nothing to share across a group, and a group leaving the fast
-// path costs four bounds-checked 48-tap pixels; measured 5.5 % of HBM peak against 3.0 % for the 4-pixel form).
-template <int MODE, int BORDER>
-__global__ void __launch_bounds__(256)
-k_bgr_warp_px(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
-              const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
-              uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
-              int dst_x0, int dst_y0, int src_al4)
-{
-    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
-    const int yo = blockIdx.y;
-    if (xo >= dw) return;
-    const int b = blockIdx.z;
-    const int slot = slots ? slots[b] : b;
-    const uint8_t* src = src_base + (size_t)slot * src_bs;
-    uint8_t* d = dst_base + (size_t)b * dst_bs + (size_t)yo * dst_stride + 3 * xo;
-    const VsWarpCoef cf = coefs[b];
-    const float xf = (float)(xo + dst_x0), yf = (float)(yo + dst_y0);
-    const float f00 = (float)cf.i00, f01 = (float)cf.i01, f02 = (float)cf.i02;
-    const float f10 = (float)cf.i10, f11 = (float)cf.i11, f12 = (float)cf.i12;
-    const float Wx = __fadd_rn(__fadd_rn(__fmul_rn(f00, xf), __fmul_rn(f01, yf)), f02);
-    const float Wy = __fadd_rn(__fadd_rn(__fmul_rn(f10, xf), __fmul_rn(f11, yf)), f12);
-    const float fWx = floorf(Wx), fWy = floorf(Wy);
-    const float rx = __fsub_rn(Wx, fWx), ry = __fsub_rn(Wy, fWy);
-    const int ix = (int)fWx, iy = (int)fWy;
-    static_assert(MODE == VS_WARP_LANCZOS2, "the bilinear mode runs k_bgr_warp");
-    const int off = 3 * (ix - 1);
-    uint32_t px;
-    if (src_al4 && ix - 1 >= 0 && iy - 1 >= 0 && iy + 3 <= h && (off & ~3) + 16 <= 3 * w) {
-        const uint32_t sh = (uint32_t)(off & 3) * 8u;
-        uint32_t u[4][3];
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const uint32_t* rowp = reinterpret_cast<const uint32_t*>(src + (size_t)(iy - 1 + t) * src_stride + (off & ~3));
-            const uint32_t w0 = __ldg(rowp), w1 = __ldg(rowp + 1), w2 = __ldg(rowp + 2), w3 = __ldg(rowp + 3);
-            u[t][0] = __funnelshift_r(w0, w1, sh); u[t][1] = __funnelshift_r(w1, w2, sh); u[t][2] = __funnelshift_r(w2, w3, sh);
-        }
-#define VS_TAPF(t, i) __fsub_rn(__uint_as_float(__byte_perm(u[t][(i) >> 2], 0x4B000000u, 0x7540u + ((i) & 3))), 8388608.0f)
-        float wx[5], wy[5];
-#pragma unroll
-        for (int q = 1; q < 5; q++) {
-            wx[q] = vs_lanczos2(__fsub_rn((float)(q - 2), rx));
-            wy[q] = vs_lanczos2(__fsub_rn((float)(q - 2), ry));
-        }
-        float num0 = 0.0f, num1 = 0.0f, num2 = 0.0f, den = 0.0f;
-#pragma unroll
-        for (int ty = 1; ty < 5; ty++) {
-#pragma unroll
-            for (int tx = 1; tx < 5; tx++) {
-                const float w2 = __fmul_rn(wx[tx], wy[ty]);
-                num0 = __fadd_rn(num0, __fmul_rn(w2, VS_TAPF(ty - 1, 3 * (tx - 1))));
-                num1 = __fadd_rn(num1, __fmul_rn(w2, VS_TAPF(ty - 1, 3 * (tx - 1) + 1)));
-                num2 = __fadd_rn(num2, __fmul_rn(w2, VS_TAPF(ty - 1, 3 * (tx - 1) + 2)));
-                den = __fadd_rn(den, w2);
-            }
-        }
-#undef VS_TAPF
-        px = wq_pack_bgr(wq_byte_bits(wq_round_clamp(__fdiv_rn(num0, den))), wq_byte_bits(wq_round_clamp(__fdiv_rn(num1, den))),
-                         wq_byte_bits(wq_round_clamp(__fdiv_rn(num2, den))));
-    } else {
-        px = bgr_warp_pixel<MODE, BORDER>(src, src_stride, w, h, ix, iy, rx, ry);
-    }
-    d[0] = (uint8_t)px; d[1] = (uint8_t)(px >> 8); d[2] = (uint8_t)(px >> 16);
-}
-
 // ------------------------------------------------------------------ the two bilinear modes: one arithmetic, two grids
 // Both bilinear modes are exact integer arithmetic on a fixed-point grid:
 //   position of output pixel (x, y):  sfx = rint(i00 x 2^P) + rint((i01 y + i02) 2^P) + 2^(P-W-1)   (likewise sfy),
@@ -580,6 +440,8 @@ k_bgr_warp_px(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t 
 template <int MODE> struct WarpGrid;
 template <> struct WarpGrid<VS_WARP_CV_EXACT_BILINEAR> { static constexpr int P = 10, W = 5; };
 template <> struct WarpGrid<VS_WARP_FLOAT_BILINEAR> { static constexpr int P = 16, W = 8; };
+// Lanczos-2 (below): the fine grid with 64 tabulated weight fractions
+template <> struct WarpGrid<VS_WARP_LANCZOS2> { static constexpr int P = 16, W = 6; };
 
 // one output pixel from four BGRX taps, any fractions: returns B | G << 8 | R << 16
 template <int MODE>
@@ -882,6 +744,9 @@ k_warp_tables(const VsWarpCoef* __restrict__ coefs, int dw, int dh, int dwp, int
     constexpr int P = WarpGrid<MODE>::P, W = WarpGrid<MODE>::W;
     constexpr double SCALE = (double)(1 << P);
     constexpr int ROUND = 1 << (P - W - 1);
+    // taps reach LO pixels before and HI pixels after the integer position (2 x 2 bilinear, 4 x 4 Lanczos-2)
+    constexpr int LO = MODE == VS_WARP_LANCZOS2 ? 1 : 0, HI = MODE == VS_WARP_LANCZOS2 ? 2 : 1;
+    constexpr int BOX_ROWS = MODE == VS_WARP_LANCZOS2 ? VS_WARP_LZ_BOX_ROWS : WG_BOX_ROWS;
     const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
     const VsWarpCoef cf = coefs[b];
     int32_t* const t = tab + (size_t)b * per;
@@ -903,13 +768,14 @@ k_warp_tables(const VsWarpCoef* __restrict__ coefs, int dw, int dh, int dwp, int
         const int XT = rowx(yt), XB = rowx(yb), YT = rowy(yt), YB = rowy(yb);
         const int sxmin = (min(XT, XB) + min(aL, aR)) >> P, sxmax = (max(XT, XB) + max(aL, aR)) >> P;
         const int symin = (min(YT, YB) + min(bL, bR)) >> P, symax = (max(YT, YB) + max(bL, bR)) >> P;
-        const int bx0 = (sxmin >> 4) * 16;                        // a TMA box starts 16-byte aligned: 16 pixels = 48 bytes
-        // pixels bx0 .. sxmax + 1 and rows symin .. symax + 1 must be inside the box
-        const bool fits = sxmax + 1 - bx0 < WG_BOX_PIXELS && symax + 1 - symin < WG_BOX_ROWS &&
+        const int bx0 = ((sxmin - LO) >> 4) * 16;                 // a TMA box starts 16-byte aligned: 16 pixels = 48 bytes
+        const int by0 = symin - LO;
+        // pixels bx0 .. sxmax + HI and rows by0 .. symax + HI must be inside the box
+        const bool fits = sxmax + HI - bx0 < WG_BOX_PIXELS && symax + HI - by0 < BOX_ROWS &&
                           sxmin > -(1 << 14) && sxmax < (1 << 14) && symin > -(1 << 14) && symax < (1 << 14);
         // bit 1: fx == fy == 0 at all four corners of the tile (then, for a near-identity transform, almost everywhere in it)
         const int fr = ((XT + aL) | (XT + aR) | (XB + aL) | (XB + aR) | (YT + bL) | (YT + bR) | (YB + bL) | (YB + bR)) & (((1 << W) - 1) << (P - W));
-        reinterpret_cast<int4*>(t + 2 * dwp + 2 * dhp)[q] = make_int4((bx0 >> 4) * 12, symin, bx0, (fits ? 1 : 0) | (fr == 0 ? 2 : 0));
+        reinterpret_cast<int4*>(t + 2 * dwp + 2 * dhp)[q] = make_int4((bx0 >> 4) * 12, by0, bx0, (fits ? 1 : 0) | (fr == 0 ? 2 : 0));
     }
 }
 
@@ -1166,6 +1032,266 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
     }
 }
 
+// ------------------------------------------------------------------ BGR warp, Lanczos-2, row groups on the raw box
+// 4 x 4 Lanczos-2 on the 16.16 grid, exact integer arithmetic (the mode has no counterpart upstream; the oracle defines it
+// the same way): weights of the 64 fractions q/64 in Q14 from a table; per pixel and channel the vertical sums of the four
+// source columns (Q14, >> 7), then their horizontal sum (Q21), rounded, clamped.  Same skeleton as k_bgr_warp_cv_rows:
+// 128 x 24 output tile, raw source box by one TMA load (160 pixels x 32 rows), a thread owns four consecutive pixels of a
+// row, a warp walks down six rows, the tile leaves by one TMA store.  A "regular" group — consecutive source columns, one
+// source row quadruple, one vertical fraction, which is what the near-identity transforms of a stabiliser give almost
+// everywhere — shares its vertical sums: the 7 source pixels x 3 channels it touches are 21 sums for 4 output pixels
+// instead of 48.  A row of the window is 7 aligned shared-memory words + 6 funnel shifts; two rows are interleaved by
+// PRMT into (row r, row r+1) byte pairs and a sum is two IDP.2A (signed 16-bit weights x unsigned bytes).  Everything
+// else (groups that are not regular, tiles whose box does not fit) goes pixel by pixel through lz_pixel.
+constexpr int LZ_BOX_ROWS = VS_WARP_LZ_BOX_ROWS;
+constexpr int LZ_RAW_BYTES = WG_RAW_PITCH * LZ_BOX_ROWS;             // 15360: the TMA transaction size
+constexpr int LZ_OUT_OFF = (LZ_RAW_BYTES + 64 + 127) / 128 * 128;
+constexpr int LZ_LIST_OFF = LZ_OUT_OFF + WG_OUT_ROW_WORDS * 4 * WG_H;
+constexpr int LZ_TAB_OFF = LZ_LIST_OFF + WG_H * 32 * 2;
+constexpr int LZ_SMEM_BYTES = LZ_TAB_OFF + 64 * 16 + 64 * 8;
+
+struct LzTables {
+    int32_t wx[64][4];       // Q14 weights of taps -1, 0, 1, 2 for fraction q / 64
+    uint32_t wy[64][2];      // the same as signed 16-bit pairs: w0 | w1 << 16, w2 | w3 << 16
+};
+
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// one pixel, any position, through a byte fetcher tap(x, y, c): returns B | G << 8 | R << 16
+template <typename TAP>
+__device__ __forceinline__ uint32_t lz_pixel(const int32_t (*wxt)[4], int sfx, int sfy, TAP tap)
+{
+    const int ix = sfx >> 16, iy = sfy >> 16;
+    const int32_t* wx = wxt[(sfx >> 10) & 63];
+    const int32_t* wy = wxt[(sfy >> 10) & 63];
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        int hsum = 1 << 20;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            int v = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) v += wy[r] * (int)tap(ix - 1 + t, iy - 1 + r, c);
+            hsum += wx[t] * (v >> 7);
+        }
+        out |= (uint32_t)__vimin_s32_relu(hsum >> 21, 255) << (8 * c);
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 6)
+k_bgr_warp_lz_rows(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map,
+                   const __grid_constant__ LzTables tables,
+                   const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
+                   const int32_t* __restrict__ slots, const int32_t* __restrict__ tab, int dwp, int dhp, int per,
+                   uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh, int dst_tma, int dst_al16,
+                   int border_flags)
+{
+    constexpr int P = 16;
+    extern __shared__ __align__(128) uint32_t lz_smem[];
+    uint32_t* const RAW = lz_smem;                                 // [LZ_BOX_ROWS][WG_BOX_WORDS]
+    uint32_t* const O = lz_smem + LZ_OUT_OFF / 4;                  // [WG_H][WG_OUT_ROW_WORDS]
+    uint16_t* const LIST = reinterpret_cast<uint16_t*>(lz_smem + LZ_LIST_OFF / 4);
+    int32_t (*const WX)[4] = reinterpret_cast<int32_t (*)[4]>(lz_smem + LZ_TAB_OFF / 4);
+    uint32_t (*const WY)[2] = reinterpret_cast<uint32_t (*)[2]>(lz_smem + LZ_TAB_OFF / 4 + 64 * 4);
+    __shared__ int2 sXY0[WG_H];                                    // row terms relative to the box origin
+    __shared__ int sCount;
+    __shared__ __align__(8) unsigned long long tma_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int ox0 = blockIdx.x * WG_W, oy0 = blockIdx.y * WG_H;
+    const int tw = min(WG_W, dw - ox0), th = min(WG_H, dh - oy0);
+    const int32_t* const T = tab + (size_t)b * per;
+    const int32_t* const AD = T + ox0;
+    const int32_t* const BD = AD + dwp;
+    const int2* const XY = reinterpret_cast<const int2*>(T + 2 * dwp) + oy0;
+    const int4 tile = __ldg(reinterpret_cast<const int4*>(T + 2 * dwp + 2 * dhp) + blockIdx.y * gridDim.x + blockIdx.x);
+    const bool staged = (tile.w & 1) != 0 && border_flags == VS_BORDER_CONSTANT0;   // bit 1 of border_flags: no source map
+    const int border = border_flags & 1;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+    if (tid == 0) {
+        sCount = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (staged) {
+            const int slot = slots ? __ldg(slots + b) : b;
+            const uint32_t dstsm = (uint32_t)__cvta_generic_to_shared(RAW);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)LZ_RAW_BYTES) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(dstsm), "l"(reinterpret_cast<uint64_t>(&src_map)), "r"(tile.x), "r"(tile.y), "r"(slot), "r"(bar)
+                : "memory");
+        }
+    }
+    for (int i = tid; i < 64 * 4; i += WG_THREADS) WX[i >> 2][i & 3] = tables.wx[i >> 2][i & 3];
+    for (int i = tid; i < 64 * 2; i += WG_THREADS) WY[i >> 1][i & 1] = tables.wy[i >> 1][i & 1];
+    const int orgx = staged ? tile.z << P : 0, orgy = staged ? tile.y << P : 0;
+    if (tid < WG_H) {
+        const int2 xy = __ldg(XY + min(tid, th - 1));
+        sXY0[tid] = make_int2(xy.x - orgx, xy.y - orgy);
+    }
+    const int4 ad4 = __ldg(reinterpret_cast<const int4*>(AD) + lane);
+    const int4 bd4 = __ldg(reinterpret_cast<const int4*>(BD) + lane);
+    __syncthreads();
+
+    uint8_t* const Ob = reinterpret_cast<uint8_t*>(O);
+    if (staged) {
+        const int a0 = ad4.x, a1 = ad4.y - (1 << P), a2 = ad4.z - (2 << P), a3 = ad4.w - (3 << P);
+        const bool whole = 4 * lane + 3 < tw;
+        uint32_t done = 0, spins = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar) : "memory");
+            if (!done && ++spins > (1u << 24)) __trap();   // a lost transaction must fail loudly, not hang the GPU
+        }
+#pragma unroll 1
+        for (int k = 0; k < WG_ROWS_PER_WARP; k++) {
+            const int r = warp * WG_ROWS_PER_WARP + k;
+            if (r >= th) break;
+            const int2 xy0 = sXY0[r];
+            const int x0 = xy0.x + a0, x1 = xy0.x + a1, x2 = xy0.x + a2, x3 = xy0.x + a3;
+            const int y0 = xy0.y + bd4.x, y1 = xy0.y + bd4.y, y2 = xy0.y + bd4.z, y3 = xy0.y + bd4.w;
+            // consecutive source columns and one source row quadruple for the four pixels; when they also share one vertical
+            // fraction (pure translations, and wherever the rotation moves y by less than 1/64 px over the group) the
+            // vertical sums are shared by the group, else every pixel forms its own from the same interleaved rows.  Which
+            // of the two forms runs is decided per warp, so no lane waits for code it does not need.
+            const uint32_t spread = (uint32_t)((x1 ^ x0) | (x2 ^ x0) | (x3 ^ x0) | (y1 ^ y0) | (y2 ^ y0) | (y3 ^ y0)) >> P;
+            const uint32_t yfrac = (uint32_t)((y1 ^ y0) | (y2 ^ y0) | (y3 ^ y0)) >> 10;
+            const bool regular = whole && spread == 0u;
+            const bool shared_wy = __all_sync(0xffffffffu, !regular || yfrac == 0u);
+            if (regular) {
+                const uint32_t byte = (uint32_t)((y0 >> P) - 1) * (uint32_t)WG_RAW_PITCH + (uint32_t)((x0 >> P) - 1) * 3u;
+                const uint32_t* const p = RAW + (byte >> 2);
+                const uint32_t sh = byte << 3;                        // funnel shifts use the low five bits: 8 (byte & 3)
+                // the 21 source bytes (7 pixels x BGR) of the four rows, interleaved as (row 0, row 1) and (row 2, row 3) byte pairs
+                uint32_t a01[6], b01[6], a23[6], b23[6];
+#pragma unroll
+                for (int q = 0; q < 6; q++) {
+                    uint32_t u[4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; rr++)
+                        u[rr] = __funnelshift_r(p[rr * WG_BOX_WORDS + q], p[rr * WG_BOX_WORDS + q + 1], sh);
+                    a01[q] = __byte_perm(u[0], u[1], 0x5140); b01[q] = __byte_perm(u[0], u[1], 0x7362);
+                    a23[q] = __byte_perm(u[2], u[3], 0x5140); b23[q] = __byte_perm(u[2], u[3], 0x7362);
+                }
+                // vertical sum of stream byte i (Q14 >> 7) under the weight pairs wy
+                auto vsum = [&](int i, const uint2 wy) -> int {
+                    const int q = i >> 2;
+                    switch (i & 3) {
+                    case 0: return dp2a_lo_su(wy.y, a23[q], dp2a_lo_su(wy.x, a01[q], 0)) >> 7;
+                    case 1: return dp2a_hi_su(wy.y, a23[q], dp2a_hi_su(wy.x, a01[q], 0)) >> 7;
+                    case 2: return dp2a_lo_su(wy.y, b23[q], dp2a_lo_su(wy.x, b01[q], 0)) >> 7;
+                    default: return dp2a_hi_su(wy.y, b23[q], dp2a_hi_su(wy.x, b01[q], 0)) >> 7;
+                    }
+                };
+                const int xs[4] = {x0, x1, x2, x3};
+                const int ys[4] = {y0, y1, y2, y3};
+                uint32_t px[4];
+                if (shared_wy) {
+                    const uint2 wy = *reinterpret_cast<const uint2*>(WY[((uint32_t)y0 >> 10) & 63u]);
+                    int vs[21];
+#pragma unroll
+                    for (int i = 0; i < 21; i++) vs[i] = vsum(i, wy);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int4 wx = *reinterpret_cast<const int4*>(WX[((uint32_t)xs[j] >> 10) & 63u]);
+                        uint32_t o = 0;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const int hsum = wx.x * vs[3 * j + c] + wx.y * vs[3 * j + 3 + c] + wx.z * vs[3 * j + 6 + c] +
+                                             wx.w * vs[3 * j + 9 + c] + (1 << 20);
+                            o |= (uint32_t)__vimin_s32_relu(hsum >> 21, 255) << (8 * c);
+                        }
+                        px[j] = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint2 wy = *reinterpret_cast<const uint2*>(WY[((uint32_t)ys[j] >> 10) & 63u]);
+                        const int4 wx = *reinterpret_cast<const int4*>(WX[((uint32_t)xs[j] >> 10) & 63u]);
+                        uint32_t o = 0;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const int hsum = wx.x * vsum(3 * j + c, wy) + wx.y * vsum(3 * j + 3 + c, wy) + wx.z * vsum(3 * j + 6 + c, wy) +
+                                             wx.w * vsum(3 * j + 9 + c, wy) + (1 << 20);
+                            o |= (uint32_t)__vimin_s32_relu(hsum >> 21, 255) << (8 * c);
+                        }
+                        px[j] = o;
+                    }
+                }
+                uint32_t* const o = O + r * WG_OUT_ROW_WORDS + 3 * lane;
+                o[0] = __byte_perm(px[0], px[1], 0x4210);
+                o[1] = __byte_perm(px[1], px[2], 0x5421);
+                o[2] = __byte_perm(px[2], px[3], 0x6542);
+            } else if (4 * lane < tw) {
+                LIST[atomicAdd(&sCount, 1)] = (uint16_t)(r * 32 + lane);
+            }
+        }
+        __syncthreads();
+        // irregular groups, pixel by pixel from the raw box (every tap of the tile is inside it)
+        const int nfix = sCount * 4;
+        const uint8_t* const Rb = reinterpret_cast<const uint8_t*>(RAW);
+        for (int i = tid; i < nfix; i += WG_THREADS) {
+            const int e = LIST[i >> 2], r = e >> 5, x = 4 * (e & 31) + (i & 3);
+            if (x >= tw) continue;
+            const int2 xy0 = sXY0[r];
+            const int sfx = xy0.x + __ldg(AD + x), sfy = xy0.y + __ldg(BD + x);
+            const uint32_t px = lz_pixel(WX, sfx, sfy, [&](int xx, int yy, int c) { return Rb[yy * WG_RAW_PITCH + xx * 3 + c]; });
+            uint8_t* const o = Ob + r * (WG_OUT_ROW_WORDS * 4) + 3 * x;
+            o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+        }
+    } else {
+        // the box does not fit (large rotation or scale) or the border repeats the edge: every pixel from global memory
+        const uint8_t* const src = src_base + (size_t)(slots ? __ldg(slots + b) : b) * src_bs;
+        for (int i = tid; i < tw * th; i += WG_THREADS) {
+            const int r = i / tw, x = i - r * tw;
+            const int2 xy0 = sXY0[r];
+            const int sfx = xy0.x + __ldg(AD + x), sfy = xy0.y + __ldg(BD + x);
+            const uint32_t px = lz_pixel(WX, sfx, sfy, [&](int xx, int yy, int c) -> uint32_t {
+                if (border == VS_BORDER_REPEAT_EDGE) { xx = vs_clampi(xx, 0, w - 1); yy = vs_clampi(yy, 0, h - 1); }
+                else if (xx < 0 || xx >= w || yy < 0 || yy >= h) return 0u;
+                return __ldg(src + (size_t)yy * src_stride + 3 * xx + c);
+            });
+            uint8_t* const o = Ob + r * (WG_OUT_ROW_WORDS * 4) + 3 * x;
+            o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+        }
+    }
+
+    if (dst_tma) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t srcsm = (uint32_t)__cvta_generic_to_shared(O);
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         ::"l"(reinterpret_cast<uint64_t>(&dst_map)), "r"(blockIdx.x * WG_OUT_ROW_WORDS), "r"(oy0), "r"(b), "r"(srcsm)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        return;
+    }
+    __syncthreads();
+    uint8_t* const drow0 = dst_base + (size_t)b * dst_bs + (size_t)oy0 * dst_stride + (size_t)ox0 * 3;
+    const int row_bytes = tw * 3;
+    for (int i = tid; i < th * row_bytes; i += WG_THREADS) {
+        const int r = i / row_bytes, c = i - r * row_bytes;
+        drow0[(size_t)r * dst_stride + c] = Ob[r * (WG_OUT_ROW_WORDS * 4) + c];
+    }
+}
+
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 }  // namespace
@@ -1333,18 +1459,86 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
                    ? launch_bgr_warp_tiled<VS_WARP_FLOAT_BILINEAR, VS_BORDER_REPEAT_EDGE>(ctx, src, d_slots, d_coef, dst, dst_x0, dst_y0)
                    : launch_bgr_warp_tiled<VS_WARP_FLOAT_BILINEAR, VS_BORDER_CONSTANT0>(ctx, src, d_slots, d_coef, dst, dst_x0, dst_y0);
     }
-    // Lanczos-2: one pixel per thread
-    const int src_al4 = ((uintptr_t)src.data % 4 == 0) && src.stride % 4 == 0 && src.batch_stride % 4 == 0;
-    const dim3 pblock(256), pgrid(vs_cdiv(dst.w, 256), dst.h, dst.batch);
+    return vs_set_error(ctx, VS_ERR_INVALID, "bgr_warp: the Lanczos-2 mode runs through vsk_bgr_warp_lz");
+}
+
+// Q14 Lanczos-2 weights of the 64 fractions q / 64 (taps at -1, 0, 1, 2): the reference's lanczos2 polynomial
+// (generators.cpp:31-47) in double, normalised; the rounding residue goes to the largest weight (rows sum to 16384)
+static const LzTables& lz_tables()
+{
+    static const LzTables t = [] {
+        LzTables r;
+        for (int q = 0; q < 64; q++) {
+            const double f = q / 64.0;
+            double wgt[4], sum = 0.0;
+            for (int k = 0; k < 4; k++) {
+                const double x = (double)(k - 1) - f, x2 = x * x;
+                double v = 0.000858519;
+                v = -0.0158853 + v * x2;
+                v = 0.128693 + v * x2;
+                v = -0.583468 + v * x2;
+                v = 1.52229 + v * x2;
+                v = -2.05238 + v * x2;
+                v = 0.999861 + v * x2;
+                wgt[k] = fabs(x) >= 2.0 ? 0.0 : v;
+                sum += wgt[k];
+            }
+            int iw[4], isum = 0, big = 0;
+            for (int k = 0; k < 4; k++) {
+                iw[k] = (int)lrint(wgt[k] / sum * 16384.0);
+                isum += iw[k];
+                if (iw[k] > iw[big]) big = k;
+            }
+            iw[big] += 16384 - isum;
+            for (int k = 0; k < 4; k++) r.wx[q][k] = iw[k];
+            r.wy[q][0] = (uint32_t)(uint16_t)(int16_t)iw[0] | ((uint32_t)(uint16_t)(int16_t)iw[1] << 16);
+            r.wy[q][1] = (uint32_t)(uint16_t)(int16_t)iw[2] | ((uint32_t)(uint16_t)(int16_t)iw[3] << 16);
+        }
+        return r;
+    }();
+    return t;
+}
+
+// Lanczos-2 BGR warp.  tensor_map: a CUtensorMap over the source viewed as u32 [image][row][word] with box
+// {120, VS_WARP_LZ_BOX_ROWS, 1}, or null (then every tile reads global memory directly: small or unaligned sources).
+// d_tab: vs_warp_rows_tab_ints(dst.w, dst.h) int32 per image.
+int vsk_bgr_warp_lz(vs_ctx* ctx, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
+                    const VsDevImg& dst, int dst_x0, int dst_y0, int border, int32_t* d_tab)
+{
+    VS_REQUIRE(ctx, d_tab && src.w > 0 && src.h > 0, "bgr_warp_lz: bad source / scratch");
+    VS_REQUIRE(ctx, border == VS_BORDER_CONSTANT0 || border == VS_BORDER_REPEAT_EDGE, "bgr_warp_lz: bad border");
+    if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
+    VS_REQUIRE(ctx, vs_cdiv(dst.h, WG_H) <= 65535 && dst.batch <= 65535, "bgr_warp_lz: grid too large");
+    VS_REQUIRE(ctx, warp_fits_fine_grid(src, dst, dst_x0, dst_y0), "bgr_warp: the 16.16 grid holds frames up to 16384 pixels");
+    const int dwp = vs_cdiv(dst.w, WG_W) * WG_W, dhp = vs_cdiv(dst.h, WG_H) * WG_H;
+    const int ntiles = (dwp / WG_W) * (dhp / WG_H);
+    const int per = (int)vs_warp_rows_tab_ints(dst.w, dst.h);
+    const int dst_al16 = aligned_to(dst.data, 16) && dst.stride % 16 == 0 && dst.batch_stride % 16 == 0;
+    CUtensorMap dst_map, src_map;
+    memset(&dst_map, 0, sizeof(dst_map));
+    memset(&src_map, 0, sizeof(src_map));
+    int dst_tma = 0;
+    if (dst_al16 && dst.w % 4 == 0 && vs_tensor_map_encoder()) {
+        const cuuint64_t dims[3] = {(cuuint64_t)(dst.w * 3 / 4), (cuuint64_t)dst.h, (cuuint64_t)dst.batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)dst.stride, (cuuint64_t)(dst.batch > 1 ? dst.batch_stride : dst.stride * dst.h)};
+        const cuuint32_t box[3] = {(cuuint32_t)WG_OUT_ROW_WORDS, (cuuint32_t)WG_H, 1}, estr[3] = {1, 1, 1};
+        CUresult r = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(vs_tensor_map_encoder())(
+            &dst_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, dst.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        dst_tma = (r == CUDA_SUCCESS);
+    }
+    // without a source map every tile takes the direct path: the kernel is told through the border argument's high bit
+    const bool have_map = tensor_map != nullptr;
+    if (have_map) src_map = *reinterpret_cast<const CUtensorMap*>(tensor_map);
+    VS_CUDA(ctx, cudaFuncSetAttribute(k_bgr_warp_lz_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
     VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
-    if (border == VS_BORDER_REPEAT_EDGE)
-        k_bgr_warp_px<VS_WARP_LANCZOS2, VS_BORDER_REPEAT_EDGE><<<pgrid, pblock, 0, ctx->stream>>>(
-            (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
-            (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4);
-    else
-        k_bgr_warp_px<VS_WARP_LANCZOS2, VS_BORDER_CONSTANT0><<<pgrid, pblock, 0, ctx->stream>>>(
-            (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_coef,
-            (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al4);
+    k_warp_tables<VS_WARP_LANCZOS2><<<dim3(vs_cdiv(dwp + dhp + ntiles, 256), dst.batch), 256, 0, ctx->stream>>>(
+        d_coef, dst.w, dst.h, dwp, dhp, per, dst_x0, dst_y0, d_tab);
+    ctx->launches++;
+    dim3 tgrid(dwp / WG_W, dhp / WG_H, dst.batch);
+    k_bgr_warp_lz_rows<<<tgrid, WG_THREADS, LZ_SMEM_BYTES, ctx->stream>>>(
+        src_map, dst_map, lz_tables(), (const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h, d_slots, d_tab, dwp, dhp,
+        per, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_tma, dst_al16, have_map ? border : (border | 2));
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
@@ -1420,6 +1614,10 @@ int vsk_bgr_warp_slots_rows(vs_ctx* ctx, const void* tensor_map, const VsDevImg&
 
 bool vs_warp_rows_usable(const VsDevImg& src, int mode, int border)
 {
+    if (mode == VS_WARP_LANCZOS2)
+        return border == VS_BORDER_CONSTANT0 && vs_tensor_map_encoder() != nullptr && aligned_to(src.data, 16) &&
+               src.stride % 16 == 0 && (src.batch <= 1 || src.batch_stride % 16 == 0) && src.w % 4 == 0 &&
+               src.w * 3 / 4 >= VS_WARP_ROWS_BOX_WORDS && src.h >= VS_WARP_LZ_BOX_ROWS;
     // whole words per row (elements past 3w/4 words are out of bounds = zero-filled = BORDER_CONSTANT(0)), a box that fits
     return (mode == VS_WARP_CV_EXACT_BILINEAR || mode == VS_WARP_FLOAT_BILINEAR) && border == VS_BORDER_CONSTANT0 &&
            vs_tensor_map_encoder() != nullptr &&
@@ -1431,6 +1629,20 @@ int vsk_bgr_warp(vs_ctx* ctx, const VsDevImg& src, const VsWarpCoef* d_coef, con
                  int dst_x0, int dst_y0, int mode, int border, int32_t* d_tab)
 {
     VS_REQUIRE(ctx, src.batch == dst.batch, "bgr_warp: batch mismatch");
+    if (mode == VS_WARP_LANCZOS2) {
+        VS_REQUIRE(ctx, d_tab, "bgr_warp: the Lanczos-2 mode needs the table scratch");
+        if (vs_warp_rows_usable(src, mode, border)) {
+            CUtensorMap map;
+            const cuuint64_t dims[3] = {(cuuint64_t)(src.w * 3 / 4), (cuuint64_t)src.h, (cuuint64_t)src.batch};
+            const cuuint64_t strides[2] = {(cuuint64_t)src.stride, (cuuint64_t)(src.batch > 1 ? src.batch_stride : src.stride * src.h)};
+            const cuuint32_t box[3] = {(cuuint32_t)VS_WARP_ROWS_BOX_WORDS, (cuuint32_t)VS_WARP_LZ_BOX_ROWS, 1}, estr[3] = {1, 1, 1};
+            CUresult r = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(vs_tensor_map_encoder())(
+                &map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) return vsk_bgr_warp_lz(ctx, &map, src, nullptr, d_coef, dst, dst_x0, dst_y0, border, d_tab);
+        }
+        return vsk_bgr_warp_lz(ctx, nullptr, src, nullptr, d_coef, dst, dst_x0, dst_y0, border, d_tab);
+    }
     if (d_tab && vs_warp_rows_usable(src, mode, border)) {
         // any device image as a u32 [image][row][word] tensor
         CUtensorMap map;

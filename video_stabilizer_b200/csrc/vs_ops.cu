@@ -366,7 +366,7 @@ int vs_bgr_warp_u8(vs_ctx* ctx, const vs_img* src, const double* M6, const vs_im
     Stage st(ctx);
     st.want_raw(coef.size() * sizeof(VsWarpCoef));
     // fixed-point tables of the row-group kernel (cv-exact mode, constant border)
-    const size_t tab_bytes = (mode == VS_WARP_CV_EXACT_BILINEAR || mode == VS_WARP_FLOAT_BILINEAR) && border == VS_BORDER_CONSTANT0
+    const size_t tab_bytes = mode == VS_WARP_LANCZOS2 || border == VS_BORDER_CONSTANT0
                                  ? vs_warp_rows_tab_ints(dst->width, dst->height) * sizeof(int32_t) * batch : 0;
     st.want_raw(tab_bytes);
     if (mem == VS_MEM_HOST) { st.want_img(src, 3); st.want_img(dst, 3); }
