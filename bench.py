@@ -643,7 +643,7 @@ def main():
     ap.add_argument("--frames", type=int, default=300, help="frames of the video per GPU")
     ap.add_argument("--frames-4k", type=int, default=120, help="frames per GPU of the 4K extra record")
     ap.add_argument("--crop", type=int, default=0)
-    ap.add_argument("--passes", type=int, default=10, help="videos per step (device-resident number)")
+    ap.add_argument("--passes", type=int, default=15, help="videos per step (device-resident number)")
     ap.add_argument("--e2e-sub", type=int, default=16, help="sub-chunk (frames) of the host-streamed partition")
     ap.add_argument("--cpu-threads", type=int, default=0, help="CPU worker threads (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
