@@ -273,6 +273,9 @@ int vs_clip_get_phase(vs_clip*, int pair, double* out3);
  * {warp-diff, selection, Hessian sums, SVD beside the first iteration + Gauss-Newton gathers, Gauss-Newton reduce + update,
  *  number of parallel partition rounds of the selection (a count, not cycles)} */
 int vs_clip_get_solver_cycles(vs_clip*, int pair, long long* out6);
+/* The same per pyramid level: out[level][8] = {warp-diff, selection, Hessian sums, SVD beside the first iteration,
+ * Gauss-Newton reduce + update, partition rounds (a count), gathers of the later iterations, 0} */
+int vs_clip_get_solver_level_cycles(vs_clip*, int pair, long long* out_levels_x8);
 /* Debug tap for the solver's 4x4 conditioning + SVD pseudo-inverse (alignment.cpp:554-583) as it runs on the device:
  * n row-major 4x4 f64 matrices from host memory -> the inverse computed by the lane-parallel form the solver uses
  * (out_quad) and by the serial restatement (out_serial), plus the condition number; the two must agree bit for bit. */

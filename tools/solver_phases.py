@@ -34,3 +34,13 @@ print("mean cycles per pair %.0f (max %.0f) = %.3f ms at 1.965 GHz" % (tot.mean(
 print("selection: %.1f parallel partition rounds per pair (all levels), %.0f cycles per round" % (rounds.mean(), cyc[:, 1].sum() / max(rounds.sum(), 1)))
 for i, nm in enumerate(names[:5]):
     print("  %-32s %9.0f cycles  %5.1f%%" % (nm, cyc[:, i].mean(), 100 * cyc[:, i].sum() / tot.sum()))
+# per level: {warp-diff, selection, Hessian sums, SVD beside the first iteration, reduce + update, rounds, later gathers, serial steps}
+L = clip.levels if hasattr(clip, "levels") else len(it[0])
+lv = np.zeros((n - 1, L, 8), np.int64)
+for p in range(n - 1):
+    capi.check(ctx.handle, ctx.lib.vs_clip_get_solver_level_cycles(clip.handle, p, capi.ptr(lv[p])), "level cycles")
+m = lv.mean(0)
+print("level  iters  warpdiff   select (rounds, serial steps)   hessian  svd||iter1  later gathers  reduce+update")
+for l in range(L - 1, -1, -1):
+    print("  L%d   %5.2f  %8.0f  %8.0f (%4.1f, %7.0f)        %7.0f    %7.0f       %7.0f        %7.0f"
+          % (l, it[:, l].mean(), m[l, 0], m[l, 1], m[l, 5], m[l, 7], m[l, 2], m[l, 3], m[l, 6], m[l, 4]))

@@ -104,6 +104,7 @@ SYMBOLS = {
     "vs_clip_get_jacobians": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "vs_clip_get_warpdiff": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "vs_clip_get_solver_cycles": (C.c_int, [_P, C.c_int, _P]),
+    "vs_clip_get_solver_level_cycles": (C.c_int, [_P, C.c_int, _P]),
     "vs_clip_get_phase": (C.c_int, [_P, C.c_int, _P]),
     "vs_phase_correlate_u8": (C.c_int, [_P, _IMG, _IMG, _P, C.c_int]),
     "vs_debug_invert4": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),

@@ -42,14 +42,18 @@ struct vs_clip {
     uint16_t* d_dbg_wd = nullptr;
     uint16_t* d_dbg_order = nullptr;
     int32_t* d_dbg_count = nullptr;
-    long long* d_dbg_clock = nullptr;   // [max_pairs][8]
+    long long* d_dbg_clock = nullptr;   // [max_pairs][VS_CLK_STRIDE]
     uint16_t* d_pos_scratch = nullptr; // [max_pairs][4][max_tiles] candidate lists of the parallel selection
+    uint4* d_patch_scratch = nullptr;  // [max_pairs][2][max_tiles] 4x4 keyframe windows of the warp-diff pass (patch cache of the solver)
+    uint8_t* d_tb_scratch = nullptr;   // [max_pairs][2][max_tiles] template bytes of the warp-diff pass
     float* d_res_scratch = nullptr;    // [max_pairs][2][max_tiles] warp-diff residuals reused by the first Gauss-Newton iteration
     uint8_t* d_warp_out = nullptr;    // staging for VS_MEM_HOST warps, grown on demand
     size_t warp_out_bytes = 0;
     // asynchronous transfer pipeline (vs_clip_upload_async / vs_clip_warp_to_host_async)
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
-    cudaEvent_t ev_compute = nullptr, ev_upload = nullptr;
+    cudaEvent_t ev_upload = nullptr;
+    cudaEvent_t ev_bgr_read = nullptr;   // recorded after every kernel that reads the BGR store (ingest, warps)
+    bool bgr_read_recorded = false;
     static const int kOutRing = 3;
     uint8_t* d_out_ring[kOutRing] = {nullptr, nullptr, nullptr};
     size_t out_ring_bytes[kOutRing] = {0, 0, 0};
@@ -104,11 +108,11 @@ void free_all(vs_clip* c)
         if (c->ev_down[i]) cudaEventDestroy(c->ev_down[i]);
     }
     cudaFree(c->d_coef_ring); cudaFree(c->d_slot_ring);
-    if (c->ev_compute) cudaEventDestroy(c->ev_compute);
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
+    if (c->ev_bgr_read) cudaEventDestroy(c->ev_bgr_read);
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
-    cudaFree(c->d_pos_scratch); cudaFree(c->d_res_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
+    cudaFree(c->d_pos_scratch); cudaFree(c->d_res_scratch); cudaFree(c->d_patch_scratch); cudaFree(c->d_tb_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
     cudaFree(c->d_warp_tab);
     cudaFree(c->d_sweep);
     cudaFree(c->pc.d_tw); cudaFree(c->pc.d_rows); cudaFree(c->pc.d_spec); cudaFree(c->pc.d_cross); cudaFree(c->pc.d_inv);
@@ -174,6 +178,15 @@ int clip_warp_launch(vs_clip* c, const int32_t* d_slots, const VsWarpCoef* d_coe
                                c->d_warp_tab);
     }
     return vsk_bgr_warp_slots(c->ctx, src, d_slots, d_coef, dst, crop, crop, mode, border);
+}
+
+// An asynchronous upload overwrites BGR frames only: it has to wait for the kernels that READ the BGR store (the ingest of
+// a slot's previous frame, the warps), not for the pyramid levels, keyframe features and solves enqueued since.
+void note_bgr_read(vs_clip* c)
+{
+    if (!c->ev_bgr_read) return;
+    cudaEventRecord(c->ev_bgr_read, c->ctx->stream);
+    c->bgr_read_recorded = true;
 }
 
 constexpr int kPhaseLevel = 2;   // alignment.hpp:69
@@ -311,11 +324,13 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_coef, (size_t)capacity);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_pos_scratch, (size_t)max_pairs * 4 * g.max_tiles);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_res_scratch, (size_t)max_pairs * 2 * g.max_tiles);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_patch_scratch, (size_t)max_pairs * 2 * g.max_tiles);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_tb_scratch, (size_t)max_pairs * 2 * g.max_tiles);
     if (r == VS_OK && (flags & VS_CLIP_DEBUG_TAPS)) {
         r = dev_alloc(ctx, &c->d_dbg_wd, (size_t)max_pairs * 2 * g.total_tiles);
         if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_order, (size_t)max_pairs * 2 * g.total_tiles);
         if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_count, (size_t)max_pairs * 2 * g.levels);
-        if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_clock, (size_t)max_pairs * 8);
+        if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_clock, (size_t)max_pairs * VS_CLK_STRIDE);
     }
     if (r != VS_OK) { free_all(c); delete c; return r; }
     // padding bytes of the pyramid rows are never read as pixels, but keep them defined
@@ -404,6 +419,7 @@ int vs_clip_build_pyramids(vs_clip* c, int slot0, int n)
         if (fused) { prev = lv1; l0 = 2; }
     }
     if (l0 == 1) VS_TRY(vsk_bgr2gray(ctx, bgr, prev));
+    note_bgr_read(c);
     for (int l = l0; l < g.levels; l++) {
         VsDevImg cur{pyr0 + g.lv[l].img_off, g.lv[l].w, g.lv[l].h, g.lv[l].pitch, n, (int64_t)g.pyr_slot_bytes};
         VS_TRY(vsk_pyr_down(ctx, prev, cur));
@@ -448,9 +464,12 @@ int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_
     a.dbg_warpdiff = c->d_dbg_wd; a.dbg_order = c->d_dbg_order; a.dbg_count = c->d_dbg_count;
     a.pos_scratch = c->d_pos_scratch;
     a.res_scratch = c->d_res_scratch;
+    a.patch_scratch = c->d_patch_scratch; a.tb_scratch = c->d_tb_scratch;
     a.force_threads = 0;
     a.dbg_clock = c->d_dbg_clock;
     if (c->params.phase_correlate) VS_TRY(phase_seed(c, pairs, c->d_pairs, n, 0, &a.init_T));
+    if (c->d_dbg_clock)
+        VS_CUDA(ctx, cudaMemsetAsync(c->d_dbg_clock, 0, (size_t)c->max_pairs * VS_CLK_STRIDE * sizeof(long long), ctx->stream));
     if (c->d_dbg_count)   // -1 marks levels a pair never reached
         VS_CUDA(ctx, cudaMemsetAsync(c->d_dbg_count, 0xFF, (size_t)c->max_pairs * 2 * c->g.levels * sizeof(int32_t), ctx->stream));
     VS_TRY(vsk_solve_pairs(ctx, c->g, a));
@@ -524,6 +543,7 @@ int vs_clip_align_sweep(vs_clip* c, const vs_pair* pairs, int n_pairs, const vs_
     a.dbg_warpdiff = nullptr; a.dbg_order = nullptr; a.dbg_count = nullptr; a.dbg_clock = nullptr;
     a.pos_scratch = c->d_pos_scratch;
     a.res_scratch = c->d_res_scratch;
+    a.patch_scratch = c->d_patch_scratch; a.tb_scratch = c->d_tb_scratch;
     a.force_threads = 0;
     a.sweep = c->d_sweep;
     a.sweep_pairs = n_pairs;
@@ -583,6 +603,8 @@ int vs_clip_align_async(vs_clip* c, const vs_pair* pairs, int n, int base, int l
     a.dbg_warpdiff = nullptr; a.dbg_order = nullptr; a.dbg_count = nullptr; a.dbg_clock = nullptr;
     a.pos_scratch = c->d_pos_scratch ? c->d_pos_scratch + (size_t)base * 4 * c->g.max_tiles : nullptr;
     a.res_scratch = c->d_res_scratch ? c->d_res_scratch + (size_t)base * 2 * c->g.max_tiles : nullptr;
+    a.patch_scratch = c->d_patch_scratch ? c->d_patch_scratch + (size_t)base * 2 * c->g.max_tiles : nullptr;
+    a.tb_scratch = c->d_tb_scratch ? c->d_tb_scratch + (size_t)base * 2 * c->g.max_tiles : nullptr;
     // all lanes must be resident on the GPU together: an SM per pair (512 threads, registers uncapped: the shortest
     // latency per pair) when every pair of every lane gets one, else three 256-thread CTAs per SM
     a.force_threads = c->max_pairs <= ctx->sm_count ? 512 : 256;
@@ -654,6 +676,7 @@ int vs_clip_warp(vs_clip* c, const int32_t* slots, int n, const double* transfor
     }
     VsDevImg dst{d_out, ow, oh, (int64_t)ow * 3, n, d_stride};
     VS_TRY(clip_warp_launch(c, c->d_slots, c->d_coef, dst, crop, mode, border, n));
+    note_bgr_read(c);
     if (mem == VS_MEM_HOST) {
         VS_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)out_frame_stride, d_out, (size_t)d_stride, (size_t)ow * oh * 3, n,
                                        cudaMemcpyDeviceToHost, ctx->stream));
@@ -669,8 +692,11 @@ static int ensure_async(vs_clip* c)
     if (c->up_stream) return VS_OK;
     VS_CUDA(ctx, cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
     VS_CUDA(ctx, cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
-    VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming));
     VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming));
+    VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_bgr_read, cudaEventDisableTiming));
+    // everything enqueued before the first asynchronous upload counts as a reader
+    VS_CUDA(ctx, cudaEventRecord(c->ev_bgr_read, ctx->stream));
+    c->bgr_read_recorded = true;
     for (int i = 0; i < vs_clip::kOutRing; i++) {
         VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_warp[i], cudaEventDisableTiming));
         VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_down[i], cudaEventDisableTiming));
@@ -690,9 +716,8 @@ int vs_clip_upload_async(vs_clip* c, int slot0, int n, const uint8_t* bgr, int64
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
     VS_TRY(ensure_async(c));
     if (n == 0) return VS_OK;
-    // the slots being overwritten may still be read by compute enqueued earlier
-    VS_CUDA(ctx, cudaEventRecord(c->ev_compute, ctx->stream));
-    VS_CUDA(ctx, cudaStreamWaitEvent(c->up_stream, c->ev_compute, 0));
+    // the slots being overwritten may still be read by the ingest / warps enqueued earlier (nothing else reads BGR frames)
+    if (c->bgr_read_recorded) VS_CUDA(ctx, cudaStreamWaitEvent(c->up_stream, c->ev_bgr_read, 0));
     if (frame_stride == row_stride * c->h) {
         VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)slot0 * c->bgr_slot_bytes, c->bgr_pitch, bgr, (size_t)row_stride,
                                        (size_t)c->w * 3, (size_t)c->h * n, cudaMemcpyHostToDevice, c->up_stream));
@@ -756,6 +781,7 @@ int vs_clip_warp_to_host_async(vs_clip* c, const int32_t* slots, int n, const do
     VS_CUDA(ctx, cudaMemcpyAsync(d_slots, slots, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     VsDevImg dst{c->d_out_ring[b], ow, oh, (int64_t)ow * 3, n, (int64_t)frame_bytes};
     VS_TRY(clip_warp_launch(c, d_slots, d_coef, dst, crop, mode, border, n));
+    note_bgr_read(c);
     VS_CUDA(ctx, cudaEventRecord(c->ev_warp[b], ctx->stream));
     VS_CUDA(ctx, cudaStreamWaitEvent(c->down_stream, c->ev_warp[b], 0));
     if (out_frame_stride == (int64_t)frame_bytes)
@@ -875,7 +901,23 @@ int vs_clip_get_solver_cycles(vs_clip* c, int pair, long long* out6)
     VS_REQUIRE(ctx, c->d_dbg_clock, "clip_get_solver_cycles: clip was created without VS_CLIP_DEBUG_TAPS");
     VS_REQUIRE(ctx, pair >= 0 && pair < c->last_pairs && out6, "clip_get_solver_cycles: bad arguments");
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
-    VS_CUDA(ctx, cudaMemcpyAsync(out6, c->d_dbg_clock + (size_t)pair * 8, 6 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    long long t[8];
+    VS_CUDA(ctx, cudaMemcpyAsync(t, c->d_dbg_clock + (size_t)pair * VS_CLK_STRIDE, 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    t[3] += t[6];   // the documented six: SVD beside the first iteration + the gathers of the later iterations
+    for (int i = 0; i < 6; i++) out6[i] = t[i];
+    return VS_OK;
+}
+
+int vs_clip_get_solver_level_cycles(vs_clip* c, int pair, long long* out)
+{
+    if (!c) return VS_ERR_INVALID;
+    vs_ctx* ctx = c->ctx;
+    VS_REQUIRE(ctx, c->d_dbg_clock, "clip_get_solver_level_cycles: clip was created without VS_CLIP_DEBUG_TAPS");
+    VS_REQUIRE(ctx, pair >= 0 && pair < c->last_pairs && out, "clip_get_solver_level_cycles: bad arguments");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VS_CUDA(ctx, cudaMemcpyAsync(out, c->d_dbg_clock + (size_t)pair * VS_CLK_STRIDE + 8, (size_t)c->g.levels * 8 * sizeof(long long),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
     VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VS_OK;
 }

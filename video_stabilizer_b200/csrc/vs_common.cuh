@@ -143,16 +143,21 @@ struct VsLzTaps {
     uint32_t row[4];
 };
 
-__device__ __forceinline__ void vs_lz_fetch(const uint8_t* __restrict__ img, int w, int h, int pitch, float ox, float oy,
-                                            float A, float B, float TX, float TY, VsLzTaps& t)
+// position part of a sample: integer origin (ix, iy) = floor(W(p)) and the fractions
+__device__ __forceinline__ void vs_lz_pos(float ox, float oy, float A, float B, float TX, float TY, int& ix, int& iy, float& rx, float& ry)
 {
     const float onepA = __fadd_rn(1.0f, A);
     const float Wx = __fadd_rn(__fsub_rn(__fmul_rn(onepA, ox), __fmul_rn(B, oy)), TX);
     const float Wy = __fadd_rn(__fadd_rn(__fmul_rn(B, ox), __fmul_rn(onepA, oy)), TY);
     const float fWx = floorf(Wx), fWy = floorf(Wy);
-    t.rx = __fsub_rn(Wx, fWx);
-    t.ry = __fsub_rn(Wy, fWy);
-    const int ix = (int)fWx, iy = (int)fWy;
+    rx = __fsub_rn(Wx, fWx);
+    ry = __fsub_rn(Wy, fWy);
+    ix = (int)fWx; iy = (int)fWy;
+}
+
+// load part: the window of origin (ix, iy); its bytes are a function of (ix, iy) alone
+__device__ __forceinline__ void vs_lz_load(const uint8_t* __restrict__ img, int w, int h, int pitch, int ix, int iy, uint32_t* row)
+{
     if (ix >= 1 && ix + 6 < w && iy >= 1 && iy + 2 < h) {
         const int off = (iy - 1) * pitch + ix - 1;
         const uint8_t* p = img + (off & ~3);
@@ -161,16 +166,24 @@ __device__ __forceinline__ void vs_lz_fetch(const uint8_t* __restrict__ img, int
         for (int j = 0; j < 4; j++) {
             const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(p + j * pitch));
             const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(p + j * pitch + 4));
-            t.row[j] = __funnelshift_r(w0, w1, sh);
+            row[j] = __funnelshift_r(w0, w1, sh);
         }
     } else {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint8_t* r = img + (size_t)vs_clampi(iy - 1 + j, 0, h - 1) * pitch;
-            t.row[j] = (uint32_t)__ldg(r + vs_clampi(ix - 1, 0, w - 1)) | ((uint32_t)__ldg(r + vs_clampi(ix, 0, w - 1)) << 8) |
-                       ((uint32_t)__ldg(r + vs_clampi(ix + 1, 0, w - 1)) << 16) | ((uint32_t)__ldg(r + vs_clampi(ix + 2, 0, w - 1)) << 24);
+            row[j] = (uint32_t)__ldg(r + vs_clampi(ix - 1, 0, w - 1)) | ((uint32_t)__ldg(r + vs_clampi(ix, 0, w - 1)) << 8) |
+                     ((uint32_t)__ldg(r + vs_clampi(ix + 1, 0, w - 1)) << 16) | ((uint32_t)__ldg(r + vs_clampi(ix + 2, 0, w - 1)) << 24);
         }
     }
+}
+
+__device__ __forceinline__ void vs_lz_fetch(const uint8_t* __restrict__ img, int w, int h, int pitch, float ox, float oy,
+                                            float A, float B, float TX, float TY, VsLzTaps& t)
+{
+    int ix, iy;
+    vs_lz_pos(ox, oy, A, B, TX, TY, ix, iy, t.rx, t.ry);
+    vs_lz_load(img, w, h, pitch, ix, iy, t.row);
 }
 
 __device__ __forceinline__ float vs_lz_eval(const VsLzTaps& t)

@@ -407,7 +407,8 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v)
 // keys[a]: n packed keys of axis a; pos[a]: 2*n u16 (posL then posR).  nth < n.
 template <int SOLVE_THREADS>
 __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1, uint16_t* const pos0, uint16_t* const pos1,
-                                   const int n, const int nth, SelShared<SOLVE_THREADS / 32>& ss, long long* rounds = nullptr)
+                                   const int n, const int nth, SelShared<SOLVE_THREADS / 32>& ss, long long* rounds = nullptr,
+                                   long long* serial_cycles = nullptr)
 {
     constexpr int NWARPS = SOLVE_THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -422,6 +423,7 @@ __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1,
             const int a = tid >> 5;
             SelAxis& st = ss.ax[a];
             uint32_t* v = a ? keys1 : keys0;
+            const long long t0 = serial_cycles ? clock64() : 0;
             if (!st.done) {
                 if (st.last - st.first <= SEL_SERIAL || st.depth == 0) {
                     vs_sel::introselect_from(v, st.first, nth, st.last, st.depth);
@@ -434,6 +436,7 @@ __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1,
                     st.pivot = v[st.first];
                 }
             }
+            if (serial_cycles) *serial_cycles += clock64() - t0;
         }
         __syncthreads();
         const bool act0 = !ss.ax[0].done, act1 = !ss.ax[1].done;
@@ -607,6 +610,12 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
     // signed residual template - keyframe(W(p)) of every tile from the warp-diff pass: the first Gauss-Newton iteration of a
     // level evaluates exactly these samples again (same transform), so it reads them back instead of the images
     float* const res = a.res_scratch ? a.res_scratch + (size_t)pair * 2 * g.max_tiles : nullptr;
+    // patch cache: the 4x4 keyframe window and the template byte of every tile as the warp-diff pass gathered them.  A later
+    // Gauss-Newton iteration whose sample still has the same integer origin (the transform moves by a fraction of a pixel
+    // within a level) reads 16 contiguous bytes instead of four sectors of the image; the window's bytes depend on the
+    // origin alone, so both routes give the same bits.
+    uint4* const patch = a.patch_scratch ? a.patch_scratch + (size_t)pair * 2 * g.max_tiles : nullptr;
+    uint8_t* const tbs = a.tb_scratch ? a.tb_scratch + (size_t)pair * 2 * g.max_tiles : nullptr;
 
     if (tid == 0) {
         sh.T[0] = sh.T[1] = sh.T[2] = sh.T[3] = 0.0;
@@ -615,10 +624,14 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         if (a.out_iters) for (int l = 0; l < g.levels; l++) a.out_iters[(size_t)pair * g.levels + l] = 0;
     }
 
-    long long clk[6] = {0, 0, 0, 0, 0, 0};   // warpdiff, select, hessian+svd, gn gather, gn reduce+update, (unused)
+    // debug taps: cycles per phase {warpdiff, select, hessian sums, svd beside the first iteration, gn reduce+update,
+    // (rounds of the selection), gn gathers of the later iterations}, summed over levels and per level
+    long long clk[7] = {0, 0, 0, 0, 0, 0, 0};
     long long t_prev = a.dbg_clock ? clock64() : 0;
-#define VS_CLK(slot) do { if (a.dbg_clock && tid == 0) { long long _t = clock64(); clk[slot] += _t - t_prev; t_prev = _t; } } while (0)
-    for (int lvl = g.levels - 1; lvl >= 0; lvl--) {
+    int lvl = g.levels - 1;
+#define VS_CLK(slot) do { if (a.dbg_clock && tid == 0) { long long _t = clock64(); clk[slot] += _t - t_prev;                     \
+                          a.dbg_clock[(size_t)pair * VS_CLK_STRIDE + 8 + lvl * 8 + (slot)] += _t - t_prev; t_prev = _t; } } while (0)
+    for (; lvl >= 0; lvl--) {
         const VsLevel L = g.lv[lvl];
         const uint8_t* timg = tpyr + L.img_off;
         const uint8_t* kimg = kpyr + L.img_off;
@@ -648,6 +661,10 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
             VsLzTaps taps;
             vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, P[0], P[1], P[2], P[3], taps);
             const uint32_t tb = __ldg(timg + (size_t)py * L.pitch + px);
+            if (patch) {
+                patch[axis * g.max_tiles + t] = make_uint4(taps.row[0], taps.row[1], taps.row[2], taps.row[3]);
+                tbs[axis * g.max_tiles + t] = (uint8_t)tb;
+            }
             const float s = vs_lz_eval(taps);
             if (res) res[axis * g.max_tiles + t] = __fsub_rn((float)tb, s);
             float d = fabsf(__fsub_rn(s, (float)tb));
@@ -661,9 +678,20 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 
         VS_CLK(0);
         // ---- keep the k smallest: exact replay of std::nth_element (alignment.cpp:460-486)
-        block_nth_element2<SOLVE_THREADS>(keys0, keys1, pos0, pos1, nt, k, sel, a.dbg_clock ? &clk[5] : nullptr);
+        // candidate lists: the unused tail of the key arrays when this level's lists fit there (every level but the
+        // largest of a clip: no shared memory is added, and the lists of those levels stay out of L2)
+        const bool tail_lists = a.pos_scratch != nullptr && 2 * nt <= g.max_tiles;
+        const long long rounds0 = clk[5];
+        long long serial_cyc = 0;
+        block_nth_element2<SOLVE_THREADS>(keys0, keys1, tail_lists ? reinterpret_cast<uint16_t*>(keys0 + nt) : pos0,
+                                          tail_lists ? reinterpret_cast<uint16_t*>(keys1 + nt) : pos1, nt, k, sel,
+                                          a.dbg_clock ? &clk[5] : nullptr, a.dbg_clock ? &serial_cyc : nullptr);
         __syncthreads();
         VS_CLK(1);
+        if (a.dbg_clock && tid == 0) {
+            a.dbg_clock[(size_t)pair * VS_CLK_STRIDE + 8 + lvl * 8 + 5] = clk[5] - rounds0;
+            a.dbg_clock[(size_t)pair * VS_CLK_STRIDE + 8 + lvl * 8 + 7] = serial_cyc;   // thread 0's share of the serial steps
+        }
 
         if (a.dbg_order) {
             for (int i = tid; i < 2 * k; i += SOLVE_THREADS) {
@@ -741,10 +769,26 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
                 const uint32_t key = (axis ? keys1 : keys0)[j];
                 const int tx = (int)(key & 0x3ffu), ty = (int)((key >> 10) & 0x3ffu);
                 const int px = tx * L.tile + (int)((key >> 20) & 31u), py = ty * L.tile + (int)((key >> 25) & 31u);
-                const float4 J = __ldg((axis ? jcl1 : jcl0) + ty * L.tw + tx);
+                const int t = ty * L.tw + tx;
+                const float4 J = __ldg((axis ? jcl1 : jcl0) + t);
                 VsLzTaps taps;
-                vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, Pg[0], Pg[1], Pg[2], Pg[3], taps);
-                const uint32_t tb = __ldg(timg + (size_t)min(py, L.h - 1) * L.pitch + min(px, L.w - 1));
+                uint32_t tb;
+                if (patch) {
+                    int ix, iy, ix0, iy0;
+                    float rx0, ry0;
+                    vs_lz_pos((float)px, (float)py, Pg[0], Pg[1], Pg[2], Pg[3], ix, iy, taps.rx, taps.ry);
+                    vs_lz_pos((float)px, (float)py, P[0], P[1], P[2], P[3], ix0, iy0, rx0, ry0);
+                    tb = __ldcg(tbs + axis * g.max_tiles + t);
+                    if (ix == ix0 && iy == iy0) {
+                        const uint4 q = __ldcg(patch + axis * g.max_tiles + t);
+                        taps.row[0] = q.x; taps.row[1] = q.y; taps.row[2] = q.z; taps.row[3] = q.w;
+                    } else {
+                        vs_lz_load(kimg, L.w, L.h, L.pitch, ix, iy, taps.row);
+                    }
+                } else {
+                    vs_lz_fetch(kimg, L.w, L.h, L.pitch, (float)px, (float)py, Pg[0], Pg[1], Pg[2], Pg[3], taps);
+                    tb = __ldg(timg + (size_t)min(py, L.h - 1) * L.pitch + min(px, L.w - 1));
+                }
                 const float r = __fsub_rn((float)tb, vs_lz_eval(taps));
                 b[0] += (double)__fmul_rn(J.x, r);
                 b[1] += (double)__fmul_rn(J.y, r);
@@ -777,7 +821,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
                 if (res) gather_cached(32, SOLVE_THREADS - 32, b);
                 else gather(32, SOLVE_THREADS - 32, b);
             }
-            VS_CLK(3);
+            VS_CLK(iter > 0 ? 6 : 3);
             double tot[4];
             block_reduce<4, NWARPS, 4>(b, sh.red4, tot);
             if (tid == 0) {
@@ -838,7 +882,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         }
         for (int c = 0; c < 4; c++) a.out_T[(size_t)pair * 4 + c] = T[c];
         a.out_status[pair] = sh.status;
-        if (a.dbg_clock) for (int c = 0; c < 6; c++) a.dbg_clock[(size_t)pair * 8 + c] = clk[c];
+        if (a.dbg_clock) for (int c = 0; c < 7; c++) a.dbg_clock[(size_t)pair * VS_CLK_STRIDE + c] = clk[c];
     }
 }
 
