@@ -301,7 +301,7 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
         g.total_tiles = toff;
         g.pyr_slot_bytes = vs_align_up(off, 256);
     }
-    if (g.max_tiles > 65535 || (size_t)2 * g.max_tiles * 4 > 200 * 1024) {
+    if (g.max_tiles > 65535 || (size_t)2 * g.max_tiles * 4 + (size_t)g.max_tiles + 64 > 216 * 1024) {   // keys + chunk words of the selection
         const int mt = g.max_tiles;
         delete c;
         return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "%d tiles on a level exceeds the on-chip selection capacity", mt);

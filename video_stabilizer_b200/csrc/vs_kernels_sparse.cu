@@ -549,6 +549,159 @@ __device__ void block_nth_element2(uint32_t* const keys0, uint32_t* const keys1,
     }
 }
 
+// ---- the same replay without candidate lists, for CTAs that have an SM to themselves ------------
+// (512 / 1024 threads: 4K clips, up to 148 pairs per launch, the per-frame API.)  The range is cut into chunks
+// of 32 consecutive keys; a warp ballot gives every chunk one bit mask of ">= pivot" and one of "<= pivot" keys,
+// a warp scan of the chunks' population counts gives their ranks, and the candidate of rank k from the left
+// finds its partner, rank k from the right, by a binary search over the chunk ranks and a bit-select in that
+// chunk's mask.  a_k - b_k grows with k, so every candidate decides its own swap and a warp stops at its first
+// chunk holding a candidate that does not swap.  The state is 16 bytes per 32 keys, in shared memory at every
+// level (no global scratch, no L2 round trips), and the two keypoint axes run on their own half of the warps
+// with their own named barrier: an axis never waits for the rounds of the other.  Measured against the list
+// form above (mean cycles per pair): 4K 1.92 M -> 1.78 M, 720p 0.68 M -> 0.63 M, one 1080p pair 0.75 M -> 0.70 M.
+// With three 256-thread CTAs per SM (the 299 pairs of a 1080p clip) the extra 5 KB per CTA push the
+// shared-memory carve-out from 132 to 164 KB, and the L1 lost to it costs more than the selection gains
+// (0.774 -> 0.803 ms): that configuration keeps the lists.
+__host__ __device__ inline int sel_chunks(int max_tiles) { return (max_tiles + 31) / 32 + 1; }
+
+// position of the set bit of rank j (from bit 0) in a mask that has more than j bits set
+__device__ __forceinline__ int sel_nth_bit(uint32_t mask, int j)
+{
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const int c = __popc(mask & (((1u << w) - 1u) << pos));
+        if (j >= c) { j -= c; pos += w; }
+    }
+    return pos;
+}
+
+template <int GROUP_THREADS>
+__device__ __forceinline__ void sel_group_bar(int axis)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(axis + 1), "n"(GROUP_THREADS) : "memory");
+}
+
+// keys[a]: n packed keys of axis a; selbuf: [2][4][nc] words (masks and ranks of the chunks).  nth < n.
+template <int SOLVE_THREADS>
+__device__ void block_nth_element2_masks(uint32_t* const keys0, uint32_t* const keys1, uint32_t* const selbuf, const int nc,
+                                         const int n, const int nth, SelAxis* const ax, long long* rounds = nullptr,
+                                         long long* serial_cycles = nullptr)
+{
+    constexpr int GT = SOLVE_THREADS / 2;      // threads of an axis group
+    constexpr int G = GT / 32;                 // its warps
+    if (n == 0 || nth == n) return;
+    const int axis = threadIdx.x / GT, gtid = threadIdx.x % GT, gw = gtid >> 5, lane = gtid & 31;
+    uint32_t* const v = axis ? keys1 : keys0;
+    SelAxis& st = ax[axis];
+    uint32_t* const maskL = selbuf + (size_t)axis * 4 * nc;
+    uint32_t* const maskR = maskL + nc;
+    uint32_t* const preL = maskR + nc;         // candidates of lower chunks, ">= pivot"
+    uint32_t* const preR = preL + nc;          // candidates of lower chunks, "<= pivot"
+    const uint32_t lt = (1u << lane) - 1u;
+    if (gtid == 0) { st.first = 0; st.last = n; st.depth = vs_sel::lg(n) * 2; st.done = 0; }
+    while (true) {
+        // ---- serial step: finish, or pick the pivot of the next round (the thread that did the bookkeeping)
+        if (gtid == 0) {
+            const long long t0 = serial_cycles && axis == 0 ? clock64() : 0;
+            if (st.last - st.first <= SEL_SERIAL || st.depth == 0) {
+                vs_sel::introselect_from(v, st.first, nth, st.last, st.depth);
+                st.done = 1;
+            } else {
+                --st.depth;
+                st.nL = 0;                              // swaps of the round
+                st.cutL = st.cutR = 0x7fffffff;
+                const int mid = st.first + (st.last - st.first) / 2;
+                vs_sel::move_median_to_first(v, st.first, st.first + 1, mid, st.last - 1);
+                st.pivot = v[st.first];
+            }
+            if (serial_cycles && axis == 0) *serial_cycles += clock64() - t0;
+        }
+        sel_group_bar<GT>(axis);
+        if (st.done) break;
+        if (rounds && axis == 0) ++*rounds;
+        const int f0 = st.first + 1, last = st.last;
+        const uint32_t pv = st.pivot >> 16;
+        const int nch = (last - f0 + 31) >> 5;
+
+        // ---- masks of the chunks
+        for (int c = gw; c < nch; c += G) {
+            const int i = f0 + 32 * c + lane;
+            const bool valid = i < last;
+            const uint32_t e = valid ? v[i] >> 16 : 0u;
+            const uint32_t mL = __ballot_sync(0xffffffffu, valid && e >= pv);
+            const uint32_t mR = __ballot_sync(0xffffffffu, valid && e <= pv);
+            if (lane == 0) { maskL[c] = mL; maskR[c] = mR; }
+        }
+        sel_group_bar<GT>(axis);
+
+        // ---- ranks of the chunks (every warp computes and writes the same values: no barrier)
+        uint32_t nR = 0;
+        {
+            uint32_t nL = 0;
+            for (int base = 0; base < nch; base += 32) {
+                const int c = base + lane;
+                const uint32_t cl = c < nch ? __popc(maskL[c]) : 0u, cr = c < nch ? __popc(maskR[c]) : 0u;
+                uint32_t il = cl, ir = cr;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t tl = __shfl_up_sync(0xffffffffu, il, o), tr = __shfl_up_sync(0xffffffffu, ir, o);
+                    if (lane >= o) { il += tl; ir += tr; }
+                }
+                if (c < nch) { preL[c] = nL + il - cl; preR[c] = nR + ir - cr; }
+                nL += __shfl_sync(0xffffffffu, il, 31);
+                nR += __shfl_sync(0xffffffffu, ir, 31);
+            }
+        }
+        __syncwarp();
+
+        // ---- the swaps
+        const int steps = 32 - __clz(nch - 1);      // 2^steps >= nch (nch >= 1)
+        int cnt = 0, minL = 0x7fffffff, minR = 0x7fffffff;
+        for (int c = gw; c < nch; c += G) {
+            const uint32_t mL = maskL[c];
+            if (mL == 0u) continue;
+            const bool cand = (mL >> lane) & 1u;
+            const uint32_t k = preL[c] + __popc(mL & lt);
+            const int a = f0 + 32 * c + lane;
+            bool swapped = false;
+            if (cand && k < nR) {
+                const uint32_t r = nR - 1u - k;          // the partner's rank from the left
+                int lo = 0, hi = nch - 1;
+                for (int s = 0; s < steps; s++) {        // largest chunk whose rank is <= r
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (preR[mid] <= r) lo = mid; else hi = mid - 1;
+                }
+                const int b = f0 + 32 * lo + sel_nth_bit(maskR[lo], (int)(r - preR[lo]));
+                if (a < b) {
+                    const uint32_t t = v[a]; v[a] = v[b]; v[b] = t;
+                    swapped = true;
+                    cnt++;
+                    minR = min(minR, b);
+                }
+            }
+            if (cand && !swapped) minL = min(minL, a);
+            if (__any_sync(0xffffffffu, cand && !swapped)) break;   // no later candidate swaps either
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        minL = __reduce_min_sync(0xffffffffu, minL);
+        minR = __reduce_min_sync(0xffffffffu, minR);
+        if (lane == 0) {
+            if (cnt) atomicAdd(&st.nL, cnt);
+            if (minL != 0x7fffffff) atomicMin(&st.cutL, minL);
+            if (minR != 0x7fffffff) atomicMin(&st.cutR, minR);
+        }
+        sel_group_bar<GT>(axis);
+        // ---- the bookkeeping of __introselect
+        if (gtid == 0) {
+            int cut = st.last;
+            if (st.cutL != 0x7fffffff) cut = st.cutL;             // a_m
+            if (st.nL > 0) cut = min(cut, st.cutR);               // b_{m-1}
+            if (cut <= nth) st.first = cut; else st.last = cut;
+        }
+    }
+}
+
 template <int N, int NWARPS, int STRIDE>
 __device__ __forceinline__ void block_reduce(double* v, double (*red)[STRIDE], double* total)
 {
@@ -603,7 +756,11 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
     const size_t feat = (size_t)pr.keyframe_slot * 2 * g.total_tiles;
     uint32_t* const keys0 = dyn_keys;
     uint32_t* const keys1 = dyn_keys + g.max_tiles;
-    // candidate position lists of the parallel selection: shared memory when they fit, else a global scratch slice
+    // the parallel selection's state: chunk masks and ranks in shared memory when the CTA has its SM to itself, else
+    // candidate position lists in shared memory when they fit, else in a global scratch slice
+    constexpr bool SEL_MASKS = MIN_CTAS == 1;
+    const int sel_nc = sel_chunks(g.max_tiles);
+    uint32_t* const selbuf = dyn_keys + 2 * g.max_tiles;
     uint16_t* const pos0 = a.pos_scratch ? a.pos_scratch + (size_t)pair * 4 * g.max_tiles
                                          : reinterpret_cast<uint16_t*>(dyn_keys + 2 * g.max_tiles);
     uint16_t* const pos1 = pos0 + 2 * g.max_tiles;
@@ -683,9 +840,13 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         const bool tail_lists = a.pos_scratch != nullptr && 2 * nt <= g.max_tiles;
         const long long rounds0 = clk[5];
         long long serial_cyc = 0;
-        block_nth_element2<SOLVE_THREADS>(keys0, keys1, tail_lists ? reinterpret_cast<uint16_t*>(keys0 + nt) : pos0,
-                                          tail_lists ? reinterpret_cast<uint16_t*>(keys1 + nt) : pos1, nt, k, sel,
-                                          a.dbg_clock ? &clk[5] : nullptr, a.dbg_clock ? &serial_cyc : nullptr);
+        if (SEL_MASKS)
+            block_nth_element2_masks<SOLVE_THREADS>(keys0, keys1, selbuf, sel_nc, nt, k, sel.ax, a.dbg_clock ? &clk[5] : nullptr,
+                                                    a.dbg_clock ? &serial_cyc : nullptr);
+        else
+            block_nth_element2<SOLVE_THREADS>(keys0, keys1, tail_lists ? reinterpret_cast<uint16_t*>(keys0 + nt) : pos0,
+                                              tail_lists ? reinterpret_cast<uint16_t*>(keys1 + nt) : pos1, nt, k, sel,
+                                              a.dbg_clock ? &clk[5] : nullptr, a.dbg_clock ? &serial_cyc : nullptr);
         __syncthreads();
         VS_CLK(1);
         if (a.dbg_clock && tid == 0) {
@@ -998,19 +1159,27 @@ int vsk_keyframe_features(vs_ctx* ctx, const VsClipGeom& g, const uint8_t* d_pyr
 int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
 {
     if (a.n_pairs <= 0) return VS_OK;
-    // keys (8 B per tile) always live in shared memory; the candidate position lists of the
-    // parallel selection (another 8 B per tile) join them when the total stays small enough
-    // for three CTAs per SM, else they come from the caller's global scratch
+    // CTA size by how many pairs are in flight (see below)
+    int threads = a.n_pairs <= ctx->sm_count ? 512 : 256;
+    if (a.force_threads == 256 || a.force_threads == 512 || a.force_threads == 1024) threads = a.force_threads;
+    // keys (8 B per tile) always live in shared memory.  A CTA that has its SM to itself adds the chunk masks and ranks
+    // of the list-free selection (1 B per tile).  Three CTAs per SM keep candidate position lists (another 8 B per
+    // tile): next to the keys when the total stays small, else in the unused tail of the key arrays and, for the
+    // largest level, in the caller's global scratch.
     const size_t key_bytes = (size_t)2 * g.max_tiles * sizeof(uint32_t);
     const size_t pos_bytes = (size_t)4 * g.max_tiles * sizeof(uint16_t);
+    const size_t sel_bytes = (size_t)2 * 4 * sel_chunks(g.max_tiles) * sizeof(uint32_t);
     VS_REQUIRE(ctx, g.max_tiles <= 65535, "solve: more than 65535 tiles per level");
-    VS_REQUIRE(ctx, key_bytes <= 200 * 1024, "solve: level too large for the shared-memory selection");
+    VS_REQUIRE(ctx, key_bytes + sel_bytes <= 220 * 1024, "solve: level too large for the shared-memory selection");
     size_t smem = key_bytes;
     VsSolveArgs args = a;
     // (Measured: keeping the lists of the shorter rounds in a shared-memory part next to the keys makes a round cheaper,
     // 9.5k -> 8.3k cycles, but every KB of shared memory is a KB of L1 taken from the gathers, which lose more: mean
     // 0.67 -> 0.97 ms per pair at 68 KB per CTA.  The keys stay alone in shared memory unless everything fits.)
-    if (key_bytes + pos_bytes <= 72 * 1024 || !a.pos_scratch) {
+    if (threads != 256) {
+        smem += sel_bytes;
+        args.pos_scratch = nullptr;
+    } else if (key_bytes + pos_bytes <= 72 * 1024 || !a.pos_scratch) {
         VS_REQUIRE(ctx, key_bytes + pos_bytes <= 220 * 1024, "solve: level too large and no selection scratch given");
         smem += pos_bytes;
         args.pos_scratch = nullptr;
@@ -1038,8 +1207,6 @@ int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
         k_solve_pairs<NT, MINB><<<a.n_pairs, NT, smem, ctx->stream>>>(g, args);                                                   \
     } while (0)
     // (1024 threads for a single pair — the per-frame API — were measured too: 980 against 1046-1078 frames/s)
-    int threads = a.n_pairs <= ctx->sm_count ? 512 : 256;
-    if (a.force_threads == 256 || a.force_threads == 512 || a.force_threads == 1024) threads = a.force_threads;
     if (threads == 1024) VS_SOLVE_LAUNCH(1024, 1);
     else if (threads == 512) VS_SOLVE_LAUNCH(512, 1);
     else VS_SOLVE_LAUNCH(256, 3);
