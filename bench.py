@@ -296,7 +296,7 @@ def exchange_name(tag):
 class PartitionedVideo:
     """One rank's share of a synthetic N x F-frame video in a given partition, with its pinned host frames."""
 
-    def __init__(self, R, args, W, H, F, sub, block, resident, tag, seed=CLIP_SEED):
+    def __init__(self, R, args, W, H, F, sub, block, resident, tag, seed=CLIP_SEED, share=None):
         import torch
         from video_stabilizer_b200 import host, synth
         from video_stabilizer_b200.imgproc import Context
@@ -305,7 +305,7 @@ class PartitionedVideo:
         p = host.stab_params_default()
         p.crop_pixels = args.crop
         self.params = p
-        threads = max(1, min(8, (os.cpu_count() or 1) // max(1, R.world)))
+        threads = max(1, min(8, (os.cpu_count() or 1) // max(1, R.world * max(1, args.inflight))))
         name = exchange_name(tag) if R.world > 1 else ""
         # rank 0 creates the shared table; the others attach once it exists
         if R.rank == 0:
@@ -319,13 +319,16 @@ class PartitionedVideo:
         self.host_threads = threads
         ps = self.ps
         n_local = len(ps.local_frames)
-        self.pinned = torch.empty((n_local, H, W, 3), dtype=torch.uint8, pin_memory=True)
-        self.frames = self.pinned.numpy()
-        ctx = Context(R.local)
-        canvas = synth.make_canvas(W, H, 1000 + seed)
-        poses = synth.jitter_path(self.total, 1001 + seed)
-        synth.render_frames_gpu(ctx, canvas, poses, ps.local_frames, W, H, self.frames, chunk=32 if W <= 1920 else 8)
-        ctx.close()
+        if share is not None:      # a second instance over the same video: the same pinned frames
+            self.pinned, self.frames = share.pinned, share.frames
+        else:
+            self.pinned = torch.empty((n_local, H, W, 3), dtype=torch.uint8, pin_memory=True)
+            self.frames = self.pinned.numpy()
+            ctx = Context(R.local)
+            canvas = synth.make_canvas(W, H, 1000 + seed)
+            poses = synth.jitter_path(self.total, 1001 + seed)
+            synth.render_frames_gpu(ctx, canvas, poses, ps.local_frames, W, H, self.frames, chunk=32 if W <= 1920 else 8)
+            ctx.close()
         self.frame_bytes = W * H * 3
         self.stream = torch.cuda.Stream()
         assert self.stream.cuda_stream != 0
@@ -351,6 +354,52 @@ def timed(R, stream, fn, steps, warmup, launches_of=None):
     R.barrier()
     t1 = time.time()
     ms = e0.elapsed_time(e1) / steps
+    timed.launches = (launches_of() - n0) if launches_of else 0
+    return R.reduce(ms, "max"), t0, t1
+
+
+def timed_inflight(R, streams, fns, steps, warmup, launches_of=None):
+    """`steps` steps over len(fns) independent instances, one host thread each (step s runs on instance s % n): the next
+    video's uploads and first stages fill the drain of the previous one.  CUDA events on every instance's stream; the
+    time is from the earliest start event to the latest end event."""
+    torch = R.torch
+    n = len(fns)
+    if n == 1:
+        return timed(R, streams[0], fns[0], steps, warmup, launches_of)
+
+    def run(count):
+        errs = []
+
+        def work(i):
+            try:
+                torch.cuda.set_device(R.local)
+                for _ in range(i, count, n):
+                    fns[i]()
+            except BaseException as e:   # noqa: BLE001 - re-raised on the main thread
+                errs.append(e)
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    run(max(warmup, 1) * n)
+    R.barrier()
+    n0 = launches_of() if launches_of else 0
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    t0 = time.time()
+    for e, st in zip(e0, streams):
+        e.record(st)
+    run(steps)
+    for e, st in zip(e1, streams):
+        e.record(st)
+    R.barrier()
+    t1 = time.time()
+    torch.cuda.synchronize()
+    ms = max(a.elapsed_time(b) for a in e0 for b in e1) / steps
     timed.launches = (launches_of() - n0) if launches_of else 0
     return R.reduce(ms, "max"), t0, t1
 
@@ -406,19 +455,31 @@ def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_
     block = F // sub
     if sub % 2 or F % sub or sub < 10:
         raise SystemExit("bench.py: --frames must be even (and at least 10)")
-    pv = PartitionedVideo(R, args, W, H, F, sub, block, True, tag + "r", seed)
+    # `inflight` videos are in flight at a time (independent instances, one host thread each): the pyramids of the next
+    # video run beside the last solves and warps of the previous one
+    inflight = max(1, args.inflight)
+    pvs = []
+    for i in range(inflight):
+        pvs.append(PartitionedVideo(R, args, W, H, F, sub, block, True, tag + "r%d" % i, seed, share=pvs[0] if i else None))
+    pv = pvs[0]
     ps = pv.ps
-    ps.upload_resident(pv.frames.ctypes.data, W * 3, pv.frame_bytes)
-    ps.synchronize()
-    out_dev = torch.empty((max(ps.outputs, 1), ps.out_h, ps.out_w, 3), dtype=torch.uint8, device="cuda")
+    outs_dev = []
+    for q in pvs:
+        q.ps.upload_resident(q.frames.ctypes.data, W * 3, q.frame_bytes)
+        q.ps.synchronize()
+        outs_dev.append(torch.empty((max(ps.outputs, 1), ps.out_h, ps.out_w, 3), dtype=torch.uint8, device="cuda"))
 
-    def step_resident():
-        for _ in range(passes):
-            k = ps.stabilize_ptr(None, 0, 0, out_dev.data_ptr(), capi.VS_MEM_DEVICE)
-            assert k == ps.outputs, k
+    def make_step(q, out):
+        def step_resident():
+            k = q.ps.stabilize_ptr(None, 0, 0, out.data_ptr(), capi.VS_MEM_DEVICE)
+            assert k == q.ps.outputs, k
+        return step_resident
 
     sampler = ClockSampler(R.local) if (R.rank == 0 and profile) else None
-    ms, t0, t1 = timed(R, pv.stream, step_resident, steps, warmup, lambda: ps.launches)
+    # a step is `passes` videos; they are handed out one by one to the instances
+    ms, t0, t1 = timed_inflight(R, [q.stream for q in pvs], [make_step(q, o) for q, o in zip(pvs, outs_dev)], steps * passes,
+                                warmup * passes, lambda: sum(q.ps.launches for q in pvs))
+    ms *= passes
     res["ms_per_step"] = ms
     res["launches"] = timed.launches
     res["clocks"] = sampler.stop(t0, t1) if sampler else None
@@ -433,9 +494,11 @@ def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_
     n_own, n_local, n_out = int((~ps.local_is_halo).sum()), len(ps.local_frames), int(ps.outputs)
     res["per_rank"] = {"frames": n_local, "keyframes": int((ps.local_frames % 2 == 1).sum()),
                        "pairs": n_own - (1 if R.rank == 0 else 0), "warped": n_out}
-    del out_dev
-    pv.ps.close()
-    del pv
+    res["videos_in_flight"] = inflight
+    del outs_dev
+    for q in pvs:
+        q.ps.close()
+    del pvs, pv, ps
     torch.cuda.empty_cache()
 
     # ---- per-kernel CUDA-event times over a second timed region: the rank's chunk as ONE sub-chunk, every stage one
@@ -474,22 +537,30 @@ def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_
 
     # ---- end to end: host frames in, host frames out, copies inside the timed region; sub-chunks interleaved over the ranks
     if e2e_steps > 0:
-        pe = PartitionedVideo(R, args, W, H, F, e2e_sub, 1, False, tag + "s", seed)
-        out_host = torch.empty((max(pe.ps.outputs, 1), pe.ps.out_h, pe.ps.out_w, 3), dtype=torch.uint8, pin_memory=True)
+        pes = []
+        for i in range(inflight):
+            pes.append(PartitionedVideo(R, args, W, H, F, e2e_sub, 1, False, tag + "s%d" % i, seed, share=pes[0] if i else None))
+        pe = pes[0]
+        outs_host = [torch.empty((max(pe.ps.outputs, 1), pe.ps.out_h, pe.ps.out_w, 3), dtype=torch.uint8, pin_memory=True)
+                     for _ in pes]
 
-        def step_e2e():
-            k = pe.ps.stabilize_ptr(pe.frames.ctypes.data, W * 3, pe.frame_bytes, out_host.data_ptr(), capi.VS_MEM_HOST)
-            assert k == pe.ps.outputs, k
+        def make_e2e(q, out):
+            def step_e2e():
+                k = q.ps.stabilize_ptr(q.frames.ctypes.data, W * 3, q.frame_bytes, out.data_ptr(), capi.VS_MEM_HOST)
+                assert k == q.ps.outputs, k
+            return step_e2e
 
-        e2e_ms, _, _ = timed(R, pe.stream, step_e2e, e2e_steps, 1)
+        e2e_ms, _, _ = timed_inflight(R, [q.stream for q in pes], [make_e2e(q, o) for q, o in zip(pes, outs_host)], e2e_steps, 1)
         h2d = R.reduce(pe.h2d_bytes, "sum")
         d2h = R.reduce(pe.d2h_bytes + (len(pe.ps.local_frames)) * 36, "sum")
         res["e2e"] = {"value": R.world * F / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                       "ms_per_step": e2e_ms, "frames_per_step": R.world * F, "sub_chunk_frames": e2e_sub,
                       "h2d_gbs": h2d / (e2e_ms / 1e3) / 1e9, "d2h_gbs": d2h / (e2e_ms / 1e3) / 1e9}
-        del out_host
-        pe.ps.close()
-        del pe
+        res["e2e"]["videos_in_flight"] = inflight
+        del outs_host
+        for q in pes:
+            q.ps.close()
+        del pes, pe
         torch.cuda.empty_cache()
     return res
 
@@ -612,6 +683,7 @@ def run_gpu_arm(args):
         "dtype": "u8/f32/f64", "data": "synthetic",
         "config": dict(workload_config(args, world), videos_per_step=args.passes, frames_per_step=main["frames_per_step"],
                        sub_chunk_frames=main["sub"], sub_chunks_per_rank=main["block"], host_threads_per_rank=main["host_threads"],
+                       videos_in_flight=main["videos_in_flight"],
                        kernel_times="`kernels` and `roofline` come from a second timed region with a rank's chunk as one sub-chunk, "
                                     "every stage one launch, back to back on one stream; `value` runs the chunk as %d sub-chunks "
                                     "whose solves overlap the other stages" % main["block"]),
@@ -644,6 +716,7 @@ def main():
     ap.add_argument("--frames-4k", type=int, default=120, help="frames per GPU of the 4K extra record")
     ap.add_argument("--crop", type=int, default=0)
     ap.add_argument("--passes", type=int, default=15, help="videos per step (device-resident number)")
+    ap.add_argument("--inflight", type=int, default=2, help="videos in flight at a time (independent stabilizer instances)")
     ap.add_argument("--e2e-sub", type=int, default=16, help="sub-chunk (frames) of the host-streamed partition")
     ap.add_argument("--cpu-threads", type=int, default=0, help="CPU worker threads (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
