@@ -316,12 +316,12 @@ void vo_image_warp(const uint8_t* in, int iw, int ih, const double T[4],
 // in the reference (its bgr_image_warp generator is gone): they are defined here, and in
 // the kernels alike, for the interpolation sweep (BASELINE.json configs[4]).  Mode 1 is the
 // same exact integer bilinear on a finer grid (16 position bits, 1/256-pixel weights); mode
-// 2 is a 4 x 4 Lanczos-2 on that grid with tabulated Q14 weights (64 fractions), integer too.
+// 2 is a 4 x 4 Lanczos-2 on that grid with tabulated Q11 weights (64 fractions), integer too.
 static inline long rint_he(double v) { return std::lrint(v); } // round-half-even (default FE mode)
 
-// Q14 Lanczos-2 weights of the 64 fractions q/64 for the taps at offsets -1, 0, 1, 2: lanczos2(t - f) with the reference's
+// Q11 Lanczos-2 weights of the 64 fractions q/64 for the taps at offsets -1, 0, 1, 2: lanczos2(t - f) with the reference's
 // polynomial (generators.cpp:31-47) in double, normalised; the rounding residue goes to the largest weight so that every
-// row sums to exactly 16384.
+// row sums to exactly 2048.
 void vo_lanczos_table(int16_t* tab /* [64][4] */)
 {
     for (int q = 0; q < 64; q++) {
@@ -341,11 +341,11 @@ void vo_lanczos_table(int16_t* tab /* [64][4] */)
         }
         int iw[4], isum = 0, big = 0;
         for (int t = 0; t < 4; t++) {
-            iw[t] = (int)std::lrint(wgt[t] / sum * 16384.0);
+            iw[t] = (int)std::lrint(wgt[t] / sum * 2048.0);
             isum += iw[t];
             if (iw[t] > iw[big]) big = t;
         }
-        iw[big] += 16384 - isum;
+        iw[big] += 2048 - isum;
         for (int t = 0; t < 4; t++) tab[q * 4 + t] = (int16_t)iw[t];
     }
 }
@@ -411,9 +411,9 @@ void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uin
         return;
     }
 
-    // Mode 2: Lanczos-2 (4 x 4 taps) on the same 16.16 grid, weights from a table of 64 fractions in Q14 (the reference's
-    // lanczos2 polynomial, generators.cpp:31-47, normalised to sum 16384), exact integer arithmetic: the vertical sums of
-    // the four source columns first (Q14, then >> 7), the horizontal sum of those (Q21), rounded and clamped.
+    // Mode 2: Lanczos-2 (4 x 4 taps) on the same 16.16 grid, weights from a table of 64 fractions in Q11 (the reference's
+    // lanczos2 polynomial, generators.cpp:31-47, normalised to sum 2048), exact integer arithmetic: the vertical sums of
+    // the four source columns first (Q11), the horizontal sum of those (Q22; |sum| < 1.4e9 fits 32 bits), rounded and clamped.
     {
         const int P = 16, W = 6;
         const double SCALE = (double)(1 << P);
@@ -431,7 +431,7 @@ void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uin
                 const int16_t* wy = tab[(sfy >> (P - W)) & 63];
                 uint8_t* d = dst + ((size_t)yo * ow + xo) * 3;
                 for (int c = 0; c < 3; c++) {
-                    int hsum = 1 << 20;
+                    int hsum = 1 << 21;
                     for (int t = 0; t < 4; t++) {
                         int v = 0;
                         for (int r = 0; r < 4; r++) {
@@ -440,9 +440,9 @@ void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uin
                             else if (xx >= 0 && xx < w && yy >= 0 && yy < h) p = src[((size_t)yy * w + xx) * 3 + c];
                             v += (int)wy[r] * p;
                         }
-                        hsum += (int)wx[t] * (v >> 7);
+                        hsum += (int)wx[t] * v;
                     }
-                    d[c] = (uint8_t)clampi(hsum >> 21, 0, 255);
+                    d[c] = (uint8_t)clampi(hsum >> 22, 0, 255);
                 }
             }
         }

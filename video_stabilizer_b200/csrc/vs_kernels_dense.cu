@@ -1034,25 +1034,27 @@ k_bgr_warp_cv_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
 
 // ------------------------------------------------------------------ BGR warp, Lanczos-2, row groups on the raw box
 // 4 x 4 Lanczos-2 on the 16.16 grid, exact integer arithmetic (the mode has no counterpart upstream; the oracle defines it
-// the same way): weights of the 64 fractions q/64 in Q14 from a table; per pixel and channel the vertical sums of the four
-// source columns (Q14, >> 7), then their horizontal sum (Q21), rounded, clamped.  Same skeleton as k_bgr_warp_cv_rows:
-// 128 x 24 output tile, raw source box by one TMA load (160 pixels x 32 rows), a thread owns four consecutive pixels of a
-// row, a warp walks down six rows, the tile leaves by one TMA store.  A "regular" group — consecutive source columns, one
-// source row quadruple, one vertical fraction, which is what the near-identity transforms of a stabiliser give almost
-// everywhere — shares its vertical sums: the 7 source pixels x 3 channels it touches are 21 sums for 4 output pixels
-// instead of 48.  A row of the window is 7 aligned shared-memory words + 6 funnel shifts; two rows are interleaved by
-// PRMT into (row r, row r+1) byte pairs and a sum is two IDP.2A (signed 16-bit weights x unsigned bytes).  Everything
-// else (groups that are not regular, tiles whose box does not fit) goes pixel by pixel through lz_pixel.
+// the same way): weights of the 64 fractions q/64 in Q11 from a table; per pixel and channel the vertical sums of the four
+// source columns (Q11), then their horizontal sum (Q22: at most 1.4e9 in magnitude, no intermediate shift), rounded,
+// clamped.  Same skeleton as k_bgr_warp_cv_rows: 128 x 24 output tile, raw source box by one TMA load (160 pixels x 32
+// rows), a thread owns four consecutive pixels of a row, a warp walks down six rows, the tile leaves by one TMA store.
+// A row of the window is 7 aligned shared-memory words + 6 funnel shifts; two rows are interleaved by PRMT into byte
+// pairs and a vertical sum is two IDP.2A (signed 16-bit weight pairs x unsigned bytes).  The four window rows live in a
+// ring of two interleaved pairs: from one output row to the next a regular group normally moves down by exactly one
+// source row at the same column, so only the new bottom row is loaded and merged (by PRMT) into the pair that held the
+// old top row, and the weight pairs are taken from the table rotated by the ring's phase (warp-uniform).  A "regular" group — consecutive source columns, one source
+// row quadruple — whose pixels also share one vertical fraction shares its vertical sums: the 7 source pixels x 3
+// channels it touches are 21 sums for 4 output pixels instead of 48.  Everything else (groups that are not regular,
+// tiles whose box does not fit) goes pixel by pixel through lz_pixel.
 constexpr int LZ_BOX_ROWS = VS_WARP_LZ_BOX_ROWS;
 constexpr int LZ_RAW_BYTES = WG_RAW_PITCH * LZ_BOX_ROWS;             // 15360: the TMA transaction size
 constexpr int LZ_OUT_OFF = (LZ_RAW_BYTES + 64 + 127) / 128 * 128;
 constexpr int LZ_LIST_OFF = LZ_OUT_OFF + WG_OUT_ROW_WORDS * 4 * WG_H;
 constexpr int LZ_TAB_OFF = LZ_LIST_OFF + WG_H * 32 * 2;
-constexpr int LZ_SMEM_BYTES = LZ_TAB_OFF + 64 * 16 + 64 * 8;
+constexpr int LZ_SMEM_BYTES = LZ_TAB_OFF + 64 * 16 + 4 * 64 * 8;
 
 struct LzTables {
-    int32_t wx[64][4];       // Q14 weights of taps -1, 0, 1, 2 for fraction q / 64
-    uint32_t wy[64][2];      // the same as signed 16-bit pairs: w0 | w1 << 16, w2 | w3 << 16
+    int32_t wx[64][4];       // Q11 weights of taps -1, 0, 1, 2 for fraction q / 64
 };
 
 __device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c)
@@ -1068,6 +1070,20 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c)
     return d;
 }
 
+// shared-memory loads by 32-bit shared address (the weight tables: keeps the lookups off generic addressing)
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t addr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 // one pixel, any position, through a byte fetcher tap(x, y, c): returns B | G << 8 | R << 16
 template <typename TAP>
 __device__ __forceinline__ uint32_t lz_pixel(const int32_t (*wxt)[4], int sfx, int sfy, TAP tap)
@@ -1078,15 +1094,15 @@ __device__ __forceinline__ uint32_t lz_pixel(const int32_t (*wxt)[4], int sfx, i
     uint32_t out = 0;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        int hsum = 1 << 20;
+        int hsum = 1 << 21;
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             int v = 0;
 #pragma unroll
             for (int r = 0; r < 4; r++) v += wy[r] * (int)tap(ix - 1 + t, iy - 1 + r, c);
-            hsum += wx[t] * (v >> 7);
+            hsum += wx[t] * v;
         }
-        out |= (uint32_t)__vimin_s32_relu(hsum >> 21, 255) << (8 * c);
+        out |= (uint32_t)__vimin_s32_relu(hsum >> 22, 255) << (8 * c);
     }
     return out;
 }
@@ -1105,7 +1121,8 @@ k_bgr_warp_lz_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
     uint32_t* const O = lz_smem + LZ_OUT_OFF / 4;                  // [WG_H][WG_OUT_ROW_WORDS]
     uint16_t* const LIST = reinterpret_cast<uint16_t*>(lz_smem + LZ_LIST_OFF / 4);
     int32_t (*const WX)[4] = reinterpret_cast<int32_t (*)[4]>(lz_smem + LZ_TAB_OFF / 4);
-    uint32_t (*const WY)[2] = reinterpret_cast<uint32_t (*)[2]>(lz_smem + LZ_TAB_OFF / 4 + 64 * 4);
+    // vertical weight pairs for the four phases of the row ring: slot s holds window row (s - phase) & 3
+    uint2* const WY = reinterpret_cast<uint2*>(lz_smem + LZ_TAB_OFF / 4 + 64 * 4);      // [4][64]
     __shared__ int2 sXY0[WG_H];                                    // row terms relative to the box origin
     __shared__ int sCount;
     __shared__ __align__(8) unsigned long long tma_bar;
@@ -1136,8 +1153,18 @@ k_bgr_warp_lz_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
                 : "memory");
         }
     }
-    for (int i = tid; i < 64 * 4; i += WG_THREADS) WX[i >> 2][i & 3] = tables.wx[i >> 2][i & 3];
-    for (int i = tid; i < 64 * 2; i += WG_THREADS) WY[i >> 1][i & 1] = tables.wy[i >> 1][i & 1];
+    if (tid < 64) {
+        // one 16-byte constant load per fraction: the horizontal weights as they are, the vertical ones as 16-bit pairs in
+        // the four rotations of the row ring
+        const int4 wq = *reinterpret_cast<const int4*>(tables.wx[tid]);
+        *reinterpret_cast<int4*>(WX[tid]) = wq;
+        const uint32_t w0 = (uint32_t)wq.x & 0xffffu, w1 = (uint32_t)wq.y & 0xffffu, w2 = (uint32_t)wq.z & 0xffffu, w3 = (uint32_t)wq.w & 0xffffu;
+        WY[0 * 64 + tid] = make_uint2(w0 | w1 << 16, w2 | w3 << 16);      // slots hold rows 0 1 2 3
+        WY[1 * 64 + tid] = make_uint2(w3 | w0 << 16, w1 | w2 << 16);      //                 3 0 1 2
+        WY[2 * 64 + tid] = make_uint2(w2 | w3 << 16, w0 | w1 << 16);      //                 2 3 0 1
+        WY[3 * 64 + tid] = make_uint2(w1 | w2 << 16, w3 | w0 << 16);      //                 1 2 3 0
+    }
+    const uint32_t wx_s = (uint32_t)__cvta_generic_to_shared(WX), wy_s = (uint32_t)__cvta_generic_to_shared(WY);
     const int orgx = staged ? tile.z << P : 0, orgy = staged ? tile.y << P : 0;
     if (tid < WG_H) {
         const int2 xy = __ldg(XY + min(tid, th - 1));
@@ -1157,8 +1184,12 @@ k_bgr_warp_lz_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
                          : "=r"(done) : "r"(bar) : "memory");
             if (!done && ++spins > (1u << 24)) __trap();   // a lost transaction must fail loudly, not hang the GPU
         }
+        // the ring: slots 0, 1 interleaved in a01 / b01 and slots 2, 3 in a23 / b23 (21 stream bytes of a row = 6 words)
+        uint32_t a01[6], b01[6], a23[6], b23[6];
+        uint32_t prev_byte = 0xffffffffu;         // window offset of this thread's previous row when that row was regular
 #pragma unroll 1
         for (int k = 0; k < WG_ROWS_PER_WARP; k++) {
+            const int phase = k & 3;              // slot of the window's top row (the same for the whole warp)
             const int r = warp * WG_ROWS_PER_WARP + k;
             if (r >= th) break;
             const int2 xy0 = sXY0[r];
@@ -1176,58 +1207,81 @@ k_bgr_warp_lz_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
                 const uint32_t byte = (uint32_t)((y0 >> P) - 1) * (uint32_t)WG_RAW_PITCH + (uint32_t)((x0 >> P) - 1) * 3u;
                 const uint32_t* const p = RAW + (byte >> 2);
                 const uint32_t sh = byte << 3;                        // funnel shifts use the low five bits: 8 (byte & 3)
-                // the 21 source bytes (7 pixels x BGR) of the four rows, interleaved as (row 0, row 1) and (row 2, row 3) byte pairs
-                uint32_t a01[6], b01[6], a23[6], b23[6];
+                // window row rr (0 = top) as six byte-aligned words
+                auto load_row = [&](int rr, uint32_t* u) {
 #pragma unroll
-                for (int q = 0; q < 6; q++) {
-                    uint32_t u[4];
+                    for (int q = 0; q < 6; q++)
+                        u[q] = __funnelshift_r(p[rr * WG_BOX_WORDS + q], p[rr * WG_BOX_WORDS + q + 1], sh);
+                };
+                if (k > 0 && byte == prev_byte + (uint32_t)WG_RAW_PITCH) {
+                    // one source row down at the same column: the new bottom row replaces the old top row in its pair
+                    uint32_t u[6];
+                    load_row(3, u);
+                    const int slot = (phase + 3) & 3;
+                    const uint32_t selA = (slot & 1) ? 0x5240u : 0x3514u, selB = (slot & 1) ? 0x7260u : 0x3716u;   // odd / even bytes of the pair
+                    if (slot < 2) {
 #pragma unroll
-                    for (int rr = 0; rr < 4; rr++)
-                        u[rr] = __funnelshift_r(p[rr * WG_BOX_WORDS + q], p[rr * WG_BOX_WORDS + q + 1], sh);
-                    a01[q] = __byte_perm(u[0], u[1], 0x5140); b01[q] = __byte_perm(u[0], u[1], 0x7362);
-                    a23[q] = __byte_perm(u[2], u[3], 0x5140); b23[q] = __byte_perm(u[2], u[3], 0x7362);
+                        for (int q = 0; q < 6; q++) { a01[q] = __byte_perm(a01[q], u[q], selA); b01[q] = __byte_perm(b01[q], u[q], selB); }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 6; q++) { a23[q] = __byte_perm(a23[q], u[q], selA); b23[q] = __byte_perm(b23[q], u[q], selB); }
+                    }
+                } else {
+#pragma unroll
+                    for (int pr = 0; pr < 2; pr++) {                  // the rows of slots 2 pr and 2 pr + 1
+                        uint32_t ue[6], uo[6];
+                        load_row((2 * pr - phase) & 3, ue);
+                        load_row((2 * pr + 1 - phase) & 3, uo);
+#pragma unroll
+                        for (int q = 0; q < 6; q++) {
+                            (pr ? a23 : a01)[q] = __byte_perm(ue[q], uo[q], 0x5140);
+                            (pr ? b23 : b01)[q] = __byte_perm(ue[q], uo[q], 0x7362);
+                        }
+                    }
                 }
-                // vertical sum of stream byte i (Q14 >> 7) under the weight pairs wy
+                prev_byte = byte;
+                // vertical sum of stream byte i (Q11) under the weight pairs wy of this phase
                 auto vsum = [&](int i, const uint2 wy) -> int {
                     const int q = i >> 2;
                     switch (i & 3) {
-                    case 0: return dp2a_lo_su(wy.y, a23[q], dp2a_lo_su(wy.x, a01[q], 0)) >> 7;
-                    case 1: return dp2a_hi_su(wy.y, a23[q], dp2a_hi_su(wy.x, a01[q], 0)) >> 7;
-                    case 2: return dp2a_lo_su(wy.y, b23[q], dp2a_lo_su(wy.x, b01[q], 0)) >> 7;
-                    default: return dp2a_hi_su(wy.y, b23[q], dp2a_hi_su(wy.x, b01[q], 0)) >> 7;
+                    case 0: return dp2a_lo_su(wy.y, a23[q], dp2a_lo_su(wy.x, a01[q], 0));
+                    case 1: return dp2a_hi_su(wy.y, a23[q], dp2a_hi_su(wy.x, a01[q], 0));
+                    case 2: return dp2a_lo_su(wy.y, b23[q], dp2a_lo_su(wy.x, b01[q], 0));
+                    default: return dp2a_hi_su(wy.y, b23[q], dp2a_hi_su(wy.x, b01[q], 0));
                     }
                 };
+                const uint32_t wyp = wy_s + (uint32_t)phase * 512u;
                 const int xs[4] = {x0, x1, x2, x3};
                 const int ys[4] = {y0, y1, y2, y3};
                 uint32_t px[4];
                 if (shared_wy) {
-                    const uint2 wy = *reinterpret_cast<const uint2*>(WY[((uint32_t)y0 >> 10) & 63u]);
+                    const uint2 wy = lds_u2(wyp + ((((uint32_t)y0 >> 10) & 63u) << 3));
                     int vs[21];
 #pragma unroll
                     for (int i = 0; i < 21; i++) vs[i] = vsum(i, wy);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const int4 wx = *reinterpret_cast<const int4*>(WX[((uint32_t)xs[j] >> 10) & 63u]);
+                        const int4 wx = lds_i4(wx_s + ((((uint32_t)xs[j] >> 10) & 63u) << 4));
                         uint32_t o = 0;
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
                             const int hsum = wx.x * vs[3 * j + c] + wx.y * vs[3 * j + 3 + c] + wx.z * vs[3 * j + 6 + c] +
-                                             wx.w * vs[3 * j + 9 + c] + (1 << 20);
-                            o |= (uint32_t)__vimin_s32_relu(hsum >> 21, 255) << (8 * c);
+                                             wx.w * vs[3 * j + 9 + c] + (1 << 21);
+                            o |= (uint32_t)__vimin_s32_relu(hsum >> 22, 255) << (8 * c);
                         }
                         px[j] = o;
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint2 wy = *reinterpret_cast<const uint2*>(WY[((uint32_t)ys[j] >> 10) & 63u]);
-                        const int4 wx = *reinterpret_cast<const int4*>(WX[((uint32_t)xs[j] >> 10) & 63u]);
+                        const uint2 wy = lds_u2(wyp + ((((uint32_t)ys[j] >> 10) & 63u) << 3));
+                        const int4 wx = lds_i4(wx_s + ((((uint32_t)xs[j] >> 10) & 63u) << 4));
                         uint32_t o = 0;
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
                             const int hsum = wx.x * vsum(3 * j + c, wy) + wx.y * vsum(3 * j + 3 + c, wy) + wx.z * vsum(3 * j + 6 + c, wy) +
-                                             wx.w * vsum(3 * j + 9 + c, wy) + (1 << 20);
-                            o |= (uint32_t)__vimin_s32_relu(hsum >> 21, 255) << (8 * c);
+                                             wx.w * vsum(3 * j + 9 + c, wy) + (1 << 21);
+                            o |= (uint32_t)__vimin_s32_relu(hsum >> 22, 255) << (8 * c);
                         }
                         px[j] = o;
                     }
@@ -1236,8 +1290,9 @@ k_bgr_warp_lz_rows(const __grid_constant__ CUtensorMap src_map, const __grid_con
                 o[0] = __byte_perm(px[0], px[1], 0x4210);
                 o[1] = __byte_perm(px[1], px[2], 0x5421);
                 o[2] = __byte_perm(px[2], px[3], 0x6542);
-            } else if (4 * lane < tw) {
-                LIST[atomicAdd(&sCount, 1)] = (uint16_t)(r * 32 + lane);
+            } else {
+                prev_byte = 0xffffffffu;
+                if (4 * lane < tw) LIST[atomicAdd(&sCount, 1)] = (uint16_t)(r * 32 + lane);
             }
         }
         __syncthreads();
@@ -1462,8 +1517,8 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
     return vs_set_error(ctx, VS_ERR_INVALID, "bgr_warp: the Lanczos-2 mode runs through vsk_bgr_warp_lz");
 }
 
-// Q14 Lanczos-2 weights of the 64 fractions q / 64 (taps at -1, 0, 1, 2): the reference's lanczos2 polynomial
-// (generators.cpp:31-47) in double, normalised; the rounding residue goes to the largest weight (rows sum to 16384)
+// Q11 Lanczos-2 weights of the 64 fractions q / 64 (taps at -1, 0, 1, 2): the reference's lanczos2 polynomial
+// (generators.cpp:31-47) in double, normalised; the rounding residue goes to the largest weight (rows sum to 2048)
 static const LzTables& lz_tables()
 {
     static const LzTables t = [] {
@@ -1485,14 +1540,12 @@ static const LzTables& lz_tables()
             }
             int iw[4], isum = 0, big = 0;
             for (int k = 0; k < 4; k++) {
-                iw[k] = (int)lrint(wgt[k] / sum * 16384.0);
+                iw[k] = (int)lrint(wgt[k] / sum * 2048.0);
                 isum += iw[k];
                 if (iw[k] > iw[big]) big = k;
             }
-            iw[big] += 16384 - isum;
+            iw[big] += 2048 - isum;
             for (int k = 0; k < 4; k++) r.wx[q][k] = iw[k];
-            r.wy[q][0] = (uint32_t)(uint16_t)(int16_t)iw[0] | ((uint32_t)(uint16_t)(int16_t)iw[1] << 16);
-            r.wy[q][1] = (uint32_t)(uint16_t)(int16_t)iw[2] | ((uint32_t)(uint16_t)(int16_t)iw[3] << 16);
         }
         return r;
     }();
