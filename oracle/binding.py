@@ -131,24 +131,24 @@ def phase_correlate_u8(a, b, fast=False):
     return out
 
 
-def pyr_down(img, ow=None, oh=None):
+def pyr_down(img, ow=None, oh=None, fast=False):
     img = np.ascontiguousarray(img, np.uint8)
     h, w = img.shape
     ow = w // 2 if ow is None else ow
     oh = h // 2 if oh is None else oh
     out = np.empty((oh, ow), np.uint8)
-    load().vo_pyr_down(_p(img), w, h, _p(out), ow, oh)
+    load(fast).vo_pyr_down(_p(img), w, h, _p(out), ow, oh)
     return out
 
 
-def grad_xy(img, ow=None, oh=None):
+def grad_xy(img, ow=None, oh=None, fast=False):
     img = np.ascontiguousarray(img, np.uint8)
     h, w = img.shape
     ow = w if ow is None else ow
     oh = h if oh is None else oh
     gx = np.empty((oh, ow), np.float32)
     gy = np.empty((oh, ow), np.float32)
-    load().vo_grad_xy(_p(img), w, h, _p(gx), _p(gy), ow, oh)
+    load(fast).vo_grad_xy(_p(img), w, h, _p(gx), _p(gy), ow, oh)
     return gx, gy
 
 

@@ -26,7 +26,14 @@
 #include <cstring>
 #include <deque>
 #include <vector>
+#ifdef VS_ORACLE_FAST
+#include <immintrin.h>
+#endif
 
+// VS_ORACLE_FAST (the *_fast.so builds, which only ever serve as the TIMED CPU baseline): pyr_down, grad_xy and the cv-exact
+// BGR warp are computed by vectorisable / AVX2 forms that produce the same bytes as the restatements below
+// (tests/test_oracle_golden.py::test_fast_kernels_equal_the_restatement) — the reference's Halide schedules and OpenCV's
+// warpAffine are vectorised too, so a scalar restatement would flatter the GPU arm.
 namespace {
 
 inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -108,6 +115,34 @@ void vo_bgr2gray(const uint8_t* bgr, int w, int h, uint8_t* gray)
 // intermediate is exactly representable so this equals (sum k_j k_i p) >> 8.
 void vo_pyr_down(const uint8_t* in, int iw, int ih, uint8_t* out, int ow, int oh)
 {
+#ifdef VS_ORACLE_FAST
+    // every intermediate of the f32 form is an exactly representable dyadic number, so it equals
+    // (sum_j sum_i k_j k_i in) >> 8 in integers: vertical [1 4 6 4 1] sums of whole rows, then the horizontal sums
+    std::vector<uint16_t> col((size_t)iw);
+    for (int y = 0; y < oh; y++) {
+        const uint8_t* r0 = in + (size_t)clampi(2 * y - 2, 0, ih - 1) * iw;
+        const uint8_t* r1 = in + (size_t)clampi(2 * y - 1, 0, ih - 1) * iw;
+        const uint8_t* r2 = in + (size_t)clampi(2 * y, 0, ih - 1) * iw;
+        const uint8_t* r3 = in + (size_t)clampi(2 * y + 1, 0, ih - 1) * iw;
+        const uint8_t* r4 = in + (size_t)clampi(2 * y + 2, 0, ih - 1) * iw;
+        for (int x = 0; x < iw; x++)
+            col[x] = (uint16_t)(r0[x] + 4 * r1[x] + 6 * r2[x] + 4 * r3[x] + r4[x]);
+        uint8_t* o = out + (size_t)y * ow;
+        const int x_lo = 1, x_hi = std::min(ow, (iw - 3) / 2 + 1);      // 2x - 2 >= 0 and 2x + 2 <= iw - 1
+        for (int x = 0; x < ow; x++) {
+            if (x >= x_lo && x < x_hi) continue;
+            const uint32_t v = col[clampi(2 * x - 2, 0, iw - 1)] + 4u * col[clampi(2 * x - 1, 0, iw - 1)] + 6u * col[clampi(2 * x, 0, iw - 1)] +
+                               4u * col[clampi(2 * x + 1, 0, iw - 1)] + col[clampi(2 * x + 2, 0, iw - 1)];
+            o[x] = (uint8_t)(v >> 8);
+        }
+        for (int x = x_lo; x < x_hi; x++) {
+            const uint16_t* cc = col.data() + 2 * x;
+            const uint32_t v = cc[-2] + 4u * cc[-1] + 6u * cc[0] + 4u * cc[1] + cc[2];
+            o[x] = (uint8_t)(v >> 8);
+        }
+    }
+    return;
+#endif
     const float c[5] = {1.0f / 16, 4.0f / 16, 6.0f / 16, 4.0f / 16, 1.0f / 16};
     for (int y = 0; y < oh; y++) {
         for (int x = 0; x < ow; x++) {
@@ -134,6 +169,23 @@ void vo_pyr_down(const uint8_t* in, int iw, int ih, uint8_t* out, int ow, int oh
 // generators.cpp:202-224 — central differences * 0.5 on repeat-edge input.
 void vo_grad_xy(const uint8_t* in, int iw, int ih, float* gx, float* gy, int ow, int oh)
 {
+#ifdef VS_ORACLE_FAST
+    if (ow <= iw && oh <= ih) {      // the same operations, rows with unclamped interiors (vectorisable)
+        for (int y = 0; y < oh; y++) {
+            const uint8_t* r = in + (size_t)y * iw;
+            const uint8_t* rp = in + (size_t)clampi(y + 1, 0, ih - 1) * iw;
+            const uint8_t* rm = in + (size_t)clampi(y - 1, 0, ih - 1) * iw;
+            float* ox = gx + (size_t)y * ow;
+            float* oy = gy + (size_t)y * ow;
+            for (int x = 0; x < ow; x++) oy[x] = 0.5f * ((float)rp[x] - (float)rm[x]);
+            const int x_hi = std::min(ow, iw - 1);
+            if (ow > 0) ox[0] = 0.5f * ((float)r[clampi(1, 0, iw - 1)] - (float)r[0]);
+            for (int x = 1; x < x_hi; x++) ox[x] = 0.5f * ((float)r[x + 1] - (float)r[x - 1]);
+            for (int x = std::max(1, x_hi); x < ow; x++) ox[x] = 0.5f * ((float)r[clampi(x + 1, 0, iw - 1)] - (float)r[clampi(x - 1, 0, iw - 1)]);
+        }
+        return;
+    }
+#endif
     for (int y = 0; y < oh; y++) {
         for (int x = 0; x < ow; x++) {
             int yc = clampi(y, 0, ih - 1), xc = clampi(x, 0, iw - 1);
@@ -350,6 +402,54 @@ void vo_lanczos_table(int16_t* tab /* [64][4] */)
     }
 }
 
+#ifdef VS_ORACLE_FAST
+// Eight output pixels of one row whose 2 x 2 taps all lie inside the source: the integer arithmetic of the scalar loop in
+// AVX2 lanes (four 32-bit gathers of B G R x, per channel four multiply-adds).  Returns false when a pixel is not inside.
+__attribute__((target("avx2"))) static inline bool warp8_avx2(const uint8_t* src, int w, int h, const int* ad, const int* bd, int X0, int Y0,
+                                                              int P, int W, uint8_t* d)
+{
+    const __m256i sfx = _mm256_add_epi32(_mm256_set1_epi32(X0), _mm256_loadu_si256((const __m256i*)ad));
+    const __m256i sfy = _mm256_add_epi32(_mm256_set1_epi32(Y0), _mm256_loadu_si256((const __m256i*)bd));
+    const __m128i cP = _mm_cvtsi32_si128(P), cPW = _mm_cvtsi32_si128(P - W);
+    const __m256i sx = _mm256_sra_epi32(sfx, cP), sy = _mm256_sra_epi32(sfy, cP);
+    // inside: 0 <= sx, sx + 1 < w, 0 <= sy, sy + 2 < h (the bottom row pair is left to the scalar loop: a 32-bit gather of the
+    // frame's last pixel would read one byte past the buffer)
+    const __m256i bad = _mm256_or_si256(_mm256_or_si256(_mm256_cmpgt_epi32(_mm256_setzero_si256(), sx), _mm256_cmpgt_epi32(_mm256_add_epi32(sx, _mm256_set1_epi32(2)), _mm256_set1_epi32(w))),
+                                        _mm256_or_si256(_mm256_cmpgt_epi32(_mm256_setzero_si256(), sy), _mm256_cmpgt_epi32(_mm256_add_epi32(sy, _mm256_set1_epi32(3)), _mm256_set1_epi32(h))));
+    if (!_mm256_testz_si256(bad, bad)) return false;
+    const __m256i one = _mm256_set1_epi32(1 << W), msk = _mm256_set1_epi32((1 << W) - 1);
+    const __m256i fx = _mm256_and_si256(_mm256_sra_epi32(sfx, cPW), msk), fy = _mm256_and_si256(_mm256_sra_epi32(sfy, cPW), msk);
+    const __m256i gx = _mm256_sub_epi32(one, fx), gy = _mm256_sub_epi32(one, fy);
+    const __m256i w00 = _mm256_mullo_epi32(gx, gy), w10 = _mm256_mullo_epi32(fx, gy), w01 = _mm256_mullo_epi32(gx, fy), w11 = _mm256_mullo_epi32(fx, fy);
+    const __m256i off = _mm256_mullo_epi32(_mm256_add_epi32(_mm256_mullo_epi32(sy, _mm256_set1_epi32(w)), sx), _mm256_set1_epi32(3));
+    const int* base = (const int*)src;
+    const __m256i t00 = _mm256_i32gather_epi32(base, off, 1);
+    const __m256i t10 = _mm256_i32gather_epi32(base, _mm256_add_epi32(off, _mm256_set1_epi32(3)), 1);
+    const __m256i t01 = _mm256_i32gather_epi32(base, _mm256_add_epi32(off, _mm256_set1_epi32(3 * w)), 1);
+    const __m256i t11 = _mm256_i32gather_epi32(base, _mm256_add_epi32(off, _mm256_set1_epi32(3 * w + 3)), 1);
+    const __m256i half = _mm256_set1_epi32(1 << (2 * W - 1)), m8 = _mm256_set1_epi32(255);
+    const __m128i c2W = _mm_cvtsi32_si128(2 * W);
+    __m256i px = _mm256_setzero_si256();
+    for (int c = 0; c < 3; c++) {
+        const __m128i sh = _mm_cvtsi32_si128(8 * c);
+        __m256i v = _mm256_mullo_epi32(w00, _mm256_and_si256(_mm256_srl_epi32(t00, sh), m8));
+        v = _mm256_add_epi32(v, _mm256_mullo_epi32(w10, _mm256_and_si256(_mm256_srl_epi32(t10, sh), m8)));
+        v = _mm256_add_epi32(v, _mm256_mullo_epi32(w01, _mm256_and_si256(_mm256_srl_epi32(t01, sh), m8)));
+        v = _mm256_add_epi32(v, _mm256_mullo_epi32(w11, _mm256_and_si256(_mm256_srl_epi32(t11, sh), m8)));
+        v = _mm256_srl_epi32(_mm256_add_epi32(v, half), c2W);
+        px = _mm256_or_si256(px, _mm256_sll_epi32(v, sh));
+    }
+    // B G R x of four pixels per 128-bit lane -> 12 packed bytes per lane
+    const __m256i pk = _mm256_shuffle_epi8(px, _mm256_setr_epi8(0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1,
+                                                                0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1));
+    alignas(32) uint8_t o[32];
+    _mm256_store_si256((__m256i*)o, pk);
+    std::memcpy(d, o, 12);
+    std::memcpy(d + 12, o + 16, 12);
+    return true;
+}
+#endif
+
 // General form: forward 2x3 matrix M (as cv::warpAffine takes it), source sw x sh, destination window dw x dh whose pixel
 // (x, y) is output pixel (x + dx0, y + dy0) of the warp.  vo_warp_bgr below and the synthetic-clip renderer use it.
 void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uint8_t* dst, int ow, int oh, int dx0, int dy0,
@@ -380,6 +480,15 @@ void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uin
             int X0 = (int)rint_he((i01 * y + i02) * SCALE) + ROUND;
             int Y0 = (int)rint_he((i11 * y + i12) * SCALE) + ROUND;
             for (int xo = 0; xo < ow; xo++) {
+#ifdef VS_ORACLE_FAST
+                // (mode 1's weights reach 2^16 and its products 2^24: still inside 32 bits)
+                static const bool have_avx2 = __builtin_cpu_supports("avx2");
+                if (have_avx2 && xo + 8 <= ow &&
+                    warp8_avx2(src, w, h, adelta.data() + xo, bdelta.data() + xo, X0, Y0, P, W, dst + ((size_t)yo * ow + xo) * 3)) {
+                    xo += 7;
+                    continue;
+                }
+#endif
                 const int sfx = X0 + adelta[xo], sfy = Y0 + bdelta[xo];
                 const int sx = sfx >> P, sy = sfy >> P;
                 const int fx = (sfx >> (P - W)) & (one - 1), fy = (sfy >> (P - W)) & (one - 1);
