@@ -779,7 +779,7 @@ int vo_introselect_depth(const uint16_t* abs_delta, int n, int nth, int depth, u
 
 //------------------------------------------------------------------------------
 // cv::phaseCorrelate (alignment.cpp:374; OpenCV imgproc/src/phasecorr.cpp, not under /root/reference) restated
-// as a direct, separable DFT in f64 with every sum taken serially in ascending index order and no FMA — the
+// as a separable two-stage DFT in f64 (pc_dft below) with every sum taken serially in ascending index order and no FMA — the
 // canonical order the CUDA kernels reproduce bit for bit.  OpenCV runs its own f32 mixed-radix FFT: its ulps are
 // not reproduced, its result is (tests/golden/phase_correlate.npz pins shift and response against cv2 4.13 to 1e-4):
 //   M, N = getOptimalDFTSize(rows), (cols); zero padding on the right / bottom (copyMakeBorder);
@@ -806,45 +806,94 @@ static void pc_twiddles(int n, std::vector<double>& c, std::vector<double>& s)
     }
 }
 
+// Every 1-D transform of length L is evaluated in two stages (L = L1 L2, L1 the largest divisor of L with L1^2 <= L;
+// input index n = L2 n1 + n2, output index k = k1 + L1 k2):
+//     A[k1][n2]    = sum_{n1 < L1} x[L2 n1 + n2] W^(L2 n1 k1)        (terms beyond the valid length are skipped)
+//     B[k1][n2]    = A[k1][n2] W^(n2 k1)
+//     X[k1 + L1 k2] = sum_{n2 < L2} B[k1][n2] W^(L1 n2 k2)
+// with W^j = (c[j mod L], s[j mod L]) from the table (the conjugate for an inverse), every sum serial in ascending index
+// order, every product and sum individually rounded: L (L1 + L2) multiply-adds instead of L^2, and an order the kernels
+// (vs_phasecorr.cu) reproduce bit for bit.
+static void pc_split(int L, int& L1, int& L2)
+{
+    L1 = 1;
+    for (int d = 1; d * d <= L; d++)
+        if (L % d == 0) L1 = d;
+    L2 = L / L1;
+}
+
+// one transform: in[n] = (re, im) for n < valid at stride `is` (complex elements), zero beyond; out[k] for k < kout at
+// stride `os`; real_in: the input has no imaginary part (in points at doubles, stride `is` doubles); conj: inverse twiddles;
+// real_out: only the real parts are produced (out points at doubles)
+static void pc_dft(const double* in, size_t is, int valid, bool real_in, int L, const std::vector<double>& c, const std::vector<double>& s,
+                   bool conj, double* out, size_t os, int kout, bool real_out, std::vector<double>& B)
+{
+    int L1, L2;
+    pc_split(L, L1, L2);
+    B.resize((size_t)L * 2);
+    for (int k1 = 0; k1 < L1; k1++)
+        for (int n2 = 0; n2 < L2; n2++) {
+            double re = 0.0, im = 0.0;
+            const int step = (int)(((long long)L2 * k1) % L);
+            int j = 0;
+            for (int n1 = 0; n1 < L1; n1++) {
+                const int n = L2 * n1 + n2;
+                if (n < valid) {
+                    if (real_in) {
+                        const double x = in[(size_t)n * is];
+                        re = re + x * c[j];
+                        im = conj ? im - x * s[j] : im + x * s[j];
+                    } else {
+                        const double ar = in[(size_t)n * is * 2], ai = in[(size_t)n * is * 2 + 1];
+                        const double t1 = ar * c[j], t2 = ai * s[j], t3 = ar * s[j], t4 = ai * c[j];
+                        if (conj) { re = re + (t1 + t2); im = im + (t4 - t3); }
+                        else      { re = re + (t1 - t2); im = im + (t3 + t4); }
+                    }
+                }
+                j += step; if (j >= L) j -= L;
+            }
+            const int jt = (int)(((long long)n2 * k1) % L);
+            const double t1 = re * c[jt], t2 = im * s[jt], t3 = re * s[jt], t4 = im * c[jt];
+            if (conj) { B[((size_t)k1 * L2 + n2) * 2] = t1 + t2; B[((size_t)k1 * L2 + n2) * 2 + 1] = t4 - t3; }
+            else      { B[((size_t)k1 * L2 + n2) * 2] = t1 - t2; B[((size_t)k1 * L2 + n2) * 2 + 1] = t3 + t4; }
+        }
+    for (int k = 0; k < kout; k++) {
+        const int k1 = k % L1, k2 = k / L1;
+        double re = 0.0, im = 0.0;
+        const int step = (int)(((long long)L1 * k2) % L);
+        int j = 0;
+        for (int n2 = 0; n2 < L2; n2++) {
+            const double ar = B[((size_t)k1 * L2 + n2) * 2], ai = B[((size_t)k1 * L2 + n2) * 2 + 1];
+            const double t1 = ar * c[j], t2 = ai * s[j], t3 = ar * s[j], t4 = ai * c[j];
+            if (conj) { re = re + (t1 + t2); im = im + (t4 - t3); }
+            else      { re = re + (t1 - t2); im = im + (t3 + t4); }
+            j += step; if (j >= L) j -= L;
+        }
+        if (real_out) out[(size_t)k * os] = re;
+        else { out[(size_t)k * os * 2] = re; out[(size_t)k * os * 2 + 1] = im; }
+    }
+}
+
 // forward transform of a real w x h image padded to N x M: G[m][k], k < N/2+1 (interleaved re, im)
 static void pc_forward(const float* img, int64_t stride, int w, int h, int M, int N,
                        const std::vector<double>& cN, const std::vector<double>& sN,
                        const std::vector<double>& cM, const std::vector<double>& sM, std::vector<double>& G)
 {
     const int Kh = N / 2 + 1;
-    std::vector<double> F((size_t)h * Kh * 2);
-    for (int r = 0; r < h; r++)
-        for (int k = 0; k < Kh; k++) {
-            double re = 0.0, im = 0.0;
-            int j = 0;
-            for (int n = 0; n < w; n++) {
-                const double x = (double)img[(size_t)r * stride + n];
-                re = re + x * cN[j];
-                im = im + x * sN[j];
-                j += k; if (j >= N) j -= N;
-            }
-            F[((size_t)r * Kh + k) * 2] = re; F[((size_t)r * Kh + k) * 2 + 1] = im;
-        }
+    std::vector<double> F((size_t)h * Kh * 2), row((size_t)w), B;
+    for (int r = 0; r < h; r++) {
+        for (int n = 0; n < w; n++) row[n] = (double)img[(size_t)r * stride + n];
+        pc_dft(row.data(), 1, w, true, N, cN, sN, false, &F[(size_t)r * Kh * 2], 1, Kh, false, B);
+    }
     G.assign((size_t)M * Kh * 2, 0.0);
-    for (int m = 0; m < M; m++)
-        for (int k = 0; k < Kh; k++) {
-            double re = 0.0, im = 0.0;
-            int j = 0;
-            for (int r = 0; r < h; r++) {
-                const double ar = F[((size_t)r * Kh + k) * 2], ai = F[((size_t)r * Kh + k) * 2 + 1];
-                const double t1 = ar * cM[j], t2 = ai * sM[j], t3 = ar * sM[j], t4 = ai * cM[j];
-                re = re + (t1 - t2);
-                im = im + (t3 + t4);
-                j += m; if (j >= M) j -= M;
-            }
-            G[((size_t)m * Kh + k) * 2] = re; G[((size_t)m * Kh + k) * 2 + 1] = im;
-        }
+    for (int k = 0; k < Kh; k++)
+        pc_dft(&F[(size_t)k * 2], (size_t)Kh, h, false, M, cM, sM, false, &G[(size_t)k * 2], (size_t)Kh, M, false, B);
 }
 
 void vo_phase_correlate(const float* img1, const float* img2, int w, int h, int64_t stride, double out[3])
 {
     const int M = vo_optimal_dft_size(h), N = vo_optimal_dft_size(w), Kh = N / 2 + 1;
-    std::vector<double> cN, sN, cM, sM, G1, G2;
+    std::vector<double> cN, sN, cM, sM, G1, G2, B;
     pc_twiddles(N, cN, sN);
     pc_twiddles(M, cM, sM);
     pc_forward(img1, stride, w, h, M, N, cN, sN, cM, sM, G1);
@@ -859,38 +908,19 @@ void vo_phase_correlate(const float* img1, const float* img2, int w, int h, int6
         C[2 * i] = (pr * mag) / den; C[2 * i + 1] = (pi * mag) / den;
     }
     // inverse along the columns (conjugate twiddles)
-    for (int r = 0; r < M; r++)
-        for (int k = 0; k < Kh; k++) {
-            double re = 0.0, im = 0.0;
-            int j = 0;
-            for (int m = 0; m < M; m++) {
-                const double ar = C[((size_t)m * Kh + k) * 2], ai = C[((size_t)m * Kh + k) * 2 + 1];
-                const double t1 = ar * cM[j], t2 = ai * sM[j], t3 = ai * cM[j], t4 = ar * sM[j];
-                re = re + (t1 + t2);
-                im = im + (t3 - t4);
-                j += r; if (j >= M) j -= M;
-            }
-            D[((size_t)r * Kh + k) * 2] = re; D[((size_t)r * Kh + k) * 2 + 1] = im;
+    for (int k = 0; k < Kh; k++)
+        pc_dft(&C[(size_t)k * 2], (size_t)Kh, M, false, M, cM, sM, true, &D[(size_t)k * 2], (size_t)Kh, M, false, B);
+    // inverse along the rows to a real surface: the row is completed by its Hermitian half, Y[N - k] = conj(Y[k]), and
+    // only the real parts of the result are formed; then the first maximum of the shifted surface
+    std::vector<double> R((size_t)M * N), Y((size_t)N * 2);
+    for (int r = 0; r < M; r++) {
+        const double* d = &D[(size_t)r * Kh * 2];
+        for (int k = 0; k < N; k++) {
+            if (k < Kh) { Y[2 * k] = d[2 * k]; Y[2 * k + 1] = d[2 * k + 1]; }
+            else { Y[2 * k] = d[2 * (N - k)]; Y[2 * k + 1] = -d[2 * (N - k) + 1]; }
         }
-    // inverse along the rows to a real surface (Hermitian halves folded), then the first maximum of the shifted surface
-    std::vector<double> R((size_t)M * N);
-    const int kfull = (N - 1) / 2;
-    for (int r = 0; r < M; r++)
-        for (int n = 0; n < N; n++) {
-            const double* d = &D[(size_t)r * Kh * 2];
-            double acc = d[0];
-            int j = 0;
-            for (int k = 1; k <= kfull; k++) {
-                j += n; if (j >= N) j -= N;
-                const double t = d[2 * k] * cN[j] + d[2 * k + 1] * sN[j];
-                acc = acc + 2.0 * t;
-            }
-            if (N % 2 == 0) {
-                j += n; if (j >= N) j -= N;
-                acc = acc + d[2 * (N / 2)] * cN[j];
-            }
-            R[(size_t)r * N + n] = acc;
-        }
+        pc_dft(Y.data(), 1, N, false, N, cN, sN, true, &R[(size_t)r * N], 1, N, true, B);
+    }
     auto shifted = [&](int y, int x) {   // fftShift: element (r, n) moves to ((r + M/2) % M, (n + N/2) % N)
         const int r = (y - M / 2 + M) % M, n = (x - N / 2 + N) % N;
         return R[(size_t)r * N + n];

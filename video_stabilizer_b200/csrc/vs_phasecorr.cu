@@ -2,108 +2,175 @@
 // (alignment.cpp:225-229, 369-388: cv::phaseCorrelate of the level-2 images of the previous and the current frame,
 // accepted when its response exceeds phase_correlate_threshold).
 //
-// cv::phaseCorrelate (OpenCV imgproc/src/phasecorr.cpp — not under /root/reference) is restated as a direct,
-// separable DFT in f64:  M, N = getOptimalDFTSize(rows), (cols), zero padding on the right / bottom;
+// cv::phaseCorrelate (OpenCV imgproc/src/phasecorr.cpp — not under /root/reference) is restated as a separable
+// DFT in f64, every 1-D transform in two stages (L = L1 L2, L (L1 + L2) multiply-adds instead of L^2):  M, N = getOptimalDFTSize(rows), (cols), zero padding on the right / bottom;
 // P = F1 conj(F2); C = P |P| / (|P|^2 + FLT_EPSILON); R = unnormalised inverse DFT of C; fftShift; first maximum;
 // 5x5 weighted centroid clamped to the array; response = window sum / (M N); shift = (N/2, M/2) - centroid.
-// Every output element is one thread's serial sum in ascending index order (no FMA, no tree reduction), which is the
+// Every stage output is one thread's serial sum in ascending index order (no FMA, no tree reduction), which is the
 // canonical order of the CPU restatement the parity tests compare with: results are bit-identical, and the solver
-// that starts from them keeps its bit-exact keypoint selections.  Sizes on this path are 5-smooth but small
-// (480x270 at 1080p, 960x540 at 4K): four dense passes of M x N x (M + N) / 2 multiply-adds on the FP64 pipe,
-// twiddles and the shared operand of a pass in shared memory, 2-4 outputs per thread so that the shared-memory
-// wavefronts and the FP64 issue rate balance.  Default off upstream, so not on the benchmarked path.
+// that starts from them keeps its bit-exact keypoint selections.  Sizes on this path are 5-smooth and small
+// (480 x 270 = (20 x 24) x (15 x 18) at 1080p, 960 x 540 at 4K): four passes (rows, columns, inverse columns, inverse
+// rows), each one launch of k_pc_dft with the transforms of a CTA, both stages and the twiddles in shared memory.
+// Default off upstream, so not on the benchmarked path.
 #include "vs_internal.h"
 
 #include <float.h>
 #include <math.h>
 
+#define VS_TRY(expr) do { int _r = (expr); if (_r != VS_OK) return _r; } while (0)
+
 namespace {
 
 constexpr int PC_THREADS = 256;
-constexpr int PC_FWD_ROWS = 8;     // image rows per CTA of the forward row pass (they share every twiddle load)
-constexpr int PC_INV_ROWS = 4;     // surface rows per CTA of the inverse row pass
-constexpr int PC_COL_M = 4;        // outputs per thread of a column pass (they share every load of the input column)
+constexpr int PC_SMEM_TARGET = 96 * 1024;    // two CTAs per SM when the transform length allows it
+constexpr int PC_SMEM_LIMIT = 200 * 1024;
 
-// forward row pass: F[slot][r][k] = sum_{n<w} x[r][n] tw_N[(k n) mod N], k < N/2+1 (real input, Hermitian half)
+enum { PC_ROWS_U8 = 0, PC_COLS = 1, PC_ROWS_HERM = 2 };
+
+// One launch = one separable pass: every CTA evaluates T 1-D transforms of length L = L1 L2 that lie next to each other
+// (T image rows, or T adjacent columns so that a column pass still moves 16 T contiguous bytes per row), in two stages
+// through shared memory, in exactly the order of the CPU restatement the parity tests compare with:
+//     A[k1][n2]     = sum_{n1 < L1} x[L2 n1 + n2] W^(L2 n1 k1)      (terms beyond the valid length skipped)
+//     B[k1][n2]     = A[k1][n2] W^(n2 k1)
+//     X[k1 + L1 k2] = sum_{n2 < L2} B[k1][n2] W^(L1 n2 k2)
+// every sum one thread's serial sum in ascending index order, every product and sum individually rounded (-fmad=false).
+struct PcPass {
+    const void* in;
+    void* out;
+    const int32_t* slots;      // batch index -> buffer index (per frame), or null (per pair)
+    const double2* tw;         // L twiddles (cos, -sin)
+    size_t in_batch, out_batch;   // elements between the buffers of two batch entries
+    int L, L1, L2;
+    int valid;                 // input length (zero padded to L)
+    int kout;                  // outputs wanted (k < kout)
+    int count;                 // transforms per batch entry (rows, or columns)
+    int T;                     // transforms per CTA
+    int pitch;                 // PC_ROWS_U8: bytes between image rows; otherwise Kh (complex elements between rows)
+    int outw;                  // elements between output rows
+};
+
+template <int MODE, bool CONJ>
 __global__ void __launch_bounds__(PC_THREADS)
-k_pc_rows_fwd(const uint8_t* __restrict__ img_base, size_t slot_bytes, int pitch, int w, int h,
-              const int32_t* __restrict__ slots, const double2* __restrict__ twN, int N, int Kh,
-              double2* __restrict__ F)
+k_pc_dft(const PcPass a)
 {
     extern __shared__ double2 pc_smem[];
+    const int L = a.L, L1 = a.L1, L2 = a.L2, T = a.T;
     double2* const tw = pc_smem;
-    double* const x = reinterpret_cast<double*>(pc_smem + N);          // [PC_FWD_ROWS][w]
-    const int slot = slots[blockIdx.y];
-    const int r0 = blockIdx.x * PC_FWD_ROWS;
-    const uint8_t* img = img_base + (size_t)slot * slot_bytes;
-    for (int j = threadIdx.x; j < N; j += PC_THREADS) tw[j] = twN[j];
-    for (int i = threadIdx.x; i < PC_FWD_ROWS * w; i += PC_THREADS) {
-        const int rr = i / w, n = i - rr * w;
-        const int r = min(r0 + rr, h - 1);                              // rows past the image repeat the last one (not stored)
-        x[i] = (double)img[(size_t)r * pitch + n];
+    double2* const B = pc_smem + L;                         // [T][L2][L1] (rows) or [L2][L1][T] (columns)
+    double2* const X = B + (size_t)T * L;                   // complex input; doubles for PC_ROWS_U8
+    double* const Xr = reinterpret_cast<double*>(X);
+    const int t0 = blockIdx.x * T;
+    const int nt = min(T, a.count - t0);
+    const size_t b = a.slots ? (size_t)a.slots[blockIdx.y] : (size_t)blockIdx.y;
+    auto at = [&](int t, int i) { return MODE == PC_COLS ? i * T + t : t * L + i; };
+
+    for (int j = threadIdx.x; j < L; j += PC_THREADS) tw[j] = a.tw[j];
+    if (MODE == PC_ROWS_U8) {
+        const uint8_t* img = static_cast<const uint8_t*>(a.in) + b * a.in_batch;
+        for (int i = threadIdx.x; i < nt * a.valid; i += PC_THREADS) {
+            const int t = i / a.valid, n = i - t * a.valid;
+            Xr[t * L + n] = (double)img[(size_t)(t0 + t) * a.pitch + n];
+        }
+    } else if (MODE == PC_COLS) {
+        const double2* in = static_cast<const double2*>(a.in) + b * a.in_batch + t0;
+        for (int i = threadIdx.x; i < T * a.valid; i += PC_THREADS) {
+            const int n = i / T, t = i - n * T;
+            if (t < nt) X[i] = __ldg(in + (size_t)n * a.pitch + t);
+        }
+    } else {
+        // the row completed by its Hermitian half: Y[k] = conj(Y[L - k]) for k > L / 2
+        const double2* in = static_cast<const double2*>(a.in) + b * a.in_batch + (size_t)t0 * a.pitch;
+        for (int i = threadIdx.x; i < nt * L; i += PC_THREADS) {
+            const int t = i / L, k = i - t * L;
+            double2 v;
+            if (k < a.pitch) v = __ldg(in + (size_t)t * a.pitch + k);
+            else { v = __ldg(in + (size_t)t * a.pitch + (L - k)); v.y = -v.y; }
+            X[i] = v;
+        }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < Kh; k += PC_THREADS) {
-        double re[PC_FWD_ROWS], im[PC_FWD_ROWS];
-#pragma unroll
-        for (int q = 0; q < PC_FWD_ROWS; q++) { re[q] = 0.0; im[q] = 0.0; }
+
+    const int n_a = (MODE == PC_COLS ? T : nt) * L;
+    for (int o = threadIdx.x; o < n_a; o += PC_THREADS) {
+        int t, rem;
+        if (MODE == PC_COLS) { rem = o / T; t = o - rem * T; if (t >= nt) continue; }
+        else { t = o / L; rem = o - t * L; }
+        const int k1 = rem / L2, n2 = rem - k1 * L2;
+        const int step = L2 * k1;                            // < L
+        int terms = a.valid > n2 ? (a.valid - n2 + L2 - 1) / L2 : 0;   // n = L2 n1 + n2 < valid
+        terms = min(terms, L1);
+        double re = 0.0, im = 0.0;
         int j = 0;
-        for (int n = 0; n < w; n++) {
-            const double2 t = tw[j];
-#pragma unroll
-            for (int q = 0; q < PC_FWD_ROWS; q++) {
-                const double v = x[q * w + n];
-                re[q] = re[q] + v * t.x;
-                im[q] = im[q] + v * t.y;
+        for (int n1 = 0; n1 < terms; n1++) {
+            const double2 w = tw[j];
+            if (MODE == PC_ROWS_U8) {
+                const double x = Xr[t * L + L2 * n1 + n2];
+                re = re + x * w.x;
+                im = CONJ ? im - x * w.y : im + x * w.y;
+            } else {
+                const double2 v = X[at(t, L2 * n1 + n2)];
+                const double t1 = v.x * w.x, t2 = v.y * w.y, t3 = v.x * w.y, t4 = v.y * w.x;
+                if (CONJ) { re = re + (t1 + t2); im = im + (t4 - t3); }
+                else      { re = re + (t1 - t2); im = im + (t3 + t4); }
             }
-            j += k; if (j >= N) j -= N;
+            j += step; if (j >= L) j -= L;
         }
-#pragma unroll
-        for (int q = 0; q < PC_FWD_ROWS; q++)
-            if (r0 + q < h) F[((size_t)slot * h + r0 + q) * Kh + k] = make_double2(re[q], im[q]);
+        const double2 w = tw[n2 * k1];                       // < L
+        const double t1 = re * w.x, t2 = im * w.y, t3 = re * w.y, t4 = im * w.x;
+        B[at(t, n2 * L1 + k1)] = CONJ ? make_double2(t1 + t2, t4 - t3) : make_double2(t1 - t2, t3 + t4);
+    }
+    __syncthreads();
+
+    const int n_b = (MODE == PC_COLS ? T : nt) * a.kout;
+    for (int o = threadIdx.x; o < n_b; o += PC_THREADS) {
+        int t, k;
+        if (MODE == PC_COLS) { k = o / T; t = o - k * T; if (t >= nt) continue; }
+        else { t = o / a.kout; k = o - t * a.kout; }
+        const int k2 = k / L1, k1 = k - k2 * L1;
+        const int step = L1 * k2;                            // < L
+        double re = 0.0, im = 0.0;
+        int j = 0;
+        for (int n2 = 0; n2 < L2; n2++) {
+            const double2 w = tw[j];
+            const double2 v = B[at(t, n2 * L1 + k1)];
+            const double t1 = v.x * w.x, t2 = v.y * w.y, t3 = v.x * w.y, t4 = v.y * w.x;
+            if (CONJ) { re = re + (t1 + t2); im = im + (t4 - t3); }
+            else      { re = re + (t1 - t2); im = im + (t3 + t4); }
+            j += step; if (j >= L) j -= L;
+        }
+        if (MODE == PC_ROWS_HERM)
+            static_cast<double*>(a.out)[b * a.out_batch + (size_t)(t0 + t) * a.outw + k] = re;
+        else if (MODE == PC_COLS)
+            static_cast<double2*>(a.out)[b * a.out_batch + (size_t)k * a.outw + t0 + t] = make_double2(re, im);
+        else
+            static_cast<double2*>(a.out)[b * a.out_batch + (size_t)(t0 + t) * a.outw + k] = make_double2(re, im);
     }
 }
 
-// column pass: out[b][m][k] = sum_{r<rows} in[b][r][k] tw_M[(m r) mod M]   (CONJ: conjugate twiddles, the inverse)
-// in / out are indexed by slots[b] when `slots` is given (forward: per frame), else by b (inverse: per pair)
-template <bool CONJ>
-__global__ void __launch_bounds__(PC_THREADS)
-k_pc_cols(const double2* __restrict__ in, size_t in_stride, int rows, const int32_t* __restrict__ slots,
-          const double2* __restrict__ twM, int M, int Kh, double2* __restrict__ out, size_t out_stride)
+// L = L1 L2 with L1 the largest divisor of L whose square does not exceed L
+void pc_split(int L, int& L1, int& L2)
 {
-    extern __shared__ double2 pc_smem[];
-    double2* const tw = pc_smem;
-    for (int j = threadIdx.x; j < M; j += PC_THREADS) tw[j] = twM[j];
-    __syncthreads();
-    const int b = slots ? slots[blockIdx.z] : blockIdx.z;
-    const int k = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int m0 = (blockIdx.y * (PC_THREADS / 32) + (threadIdx.x >> 5)) * PC_COL_M;
-    if (k >= Kh || m0 >= M) return;
-    const double2* col = in + (size_t)b * in_stride + k;
-    double re[PC_COL_M], im[PC_COL_M];
-    int j[PC_COL_M], step[PC_COL_M];
-#pragma unroll
-    for (int q = 0; q < PC_COL_M; q++) { re[q] = 0.0; im[q] = 0.0; j[q] = 0; step[q] = min(m0 + q, M - 1); }
-    for (int r = 0; r < rows; r++) {
-        const double2 a = __ldg(col + (size_t)r * Kh);
-#pragma unroll
-        for (int q = 0; q < PC_COL_M; q++) {
-            const double2 t = tw[j[q]];
-            if (CONJ) {
-                const double t1 = a.x * t.x, t2 = a.y * t.y, t3 = a.y * t.x, t4 = a.x * t.y;
-                re[q] = re[q] + (t1 + t2);
-                im[q] = im[q] + (t3 - t4);
-            } else {
-                const double t1 = a.x * t.x, t2 = a.y * t.y, t3 = a.x * t.y, t4 = a.y * t.x;
-                re[q] = re[q] + (t1 - t2);
-                im[q] = im[q] + (t3 + t4);
-            }
-            j[q] += step[q]; if (j[q] >= M) j[q] -= M;
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < PC_COL_M; q++)
-        if (m0 + q < M) out[(size_t)b * out_stride + (size_t)(m0 + q) * Kh + k] = make_double2(re[q], im[q]);
+    L1 = 1;
+    for (int d = 1; d * d <= L; d++)
+        if (L % d == 0) L1 = d;
+    L2 = L / L1;
+}
+
+template <int MODE, bool CONJ>
+int pc_launch(vs_ctx* ctx, PcPass a, int batches)
+{
+    pc_split(a.L, a.L1, a.L2);
+    const size_t per_t = (size_t)a.L * (MODE == PC_ROWS_U8 ? 24 : 32), fixed = (size_t)a.L * 16;
+    if (fixed + per_t > (size_t)PC_SMEM_LIMIT)
+        return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "phase correlation: image too large for the shared-memory tables");
+    int T = 8;
+    while (T > 1 && fixed + per_t * T > (size_t)PC_SMEM_TARGET) T >>= 1;
+    a.T = T;
+    const size_t smem = fixed + per_t * T;
+    if (smem > 48 * 1024) VS_CUDA(ctx, cudaFuncSetAttribute(k_pc_dft<MODE, CONJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pc_dft<MODE, CONJ><<<dim3((a.count + T - 1) / T, batches), PC_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches += 1;
+    return VS_OK;
 }
 
 // cross-power spectrum of a pair: previous frame x conj(current frame), normalised (mulSpectrums conjB, magSpectrums,
@@ -123,49 +190,6 @@ k_pc_cross(const double2* __restrict__ spec, size_t spec_stride, const vs_pair* 
     const double mag = sqrt(pr_ * pr_ + pi_ * pi_);
     const double den = mag * mag + (double)FLT_EPSILON;
     C[(size_t)blockIdx.y * count + i] = make_double2((pr_ * mag) / den, (pi_ * mag) / den);
-}
-
-// inverse row pass to the real correlation surface: R[p][r][n] = Re D[0] + sum_{k=1}^{(N-1)/2} 2 Re(D[k] conj tw[(k n) mod N])
-// (+ the Nyquist term for even N)
-__global__ void __launch_bounds__(PC_THREADS)
-k_pc_rows_inv(const double2* __restrict__ D, const double2* __restrict__ twN, int M, int N, int Kh, double* __restrict__ R)
-{
-    extern __shared__ double2 pc_smem[];
-    double2* const tw = pc_smem;
-    double2* const d = pc_smem + N;                                     // [PC_INV_ROWS][Kh]
-    const int r0 = blockIdx.x * PC_INV_ROWS;
-    const size_t pair = blockIdx.y;
-    for (int j = threadIdx.x; j < N; j += PC_THREADS) tw[j] = twN[j];
-    for (int i = threadIdx.x; i < PC_INV_ROWS * Kh; i += PC_THREADS) {
-        const int rr = i / Kh, k = i - rr * Kh;
-        d[i] = D[(pair * M + min(r0 + rr, M - 1)) * Kh + k];
-    }
-    __syncthreads();
-    const int kfull = (N - 1) / 2;
-    for (int n = threadIdx.x; n < N; n += PC_THREADS) {
-        double acc[PC_INV_ROWS];
-#pragma unroll
-        for (int q = 0; q < PC_INV_ROWS; q++) acc[q] = d[q * Kh].x;
-        int j = 0;
-        for (int k = 1; k <= kfull; k++) {
-            j += n; if (j >= N) j -= N;
-            const double2 t = tw[j];
-#pragma unroll
-            for (int q = 0; q < PC_INV_ROWS; q++) {
-                const double2 v = d[q * Kh + k];
-                const double s = v.x * t.x + v.y * t.y;
-                acc[q] = acc[q] + 2.0 * s;
-            }
-        }
-        if ((N & 1) == 0) {
-            j += n; if (j >= N) j -= N;
-#pragma unroll
-            for (int q = 0; q < PC_INV_ROWS; q++) acc[q] = acc[q] + d[q * Kh + N / 2].x * tw[j].x;
-        }
-#pragma unroll
-        for (int q = 0; q < PC_INV_ROWS; q++)
-            if (r0 + q < M) R[(pair * M + r0 + q) * N + n] = acc[q];
-    }
 }
 
 // first maximum of the shifted surface (minMaxLoc), 5x5 weighted centroid, response, and the seed of the solver
@@ -229,14 +253,6 @@ k_pc_peak(const double* __restrict__ R, int M, int N, const vs_pair* __restrict_
     }
 }
 
-template <typename K>
-int pc_smem_attr(vs_ctx* ctx, K kernel, size_t bytes)
-{
-    if (bytes > 200 * 1024) return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "phase correlation: image too wide for the shared-memory tables");
-    if (bytes > 48 * 1024) VS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return VS_OK;
-}
-
 }  // namespace
 
 int vs_optimal_dft_size(int n)
@@ -264,20 +280,17 @@ int vsk_phase_forward(vs_ctx* ctx, const VsPhasePlan& p, const uint8_t* d_img_ba
     if (nslots == 0) return VS_OK;
     const double2* twN = reinterpret_cast<const double2*>(p.d_tw);
     const double2* twM = twN + p.N;
-    double2* F = reinterpret_cast<double2*>(p.d_rows);
-    double2* G = reinterpret_cast<double2*>(p.d_spec);
-    const size_t smem_a = (size_t)p.N * 16 + (size_t)PC_FWD_ROWS * p.w * 8;
-    int r = pc_smem_attr(ctx, k_pc_rows_fwd, smem_a);
-    if (r != VS_OK) return r;
-    r = pc_smem_attr(ctx, k_pc_cols<false>, (size_t)p.M * 16);
-    if (r != VS_OK) return r;
-    k_pc_rows_fwd<<<dim3((p.h + PC_FWD_ROWS - 1) / PC_FWD_ROWS, nslots), PC_THREADS, smem_a, ctx->stream>>>(
-        d_img_base, slot_bytes, p.pitch, p.w, p.h, d_slots, twN, p.N, p.Kh, F);
-    const int mrows = (PC_THREADS / 32) * PC_COL_M;
-    k_pc_cols<false><<<dim3((p.Kh + 31) / 32, (p.M + mrows - 1) / mrows, nslots), PC_THREADS, (size_t)p.M * 16, ctx->stream>>>(
-        F, (size_t)p.h * p.Kh, p.h, d_slots, twM, p.M, p.Kh, G, (size_t)p.M * p.Kh);
+    PcPass rows{};   // F[slot][r][k] = row transforms of the real image, k < N/2+1 (Hermitian half)
+    rows.in = d_img_base; rows.out = p.d_rows; rows.slots = d_slots; rows.tw = twN;
+    rows.in_batch = slot_bytes; rows.out_batch = (size_t)p.h * p.Kh;
+    rows.L = p.N; rows.valid = p.w; rows.kout = p.Kh; rows.count = p.h; rows.pitch = p.pitch; rows.outw = p.Kh;
+    VS_TRY((pc_launch<PC_ROWS_U8, false>(ctx, rows, nslots)));
+    PcPass cols{};   // G[slot][m][k] = column transforms of F, the h rows zero padded to M
+    cols.in = p.d_rows; cols.out = p.d_spec; cols.slots = d_slots; cols.tw = twM;
+    cols.in_batch = (size_t)p.h * p.Kh; cols.out_batch = (size_t)p.M * p.Kh;
+    cols.L = p.M; cols.valid = p.h; cols.kout = p.M; cols.count = p.Kh; cols.pitch = p.Kh; cols.outw = p.Kh;
+    VS_TRY((pc_launch<PC_COLS, false>(ctx, cols, nslots)));
     VS_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 2;
     return VS_OK;
 }
 
@@ -289,20 +302,20 @@ int vsk_phase_pairs(vs_ctx* ctx, const VsPhasePlan& p, const vs_pair* d_pairs, i
     const double2* twM = twN + p.N;
     const double2* G = reinterpret_cast<const double2*>(p.d_spec);
     double2* C = reinterpret_cast<double2*>(p.d_cross);
-    double2* D = reinterpret_cast<double2*>(p.d_inv);
     const size_t count = (size_t)p.M * p.Kh;
-    const size_t smem_d = (size_t)p.N * 16 + (size_t)PC_INV_ROWS * p.Kh * 16;
-    int r = pc_smem_attr(ctx, k_pc_cols<true>, (size_t)p.M * 16);
-    if (r != VS_OK) return r;
-    r = pc_smem_attr(ctx, k_pc_rows_inv, smem_d);
-    if (r != VS_OK) return r;
     k_pc_cross<<<dim3((unsigned)((count + PC_THREADS - 1) / PC_THREADS), n), PC_THREADS, 0, ctx->stream>>>(G, count, d_pairs, count, C);
-    const int mrows = (PC_THREADS / 32) * PC_COL_M;
-    k_pc_cols<true><<<dim3((p.Kh + 31) / 32, (p.M + mrows - 1) / mrows, n), PC_THREADS, (size_t)p.M * 16, ctx->stream>>>(
-        C, count, p.M, nullptr, twM, p.M, p.Kh, D, count);
-    k_pc_rows_inv<<<dim3((p.M + PC_INV_ROWS - 1) / PC_INV_ROWS, n), PC_THREADS, smem_d, ctx->stream>>>(D, twN, p.M, p.N, p.Kh, p.d_surf);
+    PcPass cols{};   // inverse along the columns (conjugate twiddles)
+    cols.in = p.d_cross; cols.out = p.d_inv; cols.slots = nullptr; cols.tw = twM;
+    cols.in_batch = count; cols.out_batch = count;
+    cols.L = p.M; cols.valid = p.M; cols.kout = p.M; cols.count = p.Kh; cols.pitch = p.Kh; cols.outw = p.Kh;
+    VS_TRY((pc_launch<PC_COLS, true>(ctx, cols, n)));
+    PcPass rows{};   // inverse along the rows to the real correlation surface
+    rows.in = p.d_inv; rows.out = p.d_surf; rows.slots = nullptr; rows.tw = twN;
+    rows.in_batch = count; rows.out_batch = (size_t)p.M * p.N;
+    rows.L = p.N; rows.valid = p.N; rows.kout = p.N; rows.count = p.M; rows.pitch = p.Kh; rows.outw = p.N;
+    VS_TRY((pc_launch<PC_ROWS_HERM, true>(ctx, rows, n)));
     k_pc_peak<<<n, 1024, 0, ctx->stream>>>(p.d_surf, p.M, p.N, d_pairs, threshold, scale, d_phase, d_init);
     VS_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 4;
+    ctx->launches += 2;
     return VS_OK;
 }
