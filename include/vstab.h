@@ -157,8 +157,13 @@ int vs_image_warp_u8_f32(vs_ctx*, const vs_img* in, const float* params4, const 
  * (x+dst_x0, y+dst_y0) of the full-size warp (stabilizer.cpp:102-109 crop fused). */
 int vs_bgr_warp_u8(vs_ctx*, const vs_img* src, const double* M6, const vs_img* dst,
                    int dst_x0, int dst_y0, int mode, int border, int mem);
+/* The same warp for the planes of an NV12 frame (no counterpart upstream, whose frames are BGR cv::Mat: the data format
+ * a hardware decoder delivers): cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) of a 1-channel
+ * (Y) or 2-channel (interleaved UV) u8 image.  width in pixels, stride in bytes. */
+int vs_plane_warp_u8(vs_ctx*, const vs_img* src, int channels, const double* M6, const vs_img* dst,
+                     int dst_x0, int dst_y0, int mem);
 /* cv::phaseCorrelate(src1, src2, noArray(), &response) (alignment.cpp:374, align_test.cpp:190,386) on two u8 images of
- * one size taken as CV_32F: out3 = shift x, shift y, response (host memory).  Direct f64 DFT on the device. */
+ * one size taken as CV_32F: out3 = shift x, shift y, response (host memory).  Two-stage f64 DFT on the device. */
 int vs_phase_correlate_u8(vs_ctx*, const vs_img* src1, const vs_img* src2, double* out3, int mem);
 
 /* ------------------------------------------- fused, batched, device-resident */
@@ -183,12 +188,21 @@ typedef struct vs_pair {
     int32_t invert;
 } vs_pair;
 
-enum { VS_CLIP_DEBUG_TAPS = 1 };  /* keep per-pair warpdiff / selection for inspection */
+enum { VS_CLIP_DEBUG_TAPS = 1,    /* keep per-pair warpdiff / selection for inspection */
+       VS_CLIP_NV12 = 2 };        /* frames are NV12 instead of BGR (below) */
 
 /* A clip is `capacity` frame slots of one size resident on the GPU: BGR frame, gray
  * pyramid (ComputePyramid, alignment.cpp:149-235) and keyframe features
  * (ComputeKeyFrame, alignment.cpp:237-276).  VideoAligner uses 2 slots, the batched
  * pipeline uses one slot per frame of a chunk.  max_pairs bounds one vs_clip_align call. */
+/* VS_CLIP_NV12 (the output of a hardware decoder fed straight in; no counterpart upstream,
+ * whose frames are BGR cv::Mat): every frame the clip takes or returns is an NV12 frame: `height` rows of Y, then
+ * height/2 rows of interleaved UV, all row_stride bytes apart on input, dense (width bytes per row, 3/2 width height
+ * bytes per frame) on output; width, height and crop even.  Every `bgr` / `out` pointer below then means such a frame.
+ * The Y plane IS the gray image (cv::cvtColor(COLOR_YUV2GRAY_NV12) copies it): it is uploaded into level 0 of the
+ * pyramid, nothing is converted, and the alignment is that of a BGR clip whose three channels equal Y.  Frames are warped
+ * plane by plane with the cv-exact bilinear mode and the constant border only: Y by the correction itself, UV as a
+ * (width/2) x (height/2) two-channel image by the same similarity with half the translation. */
 int vs_clip_create(vs_ctx*, int width, int height, int capacity, int max_pairs,
                    const vs_align_params* params, int flags, vs_clip** out);
 int vs_clip_destroy(vs_clip*);
@@ -259,7 +273,7 @@ int vs_clip_warp_to_host_async(vs_clip*, const int32_t* slots, int n, const doub
 int vs_clip_sync_transfers(vs_clip*);
 
 /* inspection taps (host outputs, synchronous) used by the bit-exact parity tests */
-int vs_clip_get_bgr(vs_clip*, int slot, uint8_t* out /* w*h*3 dense */);
+int vs_clip_get_bgr(vs_clip*, int slot, uint8_t* out /* w*h*3 dense; NV12 clips: the w*h*3/2 frame */);
 int vs_clip_get_gray(vs_clip*, int slot, int level, uint8_t* out /* w*h dense */);
 int vs_clip_get_keypoints(vs_clip*, int slot, int level, int axis, uint16_t* out /* planar (tw,th,2) */);
 int vs_clip_get_jacobians(vs_clip*, int slot, int level, int axis, float* out /* planar (tw,th,4) */);

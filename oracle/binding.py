@@ -82,6 +82,8 @@ def load(fast: bool = False):
     lib.vo_image_warp.argtypes = [P, I, I, P, P, I, I]
     lib.vo_warp_bgr.argtypes = [P, I, I, P, P, I, I, I]
     lib.vo_warp_bgr_matrix.argtypes = [P, I, I, P, P, I, I, I, I, I, I]
+    lib.vo_warp_plane_matrix.argtypes = [P, I, I, I, P, P, I, I, I, I]
+    lib.vo_warp_nv12.argtypes = [P, I, I, P, P, I]
     lib.vo_tf_inverse.argtypes = [P, P]
     lib.vo_optimal_dft_size.argtypes = [I]
     lib.vo_phase_correlate_u8.argtypes = [P, P, I, I, P]
@@ -232,6 +234,26 @@ def warp_bgr_matrix(src, M6, out_w, out_h, dx0=0, dy0=0, mode=0, border=0, fast=
     assert out.flags.c_contiguous and out.shape == (out_h, out_w, 3)
     M = np.ascontiguousarray(M6, np.float64)
     load(fast).vo_warp_bgr_matrix(_p(src), w, h, _p(M), _p(out), out_w, out_h, dx0, dy0, mode, border)
+    return out
+
+
+def warp_plane_matrix(src, M6, out_w, out_h, dx0=0, dy0=0):
+    """cv::warpAffine of a (h, w) or (h, w, 2) u8 image (the Y / UV plane of an NV12 frame), window (dx0, dy0, out_w, out_h)."""
+    src = np.ascontiguousarray(src, np.uint8)
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    h, w = src.shape[:2]
+    out = np.empty((out_h, out_w) if src.ndim == 2 else (out_h, out_w, ch), np.uint8)
+    M = np.ascontiguousarray(M6, np.float64)
+    load().vo_warp_plane_matrix(_p(src), w, h, ch, _p(M), _p(out), out_w, out_h, dx0, dy0)
+    return out
+
+
+def warp_nv12(frame, w, h, T, crop=0):
+    """A dense NV12 frame (h * 3 / 2 rows of w bytes) warped by the centre-based correction T."""
+    frame = np.ascontiguousarray(frame, np.uint8).reshape(h * 3 // 2, w)
+    out = np.empty(((h - 2 * crop) * 3 // 2, w - 2 * crop), np.uint8)
+    t = _t(T)
+    load().vo_warp_nv12(_p(frame), w, h, _p(t), _p(out), crop)
     return out
 
 

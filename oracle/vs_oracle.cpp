@@ -568,6 +568,53 @@ void vo_warp_bgr(const uint8_t* src, int w, int h, const double T[4],
     vo_warp_bgr_matrix(src, w, h, M, dst, w - 2 * crop, h - 2 * crop, crop, crop, mode, border);
 }
 
+// The planes of an NV12 frame (no counterpart upstream, whose frames are BGR cv::Mat; the product's VS_CLIP_NV12 clips):
+// cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) of a u8 image with `ch` interleaved channels (1 = Y, 2 = UV), the same
+// fixed-point arithmetic as mode 0 above.  Pinned against cv2.warpAffine on 1- and 2-channel images
+// (tests/golden/plane_warp.npz).
+void vo_warp_plane_matrix(const uint8_t* src, int w, int h, int ch, const double M[6], uint8_t* dst, int ow, int oh, int dx0, int dy0)
+{
+    const double m00 = M[0], m01 = M[1], m02 = M[2], m10 = M[3], m11 = M[4], m12 = M[5];
+    double D = m00 * m11 - m01 * m10;
+    D = D != 0 ? 1.0 / D : 0;
+    const double i00 = m11 * D, i01 = m01 * (-D), i10 = m10 * (-D), i11 = m00 * D;
+    const double i02 = -i00 * m02 - i01 * m12, i12 = -i10 * m02 - i11 * m12;
+    for (int yo = 0; yo < oh; yo++) {
+        const int y = yo + dy0;
+        const int X0 = (int)rint_he((i01 * y + i02) * 1024.0) + 16, Y0 = (int)rint_he((i11 * y + i12) * 1024.0) + 16;
+        for (int xo = 0; xo < ow; xo++) {
+            const int sfx = X0 + (int)rint_he(i00 * (xo + dx0) * 1024.0), sfy = Y0 + (int)rint_he(i10 * (xo + dx0) * 1024.0);
+            const int sx = sfx >> 10, sy = sfy >> 10, fx = (sfx >> 5) & 31, fy = (sfy >> 5) & 31;
+            const int w00 = (32 - fx) * (32 - fy), w10 = fx * (32 - fy), w01 = (32 - fx) * fy, w11 = fx * fy;
+            for (int c = 0; c < ch; c++) {
+                auto tap = [&](int xx, int yy) -> int {
+                    return xx < 0 || xx >= w || yy < 0 || yy >= h ? 0 : src[((size_t)yy * w + xx) * ch + c];
+                };
+                const int v = w00 * tap(sx, sy) + w10 * tap(sx + 1, sy) + w01 * tap(sx, sy + 1) + w11 * tap(sx + 1, sy + 1);
+                dst[((size_t)yo * ow + xo) * ch + c] = (uint8_t)((v + 512) >> 10);
+            }
+        }
+    }
+}
+
+// A whole NV12 frame (w x h Y rows, then h/2 rows of interleaved UV; dense) by the centre-based correction T, cropped by
+// `crop` (even) on every side: Y as vo_warp_bgr warps a frame, UV as a (w/2) x (h/2) two-channel image by the same
+// similarity with half the translation.
+void vo_warp_nv12(const uint8_t* src, int w, int h, const double T[4], uint8_t* dst, int crop)
+{
+    const int ow = w - 2 * crop, oh = h - 2 * crop;
+    auto matrix = [](const double t[4], int pw, int ph, double M[6]) {
+        const double A = t[0], B = t[1], cx = (pw - 1) * 0.5, cy = (ph - 1) * 0.5;
+        M[0] = 1.0 + A; M[1] = -B; M[2] = t[2] - A * cx + B * cy; M[3] = B; M[4] = 1.0 + A; M[5] = t[3] - B * cx - A * cy;
+    };
+    double M[6];
+    matrix(T, w, h, M);
+    vo_warp_plane_matrix(src, w, h, 1, M, dst, ow, oh, crop, crop);
+    const double Tuv[4] = {T[0], T[1], T[2] * 0.5, T[3] * 0.5};
+    matrix(Tuv, w / 2, h / 2, M);
+    vo_warp_plane_matrix(src + (size_t)w * h, w / 2, h / 2, 2, M, dst + (size_t)ow * oh, ow / 2, oh / 2, crop / 2, crop / 2);
+}
+
 //------------------------------------------------------------------------------
 // Transform algebra — imgproc.cpp:333-437.
 

@@ -67,6 +67,8 @@ void vo_k_image_warp(const uint8_t* in, int iw, int ih, float A, float B, float 
 void vo_lanczos_table(int16_t* tab);
 void vo_warp_bgr_matrix(const uint8_t* src, int w, int h, const double M[6], uint8_t* dst, int ow, int oh, int dx0, int dy0,
                         int mode, int border);
+void vo_warp_plane_matrix(const uint8_t* src, int w, int h, int ch, const double M[6], uint8_t* dst, int ow, int oh, int dx0, int dy0);
+void vo_warp_nv12(const uint8_t* src, int w, int h, const double T[4], uint8_t* dst, int crop);
 void vo_warp_bgr(const uint8_t* src, int w, int h, const double T[4],
                  uint8_t* dst, int mode, int border, int crop);
 

@@ -17,6 +17,7 @@ VS_MEM_HOST, VS_MEM_DEVICE = 0, 1
 VS_WARP_CV_EXACT_BILINEAR, VS_WARP_FLOAT_BILINEAR, VS_WARP_LANCZOS2 = 0, 1, 2
 VS_BORDER_CONSTANT0, VS_BORDER_REPEAT_EDGE = 0, 1
 VS_CLIP_DEBUG_TAPS = 1
+VS_CLIP_NV12 = 2
 VS_KERNEL_COUNT = 12
 
 
@@ -80,6 +81,7 @@ SYMBOLS = {
                                     C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int]),
     "vs_image_warp_u8_f32": (C.c_int, [_P, _IMG, _P, _IMG, C.c_int]),
     "vs_bgr_warp_u8": (C.c_int, [_P, _IMG, _P, _IMG, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vs_plane_warp_u8": (C.c_int, [_P, _IMG, C.c_int, _P, _IMG, C.c_int, C.c_int, C.c_int]),
     "vs_align_params_default": (None, [C.POINTER(VsAlignParams)]),
     "vs_clip_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(VsAlignParams), C.c_int, C.POINTER(_P)]),
     "vs_clip_destroy": (C.c_int, [_P]),

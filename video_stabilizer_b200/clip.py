@@ -36,7 +36,10 @@ def pairs_for_frames(first_frame: int, n_frames: int, slot_of=lambda f: f):
 
 class Clip:
     def __init__(self, width: int, height: int, capacity: int, max_pairs: int | None = None,
-                 params: capi.VsAlignParams | None = None, debug: bool = False, ctx: Context | None = None):
+                 params: capi.VsAlignParams | None = None, debug: bool = False, ctx: Context | None = None,
+                 nv12: bool = False):
+        """nv12: the clip's frames are NV12 (h * 3 / 2 rows of w bytes: Y, then interleaved UV) instead of BGR."""
+        self.nv12 = nv12
         self.ctx = ctx or default_context()
         self.lib = self.ctx.lib
         self.width, self.height, self.capacity = width, height, capacity
@@ -47,7 +50,8 @@ class Clip:
         self.params = params
         h = C.c_void_p()
         capi.check(self.ctx.handle, self.lib.vs_clip_create(self.ctx.handle, width, height, capacity, self.max_pairs,
-                                                            C.byref(params), capi.VS_CLIP_DEBUG_TAPS if debug else 0,
+                                                            C.byref(params),
+                                                            (capi.VS_CLIP_DEBUG_TAPS if debug else 0) | (capi.VS_CLIP_NV12 if nv12 else 0),
                                                             C.byref(h)), "vs_clip_create")
         self.handle = h
         self.levels = self.lib.vs_clip_levels(h)
@@ -74,9 +78,10 @@ class Clip:
 
     # ---- pipeline stages
     def upload(self, slot0: int, frames: np.ndarray):
-        """frames: (n,h,w,3) uint8 host array."""
+        """frames: (n,h,w,3) uint8 host array; NV12 clips: (n, h*3/2, w)."""
         frames = np.ascontiguousarray(frames)
         n = frames.shape[0]
+        assert frames.shape[1:] == ((self.height * 3 // 2, self.width) if self.nv12 else (self.height, self.width, 3))
         self._chk(self.lib.vs_clip_upload(self.handle, slot0, n, capi.ptr(frames), frames.strides[1], frames.strides[0],
                                           capi.VS_MEM_HOST), "vs_clip_upload")
 
@@ -110,9 +115,9 @@ class Clip:
         s = np.asarray(list(slots), np.int32)
         T = np.ascontiguousarray(transforms, np.float64).reshape(len(s), 4)
         ow, oh = self.width - 2 * crop, self.height - 2 * crop
-        out = np.empty((len(s), oh, ow, 3), np.uint8)
+        out = np.empty((len(s), oh * 3 // 2, ow) if self.nv12 else (len(s), oh, ow, 3), np.uint8)
         self._chk(self.lib.vs_clip_warp(self.handle, capi.ptr(s), len(s), capi.ptr(T), mode, border, crop, capi.ptr(out),
-                                        ow * oh * 3, capi.VS_MEM_HOST), "vs_clip_warp")
+                                        out[0].nbytes if len(s) else 0, capi.VS_MEM_HOST), "vs_clip_warp")
         return out
 
     def warp_device(self, slots, transforms: np.ndarray, d_out: int, out_frame_stride: int,
@@ -124,7 +129,7 @@ class Clip:
 
     # ---- inspection taps
     def get_bgr(self, slot: int) -> np.ndarray:
-        out = np.empty((self.height, self.width, 3), np.uint8)
+        out = np.empty((self.height * 3 // 2, self.width) if self.nv12 else (self.height, self.width, 3), np.uint8)
         self._chk(self.lib.vs_clip_get_bgr(self.handle, slot, capi.ptr(out)), "vs_clip_get_bgr")
         return out
 

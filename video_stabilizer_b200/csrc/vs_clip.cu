@@ -30,6 +30,11 @@ struct vs_clip {
     VsClipGeom g;
     size_t bgr_pitch = 0, bgr_slot_bytes = 0;
     uint8_t* d_bgr = nullptr;
+    // VS_CLIP_NV12: the Y plane of a frame IS level 0 of its pyramid (uploaded there, never rewritten); the interleaved
+    // UV plane ((w/2) x (h/2) pairs) lives here.  d_bgr is not allocated.
+    bool nv12 = false;
+    size_t uv_pitch = 0, uv_slot_bytes = 0;
+    uint8_t* d_uv = nullptr;
     uint8_t* d_pyr = nullptr;
     uint32_t* d_kp = nullptr;
     float4* d_jac = nullptr;
@@ -100,7 +105,7 @@ int dev_alloc(vs_ctx* ctx, T** p, size_t count)
 
 void free_all(vs_clip* c)
 {
-    cudaFree(c->d_bgr); cudaFree(c->d_pyr); cudaFree(c->d_kp); cudaFree(c->d_jac); cudaFree(c->d_pairs);
+    cudaFree(c->d_bgr); cudaFree(c->d_uv); cudaFree(c->d_pyr); cudaFree(c->d_kp); cudaFree(c->d_jac); cudaFree(c->d_pairs);
     cudaFree(c->d_T); cudaFree(c->d_status); cudaFree(c->d_iters); cudaFree(c->d_slots); cudaFree(c->d_coef);
     for (int i = 0; i < vs_clip::kOutRing; i++) {
         cudaFree(c->d_out_ring[i]);
@@ -167,6 +172,19 @@ void build_bgr_tensor_map(vs_clip* c)
 // when the clip is too small for its TMA box; generic kernels for the other modes / borders
 int clip_warp_launch(vs_clip* c, const int32_t* d_slots, const VsWarpCoef* d_coef, const VsDevImg& dst, int crop, int mode, int border, int n)
 {
+    if (c->nv12) {
+        // dst: the Y planes of n dense NV12 frames (dst.batch_stride = frame bytes); the UV plane follows each Y plane.
+        // d_coef: n coefficient sets of the Y planes, then (c->capacity entries later) those of the UV planes.
+        if (mode != VS_WARP_CV_EXACT_BILINEAR || border != VS_BORDER_CONSTANT0)
+            return vs_set_error(c->ctx, VS_ERR_UNSUPPORTED, "clip_warp: NV12 clips warp with the cv-exact bilinear mode and the constant border");
+        const VsLevel& L0 = c->g.lv[0];
+        VsDevImg ysrc{c->d_pyr + L0.img_off, c->w, c->h, (int64_t)L0.pitch, n, (int64_t)c->g.pyr_slot_bytes};
+        VsDevImg usrc{c->d_uv, c->w / 2, c->h / 2, (int64_t)c->uv_pitch, n, (int64_t)c->uv_slot_bytes};
+        VsDevImg udst{(uint8_t*)dst.data + (size_t)dst.w * dst.h, dst.w / 2, dst.h / 2, dst.stride, n, dst.batch_stride};
+        int r = vsk_plane_warp_slots(c->ctx, ysrc, 1, d_slots, d_coef, dst, crop, crop);
+        if (r == VS_OK) r = vsk_plane_warp_slots(c->ctx, usrc, 2, d_slots, d_coef + c->capacity, udst, crop / 2, crop / 2);
+        return r;
+    }
     VsDevImg src{c->d_bgr, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
     if ((mode == VS_WARP_CV_EXACT_BILINEAR || mode == VS_WARP_FLOAT_BILINEAR) && border == VS_BORDER_CONSTANT0 &&
         c->bgr_map_rows_ok && n <= c->capacity && dst.w <= c->w && dst.h <= c->h)
@@ -187,6 +205,60 @@ void note_bgr_read(vs_clip* c)
     if (!c->ev_bgr_read) return;
     cudaEventRecord(c->ev_bgr_read, c->ctx->stream);
     c->bgr_read_recorded = true;
+}
+
+// bytes of one dense output frame of ow x oh pixels
+size_t clip_frame_bytes(const vs_clip* c, int ow, int oh)
+{
+    return c->nv12 ? (size_t)ow * oh * 3 / 2 : (size_t)ow * oh * 3;
+}
+
+// Inverse-map coefficients of n corrections: [0, n) for the BGR frame / the Y plane, and for NV12 clips
+// [capacity, capacity + n) for the UV plane, which is warped as a (w/2) x (h/2) image by the same similarity with half
+// the translation.
+void clip_warp_coefs(const vs_clip* c, const double* transforms, int n, std::vector<VsWarpCoef>& coef)
+{
+    coef.resize(c->nv12 ? (size_t)c->capacity + n : (size_t)n);
+    for (int i = 0; i < n; i++) {
+        double M[6];
+        vs_forward_matrix_from_transform(transforms + 4 * i, c->w, c->h, M);
+        vs_warp_coef_from_forward(M, &coef[i]);
+        if (c->nv12) {
+            const double* T = transforms + 4 * i;
+            const double Tuv[4] = {T[0], T[1], T[2] * 0.5, T[3] * 0.5};
+            vs_forward_matrix_from_transform(Tuv, c->w / 2, c->h / 2, M);
+            vs_warp_coef_from_forward(M, &coef[(size_t)c->capacity + i]);
+        }
+    }
+}
+
+// n frames into slots [slot0, slot0 + n) on `stream`
+int clip_enqueue_upload(vs_clip* c, int slot0, int n, const uint8_t* frames, int64_t row_stride, int64_t frame_stride,
+                        cudaMemcpyKind kind, cudaStream_t stream)
+{
+    vs_ctx* ctx = c->ctx;
+    if (c->nv12) {
+        const VsLevel& L0 = c->g.lv[0];
+        for (int i = 0; i < n; i++) {
+            const uint8_t* f = frames + (size_t)frame_stride * i;
+            VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_pyr + (size_t)(slot0 + i) * c->g.pyr_slot_bytes + L0.img_off, (size_t)L0.pitch,
+                                           f, (size_t)row_stride, (size_t)c->w, (size_t)c->h, kind, stream));
+            VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_uv + (size_t)(slot0 + i) * c->uv_slot_bytes, c->uv_pitch,
+                                           f + (size_t)row_stride * c->h, (size_t)row_stride, (size_t)c->w, (size_t)c->h / 2, kind, stream));
+        }
+        return VS_OK;
+    }
+    if (frame_stride == row_stride * c->h) {
+        // frames are back to back: one 2-D copy for the whole range
+        VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)slot0 * c->bgr_slot_bytes, c->bgr_pitch, frames, (size_t)row_stride,
+                                       (size_t)c->w * 3, (size_t)c->h * n, kind, stream));
+    } else {
+        for (int i = 0; i < n; i++)
+            VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)(slot0 + i) * c->bgr_slot_bytes, c->bgr_pitch,
+                                           frames + (size_t)frame_stride * i, (size_t)row_stride, (size_t)c->w * 3, c->h,
+                                           kind, stream));
+    }
+    return VS_OK;
 }
 
 constexpr int kPhaseLevel = 2;   // alignment.hpp:69
@@ -306,13 +378,21 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
         delete c;
         return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "%d tiles on a level exceeds the on-chip selection capacity", mt);
     }
+    c->nv12 = (flags & VS_CLIP_NV12) != 0;
+    if (c->nv12 && ((width | height) & 1)) {
+        delete c;
+        return vs_set_error(ctx, VS_ERR_INVALID, "clip_create: NV12 frames have even width and height");
+    }
     c->bgr_pitch = vs_align_up((size_t)width * 3, 128);
-    c->bgr_slot_bytes = c->bgr_pitch * height;
+    c->bgr_slot_bytes = c->nv12 ? 0 : c->bgr_pitch * height;
+    c->uv_pitch = vs_align_up((size_t)width, 128);
+    c->uv_slot_bytes = c->nv12 ? c->uv_pitch * (height / 2) : 0;
 
     int r = VS_OK;
     size_t feat = (size_t)capacity * 2 * g.total_tiles;
     int nslots = capacity > max_pairs ? capacity : max_pairs;
-    if (r == VS_OK) r = dev_alloc(ctx, &c->d_bgr, c->bgr_slot_bytes * capacity);
+    if (r == VS_OK && !c->nv12) r = dev_alloc(ctx, &c->d_bgr, c->bgr_slot_bytes * capacity);
+    if (r == VS_OK && c->nv12) r = dev_alloc(ctx, &c->d_uv, c->uv_slot_bytes * capacity);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_pyr, g.pyr_slot_bytes * capacity);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_kp, feat);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_jac, feat);
@@ -321,7 +401,7 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_status, (size_t)max_pairs);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_iters, (size_t)max_pairs * g.levels);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_slots, (size_t)nslots);
-    if (r == VS_OK) r = dev_alloc(ctx, &c->d_coef, (size_t)capacity);
+    if (r == VS_OK) r = dev_alloc(ctx, &c->d_coef, (size_t)capacity * 2);   // NV12: a second set for the UV planes
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_pos_scratch, (size_t)max_pairs * 4 * g.max_tiles);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_res_scratch, (size_t)max_pairs * 2 * g.max_tiles);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_patch_scratch, (size_t)max_pairs * 2 * g.max_tiles);
@@ -335,8 +415,11 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
     if (r != VS_OK) { free_all(c); delete c; return r; }
     // padding bytes of the pyramid rows are never read as pixels, but keep them defined
     cudaMemsetAsync(c->d_pyr, 0, g.pyr_slot_bytes * capacity, ctx->stream);
-    cudaMemsetAsync(c->d_bgr, 0, c->bgr_slot_bytes * capacity, ctx->stream);
-    build_bgr_tensor_map(c);
+    if (c->nv12) cudaMemsetAsync(c->d_uv, 0, c->uv_slot_bytes * capacity, ctx->stream);
+    else {
+        cudaMemsetAsync(c->d_bgr, 0, c->bgr_slot_bytes * capacity, ctx->stream);
+        build_bgr_tensor_map(c);
+    }
     *out = c;
     return VS_OK;
 }
@@ -382,20 +465,10 @@ int vs_clip_upload(vs_clip* c, int slot0, int n, const uint8_t* bgr, int64_t row
     vs_ctx* ctx = c->ctx;
     VS_REQUIRE(ctx, slot0 >= 0 && n >= 0 && slot0 + n <= c->capacity, "clip_upload: slot range out of bounds");
     VS_REQUIRE(ctx, n == 0 || bgr, "clip_upload: source is NULL");
-    VS_REQUIRE(ctx, row_stride >= (int64_t)c->w * 3, "clip_upload: row_stride smaller than a row");
+    VS_REQUIRE(ctx, row_stride >= (int64_t)c->w * (c->nv12 ? 1 : 3), "clip_upload: row_stride smaller than a row");
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaMemcpyKind kind = mem == VS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (frame_stride == row_stride * c->h) {
-        // frames are back to back: one 2-D copy for the whole range
-        VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)slot0 * c->bgr_slot_bytes, c->bgr_pitch, bgr, (size_t)row_stride,
-                                       (size_t)c->w * 3, (size_t)c->h * n, kind, ctx->stream));
-    } else {
-        for (int i = 0; i < n; i++)
-            VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)(slot0 + i) * c->bgr_slot_bytes, c->bgr_pitch,
-                                           bgr + (size_t)frame_stride * i, (size_t)row_stride, (size_t)c->w * 3, c->h,
-                                           kind, ctx->stream));
-    }
-    return VS_OK;
+    return clip_enqueue_upload(c, slot0, n, bgr, row_stride, frame_stride, kind, ctx->stream);
 }
 
 int vs_clip_build_pyramids(vs_clip* c, int slot0, int n)
@@ -406,10 +479,20 @@ int vs_clip_build_pyramids(vs_clip* c, int slot0, int n)
     if (n == 0) return VS_OK;
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
     const VsClipGeom& g = c->g;
-    VsDevImg bgr{c->d_bgr + (size_t)slot0 * c->bgr_slot_bytes, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
+    VsDevImg bgr{c->nv12 ? nullptr : c->d_bgr + (size_t)slot0 * c->bgr_slot_bytes, c->w, c->h, (int64_t)c->bgr_pitch, n, (int64_t)c->bgr_slot_bytes};
     uint8_t* pyr0 = c->d_pyr + (size_t)slot0 * g.pyr_slot_bytes;
     VsDevImg prev{pyr0 + g.lv[0].img_off, g.lv[0].w, g.lv[0].h, g.lv[0].pitch, n, (int64_t)g.pyr_slot_bytes};
     if (c->pc_ready) for (int i = 0; i < n; i++) c->pc_valid[slot0 + i] = 0;   // the spectra follow the pyramids
+    if (c->nv12) {
+        // level 0 is the Y plane the upload put there
+        for (int l = 1; l < g.levels; l++) {
+            VsDevImg cur{pyr0 + g.lv[l].img_off, g.lv[l].w, g.lv[l].h, g.lv[l].pitch, n, (int64_t)g.pyr_slot_bytes};
+            VS_TRY(vsk_pyr_down(ctx, prev, cur));
+            if (l == 1) note_bgr_read(c);
+            prev = cur;
+        }
+        return VS_OK;
+    }
     // gray + level 1 in one pass over the BGR frame when the geometry allows it (every 16-aligned width: 720p, 1080p, 4K ...)
     int l0 = 1;
     if (g.levels > 1) {
@@ -647,24 +730,23 @@ int vs_clip_warp(vs_clip* c, const int32_t* slots, int n, const double* transfor
     if (n == 0) return VS_OK;
     VS_REQUIRE(ctx, slots && transforms && out, "clip_warp: NULL pointer");
     VS_REQUIRE(ctx, crop >= 0 && 2 * crop < c->w && 2 * crop < c->h, "clip_warp: crop too large");
+    VS_REQUIRE(ctx, !c->nv12 || (crop & 1) == 0, "clip_warp: NV12 clips crop by an even number of pixels");
     const int ow = c->w - 2 * crop, oh = c->h - 2 * crop;
-    VS_REQUIRE(ctx, out_frame_stride >= (int64_t)ow * oh * 3, "clip_warp: out_frame_stride smaller than a frame");
+    const size_t frame_bytes = clip_frame_bytes(c, ow, oh);
+    const int64_t out_row = c->nv12 ? ow : (int64_t)ow * 3;
+    VS_REQUIRE(ctx, out_frame_stride >= (int64_t)frame_bytes, "clip_warp: out_frame_stride smaller than a frame");
     for (int i = 0; i < n; i++) VS_REQUIRE(ctx, slots[i] >= 0 && slots[i] < c->capacity, "clip_warp: slot out of range");
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
 
-    std::vector<VsWarpCoef> coef(n);
-    for (int i = 0; i < n; i++) {
-        double M[6];
-        vs_forward_matrix_from_transform(transforms + 4 * i, c->w, c->h, M);
-        vs_warp_coef_from_forward(M, &coef[i]);
-    }
-    VS_CUDA(ctx, cudaMemcpyAsync(c->d_coef, coef.data(), (size_t)n * sizeof(VsWarpCoef), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<VsWarpCoef> coef;
+    clip_warp_coefs(c, transforms, n, coef);
+    VS_CUDA(ctx, cudaMemcpyAsync(c->d_coef, coef.data(), coef.size() * sizeof(VsWarpCoef), cudaMemcpyHostToDevice, ctx->stream));
     VS_CUDA(ctx, cudaMemcpyAsync(c->d_slots, slots, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
 
     uint8_t* d_out = out;
     int64_t d_stride = out_frame_stride;
     if (mem == VS_MEM_HOST) {
-        size_t need = (size_t)ow * oh * 3 * n;
+        size_t need = frame_bytes * n;
         if (need > c->warp_out_bytes) {
             VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             cudaFree(c->d_warp_out); c->d_warp_out = nullptr; c->warp_out_bytes = 0;
@@ -672,13 +754,13 @@ int vs_clip_warp(vs_clip* c, const int32_t* slots, int n, const double* transfor
             c->warp_out_bytes = need;
         }
         d_out = c->d_warp_out;
-        d_stride = (int64_t)ow * oh * 3;
+        d_stride = (int64_t)frame_bytes;
     }
-    VsDevImg dst{d_out, ow, oh, (int64_t)ow * 3, n, d_stride};
+    VsDevImg dst{d_out, ow, oh, out_row, n, d_stride};
     VS_TRY(clip_warp_launch(c, c->d_slots, c->d_coef, dst, crop, mode, border, n));
     note_bgr_read(c);
     if (mem == VS_MEM_HOST) {
-        VS_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)out_frame_stride, d_out, (size_t)d_stride, (size_t)ow * oh * 3, n,
+        VS_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)out_frame_stride, d_out, (size_t)d_stride, frame_bytes, n,
                                        cudaMemcpyDeviceToHost, ctx->stream));
         VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -701,7 +783,7 @@ static int ensure_async(vs_clip* c)
         VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_warp[i], cudaEventDisableTiming));
         VS_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_down[i], cudaEventDisableTiming));
     }
-    VS_TRY(dev_alloc(ctx, &c->d_coef_ring, (size_t)vs_clip::kOutRing * c->capacity));
+    VS_TRY(dev_alloc(ctx, &c->d_coef_ring, (size_t)vs_clip::kOutRing * c->capacity * 2));
     VS_TRY(dev_alloc(ctx, &c->d_slot_ring, (size_t)vs_clip::kOutRing * c->capacity));
     return VS_OK;
 }
@@ -712,22 +794,15 @@ int vs_clip_upload_async(vs_clip* c, int slot0, int n, const uint8_t* bgr, int64
     vs_ctx* ctx = c->ctx;
     VS_REQUIRE(ctx, slot0 >= 0 && n >= 0 && slot0 + n <= c->capacity, "clip_upload_async: slot range out of bounds");
     VS_REQUIRE(ctx, n == 0 || bgr, "clip_upload_async: source is NULL");
-    VS_REQUIRE(ctx, row_stride >= (int64_t)c->w * 3, "clip_upload_async: row_stride smaller than a row");
+    VS_REQUIRE(ctx, row_stride >= (int64_t)c->w * (c->nv12 ? 1 : 3), "clip_upload_async: row_stride smaller than a row");
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
     VS_TRY(ensure_async(c));
     if (n == 0) return VS_OK;
-    // the slots being overwritten may still be read by the ingest / warps enqueued earlier (nothing else reads BGR frames)
+    // the slots being overwritten may still be read by the ingest / warps enqueued earlier (nothing else reads BGR frames;
+    // the Y plane of an NV12 frame is also read by the keyframe features and the solves of its pairs, which have finished
+    // by the time its warp, whose transform they decide, is enqueued)
     if (c->bgr_read_recorded) VS_CUDA(ctx, cudaStreamWaitEvent(c->up_stream, c->ev_bgr_read, 0));
-    if (frame_stride == row_stride * c->h) {
-        VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)slot0 * c->bgr_slot_bytes, c->bgr_pitch, bgr, (size_t)row_stride,
-                                       (size_t)c->w * 3, (size_t)c->h * n, cudaMemcpyHostToDevice, c->up_stream));
-    } else {
-        for (int i = 0; i < n; i++)
-            VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_bgr + (size_t)(slot0 + i) * c->bgr_slot_bytes, c->bgr_pitch,
-                                           bgr + (size_t)frame_stride * i, (size_t)row_stride, (size_t)c->w * 3, c->h,
-                                           cudaMemcpyHostToDevice, c->up_stream));
-    }
-    return VS_OK;
+    return clip_enqueue_upload(c, slot0, n, bgr, row_stride, frame_stride, cudaMemcpyHostToDevice, c->up_stream);
 }
 
 int vs_clip_wait_uploads(vs_clip* c)
@@ -750,8 +825,9 @@ int vs_clip_warp_to_host_async(vs_clip* c, const int32_t* slots, int n, const do
     if (n == 0) return VS_OK;
     VS_REQUIRE(ctx, slots && transforms && out, "clip_warp_to_host_async: NULL pointer");
     VS_REQUIRE(ctx, crop >= 0 && 2 * crop < c->w && 2 * crop < c->h, "clip_warp_to_host_async: crop too large");
+    VS_REQUIRE(ctx, !c->nv12 || (crop & 1) == 0, "clip_warp_to_host_async: NV12 clips crop by an even number of pixels");
     const int ow = c->w - 2 * crop, oh = c->h - 2 * crop;
-    const size_t frame_bytes = (size_t)ow * oh * 3;
+    const size_t frame_bytes = clip_frame_bytes(c, ow, oh);
     VS_REQUIRE(ctx, out_frame_stride >= (int64_t)frame_bytes, "clip_warp_to_host_async: out_frame_stride smaller than a frame");
     for (int i = 0; i < n; i++) VS_REQUIRE(ctx, slots[i] >= 0 && slots[i] < c->capacity, "clip_warp_to_host_async: slot out of range");
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -768,18 +844,14 @@ int vs_clip_warp_to_host_async(vs_clip* c, const int32_t* slots, int n, const do
         VS_TRY(dev_alloc(ctx, &c->d_out_ring[b], need));
         c->out_ring_bytes[b] = need;
     }
-    std::vector<VsWarpCoef> coef(n);
-    for (int i = 0; i < n; i++) {
-        double M[6];
-        vs_forward_matrix_from_transform(transforms + 4 * i, c->w, c->h, M);
-        vs_warp_coef_from_forward(M, &coef[i]);
-    }
-    VsWarpCoef* d_coef = c->d_coef_ring + (size_t)b * c->capacity;
+    std::vector<VsWarpCoef> coef;
+    clip_warp_coefs(c, transforms, n, coef);
+    VsWarpCoef* d_coef = c->d_coef_ring + (size_t)b * c->capacity * 2;
     int32_t* d_slots = c->d_slot_ring + (size_t)b * c->capacity;
     // pageable sources: both copies complete (staged) before the call returns
-    VS_CUDA(ctx, cudaMemcpyAsync(d_coef, coef.data(), (size_t)n * sizeof(VsWarpCoef), cudaMemcpyHostToDevice, ctx->stream));
+    VS_CUDA(ctx, cudaMemcpyAsync(d_coef, coef.data(), coef.size() * sizeof(VsWarpCoef), cudaMemcpyHostToDevice, ctx->stream));
     VS_CUDA(ctx, cudaMemcpyAsync(d_slots, slots, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    VsDevImg dst{c->d_out_ring[b], ow, oh, (int64_t)ow * 3, n, (int64_t)frame_bytes};
+    VsDevImg dst{c->d_out_ring[b], ow, oh, c->nv12 ? (int64_t)ow : (int64_t)ow * 3, n, (int64_t)frame_bytes};
     VS_TRY(clip_warp_launch(c, d_slots, d_coef, dst, crop, mode, border, n));
     note_bgr_read(c);
     VS_CUDA(ctx, cudaEventRecord(c->ev_warp[b], ctx->stream));
@@ -814,8 +886,16 @@ int vs_clip_get_bgr(vs_clip* c, int slot, uint8_t* out)
     vs_ctx* ctx = c->ctx;
     VS_REQUIRE(ctx, slot >= 0 && slot < c->capacity && out, "clip_get_bgr: bad arguments");
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
-    VS_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)c->w * 3, c->d_bgr + (size_t)slot * c->bgr_slot_bytes, c->bgr_pitch,
-                                   (size_t)c->w * 3, c->h, cudaMemcpyDeviceToHost, ctx->stream));
+    if (c->nv12) {
+        const VsLevel& L0 = c->g.lv[0];
+        VS_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)c->w, c->d_pyr + (size_t)slot * c->g.pyr_slot_bytes + L0.img_off, (size_t)L0.pitch,
+                                       (size_t)c->w, c->h, cudaMemcpyDeviceToHost, ctx->stream));
+        VS_CUDA(ctx, cudaMemcpy2DAsync(out + (size_t)c->w * c->h, (size_t)c->w, c->d_uv + (size_t)slot * c->uv_slot_bytes, c->uv_pitch,
+                                       (size_t)c->w, c->h / 2, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        VS_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)c->w * 3, c->d_bgr + (size_t)slot * c->bgr_slot_bytes, c->bgr_pitch,
+                                       (size_t)c->w * 3, c->h, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VS_OK;
 }

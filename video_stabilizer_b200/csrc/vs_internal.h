@@ -47,6 +47,11 @@ bool vs_warp_rows_usable(const VsDevImg& src, int mode, int border);
 int vsk_bgr_warp_slots(vs_ctx*, const VsDevImg& src, const int32_t* d_slots, const VsWarpCoef* d_coef,
                        const VsDevImg& dst, int dst_x0, int dst_y0, int mode, int border);
 
+// planar form for NV12 frames: src / dst are 1-channel (Y) or 2-channel (interleaved UV) u8 images, widths in pixels,
+// strides in bytes; cv-exact bilinear, constant border
+int vsk_plane_warp_slots(vs_ctx*, const VsDevImg& src, int channels, const int32_t* d_slots, const VsWarpCoef* d_coef,
+                         const VsDevImg& dst, int dst_x0, int dst_y0);
+
 // row-group form (the production kernel): tensor map with box {120, 28, 1} (160 pixels x 28 rows) over the same view;
 // d_tab is scratch for the per-launch fixed-point tables, vs_warp_rows_tab_ints(dst.w, dst.h) int32 per image
 int vsk_bgr_warp_slots_rows(vs_ctx*, const void* tensor_map, const VsDevImg& src, const int32_t* d_slots,

@@ -1517,6 +1517,127 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
     return vs_set_error(ctx, VS_ERR_INVALID, "bgr_warp: the Lanczos-2 mode runs through vsk_bgr_warp_lz");
 }
 
+// ------------------------------------------------------------------ planar warp (NV12 frames), cv-exact
+// cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) of a 1-channel (the Y plane) or 2-channel (the interleaved UV plane of
+// an NV12 frame) u8 image: the same fixed-point grid as the BGR warp (AB_BITS 10, INTER_BITS 5, 15-bit weights).  A warp
+// owns 128 output pixels of a row, four per lane (one 4- or 8-byte store); a CTA a 128 x 32 tile: the column terms are
+// computed once per lane, the row terms once per CTA.  Taps are byte (pair) loads through L1.
+constexpr int PW_THREADS = 256, PW_W = 128, PW_H = 32;
+
+template <int CH>
+__global__ void __launch_bounds__(PW_THREADS)
+k_plane_warp_cv(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
+                const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
+                uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
+                int dst_x0, int dst_y0, int src_al, int dst_al)
+{
+    constexpr int P = 10;
+    constexpr double SCALE = 1024.0;
+    constexpr int ROUND = 16;
+    __shared__ int2 sXY0[PW_H];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int ox0 = blockIdx.x * PW_W, oy0 = blockIdx.y * PW_H;
+    const int slot = slots ? slots[b] : b;
+    const uint8_t* src = src_base + (size_t)slot * src_bs;
+    uint8_t* dst = dst_base + (size_t)b * dst_bs;
+    const VsWarpCoef cf = coefs[b];
+    if (tid < PW_H) {
+        const double y = (double)(oy0 + tid + dst_y0);
+        sXY0[tid] = make_int2(__double2int_rn((cf.i01 * y + cf.i02) * SCALE) + ROUND,
+                              __double2int_rn((cf.i11 * y + cf.i12) * SCALE) + ROUND);
+    }
+    const int xo = ox0 + 4 * lane;
+    int ad[4], bd[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const double x = (double)(xo + j + dst_x0);
+        ad[j] = __double2int_rn(cf.i00 * x * SCALE);
+        bd[j] = __double2int_rn(cf.i10 * x * SCALE);
+    }
+    __syncthreads();
+    if (xo >= dw) return;
+    const int npx = min(4, dw - xo);
+    for (int r = warp; r < PW_H; r += PW_THREADS / 32) {
+        const int yo = oy0 + r;
+        if (yo >= dh) break;
+        const int2 xy0 = sXY0[r];
+        uint32_t px[4][CH];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int sfx = xy0.x + ad[j], sfy = xy0.y + bd[j];
+            const int sx = sfx >> P, sy = sfy >> P;
+            const uint32_t fx = ((uint32_t)sfx >> 5) & 31u, fy = ((uint32_t)sfy >> 5) & 31u;
+            const bool x0 = (unsigned)sx < (unsigned)w, x1 = (unsigned)(sx + 1) < (unsigned)w;
+            const bool y0 = (unsigned)sy < (unsigned)h, y1 = (unsigned)(sy + 1) < (unsigned)h;
+            const uint8_t* p = src + (ptrdiff_t)sy * src_stride + (ptrdiff_t)sx * CH;
+            uint32_t t[4] = {0u, 0u, 0u, 0u};        // taps (x, y), (x+1, y), (x, y+1), (x+1, y+1), channels in bytes
+            if (CH == 1) {
+                if (x0 && y0) t[0] = __ldg(p);
+                if (x1 && y0) t[1] = __ldg(p + 1);
+                if (x0 && y1) t[2] = __ldg(p + src_stride);
+                if (x1 && y1) t[3] = __ldg(p + src_stride + 1);
+            } else if (src_al) {
+                if (x0 && y0) t[0] = __ldg(reinterpret_cast<const uint16_t*>(p));
+                if (x1 && y0) t[1] = __ldg(reinterpret_cast<const uint16_t*>(p + 2));
+                if (x0 && y1) t[2] = __ldg(reinterpret_cast<const uint16_t*>(p + src_stride));
+                if (x1 && y1) t[3] = __ldg(reinterpret_cast<const uint16_t*>(p + src_stride + 2));
+            } else {
+                if (x0 && y0) t[0] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8);
+                if (x1 && y0) t[1] = (uint32_t)__ldg(p + 2) | ((uint32_t)__ldg(p + 3) << 8);
+                if (x0 && y1) t[2] = (uint32_t)__ldg(p + src_stride) | ((uint32_t)__ldg(p + src_stride + 1) << 8);
+                if (x1 && y1) t[3] = (uint32_t)__ldg(p + src_stride + 2) | ((uint32_t)__ldg(p + src_stride + 3) << 8);
+            }
+            // (sum w p + 16384) >> 15 with w = 32 wx wy  ==  (sum wx wy p + 512) >> 10
+            const uint32_t w00 = (32u - fx) * (32u - fy), w10 = fx * (32u - fy), w01 = (32u - fx) * fy, w11 = fx * fy;
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const uint32_t v = w00 * ((t[0] >> (8 * c)) & 0xffu) + w10 * ((t[1] >> (8 * c)) & 0xffu) +
+                                   w01 * ((t[2] >> (8 * c)) & 0xffu) + w11 * ((t[3] >> (8 * c)) & 0xffu);
+                px[j][c] = (v + 512u) >> 10;
+            }
+        }
+        uint8_t* d = dst + (size_t)yo * dst_stride + (size_t)xo * CH;
+        if (dst_al && npx == 4) {
+            if (CH == 1) {
+                *reinterpret_cast<uint32_t*>(d) = px[0][0] | (px[1][0] << 8) | (px[2][0] << 16) | (px[3][0] << 24);
+            } else {
+                *reinterpret_cast<uint2*>(d) = make_uint2(px[0][0] | (px[0][CH - 1] << 8) | (px[1][0] << 16) | (px[1][CH - 1] << 24),
+                                                          px[2][0] | (px[2][CH - 1] << 8) | (px[3][0] << 16) | (px[3][CH - 1] << 24));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (j < npx) {
+#pragma unroll
+                    for (int c = 0; c < CH; c++) d[j * CH + c] = (uint8_t)px[j][c];
+                }
+        }
+    }
+}
+
+int vsk_plane_warp_slots(vs_ctx* ctx, const VsDevImg& src, int channels, const int32_t* d_slots, const VsWarpCoef* d_coef,
+                         const VsDevImg& dst, int dst_x0, int dst_y0)
+{
+    VS_REQUIRE(ctx, channels == 1 || channels == 2, "plane_warp: 1 or 2 channels");
+    VS_REQUIRE(ctx, src.w > 0 && src.h > 0, "plane_warp: empty source");
+    if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
+    VS_REQUIRE(ctx, vs_cdiv(dst.h, PW_H) <= 65535 && dst.batch <= 65535, "plane_warp: grid too large");
+    const int src_al = aligned_to(src.data, 2) && src.stride % 2 == 0 && src.batch_stride % 2 == 0;
+    const int va = 4 * channels;
+    const int dst_al = aligned_to(dst.data, va) && dst.stride % va == 0 && dst.batch_stride % va == 0;
+    dim3 grid(vs_cdiv(dst.w, PW_W), vs_cdiv(dst.h, PW_H), dst.batch);
+    VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
+    if (channels == 1)
+        k_plane_warp_cv<1><<<grid, PW_THREADS, 0, ctx->stream>>>((const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
+            d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al, dst_al);
+    else
+        k_plane_warp_cv<2><<<grid, PW_THREADS, 0, ctx->stream>>>((const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
+            d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al, dst_al);
+    VS_LAUNCH_CHECK(ctx);
+    return VS_OK;
+}
+
 // Q11 Lanczos-2 weights of the 64 fractions q / 64 (taps at -1, 0, 1, 2): the reference's lanczos2 polynomial
 // (generators.cpp:31-47) in double, normalised; the rounding residue goes to the largest weight (rows sum to 2048)
 static const LzTables& lz_tables()

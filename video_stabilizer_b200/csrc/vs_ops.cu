@@ -387,6 +387,33 @@ int vs_bgr_warp_u8(vs_ctx* ctx, const vs_img* src, const double* M6, const vs_im
     return st.finish();
 }
 
+int vs_plane_warp_u8(vs_ctx* ctx, const vs_img* src, int channels, const double* M6, const vs_img* dst,
+                     int dst_x0, int dst_y0, int mem)
+{
+    if (!ctx) return VS_ERR_INVALID;
+    VS_TRY(check_mem(ctx, mem)); VS_TRY(check_img(ctx, src, "plane_warp source")); VS_TRY(check_img(ctx, dst, "plane_warp destination"));
+    VS_REQUIRE(ctx, M6, "plane_warp: matrix is NULL");
+    VS_REQUIRE(ctx, channels == 1 || channels == 2, "plane_warp: 1 or 2 channels");
+    VS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int batch = src->batch < 1 ? 1 : src->batch;
+    std::vector<VsWarpCoef> coef(batch);
+    for (int b = 0; b < batch; b++) vs_warp_coef_from_forward(M6 + 6 * b, &coef[b]);
+    Stage st(ctx);
+    st.want_raw(coef.size() * sizeof(VsWarpCoef));
+    if (mem == VS_MEM_HOST) { st.want_img(src, channels); st.want_img(dst, channels); }
+    VS_TRY(st.reserve());
+    void* dcoef;
+    VS_TRY(st.raw(coef.data(), coef.size() * sizeof(VsWarpCoef), true, &dcoef));
+    if (mem == VS_MEM_DEVICE)
+        return vsk_plane_warp_slots(ctx, vs_dev_img(src), channels, nullptr, (const VsWarpCoef*)dcoef, vs_dev_img(dst), dst_x0, dst_y0);
+    VsDevImg dsrc, ddst;
+    VS_TRY(st.img(src, channels, 1, true, &dsrc));
+    VS_TRY(st.img(dst, channels, 1, false, &ddst));
+    VS_TRY(vsk_plane_warp_slots(ctx, dsrc, channels, nullptr, (const VsWarpCoef*)dcoef, ddst, dst_x0, dst_y0));
+    VS_TRY(st.img_out(ddst, dst, channels, 1));
+    return st.finish();
+}
+
 int vs_debug_invert4(vs_ctx* ctx, const double* H, int n, double* out_quad, double* out_serial, double* out_cond)
 {
     if (!ctx) return VS_ERR_INVALID;

@@ -284,3 +284,22 @@ def warpBySimilarityTransform(src: np.ndarray, transform: SimilarityTransform, c
     capi.check(ctx.handle, ctx.lib.vs_bgr_warp_u8(ctx.handle, C.byref(capi.img_of(src)), capi.ptr(M), C.byref(capi.img_of(dst)),
                                                   crop, crop, mode, border, capi.VS_MEM_HOST), "vs_bgr_warp_u8")
     return dst
+
+
+def PlaneWarp(src: np.ndarray, M6, out_w: int | None = None, out_h: int | None = None, dx0: int = 0, dy0: int = 0,
+              ctx: Context | None = None) -> np.ndarray:
+    """cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) of a (h, w) or (h, w, 2) u8 image (the Y / UV plane of an NV12 frame;
+    vs_plane_warp_u8): window (dx0, dy0, out_w, out_h) of the output under the forward 2x3 matrix M6."""
+    ctx = ctx or default_context()
+    src = _u8(src)
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    h, w = src.shape[:2]
+    out_w = w if out_w is None else out_w
+    out_h = h if out_h is None else out_h
+    dst = np.empty((out_h, out_w) if src.ndim == 2 else (out_h, out_w, ch), np.uint8)
+    M = np.ascontiguousarray(M6, np.float64)
+    simg = capi.VsImg(src.ctypes.data, w, h, src.strides[0], 1, 0)
+    dimg = capi.VsImg(dst.ctypes.data, out_w, out_h, dst.strides[0], 1, 0)
+    capi.check(ctx.handle, ctx.lib.vs_plane_warp_u8(ctx.handle, C.byref(simg), ch, capi.ptr(M), C.byref(dimg), dx0, dy0,
+                                                    capi.VS_MEM_HOST), "vs_plane_warp_u8")
+    return dst
