@@ -84,6 +84,8 @@ int   vsh_stabilizer_process(void*, const uint8_t* bgr, int w, int h, int64_t ro
 
 /* ---- ClipStabilizer: batched VideoStabilizer (clip_stabilizer.hpp) */
 void* vsh_clipstab_create(int device, int width, int height, int chunk_frames, const vsh_stab_params* p);
+/* the same for NV12 frames in and out (VS_CLIP_NV12 in vstab.h): 3/2 bytes per pixel, even width / height / crop */
+void* vsh_clipstab_create_nv12(int device, int width, int height, int chunk_frames, const vsh_stab_params* p);
 void  vsh_clipstab_destroy(void*);
 int   vsh_clipstab_reset(void*);
 /* sub-chunk (frames) of the host-to-host transfer/compute pipeline inside feed(); default 32 */
@@ -139,6 +141,9 @@ int   vsh_parttraj_run(void*, const double* meas_all, const uint8_t* ok_all, dou
  * lanes: sub-chunks in flight on the GPU (0 = default) */
 void* vsh_partstab_create(int device, int rank, int world, int width, int height, int64_t total_frames, int sub_frames,
                           int block, const vsh_stab_params* p, const char* exchange_name, int resident, int host_threads, int lanes);
+/* the same for a video of NV12 frames (VS_CLIP_NV12 in vstab.h) */
+void* vsh_partstab_create_nv12(int device, int rank, int world, int width, int height, int64_t total_frames, int sub_frames,
+                               int block, const vsh_stab_params* p, const char* exchange_name, int resident, int host_threads, int lanes);
 void  vsh_partstab_destroy(void*);
 /* local frame list of the worker: own frames in video order, each foreign-preceded run headed by its halo frame */
 int     vsh_partstab_local_count(void*);

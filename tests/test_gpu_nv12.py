@@ -125,3 +125,82 @@ def test_nv12_clip_rejects_what_it_cannot_do(gpu):
     with pytest.raises(capi.VsError):
         clip.warp([0], T, mode=capi.VS_WARP_LANCZOS2)   # BGR-only modes
     clip.close()
+
+
+# ---------------------------------------------------------------- the batched host classes on NV12 frames
+@pytest.fixture(scope="module")
+def host(gpu):
+    from video_stabilizer_b200 import host
+    host.load()
+    return host
+
+
+@pytest.mark.parametrize("chunks,crop", [((40,), 8), ((7, 13, 1, 19), 0), ((48,), 32)])
+def test_clip_stabilizer_nv12(host, ob, chunks, crop):
+    """ClipStabilizer on NV12 frames: the measurements are those of the BGR pipeline fed the gray frames (Y in every channel),
+    the corrections follow, and every produced frame is the oracle's plane-by-plane warp of its NV12 frame."""
+    w, h, n = 320, 180, sum(chunks)
+    nv12, _ = nv12_clip(ob, w, h, n, 21)
+    gray_bgr = np.repeat(nv12[:, :h, :, None], 3, 3)
+    p = host.stab_params_default()
+    p.crop_pixels = crop
+    ref = host.ClipStabilizer(w, h, n, p, 0)
+    ref.feed(gray_bgr)
+    meas_want, ok_want, corr_want = ref.last_records(n)
+    cs = host.ClipStabilizer(w, h, max(chunks), p, 0, nv12=True)
+    cs.set_pipeline_frames(8)            # the host-to-host pipeline: asynchronous uploads into pyramid level 0
+    got, corr = [], []
+    pos = 0
+    for c in chunks:
+        out = cs.feed(nv12[pos:pos + c])
+        got.extend(list(out))
+        corr.extend(list(cs.last_records(c)[2]))
+        pos += c
+    assert len(got) == len(corr_want) == n - p.lag
+    assert got[0].shape == ((h - 2 * crop) * 3 // 2, w - 2 * crop)
+    for k in range(len(got)):
+        assert corner_displacement(corr[k], corr_want[k], w, h) <= 1e-6, k
+        assert np.array_equal(got[k], ob.warp_nv12(nv12[k], w, h, corr[k], crop)), k
+
+
+@pytest.mark.parametrize("world,sub,block,resident", [(1, 16, 3, True), (2, 12, 1, False), (3, 10, 1, True)])
+def test_partitioned_stabilizer_nv12_equals_single_stream(host, world, sub, block, resident):
+    """ONE NV12 video frame-chunk partitioned over `world` workers equals the single-stream NV12 pipeline bit for bit."""
+    import os
+    import threading
+    from video_stabilizer_b200 import _capi as capi
+    from oracle import binding as ob
+    w, h, n = 320, 180, 50
+    nv12, _ = nv12_clip(ob, w, h, n, 41)
+    p = host.stab_params_default()
+    p.crop_pixels = 8
+    want = host.ClipStabilizer(w, h, n, p, 0, nv12=True).feed(nv12)
+    name = "/vstab_gputest_nv12_%d_%d%d" % (os.getpid(), world, sub) if world > 1 else ""
+    ndev = max(1, capi.load().vs_device_count())
+    workers = [host.PartitionedStabilizer(r, world, w, h, n, sub, block, p, name, resident, device=r % ndev, host_threads=2, nv12=True)
+               for r in range(world)]
+    out, errors = {}, []
+
+    def run(r):
+        try:
+            ps = workers[r]
+            local = np.ascontiguousarray(nv12[ps.local_frames])
+            if resident:
+                ps.upload_resident(local.ctypes.data, local.strides[1], local.strides[0])
+                got = ps.stabilize(None)
+            else:
+                got = ps.stabilize(local)
+            for f, g in zip(ps.output_frames, got):
+                out[int(f)] = g
+        except Exception as e:       # noqa: BLE001
+            errors.append((r, repr(e)))
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors
+    assert sorted(out) == list(range(n - p.lag))
+    for f in range(n - p.lag):
+        assert np.array_equal(out[f], want[f]), f

@@ -10,9 +10,9 @@
 
 namespace vstab {
 
-ClipStabilizer::ClipStabilizer(int device, int width, int height, int chunk_frames, const VideoStabilizerParams& params)
+ClipStabilizer::ClipStabilizer(int device, int width, int height, int chunk_frames, const VideoStabilizerParams& params, bool nv12)
     : m_w(width), m_h(height), m_chunk(chunk_frames), m_capacity(chunk_frames + std::max(0, params.lag) + 1),
-      m_crop(std::max(0, params.crop_pixels)), m_params(params), m_trajectory(params)
+      m_crop(std::max(0, params.crop_pixels)), m_nv12(nv12), m_params(params), m_trajectory(params)
 {
     if (width <= 0 || height <= 0 || chunk_frames <= 0) throw std::runtime_error("ClipStabilizer: bad geometry");
     if (2 * m_crop >= width || 2 * m_crop >= height) throw std::runtime_error("ClipStabilizer: crop_pixels removes the whole frame");
@@ -20,7 +20,7 @@ ClipStabilizer::ClipStabilizer(int device, int width, int height, int chunk_fram
         throw std::runtime_error(std::string("ClipStabilizer: cannot create a GPU context: ") + vs_last_error(nullptr));
     vs_align_params cp;
     to_c_params(params.aligner, &cp);
-    if (vs_clip_create(m_ctx, width, height, m_capacity, chunk_frames, &cp, 0, &m_clip) != VS_OK) {
+    if (vs_clip_create(m_ctx, width, height, m_capacity, chunk_frames, &cp, nv12 ? VS_CLIP_NV12 : 0, &m_clip) != VS_OK) {
         std::string msg = std::string("ClipStabilizer: ") + vs_last_error(m_ctx);
         vs_ctx_destroy(m_ctx);
         m_ctx = nullptr;
@@ -166,8 +166,6 @@ int ClipStabilizer::process(int n, uint8_t* out, int64_t out_frame_stride, int o
     //      batches while the host is still smoothing the later ones (asynchronous outputs only)
     std::vector<int32_t> due_slots;
     std::vector<double> due_T;
-    const size_t out_frame_bytes = (size_t)out_width() * out_height() * 3;
-    (void)out_frame_bytes;
     int launched = 0;
     int batch = std::min(16, m_warp_batch);   // first launch early (the GPU idles until then), later ones grow to m_warp_batch
     auto launch_warps = [&](int upto) {

@@ -26,7 +26,9 @@ namespace vstab {
 class ClipStabilizer {
 public:
     // Throws std::runtime_error when the device or its memory is unavailable.
-    ClipStabilizer(int device, int width, int height, int chunk_frames, const VideoStabilizerParams& params);
+    // nv12: the frames fed and produced are NV12 (VS_CLIP_NV12 in vstab.h: `height` rows of Y then height / 2 rows of
+    // interleaved UV; 3/2 bytes per pixel, even width / height / crop) instead of interleaved BGR.
+    ClipStabilizer(int device, int width, int height, int chunk_frames, const VideoStabilizerParams& params, bool nv12 = false);
     ~ClipStabilizer();
     ClipStabilizer(const ClipStabilizer&) = delete;
     ClipStabilizer& operator=(const ClipStabilizer&) = delete;
@@ -35,9 +37,9 @@ public:
     // and the delay line start over.
     void reset();
 
-    // Feed the next n (<= chunk_frames) frames.  `frames`: interleaved BGR, row_stride /
+    // Feed the next n (<= chunk_frames) frames.  `frames`: interleaved BGR (or NV12 frames), row_stride /
     // frame_stride in bytes, in host (VS_MEM_HOST) or device (VS_MEM_DEVICE) memory.
-    // Stabilized frames that became due are written densely ((w-2c) x (h-2c) x 3 each,
+    // Stabilized frames that became due are written densely ((w-2c) x (h-2c) x 3 each; NV12: x 3/2,
     // out_frame_stride bytes apart) to `out` in `out_mem`; returns how many (<= n).
     // With host input AND host output the call is software-pipelined over sub-chunks of
     // pipeline_frames(): the H2D copy of sub-chunk k+1 (copy-in stream) and the D2H copy of
@@ -60,6 +62,8 @@ public:
 
     int out_width() const { return m_w - 2 * m_crop; }
     int out_height() const { return m_h - 2 * m_crop; }
+    size_t out_frame_bytes() const { return (size_t)out_width() * out_height() * 3 / (m_nv12 ? 2 : 1); }
+    bool nv12() const { return m_nv12; }
     int ring_capacity() const { return m_capacity; }
     long frames_fed() const { return m_fed; }
     vs_ctx* context() const { return m_ctx; }
@@ -73,6 +77,7 @@ public:
 
 private:
     int m_w, m_h, m_chunk, m_capacity, m_crop;
+    bool m_nv12 = false;
     int m_lanes = 3;       // device-resident chunks of >= 128 pairs: up to this many pieces on the clip's solver lanes
     int m_sub = 32;        // sub-chunk of the host-to-host pipeline
     int m_warp_batch = 96; // largest batch of due frames per warp launch while the host trajectory is still running (16, 32, 64, 96, 96 ...)

@@ -270,6 +270,12 @@ void* vsh_clipstab_create(int device, int width, int height, int chunk_frames, c
     guarded([&] { c = new vstab::ClipStabilizer(device, width, height, chunk_frames, stab_params(p)); return 0; });
     return c;
 }
+void* vsh_clipstab_create_nv12(int device, int width, int height, int chunk_frames, const vsh_stab_params* p)
+{
+    vstab::ClipStabilizer* c = nullptr;
+    guarded([&] { c = new vstab::ClipStabilizer(device, width, height, chunk_frames, stab_params(p), true); return 0; });
+    return c;
+}
 void vsh_clipstab_destroy(void* c) { delete (vstab::ClipStabilizer*)c; }
 int vsh_clipstab_reset(void* c) { return guarded([&] { ((vstab::ClipStabilizer*)c)->reset(); return 0; }); }
 int vsh_clipstab_set_pipeline_frames(void* c, int frames) { ((vstab::ClipStabilizer*)c)->set_pipeline_frames(frames); return 0; }
@@ -417,6 +423,17 @@ void* vsh_partstab_create(int device, int rank, int world, int width, int height
     guarded([&] {
         s = new vstab::PartitionedStabilizer(device, rank, world, width, height, (long)total_frames, sub_frames, block, stab_params(p),
                                              exchange_name ? exchange_name : "", resident != 0, host_threads, lanes);
+        return 0;
+    });
+    return s;
+}
+void* vsh_partstab_create_nv12(int device, int rank, int world, int width, int height, int64_t total_frames, int sub_frames,
+                               int block, const vsh_stab_params* p, const char* exchange_name, int resident, int host_threads, int lanes)
+{
+    vstab::PartitionedStabilizer* s = nullptr;
+    guarded([&] {
+        s = new vstab::PartitionedStabilizer(device, rank, world, width, height, (long)total_frames, sub_frames, block, stab_params(p),
+                                             exchange_name ? exchange_name : "", resident != 0, host_threads, lanes, true);
         return 0;
     });
     return s;

@@ -135,8 +135,8 @@ void PartitionedTrajectory::end_video()
 // ================================================================== GPU half
 PartitionedStabilizer::PartitionedStabilizer(int device, int rank, int world, int width, int height, long total_frames,
                                              int sub_frames, int block_subchunks, const VideoStabilizerParams& params,
-                                             const std::string& exchange_name, bool resident, int host_threads, int lanes)
-    : m_w(width), m_h(height), m_crop(std::max(0, params.crop_pixels)), m_resident(resident), m_params(params),
+                                             const std::string& exchange_name, bool resident, int host_threads, int lanes, bool nv12)
+    : m_w(width), m_h(height), m_crop(std::max(0, params.crop_pixels)), m_resident(resident), m_nv12(nv12), m_params(params),
       m_traj(rank, world, width, height, total_frames, sub_frames, block_subchunks, params, exchange_name, host_threads)
 {
     if (2 * m_crop >= width || 2 * m_crop >= height) throw std::runtime_error("PartitionedStabilizer: crop_pixels removes the whole frame");
@@ -148,7 +148,7 @@ PartitionedStabilizer::PartitionedStabilizer(int device, int rank, int world, in
         throw std::runtime_error(std::string("PartitionedStabilizer: cannot create a GPU context: ") + vs_last_error(nullptr));
     vs_align_params cp;
     to_c_params(params.aligner, &cp);
-    if (vs_clip_create(m_ctx, width, height, m_capacity, m_max_lanes * sub_frames, &cp, 0, &m_clip) != VS_OK) {
+    if (vs_clip_create(m_ctx, width, height, m_capacity, m_max_lanes * sub_frames, &cp, nv12 ? VS_CLIP_NV12 : 0, &m_clip) != VS_OK) {
         const std::string msg = std::string("PartitionedStabilizer: ") + vs_last_error(m_ctx);
         vs_ctx_destroy(m_ctx);
         m_ctx = nullptr;

@@ -113,9 +113,10 @@ public:
     // false: frames stream through a ring of (lanes + 1) sub-chunks.
     // lanes: sub-chunks in flight on the GPU, one solver stream each (0 = default: the sub-chunks of a chunk, at most
     // VS_CLIP_SOLVER_LANES, when resident; 2 when streamed)
+    // nv12: the video's frames, in and out, are NV12 (VS_CLIP_NV12 in vstab.h) instead of interleaved BGR
     PartitionedStabilizer(int device, int rank, int world, int width, int height, long total_frames, int sub_frames,
                           int block_subchunks, const VideoStabilizerParams& params, const std::string& exchange_name,
-                          bool resident, int host_threads = 4, int lanes = 0);
+                          bool resident, int host_threads = 4, int lanes = 0, bool nv12 = false);
     ~PartitionedStabilizer();
     PartitionedStabilizer(const PartitionedStabilizer&) = delete;
     PartitionedStabilizer& operator=(const PartitionedStabilizer&) = delete;
@@ -133,12 +134,14 @@ public:
     int lanes() const { return m_lanes; }
     int out_width() const { return m_w - 2 * m_crop; }
     int out_height() const { return m_h - 2 * m_crop; }
+    size_t out_frame_bytes() const { return (size_t)out_width() * out_height() * 3 / (m_nv12 ? 2 : 1); }
     vs_ctx* context() const { return m_ctx; }
     vs_clip* clip() const { return m_clip; }
 
 private:
     int m_w, m_h, m_crop;
     bool m_resident;
+    bool m_nv12 = false;
     int m_lanes = 3, m_max_lanes = 3;
     VideoStabilizerParams m_params;
     PartitionedTrajectory m_traj;

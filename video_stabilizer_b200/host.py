@@ -59,6 +59,7 @@ SYMBOLS = {
     "vsh_stabilizer_destroy": (None, [_P]),
     "vsh_stabilizer_process": (_I, [_P, _P, _I, _I, _I64, _P, _PI, _PI]),
     "vsh_clipstab_create": (_P, [_I, _I, _I, _I, _SP]),
+    "vsh_clipstab_create_nv12": (_P, [_I, _I, _I, _I, _SP]),
     "vsh_clipstab_destroy": (None, [_P]),
     "vsh_clipstab_reset": (_I, [_P]),
     "vsh_clipstab_set_pipeline_frames": (_I, [_P, _I]),
@@ -84,6 +85,7 @@ SYMBOLS = {
     "vsh_parttraj_output_count": (_I, [_P]),
     "vsh_parttraj_run": (_I, [_P, _P, _P, _P, _P]),
     "vsh_partstab_create": (_P, [_I, _I, _I, _I, _I, _I64, _I, _I, _SP, C.c_char_p, _I, _I, _I]),
+    "vsh_partstab_create_nv12": (_P, [_I, _I, _I, _I, _I, _I64, _I, _I, _SP, C.c_char_p, _I, _I, _I]),
     "vsh_partstab_destroy": (None, [_P]),
     "vsh_partstab_local_count": (_I, [_P]),
     "vsh_partstab_local_frame": (_I64, [_P, _I]),
@@ -353,16 +355,19 @@ class ClipStabilizer(_Handle):
     """Batched VideoStabilizer (clip_stabilizer.hpp)."""
     _destroy = "vsh_clipstab_destroy"
 
-    def __init__(self, width, height, chunk_frames, params: VshStabParams | None = None, device: int = 0):
+    def __init__(self, width, height, chunk_frames, params: VshStabParams | None = None, device: int = 0, nv12: bool = False):
+        """nv12: frames in and out are NV12 ((h * 3 / 2, w) u8 arrays) instead of (h, w, 3) BGR."""
         self.params = params or stab_params_default()
-        self.width, self.height, self.chunk = width, height, chunk_frames
-        self.h = C.c_void_p(load().vsh_clipstab_create(device, width, height, chunk_frames, C.byref(self.params)))
+        self.width, self.height, self.chunk, self.nv12 = width, height, chunk_frames, nv12
+        create = load().vsh_clipstab_create_nv12 if nv12 else load().vsh_clipstab_create
+        self.h = C.c_void_p(create(device, width, height, chunk_frames, C.byref(self.params)))
         if not self.h:
             _raise("ClipStabilizer")
         ow, oh = C.c_int(), C.c_int()
         load().vsh_clipstab_out_size(self.h, C.byref(ow), C.byref(oh))
         self.out_w, self.out_h = ow.value, oh.value
-        self.out_frame_bytes = self.out_w * self.out_h * 3
+        self.out_frame_bytes = self.out_w * self.out_h * 3 // (2 if nv12 else 1)
+        self.out_shape = (self.out_h * 3 // 2, self.out_w) if nv12 else (self.out_h, self.out_w, 3)
         self.ctx_handle = C.c_void_p(load().vsh_clipstab_context(self.h))
 
     def reset(self):
@@ -379,7 +384,7 @@ class ClipStabilizer(_Handle):
         """frames: (n,h,w,3) u8 host array; returns the (k,oh,ow,3) stabilized frames that became due."""
         frames = np.ascontiguousarray(frames, np.uint8)
         n = frames.shape[0]
-        out = np.empty((n, self.out_h, self.out_w, 3), np.uint8)
+        out = np.empty((n,) + self.out_shape, np.uint8)
         k = load().vsh_clipstab_feed(self.h, _p(frames), n, frames.strides[1], frames.strides[0], capi.VS_MEM_HOST,
                                      _p(out), self.out_frame_bytes, capi.VS_MEM_HOST)
         if k < 0:
@@ -479,10 +484,12 @@ class PartitionedStabilizer(_Handle):
     _destroy = "vsh_partstab_destroy"
 
     def __init__(self, rank, world, width, height, total_frames, sub_frames, block, params: VshStabParams | None = None,
-                 exchange_name: str = "", resident: bool = True, device: int = 0, host_threads: int = 4, lanes: int = 0):
+                 exchange_name: str = "", resident: bool = True, device: int = 0, host_threads: int = 4, lanes: int = 0,
+                 nv12: bool = False):
         self.params = params or stab_params_default()
-        self.width, self.height = width, height
-        self.h = C.c_void_p(load().vsh_partstab_create(device, rank, world, width, height, total_frames, sub_frames, block,
+        self.width, self.height, self.nv12 = width, height, nv12
+        create = load().vsh_partstab_create_nv12 if nv12 else load().vsh_partstab_create
+        self.h = C.c_void_p(create(device, rank, world, width, height, total_frames, sub_frames, block,
                                                        C.byref(self.params), exchange_name.encode(), int(resident), host_threads, lanes))
         if not self.h:
             _raise("PartitionedStabilizer")
@@ -490,7 +497,8 @@ class PartitionedStabilizer(_Handle):
         ow, oh = C.c_int(), C.c_int()
         lib.vsh_partstab_out_size(self.h, C.byref(ow), C.byref(oh))
         self.out_w, self.out_h = ow.value, oh.value
-        self.out_frame_bytes = self.out_w * self.out_h * 3
+        self.out_frame_bytes = self.out_w * self.out_h * 3 // (2 if nv12 else 1)
+        self.out_shape = (self.out_h * 3 // 2, self.out_w) if nv12 else (self.out_h, self.out_w, 3)
         self.ctx_handle = C.c_void_p(lib.vsh_partstab_context(self.h))
         n = lib.vsh_partstab_local_count(self.h)
         self.local_frames = np.array([lib.vsh_partstab_local_frame(self.h, i) for i in range(n)], np.int64)
@@ -511,7 +519,7 @@ class PartitionedStabilizer(_Handle):
 
     def stabilize(self, local_frames: np.ndarray | None) -> np.ndarray:
         """local_frames: (local_count,h,w,3) u8 host array (None when resident); returns this worker's stabilized frames."""
-        out = np.empty((max(self.outputs, 1), self.out_h, self.out_w, 3), np.uint8)
+        out = np.empty((max(self.outputs, 1),) + self.out_shape, np.uint8)
         if local_frames is None:
             k = self.stabilize_ptr(None, 0, 0, out.ctypes.data, capi.VS_MEM_HOST)
         else:
