@@ -296,7 +296,7 @@ def exchange_name(tag):
 class PartitionedVideo:
     """One rank's share of a synthetic N x F-frame video in a given partition, with its pinned host frames."""
 
-    def __init__(self, R, args, W, H, F, sub, block, resident, tag, seed=CLIP_SEED, share=None):
+    def __init__(self, R, args, W, H, F, sub, block, resident, tag, seed=CLIP_SEED, share=None, nv12=False):
         import torch
         from video_stabilizer_b200 import host, synth
         from video_stabilizer_b200.imgproc import Context
@@ -310,11 +310,11 @@ class PartitionedVideo:
         # rank 0 creates the shared table; the others attach once it exists
         if R.rank == 0:
             self.ps = host.PartitionedStabilizer(R.rank, R.world, W, H, self.total, sub, block, p, name, resident,
-                                                 device=R.local, host_threads=threads)
+                                                 device=R.local, host_threads=threads, nv12=nv12)
         R.barrier()
         if R.rank != 0:
             self.ps = host.PartitionedStabilizer(R.rank, R.world, W, H, self.total, sub, block, p, name, resident,
-                                                 device=R.local, host_threads=threads)
+                                                 device=R.local, host_threads=threads, nv12=nv12)
         R.barrier()
         self.host_threads = threads
         ps = self.ps
@@ -322,14 +322,28 @@ class PartitionedVideo:
         if share is not None:      # a second instance over the same video: the same pinned frames
             self.pinned, self.frames = share.pinned, share.frames
         else:
-            self.pinned = torch.empty((n_local, H, W, 3), dtype=torch.uint8, pin_memory=True)
+            self.pinned = torch.empty((n_local, H * 3 // 2, W) if nv12 else (n_local, H, W, 3), dtype=torch.uint8, pin_memory=True)
             self.frames = self.pinned.numpy()
             ctx = Context(R.local)
             canvas = synth.make_canvas(W, H, 1000 + seed)
             poses = synth.jitter_path(self.total, 1001 + seed)
-            synth.render_frames_gpu(ctx, canvas, poses, ps.local_frames, W, H, self.frames, chunk=32 if W <= 1920 else 8)
+            if nv12:
+                # the same video as NV12 frames: Y = the gray value (the canvas is gray replicated, so BGR2GRAY returns it),
+                # U / V derived from it (any chroma does: it is only warped)
+                bgr = np.empty((min(n_local, 32), H, W, 3), np.uint8)
+                for i0 in range(0, n_local, len(bgr)):
+                    k = min(len(bgr), n_local - i0)
+                    synth.render_frames_gpu(ctx, canvas, poses, ps.local_frames[i0:i0 + k], W, H, bgr[:k], chunk=32 if W <= 1920 else 8)
+                    self.frames[i0:i0 + k, :H] = bgr[:k, :, :, 0]
+                    uv = self.frames[i0:i0 + k, H:].reshape(k, H // 2, W // 2, 2)
+                    uv[..., 0] = bgr[:k, ::2, ::2, 0] // 2 + 64
+                    uv[..., 1] = 191 - bgr[:k, 1::2, 1::2, 0] // 2
+                del bgr
+            else:
+                synth.render_frames_gpu(ctx, canvas, poses, ps.local_frames, W, H, self.frames, chunk=32 if W <= 1920 else 8)
             ctx.close()
-        self.frame_bytes = W * H * 3
+        self.frame_bytes = W * H * 3 // 2 if nv12 else W * H * 3
+        self.row_stride = W if nv12 else W * 3
         self.stream = torch.cuda.Stream()
         assert self.stream.cuda_stream != 0
         # a real (non-default) torch stream, borrowed by the library: the CUDA events of the timed region are recorded on
@@ -444,7 +458,7 @@ def host_copy_ceiling(R, seconds=0.4, mbytes=256):
     return {"h2d_alone_gbs": R.reduce(up1, "sum"), "h2d_duplex_gbs": R.reduce(up2, "sum"), "d2h_duplex_gbs": R.reduce(down2, "sum")}
 
 
-def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_sub, profile, tag, seed=CLIP_SEED):
+def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_sub, profile, tag, seed=CLIP_SEED, nv12=False):
     """value (resident, contiguous chunk per rank) and e2e (host-streamed, interleaved sub-chunks) of one video size."""
     import torch
     from video_stabilizer_b200 import _capi as capi
@@ -460,14 +474,14 @@ def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_
     inflight = max(1, args.inflight)
     pvs = []
     for i in range(inflight):
-        pvs.append(PartitionedVideo(R, args, W, H, F, sub, block, True, tag + "r%d" % i, seed, share=pvs[0] if i else None))
+        pvs.append(PartitionedVideo(R, args, W, H, F, sub, block, True, tag + "r%d" % i, seed, share=pvs[0] if i else None, nv12=nv12))
     pv = pvs[0]
     ps = pv.ps
     outs_dev = []
     for q in pvs:
-        q.ps.upload_resident(q.frames.ctypes.data, W * 3, q.frame_bytes)
+        q.ps.upload_resident(q.frames.ctypes.data, q.row_stride, q.frame_bytes)
         q.ps.synchronize()
-        outs_dev.append(torch.empty((max(ps.outputs, 1), ps.out_h, ps.out_w, 3), dtype=torch.uint8, device="cuda"))
+        outs_dev.append(torch.empty((max(ps.outputs, 1),) + ps.out_shape, dtype=torch.uint8, device="cuda"))
 
     def make_step(q, out):
         def step_resident():
@@ -539,14 +553,14 @@ def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_
     if e2e_steps > 0:
         pes = []
         for i in range(inflight):
-            pes.append(PartitionedVideo(R, args, W, H, F, e2e_sub, 1, False, tag + "s%d" % i, seed, share=pes[0] if i else None))
+            pes.append(PartitionedVideo(R, args, W, H, F, e2e_sub, 1, False, tag + "s%d" % i, seed, share=pes[0] if i else None, nv12=nv12))
         pe = pes[0]
-        outs_host = [torch.empty((max(pe.ps.outputs, 1), pe.ps.out_h, pe.ps.out_w, 3), dtype=torch.uint8, pin_memory=True)
+        outs_host = [torch.empty((max(pe.ps.outputs, 1),) + pe.ps.out_shape, dtype=torch.uint8, pin_memory=True)
                      for _ in pes]
 
         def make_e2e(q, out):
             def step_e2e():
-                k = q.ps.stabilize_ptr(q.frames.ctypes.data, W * 3, q.frame_bytes, out.data_ptr(), capi.VS_MEM_HOST)
+                k = q.ps.stabilize_ptr(q.frames.ctypes.data, q.row_stride, q.frame_bytes, out.data_ptr(), capi.VS_MEM_HOST)
                 assert k == q.ps.outputs, k
             return step_e2e
 
@@ -585,6 +599,15 @@ def run_gpu_arm(args):
                        "ms_per_step": r4["ms_per_step"], "frames_per_step": r4["frames_per_step"],
                        "frames_per_video_per_gpu": args.frames_4k, "pairs_converged": r4["pairs_converged"], "pairs_seen": r4["pairs_seen"],
                        "e2e": r4.get("e2e")}
+
+        # the same 1080p video as NV12 frames in and out (decoder output fed straight in; VS_CLIP_NV12): half the
+        # bytes over PCIe, no colour conversion; the alignment is that of the gray frames
+        rn = measure_partitioned(R, args, W, H, F, max(2, args.steps // 2), 2, args.passes, max(1, args.steps // 2), args.e2e_sub,
+                                 False, "n", nv12=True)
+        extra["nv12"] = {"metric": "stabilized_frames_per_sec_1080p_nv12", "value": rn["value"], "unit": UNIT, "n_gpus": world,
+                         "ms_per_step": rn["ms_per_step"], "frames_per_step": rn["frames_per_step"], "size": "%dx%d" % (W, H),
+                         "pairs_converged": rn["pairs_converged"], "pairs_seen": rn["pairs_seen"], "e2e": rn.get("e2e"),
+                         "note": "frames are NV12 in and out (1.5 B per pixel each way); no counterpart upstream"}
 
     if rank != 0:
         R.close()
@@ -673,9 +696,10 @@ def run_gpu_arm(args):
     e2e["host_ceiling"] = dict(ceiling, note="pinned copies on every rank at once, both directions together; GB/s summed over ranks")
     e2e["frac_of_host_ceiling"] = achieved / ceil_sum if ceil_sum > 0 else None
     e2e["value_per_gpu"] = e2e["value"] / world
-    if "4k" in extra and extra["4k"].get("e2e"):
-        x = extra["4k"]["e2e"]
-        x["frac_of_host_ceiling"] = (x["h2d_gbs"] + x["d2h_gbs"]) / ceil_sum if ceil_sum > 0 else None
+    for key in ("4k", "nv12"):
+        if key in extra and extra[key].get("e2e"):
+            x = extra[key]["e2e"]
+            x["frac_of_host_ceiling"] = (x["h2d_gbs"] + x["d2h_gbs"]) / ceil_sum if ceil_sum > 0 else None
 
     line = {
         "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -239,6 +239,25 @@ int clip_enqueue_upload(vs_clip* c, int slot0, int n, const uint8_t* frames, int
     vs_ctx* ctx = c->ctx;
     if (c->nv12) {
         const VsLevel& L0 = c->g.lv[0];
+        if (n > 1 && row_stride > 0 && frame_stride % row_stride == 0 && c->g.pyr_slot_bytes % (size_t)L0.pitch == 0) {
+            // the Y planes of the whole range in one 3-D copy (slices = frames), the UV planes in another: a copy per
+            // plane per frame costs the DMA engine a few microseconds each, a quarter of a 16-frame sub-chunk's transfer
+            cudaMemcpy3DParms py = {};
+            py.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(frames), (size_t)row_stride, (size_t)c->w, (size_t)(frame_stride / row_stride));
+            py.dstPtr = make_cudaPitchedPtr(c->d_pyr + (size_t)slot0 * c->g.pyr_slot_bytes + L0.img_off, (size_t)L0.pitch, (size_t)c->w,
+                                            c->g.pyr_slot_bytes / (size_t)L0.pitch);
+            py.extent = make_cudaExtent((size_t)c->w, (size_t)c->h, (size_t)n);
+            py.kind = kind;
+            VS_CUDA(ctx, cudaMemcpy3DAsync(&py, stream));
+            cudaMemcpy3DParms pu = {};
+            pu.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(frames) + (size_t)row_stride * c->h, (size_t)row_stride, (size_t)c->w,
+                                            (size_t)(frame_stride / row_stride));
+            pu.dstPtr = make_cudaPitchedPtr(c->d_uv + (size_t)slot0 * c->uv_slot_bytes, c->uv_pitch, (size_t)c->w, (size_t)c->h / 2);
+            pu.extent = make_cudaExtent((size_t)c->w, (size_t)c->h / 2, (size_t)n);
+            pu.kind = kind;
+            VS_CUDA(ctx, cudaMemcpy3DAsync(&pu, stream));
+            return VS_OK;
+        }
         for (int i = 0; i < n; i++) {
             const uint8_t* f = frames + (size_t)frame_stride * i;
             VS_CUDA(ctx, cudaMemcpy2DAsync(c->d_pyr + (size_t)(slot0 + i) * c->g.pyr_slot_bytes + L0.img_off, (size_t)L0.pitch,
@@ -372,6 +391,8 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
         }
         g.total_tiles = toff;
         g.pyr_slot_bytes = vs_align_up(off, 256);
+        // NV12 clips upload the Y planes of a run of slots as the slices of one 3-D copy: whole level-0 rows per slot
+        if (flags & VS_CLIP_NV12) g.pyr_slot_bytes = vs_align_up(off, (size_t)2 * g.lv[0].pitch);
     }
     if (g.max_tiles > 65535 || (size_t)2 * g.max_tiles * 4 + (size_t)g.max_tiles + 64 > 216 * 1024) {   // keys + chunk words of the selection
         const int mt = g.max_tiles;
