@@ -1519,17 +1519,18 @@ int vsk_bgr_warp_slots(vs_ctx* ctx, const VsDevImg& src, const int32_t* d_slots,
 
 // ------------------------------------------------------------------ planar warp (NV12 frames), cv-exact
 // cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) of a 1-channel (the Y plane) or 2-channel (the interleaved UV plane of
-// an NV12 frame) u8 image: the same fixed-point grid as the BGR warp (AB_BITS 10, INTER_BITS 5, 15-bit weights).  A warp
-// owns 128 output pixels of a row, four per lane (one 4- or 8-byte store); a CTA a 128 x 32 tile: the column terms are
-// computed once per lane, the row terms once per CTA.  Taps are byte (pair) loads through L1.
+// an NV12 frame) u8 image: the same fixed-point grid as the BGR warp (AB_BITS 10, INTER_BITS 5, 15-bit weights).  A lane
+// owns four output pixels of a row (one 4- or 8-byte store), a CTA a 128 x 32 tile: the column terms are computed once
+// per lane, the row terms once per CTA.  Regular groups read two aligned word windows through L1, the others byte taps.
 constexpr int PW_THREADS = 256, PW_W = 128, PW_H = 32;
+static_assert(PW_THREADS == 256 && PW_W == 128 && PW_H == 32, "k_plane_warp_cv maps 8 warps onto 4 x 2 blocks of 32 x 16 pixels");
 
 template <int CH>
 __global__ void __launch_bounds__(PW_THREADS)
 k_plane_warp_cv(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
                 const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
                 uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
-                int dst_x0, int dst_y0, int src_al, int dst_al)
+                int dst_x0, int dst_y0, int src_al, int src_al4, int dst_al)
 {
     constexpr int P = 10;
     constexpr double SCALE = 1024.0;
@@ -1547,7 +1548,11 @@ k_plane_warp_cv(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_
         sXY0[tid] = make_int2(__double2int_rn((cf.i01 * y + cf.i02) * SCALE) + ROUND,
                               __double2int_rn((cf.i11 * y + cf.i12) * SCALE) + ROUND);
     }
-    const int xo = ox0 + 4 * lane;
+    // a warp covers 32 pixels x 4 rows per step (eight lanes of four pixels per row), a quarter of the tile's width over 16
+    // of its rows: a similarity's irregular groups (where the source column or row index steps by 0 or 2) lie on two nearly
+    // straight lines about 1 / |A| and 1 / |B| pixels apart, and a compact footprint meets them four times less often
+    // than a 128-pixel row segment would
+    const int xo = ox0 + 32 * (warp & 3) + 4 * (lane & 7);
     int ad[4], bd[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -1558,16 +1563,70 @@ k_plane_warp_cv(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_
     __syncthreads();
     if (xo >= dw) return;
     const int npx = min(4, dw - xo);
-    for (int r = warp; r < PW_H; r += PW_THREADS / 32) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int r = 16 * (warp >> 2) + 4 * k + (lane >> 3);
         const int yo = oy0 + r;
-        if (yo >= dh) break;
+        if (yo >= dh) continue;
         const int2 xy0 = sXY0[r];
         uint32_t px[4][CH];
+        int sfx[4], sfy[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { sfx[j] = xy0.x + ad[j]; sfy[j] = xy0.y + bd[j]; }
+        const int sx0 = sfx[0] >> P, sy0 = sfy[0] >> P;
+        // regular group: the four pixels read source columns sx0 .. sx0 + 4 of rows sy0, sy0 + 1, all inside the image (any
+        // similarity close to the identity, away from the border): two aligned word windows instead of 16 byte loads, the
+        // vertical blend of a column pair as one packed multiply-add, the horizontal one as IDP.2A; fractions stay per pixel
+        // (the aligned words that hold the window must end inside the row: the last row of a tightly packed image has
+        // nothing behind it)
+        bool regular = src_al4 && sx0 >= 0 && sx0 + 4 < w && sy0 >= 0 && sy0 + 1 < h &&
+                       (((sx0 * CH) >> 2) + CH + 1) * 4 <= w * CH;
+#pragma unroll
+        for (int j = 1; j < 4; j++) regular = regular && (sfx[j] >> P) == sx0 + j && (sfy[j] >> P) == sy0;
+        if (regular) {
+            const uint8_t* row = src + (size_t)sy0 * src_stride;
+            const int byte0 = sx0 * CH;
+            const uint32_t* wt_ = reinterpret_cast<const uint32_t*>(row) + (byte0 >> 2);
+            const uint32_t* wb_ = reinterpret_cast<const uint32_t*>(row + src_stride) + (byte0 >> 2);
+            const uint32_t sh = 8u * (uint32_t)(byte0 & 3);
+            uint32_t qt[4], qb[4];     // CH 1: [p_j, 0, p_j+1, 0] per pixel; CH 2: [U_j V_j U_j+1 V_j+1]
+            if (CH == 1) {
+                const uint32_t t0 = __ldg(wt_), t1 = __ldg(wt_ + 1), b0 = __ldg(wb_), b1 = __ldg(wb_ + 1);
+                const uint32_t ta = __funnelshift_r(t0, t1, sh), te = (t1 >> sh) & 0xffu;
+                const uint32_t ba = __funnelshift_r(b0, b1, sh), be = (b1 >> sh) & 0xffu;
+                qt[0] = __byte_perm(ta, te, 0x5150); qt[1] = __byte_perm(ta, te, 0x5251);
+                qt[2] = __byte_perm(ta, te, 0x5352); qt[3] = __byte_perm(ta, te, 0x5453);
+                qb[0] = __byte_perm(ba, be, 0x5150); qb[1] = __byte_perm(ba, be, 0x5251);
+                qb[2] = __byte_perm(ba, be, 0x5352); qb[3] = __byte_perm(ba, be, 0x5453);
+            } else {
+                const uint32_t t0 = __ldg(wt_), t1 = __ldg(wt_ + 1), t2 = __ldg(wt_ + 2);
+                const uint32_t b0 = __ldg(wb_), b1 = __ldg(wb_ + 1), b2 = __ldg(wb_ + 2);
+                qt[0] = __funnelshift_r(t0, t1, sh); qt[2] = __funnelshift_r(t1, t2, sh);
+                qb[0] = __funnelshift_r(b0, b1, sh); qb[2] = __funnelshift_r(b1, b2, sh);
+                const uint32_t te = t2 >> sh, be = b2 >> sh;
+                qt[1] = __byte_perm(qt[0], qt[2], 0x5432); qt[3] = __byte_perm(qt[2], te, 0x5432);
+                qb[1] = __byte_perm(qb[0], qb[2], 0x5432); qb[3] = __byte_perm(qb[2], be, 0x5432);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t fx = ((uint32_t)sfx[j] >> 5) & 31u, fy = ((uint32_t)sfy[j] >> 5) & 31u;
+                const uint32_t wx = fx * 255u + 32u;                     // (32 - fx) | fx << 8
+                // (sum w p + 16384) >> 15 with w = 32 wx wy  ==  ((32 - fx) v_j + fx v_j+1 + 512) >> 10, v = (32 - fy) top + fy bottom
+                if (CH == 1) {
+                    const uint32_t v = (32u - fy) * qt[j] + fy * qb[j];
+                    px[j][0] = __dp2a_lo(v, wx, 512u) >> 10;
+                } else {
+                    const uint32_t vu = (32u - fy) * (qt[j] & 0x00ff00ffu) + fy * (qb[j] & 0x00ff00ffu);
+                    const uint32_t vv = (32u - fy) * ((qt[j] >> 8) & 0x00ff00ffu) + fy * ((qb[j] >> 8) & 0x00ff00ffu);
+                    px[j][0] = __dp2a_lo(vu, wx, 512u) >> 10;
+                    px[j][CH - 1] = __dp2a_lo(vv, wx, 512u) >> 10;
+                }
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int sfx = xy0.x + ad[j], sfy = xy0.y + bd[j];
-            const int sx = sfx >> P, sy = sfy >> P;
-            const uint32_t fx = ((uint32_t)sfx >> 5) & 31u, fy = ((uint32_t)sfy >> 5) & 31u;
+            const int sx = sfx[j] >> P, sy = sfy[j] >> P;
+            const uint32_t fx = ((uint32_t)sfx[j] >> 5) & 31u, fy = ((uint32_t)sfy[j] >> 5) & 31u;
             const bool x0 = (unsigned)sx < (unsigned)w, x1 = (unsigned)(sx + 1) < (unsigned)w;
             const bool y0 = (unsigned)sy < (unsigned)h, y1 = (unsigned)(sy + 1) < (unsigned)h;
             const uint8_t* p = src + (ptrdiff_t)sy * src_stride + (ptrdiff_t)sx * CH;
@@ -1597,6 +1656,7 @@ k_plane_warp_cv(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_
                 px[j][c] = (v + 512u) >> 10;
             }
         }
+        }
         uint8_t* d = dst + (size_t)yo * dst_stride + (size_t)xo * CH;
         if (dst_al && npx == 4) {
             if (CH == 1) {
@@ -1624,16 +1684,17 @@ int vsk_plane_warp_slots(vs_ctx* ctx, const VsDevImg& src, int channels, const i
     if (dst.w <= 0 || dst.h <= 0 || dst.batch <= 0) return VS_OK;
     VS_REQUIRE(ctx, vs_cdiv(dst.h, PW_H) <= 65535 && dst.batch <= 65535, "plane_warp: grid too large");
     const int src_al = aligned_to(src.data, 2) && src.stride % 2 == 0 && src.batch_stride % 2 == 0;
+    const int src_al4 = aligned_to(src.data, 4) && src.stride % 4 == 0 && src.batch_stride % 4 == 0;
     const int va = 4 * channels;
     const int dst_al = aligned_to(dst.data, va) && dst.stride % va == 0 && dst.batch_stride % va == 0;
     dim3 grid(vs_cdiv(dst.w, PW_W), vs_cdiv(dst.h, PW_H), dst.batch);
     VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
     if (channels == 1)
         k_plane_warp_cv<1><<<grid, PW_THREADS, 0, ctx->stream>>>((const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
-            d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al, dst_al);
+            d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al, src_al4, dst_al);
     else
         k_plane_warp_cv<2><<<grid, PW_THREADS, 0, ctx->stream>>>((const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
-            d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al, dst_al);
+            d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al, src_al4, dst_al);
     VS_LAUNCH_CHECK(ctx);
     return VS_OK;
 }
