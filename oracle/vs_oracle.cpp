@@ -804,10 +804,14 @@ static size_t select_smallest(const uint16_t* abs_delta, int tw, int th, float f
 
 int vo_select_smallest(const uint16_t* abs_delta, int n, float fraction, uint32_t* order)
 {
-    // a single row of n tiles: tile_x is the linear index (n < 65536 for this entry point)
-    std::vector<DeltaPixel> dp;
-    size_t k = select_smallest(abs_delta, n, 1, fraction, dp);
-    for (size_t i = 0; i < k; i++) order[i] = dp[i].tile_x;
+    // n tiles in scan order; the linear index rides in (tile_y, tile_x) = (i >> 15, i & 32767), which std::nth_element
+    // only carries along (the comparator reads abs_delta)
+    std::vector<DeltaPixel> dp(n);
+    for (int i = 0; i < n; i++) { dp[i].abs_delta = abs_delta[i]; dp[i].tile_x = (uint16_t)(i & 32767); dp[i].tile_y = (uint16_t)(i >> 15); }
+    const size_t k = static_cast<size_t>(dp.size() * fraction);
+    std::nth_element(dp.begin(), dp.begin() + k, dp.end(),
+                     [](const DeltaPixel& l, const DeltaPixel& r) { return l.abs_delta < r.abs_delta; });
+    for (size_t i = 0; i < k; i++) order[i] = ((uint32_t)dp[i].tile_y << 15) | dp[i].tile_x;
     return (int)k;
 }
 

@@ -7,7 +7,8 @@
 
 extern "C" {
 
-// keys: (abs_delta << 16 | index); replays std::nth_element(keys, keys+nth, keys+n)
+// keys: (abs_delta << th_key_shift() | index); replays std::nth_element(keys, keys+nth, keys+n)
+int th_key_shift() { return vs_sel::KEY_SHIFT; }
 void th_nth_element(uint32_t* keys, int n, int nth) { vs_sel::nth_element_serial(keys, n, nth); }
 int th_selected_count(int n, float fraction) { return vs_sel::selected_count(n, fraction); }
 // forces the heap-select fallback from the first round (depth limit 0)

@@ -310,6 +310,16 @@ def test_clip_alignment_4k(gpu, ob):
     assert status.all() and worst < 1e-6
 
 
+def test_clip_alignment_8k(gpu, ob):
+    """7680x4320: 82 944 tiles at L0, more than a 16-bit tile index and more keys than shared memory holds: the selection
+    keys of a pair live in global memory (17-bit tile index) and only its chunk masks on chip.  Pyramids, warp-diffs,
+    selections, iteration counts, status and transforms of two pairs against the oracle."""
+    from video_stabilizer_b200 import synth
+    frames, poses = synth.make_clip_gpu(gpu, 7680, 4320, 3, 23, chunk=4)
+    worst, T, status, ref = check_clip_against_oracle(gpu, ob, frames, deep=False)
+    assert status.all() and worst < 1e-6
+
+
 def test_clips_in_shared_launches_equal_each_clip_alone(gpu):
     """BASELINE.json configs[3] (many independent 720p clips aligned and warped concurrently): the pyramids, keyframe
     features, ONE solver launch and ONE warp launch over all clips give each clip exactly what it gets alone."""

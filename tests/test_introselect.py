@@ -7,14 +7,20 @@ import numpy as np
 import pytest
 
 
+def pack(hooks, v):
+    """keys = abs_delta << KEY_SHIFT | index (KEY_SHIFT = 17: abs_delta below 32768, up to 131071 tiles)"""
+    shift = hooks.th_key_shift()
+    assert int(v.max(initial=0)) < (1 << (32 - shift))
+    return ((v.astype(np.uint32) << shift) | np.arange(len(v), dtype=np.uint32)).astype(np.uint32), (1 << shift) - 1
+
+
 def replay(hooks, v, k):
-    n = len(v)
-    keys = ((v.astype(np.uint32) << 16) | np.arange(n, dtype=np.uint32)).astype(np.uint32)
-    hooks.th_nth_element(keys.ctypes.data_as(C.c_void_p), n, k)
-    return keys & 0xFFFF
+    keys, mask = pack(hooks, v)
+    hooks.th_nth_element(keys.ctypes.data_as(C.c_void_p), len(v), k)
+    return keys & mask
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 16, 176, 220, 480, 1296, 2304, 5184, 20736])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 16, 176, 220, 480, 1296, 2304, 5184, 20736, 82944])
 def test_matches_std_nth_element(ob, hooks, n):
     rng = np.random.default_rng(n)
     for trial in range(12):
@@ -22,7 +28,7 @@ def test_matches_std_nth_element(ob, hooks, n):
         if kind == 0:
             v = rng.integers(0, 256, n)
         elif kind == 1:   # residual-like: geometric, heavy ties at small values
-            v = np.minimum(rng.exponential(6, n).astype(np.int64), 65535)
+            v = np.minimum(rng.exponential(6, n).astype(np.int64), 32767)
         elif kind == 2:
             v = rng.integers(0, 3, n)
         elif kind == 3:
@@ -30,7 +36,7 @@ def test_matches_std_nth_element(ob, hooks, n):
         elif kind == 4:
             v = np.zeros(n, np.int64)
         else:
-            v = rng.integers(0, 65536, n)
+            v = rng.integers(0, 32768, n)
         v = v.astype(np.uint16)
         k = hooks.th_selected_count(n, C.c_float(0.8))
         ref = ob.select_smallest(v, 0.8)
@@ -45,12 +51,12 @@ def test_heap_select_fallback_matches_libstdcxx(ob, hooks):
     for trial in range(400):
         n = int(rng.integers(5, 3000))
         depth = int(rng.integers(0, 4))
-        v = rng.integers(0, [4, 256, 65536][trial % 3], n).astype(np.uint16)
+        v = rng.integers(0, [4, 256, 32768][trial % 3], n).astype(np.uint16)
         nth = int(rng.integers(0, n))
         ref = ob.introselect_depth(v, nth, depth)
-        keys = ((v.astype(np.uint32) << 16) | np.arange(n, dtype=np.uint32)).astype(np.uint32)
+        keys, mask = pack(hooks, v)
         hooks.th_introselect_depth(keys.ctypes.data_as(C.c_void_p), n, nth, depth)
-        assert np.array_equal(keys & 0xFFFF, ref)
+        assert np.array_equal(keys & mask, ref)
 
 
 def test_selected_count_is_float_product(hooks):

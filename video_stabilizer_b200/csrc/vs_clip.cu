@@ -45,12 +45,13 @@ struct vs_clip {
     int32_t* d_slots = nullptr;       // max(capacity, max_pairs) ints
     VsWarpCoef* d_coef = nullptr;     // capacity entries
     uint16_t* d_dbg_wd = nullptr;
-    uint16_t* d_dbg_order = nullptr;
+    uint32_t* d_dbg_order = nullptr;
     int32_t* d_dbg_count = nullptr;
     long long* d_dbg_clock = nullptr;   // [max_pairs][VS_CLK_STRIDE]
     uint16_t* d_pos_scratch = nullptr; // [max_pairs][4][max_tiles] candidate lists of the parallel selection
     uint4* d_patch_scratch = nullptr;  // [max_pairs][2][max_tiles] 4x4 keyframe windows of the warp-diff pass (patch cache of the solver)
     uint8_t* d_tb_scratch = nullptr;   // [max_pairs][2][max_tiles] template bytes of the warp-diff pass
+    uint32_t* d_key_scratch = nullptr; // [max_pairs][2][max_tiles] selection keys of clips whose largest level does not fit shared memory (8K)
     float* d_res_scratch = nullptr;    // [max_pairs][2][max_tiles] warp-diff residuals reused by the first Gauss-Newton iteration
     uint8_t* d_warp_out = nullptr;    // staging for VS_MEM_HOST warps, grown on demand
     size_t warp_out_bytes = 0;
@@ -117,7 +118,7 @@ void free_all(vs_clip* c)
     if (c->ev_bgr_read) cudaEventDestroy(c->ev_bgr_read);
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
-    cudaFree(c->d_pos_scratch); cudaFree(c->d_res_scratch); cudaFree(c->d_patch_scratch); cudaFree(c->d_tb_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
+    cudaFree(c->d_pos_scratch); cudaFree(c->d_res_scratch); cudaFree(c->d_patch_scratch); cudaFree(c->d_tb_scratch); cudaFree(c->d_key_scratch); cudaFree(c->d_dbg_wd); cudaFree(c->d_dbg_order); cudaFree(c->d_dbg_count); cudaFree(c->d_dbg_clock); cudaFree(c->d_warp_out);
     cudaFree(c->d_warp_tab);
     cudaFree(c->d_sweep);
     cudaFree(c->pc.d_tw); cudaFree(c->pc.d_rows); cudaFree(c->pc.d_spec); cudaFree(c->pc.d_cross); cudaFree(c->pc.d_inv);
@@ -394,10 +395,13 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
         // NV12 clips upload the Y planes of a run of slots as the slices of one 3-D copy: whole level-0 rows per slot
         if (flags & VS_CLIP_NV12) g.pyr_slot_bytes = vs_align_up(off, (size_t)2 * g.lv[0].pitch);
     }
-    if (g.max_tiles > 65535 || (size_t)2 * g.max_tiles * 4 + (size_t)g.max_tiles + 64 > 216 * 1024) {   // keys + chunk words of the selection
+    // the solver keeps a level's selection keys (8 B per tile) in shared memory when they fit (up to ~24 k tiles: 4K has
+    // 20 736) and in a global scratch slice per pair otherwise (8K: 82 944); a key holds the tile index in 17 bits
+    const bool keys_global = (size_t)2 * g.max_tiles * 4 + (size_t)g.max_tiles + 64 > 216 * 1024;
+    if (g.max_tiles > 131071 || (size_t)g.max_tiles + 64 > 200 * 1024) {
         const int mt = g.max_tiles;
         delete c;
-        return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "%d tiles on a level exceeds the on-chip selection capacity", mt);
+        return vs_set_error(ctx, VS_ERR_UNSUPPORTED, "%d tiles on a level exceeds the selection's capacity", mt);
     }
     c->nv12 = (flags & VS_CLIP_NV12) != 0;
     if (c->nv12 && ((width | height) & 1)) {
@@ -427,6 +431,7 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_res_scratch, (size_t)max_pairs * 2 * g.max_tiles);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_patch_scratch, (size_t)max_pairs * 2 * g.max_tiles);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_tb_scratch, (size_t)max_pairs * 2 * g.max_tiles);
+    if (r == VS_OK && keys_global) r = dev_alloc(ctx, &c->d_key_scratch, (size_t)max_pairs * 2 * g.max_tiles);
     if (r == VS_OK && (flags & VS_CLIP_DEBUG_TAPS)) {
         r = dev_alloc(ctx, &c->d_dbg_wd, (size_t)max_pairs * 2 * g.total_tiles);
         if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_order, (size_t)max_pairs * 2 * g.total_tiles);
@@ -568,7 +573,7 @@ int vs_clip_align(vs_clip* c, const vs_pair* pairs, int n, double* out_T, int32_
     a.dbg_warpdiff = c->d_dbg_wd; a.dbg_order = c->d_dbg_order; a.dbg_count = c->d_dbg_count;
     a.pos_scratch = c->d_pos_scratch;
     a.res_scratch = c->d_res_scratch;
-    a.patch_scratch = c->d_patch_scratch; a.tb_scratch = c->d_tb_scratch;
+    a.patch_scratch = c->d_patch_scratch; a.tb_scratch = c->d_tb_scratch; a.key_scratch = c->d_key_scratch;
     a.force_threads = 0;
     a.dbg_clock = c->d_dbg_clock;
     if (c->params.phase_correlate) VS_TRY(phase_seed(c, pairs, c->d_pairs, n, 0, &a.init_T));
@@ -647,7 +652,7 @@ int vs_clip_align_sweep(vs_clip* c, const vs_pair* pairs, int n_pairs, const vs_
     a.dbg_warpdiff = nullptr; a.dbg_order = nullptr; a.dbg_count = nullptr; a.dbg_clock = nullptr;
     a.pos_scratch = c->d_pos_scratch;
     a.res_scratch = c->d_res_scratch;
-    a.patch_scratch = c->d_patch_scratch; a.tb_scratch = c->d_tb_scratch;
+    a.patch_scratch = c->d_patch_scratch; a.tb_scratch = c->d_tb_scratch; a.key_scratch = c->d_key_scratch;
     a.force_threads = 0;
     a.sweep = c->d_sweep;
     a.sweep_pairs = n_pairs;
@@ -709,6 +714,7 @@ int vs_clip_align_async(vs_clip* c, const vs_pair* pairs, int n, int base, int l
     a.res_scratch = c->d_res_scratch ? c->d_res_scratch + (size_t)base * 2 * c->g.max_tiles : nullptr;
     a.patch_scratch = c->d_patch_scratch ? c->d_patch_scratch + (size_t)base * 2 * c->g.max_tiles : nullptr;
     a.tb_scratch = c->d_tb_scratch ? c->d_tb_scratch + (size_t)base * 2 * c->g.max_tiles : nullptr;
+    a.key_scratch = c->d_key_scratch ? c->d_key_scratch + (size_t)base * 2 * c->g.max_tiles : nullptr;
     // all lanes must be resident on the GPU together: an SM per pair (512 threads, registers uncapped: the shortest
     // latency per pair) when every pair of every lane gets one, else three 256-thread CTAs per SM
     a.force_threads = c->max_pairs <= ctx->sm_count ? 512 : 256;
@@ -1037,13 +1043,11 @@ int vs_clip_get_selected(vs_clip* c, int pair, int level, int axis, uint32_t* ou
                                  cudaMemcpyDeviceToHost, ctx->stream));
     VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (k < 0 || k > L.ntiles) return vs_set_error(ctx, VS_ERR_INVALID, "clip_get_selected: level %d was not reached by this pair", level);
-    std::vector<uint16_t> tmp(k);
     if (k) {
-        VS_CUDA(ctx, cudaMemcpyAsync(tmp.data(), c->d_dbg_order + ((size_t)pair * 2 + axis) * c->g.total_tiles + L.tile_off,
-                                     (size_t)k * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        VS_CUDA(ctx, cudaMemcpyAsync(out_order, c->d_dbg_order + ((size_t)pair * 2 + axis) * c->g.total_tiles + L.tile_off,
+                                     (size_t)k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    for (int i = 0; i < k; i++) out_order[i] = tmp[i];
     *out_k = k;
     return VS_OK;
 }

@@ -123,13 +123,14 @@ struct VsSolveArgs {
     int32_t* out_status;      // 1 per pair
     int32_t* out_iters;       // levels per pair
     uint16_t* dbg_warpdiff;   // [pair][axis][total_tiles] or null
-    uint16_t* dbg_order;      // [pair][axis][total_tiles] or null
+    uint32_t* dbg_order;      // [pair][axis][total_tiles] or null
     int32_t* dbg_count;       // [pair][axis][levels] or null
     long long* dbg_clock;     // [pair][VS_CLK_STRIDE] cycles per phase, totals then per level (debug taps only; zeroed by the caller), or null
     uint16_t* pos_scratch;    // [pair][4][max_tiles] selection scratch in global memory, or null (shared memory)
     float* res_scratch;       // [pair][2][max_tiles] signed residual of every tile from the warp-diff pass, or null
     uint4* patch_scratch = nullptr;   // [pair][2][max_tiles] the 4x4 keyframe window of every tile as gathered by the warp-diff pass, or null
     uint8_t* tb_scratch = nullptr;    // [pair][2][max_tiles] the template byte of every tile (with patch_scratch)
+    uint32_t* key_scratch = nullptr;  // [pair][2][max_tiles] the selection keys when a level does not fit shared memory, or null
     int force_threads;        // 0 = CTA size by pair count; 256 when several launches must be resident together
     const double* init_T = nullptr;   // [pair][2] initial (TX, TY) at the coarsest level (phase-correlation seed), or null
     const VsSweepSet* sweep = nullptr;   // device array of parameter sets, or null: n_pairs = sets * sweep_pairs jobs

@@ -7,8 +7,11 @@
 // __heap_select / __insertion_sort, bits/stl_heap.h: __make_heap / __pop_heap /
 // __adjust_heap / __push_heap) and it changes the recovered transform by more than the
 // 0.01 px parity budget (SURVEY.md finding 3).  The functions here replay that algorithm
-// move for move on keys = (abs_delta << 16 | tile_index); only the high 16 bits take part
-// in comparisons, exactly like the reference's comparator.
+// move for move on keys = (abs_delta << KEY_SHIFT | tile_index); only the abs_delta bits take
+// part in comparisons, exactly like the reference's comparator.  KEY_SHIFT = 17 leaves 17 bits
+// for the tile (131 071 tiles per level: 8K has 82 944) and 15 for abs_delta: |template - sample|
+// of u8 images stays below 1024 (the normalised Lanczos-2 weights sum to at most 1.4 in absolute
+// value per axis), so the clamp at 32 767 never acts.
 //
 // Host+device so the emulation is checked against the real std::nth_element on the CPU
 // (tests/test_introselect.py) before it ever runs on a GPU.
@@ -24,7 +27,16 @@
 
 namespace vs_sel {
 
-VS_SEL_HD bool less(uint32_t a, uint32_t b) { return (a >> 16) < (b >> 16); }
+constexpr int KEY_SHIFT = 17;
+constexpr uint32_t KEY_TILE_MASK = (1u << KEY_SHIFT) - 1u;
+constexpr uint32_t KEY_VALUE_MAX = (1u << (32 - KEY_SHIFT)) - 1u;
+VS_SEL_HD uint32_t make_key(uint32_t abs_delta, uint32_t tile)
+{
+    return ((abs_delta < KEY_VALUE_MAX ? abs_delta : KEY_VALUE_MAX) << KEY_SHIFT) | tile;
+}
+VS_SEL_HD uint32_t key_value(uint32_t k) { return k >> KEY_SHIFT; }
+VS_SEL_HD uint32_t key_tile(uint32_t k) { return k & KEY_TILE_MASK; }
+VS_SEL_HD bool less(uint32_t a, uint32_t b) { return (a >> KEY_SHIFT) < (b >> KEY_SHIFT); }
 VS_SEL_HD void swp(uint32_t* a, int i, int j) { uint32_t t = a[i]; a[i] = a[j]; a[j] = t; }
 
 // std::__lg

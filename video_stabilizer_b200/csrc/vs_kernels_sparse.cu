@@ -621,14 +621,14 @@ __device__ void block_nth_element2_masks(uint32_t* const keys0, uint32_t* const 
         if (st.done) break;
         if (rounds && axis == 0) ++*rounds;
         const int f0 = st.first + 1, last = st.last;
-        const uint32_t pv = st.pivot >> 16;
+        const uint32_t pv = vs_sel::key_value(st.pivot);
         const int nch = (last - f0 + 31) >> 5;
 
         // ---- masks of the chunks
         for (int c = gw; c < nch; c += G) {
             const int i = f0 + 32 * c + lane;
             const bool valid = i < last;
-            const uint32_t e = valid ? v[i] >> 16 : 0u;
+            const uint32_t e = valid ? vs_sel::key_value(v[i]) : 0u;
             const uint32_t mL = __ballot_sync(0xffffffffu, valid && e >= pv);
             const uint32_t mR = __ballot_sync(0xffffffffu, valid && e <= pv);
             if (lane == 0) { maskL[c] = mL; maskR[c] = mR; }
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, MIN_CTAS)
 k_solve_pairs(VsClipGeom g, VsSolveArgs a)
 {
     constexpr int NWARPS = SOLVE_THREADS / 32;
-    extern __shared__ uint32_t dyn_keys[];   // keys[2][max_tiles]: abs_delta << 16 | tile, then (optionally) pos[2][2*max_tiles] u16
+    extern __shared__ uint32_t dyn_keys[];   // keys[2][max_tiles]: abs_delta << KEY_SHIFT | tile, then (optionally) pos[2][2*max_tiles] u16
     __shared__ SolveShared<SOLVE_THREADS / 32> sh;
     __shared__ SelShared<SOLVE_THREADS / 32> sel;
     const int tid = threadIdx.x;
@@ -754,13 +754,15 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
     const uint8_t* tpyr = a.pyr + (size_t)pr.template_slot * g.pyr_slot_bytes;
     const uint8_t* kpyr = a.pyr + (size_t)pr.keyframe_slot * g.pyr_slot_bytes;
     const size_t feat = (size_t)pr.keyframe_slot * 2 * g.total_tiles;
-    uint32_t* const keys0 = dyn_keys;
-    uint32_t* const keys1 = dyn_keys + g.max_tiles;
+    // levels too large for shared memory (8K: 82 944 tiles, 663 KB of keys) keep the keys of the pair in global memory
+    // (L2-resident); only the chunk masks of the selection stay on chip
+    uint32_t* const keys0 = a.key_scratch ? a.key_scratch + (size_t)pair * 2 * g.max_tiles : dyn_keys;
+    uint32_t* const keys1 = keys0 + g.max_tiles;
     // the parallel selection's state: chunk masks and ranks in shared memory when the CTA has its SM to itself, else
     // candidate position lists in shared memory when they fit, else in a global scratch slice
     constexpr bool SEL_MASKS = MIN_CTAS == 1;
     const int sel_nc = sel_chunks(g.max_tiles);
-    uint32_t* const selbuf = dyn_keys + 2 * g.max_tiles;
+    uint32_t* const selbuf = a.key_scratch ? dyn_keys : dyn_keys + 2 * g.max_tiles;
     uint16_t* const pos0 = a.pos_scratch ? a.pos_scratch + (size_t)pair * 4 * g.max_tiles
                                          : reinterpret_cast<uint16_t*>(dyn_keys + 2 * g.max_tiles);
     uint16_t* const pos1 = pos0 + 2 * g.max_tiles;
@@ -827,7 +829,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
             float d = fabsf(__fsub_rn(s, (float)tb));
             d = fmaxf(fminf(d, 65535.0f), 0.0f);
             const uint32_t u = (uint32_t)d;
-            (axis ? keys1 : keys0)[t] = (u << 16) | (uint32_t)t;
+            (axis ? keys1 : keys0)[t] = vs_sel::make_key(u, (uint32_t)t);
             if (a.dbg_warpdiff)
                 a.dbg_warpdiff[((size_t)pair * 2 + axis) * g.total_tiles + L.tile_off + t] = (uint16_t)u;
         }
@@ -857,7 +859,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
         if (a.dbg_order) {
             for (int i = tid; i < 2 * k; i += SOLVE_THREADS) {
                 const int axis = i >= k, j = i - axis * k;
-                a.dbg_order[((size_t)pair * 2 + axis) * g.total_tiles + L.tile_off + j] = (uint16_t)((axis ? keys1 : keys0)[j] & 0xffffu);
+                a.dbg_order[((size_t)pair * 2 + axis) * g.total_tiles + L.tile_off + j] = vs_sel::key_tile((axis ? keys1 : keys0)[j]);
             }
             if (tid < 2) a.dbg_count[((size_t)pair * 2 + tid) * g.levels + lvl] = k;
         }
@@ -871,7 +873,7 @@ k_solve_pairs(VsClipGeom g, VsSolveArgs a)
             for (int i = tid; i < 2 * k; i += SOLVE_THREADS) {
                 const int axis = i >= k, j = i - axis * k;
                 uint32_t* const kj = (axis ? keys1 : keys0) + j;
-                const int t = (int)(*kj & 0xffffu);
+                const int t = (int)vs_sel::key_tile(*kj);
                 const uint32_t kv = __ldg((axis ? kpl1 : kpl0) + t);
                 float4 J = __ldg((axis ? jcl1 : jcl0) + t);
                 const int ty = t / L.tw, tx = t - ty * L.tw;
@@ -1169,10 +1171,16 @@ int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
     const size_t key_bytes = (size_t)2 * g.max_tiles * sizeof(uint32_t);
     const size_t pos_bytes = (size_t)4 * g.max_tiles * sizeof(uint16_t);
     const size_t sel_bytes = (size_t)2 * 4 * sel_chunks(g.max_tiles) * sizeof(uint32_t);
-    VS_REQUIRE(ctx, g.max_tiles <= 65535, "solve: more than 65535 tiles per level");
-    VS_REQUIRE(ctx, key_bytes + sel_bytes <= 220 * 1024, "solve: level too large for the shared-memory selection");
-    size_t smem = key_bytes;
+    VS_REQUIRE(ctx, (uint32_t)g.max_tiles <= vs_sel::KEY_TILE_MASK, "solve: more tiles per level than a key's tile index holds");
+    // a level whose keys do not fit shared memory (8K) keeps them in the caller's global scratch; the masks of the
+    // list-free selection stay on chip
+    const bool keys_global = key_bytes + sel_bytes > 220 * 1024;
+    VS_REQUIRE(ctx, !keys_global || a.key_scratch, "solve: level too large for the shared-memory selection and no key scratch given");
+    VS_REQUIRE(ctx, sel_bytes <= 200 * 1024, "solve: level too large for the on-chip selection masks");
+    if (keys_global) threads = 1024;
+    size_t smem = keys_global ? 0 : key_bytes;
     VsSolveArgs args = a;
+    if (!keys_global) args.key_scratch = nullptr;
     // (Measured: keeping the lists of the shorter rounds in a shared-memory part next to the keys makes a round cheaper,
     // 9.5k -> 8.3k cycles, but every KB of shared memory is a KB of L1 taken from the gathers, which lose more: mean
     // 0.67 -> 0.97 ms per pair at 68 KB per CTA.  The keys stay alone in shared memory unless everything fits.)
