@@ -492,6 +492,7 @@ int vs_clip_upload(vs_clip* c, int slot0, int n, const uint8_t* bgr, int64_t row
     VS_REQUIRE(ctx, slot0 >= 0 && n >= 0 && slot0 + n <= c->capacity, "clip_upload: slot range out of bounds");
     VS_REQUIRE(ctx, n == 0 || bgr, "clip_upload: source is NULL");
     VS_REQUIRE(ctx, row_stride >= (int64_t)c->w * (c->nv12 ? 1 : 3), "clip_upload: row_stride smaller than a row");
+    VS_REQUIRE(ctx, !c->nv12 || n <= 1 || frame_stride >= row_stride * (c->h + c->h / 2), "clip_upload: frame_stride smaller than an NV12 frame");
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaMemcpyKind kind = mem == VS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     return clip_enqueue_upload(c, slot0, n, bgr, row_stride, frame_stride, kind, ctx->stream);
@@ -822,6 +823,7 @@ int vs_clip_upload_async(vs_clip* c, int slot0, int n, const uint8_t* bgr, int64
     VS_REQUIRE(ctx, slot0 >= 0 && n >= 0 && slot0 + n <= c->capacity, "clip_upload_async: slot range out of bounds");
     VS_REQUIRE(ctx, n == 0 || bgr, "clip_upload_async: source is NULL");
     VS_REQUIRE(ctx, row_stride >= (int64_t)c->w * (c->nv12 ? 1 : 3), "clip_upload_async: row_stride smaller than a row");
+    VS_REQUIRE(ctx, !c->nv12 || n <= 1 || frame_stride >= row_stride * (c->h + c->h / 2), "clip_upload_async: frame_stride smaller than an NV12 frame");
     VS_CUDA(ctx, cudaSetDevice(ctx->device));
     VS_TRY(ensure_async(c));
     if (n == 0) return VS_OK;
