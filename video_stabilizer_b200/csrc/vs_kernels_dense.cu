@@ -1676,6 +1676,138 @@ k_plane_warp_cv(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_
     }
 }
 
+// One pixel of a one-channel plane from its four byte taps (zero outside the image): the general path.
+__device__ __forceinline__ uint32_t plane_pixel_taps(const uint8_t* __restrict__ src, int64_t src_stride, int w, int h, int sfx, int sfy)
+{
+    const int sx = sfx >> 10, sy = sfy >> 10;
+    const uint32_t fx = ((uint32_t)sfx >> 5) & 31u, fy = ((uint32_t)sfy >> 5) & 31u;
+    const bool x0 = (unsigned)sx < (unsigned)w, x1 = (unsigned)(sx + 1) < (unsigned)w;
+    const bool y0 = (unsigned)sy < (unsigned)h, y1 = (unsigned)(sy + 1) < (unsigned)h;
+    const uint8_t* p = src + (ptrdiff_t)sy * src_stride + sx;
+    uint32_t t00 = 0u, t10 = 0u, t01 = 0u, t11 = 0u;
+    if (x0 && y0) t00 = __ldg(p);
+    if (x1 && y0) t10 = __ldg(p + 1);
+    if (x0 && y1) t01 = __ldg(p + src_stride);
+    if (x1 && y1) t11 = __ldg(p + src_stride + 1);
+    const uint32_t v = (32u - fx) * (32u - fy) * t00 + fx * (32u - fy) * t10 + (32u - fx) * fy * t01 + fx * fy * t11;
+    return (v + 512u) >> 10;
+}
+
+// The Y plane, eight pixels per lane (one 8-byte store).  A warp covers 32 pixels x 8 rows per step (compact footprint, as
+// above), a CTA the same 128 x 32 tile.  The column terms of a lane are kept relative to its first pixel: with
+// r = (X0 + adelta[0]) & 1023 the pixel j of a regular group (source column sx0 + j) has r + off_j in [0, 1024), where
+// off_j = adelta[j] - adelta[0] - 1024 j is a lane constant of a few units; the eight values travel as four packed pairs of
+// 16-bit halves biased by 1024 (one add per pair, one LOP3 per pair for the test, the horizontal fractions by one shift
+// and mask per pair, the IDP.2A weight bytes of two pixels by one multiply-add).  The row terms stay per pixel (their
+// column part is monotone, so the eight rows coincide when the first and the last do).  A regular group reads three
+// aligned words per source row; pixel j blends its column pair [p_j, p_j+1] vertically as one packed multiply-add
+// (32 top + fy (bottom - top) on the packed word: the halves cannot interfere because the true result has none) and
+// horizontally by IDP.2A.  Anything else (borders, a skipped source column or row, tile tails) goes pixel by pixel.
+template <int DUMMY>
+__global__ void __launch_bounds__(PW_THREADS)
+k_plane_warp_y8(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
+                const int32_t* __restrict__ slots, const VsWarpCoef* __restrict__ coefs,
+                uint8_t* __restrict__ dst_base, int64_t dst_stride, int64_t dst_bs, int dw, int dh,
+                int dst_x0, int dst_y0)
+{
+    constexpr double SCALE = 1024.0;
+    constexpr int ROUND = 16;
+    __shared__ int2 sXY0[PW_H];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int ox0 = blockIdx.x * PW_W, oy0 = blockIdx.y * PW_H;
+    const int slot = slots ? slots[b] : b;
+    const uint8_t* src = src_base + (size_t)slot * src_bs;
+    uint8_t* dst = dst_base + (size_t)b * dst_bs;
+    const VsWarpCoef cf = coefs[b];
+    if (tid < PW_H) {
+        const double y = (double)(oy0 + tid + dst_y0);
+        sXY0[tid] = make_int2(__double2int_rn((cf.i01 * y + cf.i02) * SCALE) + ROUND,
+                              __double2int_rn((cf.i11 * y + cf.i12) * SCALE) + ROUND);
+    }
+    const int xo = ox0 + 32 * (warp & 3) + 8 * (lane & 3);
+    int ad0, bd[8];
+    uint32_t cax[4];            // (off_2k + 1024) | (off_2k+1 + 1024) << 16
+    bool lane_ok = true;        // offsets small enough for the packed form
+    {
+        int ad[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double x = (double)(xo + j + dst_x0);
+            ad[j] = __double2int_rn(cf.i00 * x * SCALE);
+            bd[j] = __double2int_rn(cf.i10 * x * SCALE);
+        }
+        ad0 = ad[0];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int o0 = ad[2 * k] - ad0 - 1024 * (2 * k), o1 = ad[2 * k + 1] - ad0 - 1024 * (2 * k + 1);
+            lane_ok = lane_ok && o0 >= -1024 && o0 <= 1024 && o1 >= -1024 && o1 <= 1024;
+            cax[k] = (uint32_t)(o0 + 1024) | ((uint32_t)(o1 + 1024) << 16);
+        }
+    }
+    __syncthreads();
+    if (xo >= dw) return;
+    const bool full = xo + 8 <= dw;
+    uint8_t* const dcol = dst + xo;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int r = 16 * (warp >> 2) + 8 * k + (lane >> 2);
+        const int yo = oy0 + r;
+        if (yo >= dh) continue;
+        const int2 xy0 = sXY0[r];
+        uint8_t* const d = dcol + (size_t)yo * dst_stride;
+        const int s0x = xy0.x + ad0, sx0 = s0x >> 10;
+        const int sfy0 = xy0.y + bd[0], sfy7 = xy0.y + bd[7], sy0 = sfy0 >> 10;
+        const uint32_t rx2 = (uint32_t)(s0x & 1023) * 0x10001u;
+        uint32_t rel[4];
+        uint32_t bad = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            rel[q] = rx2 + cax[q];
+            bad |= rel[q] ^ 0x04000400u;
+        }
+        // the three aligned words that hold source columns sx0 .. sx0 + 8 must end inside the row
+        const bool regular = full && lane_ok && (bad & 0xfc00fc00u) == 0u && (sfy7 >> 10) == sy0 && sx0 >= 0 && sy0 >= 0 &&
+                             sy0 + 1 < h && ((sx0 >> 2) + 3) * 4 <= w;
+        if (regular) {
+            const uint32_t* wt_ = reinterpret_cast<const uint32_t*>(src + (size_t)sy0 * src_stride) + (sx0 >> 2);
+            const uint32_t* wb_ = reinterpret_cast<const uint32_t*>(src + (size_t)(sy0 + 1) * src_stride) + (sx0 >> 2);
+            const uint32_t t0 = __ldg(wt_), t1 = __ldg(wt_ + 1), t2 = __ldg(wt_ + 2);
+            const uint32_t b0 = __ldg(wb_), b1 = __ldg(wb_ + 1), b2 = __ldg(wb_ + 2);
+            const uint32_t sh = 8u * (uint32_t)(sx0 & 3);
+            const uint32_t ta = __funnelshift_r(t0, t1, sh), tb = __funnelshift_r(t1, t2, sh), tc = (t2 >> sh) & 0xffu;
+            const uint32_t ba = __funnelshift_r(b0, b1, sh), bb = __funnelshift_r(b1, b2, sh), bc = (b2 >> sh) & 0xffu;
+            uint32_t out[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                // [p_j, 0, p_j+1, 0] of both rows (the second operand supplies the zero bytes, and p_8)
+                uint32_t top, bot;
+                if (j < 3)       { top = __byte_perm(ta, 0u, 0x4140 + 0x0101 * j); bot = __byte_perm(ba, 0u, 0x4140 + 0x0101 * j); }
+                else if (j == 3) { top = __byte_perm(ta, tb & 0xffu, 0x5453); bot = __byte_perm(ba, bb & 0xffu, 0x5453); }
+                else if (j < 7)  { top = __byte_perm(tb, 0u, 0x4140 + 0x0101 * (j - 4)); bot = __byte_perm(bb, 0u, 0x4140 + 0x0101 * (j - 4)); }
+                else             { top = __byte_perm(tb, tc, 0x5453); bot = __byte_perm(bb, bc, 0x5453); }
+                const uint32_t fy = ((uint32_t)(xy0.y + bd[j]) >> 5) & 31u;
+                const uint32_t v = (top << 5) + fy * (bot - top);                  // halves: 32 top + fy (bottom - top) <= 8160
+                const uint32_t fxp = (rel[j >> 1] >> 5) & 0x001f001fu;             // fx of pixels j & ~1 and j | 1
+                const uint32_t wxp = fxp * 255u + 0x00200020u;                     // (32 - fx) | fx << 8 in each half
+                // (sum w p + 16384) >> 15 with w = 32 wx wy  ==  ((32 - fx) v_j + fx v_j+1 + 512) >> 10
+                out[j] = ((j & 1) ? __dp2a_hi(v, wxp, 512u) : __dp2a_lo(v, wxp, 512u)) >> 10;
+            }
+            *reinterpret_cast<uint2*>(d) = make_uint2(out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24),
+                                                      out[4] | (out[5] << 8) | (out[6] << 16) | (out[7] << 24));
+        } else {
+            const int npx = min(8, dw - xo);
+#pragma unroll 1
+            for (int j = 0; j < npx; j++) {
+                // the column terms again (a dynamic index into the register arrays would spill them; this path is rare)
+                const double x = (double)(xo + j + dst_x0);
+                const int a = __double2int_rn(cf.i00 * x * SCALE), bq = __double2int_rn(cf.i10 * x * SCALE);
+                d[j] = (uint8_t)plane_pixel_taps(src, src_stride, w, h, xy0.x + a, xy0.y + bq);
+            }
+        }
+    }
+}
+
 int vsk_plane_warp_slots(vs_ctx* ctx, const VsDevImg& src, int channels, const int32_t* d_slots, const VsWarpCoef* d_coef,
                          const VsDevImg& dst, int dst_x0, int dst_y0)
 {
@@ -1689,7 +1821,11 @@ int vsk_plane_warp_slots(vs_ctx* ctx, const VsDevImg& src, int channels, const i
     const int dst_al = aligned_to(dst.data, va) && dst.stride % va == 0 && dst.batch_stride % va == 0;
     dim3 grid(vs_cdiv(dst.w, PW_W), vs_cdiv(dst.h, PW_H), dst.batch);
     VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
-    if (channels == 1)
+    const bool y8 = channels == 1 && src_al4 && aligned_to(dst.data, 8) && dst.stride % 8 == 0 && dst.batch_stride % 8 == 0;
+    if (y8)
+        k_plane_warp_y8<0><<<grid, PW_THREADS, 0, ctx->stream>>>((const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
+            d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0);
+    else if (channels == 1)
         k_plane_warp_cv<1><<<grid, PW_THREADS, 0, ctx->stream>>>((const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
             d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0, src_al, src_al4, dst_al);
     else
