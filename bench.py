@@ -552,6 +552,9 @@ def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_
     # ---- end to end: host frames in, host frames out, copies inside the timed region; sub-chunks interleaved over the ranks
     if e2e_steps > 0:
         pes = []
+        # end to end a third video in flight fills more of the pipeline's fill and drain (0.86 -> 0.89 of the copy ceiling on
+        # one GPU); with many ranks the host memory system is the limit and more instances only add contention
+        inflight = max(1, args.e2e_inflight) if getattr(args, "e2e_inflight", 0) > 0 else (max(inflight, 3) if R.world <= 2 else inflight)
         for i in range(inflight):
             pes.append(PartitionedVideo(R, args, W, H, F, e2e_sub, 1, False, tag + "s%d" % i, seed, share=pes[0] if i else None, nv12=nv12))
         pe = pes[0]
@@ -742,6 +745,7 @@ def main():
     ap.add_argument("--passes", type=int, default=15, help="videos per step (device-resident number)")
     ap.add_argument("--inflight", type=int, default=2, help="videos in flight at a time (independent stabilizer instances)")
     ap.add_argument("--e2e-sub", type=int, default=16, help="sub-chunk (frames) of the host-streamed partition")
+    ap.add_argument("--e2e-inflight", type=int, default=0, help="videos in flight in the end-to-end region (0 = 3 on up to two GPUs, else --inflight)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="CPU worker threads (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the 4K / configs[3] / warp-sweep records")

@@ -25,7 +25,7 @@ def main():
     ceil_sum = ceiling["h2d_duplex_gbs"] + ceiling["d2h_duplex_gbs"]
     for infl in [int(x) for x in a.inflight.split(",")]:
         for sub in [int(x) for x in a.subs.split(",")]:
-            args = types.SimpleNamespace(crop=0, inflight=infl, width=a.width, height=a.height, frames=a.frames)
+            args = types.SimpleNamespace(crop=0, inflight=infl, e2e_inflight=infl, width=a.width, height=a.height, frames=a.frames)
             r = bench.measure_partitioned(R, args, a.width, a.height, a.frames, 2, 1, 4, 4, sub, False, "t%d_%d" % (infl, sub),
                                           nv12=not a.bgr)
             e = r["e2e"]
