@@ -465,7 +465,8 @@ def measure_partitioned(R, args, W, H, F, steps, warmup, passes, e2e_steps, e2e_
     lib = capi.load()
     res = {}
     # ---- device-resident: each rank's contiguous chunk as three sub-chunks (the solve of one beside the pyramids of the next)
-    sub = F // 3 if (F // 3) % 2 == 0 and F % 3 == 0 else F
+    nsub = max(1, getattr(args, "sub_chunks", 3))
+    sub = F // nsub if (F // nsub) % 2 == 0 and F % nsub == 0 else F
     block = F // sub
     if sub % 2 or F % sub or sub < 10:
         raise SystemExit("bench.py: --frames must be even (and at least 10)")
@@ -605,12 +606,15 @@ def run_gpu_arm(args):
 
         # the same 1080p video as NV12 frames in and out (decoder output fed straight in; VS_CLIP_NV12): half the
         # bytes over PCIe, no colour conversion; the alignment is that of the gray frames
-        rn = measure_partitioned(R, args, W, H, F, max(2, args.steps // 2), 2, args.passes, max(1, args.steps // 2), args.e2e_sub,
-                                 False, "n", nv12=True)
-        extra["nv12"] = {"metric": "stabilized_frames_per_sec_1080p_nv12", "value": rn["value"], "unit": UNIT, "n_gpus": world,
-                         "ms_per_step": rn["ms_per_step"], "frames_per_step": rn["frames_per_step"], "size": "%dx%d" % (W, H),
-                         "pairs_converged": rn["pairs_converged"], "pairs_seen": rn["pairs_seen"], "e2e": rn.get("e2e"),
-                         "note": "frames are NV12 in and out (1.5 B per pixel each way); no counterpart upstream"}
+        rn = None
+        if W % 2 == 0 and H % 2 == 0 and crop % 2 == 0:
+            rn = measure_partitioned(R, args, W, H, F, max(2, args.steps // 2), 2, args.passes, max(1, args.steps // 2), args.e2e_sub,
+                                     False, "n", nv12=True)
+        if rn:
+            extra["nv12"] = {"metric": "stabilized_frames_per_sec_1080p_nv12", "value": rn["value"], "unit": UNIT, "n_gpus": world,
+                             "ms_per_step": rn["ms_per_step"], "frames_per_step": rn["frames_per_step"], "size": "%dx%d" % (W, H),
+                             "pairs_converged": rn["pairs_converged"], "pairs_seen": rn["pairs_seen"], "e2e": rn.get("e2e"),
+                             "note": "frames are NV12 in and out (1.5 B per pixel each way); no counterpart upstream"}
 
     if rank != 0:
         R.close()
@@ -744,6 +748,7 @@ def main():
     ap.add_argument("--crop", type=int, default=0)
     ap.add_argument("--passes", type=int, default=15, help="videos per step (device-resident number)")
     ap.add_argument("--inflight", type=int, default=2, help="videos in flight at a time (independent stabilizer instances)")
+    ap.add_argument("--sub-chunks", type=int, default=3, help="sub-chunks a rank's resident chunk is cut into (one solver lane each)")
     ap.add_argument("--e2e-sub", type=int, default=16, help="sub-chunk (frames) of the host-streamed partition")
     ap.add_argument("--e2e-inflight", type=int, default=0, help="videos in flight in the end-to-end region (0 = 3 on up to two GPUs, else --inflight)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="CPU worker threads (0 = all cores)")
