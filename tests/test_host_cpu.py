@@ -152,3 +152,29 @@ def test_flow_median_of_a_translation_and_a_rotation():
     assert 0.2 < r < 1.2
     g = host.reference_grid()
     assert g.shape == (54, 4) and g[0].tolist() == [0.0, 0.02, np.float32(0.3), 6.0] and g[-1, 0] == 1.0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own host sources on the host cores) prints ONE JSON line with the keys the
+    driver reads, on the GPU arm's metric / unit / config; and the GPU arm refuses to run without a device."""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--width", "320", "--height", "180", "--frames", "20", "--cpu-threads", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "stabilized_frames_per_sec_1080p" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["width"] == 320 and "workload" in d["config"]
+    import torch
+    if not torch.cuda.is_available():
+        gpu = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--steps", "1", "--warmup", "0"],
+                             capture_output=True, text=True, timeout=300)
+        assert gpu.returncode != 0 and "no CUDA device" in (gpu.stderr + gpu.stdout)
