@@ -1694,7 +1694,7 @@ __device__ __forceinline__ uint32_t plane_pixel_taps(const uint8_t* __restrict__
 }
 
 // The Y plane, eight pixels per lane (one 8-byte store).  A warp covers 32 pixels x 8 rows per step (compact footprint, as
-// above), a CTA the same 128 x 32 tile.  The column terms of a lane are kept relative to its first pixel: with
+// above), a CTA a 128 x 64 tile.  The column terms of a lane are kept relative to its first pixel: with
 // r = (X0 + adelta[0]) & 1023 the pixel j of a regular group (source column sx0 + j) has r + off_j in [0, 1024), where
 // off_j = adelta[j] - adelta[0] - 1024 j is a lane constant of a few units; the eight values travel as four packed pairs of
 // 16-bit halves biased by 1024 (one add per pair, one LOP3 per pair for the test, the horizontal fractions by one shift
@@ -1703,6 +1703,8 @@ __device__ __forceinline__ uint32_t plane_pixel_taps(const uint8_t* __restrict__
 // aligned words per source row; pixel j blends its column pair [p_j, p_j+1] vertically as one packed multiply-add
 // (32 top + fy (bottom - top) on the packed word: the halves cannot interfere because the true result has none) and
 // horizontally by IDP.2A.  Anything else (borders, a skipped source column or row, tile tails) goes pixel by pixel.
+constexpr int PW8_H = 64;      // rows of the Y kernel's tile: the column terms of a lane serve four steps of eight rows
+
 template <int DUMMY>
 __global__ void __launch_bounds__(PW_THREADS)
 k_plane_warp_y8(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_t src_bs, int w, int h,
@@ -1712,19 +1714,26 @@ k_plane_warp_y8(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_
 {
     constexpr double SCALE = 1024.0;
     constexpr int ROUND = 16;
-    __shared__ int2 sXY0[PW_H];
+    __shared__ int2 sXY0[PW8_H];
+    __shared__ __align__(16) int2 sCol[PW_W];     // (adelta, bdelta) of the tile's columns: two f64 products per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
-    const int ox0 = blockIdx.x * PW_W, oy0 = blockIdx.y * PW_H;
+    const int ox0 = blockIdx.x * PW_W, oy0 = blockIdx.y * PW8_H;
     const int slot = slots ? slots[b] : b;
     const uint8_t* src = src_base + (size_t)slot * src_bs;
     uint8_t* dst = dst_base + (size_t)b * dst_bs;
     const VsWarpCoef cf = coefs[b];
-    if (tid < PW_H) {
+    if (tid < PW8_H) {
         const double y = (double)(oy0 + tid + dst_y0);
         sXY0[tid] = make_int2(__double2int_rn((cf.i01 * y + cf.i02) * SCALE) + ROUND,
                               __double2int_rn((cf.i11 * y + cf.i12) * SCALE) + ROUND);
     }
+    if (tid >= PW_THREADS - PW_W) {
+        const int c = tid - (PW_THREADS - PW_W);
+        const double x = (double)(ox0 + c + dst_x0);
+        sCol[c] = make_int2(__double2int_rn(cf.i00 * x * SCALE), __double2int_rn(cf.i10 * x * SCALE));
+    }
+    __syncthreads();
     const int xo = ox0 + 32 * (warp & 3) + 8 * (lane & 3);
     int ad0, bd[8];
     uint32_t cax[4];            // (off_2k + 1024) | (off_2k+1 + 1024) << 16
@@ -1732,10 +1741,9 @@ k_plane_warp_y8(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_
     {
         int ad[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const double x = (double)(xo + j + dst_x0);
-            ad[j] = __double2int_rn(cf.i00 * x * SCALE);
-            bd[j] = __double2int_rn(cf.i10 * x * SCALE);
+        for (int j = 0; j < 8; j += 2) {
+            const int4 c2 = *reinterpret_cast<const int4*>(&sCol[xo - ox0 + j]);
+            ad[j] = c2.x; bd[j] = c2.y; ad[j + 1] = c2.z; bd[j + 1] = c2.w;
         }
         ad0 = ad[0];
 #pragma unroll
@@ -1745,13 +1753,12 @@ k_plane_warp_y8(const uint8_t* __restrict__ src_base, int64_t src_stride, int64_
             cax[k] = (uint32_t)(o0 + 1024) | ((uint32_t)(o1 + 1024) << 16);
         }
     }
-    __syncthreads();
     if (xo >= dw) return;
     const bool full = xo + 8 <= dw;
     uint8_t* const dcol = dst + xo;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const int r = 16 * (warp >> 2) + 8 * k + (lane >> 2);
+    for (int k = 0; k < PW8_H / 16; k++) {
+        const int r = (PW8_H / 2) * (warp >> 2) + 8 * k + (lane >> 2);
         const int yo = oy0 + r;
         if (yo >= dh) continue;
         const int2 xy0 = sXY0[r];
@@ -1823,7 +1830,7 @@ int vsk_plane_warp_slots(vs_ctx* ctx, const VsDevImg& src, int channels, const i
     VS_LAUNCH_BEGIN(ctx, VSK_BGR_WARP);
     const bool y8 = channels == 1 && src_al4 && aligned_to(dst.data, 8) && dst.stride % 8 == 0 && dst.batch_stride % 8 == 0;
     if (y8)
-        k_plane_warp_y8<0><<<grid, PW_THREADS, 0, ctx->stream>>>((const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
+        k_plane_warp_y8<0><<<dim3(vs_cdiv(dst.w, PW_W), vs_cdiv(dst.h, PW8_H), dst.batch), PW_THREADS, 0, ctx->stream>>>((const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
             d_slots, d_coef, (uint8_t*)dst.data, dst.stride, dst.batch_stride, dst.w, dst.h, dst_x0, dst_y0);
     else if (channels == 1)
         k_plane_warp_cv<1><<<grid, PW_THREADS, 0, ctx->stream>>>((const uint8_t*)src.data, src.stride, src.batch_stride, src.w, src.h,
