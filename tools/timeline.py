@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Timeline of one device-resident video through PartitionedStabilizer (CUDA events around every launch, all streams):
-where the GPU idles and which kernels overlap.   python tools/timeline.py [sub_frames block lanes]"""
+where the GPU idles and which kernels overlap.   python tools/timeline.py [sub_frames block lanes [width height frames]]"""
 import ctypes as C
 import json
 import os
@@ -15,6 +15,8 @@ from video_stabilizer_b200 import _capi as capi, host, synth  # noqa: E402
 from video_stabilizer_b200.imgproc import Context  # noqa: E402
 
 W, H, F = 1920, 1080, 300
+if len(sys.argv) > 6:
+    W, H, F = int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
 sub = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 block = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 lanes = int(sys.argv[3]) if len(sys.argv) > 3 else 3
@@ -23,7 +25,7 @@ p.crop_pixels = 0
 ps = host.PartitionedStabilizer(0, 1, W, H, F, sub, block, p, "", True, device=0, host_threads=8, lanes=lanes)
 ctx = Context(0)
 frames = torch.empty((F, H, W, 3), dtype=torch.uint8, pin_memory=True).numpy()
-synth.make_clip_gpu(ctx, W, H, F, 100, out=frames, chunk=50)
+synth.make_clip_gpu(ctx, W, H, F, 100, out=frames, chunk=50 if W <= 1920 else 8)
 ctx.close()
 ps.upload_resident(frames.ctypes.data, W * 3, W * H * 3)
 out = torch.empty((ps.outputs, ps.out_h, ps.out_w, 3), dtype=torch.uint8, device="cuda")

@@ -51,7 +51,7 @@ struct vs_clip {
     uint16_t* d_pos_scratch = nullptr; // [max_pairs][4][max_tiles] candidate lists of the parallel selection
     uint4* d_patch_scratch = nullptr;  // [max_pairs][2][max_tiles] 4x4 keyframe windows of the warp-diff pass (patch cache of the solver)
     uint8_t* d_tb_scratch = nullptr;   // [max_pairs][2][max_tiles] template bytes of the warp-diff pass
-    uint32_t* d_key_scratch = nullptr; // [max_pairs][2][max_tiles] selection keys of clips whose largest level does not fit shared memory (8K)
+    uint32_t* d_key_scratch = nullptr; // [max_pairs][2][max_tiles] selection keys of 4K-class and larger clips (vsk_solve_pairs decides per launch)
     float* d_res_scratch = nullptr;    // [max_pairs][2][max_tiles] warp-diff residuals reused by the first Gauss-Newton iteration
     uint8_t* d_warp_out = nullptr;    // staging for VS_MEM_HOST warps, grown on demand
     size_t warp_out_bytes = 0;
@@ -431,7 +431,8 @@ int vs_clip_create(vs_ctx* ctx, int width, int height, int capacity, int max_pai
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_res_scratch, (size_t)max_pairs * 2 * g.max_tiles);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_patch_scratch, (size_t)max_pairs * 2 * g.max_tiles);
     if (r == VS_OK) r = dev_alloc(ctx, &c->d_tb_scratch, (size_t)max_pairs * 2 * g.max_tiles);
-    if (r == VS_OK && keys_global) r = dev_alloc(ctx, &c->d_key_scratch, (size_t)max_pairs * 2 * g.max_tiles);
+    if (r == VS_OK && (keys_global || (size_t)2 * g.max_tiles * 4 > VS_SOLVE_BIG_KEYS))
+        r = dev_alloc(ctx, &c->d_key_scratch, (size_t)max_pairs * 2 * g.max_tiles);
     if (r == VS_OK && (flags & VS_CLIP_DEBUG_TAPS)) {
         r = dev_alloc(ctx, &c->d_dbg_wd, (size_t)max_pairs * 2 * g.total_tiles);
         if (r == VS_OK) r = dev_alloc(ctx, &c->d_dbg_order, (size_t)max_pairs * 2 * g.total_tiles);

@@ -159,5 +159,7 @@ int vsk_phase_pairs(vs_ctx*, const VsPhasePlan& p, const vs_pair* d_pairs, int n
 
 int vsk_keyframe_features(vs_ctx*, const VsClipGeom& g, const uint8_t* d_pyr, const int32_t* d_slots,
                           int n_slots, uint32_t* d_kp, float4* d_jac);
+// selection keys of a level beyond this many bytes (2 axes x 4 B per tile: 4K-class clips) may live in VsSolveArgs::key_scratch
+constexpr size_t VS_SOLVE_BIG_KEYS = 100 * 1024;
 int vsk_solve_pairs(vs_ctx*, const VsClipGeom& g, const VsSolveArgs& a);
 int vsk_debug_invert4(vs_ctx*, const double* d_H, int n, double* d_quad, double* d_serial, double* d_cond);

@@ -1174,10 +1174,21 @@ int vsk_solve_pairs(vs_ctx* ctx, const VsClipGeom& g, const VsSolveArgs& a)
     VS_REQUIRE(ctx, (uint32_t)g.max_tiles <= vs_sel::KEY_TILE_MASK, "solve: more tiles per level than a key's tile index holds");
     // a level whose keys do not fit shared memory (8K) keeps them in the caller's global scratch; the masks of the
     // list-free selection stay on chip
-    const bool keys_global = key_bytes + sel_bytes > 220 * 1024;
+    bool keys_global = key_bytes + sel_bytes > 220 * 1024;
     VS_REQUIRE(ctx, !keys_global || a.key_scratch, "solve: level too large for the shared-memory selection and no key scratch given");
     VS_REQUIRE(ctx, sel_bytes <= 200 * 1024, "solve: level too large for the on-chip selection masks");
+    // 4K-class levels (keys beyond 100 KB: one CTA per SM either way): a launch of several pairs runs 1024 threads per pair
+    // with the keys in global memory, which leaves the SM's 256 KB to L1 for the gathers (119 pairs of a 4K video: 1.79 ms
+    // with 512 threads and the keys in shared memory, 1.12 with 1024 threads, 1.03 with the keys in global memory as well);
+    // a single pair (the per-frame API) is quicker the old way (0.70 against 0.74 ms).  At 1080p the keys stay on chip
+    // (three CTAs per SM: 0.79 against 0.86 ms).
+    // More pairs than SMs: three 256-thread CTAs per SM with keys and candidate lists in global memory, so that every pair
+    // is resident (the keys of ONE 4K pair would fill an SM's shared memory).
     if (keys_global) threads = 1024;
+    else if (a.key_scratch && a.pos_scratch && key_bytes > VS_SOLVE_BIG_KEYS && a.n_pairs >= 8) {
+        keys_global = true;
+        threads = a.n_pairs <= ctx->sm_count ? 1024 : 256;
+    }
     size_t smem = keys_global ? 0 : key_bytes;
     VsSolveArgs args = a;
     if (!keys_global) args.key_scratch = nullptr;
